@@ -1,0 +1,222 @@
+// runtime.cpp — device context, backend stream, error slot, transfers.
+//
+// B200 counterpart of the reference's MetalExecutionStream singleton (one async stream per device,
+// host synchronises only when it reads: src/backends/metal/metal_common.hpp:53-123,
+// metal_storage.mm:66-93) and of system::is_metal_available (src/tensor/system.cpp:12-29).
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+#include "axb_internal.h"
+
+namespace axb {
+
+std::atomic<uint64_t> g_launches{0};
+
+std::string &last_error_ref() {
+    thread_local std::string e;
+    return e;
+}
+
+axb_status fail(axb_status st, const char *fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    last_error_ref() = buf;
+    return st;
+}
+
+namespace {
+std::mutex g_ctx_mu;
+std::vector<DeviceCtx *> g_ctx; // indexed by device ordinal, created on first use, never destroyed
+} // namespace
+
+DeviceCtx *current_ctx() {
+    int dev = -1;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) {
+        fail(AXB_ERR_CUDA, "cudaGetDevice failed: %s (is a CUDA device present?)", cudaGetErrorString(e));
+        return nullptr;
+    }
+    std::lock_guard<std::mutex> lk(g_ctx_mu);
+    if ((int)g_ctx.size() <= dev)
+        g_ctx.resize(dev + 1, nullptr);
+    if (!g_ctx[dev]) {
+        auto *c = new DeviceCtx();
+        c->device = dev;
+        cudaDeviceProp p{};
+        e = cudaGetDeviceProperties(&p, dev);
+        if (e != cudaSuccess) {
+            fail(AXB_ERR_CUDA, "cudaGetDeviceProperties failed: %s", cudaGetErrorString(e));
+            delete c;
+            return nullptr;
+        }
+        if (p.major != 10) {
+            // sm_100a-only binary: refuse to pretend (no fallback path exists).
+            fail(AXB_ERR_UNSUPPORTED, "device %d is sm_%d%d; this backend is built for sm_100a (B200) only", dev,
+                 p.major, p.minor);
+            delete c;
+            return nullptr;
+        }
+        c->sm_count = p.multiProcessorCount;
+        c->smem_optin = p.sharedMemPerBlockOptin;
+        e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+        if (e != cudaSuccess) {
+            fail(AXB_ERR_CUDA, "cudaStreamCreate failed: %s", cudaGetErrorString(e));
+            delete c;
+            return nullptr;
+        }
+        g_ctx[dev] = c;
+    }
+    return g_ctx[dev];
+}
+
+axb_status resolve_stream(axb_stream_t s, cudaStream_t *out, DeviceCtx **ctx) {
+    DeviceCtx *c = current_ctx();
+    if (!c)
+        return AXB_ERR_CUDA;
+    if (ctx)
+        *ctx = c;
+    *out = s ? static_cast<cudaStream_t>(s) : c->stream;
+    return AXB_OK;
+}
+
+} // namespace axb
+
+using namespace axb;
+
+extern "C" {
+
+int axb_abi_version(void) { return AXB_ABI_VERSION; }
+const char *axb_last_error(void) { return last_error_ref().c_str(); }
+uint64_t axb_launch_count(void) { return g_launches.load(); }
+
+axb_status axb_device_count(int *count) {
+    AXB_REQUIRE(count, AXB_ERR_INVALID, "axb_device_count: null out");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        *count = 0;
+        return fail(AXB_ERR_CUDA, "cudaGetDeviceCount failed: %s", cudaGetErrorString(e));
+    }
+    *count = n;
+    return AXB_OK;
+}
+axb_status axb_set_device(int device) {
+    AXB_CUDA(cudaSetDevice(device));
+    return current_ctx() ? AXB_OK : AXB_ERR_CUDA;
+}
+axb_status axb_get_device(int *device) {
+    AXB_REQUIRE(device, AXB_ERR_INVALID, "axb_get_device: null out");
+    AXB_CUDA(cudaGetDevice(device));
+    return AXB_OK;
+}
+axb_status axb_device_name(int device, char *buf, size_t buflen) {
+    AXB_REQUIRE(buf && buflen, AXB_ERR_INVALID, "axb_device_name: null buffer");
+    cudaDeviceProp p{};
+    AXB_CUDA(cudaGetDeviceProperties(&p, device));
+    snprintf(buf, buflen, "%s", p.name);
+    return AXB_OK;
+}
+axb_status axb_device_sm_count(int device, int *sms) {
+    AXB_REQUIRE(sms, AXB_ERR_INVALID, "axb_device_sm_count: null out");
+    AXB_CUDA(cudaDeviceGetAttribute(sms, cudaDevAttrMultiProcessorCount, device));
+    return AXB_OK;
+}
+axb_status axb_default_stream(axb_stream_t *stream) {
+    AXB_REQUIRE(stream, AXB_ERR_INVALID, "axb_default_stream: null out");
+    DeviceCtx *c = current_ctx();
+    if (!c)
+        return AXB_ERR_CUDA;
+    *stream = c->stream;
+    return AXB_OK;
+}
+axb_status axb_stream_sync(axb_stream_t stream) {
+    cudaStream_t s;
+    AXB_TRY(resolve_stream(stream, &s));
+    AXB_CUDA(cudaStreamSynchronize(s));
+    return AXB_OK;
+}
+
+axb_status axb_event_create(axb_event_t *ev) {
+    AXB_REQUIRE(ev, AXB_ERR_INVALID, "axb_event_create: null out");
+    if (!current_ctx())
+        return AXB_ERR_CUDA;
+    cudaEvent_t e;
+    AXB_CUDA(cudaEventCreate(&e));
+    *ev = e;
+    return AXB_OK;
+}
+axb_status axb_event_destroy(axb_event_t ev) {
+    if (ev)
+        AXB_CUDA(cudaEventDestroy(static_cast<cudaEvent_t>(ev)));
+    return AXB_OK;
+}
+axb_status axb_event_record(axb_event_t ev, axb_stream_t stream) {
+    cudaStream_t s;
+    AXB_TRY(resolve_stream(stream, &s));
+    AXB_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(ev), s));
+    return AXB_OK;
+}
+axb_status axb_event_sync(axb_event_t ev) {
+    AXB_CUDA(cudaEventSynchronize(static_cast<cudaEvent_t>(ev)));
+    return AXB_OK;
+}
+axb_status axb_event_elapsed_ms(axb_event_t start, axb_event_t end, float *ms) {
+    AXB_REQUIRE(ms, AXB_ERR_INVALID, "axb_event_elapsed_ms: null out");
+    AXB_CUDA(cudaEventElapsedTime(ms, static_cast<cudaEvent_t>(start), static_cast<cudaEvent_t>(end)));
+    return AXB_OK;
+}
+
+axb_status axb_host_alloc(size_t bytes, void **ptr) {
+    AXB_REQUIRE(ptr, AXB_ERR_INVALID, "axb_host_alloc: null out");
+    *ptr = nullptr;
+    if (bytes == 0)
+        return AXB_OK;
+    AXB_CUDA(cudaHostAlloc(ptr, bytes, cudaHostAllocDefault));
+    return AXB_OK;
+}
+axb_status axb_host_free(void *ptr) {
+    if (ptr)
+        AXB_CUDA(cudaFreeHost(ptr));
+    return AXB_OK;
+}
+axb_status axb_memcpy_h2d(void *dst, const void *src, size_t bytes, axb_stream_t stream) {
+    if (!bytes)
+        return AXB_OK;
+    cudaStream_t s;
+    AXB_TRY(resolve_stream(stream, &s));
+    AXB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, s));
+    return AXB_OK;
+}
+axb_status axb_memcpy_d2h(void *dst, const void *src, size_t bytes, axb_stream_t stream, int sync) {
+    cudaStream_t s;
+    AXB_TRY(resolve_stream(stream, &s));
+    if (bytes)
+        AXB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, s));
+    if (sync)
+        AXB_CUDA(cudaStreamSynchronize(s));
+    return AXB_OK;
+}
+axb_status axb_memcpy_d2d(void *dst, const void *src, size_t bytes, axb_stream_t stream) {
+    if (!bytes)
+        return AXB_OK;
+    cudaStream_t s;
+    AXB_TRY(resolve_stream(stream, &s));
+    AXB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, s));
+    return AXB_OK;
+}
+axb_status axb_memset(void *dst, int value, size_t bytes, axb_stream_t stream) {
+    if (!bytes)
+        return AXB_OK;
+    cudaStream_t s;
+    AXB_TRY(resolve_stream(stream, &s));
+    AXB_CUDA(cudaMemsetAsync(dst, value, bytes, s));
+    return AXB_OK;
+}
+
+size_t axb_dtype_size(int32_t dtype) { return dtype_size(dtype); }
+
+} // extern "C"

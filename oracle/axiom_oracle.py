@@ -1,0 +1,491 @@
+"""oracle/axiom_oracle.py — CPU restatement (numpy + oracle/axiom_oracle.c) of the reference algorithms on
+the hot path. TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline leg; never by axiom_b200/.
+
+Pinned against the reference itself (oracle/_ref/libaxiom_ref.so, built from /root/reference by
+oracle/Makefile) in tests/test_oracle_pin.py, and against the reference's own known-answer tests
+transcribed in tests/golden/.  Every function cites the reference lines it restates.
+
+Arrays are numpy arrays; bfloat16 is carried as uint16 bit patterns and tagged with dtype code BF16.
+dtype / op codes are axiom::DType / axiom::ops::OpType values (include/axiom/dtype.hpp:170-192,
+include/axiom/operations.hpp:55-208).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+from typing import Optional, Sequence, Tuple
+
+import numpy as np
+
+BOOL, I8, I16, I32, I64, U8, U16, U32, U64, F16, BF16, F32, F64 = range(13)
+NP_OF = {BOOL: np.bool_, I8: np.int8, I16: np.int16, I32: np.int32, I64: np.int64, U8: np.uint8, U16: np.uint16,
+         U32: np.uint32, U64: np.uint64, F16: np.float16, BF16: np.uint16, F32: np.float32, F64: np.float64}
+CODE_OF = {np.dtype(v): k for k, v in NP_OF.items() if k != BOOL and k != BF16}
+CODE_OF[np.dtype(np.bool_)] = BOOL
+CODE_OF[np.dtype(np.uint16)] = U16
+
+OP = dict(add=0, sub=1, mul=2, div=3, pow=4, mod=5, eq=6, ne=7, lt=8, le=9, gt=10, ge=11, logical_and=12,
+          logical_or=13, logical_xor=14, logical_not=15, bit_and=16, bit_or=17, bit_xor=18, shl=19, shr=20,
+          maximum=21, minimum=22, atan2=23, hypot=24, neg=25, abs=26, sqrt=27, exp=28, log=29, sin=30, cos=31,
+          tan=32, erf=33, sign=34, floor=35, ceil=36, trunc=37, round=38, reciprocal=39, square=40, cbrt=41,
+          isnan=42, isinf=43, isfinite=44, relu=48, leaky_relu=49, silu=50, sigmoid=51, tanh=52, gelu=53,
+          sum=56, mean=57, max=58, min=59, argmax=60, argmin=61, any=62, all=63, prod=64)
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "liboracle.so")
+_SRC = os.path.join(_HERE, "axiom_oracle.c")
+_clib: Optional[ctypes.CDLL] = None
+
+
+def build_c_oracle(force: bool = False) -> str:
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(_SRC):
+        subprocess.check_call(["gcc", "-O2", "-ffp-contract=off", "-fPIC", "-shared", _SRC, "-o", _SO, "-lm"])
+    return _SO
+
+
+def clib() -> ctypes.CDLL:
+    global _clib
+    if _clib is None:
+        L = ctypes.CDLL(build_c_oracle())
+        fp = ctypes.POINTER(ctypes.c_float)
+        L.axo_unary_f32.argtypes = [ctypes.c_int, fp, fp, ctypes.c_int64, ctypes.c_int]
+        L.axo_binary_f32.argtypes = [ctypes.c_int, fp, fp, fp, ctypes.c_int64, ctypes.c_int]
+        L.axo_softmax_rows_f32.argtypes = [fp, fp, ctypes.c_int64, ctypes.c_int64, ctypes.c_int]
+        _clib = L
+    return _clib
+
+
+def _fp(a: np.ndarray):
+    return a.ctypes.data_as(ctypes.POINTER(ctypes.c_float))
+
+
+# ---- bfloat16 helpers (include/axiom/bfloat16.hpp:16-27,41-46) ---------------------------------------
+def bf16_to_f32(bits: np.ndarray) -> np.ndarray:
+    return (bits.astype(np.uint32) << 16).view(np.float32)
+
+
+def f32_to_bf16(x: np.ndarray) -> np.ndarray:
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    b = x.view(np.uint32).astype(np.uint64)
+    r = ((b + 0x7FFF + ((b >> 16) & 1)) >> 16).astype(np.uint16)
+    return np.where(np.isnan(x), np.uint16(0x7FC0), r)
+
+
+def to_f32(a: np.ndarray, dt: int) -> np.ndarray:
+    if dt == BF16:
+        return bf16_to_f32(a)
+    return a.astype(np.float32)
+
+
+# ---- type rules -------------------------------------------------------------------------------------
+_RANK = {BOOL: 0, I8: 1, U8: 2, I16: 3, U16: 4, I32: 5, U32: 6, I64: 7, U64: 8, F16: 9, BF16: 10, F32: 11, F64: 12}
+_SIZE = {BOOL: 1, I8: 1, I16: 2, I32: 4, I64: 8, U8: 1, U16: 2, U32: 4, U64: 8, F16: 2, BF16: 2, F32: 4, F64: 8}
+
+
+def promote_types(a: int, b: int) -> int:
+    """src/tensor/operations.cpp:346-397"""
+    if a == b:
+        return a
+    t1, t2 = (a, b) if _RANK[a] > _RANK[b] else (b, a)
+    if t1 in (F16, BF16, F32, F64):
+        return t1
+    s1, s2 = t1 in (I8, I16, I32, I64), t2 in (I8, I16, I32, I64)
+    z1, z2 = _SIZE[t1], _SIZE[t2]
+    if s1 == s2:
+        return t1
+    if z1 > z2:
+        return t1
+    return {1: I16, 2: I32, 4: I64}.get(max(z1, z2), F64)
+
+
+def cast(a: np.ndarray, src: int, dst: int) -> np.ndarray:
+    """Tensor::astype (src/tensor/tensor.cpp:1656-1701, type_conversion.cpp): static_cast semantics;
+    float->bf16 RNE with NaN->0x7FC0; anything->Bool is x != 0."""
+    if src == dst:
+        return a
+    if dst == BOOL:
+        return (to_f32(a, src) != 0) if src == BF16 else (a != 0)
+    if src == BF16:
+        a = bf16_to_f32(a)
+    if dst == BF16:
+        return f32_to_bf16(a.astype(np.float32))
+    if np.issubdtype(a.dtype, np.floating) and np.issubdtype(NP_OF[dst], np.integer):
+        a = np.trunc(a)
+    with np.errstate(all="ignore"):
+        return a.astype(NP_OF[dst])
+
+
+# ---- elementwise ------------------------------------------------------------------------------------
+_CMP = {"eq": np.equal, "ne": np.not_equal, "lt": np.less, "le": np.less_equal, "gt": np.greater,
+        "ge": np.greater_equal}
+
+
+def _c_unary(op: str, x: np.ndarray, lanes: int) -> np.ndarray:
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    out = np.empty_like(x)
+    rc = clib().axo_unary_f32(OP[op], _fp(x), _fp(out), x.size, lanes)
+    assert rc == 0, op
+    return out
+
+
+def unary(op: str, x: np.ndarray, dt: int, lanes: int = 0, param: float = 0.01) -> Tuple[np.ndarray, int]:
+    """CPUUnaryOperation (cpu_operations.cpp:824-1273). `lanes` = SIMD width of the reference host for the
+    vector-body/scalar-tail split of transcendental fp32 ops (0 = polynomial everywhere)."""
+    if op == "logical_not":
+        return ~(cast(x, dt, BOOL)), BOOL
+    if op in ("isnan", "isinf", "isfinite"):
+        if dt in (F32, F64, F16):
+            return getattr(np, op)(x), BOOL
+        if dt == BF16:  # not is_floating_point_v, not float16_t -> constant (cpu_operations.hpp:806-845)
+            return np.full(x.shape, op == "isfinite"), BOOL
+        return np.full(x.shape, op == "isfinite"), BOOL
+    if dt == F32:
+        x = x.astype(np.float32)
+        with np.errstate(all="ignore"):
+            if op in ("exp", "log", "sin", "cos", "tan", "erf", "cbrt", "silu", "sigmoid", "tanh", "gelu"):
+                return _c_unary(op, x, lanes).reshape(x.shape), F32
+            r = {"neg": lambda: -x, "abs": lambda: np.abs(x), "sqrt": lambda: np.sqrt(x),
+                 "sign": lambda: np.sign(x).astype(np.float32), "floor": lambda: np.floor(x),
+                 "ceil": lambda: np.ceil(x), "trunc": lambda: np.trunc(x), "round": lambda: np.rint(x),
+                 "reciprocal": lambda: (np.float32(1) / x), "square": lambda: x * x,
+                 "relu": lambda: np.where(x > 0, x, np.float32(0)),
+                 "leaky_relu": lambda: np.where(x > 0, x, np.float32(param) * x)}[op]()
+        return r.astype(np.float32), F32
+    if dt in (BF16, F16):
+        # scalar functors on half types: evaluate in double (cpu_operations.hpp:383-700), round once to float,
+        # then to the half type
+        xf = to_f32(x, dt)
+        xd = xf.astype(np.float64)
+        with np.errstate(all="ignore"):
+            if op in ("neg", "abs", "relu", "square", "sign", "reciprocal", "leaky_relu", "floor", "ceil", "trunc",
+                      "round"):
+                if dt == BF16 and op in ("floor", "ceil", "trunc", "round"):
+                    rf = xf  # identity for bfloat16 (cpu_operations.hpp:728-770)
+                elif op == "leaky_relu":
+                    slope = to_f32(cast(np.array([param], np.float32), F32, dt), dt)[0]
+                    rf = np.where(xf > 0, xf, slope * xf)
+                elif op == "round":
+                    rf = np.where(xf >= 0, np.floor(xf + np.float32(0.5)), np.ceil(xf - np.float32(0.5)))  # std::round
+                else:
+                    rf = {"neg": lambda: -xf, "abs": lambda: np.abs(xf), "relu": lambda: np.where(xf > 0, xf, 0),
+                          "square": lambda: xf * xf, "sign": lambda: np.sign(xf),
+                          "reciprocal": lambda: np.float32(1) / xf, "floor": lambda: np.floor(xf),
+                          "ceil": lambda: np.ceil(xf), "trunc": lambda: np.trunc(xf)}[op]()
+                return cast(np.asarray(rf, np.float32), F32, dt), dt
+            import scipy.special as sp
+            e = np.exp(-np.abs(xd))
+            rd = {"sqrt": lambda: np.sqrt(xd), "exp": lambda: np.exp(xd), "log": lambda: np.log(xd),
+                  "sin": lambda: np.sin(xd), "cos": lambda: np.cos(xd), "tan": lambda: np.tan(xd),
+                  "erf": lambda: sp.erf(xd), "cbrt": lambda: np.cbrt(xd), "tanh": lambda: np.tanh(xd),
+                  "gelu": lambda: 0.5 * xd * (1.0 + sp.erf(xd / 1.4142135623730951)),
+                  "sigmoid": lambda: np.where(xd >= 0, 1.0 / (1.0 + e), e / (1.0 + e)),
+                  "silu": lambda: np.where(xd >= 0, xd / (1.0 + e), (xd * e) / (1.0 + e))}[op]()
+        return cast(rd.astype(np.float32), F32, dt), dt
+    if dt == F64:
+        import scipy.special as sp
+        with np.errstate(all="ignore"):
+            r = {"neg": lambda: -x, "abs": lambda: np.abs(x), "sqrt": lambda: np.sqrt(x), "exp": lambda: np.exp(x),
+                 "log": lambda: np.log(x), "sin": lambda: np.sin(x), "cos": lambda: np.cos(x),
+                 "tan": lambda: np.tan(x), "erf": lambda: sp.erf(x), "tanh": lambda: np.tanh(x),
+                 "sign": lambda: np.sign(x), "floor": lambda: np.floor(x), "ceil": lambda: np.ceil(x),
+                 "trunc": lambda: np.trunc(x), "round": lambda: np.rint(x), "reciprocal": lambda: 1.0 / x,
+                 "square": lambda: x * x, "relu": lambda: np.where(x > 0, x, 0.0)}[op]()
+        return r.astype(np.float64), F64
+    # integers / bool
+    if dt == BOOL:
+        return {"neg": lambda: ~x}.get(op, lambda: x)(), BOOL
+    unsigned = dt in (U8, U16, U32, U64)
+    with np.errstate(all="ignore"):
+        r = {"neg": lambda: (0 - x).astype(x.dtype), "abs": lambda: x if unsigned else np.abs(x),
+             "sign": lambda: (x > 0).astype(x.dtype) if unsigned else np.sign(x).astype(x.dtype),
+             "square": lambda: (x * x).astype(x.dtype), "relu": lambda: np.where(x > 0, x, 0).astype(x.dtype),
+             "floor": lambda: x, "ceil": lambda: x, "trunc": lambda: x, "round": lambda: x}[op]()
+    return r, dt
+
+
+def binary(op: str, a: np.ndarray, adt: int, b: np.ndarray, bdt: int, lanes: int = 0,
+           simd_path: bool = True) -> Tuple[np.ndarray, int]:
+    """CPUBinaryOperation::execute_binary (cpu_operations.cpp:28-88, 109-583). simd_path=False forces the
+    scalar-functor algorithms the reference uses when an operand is broadcast or non-contiguous."""
+    if op in _CMP or op in ("logical_and", "logical_or", "logical_xor"):
+        # both operands are converted to Float32 first (cpu_operations.cpp:115-126,286-296)
+        af, bf = to_f32(a, adt) if adt == BF16 else a.astype(np.float32), \
+            to_f32(b, bdt) if bdt == BF16 else b.astype(np.float32)
+        if op in _CMP:
+            return _CMP[op](af, bf), BOOL
+        ab, bb = af != 0, bf != 0
+        return {"logical_and": ab & bb, "logical_or": ab | bb, "logical_xor": ab ^ bb}[op], BOOL
+    rdt = promote_types(adt, bdt)
+    if rdt == BOOL:  # arithmetic on two Bool tensors runs in float and is cast back (T = bool path)
+        r, _ = binary(op, a.astype(np.float32), F32, b.astype(np.float32), F32, lanes)
+        return r != 0, BOOL
+    x, y = cast(a, adt, rdt), cast(b, bdt, rdt)
+    if rdt in (BF16, F16):
+        xf, yf = to_f32(x, rdt), to_f32(y, rdt)
+        with np.errstate(all="ignore"):
+            if op in ("pow", "hypot", "atan2"):
+                rd = {"pow": np.power, "hypot": np.hypot, "atan2": np.arctan2}[op](xf.astype(np.float64),
+                                                                                     yf.astype(np.float64))
+                rf = rd.astype(np.float32)
+            else:
+                rf, _ = binary(op, xf, F32, yf, F32)
+        return cast(np.asarray(rf, np.float32), F32, rdt), rdt
+    with np.errstate(all="ignore"):
+        if rdt in (F32, F64):
+            same_shape = (np.shape(x) == np.shape(y))
+            if op in ("pow", "hypot") and rdt == F32 and same_shape and simd_path:
+                # Highway kernels only on the same-shape contiguous path (cpu_operations.cpp:229-262);
+                # broadcast / strided operands use the scalar libm functors (:516-583)
+                xb, yb = np.ascontiguousarray(x), np.ascontiguousarray(y)
+                out = np.empty_like(xb)
+                clib().axo_binary_f32(OP[op], _fp(xb), _fp(yb), _fp(out), out.size, lanes)
+                return out, rdt
+            f = {"add": np.add, "sub": np.subtract, "mul": np.multiply, "div": np.divide, "pow": np.power,
+                 "mod": np.fmod, "maximum": lambda p, q: np.where(p < q, q, p),
+                 "minimum": lambda p, q: np.where(q < p, q, p), "atan2": np.arctan2, "hypot": np.hypot}[op]
+            return np.asarray(f(x, y)).astype(NP_OF[rdt]), rdt
+        # integers
+        if op == "div":
+            q = np.where(y == 0, 0, np.trunc(x.astype(np.float64) / np.where(y == 0, 1, y).astype(np.float64)))
+            return q.astype(NP_OF[rdt]), rdt
+        if op == "mod":
+            yy = np.where(y == 0, 1, y)
+            r = np.fmod(x, yy)
+            return np.where(y == 0, 0, r).astype(NP_OF[rdt]), rdt
+        f = {"add": np.add, "sub": np.subtract, "mul": np.multiply, "maximum": np.maximum, "minimum": np.minimum,
+             "bit_and": np.bitwise_and, "bit_or": np.bitwise_or, "bit_xor": np.bitwise_xor,
+             "shl": np.left_shift, "shr": np.right_shift}[op]
+        return np.asarray(f(x, y)).astype(NP_OF[rdt]), rdt
+
+
+def where(cond: np.ndarray, cdt: int, a: np.ndarray, adt: int, b: np.ndarray, bdt: int) -> Tuple[np.ndarray, int]:
+    """CPUWhereOperation (cpu_operations.cpp:2408-2589): any non-zero BYTE of cond is true (:2503-2513)."""
+    rdt = promote_types(adt, bdt)
+    if cdt == BOOL:
+        c = cond.astype(bool)
+    else:
+        raw = np.ascontiguousarray(cond)
+        c = raw.view(np.uint8).reshape(raw.shape + (raw.dtype.itemsize,)).any(axis=-1)
+    return np.where(c, cast(a, adt, rdt), cast(b, bdt, rdt)), rdt
+
+
+def masked_fill(x: np.ndarray, xdt: int, mask: np.ndarray, value: float) -> Tuple[np.ndarray, int]:
+    """cpu_operations.cpp:2596-2700; the value goes through a Float32 {1} tensor (operations.cpp:1585-1592)."""
+    v = cast(np.array([value], np.float32), F32, xdt)
+    return np.where(mask.astype(bool), v, x), xdt
+
+
+# ---- reductions -------------------------------------------------------------------------------------
+def _tree_lanes(acc: np.ndarray, f) -> np.ndarray:
+    """hn::ReduceSum/Max/Min over one vector, in Highway's shuffle order: ReduceAcrossBlocks
+    (x86_512-inl.h:7641-7646: v+=SwapAdjacentBlocks, v+=ReverseBlocks; AVX2 generic_ops-inl.h:1041-1045) then
+    ReduceWithinBlocks on a 128-bit block (generic_ops-inl.h:1050-1071)."""
+    L = acc.shape[-1]
+    lpb = max(1, min(L, 16 // acc.dtype.itemsize))  # lanes per 128-bit block
+    nb = max(1, L // lpb)
+    b = acc.reshape(acc.shape[:-1] + (nb, lpb))
+    if nb == 4:
+        y = f(f(b[..., 0, :], b[..., 1, :]), f(b[..., 3, :], b[..., 2, :]))
+    elif nb == 2:
+        y = f(b[..., 0, :], b[..., 1, :])
+    else:
+        y = b[..., 0, :]
+        for k in range(1, nb):
+            y = f(y, b[..., k, :])
+    if lpb == 4:
+        return f(f(y[..., 0], y[..., 3]), f(y[..., 1], y[..., 2]))
+    if lpb == 2:
+        return f(y[..., 0], y[..., 1])
+    r = y[..., 0]
+    for k in range(1, lpb):
+        r = f(r, y[..., k])
+    return r
+
+
+def _reduce_rows(x2: np.ndarray, op: str, lanes: int) -> np.ndarray:
+    """Per-row SIMD reduce (hwy_kernels-inl.h:678-767): `lanes` lane-strided serial partials, horizontal
+    tree, then the scalar tail. x2: (rows, n) in the accumulation dtype."""
+    rows, n = x2.shape
+    f = {"sum": np.add, "prod": np.multiply, "max": np.maximum, "min": np.minimum}[op]
+    ident = {"sum": 0, "prod": 1, "max": np.finfo(x2.dtype).min if x2.dtype.kind == "f" else np.iinfo(x2.dtype).min,
+             "min": np.finfo(x2.dtype).max if x2.dtype.kind == "f" else np.iinfo(x2.dtype).max}[op]
+    L = max(int(lanes), 1)
+    nb = (n // L) * L
+    acc = np.full((rows, L), ident, dtype=x2.dtype)
+    with np.errstate(all="ignore"):
+        for i in range(0, nb, L):
+            acc = f(acc, x2[:, i:i + L])
+        if op == "prod":  # horizontal product is a serial loop over lanes (hwy_kernels-inl.h:752-758)
+            r = np.full((rows,), 1, dtype=x2.dtype)
+            for j in range(L):
+                r = r * acc[:, j]
+        else:
+            r = _tree_lanes(acc, f)
+        for i in range(nb, n):
+            r = f(r, x2[:, i])
+    return r
+
+
+def reduce_result_dtype(op: str, dt: int) -> int:
+    """What the caller of ops::sum/mean/... observes (infer_reduction_dtype graph_registry.cpp:265-291 +
+    executor promotion graph_executor.cpp:396-403): Mean of half -> Float32 (value already rounded to half)."""
+    if op == "mean" and dt in (F16, BF16):
+        return F32
+    return dt
+
+
+def reduce(op: str, x: np.ndarray, dt: int, axes: Sequence[int] = (), keep_dims: bool = False,
+           lanes: int = 16) -> Tuple[np.ndarray, int]:
+    """CPUReductionOperation::execute_reduction_typed (cpu_operations.cpp:1419-1712)."""
+    nd = x.ndim
+    axes = sorted(set(int(a) for a in axes)) if len(axes) else list(range(nd))
+    half = dt in (F16, BF16)
+    xa = to_f32(x, dt) if half else x  # fp32 accumulation for half types (:1422-1424)
+    adt = F32 if half else dt
+    base = "sum" if op == "mean" else op
+    n_red = int(np.prod([x.shape[a] for a in axes])) if axes else 1
+    full = len(axes) == nd
+    simd_ok = adt in (F32, F64, I32, I64) and base in ("sum", "max", "min", "prod")
+    if op in ("any", "all"):
+        xb = xa != 0
+        r = xb.any(axis=tuple(axes), keepdims=keep_dims) if op == "any" else xb.all(axis=tuple(axes),
+                                                                                      keepdims=keep_dims)
+        if full and not keep_dims:
+            r = np.asarray(r).reshape(1)
+        return cast(np.asarray(r), BOOL, dt), dt
+    with np.errstate(all="ignore"):
+        if full and simd_ok:
+            r = _reduce_rows(np.ascontiguousarray(xa).reshape(1, -1), base, lanes)
+            r = r.reshape([1] * nd if keep_dims else [1])
+        elif len(axes) == 1 and axes[0] == nd - 1 and nd >= 2 and simd_ok:
+            r = _reduce_rows(np.ascontiguousarray(xa).reshape(-1, x.shape[-1]), base, lanes)
+            r = r.reshape(x.shape[:-1] + ((1,) if keep_dims else ()))
+        else:
+            # first-axis SIMD accumulate and the recursive scalar fallback both add elements of each output
+            # in increasing index order (cpu_operations.cpp:1620-1711)
+            keep = [a for a in range(nd) if a not in axes]
+            xt = np.transpose(xa, keep + axes).reshape([x.shape[a] for a in keep] + [n_red])
+            f = {"sum": np.add, "prod": np.multiply, "max": lambda p, q: np.where(p < q, q, p),
+                 "min": lambda p, q: np.where(q < p, q, p)}[base]
+            if axes == [0] and nd >= 2 and adt in (F32, F64):
+                r = xt[..., 0].copy()
+                start = 1
+            else:
+                ident = {"sum": 0, "prod": 1,
+                         "max": np.finfo(xt.dtype).min if xt.dtype.kind == "f" else np.iinfo(xt.dtype).min if xt.dtype.kind in "iu" else False,
+                         "min": np.finfo(xt.dtype).max if xt.dtype.kind == "f" else np.iinfo(xt.dtype).max if xt.dtype.kind in "iu" else True}[base]
+                r = np.full(xt.shape[:-1], ident, dtype=xt.dtype)
+                start = 0
+            for j in range(start, n_red):
+                r = f(r, xt[..., j]).astype(xt.dtype)
+            if keep_dims:
+                shp = [1 if a in axes else x.shape[a] for a in range(nd)]
+                r = r.reshape(shp)
+            elif r.ndim == 0:
+                r = r.reshape(1)
+        if op == "mean":
+            r = (r / np.asarray(n_red, dtype=r.dtype)).astype(r.dtype) if r.dtype.kind == "f" else \
+                np.trunc(r / n_red).astype(r.dtype)
+    r = np.asarray(r)
+    if half:
+        rb = cast(r.astype(np.float32), F32, dt)  # rounded once to the half type (:1613-1614)
+        if op == "mean":
+            return to_f32(rb, dt), F32
+        return rb, dt
+    return r.astype(NP_OF[adt]), adt
+
+
+def argreduce(op: str, x: np.ndarray, dt: int, axis: int, keep_dims: bool = False) -> np.ndarray:
+    """CPUArgMax/ArgMin (cpu_operations.cpp:2157-2350): strict compare from lowest()/max() => first extreme wins,
+    NaN never wins, all-NaN (or all == lowest) -> 0; axis < 0 => flattened, rank-0 result."""
+    xf = to_f32(x, dt) if dt == BF16 else x
+    if axis < 0:
+        xf = xf.reshape(-1)
+        axis = 0
+        flat = True
+    else:
+        flat = False
+    xm = np.moveaxis(xf, axis, -1)
+    if xm.dtype.kind == "f":
+        fill = -np.inf if op == "argmax" else np.inf
+        clean = np.where(np.isnan(xm), fill, xm)
+        lowest = np.finfo(xm.dtype).min if op == "argmax" else np.finfo(xm.dtype).max
+    else:
+        clean = xm
+        lowest = None
+    idx = np.argmax(clean, axis=-1) if op == "argmax" else np.argmin(clean, axis=-1)
+    if lowest is not None:
+        best = np.take_along_axis(clean, idx[..., None], axis=-1)[..., 0]
+        # values that never beat the initial best (-inf, or NaN everywhere) leave best_idx at 0
+        never = (best <= lowest) if op == "argmax" else (best >= lowest)
+        idx = np.where(never, 0, idx)
+    idx = idx.astype(np.int64)
+    if keep_dims:
+        idx = np.expand_dims(idx, axis if not flat else 0)
+        if flat:
+            idx = idx.reshape([1] * x.ndim)
+    return idx
+
+
+def softmax(x: np.ndarray, dt: int, axis: int = -1, log: bool = False) -> np.ndarray:
+    """CPUSoftmaxOperation (cpu_operations.cpp:3067-3241): per slice max, libm exp, SERIAL fp32 sum, divide;
+    half dtypes round-trip through Float32."""
+    xf = to_f32(x, dt) if dt in (BF16, F16) else x
+    if dt == F64:
+        m = xf.max(axis=axis, keepdims=True)
+        e = np.exp(xf - m)
+        s = e.sum(axis=axis, keepdims=True)
+        return (xf - m - np.log(s)) if log else e / s
+    xm = np.ascontiguousarray(np.moveaxis(xf.astype(np.float32), axis, -1))
+    rows = xm.reshape(-1, xm.shape[-1])
+    out = np.empty_like(rows)
+    clib().axo_softmax_rows_f32(_fp(rows), _fp(out), rows.shape[0], rows.shape[1], int(log))
+    r = np.moveaxis(out.reshape(xm.shape), -1, axis)
+    return cast(np.ascontiguousarray(r), F32, dt) if dt in (BF16, F16) else np.ascontiguousarray(r)
+
+
+def layer_norm(x: np.ndarray, dt: int, w: np.ndarray, wdt: int, b: np.ndarray, bdt: int, axis: int = -1,
+               eps: float = 1e-5, lanes: int = 16) -> Tuple[np.ndarray, int]:
+    """ops::layer_norm on CPU = 9 composed ops (src/tensor/operations.cpp:1803-1817): mean, sub, mul, mean,
+    +eps, sqrt, div, *w, +b — each op rounded to its dtype. Half input => Float32 from the first mean on."""
+    ax = axis % x.ndim
+    mean, mdt = reduce("mean", x, dt, [ax], True, lanes)
+    xc, cdt = binary("sub", x, dt, mean, mdt)
+    sq, sdt = binary("mul", xc, cdt, xc, cdt)
+    var, vdt = reduce("mean", sq, sdt, [ax], True, lanes)
+    ve, edt = binary("add", var, vdt, np.array([eps], np.float32), F32)
+    sd, ddt = unary("sqrt", ve, edt)
+    nrm, ndt = binary("div", xc, cdt, sd, ddt)
+    sc, scdt = binary("mul", nrm, ndt, w, wdt)
+    return binary("add", sc, scdt, b, bdt)
+
+
+def rms_norm(x: np.ndarray, dt: int, w: np.ndarray, wdt: int, axis: int = -1, eps: float = 1e-5,
+             lanes: int = 16) -> Tuple[np.ndarray, int]:
+    """ops::rms_norm CPU composition (src/tensor/operations.cpp:1841-1857)."""
+    ax = axis % x.ndim
+    sq, sdt = binary("mul", x, dt, x, dt)
+    ms, mdt = reduce("mean", sq, sdt, [ax], True, lanes)
+    me, edt = binary("add", ms, mdt, np.array([eps], np.float32), F32)
+    rms, rdt = unary("sqrt", me, edt)
+    nrm, ndt = binary("div", x, dt, rms, rdt)
+    return binary("mul", nrm, ndt, w, wdt)
+
+
+def matmul(a: np.ndarray, adt: int, b: np.ndarray, bdt: int, ta: bool = False, tb: bool = False) -> Tuple[np.ndarray, int]:
+    """CPUMatMulOperation (cpu_operations.cpp:1886-2150). fp32/fp64 go to sgemm/dgemm (any summation order:
+    compared with tolerance); the governing spec for bf16 is 'vs an fp32 reference' (north_star), so bf16
+    inputs are multiplied in fp32 (fp64 accumulate) and rounded once."""
+    rdt = promote_types(adt, bdt)
+    x = to_f32(a, adt) if adt in (BF16, F16) else a
+    y = to_f32(b, bdt) if bdt in (BF16, F16) else b
+    if ta:
+        x = np.swapaxes(x, -1, -2) if x.ndim >= 2 else x
+    if tb:
+        y = np.swapaxes(y, -1, -2) if y.ndim >= 2 else y
+    r = np.matmul(x.astype(np.float64), y.astype(np.float64))
+    if rdt in (BF16, F16):
+        return cast(np.asarray(r, np.float32), F32, rdt), rdt
+    return np.asarray(r).astype(NP_OF[rdt]), rdt

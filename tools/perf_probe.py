@@ -1,0 +1,56 @@
+"""Quick device-timed probe of individual workloads (dev tool; bench.py is the contract)."""
+import ctypes, sys, os, json
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+from axiom_b200 import capi, device as dev
+
+L = capi.lib()
+capi.check(L.axb_set_device(0))
+
+def timeit(fn, iters=20, warm=5):
+    for _ in range(warm): fn()
+    e0, e1 = ctypes.c_void_p(), ctypes.c_void_p()
+    capi.check(L.axb_event_create(ctypes.byref(e0))); capi.check(L.axb_event_create(ctypes.byref(e1)))
+    ts = []
+    for _ in range(iters):
+        capi.check(L.axb_event_record(e0, None)); fn(); capi.check(L.axb_event_record(e1, None))
+        capi.check(L.axb_event_sync(e1)); ms = ctypes.c_float(); capi.check(L.axb_event_elapsed_ms(e0, e1, ctypes.byref(ms))); ts.append(ms.value)
+    return float(np.median(ts)), float(np.min(ts))
+
+def c2(rows=4096, cols=16384):
+    a = dev.randn((rows, 1), 1); b = dev.randn((1, cols), 2); c = dev.randn((rows, cols), 3)
+    one = dev.DeviceArray.from_numpy(np.array([1.0], np.float32)); zi = dev.DeviceArray.from_numpy(np.array([0], np.int32)); zf = dev.DeviceArray.from_numpy(np.array([0.0], np.float32))
+    F, B, V = capi.F32, capi.BOOL, capi.SRC_VALUE
+    prog = [capi.make_instr(capi.OP["relu"], F, 0), capi.make_instr(capi.OP["add"], F, V(0), 1), capi.make_instr(capi.OP["mul"], F, V(1), 2),
+            capi.make_instr(capi.OP["gt"], B, 3, 4), capi.make_instr(capi.OP["where"], F, V(3), V(2), 5)]
+    out = dev.DeviceArray.empty((rows, cols), F)
+    ins = [a, one, b, c, zi, zf]
+    fn = lambda: dev.elementwise(prog, ins, out=out)
+    med, mn = timeit(fn)
+    nbytes = rows*cols*8 + rows*4 + cols*4
+    return dict(workload="c2_chain", ms_med=med, ms_min=mn, GBps_med=nbytes/med/1e6, GBps_min=nbytes/mn/1e6)
+
+def simple(op, n=1<<28):
+    x = dev.randn((n,), 5); out = dev.DeviceArray.empty((n,), capi.F32)
+    o = capi.OP[op]
+    fn = lambda: capi.check(L.axb_unary(o, ctypes.byref(x.desc()), ctypes.byref(out.desc()), 0.0, None))
+    med, mn = timeit(fn)
+    return dict(workload="unary_"+op, ms_med=med, GBps_med=n*8/med/1e6, GBps_min=n*8/mn/1e6)
+
+def add(n=1<<27):
+    x = dev.randn((n,), 5); y = dev.randn((n,), 6); out = dev.DeviceArray.empty((n,), capi.F32)
+    fn = lambda: capi.check(L.axb_binary(0, ctypes.byref(x.desc()), ctypes.byref(y.desc()), ctypes.byref(out.desc()), None))
+    med, mn = timeit(fn)
+    return dict(workload="add", ms_med=med, GBps_med=n*12/med/1e6, GBps_min=n*12/mn/1e6)
+
+def d2d(n=1<<28):
+    x = dev.randn((n,), 5); out = dev.DeviceArray.empty((n,), capi.F32)
+    fn = lambda: capi.check(L.axb_memcpy_d2d(ctypes.c_void_p(out.storage.ptr), ctypes.c_void_p(x.storage.ptr), n*4, None))
+    med, mn = timeit(fn)
+    return dict(workload="cudaMemcpy_d2d", ms_med=med, GBps_med=n*8/med/1e6, GBps_min=n*8/mn/1e6)
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["d2d", "relu", "exp", "gelu", "add", "c2"]
+    for w in which:
+        r = d2d() if w == "d2d" else c2() if w == "c2" else add() if w == "add" else simple(w)
+        print(json.dumps(r), flush=True)
