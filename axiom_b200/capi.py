@@ -60,6 +60,10 @@ class AxbAllocStats(ctypes.Structure):
                 ("bytes_in_use", "bytes_cached", "peak_bytes_in_use", "n_cuda_malloc", "n_cache_hits", "n_allocs")]
 
 
+class AxbJitStats(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_uint64) for n in ("mem_hits", "disk_hits", "compiles")]
+
+
 class AxbMatmulEpilogue(ctypes.Structure):
     _fields_ = [("bias", ctypes.POINTER(AxbTensor)), ("activation", ctypes.c_int32)]
 
@@ -122,6 +126,8 @@ def lib() -> ctypes.CDLL:
         "axb_memcpy_d2d": (i32, [vp, vp, sz, vp]),
         "axb_memset": (i32, [vp, i32, sz, vp]),
         "axb_elementwise": (i32, [I, i32, T, i32, T, vp]),
+        "axb_elementwise_precompile": (i32, [I, i32, T, i32, T]),
+        "axb_get_jit_stats": (i32, [ctypes.POINTER(AxbJitStats)]),
         "axb_promote_types": (i32, [i32, i32]),
         "axb_binary_result_dtype": (i32, [i32, i32, i32]),
         "axb_unary_result_dtype": (i32, [i32, i32]),

@@ -1,13 +1,17 @@
-// elementwise.cu — host side of kernel family 1: compiles an axb_instr program into the register-machine
-// micro-program of elementwise.cuh, collapses the iteration space and launches ONE kernel.
+// elementwise.cu — host side of kernel family 1: lowers an axb_instr program to the straight-line statement
+// list of ew_prelude.cuh (one specialised sm_100a kernel per program signature, see jit.cpp), collapses the
+// iteration space and launches ONE kernel per fusion group.
 //
 // Semantics follow the reference op by op (file:line in each rule below); see include/axb.h.
 #include <algorithm>
 #include <cstring>
+#include <string>
 #include <vector>
 
 #include "axb_internal.h"
-#include "elementwise.cuh"
+#include "ew_micro_table.h"
+#include "ew_prelude.cuh"
+#include "jit.h"
 
 namespace axb {
 namespace ew {
@@ -26,23 +30,88 @@ Cls cls_of(int dt) {
 }
 bool is_unsigned(int dt) { return dt == AXB_U8 || dt == AXB_U16 || dt == AXB_U32 || dt == AXB_U64 || dt == AXB_BOOL; }
 
+const MicroDef *micro_def(uint32_t op) {
+    for (const MicroDef &d : kMicroDefs)
+        if (d.id == op)
+            return &d;
+    return nullptr;
+}
+const char *reg_name(uint32_t r) {
+    static const char *names[] = {"t", "acc", "u", "s0", "s1", "s2", "s3"};
+    return r < 7 ? names[r] : "acc";
+}
+const char *mode_name(int m) { return m == MODE_VEC ? "MODE_VEC" : m == MODE_BCAST ? "MODE_BCAST" : "MODE_STRIDED"; }
+
+// Emits the statement list of one specialised kernel. The text depends only on the program SIGNATURE (ops,
+// dtypes, operand access modes): shapes, strides, pointers and immediates stay run-time parameters.
 struct Builder {
     Params &p;
     bool wide;
     int n_micro = 0, n_imm = 0;
+    std::string code;
     axb_status st = AXB_OK;
     explicit Builder(Params &pp, bool w) : p(pp), wide(w) {}
+    void line(const std::string &s) {
+        code += "            ";
+        code += s;
+        code += "\n";
+        ++n_micro;
+    }
     void emit(uint32_t op, uint32_t a = 0, uint32_t b = 0, uint32_t fl = 0) {
+        if (st != AXB_OK)
+            return;
         if (n_micro >= kMaxMicro) {
-            st = fail(AXB_ERR_UNSUPPORTED, "axb_elementwise: program too long after lowering (> %d micro-ops)", kMaxMicro);
+            st = fail(AXB_ERR_UNSUPPORTED, "axb_elementwise: program too long after lowering (> %d statements)", kMaxMicro);
             return;
         }
-        p.micro[n_micro++] = op | (a << 8) | (b << 16) | (fl << 24);
+        char buf[512];
+        switch (op) {
+        case M_LOAD:
+            snprintf(buf, sizeof buf, "EW_LOAD(%u, %d, %s, %s)", a, (int)p.in[a].dtype, mode_name(p.in[a].mode), reg_name(b));
+            line(buf);
+            return;
+        case M_IMM:
+            snprintf(buf, sizeof buf, "EW_IMM(%u, %s)", a, reg_name(b));
+            line(buf);
+            return;
+        case M_MOV:
+            snprintf(buf, sizeof buf, "EW_MOV(%s, %s)", reg_name(a), reg_name(b));
+            line(buf);
+            return;
+        case M_STORE:
+            snprintf(buf, sizeof buf, "EW_STORE(%d, %s)", (int)p.out.dtype, mode_name(p.out.mode));
+            line(buf);
+            return;
+        case M_SEL: line("EW_SEL"); return;
+        case M_F_LEAKY:
+            snprintf(buf, sizeof buf, "EW_LEAKY(%u)", a);
+            line(buf);
+            break;
+        default: {
+            const MicroDef *d = micro_def(op);
+            if (!d) {
+                st = fail(AXB_ERR_UNSUPPORTED, "axb_elementwise: internal: micro-op %u has no definition", op);
+                return;
+            }
+            std::string s;
+            if (!strcmp(d->kind, "CVT") || !strcmp(d->kind, "CVT64")) {
+                s = std::string("EW_CVT_ON(") + (a == R_T ? "R_T" : a == R_ACC ? "R_ACC" : "R_U") + ", AXB_" + d->kind + "(" +
+                    d->expr + "))";
+                line(s);
+                return; // conversions carry no rounding flag
+            }
+            s = std::string("EW_OP(") + ((fl & FL_SWAP) ? "true" : "false") + ", AXB_" + d->kind + "(" + d->expr + "))";
+            line(s);
+            break;
+        }
+        }
+        if ((fl & 3u) == RND_BF16)
+            line("EW_RND_BF16");
+        else if ((fl & 3u) == RND_F16)
+            line("EW_RND_F16");
     }
     int add_imm(uint64_t bits) {
-        for (int i = 0; i < n_imm; ++i)
-            if (p.imm[i] == bits)
-                return i;
+        // no de-duplication: the slot numbering (and so the kernel text) must not depend on immediate VALUES
         if (n_imm >= kMaxImm) {
             st = fail(AXB_ERR_UNSUPPORTED, "axb_elementwise: too many immediates (> %d)", kMaxImm);
             return 0;
@@ -401,7 +470,7 @@ uint32_t cmp_micro(int op) {
 
 // Lower the typed program to micro-ops. `src_dtype(k)` = dtype of input k.
 axb_status lower_program(const axb_instr *prog, int n_instr, const axb_tensor *inputs, int n_inputs, bool wide,
-                         Params &p, int *final_dtype, bool emit_store) {
+                         Params &p, int *final_dtype, bool emit_store, std::string *code_out) {
     Builder B(p, wide);
     std::vector<int> last_use(n_instr, -1), n_uses(n_instr, 0), slot_of(n_instr, -1);
     for (int i = 0; i < n_instr; ++i) {
@@ -652,7 +721,7 @@ axb_status lower_program(const axb_instr *prog, int n_instr, const axb_tensor *i
     if (emit_store)
         B.emit(M_STORE);
     AXB_TRY(B.st);
-    p.n_micro = B.n_micro;
+    *code_out = B.code;
     *final_dtype = prog[n_instr - 1].dtype;
     return AXB_OK;
 }
@@ -787,30 +856,25 @@ axb_status broadcast_all(const axb_tensor *inputs, int n_inputs, int64_t *oshape
     return AXB_OK;
 }
 
-template <int VEC, typename W>
-axb_status launch(const Params &p, DeviceCtx *ctx, cudaStream_t s) {
-    const int threads = 256;
-    int64_t blocks = ((int64_t)p.total_vec + threads - 1) / threads;
-    int64_t cap = (int64_t)ctx->sm_count * 16;
-    if (blocks > cap)
-        blocks = cap;
-    if (blocks < 1)
-        blocks = 1;
-    elementwise_kernel<VEC, W><<<(unsigned)blocks, threads, 0, s>>>(p);
-    AXB_CHECK_LAUNCH();
-    return AXB_OK;
+// Full translation unit of one specialised kernel.
+std::string kernel_source(const std::string &body, bool wide, int n_outer) {
+    std::string s = jit::ew_prelude_text();
+    char hdr[128];
+    snprintf(hdr, sizeof hdr, "\nEW_KERNEL_BEGIN(axb_ew, %d, %s, %d)\n", wide ? 4 : 8, wide ? "uint64_t" : "uint32_t", n_outer);
+    s += hdr;
+    s += body;
+    s += "EW_KERNEL_END\n";
+    return s;
 }
 
-} // namespace ew
-} // namespace axb
+struct Prepared {
+    Params p;
+    std::string source;
+};
 
-using namespace axb;
-using namespace axb::ew;
-
-extern "C" {
-
-axb_status axb_elementwise(const axb_instr *prog, int n_instr, const axb_tensor *inputs, int n_inputs,
-                           const axb_tensor *out, axb_stream_t stream) {
+// Validates, plans the iteration space and generates the kernel text. No device needed.
+axb_status prepare(const axb_instr *prog, int n_instr, const axb_tensor *inputs, int n_inputs, const axb_tensor *out,
+                   Prepared *P, bool *empty) {
     AXB_REQUIRE(prog && n_instr > 0 && n_instr <= AXB_MAX_INSTRS, AXB_ERR_INVALID,
                 "axb_elementwise: need 1..%d instructions", AXB_MAX_INSTRS);
     AXB_REQUIRE(n_inputs >= 0 && n_inputs <= AXB_MAX_INPUTS, AXB_ERR_INVALID, "axb_elementwise: at most %d inputs",
@@ -831,7 +895,6 @@ axb_status axb_elementwise(const axb_instr *prog, int n_instr, const axb_tensor 
     int ondim = 0;
     if (n_inputs > 0) {
         AXB_TRY(broadcast_all(inputs, n_inputs, oshape, &ondim));
-        // out may carry extra leading dims / larger extents only if it equals the broadcast shape
         AXB_REQUIRE(out->ndim >= ondim, AXB_ERR_SHAPE, "axb_elementwise: out rank %d < broadcast rank %d", out->ndim,
                     ondim);
         for (int d = 0; d < out->ndim; ++d) {
@@ -845,23 +908,74 @@ axb_status axb_elementwise(const axb_instr *prog, int n_instr, const axb_tensor 
     ondim = out->ndim;
     for (int d = 0; d < ondim; ++d)
         oshape[d] = out->shape[d];
-    if (numel(*out) == 0)
+    *empty = numel(*out) == 0;
+    if (*empty)
+        return AXB_OK;
+    Params &p = P->p;
+    memset(&p, 0, sizeof(p));
+    const int vec = wide ? 4 : 8;
+    AXB_TRY(plan_iteration(inputs, n_inputs, out, oshape, ondim, vec, p));
+    int fdt = 0;
+    std::string body;
+    AXB_TRY(lower_program(prog, n_instr, inputs, n_inputs, wide, p, &fdt, true, &body));
+    AXB_REQUIRE(fdt == out->dtype, AXB_ERR_INVALID, "axb_elementwise: last instruction yields dtype %d but out is %d", fdt,
+                out->dtype);
+    P->source = kernel_source(body, wide, (int)p.n_outer);
+    return AXB_OK;
+}
+
+} // namespace ew
+} // namespace axb
+
+using namespace axb;
+using namespace axb::ew;
+
+extern "C" {
+
+axb_status axb_elementwise(const axb_instr *prog, int n_instr, const axb_tensor *inputs, int n_inputs,
+                           const axb_tensor *out, axb_stream_t stream) {
+    Prepared P;
+    bool empty = false;
+    AXB_TRY(prepare(prog, n_instr, inputs, n_inputs, out, &P, &empty));
+    if (empty)
         return AXB_OK;
     cudaStream_t s;
     DeviceCtx *ctx;
     AXB_TRY(resolve_stream(stream, &s, &ctx));
+    jit::Kernel k;
+    AXB_TRY(jit::get_kernel(P.source, "axb_ew", ctx->device, &k));
+    const int threads = 256;
+    int64_t blocks = ((int64_t)P.p.total_vec + threads - 1) / threads;
+    const int64_t cap = (int64_t)ctx->sm_count * 16;
+    if (blocks > cap)
+        blocks = cap;
+    if (blocks < 1)
+        blocks = 1;
+    void *args[] = {&P.p};
+    AXB_TRY(jit::launch(k, (unsigned)blocks, threads, 0, s, args));
+    count_launch();
+    return AXB_OK;
+}
 
-    Params p;
-    memset(&p, 0, sizeof(p));
-    int fdt = 0;
-    AXB_TRY(lower_program(prog, n_instr, inputs, n_inputs, wide, p, &fdt, true));
-    AXB_REQUIRE(fdt == out->dtype, AXB_ERR_INVALID, "axb_elementwise: last instruction yields dtype %d but out is %d", fdt,
-                out->dtype);
-    const int vec = wide ? 4 : 8;
-    AXB_TRY(plan_iteration(inputs, n_inputs, out, oshape, ondim, vec, p));
-    if (wide)
-        return launch<4, uint64_t>(p, ctx, s);
-    return launch<8, uint32_t>(p, ctx, s);
+// Compile-only entry (no device needed): makes sure the specialised kernel of this program signature is in
+// the in-tree cubin cache. build() calls it for the BASELINE configs so the named hot path never JITs.
+axb_status axb_elementwise_precompile(const axb_instr *prog, int n_instr, const axb_tensor *inputs, int n_inputs,
+                                      const axb_tensor *out) {
+    Prepared P;
+    bool empty = false;
+    AXB_TRY(prepare(prog, n_instr, inputs, n_inputs, out, &P, &empty));
+    if (empty)
+        return AXB_OK;
+    return jit::precompile(P.source);
+}
+
+axb_status axb_get_jit_stats(axb_jit_stats *out) {
+    AXB_REQUIRE(out, AXB_ERR_INVALID, "axb_get_jit_stats: null");
+    jit::Stats s = jit::stats();
+    out->mem_hits = s.mem_hits;
+    out->disk_hits = s.disk_hits;
+    out->compiles = s.compiles;
+    return AXB_OK;
 }
 
 } // extern "C"

@@ -1,23 +1,50 @@
-// elementwise.cuh — device side of kernel family 1: the fused elementwise / broadcast / where chain.
+// ew_prelude.cuh — device side of kernel family 1: the fused elementwise / broadcast / where chain.
 //
-// One kernel runs a whole fusion group: every thread owns VEC consecutive output
-// elements of one innermost run, keeps the chain's live values in registers and walks a tiny
-// warp-uniform micro-program (decoded from kernel parameters = constant bank, no divergence).
-// Memory side: inputs whose innermost run is contiguous and 16-byte aligned are read with 128-bit
-// loads, broadcast inputs with one scalar load, anything else with per-lane strided loads; the output is
-// written with 128-bit stores. HBM-bound by construction: every operand byte is read once.
+// One kernel runs a whole fusion group. The host (elementwise.cu) lowers the typed
+// axb_instr program to a straight-line sequence of the EW_* statements defined here and the resulting
+// translation unit (this prelude + ~20 generated lines) is specialised per program SIGNATURE (ops, dtypes,
+// operand access modes — never shapes or immediates) by NVRTC for sm_100a, cached as a cubin in-tree
+// (axiom_b200/kernel_cache/) and in memory. build() pre-compiles the signatures of the BASELINE configs, so
+// the named hot path never compiles at run time. Everything is static in the specialised kernel: every thread
+// owns VEC consecutive output elements of one innermost run and keeps the chain's live values in registers.
+// Memory side: inputs whose innermost run is contiguous and 16-byte aligned are read with 128-bit streaming
+// loads, broadcast inputs with one scalar load, anything else with per-lane strided loads; the output is written
+// with 128-bit stores. HBM-bound by construction: every operand byte is read once.
 //
-// Register machine (per thread): acc, t, u and NSLOT save slots, each VEC words wide.
+// Register model (per thread): acc, t, u and NSLOT save slots, each VEC words wide.
 //   canonical value forms   F: fp32 (bf16/fp16 values are fp32 values already rounded to that format)
 //                           I: 32-bit integer (narrow ints sign/zero-extended, bool = 0/1)
 //                           D: fp64, L: 64-bit integer          (only in the 64-bit-word instantiation)
+//
+// This file must stay self-contained (no system headers under NVRTC): it is embedded into libaxb.so as a string.
 #pragma once
-#include <cuda_bf16.h>
-#include <cuda_fp16.h>
+#ifndef __CUDACC_RTC__
 #include <cuda_runtime.h>
 #include <stdint.h>
+#else
+typedef signed char int8_t;
+typedef unsigned char uint8_t;
+typedef short int16_t;
+typedef unsigned short uint16_t;
+typedef int int32_t;
+typedef unsigned int uint32_t;
+typedef long long int64_t;
+typedef unsigned long long uint64_t;
+#ifndef INT32_MIN
+#define INT32_MIN (-2147483647 - 1)
+#endif
+#ifndef INT64_MIN
+#define INT64_MIN (-9223372036854775807LL - 1)
+#endif
+#endif
 
 #include "hwy_math.cuh"
+
+#ifndef AXB_H
+// == axb_dtype (include/axb.h) == axiom::DType
+enum { AXB_BOOL = 0, AXB_I8 = 1, AXB_I16 = 2, AXB_I32 = 3, AXB_I64 = 4, AXB_U8 = 5, AXB_U16 = 6, AXB_U32 = 7,
+       AXB_U64 = 8, AXB_F16 = 9, AXB_BF16 = 10, AXB_F32 = 11, AXB_F64 = 12, AXB_C64 = 13, AXB_C128 = 14 };
+#endif
 
 namespace axb {
 namespace ew {
@@ -33,45 +60,6 @@ enum Mode : uint8_t { MODE_VEC = 0, MODE_STRIDED = 1, MODE_BCAST = 2 };
 enum Round : uint8_t { RND_NONE = 0, RND_BF16 = 1, RND_F16 = 2 };
 enum Flag : uint8_t { FL_SWAP = 4 }; // low 2 bits of flags = Round
 
-enum M : uint8_t {
-    M_END = 0,
-    M_LOAD,  // a = input, b = dst sel (t/acc/u)
-    M_IMM,   // a = imm index, b = dst sel
-    M_MOV,   // a = src sel, b = dst sel
-    M_STORE, // store acc
-    M_SEL,   // acc = (acc != 0) ? t : u
-    // conversions, a = register sel (t/acc/u)
-    M_CVT_RND_BF16, M_CVT_RND_F16, M_CVT_I2F, M_CVT_U2F, M_CVT_F2I, M_CVT_F2U, M_CVT_F2BOOL, M_CVT_I2BOOL,
-    M_CVT_WRAP_I8, M_CVT_WRAP_U8, M_CVT_WRAP_I16, M_CVT_WRAP_U16,
-    // 64-bit word conversions
-    M_CVT_F2D, M_CVT_D2F, M_CVT_I2L, M_CVT_U2L, M_CVT_L2I, M_CVT_L2F, M_CVT_UL2F, M_CVT_L2D, M_CVT_UL2D,
-    M_CVT_D2L, M_CVT_D2UL, M_CVT_F2L, M_CVT_F2UL, M_CVT_D2BOOL, M_CVT_L2BOOL, M_CVT_I2D, M_CVT_U2D, M_CVT_D2I,
-    M_CVT_D2U,
-    // F unary (acc)
-    M_F_NEG, M_F_ABS, M_F_SQRT, M_F_EXP, M_F_LOG, M_F_SIN, M_F_COS, M_F_TAN, M_F_ERF, M_F_SIGN, M_F_FLOOR,
-    M_F_CEIL, M_F_TRUNC, M_F_ROUND, M_F_RECIP, M_F_SQUARE, M_F_CBRT, M_F_RELU, M_F_LEAKY, M_F_SILU, M_F_SIGMOID,
-    M_F_TANH, M_F_GELU, M_F_ISNAN, M_F_ISINF, M_F_ISFINITE, M_F_LNOT,
-    // F unary, libm-accurate variants used for bf16/fp16 (reference evaluates those in double)
-    M_FA_SQRT, M_FA_EXP, M_FA_LOG, M_FA_SIN, M_FA_COS, M_FA_TAN, M_FA_ERF, M_FA_CBRT, M_FA_SILU, M_FA_SIGMOID,
-    M_FA_TANH, M_FA_GELU,
-    // F binary: acc = f(acc, t)  (FL_SWAP: f(t, acc))
-    M_F_ADD, M_F_SUB, M_F_MUL, M_F_DIV, M_F_POW, M_F_MOD, M_F_MAX, M_F_MIN, M_F_ATAN2, M_F_HYPOT, M_FA_POW,
-    M_FA_HYPOT,
-    M_F_EQ, M_F_NE, M_F_LT, M_F_LE, M_F_GT, M_F_GE, M_F_LAND, M_F_LOR, M_F_LXOR,
-    // I unary / binary (32-bit ints; U = unsigned flavour where it matters)
-    M_I_NEG, M_I_ABS, M_I_SIGN, M_I_SQUARE, M_I_RELU, M_I_RECIP, M_U_RECIP, M_I_LNOT,
-    M_I_ADD, M_I_SUB, M_I_MUL, M_I_DIV, M_U_DIV, M_I_MOD, M_U_MOD, M_I_MAX, M_U_MAX, M_I_MIN, M_U_MIN, M_I_AND,
-    M_I_OR, M_I_XOR, M_I_SHL, M_I_SHR, M_U_SHR,
-    // D (fp64) and L (int64)
-    M_D_NEG, M_D_ABS, M_D_SQRT, M_D_EXP, M_D_LOG, M_D_SIN, M_D_COS, M_D_TAN, M_D_TANH, M_D_ERF, M_D_SIGN,
-    M_D_FLOOR, M_D_CEIL, M_D_TRUNC, M_D_ROUND, M_D_RECIP, M_D_SQUARE, M_D_RELU, M_D_SIGMOID, M_D_ISNAN,
-    M_D_ISINF, M_D_ISFINITE, M_D_LNOT,
-    M_D_ADD, M_D_SUB, M_D_MUL, M_D_DIV, M_D_POW, M_D_MOD, M_D_MAX, M_D_MIN, M_D_HYPOT, M_D_ATAN2,
-    M_L_NEG, M_L_ABS, M_L_SIGN, M_L_SQUARE, M_L_RELU, M_L_LNOT,
-    M_L_ADD, M_L_SUB, M_L_MUL, M_L_DIV, M_UL_DIV, M_L_MOD, M_UL_MOD, M_L_MAX, M_UL_MAX, M_L_MIN, M_UL_MIN,
-    M_L_AND, M_L_OR, M_L_XOR, M_L_SHL, M_L_SHR, M_UL_SHR,
-    M_COUNT
-};
 
 struct Operand {
     const char *ptr;            // base + byte_offset
@@ -86,7 +74,6 @@ struct Params {
     Operand in[kMaxIn];
     Operand out;
     uint64_t imm[kMaxImm];
-    uint32_t micro[kMaxMicro]; // op | a<<8 | b<<16 | flags<<24
     // iteration space: innermost run of `inner_len` elements, n_outer collapsed outer dims
     uint32_t inner_len;
     uint32_t nvec_inner; // ceil(inner_len / VEC)
@@ -95,7 +82,7 @@ struct Params {
     uint32_t outer_shape[kMaxOuter];
     uint32_t div_m[kMaxOuter + 1]; // fast-div magics: [0] = nvec_inner, [1+d] = outer_shape[d]
     uint32_t div_s[kMaxOuter + 1];
-    int32_t n_micro;
+    int32_t pad0;
     int32_t reduce_op; // fused full reduction (axb_elementwise_reduce): 0 = none
     void *reduce_ws;   // per-block partials
 };
@@ -104,12 +91,22 @@ __device__ __forceinline__ uint32_t fastdiv(uint32_t n, uint32_t m, uint32_t s) 
     return (__umulhi(n, m) + n) >> s;
 }
 
+__device__ __forceinline__ float h2f(unsigned short h) {
+    float f;
+    asm("cvt.f32.f16 %0, %1;" : "=f"(f) : "h"(h));
+    return f;
+}
+__device__ __forceinline__ unsigned short f2h(float f) {
+    unsigned short h;
+    asm("cvt.rn.f16.f32 %0, %1;" : "=h"(h) : "f"(f));
+    return h;
+}
 // ---- canonicalisation of storage bits -------------------------------------------------------------
 template <typename W> __device__ __forceinline__ W canon(uint64_t raw, int dt) {
     switch (dt) {
     case AXB_F32: case AXB_I32: case AXB_U32: return (W)(uint32_t)raw;
     case AXB_BF16: return (W)((uint32_t)raw << 16);
-    case AXB_F16: return (W)__float_as_uint(__half2float(__ushort_as_half((unsigned short)raw)));
+    case AXB_F16: return (W)__float_as_uint(h2f((unsigned short)raw));
     case AXB_I16: return (W)(uint32_t)(int32_t)(int16_t)raw;
     case AXB_U16: return (W)(uint32_t)(uint16_t)raw;
     case AXB_I8: return (W)(uint32_t)(int32_t)(int8_t)raw;
@@ -126,12 +123,12 @@ __device__ __forceinline__ uint32_t f32_to_bf16_bits(float f) {
     return b >> 16;
 }
 __device__ __forceinline__ float round_bf16(float f) { return __uint_as_float(f32_to_bf16_bits(f) << 16); }
-__device__ __forceinline__ float round_f16(float f) { return __half2float(__float2half_rn(f)); }
+__device__ __forceinline__ float round_f16(float f) { return h2f(f2h(f)); }
 
 template <typename W> __device__ __forceinline__ uint64_t decanon(W v, int dt) {
     switch (dt) {
     case AXB_BF16: return f32_to_bf16_bits(__uint_as_float((uint32_t)v));
-    case AXB_F16: return __half_as_ushort(__float2half_rn(__uint_as_float((uint32_t)v)));
+    case AXB_F16: return f2h(__uint_as_float((uint32_t)v));
     case AXB_BOOL: return ((uint32_t)v != 0) ? 1u : 0u;
     default: return (uint64_t)v;
     }
@@ -153,7 +150,7 @@ __device__ __forceinline__ void st_raw(char *p, int size, uint64_t v) {
     default: *reinterpret_cast<uint64_t *>(p) = v; break;
     }
 }
-__device__ __forceinline__ int dsize(int dt) {
+__device__ __host__ constexpr int dsize(int dt) {
     return (dt == AXB_BOOL || dt == AXB_I8 || dt == AXB_U8)                      ? 1
            : (dt == AXB_I16 || dt == AXB_U16 || dt == AXB_F16 || dt == AXB_BF16) ? 2
            : (dt == AXB_I32 || dt == AXB_U32 || dt == AXB_F32)                   ? 4
@@ -183,20 +180,20 @@ __device__ __forceinline__ void stg64(void *p, uint2 v) {
 }
 
 // Load VEC elements of operand `o` starting at element column `col` of the current run.
-template <int VEC, typename W>
+template <int VEC, typename W, int DT, int MODE>
 __device__ __forceinline__ void load_vec(const Operand &o, int64_t outer_off, uint32_t col, int valid,
                                          W (&r)[VEC]) {
-    const int dt = o.dtype;
-    const int sz = dsize(dt);
+    constexpr int dt = DT;
+    constexpr int sz = dsize(dt);
     const char *base = o.ptr + outer_off;
-    if (o.mode == MODE_BCAST) {
+    if (MODE == MODE_BCAST) {
         W v = canon<W>(ld_raw(base, sz), dt);
 #pragma unroll
         for (int i = 0; i < VEC; ++i)
             r[i] = v;
         return;
     }
-    if (VEC == 8 && o.mode == MODE_VEC && valid == VEC) {
+    if (VEC == 8 && MODE == MODE_VEC && valid == VEC) {
         const char *p = base + (int64_t)col * sz;
         if (sz == 4) {
             uint4 a = ldg128(p), b = ldg128(p + 16);
@@ -223,7 +220,7 @@ __device__ __forceinline__ void load_vec(const Operand &o, int64_t outer_off, ui
             return;
         }
     }
-    if (VEC == 4 && sizeof(W) == 8 && o.mode == MODE_VEC && valid == VEC && sz == 8) {
+    if (VEC == 4 && sizeof(W) == 8 && MODE == MODE_VEC && valid == VEC && sz == 8) {
         const char *p = base + (int64_t)col * 8;
         uint4 a = ldg128(p), b = ldg128(p + 16);
         r[0] = (W)(((uint64_t)a.y << 32) | a.x);
@@ -241,13 +238,13 @@ __device__ __forceinline__ void load_vec(const Operand &o, int64_t outer_off, ui
     }
 }
 
-template <int VEC, typename W>
+template <int VEC, typename W, int DT, int MODE>
 __device__ __forceinline__ void store_vec(const Operand &o, int64_t outer_off, uint32_t col, int valid,
                                           const W (&r)[VEC]) {
-    const int dt = o.dtype;
-    const int sz = dsize(dt);
+    constexpr int dt = DT;
+    constexpr int sz = dsize(dt);
     char *base = const_cast<char *>(o.ptr) + outer_off;
-    if (VEC == 8 && o.mode == MODE_VEC && valid == VEC) {
+    if (VEC == 8 && MODE == MODE_VEC && valid == VEC) {
         char *p = base + (int64_t)col * sz;
         if (sz == 4) {
             stg128(p, make_uint4((uint32_t)r[0], (uint32_t)r[1 % VEC], (uint32_t)r[2 % VEC], (uint32_t)r[3 % VEC]));
@@ -273,7 +270,7 @@ __device__ __forceinline__ void store_vec(const Operand &o, int64_t outer_off, u
             return;
         }
     }
-    if (VEC == 4 && sizeof(W) == 8 && o.mode == MODE_VEC && valid == VEC && sz == 8) {
+    if (VEC == 4 && sizeof(W) == 8 && MODE == MODE_VEC && valid == VEC && sz == 8) {
         char *p = base + (int64_t)col * 8;
         stg128(p, make_uint4((uint32_t)r[0], (uint32_t)((uint64_t)r[0] >> 32), (uint32_t)r[1 % VEC],
                              (uint32_t)((uint64_t)r[1 % VEC] >> 32)));
@@ -359,16 +356,14 @@ __device__ __forceinline__ int64_t l_mod(int64_t a, int64_t b) { return b == 0 ?
             float a = asF<W>(acc[i]);                                                                   \
             acc[i] = fromF<W>(EXPR);                                                                    \
         }                                                                                               \
-    }                                                                                                   \
-    break;
+    }                                                                                                   
 #define AXB_UN_F2I(EXPR)                                                                                \
     {                                                                                                   \
         _Pragma("unroll") for (int i = 0; i < VEC; ++i) {                                               \
             float a = asF<W>(acc[i]);                                                                   \
             acc[i] = fromI<W>((EXPR) ? 1 : 0);                                                          \
         }                                                                                               \
-    }                                                                                                   \
-    break;
+    }                                                                                                   
 #define AXB_BIN_F(EXPR)                                                                                 \
     {                                                                                                   \
         _Pragma("unroll") for (int i = 0; i < VEC; ++i) {                                               \
@@ -376,8 +371,7 @@ __device__ __forceinline__ int64_t l_mod(int64_t a, int64_t b) { return b == 0 ?
             float b = asF<W>(swap ? acc[i] : t[i]);                                                     \
             acc[i] = fromF<W>(EXPR);                                                                    \
         }                                                                                               \
-    }                                                                                                   \
-    break;
+    }                                                                                                   
 #define AXB_CMP_F(EXPR)                                                                                 \
     {                                                                                                   \
         _Pragma("unroll") for (int i = 0; i < VEC; ++i) {                                               \
@@ -385,8 +379,7 @@ __device__ __forceinline__ int64_t l_mod(int64_t a, int64_t b) { return b == 0 ?
             float b = asF<W>(swap ? acc[i] : t[i]);                                                     \
             acc[i] = fromI<W>((EXPR) ? 1 : 0);                                                          \
         }                                                                                               \
-    }                                                                                                   \
-    break;
+    }                                                                                                   
 #define AXB_UN_I(EXPR)                                                                                  \
     {                                                                                                   \
         _Pragma("unroll") for (int i = 0; i < VEC; ++i) {                                               \
@@ -395,8 +388,7 @@ __device__ __forceinline__ int64_t l_mod(int64_t a, int64_t b) { return b == 0 ?
             (void)ua;                                                                                   \
             acc[i] = fromI<W>((int32_t)(EXPR));                                                         \
         }                                                                                               \
-    }                                                                                                   \
-    break;
+    }                                                                                                   
 #define AXB_BIN_I(EXPR)                                                                                 \
     {                                                                                                   \
         _Pragma("unroll") for (int i = 0; i < VEC; ++i) {                                               \
@@ -407,8 +399,7 @@ __device__ __forceinline__ int64_t l_mod(int64_t a, int64_t b) { return b == 0 ?
             (void)ub;                                                                                   \
             acc[i] = fromI<W>((int32_t)(EXPR));                                                         \
         }                                                                                               \
-    }                                                                                                   \
-    break;
+    }                                                                                                   
 #define AXB_UN_D(EXPR)                                                                                  \
     {                                                                                                   \
         if constexpr (sizeof(W) == 8) {                                                                 \
@@ -417,8 +408,7 @@ __device__ __forceinline__ int64_t l_mod(int64_t a, int64_t b) { return b == 0 ?
                 acc[i] = fromD(EXPR);                                                                   \
             }                                                                                           \
         }                                                                                               \
-    }                                                                                                   \
-    break;
+    }                                                                                                   
 #define AXB_UN_D2I(EXPR)                                                                                \
     {                                                                                                   \
         if constexpr (sizeof(W) == 8) {                                                                 \
@@ -427,8 +417,7 @@ __device__ __forceinline__ int64_t l_mod(int64_t a, int64_t b) { return b == 0 ?
                 acc[i] = (W)((EXPR) ? 1 : 0);                                                           \
             }                                                                                           \
         }                                                                                               \
-    }                                                                                                   \
-    break;
+    }                                                                                                   
 #define AXB_BIN_D(EXPR)                                                                                 \
     {                                                                                                   \
         if constexpr (sizeof(W) == 8) {                                                                 \
@@ -438,8 +427,7 @@ __device__ __forceinline__ int64_t l_mod(int64_t a, int64_t b) { return b == 0 ?
                 acc[i] = fromD(EXPR);                                                                   \
             }                                                                                           \
         }                                                                                               \
-    }                                                                                                   \
-    break;
+    }                                                                                                   
 #define AXB_UN_L(EXPR)                                                                                  \
     {                                                                                                   \
         if constexpr (sizeof(W) == 8) {                                                                 \
@@ -448,8 +436,7 @@ __device__ __forceinline__ int64_t l_mod(int64_t a, int64_t b) { return b == 0 ?
                 acc[i] = (W)(int64_t)(EXPR);                                                            \
             }                                                                                           \
         }                                                                                               \
-    }                                                                                                   \
-    break;
+    }                                                                                                   
 #define AXB_BIN_L(EXPR)                                                                                 \
     {                                                                                                   \
         if constexpr (sizeof(W) == 8) {                                                                 \
@@ -462,8 +449,7 @@ __device__ __forceinline__ int64_t l_mod(int64_t a, int64_t b) { return b == 0 ?
                 acc[i] = (W)(int64_t)(EXPR);                                                            \
             }                                                                                           \
         }                                                                                               \
-    }                                                                                                   \
-    break;
+    }                                                                                                   
 // conversion applied to the register selected by `a` (t / acc / u)
 #define AXB_CVT(EXPR)                                                                                   \
     {                                                                                                   \
@@ -477,8 +463,7 @@ __device__ __forceinline__ int64_t l_mod(int64_t a, int64_t b) { return b == 0 ?
             else                                                                                        \
                 u[i] = y;                                                                               \
         }                                                                                               \
-    }                                                                                                   \
-    break;
+    }                                                                                                   
 #define AXB_CVT64(EXPR)                                                                                 \
     {                                                                                                   \
         if constexpr (sizeof(W) == 8) {                                                                 \
@@ -493,322 +478,94 @@ __device__ __forceinline__ int64_t l_mod(int64_t a, int64_t b) { return b == 0 ?
                     u[i] = y;                                                                           \
             }                                                                                           \
         }                                                                                               \
-    }                                                                                                   \
-    break;
+    }                                                                                                   
 
-// Executes the micro-program for one vector. Returns with the final value in acc (after M_STORE if any).
-template <int VEC, typename W>
-__device__ __forceinline__ void run_program(const Params &p, const int64_t *__restrict__ coord_unused,
-                                            const uint32_t (&c)[kMaxOuter], uint32_t col, int valid,
-                                            W (&acc)[VEC], bool do_store) {
-    (void)coord_unused;
-    W t[VEC], u[VEC], s[kNSlot][VEC];
-#pragma unroll
-    for (int i = 0; i < VEC; ++i) {
-        t[i] = 0;
-        u[i] = 0;
-        acc[i] = 0;
-#pragma unroll
-        for (int k = 0; k < kNSlot; ++k)
-            s[k][i] = 0;
-    }
-    const int n_outer = p.n_outer;
-    auto outer_off = [&](const Operand &o) -> int64_t {
-        int64_t off = 0;
-#pragma unroll
-        for (int d = 0; d < kMaxOuter; ++d)
-            if (d < n_outer)
-                off += (int64_t)c[d] * o.stride[d];
-        return off;
-    };
 
-    for (int pc = 0; pc < p.n_micro; ++pc) {
-        const uint32_t m = p.micro[pc];
-        const uint32_t op = m & 0xFFu, ra = (m >> 8) & 0xFFu, rb = (m >> 16) & 0xFFu, fl = m >> 24;
-        const bool swap = (fl & FL_SWAP) != 0;
-        switch (op) {
-        case M_LOAD: {
-            const Operand &o = p.in[ra];
-            int64_t off = outer_off(o);
-            if (rb == R_T)
-                load_vec<VEC, W>(o, off, col, valid, t);
-            else if (rb == R_ACC)
-                load_vec<VEC, W>(o, off, col, valid, acc);
-            else
-                load_vec<VEC, W>(o, off, col, valid, u);
-            break;
-        }
-        case M_IMM: {
-            W v = (W)p.imm[ra];
+// ---- statements emitted by the host code generator (elementwise.cu) --------------------------------------
+// All of them run inside EW_KERNEL_BEGIN/END, which declares: p (Params), VEC, W, c[] (outer coordinates),
+// col, valid and the register arrays acc/t/u/s0..s3.
+#define EW_OUTER_OFF(o) outer_off<NOUT>((o), c)
+template <int NOUT> __device__ __forceinline__ int64_t outer_off(const Operand &o, const uint32_t (&c)[kMaxOuter]) {
+    int64_t off = 0;
 #pragma unroll
-            for (int i = 0; i < VEC; ++i) {
-                if (rb == R_T)
-                    t[i] = v;
-                else if (rb == R_ACC)
-                    acc[i] = v;
-                else
-                    u[i] = v;
-            }
-            break;
-        }
-        case M_MOV: {
-            W tmp[VEC];
-#pragma unroll
-            for (int i = 0; i < VEC; ++i) {
-                switch (ra) {
-                case R_T: tmp[i] = t[i]; break;
-                case R_ACC: tmp[i] = acc[i]; break;
-                case R_U: tmp[i] = u[i]; break;
-                case R_S0: tmp[i] = s[0][i]; break;
-                case R_S0 + 1: tmp[i] = s[1][i]; break;
-                case R_S0 + 2: tmp[i] = s[2][i]; break;
-                default: tmp[i] = s[3][i]; break;
-                }
-            }
-#pragma unroll
-            for (int i = 0; i < VEC; ++i) {
-                switch (rb) {
-                case R_T: t[i] = tmp[i]; break;
-                case R_ACC: acc[i] = tmp[i]; break;
-                case R_U: u[i] = tmp[i]; break;
-                case R_S0: s[0][i] = tmp[i]; break;
-                case R_S0 + 1: s[1][i] = tmp[i]; break;
-                case R_S0 + 2: s[2][i] = tmp[i]; break;
-                default: s[3][i] = tmp[i]; break;
-                }
-            }
-            break;
-        }
-        case M_STORE:
-            if (do_store)
-                store_vec<VEC, W>(p.out, outer_off(p.out), col, valid, acc);
-            break;
-        case M_SEL: {
-#pragma unroll
-            for (int i = 0; i < VEC; ++i)
-                acc[i] = (acc[i] != 0) ? t[i] : u[i];
-            break;
-        }
-        // ---- conversions -------------------------------------------------------------------------
-        case M_CVT_RND_BF16: AXB_CVT(fromF<W>(round_bf16(asF<W>(x))))
-        case M_CVT_RND_F16: AXB_CVT(fromF<W>(round_f16(asF<W>(x))))
-        case M_CVT_I2F: AXB_CVT(fromF<W>(__int2float_rn(asI<W>(x))))
-        case M_CVT_U2F: AXB_CVT(fromF<W>(__uint2float_rn((uint32_t)x)))
-        case M_CVT_F2I: AXB_CVT(fromI<W>(__float2int_rz(asF<W>(x))))
-        case M_CVT_F2U: AXB_CVT((W)__float2uint_rz(asF<W>(x)))
-        case M_CVT_F2BOOL: AXB_CVT((W)(asF<W>(x) != 0.0f ? 1u : 0u))
-        case M_CVT_I2BOOL: AXB_CVT((W)((uint32_t)x != 0u ? 1u : 0u))
-        case M_CVT_WRAP_I8: AXB_CVT(fromI<W>((int32_t)(int8_t)(uint32_t)x))
-        case M_CVT_WRAP_U8: AXB_CVT((W)((uint32_t)x & 0xFFu))
-        case M_CVT_WRAP_I16: AXB_CVT(fromI<W>((int32_t)(int16_t)(uint32_t)x))
-        case M_CVT_WRAP_U16: AXB_CVT((W)((uint32_t)x & 0xFFFFu))
-        case M_CVT_F2D: AXB_CVT64(fromD((double)asF<W>(x)))
-        case M_CVT_D2F: AXB_CVT64(fromF<W>((float)asD(x)))
-        case M_CVT_I2L: AXB_CVT64((W)(int64_t)asI<W>(x))
-        case M_CVT_U2L: AXB_CVT64((W)(uint64_t)(uint32_t)x)
-        case M_CVT_L2I: AXB_CVT64((W)(uint32_t)x)
-        case M_CVT_L2F: AXB_CVT64(fromF<W>(__ll2float_rn((long long)x)))
-        case M_CVT_UL2F: AXB_CVT64(fromF<W>(__ull2float_rn((unsigned long long)x)))
-        case M_CVT_L2D: AXB_CVT64(fromD(__ll2double_rn((long long)x)))
-        case M_CVT_UL2D: AXB_CVT64(fromD(__ull2double_rn((unsigned long long)x)))
-        case M_CVT_D2L: AXB_CVT64((W)__double2ll_rz(asD(x)))
-        case M_CVT_D2UL: AXB_CVT64((W)__double2ull_rz(asD(x)))
-        case M_CVT_F2L: AXB_CVT64((W)__float2ll_rz(asF<W>(x)))
-        case M_CVT_F2UL: AXB_CVT64((W)__float2ull_rz(asF<W>(x)))
-        case M_CVT_D2BOOL: AXB_CVT64((W)(asD(x) != 0.0 ? 1u : 0u))
-        case M_CVT_L2BOOL: AXB_CVT64((W)(x != 0 ? 1u : 0u))
-        case M_CVT_I2D: AXB_CVT64(fromD((double)asI<W>(x)))
-        case M_CVT_U2D: AXB_CVT64(fromD((double)(uint32_t)x))
-        case M_CVT_D2I: AXB_CVT64(fromI<W>(__double2int_rz(asD(x))))
-        case M_CVT_D2U: AXB_CVT64((W)__double2uint_rz(asD(x)))
-        // ---- fp32 unary (Highway-exact forms) ------------------------------------------------------
-        case M_F_NEG: AXB_UN_F(__uint_as_float(__float_as_uint(a) ^ 0x80000000u))
-        case M_F_ABS: AXB_UN_F(fabsf(a))
-        case M_F_SQRT: AXB_UN_F(__fsqrt_rn(a))
-        case M_F_EXP: AXB_UN_F(hwym::Exp(a))
-        case M_F_LOG: AXB_UN_F(hwym::Log(a))
-        case M_F_SIN: AXB_UN_F(hwym::Sin(a))
-        case M_F_COS: AXB_UN_F(hwym::Cos(a))
-        case M_F_TAN: AXB_UN_F(hwym::Tan(a))
-        case M_F_ERF: AXB_UN_F(hwym::Erf(a))
-        case M_F_SIGN: AXB_UN_F(f_sign(a))
-        case M_F_FLOOR: AXB_UN_F(floorf(a))
-        case M_F_CEIL: AXB_UN_F(ceilf(a))
-        case M_F_TRUNC: AXB_UN_F(truncf(a))
-        case M_F_ROUND: AXB_UN_F(rintf(a)) // hn::Round = nearest-even (hwy_kernels-inl.h:640-655)
-        case M_F_RECIP: AXB_UN_F(__fdiv_rn(1.0f, a))
-        case M_F_SQUARE: AXB_UN_F(__fmul_rn(a, a))
-        case M_F_CBRT: AXB_UN_F(hwym::Cbrt(a))
-        case M_F_RELU: AXB_UN_F(a > 0.0f ? a : 0.0f)
-        case M_F_LEAKY: {
-            const float slope = __uint_as_float((uint32_t)p.imm[ra]);
-            AXB_UN_F(a > 0.0f ? a : __fmul_rn(slope, a))
-        }
-        case M_F_SILU: AXB_UN_F(hwym::Silu(a))
-        case M_F_SIGMOID: AXB_UN_F(hwym::Sigmoid(a))
-        case M_F_TANH: AXB_UN_F(hwym::Tanh(a))
-        case M_F_GELU: AXB_UN_F(hwym::Gelu(a))
-        case M_F_ISNAN: AXB_UN_F2I(a != a)
-        case M_F_ISINF: AXB_UN_F2I(isinf(a))
-        case M_F_ISFINITE: AXB_UN_F2I(isfinite(a))
-        case M_F_LNOT: AXB_UN_F2I(!(a != 0.0f))
-        // libm-accurate variants (half dtypes; reference computes these in double then rounds)
-        case M_FA_SQRT: AXB_UN_F((float)sqrt((double)a))
-        case M_FA_EXP: AXB_UN_F(slow::f_exp(a))
-        case M_FA_LOG: AXB_UN_F(slow::f_log(a))
-        case M_FA_SIN: AXB_UN_F(slow::f_sin(a))
-        case M_FA_COS: AXB_UN_F(slow::f_cos(a))
-        case M_FA_TAN: AXB_UN_F(slow::f_tan(a))
-        case M_FA_ERF: AXB_UN_F(slow::f_erf(a))
-        case M_FA_CBRT: AXB_UN_F(slow::f_cbrt(a))
-        case M_FA_SILU: AXB_UN_F(slow::f_silu(a))
-        case M_FA_SIGMOID: AXB_UN_F(slow::f_sigmoid(a))
-        case M_FA_TANH: AXB_UN_F(slow::f_tanh(a))
-        case M_FA_GELU: AXB_UN_F(slow::f_gelu(a))
-        // ---- fp32 binary -------------------------------------------------------------------------
-        case M_F_ADD: AXB_BIN_F(__fadd_rn(a, b))
-        case M_F_SUB: AXB_BIN_F(__fsub_rn(a, b))
-        case M_F_MUL: AXB_BIN_F(__fmul_rn(a, b))
-        case M_F_DIV: AXB_BIN_F(__fdiv_rn(a, b))
-        case M_F_POW: AXB_BIN_F(hwym::Pow(a, b))
-        case M_F_MOD: AXB_BIN_F(slow::f_fmod(a, b))
-        case M_F_MAX: AXB_BIN_F((a < b) ? b : a) // std::max (cpu_operations.hpp:337-341)
-        case M_F_MIN: AXB_BIN_F((b < a) ? b : a) // std::min
-        case M_F_ATAN2: AXB_BIN_F(slow::f_atan2(a, b))
-        case M_F_HYPOT: AXB_BIN_F(hwym::Hypot(a, b))
-        case M_FA_POW: AXB_BIN_F(slow::f_pow(a, b))
-        case M_FA_HYPOT: AXB_BIN_F(slow::f_hypot(a, b))
-        case M_F_EQ: AXB_CMP_F(a == b)
-        case M_F_NE: AXB_CMP_F(a != b)
-        case M_F_LT: AXB_CMP_F(a < b)
-        case M_F_LE: AXB_CMP_F(a <= b)
-        case M_F_GT: AXB_CMP_F(a > b)
-        case M_F_GE: AXB_CMP_F(a >= b)
-        case M_F_LAND: AXB_CMP_F((a != 0.0f) && (b != 0.0f))
-        case M_F_LOR: AXB_CMP_F((a != 0.0f) || (b != 0.0f))
-        case M_F_LXOR: AXB_CMP_F((a != 0.0f) != (b != 0.0f))
-        // ---- int32 ---------------------------------------------------------------------------------
-        case M_I_NEG: AXB_UN_I(0u - ua)
-        case M_I_ABS: AXB_UN_I(a < 0 ? (int32_t)(0u - ua) : a)
-        case M_I_SIGN: AXB_UN_I(a > 0 ? 1 : (a < 0 ? -1 : 0))
-        case M_I_SQUARE: AXB_UN_I(ua * ua)
-        case M_I_RELU: AXB_UN_I(a > 0 ? a : 0)
-        case M_I_RECIP: AXB_UN_I(a != 0 ? i_div(1, a) : 0)
-        case M_U_RECIP: AXB_UN_I(ua != 0u ? 1u / ua : 0u)
-        case M_I_LNOT: AXB_UN_I(ua == 0u ? 1 : 0)
-        case M_I_ADD: AXB_BIN_I(ua + ub)
-        case M_I_SUB: AXB_BIN_I(ua - ub)
-        case M_I_MUL: AXB_BIN_I(ua * ub)
-        case M_I_DIV: AXB_BIN_I(i_div(a, b))
-        case M_U_DIV: AXB_BIN_I(ub == 0u ? 0u : ua / ub)
-        case M_I_MOD: AXB_BIN_I(i_mod(a, b))
-        case M_U_MOD: AXB_BIN_I(ub == 0u ? 0u : ua % ub)
-        case M_I_MAX: AXB_BIN_I(a < b ? b : a)
-        case M_U_MAX: AXB_BIN_I(ua < ub ? ub : ua)
-        case M_I_MIN: AXB_BIN_I(b < a ? b : a)
-        case M_U_MIN: AXB_BIN_I(ub < ua ? ub : ua)
-        case M_I_AND: AXB_BIN_I(ua & ub)
-        case M_I_OR: AXB_BIN_I(ua | ub)
-        case M_I_XOR: AXB_BIN_I(ua ^ ub)
-        case M_I_SHL: AXB_BIN_I(ua << (ub & 31u))
-        case M_I_SHR: AXB_BIN_I(a >> (ub & 31u))
-        case M_U_SHR: AXB_BIN_I(ua >> (ub & 31u))
-        // ---- fp64 ----------------------------------------------------------------------------------
-        case M_D_NEG: AXB_UN_D(-a)
-        case M_D_ABS: AXB_UN_D(fabs(a))
-        case M_D_SQRT: AXB_UN_D(sqrt(a))
-        case M_D_EXP: AXB_UN_D(slow::d_exp(a))
-        case M_D_LOG: AXB_UN_D(slow::d_log(a))
-        case M_D_SIN: AXB_UN_D(slow::d_sin(a))
-        case M_D_COS: AXB_UN_D(slow::d_cos(a))
-        case M_D_TAN: AXB_UN_D(slow::d_tan(a))
-        case M_D_TANH: AXB_UN_D(slow::d_tanh(a))
-        case M_D_ERF: AXB_UN_D(slow::d_erf(a))
-        case M_D_SIGN: AXB_UN_D(a > 0.0 ? 1.0 : (a < 0.0 ? -1.0 : 0.0))
-        case M_D_FLOOR: AXB_UN_D(floor(a))
-        case M_D_CEIL: AXB_UN_D(ceil(a))
-        case M_D_TRUNC: AXB_UN_D(trunc(a))
-        case M_D_ROUND: AXB_UN_D(rint(a))
-        case M_D_RECIP: AXB_UN_D(1.0 / a)
-        case M_D_SQUARE: AXB_UN_D(a * a)
-        case M_D_RELU: AXB_UN_D(a > 0.0 ? a : 0.0)
-        case M_D_SIGMOID: AXB_UN_D(slow::d_sigmoid(a))
-        case M_D_ISNAN: AXB_UN_D2I(a != a)
-        case M_D_ISINF: AXB_UN_D2I(isinf(a))
-        case M_D_ISFINITE: AXB_UN_D2I(isfinite(a))
-        case M_D_LNOT: AXB_UN_D2I(!(a != 0.0))
-        case M_D_ADD: AXB_BIN_D(__dadd_rn(a, b))
-        case M_D_SUB: AXB_BIN_D(__dsub_rn(a, b))
-        case M_D_MUL: AXB_BIN_D(__dmul_rn(a, b))
-        case M_D_DIV: AXB_BIN_D(__ddiv_rn(a, b))
-        case M_D_POW: AXB_BIN_D(slow::d_pow(a, b))
-        case M_D_MOD: AXB_BIN_D(slow::d_fmod(a, b))
-        case M_D_MAX: AXB_BIN_D((a < b) ? b : a)
-        case M_D_MIN: AXB_BIN_D((b < a) ? b : a)
-        case M_D_HYPOT: AXB_BIN_D(slow::d_hypot(a, b))
-        case M_D_ATAN2: AXB_BIN_D(slow::d_atan2(a, b))
-        // ---- int64 ---------------------------------------------------------------------------------
-        case M_L_NEG: AXB_UN_L(0ull - (uint64_t)a)
-        case M_L_ABS: AXB_UN_L(a < 0 ? (int64_t)(0ull - (uint64_t)a) : a)
-        case M_L_SIGN: AXB_UN_L(a > 0 ? 1 : (a < 0 ? -1 : 0))
-        case M_L_SQUARE: AXB_UN_L((uint64_t)a * (uint64_t)a)
-        case M_L_RELU: AXB_UN_L(a > 0 ? a : 0)
-        case M_L_LNOT: AXB_UN_L(a == 0 ? 1 : 0)
-        case M_L_ADD: AXB_BIN_L(ua + ub)
-        case M_L_SUB: AXB_BIN_L(ua - ub)
-        case M_L_MUL: AXB_BIN_L(ua * ub)
-        case M_L_DIV: AXB_BIN_L(l_div(a, b))
-        case M_UL_DIV: AXB_BIN_L(ub == 0 ? 0ull : ua / ub)
-        case M_L_MOD: AXB_BIN_L(l_mod(a, b))
-        case M_UL_MOD: AXB_BIN_L(ub == 0 ? 0ull : ua % ub)
-        case M_L_MAX: AXB_BIN_L(a < b ? b : a)
-        case M_UL_MAX: AXB_BIN_L(ua < ub ? ub : ua)
-        case M_L_MIN: AXB_BIN_L(b < a ? b : a)
-        case M_UL_MIN: AXB_BIN_L(ub < ua ? ub : ua)
-        case M_L_AND: AXB_BIN_L(ua & ub)
-        case M_L_OR: AXB_BIN_L(ua | ub)
-        case M_L_XOR: AXB_BIN_L(ua ^ ub)
-        case M_L_SHL: AXB_BIN_L(ua << (ub & 63u))
-        case M_L_SHR: AXB_BIN_L(a >> (ub & 63u))
-        case M_UL_SHR: AXB_BIN_L(ua >> (ub & 63u))
-        default: break;
-        }
-        // post-op rounding of acc to the instruction's half dtype
-        const uint32_t rnd = fl & 3u;
-        if (rnd == RND_BF16) {
-#pragma unroll
-            for (int i = 0; i < VEC; ++i)
-                acc[i] = fromF<W>(round_bf16(asF<W>(acc[i])));
-        } else if (rnd == RND_F16) {
-#pragma unroll
-            for (int i = 0; i < VEC; ++i)
-                acc[i] = fromF<W>(round_f16(asF<W>(acc[i])));
-        }
-    }
+    for (int d = 0; d < NOUT; ++d)
+        off += (int64_t)c[d] * o.stride[d];
+    return off;
 }
-
-template <int VEC, typename W>
-__global__ void __launch_bounds__(256, 3) elementwise_kernel(const __grid_constant__ Params p) {
-    const uint32_t stride = gridDim.x * blockDim.x;
-    for (uint32_t vi = blockIdx.x * blockDim.x + threadIdx.x; vi < p.total_vec; vi += stride) {
-        uint32_t row = fastdiv(vi, p.div_m[0], p.div_s[0]);
-        uint32_t col = (vi - row * p.nvec_inner) * VEC;
-        int valid = (int)min((uint32_t)VEC, p.inner_len - col);
-        uint32_t c[kMaxOuter];
-        uint32_t rem = row;
-#pragma unroll
-        for (int d = 0; d < kMaxOuter; ++d) {
-            c[d] = 0;
-            if (d < (int)p.n_outer) {
-                uint32_t q = fastdiv(rem, p.div_m[1 + d], p.div_s[1 + d]);
-                c[d] = rem - q * p.outer_shape[d];
-                rem = q;
-            }
-        }
-        W acc[VEC];
-        run_program<VEC, W>(p, nullptr, c, col, valid, acc, true);
+#define EW_LOAD(K, DT, MODE, DST) load_vec<VEC, W, DT, MODE>(p.in[K], EW_OUTER_OFF(p.in[K]), col, valid, DST);
+#define EW_STORE(DT, MODE) store_vec<VEC, W, DT, MODE>(p.out, EW_OUTER_OFF(p.out), col, valid, acc);
+#define EW_IMM(K, DST)                                                                                  \
+    {                                                                                                   \
+        const W v_ = (W)p.imm[K];                                                                       \
+        _Pragma("unroll") for (int i = 0; i < VEC; ++i) DST[i] = v_;                                    \
     }
-}
+#define EW_MOV(SRC, DST)                                                                                \
+    {                                                                                                   \
+        _Pragma("unroll") for (int i = 0; i < VEC; ++i) DST[i] = SRC[i];                                \
+    }
+#define EW_SEL                                                                                          \
+    {                                                                                                   \
+        _Pragma("unroll") for (int i = 0; i < VEC; ++i) acc[i] = (acc[i] != 0) ? t[i] : u[i];           \
+    }
+#define EW_LEAKY(K)                                                                                     \
+    {                                                                                                   \
+        const float slope = __uint_as_float((uint32_t)p.imm[K]);                                        \
+        AXB_UN_F(a > 0.0f ? a : __fmul_rn(slope, a))                                                    \
+    }
+#define EW_RND_BF16                                                                                     \
+    {                                                                                                   \
+        _Pragma("unroll") for (int i = 0; i < VEC; ++i) acc[i] = fromF<W>(round_bf16(asF<W>(acc[i])));  \
+    }
+#define EW_RND_F16                                                                                      \
+    {                                                                                                   \
+        _Pragma("unroll") for (int i = 0; i < VEC; ++i) acc[i] = fromF<W>(round_f16(asF<W>(acc[i])));   \
+    }
+// binary statements take the operand order as a literal: EW_OP(SWAP, stmt)
+#define EW_OP(SWAP, STMT)                                                                               \
+    {                                                                                                   \
+        constexpr bool swap = SWAP;                                                                     \
+        (void)swap;                                                                                     \
+        STMT                                                                                            \
+    }
+// conversions act on register RA (R_T / R_ACC / R_U)
+#define EW_CVT_ON(RA, STMT)                                                                             \
+    {                                                                                                   \
+        constexpr int ra = RA;                                                                          \
+        STMT                                                                                            \
+    }
+
+// Grid-stride loop over the collapsed iteration space: one VEC-wide vector of one innermost run per iteration.
+#define EW_KERNEL_BEGIN(NAME, VEC_, WTYPE, NOUT_)                                                       \
+    extern "C" __global__ void __launch_bounds__(256) NAME(const __grid_constant__ axb::ew::Params p) { \
+        using namespace axb::ew;                                                                        \
+        constexpr int VEC = VEC_;                                                                       \
+        constexpr int NOUT = NOUT_;                                                                     \
+        typedef WTYPE W;                                                                                \
+        const uint32_t stride_ = gridDim.x * blockDim.x;                                                \
+        for (uint32_t vi = blockIdx.x * blockDim.x + threadIdx.x; vi < p.total_vec; vi += stride_) {    \
+            uint32_t row = (NOUT > 0) ? fastdiv(vi, p.div_m[0], p.div_s[0]) : 0u;                       \
+            const uint32_t col = (vi - row * p.nvec_inner) * VEC;                                       \
+            const int valid = (int)min((uint32_t)VEC, p.inner_len - col);                               \
+            uint32_t c[kMaxOuter];                                                                      \
+            _Pragma("unroll") for (int d = 0; d < kMaxOuter; ++d) {                                     \
+                c[d] = 0;                                                                               \
+                if (d < NOUT) {                                                                         \
+                    if (d == NOUT - 1) {                                                                \
+                        c[d] = row;                                                                     \
+                    } else {                                                                            \
+                        uint32_t q = fastdiv(row, p.div_m[1 + d], p.div_s[1 + d]);                      \
+                        c[d] = row - q * p.outer_shape[d];                                              \
+                        row = q;                                                                        \
+                    }                                                                                   \
+                }                                                                                       \
+            }                                                                                           \
+            W acc[VEC], t[VEC], u[VEC], s0[VEC], s1[VEC], s2[VEC], s3[VEC];                             \
+            _Pragma("unroll") for (int i = 0; i < VEC; ++i) {                                           \
+                acc[i] = t[i] = u[i] = s0[i] = s1[i] = s2[i] = s3[i] = 0;                               \
+            }
+#define EW_KERNEL_END                                                                                   \
+        }                                                                                               \
+    }
 
 } // namespace ew
 } // namespace axb

@@ -1,0 +1,35 @@
+// gemm.h — normalised GEMM problem shared by the SIMT kernel (matmul.cu) and the tcgen05 kernel (gemm_tcgen05.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "axb_internal.h"
+
+namespace axb {
+namespace gemm {
+
+constexpr int kMaxBatchDims = 6;
+
+// C[b] = act(op(A)[b] . op(B)[b] + bias).  All strides are in BYTES; transposes are already folded into them.
+struct Desc {
+    const char *a, *b;
+    char *c;
+    const char *bias;
+    int64_t M, N, K, batch;
+    int64_t a_rs, a_cs; // A[m][k]
+    int64_t b_rs, b_cs; // B[k][n]
+    int64_t c_rs, c_cs; // C[m][n]
+    int64_t bias_rs, bias_cs;
+    int32_t nb;         // batch dims, index 0 = innermost
+    int32_t act;        // 0 or a unary axb_op
+    int32_t bias_dtype;
+    int32_t pad;
+    int64_t bshape[kMaxBatchDims];
+    int64_t a_bs[kMaxBatchDims], b_bs[kMaxBatchDims], c_bs[kMaxBatchDims], bias_bs[kMaxBatchDims];
+};
+
+// Runs the tensor-core path when the problem qualifies (sets *done), otherwise leaves it to the SIMT kernel.
+axb_status try_tcgen05(const Desc &d, int adt, int bdt, int cdt, DeviceCtx *ctx, cudaStream_t s, bool *done);
+
+} // namespace gemm
+} // namespace axb

@@ -104,4 +104,74 @@ axb_status axb_elementwise_host(const axb_instr *prog, int n_instr, const axb_te
     return copy_back_and_release(*host_out, o, ins, s, st);
 }
 
+axb_status axb_reduce_host(int32_t op, const axb_tensor *host_in, const int32_t *axes, int n_axes, int keep_dims,
+                           const axb_tensor *host_out) {
+    AXB_TRY(validate_tensor(host_in, "axb_reduce_host(in)"));
+    AXB_TRY(validate_tensor(host_out, "axb_reduce_host(out)"));
+    cudaStream_t s;
+    AXB_TRY(resolve_stream(nullptr, &s));
+    std::vector<Staged> ins(1);
+    axb_status st = stage_in(*host_in, s, &ins[0]);
+    Staged o;
+    if (st == AXB_OK)
+        st = alloc_out(*host_out, s, &o);
+    if (st == AXB_OK)
+        st = axb_reduce(op, &ins[0].desc, axes, n_axes, keep_dims, &o.desc, s);
+    return copy_back_and_release(*host_out, o, ins, s, st);
+}
+
+axb_status axb_matmul_host(const axb_tensor *host_a, const axb_tensor *host_b, int transpose_a, int transpose_b,
+                           const axb_tensor *host_out) {
+    AXB_TRY(validate_tensor(host_a, "axb_matmul_host(a)"));
+    AXB_TRY(validate_tensor(host_b, "axb_matmul_host(b)"));
+    AXB_TRY(validate_tensor(host_out, "axb_matmul_host(out)"));
+    cudaStream_t s;
+    AXB_TRY(resolve_stream(nullptr, &s));
+    std::vector<Staged> ins(2);
+    axb_status st = stage_in(*host_a, s, &ins[0]);
+    if (st == AXB_OK)
+        st = stage_in(*host_b, s, &ins[1]);
+    Staged o;
+    if (st == AXB_OK)
+        st = alloc_out(*host_out, s, &o);
+    if (st == AXB_OK)
+        st = axb_matmul(&ins[0].desc, &ins[1].desc, transpose_a, transpose_b, nullptr, &o.desc, s);
+    return copy_back_and_release(*host_out, o, ins, s, st);
+}
+
+// FusedReductionStep (include/axiom/graph/compiled_graph.hpp:61-66): elementwise chain + FULL reduction.
+// Round 1: the chain's value is materialised once in a pooled scratch block and reduced by the row kernel (2 launches +
+// finish); folding the reduction into the chain kernel's epilogue is the next step for this entry point.
+axb_status axb_elementwise_reduce(const axb_instr *prog, int n_instr, const axb_tensor *inputs, int n_inputs,
+                                  int32_t reduce_op, const axb_tensor *out, axb_stream_t stream) {
+    AXB_REQUIRE(prog && n_instr > 0 && n_inputs > 0 && inputs, AXB_ERR_INVALID, "axb_elementwise_reduce: bad arguments");
+    AXB_TRY(validate_tensor(out, "axb_elementwise_reduce(out)"));
+    int64_t shape[AXB_MAX_DIMS];
+    int nd = 0;
+    {
+        int64_t cur[AXB_MAX_DIMS];
+        int ncur = inputs[0].ndim;
+        memcpy(cur, inputs[0].shape, sizeof(int64_t) * ncur);
+        for (int k = 1; k < n_inputs; ++k) {
+            AXB_TRY(axb_broadcast_shape(cur, ncur, inputs[k].shape, inputs[k].ndim, shape, &nd));
+            memcpy(cur, shape, sizeof(int64_t) * nd);
+            ncur = nd;
+        }
+        memcpy(shape, cur, sizeof(int64_t) * ncur);
+        nd = ncur;
+    }
+    cudaStream_t s;
+    AXB_TRY(resolve_stream(stream, &s));
+    const int32_t vdt = prog[n_instr - 1].dtype;
+    axb_tensor tmp = make_contiguous_desc(nullptr, vdt, shape, nd);
+    void *buf = nullptr;
+    AXB_TRY(axb_alloc((size_t)numel(tmp) * dtype_size(vdt), s, &buf));
+    tmp.base = buf;
+    axb_status st = axb_elementwise(prog, n_instr, inputs, n_inputs, &tmp, s);
+    if (st == AXB_OK)
+        st = axb_reduce(reduce_op, &tmp, nullptr, 0, 0, out, s);
+    axb_free(buf, s);
+    return st;
+}
+
 } // extern "C"

@@ -13,8 +13,10 @@
 //   hn::NegMulAdd(a,b,c)=c-a*b -> __fmaf_rn(-a,b,c), hn::MulSub(a,b,c)=a*b-c -> __fmaf_rn(a,b,-c),
 //   hn::Div -> __fdiv_rn, hn::Sqrt -> __fsqrt_rn, ConvertTo<int32>(float) -> __float2int_rz (saturating).
 #pragma once
+#ifndef __CUDACC_RTC__
 #include <cuda_runtime.h>
 #include <stdint.h>
+#endif
 
 namespace hwym {
 

@@ -1,0 +1,420 @@
+// rownorm.cu — kernel family 2b: softmax / log_softmax / layer_norm / rms_norm along one axis.
+//
+// Replaces CPUSoftmaxOperation (src/backends/cpu/cpu_operations.cpp:3067-3241) and ops::layer_norm / rms_norm
+// (src/tensor/operations.cpp:1775-1858; the Metal backend's fused formula is mpsgraph_graph_compiler.mm:303-330 and its
+// hand-written layer_norm_fwd kernel src/backends/metal/kernels.metal:167-411).
+//
+// HBM-bound: each row is read ONCE, kept in REGISTERS (fp32, up to 32 values per thread), reduced with warp
+// shuffles (+ one shared-memory hop for multi-warp rows) and written once: algorithmic traffic = in + out
+// (SURVEY.md §8d C3). Three resident shapes cover rows up to 32 768 elements: one warp per row (<= 1024), 256 threads
+// per row (<= 8192), 1024 threads per row (<= 32 768: 128 KiB of fp32 = half the SM's register file). Longer rows
+// stream from global memory in three passes. Contiguous rows use 128-bit (fp32) / 64-bit (half) streaming accesses.
+//
+// Numerics mirror the reference op sequence, every step rounded to fp32 (no FMA contraction):
+//   softmax    m = max, e = exp(x - m), s = sum(e), y = e / s           (log: y = x - m - log(s))   [:3123-3162]
+//   layer_norm mean = sum(x)/n; xc = x - mean; var = sum(xc*xc)/n; y = xc / sqrt(var + eps) * w + b  [:1803-1817]
+//   rms_norm   ms = sum(x*x)/n; y = x / sqrt(ms + eps) * w                                           [:1841-1857]
+// Half inputs: the CPU path rounds mean (layer_norm) and x*x, ms (rms_norm) to the half type because those steps run
+// in the input dtype (bfloat16.hpp:55-66, cpu_operations.cpp:1613-1614); mirrored here. Sums are trees, not the
+// reference's serial / lane-strided order: results agree to rounding (tests use the north_star's 1e-5 bound).
+#include <cstring>
+
+#include "axb_internal.h"
+#include "reduce_common.cuh"
+
+namespace axb {
+namespace rown {
+
+using namespace axb::red;
+
+enum Kind { K_SOFTMAX = 0, K_LOG_SOFTMAX = 1, K_LAYER_NORM = 2, K_RMS_NORM = 3 };
+
+struct RowParams {
+    const char *in;
+    char *out;
+    const char *w, *b;     // may be null
+    int32_t nk;            // outer dims (all dims but the axis), index 0 = innermost
+    uint32_t kshape[kMaxDims];
+    int64_t in_kstride[kMaxDims], out_kstride[kMaxDims];
+    int64_t in_es, out_es; // byte stride along the axis
+    int64_t w_es, b_es;    // byte stride of weight / bias along the axis
+    int64_t rows;
+    int32_t n;             // row length
+    int32_t vec_ok;        // rows contiguous and suitably aligned -> vector accesses
+    int32_t in_dtype, out_dtype, w_dtype, b_dtype;
+    float eps;
+};
+
+__device__ __forceinline__ void row_offsets(const RowParams &p, int64_t row, int64_t *in_off, int64_t *out_off) {
+    int64_t a = 0, b = 0;
+#pragma unroll 1
+    for (int d = 0; d < p.nk; ++d) {
+        int64_t q = row / p.kshape[d];
+        int64_t c = row - q * p.kshape[d];
+        a += c * p.in_kstride[d];
+        b += c * p.out_kstride[d];
+        row = q;
+    }
+    *in_off = a;
+    *out_off = b;
+}
+
+template <typename T> __device__ __forceinline__ float ld_f(const char *p);
+template <> __device__ __forceinline__ float ld_f<float>(const char *p) { return *reinterpret_cast<const float *>(p); }
+template <> __device__ __forceinline__ float ld_f<bf16_t>(const char *p) { return bf2f(*reinterpret_cast<const uint16_t *>(p)); }
+template <> __device__ __forceinline__ float ld_f<f16_t>(const char *p) { return h2f(*reinterpret_cast<const uint16_t *>(p)); }
+template <typename T> __device__ __forceinline__ void st_f(char *p, float v);
+template <> __device__ __forceinline__ void st_f<float>(char *p, float v) { *reinterpret_cast<float *>(p) = v; }
+template <> __device__ __forceinline__ void st_f<bf16_t>(char *p, float v) { *reinterpret_cast<uint16_t *>(p) = f2bf(v); }
+template <> __device__ __forceinline__ void st_f<f16_t>(char *p, float v) { *reinterpret_cast<uint16_t *>(p) = f2h(v); }
+__device__ __forceinline__ float ld_dyn(const char *p, int dt) {
+    return dt == AXB_F32 ? ld_f<float>(p) : dt == AXB_BF16 ? ld_f<bf16_t>(p) : ld_f<f16_t>(p);
+}
+template <typename T> __device__ __forceinline__ float round_to(float v) { return v; }
+template <> __device__ __forceinline__ float round_to<bf16_t>(float v) { return bf2f(f2bf(v)); }
+template <> __device__ __forceinline__ float round_to<f16_t>(float v) { return h2f(f2h(v)); }
+
+// 4 consecutive elements
+template <typename T> __device__ __forceinline__ void ld4(const char *p, float (&v)[4]);
+template <> __device__ __forceinline__ void ld4<float>(const char *p, float (&v)[4]) {
+    uint4 q = ldg_stream(reinterpret_cast<const uint4 *>(p));
+    v[0] = __uint_as_float(q.x); v[1] = __uint_as_float(q.y); v[2] = __uint_as_float(q.z); v[3] = __uint_as_float(q.w);
+}
+__device__ __forceinline__ uint2 ldg64_stream(const void *p) {
+    uint2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+    return r;
+}
+template <> __device__ __forceinline__ void ld4<bf16_t>(const char *p, float (&v)[4]) {
+    uint2 q = ldg64_stream(p);
+    v[0] = __uint_as_float(q.x << 16); v[1] = __uint_as_float(q.x & 0xFFFF0000u);
+    v[2] = __uint_as_float(q.y << 16); v[3] = __uint_as_float(q.y & 0xFFFF0000u);
+}
+template <> __device__ __forceinline__ void ld4<f16_t>(const char *p, float (&v)[4]) {
+    uint2 q = ldg64_stream(p);
+    v[0] = h2f((uint16_t)(q.x & 0xFFFFu)); v[1] = h2f((uint16_t)(q.x >> 16));
+    v[2] = h2f((uint16_t)(q.y & 0xFFFFu)); v[3] = h2f((uint16_t)(q.y >> 16));
+}
+template <typename T> __device__ __forceinline__ void st4(char *p, const float (&v)[4]);
+template <> __device__ __forceinline__ void st4<float>(char *p, const float (&v)[4]) {
+    stg_stream(reinterpret_cast<uint4 *>(p), make_uint4(__float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]),
+                                                        __float_as_uint(v[3])));
+}
+__device__ __forceinline__ void stg64_stream(void *p, uint2 v) {
+    asm volatile("st.global.L1::no_allocate.v2.u32 [%0], {%1,%2};" ::"l"(p), "r"(v.x), "r"(v.y) : "memory");
+}
+template <> __device__ __forceinline__ void st4<bf16_t>(char *p, const float (&v)[4]) {
+    stg64_stream(p, make_uint2((uint32_t)f2bf(v[0]) | ((uint32_t)f2bf(v[1]) << 16),
+                               (uint32_t)f2bf(v[2]) | ((uint32_t)f2bf(v[3]) << 16)));
+}
+template <> __device__ __forceinline__ void st4<f16_t>(char *p, const float (&v)[4]) {
+    stg64_stream(p, make_uint2((uint32_t)f2h(v[0]) | ((uint32_t)f2h(v[1]) << 16),
+                               (uint32_t)f2h(v[2]) | ((uint32_t)f2h(v[3]) << 16)));
+}
+
+struct FMax {
+    __device__ static float apply(float a, float b) { return fmaxf(a, b); }
+};
+struct FAdd {
+    __device__ static float apply(float a, float b) { return a + b; }
+};
+// reduce over the THREADS threads that share a row; result broadcast to all of them
+template <int THREADS, class F> __device__ __forceinline__ float row_allreduce(float v, float *smem) {
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1)
+        v = F::apply(v, __shfl_xor_sync(0xFFFFFFFFu, v, d));
+    if (THREADS > 32) {
+        constexpr int NW = THREADS / 32;
+        const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+        __syncthreads(); // smem reuse between consecutive reductions
+        if (l == 0)
+            smem[w] = v;
+        __syncthreads();
+        float t = smem[l % NW];
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1)
+            if (d < NW)
+                t = F::apply(t, __shfl_xor_sync(0xFFFFFFFFu, t, d));
+        v = t;
+    }
+    return v;
+}
+
+// THREADS threads per row (32: one warp per row, 256/THREADS... rows per CTA), VPT resident values per thread.
+// RESIDENT = false: rows longer than THREADS*VPT re-read global memory in every pass.
+template <typename In, typename Out, int THREADS, int VPT, int KIND, bool RESIDENT>
+__global__ void __launch_bounds__(THREADS == 32 ? 256 : THREADS) rownorm_kernel(const __grid_constant__ RowParams p) {
+    constexpr int CTA = THREADS == 32 ? 256 : THREADS;
+    constexpr int ROWS = CTA / THREADS;
+    constexpr int NCH = VPT / 4; // 4-element chunks per thread
+    __shared__ float smem[32];
+    const int tid = threadIdx.x % THREADS;
+    const int n = p.n;
+    const float inv_n = 0.0f; (void)inv_n;
+    for (int64_t row0 = (int64_t)blockIdx.x * ROWS; row0 < p.rows; row0 += (int64_t)gridDim.x * ROWS) {
+        const int64_t row = row0 + threadIdx.x / THREADS;
+        const bool row_ok = row < p.rows; // only differs inside a CTA when THREADS == 32 (no __syncthreads there)
+        int64_t in_off = 0, out_off = 0;
+        if (row_ok)
+            row_offsets(p, row, &in_off, &out_off);
+        const char *src = p.in + in_off;
+        char *dst = p.out + out_off;
+        float x[RESIDENT ? VPT : 4];
+
+        // element access helpers -------------------------------------------------------------------
+        auto load_chunk = [&](int e0, float (&v)[4]) { // elements e0..e0+3 (e0 % 4 == 0)
+            if (p.vec_ok && e0 + 4 <= n) {
+                ld4<In>(src + (int64_t)e0 * sizeof(In), v);
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    v[k] = (e0 + k < n) ? ld_f<In>(src + (int64_t)(e0 + k) * p.in_es) : 0.0f;
+            }
+        };
+        auto store_chunk = [&](int e0, const float (&v)[4]) {
+            if (p.vec_ok && e0 + 4 <= n) {
+                st4<Out>(dst + (int64_t)e0 * sizeof(Out), v);
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (e0 + k < n)
+                        st_f<Out>(dst + (int64_t)(e0 + k) * p.out_es, v[k]);
+            }
+        };
+        // visits every element of the row owned by this thread: f(e, value&) — value is the resident register or a
+        // fresh load; WRITE stores f's updated value to `dst`
+        auto sweep = [&](auto f, bool reload, bool write) {
+            if (RESIDENT) {
+#pragma unroll
+                for (int j = 0; j < NCH; ++j) {
+                    const int e0 = (j * THREADS + tid) * 4;
+                    if (e0 < n && row_ok) {
+                        float v[4];
+                        if (reload) {
+                            load_chunk(e0, v);
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                x[(RESIDENT ? j * 4 : 0) + k] = v[k];
+                        }
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            v[k] = x[(RESIDENT ? j * 4 : 0) + k];
+                            if (e0 + k < n)
+                                f(e0 + k, v[k]);
+                            x[(RESIDENT ? j * 4 : 0) + k] = v[k];
+                        }
+                        if (write)
+                            store_chunk(e0, v);
+                    }
+                }
+            } else {
+                for (int e0 = tid * 4; e0 < n && row_ok; e0 += THREADS * 4) {
+                    float v[4];
+                    load_chunk(e0, v);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        if (e0 + k < n)
+                            f(e0 + k, v[k]);
+                    if (write)
+                        store_chunk(e0, v);
+                }
+            }
+        };
+
+        if (KIND == K_SOFTMAX || KIND == K_LOG_SOFTMAX) {
+            float m = -INFINITY;
+            sweep([&](int, float &v) { m = fmaxf(m, v); }, true, false);
+            m = row_allreduce<THREADS, FMax>(m, smem);
+            float s = 0.0f;
+            if (KIND == K_SOFTMAX) {
+                if (RESIDENT) { // e = exp(x - m) kept in registers, y = e / s
+                    sweep([&](int, float &v) { v = expf(__fsub_rn(v, m)); s += v; }, false, false);
+                    s = row_allreduce<THREADS, FAdd>(s, smem);
+                    sweep([&](int, float &v) { v = __fdiv_rn(v, s); }, false, true);
+                } else {
+                    sweep([&](int, float &v) { s += expf(__fsub_rn(v, m)); }, true, false);
+                    s = row_allreduce<THREADS, FAdd>(s, smem);
+                    sweep([&](int, float &v) { v = __fdiv_rn(expf(__fsub_rn(v, m)), s); }, true, true);
+                }
+            } else {
+                sweep([&](int, float &v) { s += expf(__fsub_rn(v, m)); }, !RESIDENT, false);
+                s = row_allreduce<THREADS, FAdd>(s, smem);
+                const float ls = logf(s);
+                sweep([&](int, float &v) { v = __fsub_rn(__fsub_rn(v, m), ls); }, !RESIDENT, true);
+            }
+        } else if (KIND == K_LAYER_NORM) {
+            float s = 0.0f;
+            sweep([&](int, float &v) { s += v; }, true, false);
+            s = row_allreduce<THREADS, FAdd>(s, smem);
+            const float mean = round_to<In>(__fdiv_rn(s, (float)n));
+            float q = 0.0f;
+            sweep([&](int, float &v) { v = __fsub_rn(v, mean); q += __fmul_rn(v, v); }, !RESIDENT, false);
+            q = row_allreduce<THREADS, FAdd>(q, smem);
+            const float sd = __fsqrt_rn(__fadd_rn(__fdiv_rn(q, (float)n), p.eps));
+            sweep([&](int e, float &v) {
+                float xc = RESIDENT ? v : __fsub_rn(v, mean);
+                float y = __fdiv_rn(xc, sd);
+                if (p.w)
+                    y = __fmul_rn(y, ld_dyn(p.w + (int64_t)e * p.w_es, p.w_dtype));
+                if (p.b)
+                    y = __fadd_rn(y, ld_dyn(p.b + (int64_t)e * p.b_es, p.b_dtype));
+                v = y;
+            }, !RESIDENT, true);
+        } else { // K_RMS_NORM
+            float q = 0.0f;
+            sweep([&](int, float &v) { q += round_to<In>(__fmul_rn(v, v)); }, true, false);
+            q = row_allreduce<THREADS, FAdd>(q, smem);
+            const float ms = round_to<In>(__fdiv_rn(q, (float)n));
+            const float rms = __fsqrt_rn(__fadd_rn(ms, p.eps));
+            sweep([&](int e, float &v) {
+                float y = __fdiv_rn(v, rms);
+                if (p.w)
+                    y = __fmul_rn(y, ld_dyn(p.w + (int64_t)e * p.w_es, p.w_dtype));
+                v = y;
+            }, !RESIDENT, true);
+        }
+    }
+}
+
+namespace {
+
+template <typename In, typename Out, int KIND> axb_status launch_cfg(const RowParams &p, DeviceCtx *ctx, cudaStream_t s) {
+    const int n = p.n;
+    const int64_t max_ctas = (int64_t)ctx->sm_count * 32;
+    if (n <= 256) {
+        int64_t g = std::min<int64_t>((p.rows + 7) / 8, max_ctas);
+        rownorm_kernel<In, Out, 32, 8, KIND, true><<<(unsigned)g, 256, 0, s>>>(p);
+    } else if (n <= 1024) {
+        int64_t g = std::min<int64_t>((p.rows + 7) / 8, max_ctas);
+        rownorm_kernel<In, Out, 32, 32, KIND, true><<<(unsigned)g, 256, 0, s>>>(p);
+    } else if (n <= 8192) {
+        int64_t g = std::min<int64_t>(p.rows, max_ctas);
+        rownorm_kernel<In, Out, 256, 32, KIND, true><<<(unsigned)g, 256, 0, s>>>(p);
+    } else if (n <= 32768) {
+        int64_t g = std::min<int64_t>(p.rows, max_ctas);
+        rownorm_kernel<In, Out, 1024, 32, KIND, true><<<(unsigned)g, 1024, 0, s>>>(p);
+    } else {
+        int64_t g = std::min<int64_t>(p.rows, max_ctas);
+        rownorm_kernel<In, Out, 1024, 4, KIND, false><<<(unsigned)g, 1024, 0, s>>>(p);
+    }
+    AXB_CHECK_LAUNCH();
+    return AXB_OK;
+}
+
+template <int KIND> axb_status dispatch(const RowParams &p, DeviceCtx *ctx, cudaStream_t s) {
+    const int i = p.in_dtype, o = p.out_dtype;
+    if (i == AXB_F32 && o == AXB_F32)
+        return launch_cfg<float, float, KIND>(p, ctx, s);
+    if (i == AXB_BF16 && o == AXB_BF16)
+        return launch_cfg<bf16_t, bf16_t, KIND>(p, ctx, s);
+    if (i == AXB_F16 && o == AXB_F16)
+        return launch_cfg<f16_t, f16_t, KIND>(p, ctx, s);
+    if (KIND == K_LAYER_NORM || KIND == K_RMS_NORM) { // CPU path yields Float32 for half inputs
+        if (i == AXB_BF16 && o == AXB_F32)
+            return launch_cfg<bf16_t, float, (KIND == K_LAYER_NORM || KIND == K_RMS_NORM) ? KIND : K_LAYER_NORM>(p, ctx, s);
+        if (i == AXB_F16 && o == AXB_F32)
+            return launch_cfg<f16_t, float, (KIND == K_LAYER_NORM || KIND == K_RMS_NORM) ? KIND : K_LAYER_NORM>(p, ctx, s);
+    }
+    return fail(AXB_ERR_UNSUPPORTED, "row kernel: dtype combination in=%d out=%d has no GPU kernel (fp32/bf16/fp16 only)", i, o);
+}
+
+axb_status run(int kind, const axb_tensor *in, const axb_tensor *w, const axb_tensor *b, int axis, float eps,
+               const axb_tensor *out, axb_stream_t stream, const char *what) {
+    AXB_TRY(validate_tensor(in, what));
+    AXB_TRY(validate_tensor(out, what));
+    AXB_REQUIRE(in->ndim >= 1, AXB_ERR_SHAPE, "%s: rank-0 input", what);
+    AXB_REQUIRE(in->ndim == out->ndim, AXB_ERR_SHAPE, "%s: out rank differs", what);
+    for (int d = 0; d < in->ndim; ++d)
+        AXB_REQUIRE(in->shape[d] == out->shape[d], AXB_ERR_SHAPE, "%s: out shape differs in dim %d", what, d);
+    if (axis < 0)
+        axis += in->ndim; // softmax(-1) / layer_norm(-1) normalise (cpu_operations.cpp:3074-3078, operations.cpp:1797-1801)
+    AXB_REQUIRE(axis >= 0 && axis < in->ndim, AXB_ERR_INVALID, "%s: axis out of range", what);
+    if (numel(*in) == 0)
+        return AXB_OK;
+    AXB_REQUIRE(in->shape[axis] < (1ll << 31), AXB_ERR_UNSUPPORTED, "%s: row too long", what);
+    RowParams p;
+    memset(&p, 0, sizeof p);
+    p.in = tensor_ptr(*in);
+    p.out = tensor_ptr(*out);
+    p.n = (int)in->shape[axis];
+    p.in_es = in->strides[axis];
+    p.out_es = out->strides[axis];
+    p.in_dtype = in->dtype;
+    p.out_dtype = out->dtype;
+    p.eps = eps;
+    p.rows = 1;
+    for (int d = in->ndim - 1; d >= 0; --d) {
+        if (d == axis || in->shape[d] == 1)
+            continue;
+        p.kshape[p.nk] = (uint32_t)in->shape[d];
+        p.in_kstride[p.nk] = in->strides[d];
+        p.out_kstride[p.nk] = out->strides[d];
+        p.rows *= in->shape[d];
+        p.nk++;
+    }
+    const int64_t isz = (int64_t)dtype_size(in->dtype), osz = (int64_t)dtype_size(out->dtype);
+    bool vec = p.in_es == isz && p.out_es == osz && (reinterpret_cast<uintptr_t>(p.in) % (4 * isz)) == 0 &&
+               (reinterpret_cast<uintptr_t>(p.out) % (4 * osz)) == 0;
+    for (int d = 0; d < p.nk && vec; ++d)
+        vec = p.in_kstride[d] % (4 * isz) == 0 && p.out_kstride[d] % (4 * osz) == 0;
+    p.vec_ok = vec ? 1 : 0;
+    auto bind_vec = [&](const axb_tensor *t, const char **ptr, int64_t *es, int32_t *dt, const char *nm) -> axb_status {
+        if (!t)
+            return AXB_OK;
+        AXB_TRY(validate_tensor(t, nm));
+        AXB_REQUIRE(t->dtype == AXB_F32 || t->dtype == AXB_BF16 || t->dtype == AXB_F16, AXB_ERR_UNSUPPORTED,
+                    "%s: weight/bias dtype %d unsupported", what, t->dtype);
+        // weight/bias broadcast against the input: only the axis extent may be > 1
+        int64_t stride = 0;
+        for (int d = 0; d < t->ndim; ++d) {
+            int id = d + (in->ndim - t->ndim);
+            if (t->shape[d] == 1)
+                continue;
+            AXB_REQUIRE(id == axis && t->shape[d] == in->shape[axis], AXB_ERR_SHAPE,
+                        "%s: weight/bias must have shape {%lld} along the normalised axis", what, (long long)in->shape[axis]);
+            stride = t->strides[d];
+        }
+        *ptr = tensor_ptr(*t);
+        *es = stride;
+        *dt = t->dtype;
+        return AXB_OK;
+    };
+    AXB_TRY(bind_vec(w, &p.w, &p.w_es, &p.w_dtype, "weight"));
+    AXB_TRY(bind_vec(b, &p.b, &p.b_es, &p.b_dtype, "bias"));
+    cudaStream_t s;
+    DeviceCtx *ctx;
+    AXB_TRY(resolve_stream(stream, &s, &ctx));
+    switch (kind) {
+    case K_SOFTMAX: return dispatch<K_SOFTMAX>(p, ctx, s);
+    case K_LOG_SOFTMAX: return dispatch<K_LOG_SOFTMAX>(p, ctx, s);
+    case K_LAYER_NORM: return dispatch<K_LAYER_NORM>(p, ctx, s);
+    default: return dispatch<K_RMS_NORM>(p, ctx, s);
+    }
+}
+
+} // namespace
+} // namespace rown
+} // namespace axb
+
+using namespace axb;
+
+extern "C" {
+
+axb_status axb_softmax(const axb_tensor *in, int axis, int is_log, const axb_tensor *out, axb_stream_t stream) {
+    if (in && out)
+        AXB_REQUIRE(in->dtype == out->dtype, AXB_ERR_INVALID, "axb_softmax: out dtype must equal the input dtype");
+    return rown::run(is_log ? rown::K_LOG_SOFTMAX : rown::K_SOFTMAX, in, nullptr, nullptr, axis, 0.0f, out, stream,
+                     "axb_softmax");
+}
+
+axb_status axb_layer_norm(const axb_tensor *in, const axb_tensor *weight, const axb_tensor *bias, int axis, float eps,
+                          const axb_tensor *out, axb_stream_t stream) {
+    return rown::run(rown::K_LAYER_NORM, in, weight, bias, axis, eps, out, stream, "axb_layer_norm");
+}
+
+axb_status axb_rms_norm(const axb_tensor *in, const axb_tensor *weight, int axis, float eps, const axb_tensor *out,
+                        axb_stream_t stream) {
+    return rown::run(rown::K_RMS_NORM, in, weight, nullptr, axis, eps, out, stream, "axb_rms_norm");
+}
+
+} // extern "C"

@@ -211,7 +211,7 @@ def _reduced_shape(shape, axes, keep_dims):
                 out.append(1)
         else:
             out.append(e)
-    return tuple(out)
+    return tuple(out) if out else (1,)  # a full reduction is {1}, not rank-0 (graph_registry.cpp:101-111)
 
 
 def reduce(op: str, x: DeviceArray, axes: Sequence[int] = (), keep_dims: bool = False) -> DeviceArray:

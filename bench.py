@@ -1,0 +1,387 @@
+#!/usr/bin/env python
+"""bench.py — the measurement contract of this repo (see the task brief, section 4, and DESIGN.md "Measurement").
+
+One "step" = one pass of the hot path over one batch of synthetic input: the BASELINE config-2 fused chain
+    ((a.relu() + 1.0f) * b).where(c > 0, 0)   a{4096,1} b{1,16384} c{4096,16384} fp32   
+which is ONE launch of the specialised elementwise kernel. Algorithmic bytes per launch = c + out + a + b
+= 536 952 832 B. At N > 1 every rank runs the same shape on its own shard of rows (weak scaling, no
+data-path collective: the rows are independent); `value` = bytes all ranks processed / max-over-ranks device time.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]          our arm (CUDA path through the C ABI)
+  python bench.py --impl reference ...                         the reference's own CPU backend on the host cores
+
+Extra keys: `roofline` (dominant kernel vs MEASURED_PEAKS.json), `cpu_baseline` (oracle/_ref timed on the host cores),
+`e2e` (same metric through axb_elementwise_host: pinned HOST buffers, H2D + launch + D2H inside the timed region),
+`gpu_launches`, `clocks`, and `extras` (the other BASELINE configs: C3 reductions / softmax / layer_norm GB/s, C4 bf16
+batched matmul TFLOP/s, C1 README chain ms) measured with CUDA events outside the timed region of the headline.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+ROWS, COLS = 4096, 16384
+ALG_BYTES = ROWS * COLS * 4 * 2 + ROWS * 4 + COLS * 4  # 536 952 832
+WORKLOAD = "config2 fused chain ((a.relu()+1.0f)*b).where(c>0,0): a{4096,1} b{1,16384} c{4096,16384} fp32"
+
+
+def _peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), float(p.get("bf16_tflops", 1590.0)), float(p.get("bf16_tflops_sustained", 1400.0)), "measured"
+    except Exception:
+        return 6650.0, 1590.0, 1400.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi sampled DURING the timed region (B200_PROFILING.md clocks line)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                pass
+        sm, mx, reasons = [], 0.0, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx = max(mx, float(r[2]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                continue
+        busy = sorted(s for s in sm if s > 0)
+        top = busy[len(busy) // 2:] if busy else []  # samples under load = upper half
+        return {"sm_mhz": float(np.median(top)) if top else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    from oracle import ref
+    if not ref.available():
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libaxiom_ref.so was not built"}))
+        return
+    rng = np.random.default_rng(1)
+    a = rng.standard_normal((ROWS, 1), dtype=np.float32)
+    b = rng.standard_normal((1, COLS), dtype=np.float32)
+    c = rng.standard_normal((ROWS, COLS), dtype=np.float32)
+    ra, rb, rc = (ref.RefTensor.from_numpy(t) for t in (a, b, c))
+    cores = ref.num_threads()
+
+    def step():
+        t0 = time.perf_counter()
+        ref.config2_chain(ra, rb, rc).sync()
+        return time.perf_counter() - t0
+
+    for _ in range(args.warmup):
+        step()
+    ts = [step() for _ in range(args.steps)]
+    t = float(np.mean(ts))
+    val = ALG_BYTES / t / 1e9
+    out = {"impl": "reference", "metric": "fused_elementwise_chain_throughput", "value": val, "unit": "GB/s",
+           "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3,
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": WORKLOAD, "backend": "reference CPU backend (Highway SIMD + native BLAS + OpenMP)"},
+           "cpu_baseline": {"value": val, "unit": "GB/s", "cores": cores, "kind": "reference",
+                            "sample": f"full config-2 chain per step, {args.steps} steps"},
+           "e2e": {"value": val, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out))
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-extras", action="store_true", help="skip the C1/C3/C4 side measurements")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        return run_reference(args, rank)
+
+    from axiom_b200 import capi, device as dev  # fails loudly if libaxb.so is missing: no fallback
+    L = capi.lib()
+    capi.check(L.axb_set_device(local_rank))
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        dev.synchronize()
+        if dist is not None:
+            import torch
+            torch.cuda.synchronize()
+            dist.barrier()
+
+    def max_over_ranks(x: float) -> float:
+        if dist is None:
+            return x
+        import torch
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- inputs resident in HBM (generated on device: SURVEY.md §8d) ---------------------------------------------
+    F, B, V = capi.F32, capi.BOOL, capi.SRC_VALUE
+    a = dev.randn((ROWS, 1), 1 + 100 * rank)
+    b = dev.randn((1, COLS), 2)
+    c = dev.randn((ROWS, COLS), 3 + 100 * rank)
+    one = dev.DeviceArray.from_numpy(np.array([1.0], np.float32))
+    zi = dev.DeviceArray.from_numpy(np.array([0], np.int32))
+    zf = dev.DeviceArray.from_numpy(np.array([0.0], np.float32))
+    out = dev.DeviceArray.empty((ROWS, COLS), F)
+    prog = [capi.make_instr(capi.OP["relu"], F, 0), capi.make_instr(capi.OP["add"], F, V(0), 1),
+            capi.make_instr(capi.OP["mul"], F, V(1), 2), capi.make_instr(capi.OP["gt"], B, 3, 4),
+            capi.make_instr(capi.OP["where"], F, V(3), V(2), 5)]
+    P = (capi.AxbInstr * len(prog))(*prog)
+    ins = [a, one, b, c, zi, zf]
+    I = (capi.AxbTensor * len(ins))(*[t.desc() for t in ins])
+    od = out.desc()
+
+    def step():
+        capi.check(L.axb_elementwise(P, len(prog), I, len(ins), ctypes.byref(od), None))
+
+    e0, e1 = ctypes.c_void_p(), ctypes.c_void_p()
+    capi.check(L.axb_event_create(ctypes.byref(e0)))
+    capi.check(L.axb_event_create(ctypes.byref(e1)))
+
+    def timed(fn, k):
+        """k back-to-back calls between two events on the backend stream -> ms per call."""
+        capi.check(L.axb_event_record(e0, None))
+        for _ in range(k):
+            fn()
+        capi.check(L.axb_event_record(e1, None))
+        capi.check(L.axb_event_sync(e1))
+        ms = ctypes.c_float()
+        capi.check(L.axb_event_elapsed_ms(e0, e1, ctypes.byref(ms)))
+        return ms.value / k
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank).start() if rank == 0 else None
+    n0 = dev.launch_count()
+    ms = timed(step, args.steps)
+    launches = dev.launch_count() - n0
+    barrier()
+    ms_max = max_over_ranks(ms)
+    value = world * ALG_BYTES / (ms_max * 1e-3) / 1e9
+
+    # ---- e2e: the same chain through the host-buffer entry point (H2D + launch + D2H every step) ------------------
+    def pinned(shape, dtype):
+        n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        p = ctypes.c_void_p()
+        capi.check(L.axb_host_alloc(n, ctypes.byref(p)))
+        buf = (ctypes.c_char * n).from_address(p.value)
+        return np.frombuffer(buf, dtype=dtype).reshape(shape), p
+
+    rng = np.random.default_rng(7 + rank)
+    ha, pa = pinned((ROWS, 1), np.float32)
+    hb, pb = pinned((1, COLS), np.float32)
+    hc, pc = pinned((ROWS, COLS), np.float32)
+    ho, po = pinned((ROWS, COLS), np.float32)
+    ha[...] = rng.standard_normal(ha.shape, dtype=np.float32)
+    hb[...] = rng.standard_normal(hb.shape, dtype=np.float32)
+    hc[...] = c.numpy()
+    h1, hzi, hzf = np.array([1.0], np.float32), np.array([0], np.int32), np.array([0.0], np.float32)
+    hins = [ha, h1, hb, hc, hzi, hzf]
+    HI = (capi.AxbTensor * len(hins))(*[capi.make_tensor(t.ctypes.data, dev._NP2AXB[t.dtype], t.shape) for t in hins])
+    HO = capi.make_tensor(ho.ctypes.data, F, ho.shape)
+
+    def e2e_step():
+        capi.check(L.axb_elementwise_host(P, len(prog), HI, len(hins), ctypes.byref(HO)))
+
+    for _ in range(3):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    e2e_s = (time.perf_counter() - t0) / args.steps
+    barrier()
+    e2e_s = max_over_ranks(e2e_s)
+    e2e_val = world * ALG_BYTES / e2e_s / 1e9
+    h2d = sum(int(t.nbytes) for t in hins)
+    d2h = int(ho.nbytes)
+    clocks = sampler.stop() if sampler else None
+    # sanity of the e2e result against the device-resident run of the same c
+    if rank == 0:
+        exp = np.where(hc > 0, (np.maximum(ha, 0) + np.float32(1)) * hb, np.float32(0))
+        assert np.array_equal(ho, exp), "e2e result differs from the closed form"
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    hbm_peak, tf_peak, tf_sust, peak_src = _peaks()
+    achieved = ALG_BYTES / (ms * 1e-3) / 1e9
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            traffic = json.load(f).get("axb_ew_config2_dram_bytes_per_launch")
+    except Exception:
+        pass
+    result = {
+        "metric": "fused_elementwise_chain_throughput", "value": value, "unit": "GB/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "per_gpu_rows": ROWS, "cols": COLS,
+                   "sharding": "rows of the broadcast result; every rank runs {4096,16384}; no collective",
+                   "l2": "512 MiB touched per step >> 126 MB L2 (inputs larger than L2, no flush needed)",
+                   "algorithmic_bytes_per_step_per_gpu": ALG_BYTES},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                     "traffic": traffic, "peak_source": peak_src + " (MEASURED_PEAKS.json hbm_gbs, copy kernel)",
+                     "kernel": "axb_ew (specialised fused chain)"},
+        "e2e": {"value": e2e_val, "unit": "GB/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": e2e_s * 1e3, "api": "axb_elementwise_host (pinned host buffers)"},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+    }
+
+    if world == 1:
+        result["cpu_baseline"] = cpu_baseline()
+        if not args.no_extras:
+            try:
+                result["extras"] = extras(L, capi, dev, timed, hbm_peak, tf_peak)
+            except Exception as ex:  # the headline must still print
+                result["extras"] = {"error": repr(ex)}
+    print(json.dumps(result))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def cpu_baseline():
+    """The reference's own CPU backend (oracle/_ref) on the host cores: the same chain, full size, a bounded number of
+    iterations (reference methodology: warm-up then wall-clock mean, benchmarks/compare/elementwise_axiom.cpp:32-61)."""
+    try:
+        from oracle import ref
+        if not ref.available():
+            return {"value": None, "unit": "GB/s", "cores": 0, "kind": "reference", "sample": "oracle/_ref not built"}
+        rng = np.random.default_rng(1)
+        a = rng.standard_normal((ROWS, 1), dtype=np.float32)
+        b = rng.standard_normal((1, COLS), dtype=np.float32)
+        c = rng.standard_normal((ROWS, COLS), dtype=np.float32)
+        ra, rb, rc = (ref.RefTensor.from_numpy(t) for t in (a, b, c))
+        ref.config2_chain(ra, rb, rc).sync()
+        ts = []
+        t_end = time.perf_counter() + 15.0
+        while len(ts) < 10 and (len(ts) < 3 or time.perf_counter() < t_end):
+            t0 = time.perf_counter()
+            ref.config2_chain(ra, rb, rc).sync()
+            ts.append(time.perf_counter() - t0)
+        t = float(np.mean(ts))
+        return {"value": ALG_BYTES / t / 1e9, "unit": "GB/s", "cores": ref.num_threads(), "kind": "reference",
+                "sample": f"full-size config-2 chain, 1 warm-up + {len(ts)} timed iterations, {t * 1e3:.1f} ms each"}
+    except Exception as ex:
+        return {"value": None, "unit": "GB/s", "cores": 0, "kind": "reference", "sample": "failed: " + repr(ex)}
+
+
+def extras(L, capi, dev, timed, hbm_peak, tf_peak):
+    """Side measurements for the other BASELINE configs (CUDA events, inputs resident, >= 3 warm-ups each)."""
+    ex = {}
+
+    def run(name, fn, nbytes=None, flops=None, k=10):
+        for _ in range(3):
+            fn()
+        ms = timed(fn, k)
+        r = {"ms": ms}
+        if nbytes:
+            r["GBps"] = nbytes / ms / 1e6
+            r["frac_hbm"] = r["GBps"] / hbm_peak
+        if flops:
+            r["TFLOPs"] = flops / ms / 1e9
+            r["frac_bf16_peak"] = r["TFLOPs"] / tf_peak
+        ex[name] = r
+
+    rows, n = 8192, 32768
+    for dt in ("f32", "bf16"):
+        x = dev.randn((rows, n), 7)
+        isz = 4
+        if dt == "bf16":
+            x = dev.cast(x, capi.BF16)
+            isz = 2
+        w, b = dev.randn((n,), 8, 1.0, 0.1), dev.randn((n,), 9, 0.0, 0.1)
+        osum = dev.DeviceArray.empty((rows,), x.dtype)
+        oarg = dev.DeviceArray.empty((rows,), capi.I64)
+        obig = dev.DeviceArray.empty((rows, n), x.dtype)
+        xd, wd, bd = x.desc(), w.desc(), b.desc()
+        ax = (ctypes.c_int32 * 1)(1)
+        by = ctypes.byref
+        run(f"c3_sum_{dt}", lambda: capi.check(L.axb_reduce(capi.OP["sum"], by(xd), ax, 1, 0, by(osum.desc()), None)),
+            rows * n * isz + rows * isz)
+        run(f"c3_max_{dt}", lambda: capi.check(L.axb_reduce(capi.OP["max"], by(xd), ax, 1, 0, by(osum.desc()), None)),
+            rows * n * isz + rows * isz)
+        run(f"c3_argmax_{dt}", lambda: capi.check(L.axb_argreduce(capi.OP["argmax"], by(xd), 1, 0, by(oarg.desc()), None)),
+            rows * n * isz + rows * 8)
+        run(f"c3_softmax_{dt}", lambda: capi.check(L.axb_softmax(by(xd), -1, 0, by(obig.desc()), None)), 2 * rows * n * isz)
+        run(f"c3_layer_norm_{dt}", lambda: capi.check(L.axb_layer_norm(by(xd), by(wd), by(bd), -1, 1e-5, by(obig.desc()), None)),
+            2 * rows * n * isz + 2 * n * 4)
+        del x, obig
+    # C4: bf16 batched matmul {64,4096,4096}^2 (one GPU's share at N=1 is the whole batch)
+    nb, m = 64, 4096
+    A = dev.cast(dev.randn((nb, m, m), 11), capi.BF16)
+    Bm = dev.cast(dev.randn((nb, m, m), 12, 0.0, 1.0 / 64.0), capi.BF16)
+    C = dev.DeviceArray.empty((nb, m, m), capi.BF16)
+    ad, bd, cd = A.desc(), Bm.desc(), C.desc()
+    run("c4_bmm_bf16_64x4096", lambda: capi.check(L.axb_matmul(ctypes.byref(ad), ctypes.byref(bd), 0, 0, None, ctypes.byref(cd), None)),
+        flops=2.0 * nb * m ** 3, k=3)
+    del A, Bm, C
+    # C1: README chain fp32 1024^2 (launch/latency bound; reported, not graded against peak)
+    x = dev.randn((1024, 1024), 1234)
+
+    def readme():
+        s = dev.matmul(x, x.T())
+        p = dev.softmax(s, -1)
+        dev.reduce("sum", p, [1])
+
+    run("c1_readme_chain_f32_1024", readme, k=10)
+    return ex
+
+
+if __name__ == "__main__":
+    main()

@@ -178,6 +178,18 @@ typedef struct axb_instr {
 axb_status axb_elementwise(const axb_instr *prog, int n_instr, const axb_tensor *inputs, int n_inputs,
                            const axb_tensor *out, axb_stream_t stream);
 
+/* Compile-only twin of axb_elementwise (needs no GPU): makes sure the kernel specialised for this program
+ * SIGNATURE (ops, dtypes, operand access modes — never shapes or immediates) is in the in-tree cubin cache
+ * axiom_b200/kernel_cache/. Tensor descriptors only need plausible alignment (base may be any non-null
+ * address). build() calls it for the BASELINE configs; unseen signatures are specialised by NVRTC on first
+ * use (the analogue of the reference's per-signature MPSGraph cache, mpsgraph_fused.mm:373-377). */
+axb_status axb_elementwise_precompile(const axb_instr *prog, int n_instr, const axb_tensor *inputs, int n_inputs,
+                                      const axb_tensor *out);
+typedef struct axb_jit_stats {
+    uint64_t mem_hits, disk_hits, compiles;
+} axb_jit_stats;
+axb_status axb_get_jit_stats(axb_jit_stats *out);
+
 /* Type rules as pure host functions, so the glue infers shapes/dtypes exactly like the reference:
  * promote_types (src/tensor/operations.cpp:346-397); binary result dtype incl. comparison->Bool
  * (cpu_operations.cpp:36-49); unary result dtype (cpu_operations.cpp:836-853). */

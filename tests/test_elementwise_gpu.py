@@ -107,7 +107,7 @@ def test_unary_f32_transcendental_matches_highway_restatement(gpu, op, n):
     if ref.available():
         r = ref.RefTensor.from_numpy(x).unary(REFNAME[op]).numpy()
         body = (n // 16) * 16  # the reference's last n%lanes elements use libm (hwy_kernels-inl.h tails)
-        tol = 1 if op == "cbrt" else 0
+        tol = 2 if op == "cbrt" else 0  # north_star: <=2 ulp for fp32 elementwise
         assert int(ulp_diff(got[:body], r[:body]).max()) <= tol, f"{op}: differs from the reference body"
         # fp32 elementwise bar from north_star: <= 2 ulp. erf/gelu/tanh tails differ more because the reference
         # itself switches from its Abramowitz-Stegun polynomial to libm there (documented in DESIGN.md).

@@ -1,0 +1,162 @@
+"""GPU parity for kernel family 3 (matmul / batched matmul) through the C ABI.
+
+Mirrors the reference's tests/test_tensor_matmul.cpp (:4-161: 2D/1D/batched/broadcast/transpose flags, closed-form
+integer-valued answers) and tests/test_cpu_gpu_parity.cpp (:376-400), extended with odd sizes, strided / transposed
+views, mixed dtypes, the fused bias + activation epilogue (nn::Linear, MatMulActivationStep), the README chain at
+1024^2 and bf16/fp16 tensor-core shapes.
+
+Bars (north_star): fp32 matmul <= 1e-4 relative of the fp64 product magnitude (the reference's own parity test uses
+allclose 1e-4); bf16 matmul <= 1e-2 relative against an fp32 reference (governing spec: bf16 parity is UNPINNED by
+the reference's tests; the CPU bf16 path accumulates in bf16 and is not the target).
+"""
+import numpy as np
+import pytest
+
+from axiom_b200 import capi, device as dev
+from oracle import axiom_oracle as ao
+from oracle import ref
+from tests.helpers import as_bf16, rand_f32
+
+pytestmark = pytest.mark.gpu
+
+
+def _mm(a, b, **kw):
+    return dev.matmul(dev.DeviceArray.from_numpy(a), dev.DeviceArray.from_numpy(b), **kw).numpy()
+
+
+def _close_f32(got, a, b, rtol=1e-4):
+    exp = np.matmul(a.astype(np.float64), b.astype(np.float64))
+    mag = np.matmul(np.abs(a.astype(np.float64)), np.abs(b.astype(np.float64)))
+    assert got.shape == exp.shape, (got.shape, exp.shape)
+    assert np.all(np.abs(got - exp) <= rtol * mag + 1e-30), float(np.max(np.abs(got - exp) / (mag + 1e-30)))
+
+
+def test_known_answers(gpu):
+    a = np.arange(6, dtype=np.float32).reshape(2, 3)
+    b = np.arange(12, dtype=np.float32).reshape(3, 4)
+    assert _mm(a, b).tolist() == [[20, 23, 26, 29], [56, 68, 80, 92]]
+    v = np.arange(4, dtype=np.float32)
+    r = _mm(v, v)
+    assert r.shape == () and float(r) == 14.0                                   # 1D x 1D -> rank-0
+    assert _mm(np.arange(3, dtype=np.float32), b).tolist() == [20, 23, 26, 29]  # 1D x 2D
+    assert _mm(a, np.arange(3, dtype=np.float32)).tolist() == [5, 14]           # 2D x 1D
+    A = np.arange(24, dtype=np.float32).reshape(2, 3, 4)
+    B = np.arange(40, dtype=np.float32).reshape(2, 4, 5)
+    assert np.array_equal(_mm(A, B), np.matmul(A, B))
+    A = np.arange(24, dtype=np.float32).reshape(2, 1, 3, 4)
+    B = np.arange(20, dtype=np.float32).reshape(4, 5)
+    assert np.array_equal(_mm(A, B), np.matmul(A, B))                          # broadcast batch
+
+
+def test_transpose_flags_and_views(gpu):
+    rng = np.random.default_rng(1)
+    a, b = rand_f32(rng, (37, 53)), rand_f32(rng, (53, 29))
+    _close_f32(_mm(a, b), a, b)
+    _close_f32(_mm(np.ascontiguousarray(a.T), b, transpose_a=True), a, b)
+    _close_f32(_mm(a, np.ascontiguousarray(b.T), transpose_b=True), a, b)
+    _close_f32(_mm(a.T.copy().T, b.T.copy().T), a, b)                 # zero-copy transposed views (x.T())
+    big = rand_f32(rng, (80, 120))
+    av, bv = big[3:40, 5:111:2], big[10:63, 1:88:3]                    # offset + strided views
+    _close_f32(_mm(av, bv), av, bv)
+    x = rand_f32(rng, (64, 64))
+    _close_f32(_mm(x, x.T), x, x.T)                                    # README pattern: operand aliases its transpose
+    with pytest.raises(capi.AxbError):
+        _mm(a, a)                                                      # inner dims differ -> ShapeError
+
+
+@pytest.mark.parametrize("shape", [(1, 1, 1), (5, 1, 7), (64, 64, 64), (65, 63, 17), (128, 256, 96), (300, 200, 100)])
+def test_f32_shapes_vs_reference(gpu, shape):
+    m, k, n = shape
+    rng = np.random.default_rng(m * 1000 + n)
+    a, b = rand_f32(rng, (m, k)), rand_f32(rng, (k, n))
+    got = _mm(a, b)
+    _close_f32(got, a, b)
+    if ref.available():
+        r = ref.RefTensor.from_numpy(a).matmul(ref.RefTensor.from_numpy(b)).numpy()
+        assert np.allclose(got, r, rtol=1e-4, atol=1e-4)                # the reference's own parity tolerance
+
+
+def test_batched_broadcast_random(gpu):
+    rng = np.random.default_rng(4)
+    a, b = rand_f32(rng, (3, 1, 17, 33)), rand_f32(rng, (1, 4, 33, 9))
+    got = _mm(a, b)
+    assert got.shape == (3, 4, 17, 9)
+    _close_f32(got, a, b)
+    f64a, f64b = a.astype(np.float64), b.astype(np.float64)
+    assert np.allclose(_mm(f64a, f64b), np.matmul(f64a, f64b), rtol=1e-12)
+
+
+def test_readme_chain_1024(gpu):
+    """BASELINE config 1: x.matmul(x.T()).softmax(-1).sum({1}) on fp32 {1024,1024}; every row sums to 1."""
+    x = dev.randn((1024, 1024), 1234)
+    s = dev.matmul(x, x.T())
+    p = dev.softmax(s, -1)
+    r = dev.reduce("sum", p, [1]).numpy()
+    assert r.shape == (1024,) and np.allclose(r, 1.0, atol=1e-4)
+    hx = x.numpy()
+    _close_f32(s.numpy(), hx, hx.T)
+    if ref.available():
+        rr = ref.readme_chain(ref.RefTensor.from_numpy(hx)).numpy()
+        assert np.allclose(r, rr, atol=1e-4)
+
+
+@pytest.mark.parametrize("act", [None, "relu", "gelu", "silu", "sigmoid", "tanh"])
+def test_linear_epilogue_bias_activation(gpu, act):
+    rng = np.random.default_rng(6)
+    x, w, bias = rand_f32(rng, (50, 96), 0.5), rand_f32(rng, (72, 96), 0.5), rand_f32(rng, (72,), 0.5)
+    got = dev.matmul(dev.DeviceArray.from_numpy(x), dev.DeviceArray.from_numpy(w), transpose_b=True,
+                     bias=dev.DeviceArray.from_numpy(bias), activation=act).numpy()
+    y = (np.matmul(x.astype(np.float64), w.T.astype(np.float64))).astype(np.float32) + bias
+    if act:
+        y, _ = ao.unary(act, np.ascontiguousarray(y), ao.F32)
+    assert np.allclose(got, y, rtol=1e-4, atol=1e-4), act
+
+
+@pytest.mark.parametrize("dt", ["bf16", "f16"])
+@pytest.mark.parametrize("shape", [(128, 128, 128), (256, 512, 384), (200, 264, 136), (130, 72, 40), (1, 64, 64),
+                                   (1500, 384, 1536)])
+def test_half_matmul_vs_fp32_reference(gpu, dt, shape):
+    m, k, n = shape
+    rng = np.random.default_rng(m + n + k)
+    a, b = rand_f32(rng, (m, k), 1.0), rand_f32(rng, (k, n), 1.0 / np.sqrt(k))
+    if dt == "bf16":
+        ha, hb = as_bf16(a), as_bf16(b)
+        fa, fb = ao.bf16_to_f32(ha), ao.bf16_to_f32(hb)
+        da, db = dev.DeviceArray.from_numpy(ha, bf16=True), dev.DeviceArray.from_numpy(hb, bf16=True)
+    else:
+        ha, hb = a.astype(np.float16), b.astype(np.float16)
+        fa, fb = ha.astype(np.float32), hb.astype(np.float32)
+        da, db = dev.DeviceArray.from_numpy(ha), dev.DeviceArray.from_numpy(hb)
+    exp = np.matmul(fa.astype(np.float64), fb.astype(np.float64))
+    mag = np.matmul(np.abs(fa.astype(np.float64)), np.abs(fb.astype(np.float64)))
+    for variant in ("nn", "nt", "tn"):
+        if variant == "nn":
+            got = dev.matmul(da, db).numpy()
+        elif variant == "nt":  # weight stored {N,K}, transpose_b (nn::Linear layout)
+            dbt = dev.DeviceArray.from_numpy(np.ascontiguousarray(hb.T), bf16=(dt == "bf16"))
+            got = dev.matmul(da, dbt, transpose_b=True).numpy()
+        else:
+            dat = dev.DeviceArray.from_numpy(np.ascontiguousarray(ha.T), bf16=(dt == "bf16"))
+            got = dev.matmul(dat, db, transpose_a=True).numpy()
+        gf = ao.bf16_to_f32(got) if dt == "bf16" else got.astype(np.float32)
+        # north_star: <= 1e-2 relative vs an fp32 reference (fp32 accumulate + one rounding gives 2^-9 ~ 2e-3)
+        assert np.all(np.abs(gf - exp) <= 1e-2 * np.maximum(np.abs(exp), 0) + 4e-3 * mag / np.sqrt(k) + 1e-6), (dt, shape, variant)
+
+
+def test_bf16_batched_config4_subbatch(gpu):
+    """BASELINE config 4 at parity size: bf16 {2,4096,4096} x {2,4096,4096}; sampled 128x128 output tiles are checked
+    against an fp64 product of the same bf16 inputs."""
+    nb, n = 2, 4096
+    a = dev.cast(dev.randn((nb, n, n), 11, 0.0, 1.0), capi.BF16)
+    b = dev.cast(dev.randn((nb, n, n), 12, 0.0, 1.0 / 64.0), capi.BF16)
+    c = dev.matmul(a, b)
+    assert c.shape == (nb, n, n) and c.dtype == capi.BF16
+    rng = np.random.default_rng(0)
+    for _ in range(6):
+        bi, r0, c0 = int(rng.integers(nb)), int(rng.integers(0, n - 128)), int(rng.integers(0, n - 128))
+        ar = dev.DeviceArray(a.storage, a.dtype, (128, n), a.strides[1:], a.offset + bi * a.strides[0] + r0 * a.strides[1]).numpy()
+        bc = dev.DeviceArray(b.storage, b.dtype, (n, 128), b.strides[1:], b.offset + bi * b.strides[0] + c0 * b.strides[2]).numpy()
+        cc = dev.DeviceArray(c.storage, c.dtype, (128, 128), c.strides[1:], c.offset + bi * c.strides[0] + r0 * c.strides[1] + c0 * c.strides[2]).numpy()
+        exp = np.matmul(ao.bf16_to_f32(ar).astype(np.float64), ao.bf16_to_f32(bc).astype(np.float64))
+        got = ao.bf16_to_f32(cc)
+        assert np.all(np.abs(got - exp) <= 1e-2 * np.abs(exp) + 2e-2), float(np.max(np.abs(got - exp)))

@@ -1,0 +1,309 @@
+"""GPU parity for kernel family 2 (axis reductions, argmax/argmin, softmax, layer/RMS norm) through the C ABI.
+
+Mirrors the reference's tests/test_tensor_reductions.cpp (known answers on arange(6).reshape({2,3}) :14-136, the
+non-contiguous multi-axis GPU case :138-165), tests/test_cpu_gpu_parity.cpp reductions/argmax/softmax (:288-370,
+:406-420), tests/test_tensor_argmax_argmin.cpp (:35-148) and tests/test_tensor_normalization.cpp (:9-130), extended
+with what the reference never runs on a GPU: wide rows, odd sizes, split (multi-CTA) reductions, strided / offset /
+permuted inputs, bf16/fp16/int dtypes, ties and NaNs for argmax, and the BASELINE config-3 shape {8192,32768}.
+
+Bars (north_star): argmax/argmin bit-exact; fp32 reductions <= 1e-5 relative — measured, as SURVEY.md §7 explains,
+against sum(|x|) (a tree and the reference's 16-lane serial order both round at 1e-7 * sum|x|, and randn rows cancel);
+softmax / norms <= 1e-5 relative+absolute vs the oracle; max/min exact.
+"""
+import numpy as np
+import pytest
+
+from axiom_b200 import capi, device as dev
+from oracle import axiom_oracle as ao
+from oracle import ref
+from tests.helpers import as_bf16, bits_equal, rand_f32
+
+pytestmark = pytest.mark.gpu
+
+REF_RED = dict(sum="Sum", mean="Mean", max="Max", min="Min", prod="Prod", any="Any", all="All")
+
+
+def _sum_close(got, exp, x, axes, rtol=1e-5):
+    """|got - exp| <= rtol * sum(|x|) over the reduced axes (+ tiny absolute slack)."""
+    mag = np.abs(x.astype(np.float64)).sum(axis=tuple(axes) if axes else None)
+    mag = np.asarray(mag).reshape(np.asarray(exp).shape)
+    err = np.abs(np.asarray(got, np.float64) - np.asarray(exp, np.float64))
+    assert np.all(err <= rtol * mag + 1e-30), f"max err {err.max()} vs bound {(rtol * mag).min()}"
+
+
+# ---- known answers (tests/test_tensor_reductions.cpp:14-63) ----------------------------------------------------
+def test_known_answers_arange6(gpu):
+    x = np.arange(6, dtype=np.float32).reshape(2, 3)
+    d = dev.DeviceArray.from_numpy(x)
+    assert dev.reduce("sum", d).numpy().tolist() == [15.0]
+    assert dev.reduce("sum", d, [0]).numpy().tolist() == [3.0, 5.0, 7.0]
+    assert dev.reduce("sum", d, [1]).numpy().tolist() == [3.0, 12.0]
+    assert dev.reduce("mean", d).numpy().tolist() == [2.5]
+    assert dev.reduce("mean", d, [1]).numpy().tolist() == [1.0, 4.0]
+    assert dev.reduce("max", d).numpy().tolist() == [5.0]
+    assert dev.reduce("min", d, [0]).numpy().tolist() == [0.0, 1.0, 2.0]
+    assert dev.reduce("sum", d, [1], keep_dims=True).numpy().tolist() == [[3.0], [12.0]]
+    assert dev.reduce("sum", d, [], keep_dims=True).numpy().tolist() == [[15.0]]
+
+
+def test_noncontiguous_sum_gpu(gpu):
+    """tests/test_tensor_reductions.cpp:138-165 — sliced (non-zero offset) + permuted view, axes {1,2}."""
+    base = np.arange(2 * 5 * 4 * 3, dtype=np.float32).reshape(2, 5, 4, 3)
+    v = base[:, 1:4].transpose(0, 2, 1, 3)  # offset + permute
+    got = dev.reduce("sum", dev.DeviceArray.from_numpy(v), [1, 2]).numpy()
+    assert np.array_equal(got, v.sum(axis=(1, 2)))
+
+
+SHAPES_AXES = [((4, 5), [0]), ((4, 5), [1]), ((4, 5), []), ((4, 5, 3), [1]), ((4, 5, 3), [0, 2]), ((2, 4, 5), [2]),
+               ((1,), []), ((31,), [0]), ((33, 7), [0]), ((1023,), []), ((257, 129), [1]), ((257, 129), [0]),
+               ((7, 1, 33), [0, 1]), ((3, 4000), [1]), ((5, 70001), [1]), ((2, 3, 5, 7, 4), [1, 3]), ((300000,), []),
+               ((64, 96, 32), [1])]
+
+
+@pytest.mark.parametrize("shape,axes", SHAPES_AXES)
+@pytest.mark.parametrize("op", ["sum", "mean", "max", "min"])
+def test_reduce_f32_vs_oracle_and_reference(gpu, op, shape, axes):
+    rng = np.random.default_rng(abs(hash((op, shape, tuple(axes)))) % 2**31)
+    x = rand_f32(rng, shape)
+    for keep in (False, True):
+        got = dev.reduce(op, dev.DeviceArray.from_numpy(x), axes, keep).numpy()
+        exp, dt = ao.reduce(op, x, ao.F32, axes, keep)
+        assert got.shape == np.asarray(exp).shape
+        if op in ("max", "min"):
+            assert bits_equal(got, np.asarray(exp, np.float32))
+        else:
+            xs = x / (np.prod([shape[a] for a in (axes or range(len(shape)))]) if op == "mean" else 1)
+            _sum_close(got, exp, xs, axes or list(range(len(shape))))
+    if ref.available() and all(a >= 0 for a in axes):
+        r = ref.RefTensor.from_numpy(x).reduce(REF_RED[op], axes, False).numpy()
+        got = dev.reduce(op, dev.DeviceArray.from_numpy(x), axes, False).numpy()
+        if op in ("max", "min"):
+            assert bits_equal(got, r)
+        else:
+            xs = x / (np.prod([shape[a] for a in (axes or range(len(shape)))]) if op == "mean" else 1)
+            _sum_close(got, r, xs, axes or list(range(len(shape))))
+
+
+@pytest.mark.parametrize("dtname", ["bf16", "f16", "f64", "i32", "i64", "i16", "u8"])
+@pytest.mark.parametrize("op", ["sum", "mean", "max", "min", "prod"])
+def test_reduce_other_dtypes(gpu, op, dtname):
+    rng = np.random.default_rng(5)
+    shape, axes = (6, 130), [1]
+    if dtname in ("bf16", "f16", "f64"):
+        xf = rand_f32(rng, shape, 1.0)
+        if op == "prod":
+            xf = (1.0 + 0.01 * xf).astype(np.float32)
+        if dtname == "bf16":
+            x, dt, bf = as_bf16(xf), ao.BF16, True
+        elif dtname == "f16":
+            x, dt, bf = xf.astype(np.float16), ao.F16, False
+        else:
+            x, dt, bf = xf.astype(np.float64), ao.F64, False
+    else:
+        npdt = dict(i32=np.int32, i64=np.int64, i16=np.int16, u8=np.uint8)[dtname]
+        lo, hi = (0, 4) if op == "prod" else (0, 50) if dtname == "u8" else (-50, 50)
+        x = rng.integers(lo, hi, size=shape).astype(npdt)
+        if op == "prod":
+            x = np.where(rng.random(shape) < 0.9, 1, x).astype(npdt)
+        dt, bf = dict(i32=ao.I32, i64=ao.I64, i16=ao.I16, u8=ao.U8)[dtname], False
+    got = dev.reduce(op, dev.DeviceArray.from_numpy(x, bf16=bf), axes).numpy()
+    exp, edt = ao.reduce(op, x, dt, axes)
+    exp = np.asarray(exp)
+    if dtname in ("bf16", "f16"):
+        g = ao.to_f32(got, edt) if edt in (ao.BF16, ao.F16) else got
+        e = ao.to_f32(exp, edt) if edt in (ao.BF16, ao.F16) else exp
+        assert np.allclose(g, e, rtol=2 ** -7, atol=1e-2), (op, dtname)  # one half-ulp of the rounded result
+    elif dtname == "f64":
+        assert np.allclose(got, exp, rtol=1e-12, atol=1e-12)
+    else:
+        assert np.array_equal(got, exp.astype(got.dtype)), (op, dtname)
+
+
+def test_any_all(gpu):
+    x = np.zeros((5, 300), np.float32)
+    x[1, 7] = 2.0
+    x[3, :] = 1.0
+    d = dev.DeviceArray.from_numpy(x)
+    assert dev.reduce("any", d, [1]).numpy().astype(bool).tolist() == [False, True, False, True, False]
+    assert dev.reduce("all", d, [1]).numpy().astype(bool).tolist() == [False, False, False, True, False]
+    assert bool(dev.reduce("any", d).numpy()[0]) and not bool(dev.reduce("all", d).numpy()[0])
+
+
+# ---- argmax / argmin: bit-exact, first index on ties, NaN never wins ---------------------------
+def test_argmax_quirks_known_rows(gpu):
+    rows = np.array([[1, 5, 5], [np.nan, 2, 2], [np.nan, np.nan, np.nan], [-np.inf, -np.inf, -np.inf]], np.float32)
+    got = dev.argreduce("argmax", dev.DeviceArray.from_numpy(rows), 1).numpy()
+    assert got.tolist() == [1, 1, 0, 0]
+    got = dev.argreduce("argmin", dev.DeviceArray.from_numpy(rows), 1).numpy()
+    assert got.tolist() == [0, 1, 0, 0]
+    assert got.dtype == np.int64
+
+
+@pytest.mark.parametrize("shape,axis", [((4, 5), 1), ((4, 5), 0), ((2, 4, 5), 1), ((6,), 0), ((33, 1025), 1),
+                                        ((1025, 33), 0), ((3, 70001), 1), ((200000,), -1), ((7, 9), -1)])
+@pytest.mark.parametrize("op", ["argmax", "argmin"])
+def test_argreduce_bit_exact(gpu, op, shape, axis):
+    rng = np.random.default_rng(3)
+    x = np.round(rand_f32(rng, shape) * 4) / 4  # plenty of exact ties
+    x.flat[::97] = np.nan
+    got = dev.argreduce(op, dev.DeviceArray.from_numpy(x), axis).numpy()
+    exp = ao.argreduce(op, x, ao.F32, axis)
+    assert got.shape == exp.shape and np.array_equal(got, exp), (op, shape, axis)
+    if ref.available() and axis >= 0:
+        r = ref.RefTensor.from_numpy(x).argreduce("ArgMax" if op == "argmax" else "ArgMin", axis).numpy()
+        assert np.array_equal(got, r)
+    for dt, conv in ((ao.I32, lambda a: np.nan_to_num(a * 4).astype(np.int32)), (ao.BF16, None)):
+        if conv is None:
+            xb = as_bf16(np.nan_to_num(x))
+            g = dev.argreduce(op, dev.DeviceArray.from_numpy(xb, bf16=True), axis).numpy()
+            e = ao.argreduce(op, xb, ao.BF16, axis)
+        else:
+            xi = conv(x)
+            g = dev.argreduce(op, dev.DeviceArray.from_numpy(xi), axis).numpy()
+            e = ao.argreduce(op, xi, dt, axis)
+        assert np.array_equal(g, e), (op, shape, axis, dt)
+
+
+def test_argmax_strided_input(gpu):
+    rng = np.random.default_rng(9)
+    base = rand_f32(rng, (40, 60))
+    v = base[3:, ::2].T  # offset, strided, transposed
+    got = dev.argreduce("argmax", dev.DeviceArray.from_numpy(v), 0).numpy()
+    assert np.array_equal(got, np.argmax(v, axis=0))
+
+
+# ---- softmax / log_softmax ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("shape,axis", [((4, 5), -1), ((4, 5), 0), ((2, 4, 5), 1), ((3, 257), -1), ((9, 1024), -1),
+                                        ((5, 1500), -1), ((3, 8192), -1), ((2, 8200), -1), ((2, 32768), -1),
+                                        ((2, 40000), -1), ((1, 7), -1)])
+@pytest.mark.parametrize("log", [False, True])
+def test_softmax_f32(gpu, shape, axis, log):
+    rng = np.random.default_rng(21)
+    x = rand_f32(rng, shape, 3.0)
+    got = dev.softmax(dev.DeviceArray.from_numpy(x), axis, log).numpy()
+    # (1) against the exact (fp64) softmax: <= 1e-5 relative — the north_star bound, measured against the truth
+    x64 = x.astype(np.float64)
+    z = x64 - x64.max(axis=axis, keepdims=True)
+    lse = np.log(np.exp(z).sum(axis=axis, keepdims=True))
+    truth = (z - lse) if log else np.exp(z - lse)
+    assert np.allclose(got, truth, rtol=1e-5, atol=1e-6 if not log else 1e-5), (shape, axis, log)
+    if not log:
+        assert np.allclose(got.sum(axis=axis), 1.0, atol=1e-4)
+    # (2) against the oracle / the reference itself. Their denominator is a SERIAL fp32 sum (cpu_operations.cpp:3132-3158)
+    # whose own rounding error grows like sqrt(n)*2^-24 (2.5e-5 at n = 32768), so beyond n ~ 4096 the comparison uses the
+    # reference's own CPU/GPU parity tolerance for softmax (tests/test_cpu_gpu_parity.cpp: 1e-4).
+    tol = 1e-5 if x.shape[axis] <= 4096 else 1e-4
+    exp = ao.softmax(x, ao.F32, axis, log)
+    assert np.allclose(got, exp, rtol=tol, atol=1e-6 if not log else tol), (shape, axis, log)
+    if ref.available():
+        r = ref.RefTensor.from_numpy(x).softmax(axis, log).numpy()
+        assert np.allclose(got, r, rtol=tol, atol=1e-6 if not log else tol)
+
+
+def test_softmax_half_and_strided(gpu):
+    rng = np.random.default_rng(22)
+    x = rand_f32(rng, (6, 300), 2.0)
+    xb = as_bf16(x)
+    got = dev.softmax(dev.DeviceArray.from_numpy(xb, bf16=True), -1).numpy()
+    exp = ao.softmax(xb, ao.BF16, -1)
+    assert np.max(np.abs(ao.bf16_to_f32(got) - ao.bf16_to_f32(exp))) <= 2 ** -8 * np.max(ao.bf16_to_f32(exp))
+    xh = x.astype(np.float16)
+    got = dev.softmax(dev.DeviceArray.from_numpy(xh), -1).numpy()
+    exp = ao.softmax(xh, ao.F16, -1)
+    assert np.allclose(got.astype(np.float32), np.asarray(exp).astype(np.float32), rtol=2e-3, atol=1e-6)
+    v = rand_f32(rng, (64, 48))[5:, ::3].T  # strided view, softmax along a non-contiguous axis
+    got = dev.softmax(dev.DeviceArray.from_numpy(v), 0).numpy()
+    assert np.allclose(got, ao.softmax(np.ascontiguousarray(v), ao.F32, 0), rtol=1e-5, atol=1e-6)
+
+
+# ---- layer_norm / rms_norm (tests/test_tensor_normalization.cpp:9-130) --------------------------------------------
+@pytest.mark.parametrize("shape", [(2, 3, 4), (4, 384), (3, 1000), (2, 1500, 384), (2, 8192), (2, 32768), (1, 33000)])
+def test_layer_and_rms_norm_f32(gpu, shape):
+    rng = np.random.default_rng(31)
+    x = rand_f32(rng, shape, 2.0) + np.float32(0.5)
+    n = shape[-1]
+    w = (1 + 0.1 * rng.standard_normal(n)).astype(np.float32)
+    b = (0.1 * rng.standard_normal(n)).astype(np.float32)
+    dx, dw, db = (dev.DeviceArray.from_numpy(t) for t in (x, w, b))
+    got = dev.layer_norm(dx, dw, db, -1, 1e-5).numpy()
+    exp, _ = ao.layer_norm(x, ao.F32, w, ao.F32, b, ao.F32, -1, 1e-5)
+    assert np.allclose(got, exp, rtol=1e-5, atol=2e-5), shape
+    got_r = dev.rms_norm(dx, dw, -1, 1e-5).numpy()
+    exp_r, _ = ao.rms_norm(x, ao.F32, w, ao.F32, -1, 1e-5)
+    assert np.allclose(got_r, exp_r, rtol=1e-5, atol=2e-5), shape
+    if ref.available() and np.prod(shape) <= 2_000_000:
+        rx, rw, rb = (ref.RefTensor.from_numpy(t) for t in (x, w, b))
+        assert np.allclose(got, rx.layer_norm(rw, rb, -1, 1e-5).numpy(), rtol=1e-5, atol=2e-5)
+        assert np.allclose(got_r, rx.rms_norm(rw, -1, 1e-5).numpy(), rtol=1e-5, atol=2e-5)
+
+
+def test_layer_norm_known_answer_and_no_affine(gpu):
+    x = np.array([[1, 2, 3, 4]], np.float32)
+    got = dev.layer_norm(dev.DeviceArray.from_numpy(x), None, None, -1, 0.0).numpy()
+    e = (x - 2.5) / np.sqrt(1.25)
+    assert np.allclose(got, e, rtol=1e-6)
+
+
+def test_layer_norm_bf16_matches_cpu_float32_result(gpu):
+    """the CPU path returns Float32 for bf16 input (mean rounded to bf16 first); the GPU lazy node
+    declares the input dtype. Both output dtypes are offered; the Float32 one is compared with the oracle."""
+    rng = np.random.default_rng(33)
+    x = as_bf16(rand_f32(rng, (5, 384), 2.0))
+    w = (1 + 0.1 * rng.standard_normal(384)).astype(np.float32)
+    b = (0.1 * rng.standard_normal(384)).astype(np.float32)
+    dx, dw, db = dev.DeviceArray.from_numpy(x, bf16=True), dev.DeviceArray.from_numpy(w), dev.DeviceArray.from_numpy(b)
+    got32 = dev.layer_norm(dx, dw, db, -1, 1e-5, out_dtype=capi.F32).numpy()
+    exp, edt = ao.layer_norm(x, ao.BF16, w, ao.F32, b, ao.F32, -1, 1e-5)
+    assert edt == ao.F32 and np.allclose(got32, exp, rtol=1e-5, atol=2e-5)
+    got16 = dev.layer_norm(dx, dw, db, -1, 1e-5).numpy()
+    assert np.array_equal(got16, ao.f32_to_bf16(got32))
+
+
+# ---- BASELINE config 3: {8192, 32768} rows, fp32 and bf16 ---------------------------------------------------------
+@pytest.mark.parametrize("dt", ["f32", "bf16"])
+def test_config3_full_size(gpu, dt):
+    rows, n = 8192, 32768
+    x = dev.randn((rows, n), 7)
+    if dt == "bf16":
+        x = dev.cast(x, capi.BF16)
+    # a 64-row sample goes to the host oracle; whole-tensor properties cover the rest
+    sample = dev.DeviceArray(x.storage, x.dtype, (64, n), x.strides, x.offset + 4000 * x.strides[0])
+    hs = sample.numpy()
+    odt = ao.BF16 if dt == "bf16" else ao.F32
+    hf = ao.to_f32(hs, odt) if dt == "bf16" else hs
+
+    s = dev.reduce("sum", x, [1]).numpy()
+    es, _ = ao.reduce("sum", hs, odt, [1])
+    if dt == "bf16":
+        assert np.max(np.abs(ao.bf16_to_f32(s[4000:4064]) - ao.bf16_to_f32(np.asarray(es)))) <= 2.0  # 1 bf16 ulp at ~256
+    else:
+        _sum_close(s[4000:4064], es, hf, [1])
+    m = dev.reduce("max", x, [1]).numpy()
+    em, _ = ao.reduce("max", hs, odt, [1])
+    assert bits_equal(m[4000:4064], np.asarray(em).astype(m.dtype))
+    am = dev.argreduce("argmax", x, 1).numpy()
+    assert np.array_equal(am[4000:4064], ao.argreduce("argmax", hs, odt, 1))
+    # property over ALL rows: the element at argmax equals the row max
+    idx = dev.DeviceArray.from_numpy(am.reshape(rows, 1))
+    picked = dev.gather(x, 1, idx).numpy().reshape(rows)
+    assert bits_equal(picked, m)
+
+    sm = dev.softmax(x, -1)
+    sms = dev.DeviceArray(sm.storage, sm.dtype, (64, n), sm.strides, sm.offset + 4000 * sm.strides[0]).numpy()
+    esm = ao.softmax(hs, odt, -1)
+    if dt == "bf16":
+        assert np.max(np.abs(ao.bf16_to_f32(sms) - ao.bf16_to_f32(esm))) <= 2 ** -8 * ao.bf16_to_f32(esm).max()
+    else:
+        assert np.allclose(sms, esm, rtol=1e-4, atol=1e-9)  # serial fp32 denominator in the reference, see test_softmax_f32
+        h64 = hf.astype(np.float64)
+        z = h64 - h64.max(axis=1, keepdims=True)
+        assert np.allclose(sms, np.exp(z) / np.exp(z).sum(axis=1, keepdims=True), rtol=1e-5, atol=1e-12)
+        rs = dev.reduce("sum", sm, [1]).numpy()  # every softmax row sums to 1
+        assert np.allclose(rs, 1.0, atol=1e-4)
+
+    w = dev.randn((n,), 8, 1.0, 0.1)
+    b = dev.randn((n,), 9, 0.0, 0.1)
+    ln = dev.layer_norm(x, w, b, -1, 1e-5, out_dtype=capi.F32)
+    lns = dev.DeviceArray(ln.storage, ln.dtype, (64, n), ln.strides, ln.offset + 4000 * ln.strides[0]).numpy()
+    eln, _ = ao.layer_norm(hs, odt, w.numpy(), ao.F32, b.numpy(), ao.F32, -1, 1e-5)
+    assert np.allclose(lns, eln, rtol=1e-5, atol=3e-5)
