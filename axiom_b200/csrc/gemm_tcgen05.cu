@@ -1,10 +1,467 @@
-// gemm_tcgen05.cu — placeholder while the tensor-core kernel is being brought up: nothing qualifies yet.
+// gemm_tcgen05.cu — kernel family 3: bf16 / fp16 matmul and batched matmul on the 5th-generation tensor cores.
+//
+// Replaces the BLAS call of the reference's matmul path (CPUMatMulOperation -> matmul_2d -> BlasBackend::sgemm,
+// src/backends/cpu/cpu_operations.cpp:1773-1883, :2028-2053 for the batch loop) for half-precision operands; the
+// reference has no BLAS path for bf16 at all (tiled triple loop with a bf16 accumulator, :1835-1882), so the numerics
+// contract is the north_star's: fp32 accumulate, ONE rounding to the output type, <= 1e-2 relative vs fp32.
+//
+// Design (persistent, warp-specialised, one CTA per SM):
+//   warp 0      TMA producer : cp.async.bulk.tensor (3-D maps: inner, rows, batch) into a 4-stage shared-memory ring,
+//                              128-byte swizzle, completion on mbarriers (expect_tx)
+//   warp 1      MMA issuer   : one elected thread issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=256, K=16),
+//                              A/B straight from shared memory through UMMA descriptors, fp32 accumulators in TMEM;
+//                              tcgen05.commit releases ring slots / publishes finished accumulators
+//   warps 2..5  epilogue     : tcgen05.ld (32 lanes x 32 columns per warp) -> bias / activation -> one rounding ->
+//                              128-bit global stores. TMEM holds TWO 128x256 fp32 accumulators (all 512 columns), so the
+//                              epilogue of tile i overlaps the MMAs of tile i+1.
+// Transposes are never materialised: an operand whose contraction dim is contiguous is fed K-major, one whose M/N dim
+// is contiguous is fed MN-major (instruction-descriptor major bits + the matching UMMA canonical layout), which covers
+// x.T() views and nn::Linear's transpose_b. Ragged M/N/K use TMA's out-of-bounds zero fill and masked stores.
+// Anything TMA cannot describe (unaligned base/strides, inner stride != 1, non-collapsible batch) returns to the SIMT path.
+#include <cuda.h>
+
+#include <algorithm>
+#include <cstring>
+
+#include "driver.h"
 #include "gemm.h"
+#include "hwy_math.cuh"
+#include "reduce_common.cuh"
+
 namespace axb {
 namespace gemm {
-axb_status try_tcgen05(const Desc &, int, int, int, DeviceCtx *, cudaStream_t, bool *done) {
-    *done = false;
+
+namespace {
+
+constexpr int BM = 128, BN = 256, BK = 64;
+constexpr int STAGES = 4;
+constexpr int A_BYTES = BM * BK * 2;        // 16 KiB
+constexpr int B_BYTES = BN * BK * 2;        // 32 KiB
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
+constexpr int NUM_THREADS = 192;
+constexpr uint32_t TMEM_COLS = 512;
+
+struct TcParams {
+    int64_t M, N, K, batch;
+    int32_t tiles_m, tiles_n;
+    int64_t num_tiles;
+    char *c;
+    int64_t c_rs, c_cs, c_bs;       // bytes
+    const char *bias;
+    int64_t bias_rs, bias_cs, bias_bs;
+    int32_t bias_dtype, act, out_dtype;
+    int32_t a_bmult, b_bmult;       // 0 when the operand is broadcast over the batch
+    uint32_t idesc;
+};
+
+// ---- PTX wrappers ---------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done)
+                     : "r"(bar), "r"(parity)
+                     : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+                 : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                 "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                   "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+                   "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+                   "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                 : "r"(taddr)
+                 : "memory");
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// UMMA shared-memory descriptor (cute/arch/mma_sm100_desc.hpp SmemDescriptor): start>>4 [0,14), LBO>>4 [16,30),
+// SBO>>4 [32,46), version=1 [46,48), layout SWIZZLE_128B=2 [61,64).
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46) | (2ull << 61);
+}
+
+__device__ __forceinline__ float act_f(float v, int act) {
+    switch (act) {
+    case AXB_OP_RELU: return v > 0.0f ? v : 0.0f;
+    case AXB_OP_GELU: return hwym::Gelu(v);
+    case AXB_OP_SILU: return hwym::Silu(v);
+    case AXB_OP_SIGMOID: return hwym::Sigmoid(v);
+    case AXB_OP_TANH: return hwym::Tanh(v);
+    default: return v;
+    }
+}
+__device__ __forceinline__ float ld_bias(const char *p, int dt) {
+    return dt == AXB_F32 ? *reinterpret_cast<const float *>(p)
+                         : dt == AXB_BF16 ? red::bf2f(*reinterpret_cast<const uint16_t *>(p))
+                                          : red::h2f(*reinterpret_cast<const uint16_t *>(p));
+}
+
+// A_MN / B_MN: operand is MN-major (its M / N dim is the contiguous one) instead of K-major.
+template <bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+               const __grid_constant__ TcParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t smem = (raw + 1023u) & ~1023u; // SWIZZLE_128B tiles need 1024-byte alignment
+    const uint32_t bar_base = smem + STAGES * STAGE_BYTES;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+    auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
+    auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
+    const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
+    uint32_t *tmem_slot_ptr = reinterpret_cast<uint32_t *>(smem_raw + (tmem_slot - raw));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(tfull_bar(a), 1);
+            mbar_init(tempty_bar(a), 4); // one arrive per epilogue warp
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+    const int num_kb = (int)((p.K + BK - 1) / BK);
+    const int64_t tiles_per_batch = (int64_t)p.tiles_m * p.tiles_n;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int64_t t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+                const int64_t b = t / tiles_per_batch;
+                const int r = (int)(t - b * tiles_per_batch);
+                const int m0 = (r / p.tiles_n) * BM, n0 = (r % p.tiles_n) * BN;
+                const int ba = (int)b * p.a_bmult, bb = (int)b * p.b_bmult;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(empty_bar(stage), phase ^ 1u);
+                    mbar_expect_tx(full_bar(stage), STAGE_BYTES);
+                    const uint32_t sa = smem + stage * STAGE_BYTES, sb = sa + A_BYTES;
+                    const int k0 = kb * BK;
+                    if (!A_MN) {
+                        tma_load_3d(sa, &tma_a, full_bar(stage), k0, m0, ba); // box {64 k, 128 m}
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < BM / 64; ++j) // box {64 m, 64 k} per 64-wide M chunk
+                            tma_load_3d(sa + j * (64 * BK * 2), &tma_a, full_bar(stage), m0 + 64 * j, k0, ba);
+                    }
+                    if (!B_MN) {
+                        tma_load_3d(sb, &tma_b, full_bar(stage), k0, n0, bb); // box {64 k, 256 n}
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < BN / 64; ++j)
+                            tma_load_3d(sb + j * (64 * BK * 2), &tma_b, full_bar(stage), n0 + 64 * j, k0, bb);
+                    }
+                    if (++stage == STAGES) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            int stage = 0, acc = 0;
+            uint32_t phase = 0, acc_phase = 0;
+            for (int64_t t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+                mbar_wait(tempty_bar(acc), acc_phase ^ 1u); // epilogue has drained this accumulator
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + (uint32_t)acc * BN;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(full_bar(stage), phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem + stage * STAGE_BYTES, sb = sa + A_BYTES;
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k) {
+                        // K-major SW128: rows of 128 B, 8-row groups 1024 B apart (SBO); a K step of 16 elements = +32 B.
+                        // MN-major SW128: 64-element MN chunks 8 KiB apart (LBO), 8-row K groups 1024 B apart (SBO);
+                        //                 a K step of 16 rows = +2048 B.
+                        const uint64_t ad = A_MN ? umma_desc(sa + k * 2048, 64 * BK * 2, 1024) : umma_desc(sa + k * 32, 16, 1024);
+                        const uint64_t bd = B_MN ? umma_desc(sb + k * 2048, 64 * BK * 2, 1024) : umma_desc(sb + k * 32, 16, 1024);
+                        tc_mma(tmem_d, ad, bd, p.idesc, (kb | k) != 0);
+                    }
+                    tc_commit(empty_bar(stage)); // slot is free once these MMAs have read it
+                    if (++stage == STAGES) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
+                }
+                tc_commit(tfull_bar(acc)); // accumulator complete
+                if (++acc == 2) {
+                    acc = 0;
+                    acc_phase ^= 1u;
+                }
+            }
+        }
+    } else {
+        // epilogue: warp w may only touch TMEM lanes [32*(w%4), 32*(w%4)+32)
+        const int q = warp & 3;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        const bool c_vec = (p.c_cs == 2) && ((reinterpret_cast<uintptr_t>(p.c) | (uintptr_t)p.c_rs | (uintptr_t)p.c_bs) % 16 == 0);
+        for (int64_t t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+            const int64_t b = t / tiles_per_batch;
+            const int r = (int)(t - b * tiles_per_batch);
+            const int m0 = (r / p.tiles_n) * BM, n0 = (r % p.tiles_n) * BN;
+            const int64_t m = m0 + q * 32 + lane;
+            mbar_wait(tfull_bar(acc), acc_phase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * BN;
+            char *crow = p.c + b * p.c_bs + m * p.c_rs;
+            const char *brow = p.bias ? p.bias + b * p.bias_bs + m * p.bias_rs : nullptr;
+#pragma unroll 1
+            for (int c = 0; c < BN / 32; ++c) {
+                uint32_t v[32];
+                tc_ld32(taddr + c * 32, v);
+                tc_wait_ld();
+                const int64_t nbase = n0 + c * 32;
+                if (m < p.M && nbase < p.N) {
+                    float f[32];
+#pragma unroll
+                    for (int i = 0; i < 32; ++i)
+                        f[i] = __uint_as_float(v[i]);
+                    if (p.bias || p.act) {
+                        // separate ops in the reference: each intermediate is rounded to the output dtype
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            float x = f[i];
+                            if (p.bias && nbase + i < p.N) {
+                                x = p.out_dtype == AXB_BF16 ? red::bf2f(red::f2bf(x)) : red::h2f(red::f2h(x));
+                                x += ld_bias(brow + (nbase + i) * p.bias_cs, p.bias_dtype);
+                            }
+                            if (p.act) {
+                                x = p.out_dtype == AXB_BF16 ? red::bf2f(red::f2bf(x)) : red::h2f(red::f2h(x));
+                                x = act_f(x, p.act);
+                            }
+                            f[i] = x;
+                        }
+                    }
+                    uint32_t h[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const uint32_t lo = p.out_dtype == AXB_BF16 ? red::f2bf(f[2 * i]) : red::f2h(f[2 * i]);
+                        const uint32_t hi = p.out_dtype == AXB_BF16 ? red::f2bf(f[2 * i + 1]) : red::f2h(f[2 * i + 1]);
+                        h[i] = lo | (hi << 16);
+                    }
+                    if (c_vec && nbase + 32 <= p.N) {
+                        uint4 *dst = reinterpret_cast<uint4 *>(crow + nbase * 2);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+                            dst[i] = make_uint4(h[4 * i], h[4 * i + 1], h[4 * i + 2], h[4 * i + 3]);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i)
+                            if (nbase + i < p.N)
+                                *reinterpret_cast<uint16_t *>(crow + (nbase + i) * p.c_cs) =
+                                    (uint16_t)((i & 1) ? (h[i >> 1] >> 16) : (h[i >> 1] & 0xFFFFu));
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0)
+                mbar_arrive(tempty_bar(acc));
+            if (++acc == 2) {
+                acc = 0;
+                acc_phase ^= 1u;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        __syncwarp();
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+// collapses the batch dims of one operand to a single (extent, byte stride); false if impossible
+bool collapse_batch(const Desc &d, const int64_t *bs, int64_t *stride, int *mult) {
+    bool all_zero = true;
+    for (int i = 0; i < d.nb; ++i)
+        if (d.bshape[i] != 1 && bs[i] != 0)
+            all_zero = false;
+    if (d.batch == 1 || all_zero) {
+        *stride = 0;
+        *mult = 0;
+        return true;
+    }
+    int64_t expect = -1, inner = 0;
+    for (int i = 0; i < d.nb; ++i) { // innermost first
+        if (d.bshape[i] == 1)
+            continue;
+        if (expect < 0) {
+            inner = bs[i];
+            expect = bs[i] * d.bshape[i];
+        } else {
+            if (bs[i] != expect)
+                return false;
+            expect *= d.bshape[i];
+        }
+    }
+    *stride = inner;
+    *mult = 1;
+    return inner > 0;
+}
+
+struct Operand {
+    bool mn_major;
+    int64_t ld; // byte stride of the non-contiguous matrix dim
+};
+// rows/cols strides of the logical [MN][K] operand -> major-ness; false if neither dim is contiguous
+bool classify(int64_t mn_stride, int64_t k_stride, int64_t mn_extent, int64_t k_extent, Operand *o) {
+    if (k_stride == 2 || k_extent == 1) { // contraction dim contiguous -> K-major
+        o->mn_major = false;
+        o->ld = mn_extent == 1 ? 0 : mn_stride;
+        return o->ld >= 0;
+    }
+    if (mn_stride == 2 || mn_extent == 1) {
+        o->mn_major = true;
+        o->ld = k_stride;
+        return o->ld >= 0;
+    }
+    return false;
+}
+
+axb_status make_map(CUtensorMap *map, const drv::Api *api, int dtype, const void *base, uint64_t d0, uint64_t d1, uint64_t d2,
+                    uint64_t s1, uint64_t s2, uint32_t b0, uint32_t b1) {
+    cuuint64_t gdim[3] = {d0, d1, d2};
+    cuuint64_t gstr[2] = {s1, s2};
+    cuuint32_t box[3] = {b0, b1, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = api->TensorMapEncodeTiled(map, dtype == AXB_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3,
+                                           const_cast<void *>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+        return fail(AXB_ERR_CUDA, "cuTensorMapEncodeTiled failed: %s", drv::err_str(r));
     return AXB_OK;
 }
+
+template <bool A_MN, bool B_MN>
+axb_status launch(const CUtensorMap &ma, const CUtensorMap &mb, const TcParams &p, int sm_count, cudaStream_t s) {
+    static bool configured = false; // per instantiation; benign race (same value)
+    if (!configured) {
+        AXB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        configured = true;
+    }
+    const unsigned grid = (unsigned)std::min<int64_t>(p.num_tiles, sm_count);
+    gemm_tc_kernel<A_MN, B_MN><<<grid, NUM_THREADS, SMEM_BYTES, s>>>(ma, mb, p);
+    AXB_CHECK_LAUNCH();
+    return AXB_OK;
+}
+
+} // namespace
+
+axb_status try_tcgen05(const Desc &d, int adt, int bdt, int cdt, DeviceCtx *ctx, cudaStream_t s, bool *done) {
+    *done = false;
+    if (!((adt == AXB_BF16 || adt == AXB_F16) && adt == bdt && cdt == adt))
+        return AXB_OK;
+    if (d.M * d.N * d.K < 64 * 64 * 64 || d.M >= (1ll << 31) || d.N >= (1ll << 31) || d.K >= (1ll << 31) || d.batch >= (1ll << 31))
+        return AXB_OK; // tiny problems stay on the SIMT kernel
+    Operand oa, ob;
+    if (!classify(d.a_rs, d.a_cs, d.M, d.K, &oa) || !classify(d.b_cs, d.b_rs, d.N, d.K, &ob))
+        return AXB_OK;
+    int64_t a_bs, b_bs, c_bs, bias_bs = 0;
+    int a_mult, b_mult, c_mult, bias_mult = 0;
+    if (!collapse_batch(d, d.a_bs, &a_bs, &a_mult) || !collapse_batch(d, d.b_bs, &b_bs, &b_mult) ||
+        !collapse_batch(d, d.c_bs, &c_bs, &c_mult))
+        return AXB_OK;
+    if (d.bias && !collapse_batch(d, d.bias_bs, &bias_bs, &bias_mult))
+        return AXB_OK;
+    if (d.batch > 1 && !c_mult)
+        return AXB_OK;
+    auto aligned16 = [](int64_t v) { return v % 16 == 0; };
+    if (!aligned16((int64_t)reinterpret_cast<uintptr_t>(d.a)) || !aligned16((int64_t)reinterpret_cast<uintptr_t>(d.b)) ||
+        !aligned16(oa.ld) || !aligned16(ob.ld) || !aligned16(a_bs) || !aligned16(b_bs))
+        return AXB_OK;
+    if (d.c_rs < 0 || d.c_cs < 0)
+        return AXB_OK;
+    const drv::Api *api = drv::api();
+    if (!api)
+        return AXB_ERR_CUDA;
+    // degenerate extents: a dim of extent 1 may carry any stride; give TMA a legal one
+    const uint64_t a_ld = (uint64_t)std::max<int64_t>(oa.ld, 16), b_ld = (uint64_t)std::max<int64_t>(ob.ld, 16);
+    const uint64_t a_b = (uint64_t)std::max<int64_t>(a_bs, 16), b_b = (uint64_t)std::max<int64_t>(b_bs, 16);
+    const uint64_t abatch = a_mult ? (uint64_t)d.batch : 1, bbatch = b_mult ? (uint64_t)d.batch : 1;
+    CUtensorMap ma, mb;
+    if (!oa.mn_major)
+        AXB_TRY(make_map(&ma, api, adt, d.a, (uint64_t)d.K, (uint64_t)d.M, abatch, a_ld, a_b, BK, BM));
+    else
+        AXB_TRY(make_map(&ma, api, adt, d.a, (uint64_t)d.M, (uint64_t)d.K, abatch, a_ld, a_b, 64, BK));
+    if (!ob.mn_major)
+        AXB_TRY(make_map(&mb, api, bdt, d.b, (uint64_t)d.K, (uint64_t)d.N, bbatch, b_ld, b_b, BK, BN));
+    else
+        AXB_TRY(make_map(&mb, api, bdt, d.b, (uint64_t)d.N, (uint64_t)d.K, bbatch, b_ld, b_b, 64, BK));
+    TcParams p;
+    memset(&p, 0, sizeof p);
+    p.M = d.M; p.N = d.N; p.K = d.K; p.batch = d.batch;
+    p.tiles_m = (int)((d.M + BM - 1) / BM);
+    p.tiles_n = (int)((d.N + BN - 1) / BN);
+    p.num_tiles = (int64_t)p.tiles_m * p.tiles_n * d.batch;
+    p.c = d.c; p.c_rs = d.c_rs; p.c_cs = d.c_cs; p.c_bs = c_bs;
+    p.bias = d.bias; p.bias_rs = d.bias_rs; p.bias_cs = d.bias_cs; p.bias_bs = bias_mult ? bias_bs : 0;
+    p.bias_dtype = d.bias_dtype; p.act = d.act; p.out_dtype = cdt;
+    p.a_bmult = a_mult; p.b_bmult = b_mult;
+    // instruction descriptor (cute/arch/mma_sm100_desc.hpp InstrDescriptor): c_format F32 = 1 @4, a/b format (F16 = 0,
+    // BF16 = 1) @7/@10, a/b major (MN = 1) @15/@16, N>>3 @17, M>>4 @24
+    const uint32_t fmt = adt == AXB_BF16 ? 1u : 0u;
+    p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((oa.mn_major ? 1u : 0u) << 15) | ((ob.mn_major ? 1u : 0u) << 16) |
+              ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    axb_status st;
+    if (!oa.mn_major && !ob.mn_major)
+        st = launch<false, false>(ma, mb, p, ctx->sm_count, s);
+    else if (!oa.mn_major && ob.mn_major)
+        st = launch<false, true>(ma, mb, p, ctx->sm_count, s);
+    else if (oa.mn_major && !ob.mn_major)
+        st = launch<true, false>(ma, mb, p, ctx->sm_count, s);
+    else
+        st = launch<true, true>(ma, mb, p, ctx->sm_count, s);
+    if (st == AXB_OK)
+        *done = true;
+    return st;
+}
+
 } // namespace gemm
 } // namespace axb

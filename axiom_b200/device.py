@@ -127,7 +127,16 @@ class DeviceArray:
 
 
 def _bshape(*shapes: Sequence[int]) -> Tuple[int, ...]:
-    return tuple(np.broadcast_shapes(*[tuple(s) for s in shapes]))
+    """NumPy broadcast through the library's own rule (ops::compute_broadcast_info): errors surface as AxbError."""
+    cur = tuple(int(e) for e in shapes[0])
+    for s in shapes[1:]:
+        a = (ctypes.c_int64 * capi.AXB_MAX_DIMS)(*cur)
+        b = (ctypes.c_int64 * capi.AXB_MAX_DIMS)(*[int(e) for e in s])
+        out = (ctypes.c_int64 * capi.AXB_MAX_DIMS)()
+        n = ctypes.c_int32()
+        check(lib().axb_broadcast_shape(a, len(cur), b, len(s), out, ctypes.byref(n)))
+        cur = tuple(out[i] for i in range(n.value))
+    return cur
 
 
 def synchronize() -> None:
