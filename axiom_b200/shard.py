@@ -1,0 +1,72 @@
+"""Batch-dimension sharding across the GPUs of one box.
+
+The reference has no multi-device notion (enum Device {CPU, GPU} carries no index, include/axiom/storage.hpp:8-11), so
+this is new functionality that lives BESIDE the unchanged API: one process per GPU, every rank owns a contiguous block of
+the leading (batch / row) dimension, and the only exchange step is the combine of FULL-tensor reductions — per-row
+reductions, softmax / norms, batched matmul and elementwise chains need no collective at all.
+
+`torch.distributed` is the plumbing (NCCL over NVLink on the GPU box, gloo in the CPU tests); the partials themselves
+come from libaxb kernels (or, in the CPU tests, from numpy). Nothing here computes on the data path.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import numpy as np
+
+
+def plan_rows(total: int, world: int, rank: int) -> Tuple[int, int]:
+    """[start, stop) of `rank`'s block of a dimension of extent `total`: blocks differ by at most one row, earlier
+    ranks take the extra ones (so shard r starts at r*q + min(r, rem))."""
+    if world < 1 or not (0 <= rank < world):
+        raise ValueError("bad world/rank")
+    q, rem = divmod(int(total), world)
+    start = rank * q + min(rank, rem)
+    return start, start + q + (1 if rank < rem else 0)
+
+
+def _dist():
+    import torch.distributed as dist
+    return dist
+
+
+def combine_full_reduction(op: str, partial: np.ndarray, local_count: int, device: Optional[str] = None) -> np.ndarray:
+    """Combines per-shard partials of a full-tensor reduction with ONE all-reduce.
+
+    sum/prod/max/min/any/all map onto the matching collective op; mean all-reduces (sum, count) so that ragged shards
+    are weighted correctly. `partial` is the shard's {1} result in its accumulation dtype (fp32 for half inputs)."""
+    import torch
+    dist = _dist()
+    t = torch.from_numpy(np.ascontiguousarray(partial).copy())
+    if device:
+        t = t.to(device)
+    if op == "mean":
+        acc = torch.stack([t.double().reshape(-1)[0] * float(local_count), torch.tensor(float(local_count), dtype=torch.float64, device=t.device)])
+        dist.all_reduce(acc, op=dist.ReduceOp.SUM)
+        out = (acc[0] / acc[1]).to(t.dtype).reshape(t.shape)
+    else:
+        red = {"sum": dist.ReduceOp.SUM, "prod": dist.ReduceOp.PRODUCT, "max": dist.ReduceOp.MAX, "min": dist.ReduceOp.MIN,
+               "any": dist.ReduceOp.MAX, "all": dist.ReduceOp.MIN}[op]
+        dist.all_reduce(t, op=red)
+        out = t
+    return out.cpu().numpy()
+
+
+def combine_argreduce(op: str, value: float, local_index: int, shard_offset: int, device: Optional[str] = None) -> int:
+    """Full argmax/argmin of a row-sharded flattened tensor: all-gather (value, global index) pairs and apply the
+    reference's rule on the host — strict compare from lowest()/max(), first (lowest index) extreme wins, NaN never wins
+    (cpu_operations.cpp:2211-2228). `shard_offset` = number of elements that precede this shard in C order."""
+    import torch
+    dist = _dist()
+    pair = torch.tensor([float(value), float(local_index + shard_offset)], dtype=torch.float64)
+    if device:
+        pair = pair.to(device)
+    gathered = [torch.empty_like(pair) for _ in range(dist.get_world_size())]
+    dist.all_gather(gathered, pair)
+    best_val = -np.finfo(np.float64).max if op == "argmax" else np.finfo(np.float64).max
+    best_idx = 0
+    for g in sorted((g.cpu().numpy() for g in gathered), key=lambda a: a[1]):
+        v, i = float(g[0]), int(g[1])
+        if (op == "argmax" and v > best_val) or (op == "argmin" and v < best_val):
+            best_val, best_idx = v, i
+    return best_idx

@@ -49,8 +49,26 @@ def d2d(n=1<<28):
     med, mn = timeit(fn)
     return dict(workload="cudaMemcpy_d2d", ms_med=med, GBps_med=n*8/med/1e6, GBps_min=n*8/mn/1e6)
 
+def bmm(nb=64, m=4096, iters=5):
+    A = dev.cast(dev.randn((nb, m, m), 11), capi.BF16); B = dev.cast(dev.randn((nb, m, m), 12, 0.0, 1.0/64), capi.BF16)
+    C = dev.DeviceArray.empty((nb, m, m), capi.BF16)
+    ad, bd, cd = A.desc(), B.desc(), C.desc()
+    fn = lambda: capi.check(L.axb_matmul(ctypes.byref(ad), ctypes.byref(bd), 0, 0, None, ctypes.byref(cd), None))
+    med, mn = timeit(fn, iters=iters, warm=2)
+    fl = 2.0*nb*m**3
+    return dict(workload=f"bmm_bf16_{nb}x{m}", ms_med=med, TFLOPs_med=fl/med/1e9, TFLOPs_best=fl/mn/1e9)
+
+def bmm_nt(nb=64, m=4096, iters=5):
+    A = dev.cast(dev.randn((nb, m, m), 11), capi.BF16); B = dev.cast(dev.randn((nb, m, m), 12, 0.0, 1.0/64), capi.BF16)
+    C = dev.DeviceArray.empty((nb, m, m), capi.BF16)
+    ad, bd, cd = A.desc(), B.desc(), C.desc()
+    fn = lambda: capi.check(L.axb_matmul(ctypes.byref(ad), ctypes.byref(bd), 0, 1, None, ctypes.byref(cd), None))
+    med, mn = timeit(fn, iters=iters, warm=2)
+    fl = 2.0*nb*m**3
+    return dict(workload=f"bmm_nt_bf16_{nb}x{m}", ms_med=med, TFLOPs_med=fl/med/1e9, TFLOPs_best=fl/mn/1e9)
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["d2d", "relu", "exp", "gelu", "add", "c2"]
     for w in which:
-        r = d2d() if w == "d2d" else c2() if w == "c2" else add() if w == "add" else simple(w)
+        r = bmm() if w == "bmm" else bmm_nt() if w == "bmm_nt" else bmm(8, 4096) if w == "bmm8" else d2d() if w == "d2d" else c2() if w == "c2" else add() if w == "add" else simple(w)
         print(json.dumps(r), flush=True)
