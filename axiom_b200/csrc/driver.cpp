@@ -33,6 +33,7 @@ const Api *api() {
         ok = ok && resolve("cuGetErrorString", &g_api.GetErrorString);
         ok = ok && resolve("cuFuncSetAttribute", &g_api.FuncSetAttribute);
         ok = ok && resolve("cuTensorMapEncodeTiled", &g_api.TensorMapEncodeTiled);
+        ok = ok && resolve("cuOccupancyMaxActiveBlocksPerMultiprocessor", &g_api.OccupancyMaxActiveBlocksPerMultiprocessor);
         g_api.ok = ok;
     });
     if (!g_api.ok) {

@@ -48,7 +48,8 @@ struct Builder {
     Params &p;
     bool wide;
     int n_micro = 0, n_imm = 0;
-    std::string code;
+    std::string code, loads;
+    bool preloaded[kMaxIn] = {false, false, false, false, false, false, false, false};
     axb_status st = AXB_OK;
     explicit Builder(Params &pp, bool w) : p(pp), wide(w) {}
     void line(const std::string &s) {
@@ -67,7 +68,12 @@ struct Builder {
         char buf[512];
         switch (op) {
         case M_LOAD:
-            snprintf(buf, sizeof buf, "EW_LOAD(%u, %d, %s, %s)", a, (int)p.in[a].dtype, mode_name(p.in[a].mode), reg_name(b));
+            if (!preloaded[a]) { // every input is fetched once per vector, up front (ew_run issues these for U vectors)
+                preloaded[a] = true;
+                snprintf(buf, sizeof buf, "            EW_PRELOAD(%u, %d, %s)\n", a, (int)p.in[a].dtype, mode_name(p.in[a].mode));
+                loads += buf;
+            }
+            snprintf(buf, sizeof buf, "EW_USE(%u, %s)", a, reg_name(b));
             line(buf);
             return;
         case M_IMM:
@@ -470,7 +476,7 @@ uint32_t cmp_micro(int op) {
 
 // Lower the typed program to micro-ops. `src_dtype(k)` = dtype of input k.
 axb_status lower_program(const axb_instr *prog, int n_instr, const axb_tensor *inputs, int n_inputs, bool wide,
-                         Params &p, int *final_dtype, bool emit_store, std::string *code_out) {
+                         Params &p, int *final_dtype, bool emit_store, std::string *code_out, std::string *loads_out) {
     Builder B(p, wide);
     std::vector<int> last_use(n_instr, -1), n_uses(n_instr, 0), slot_of(n_instr, -1);
     for (int i = 0; i < n_instr; ++i) {
@@ -722,6 +728,7 @@ axb_status lower_program(const axb_instr *prog, int n_instr, const axb_tensor *i
         B.emit(M_STORE);
     AXB_TRY(B.st);
     *code_out = B.code;
+    *loads_out = B.loads;
     *final_dtype = prog[n_instr - 1].dtype;
     return AXB_OK;
 }
@@ -857,12 +864,15 @@ axb_status broadcast_all(const axb_tensor *inputs, int n_inputs, int64_t *oshape
 }
 
 // Full translation unit of one specialised kernel.
-std::string kernel_source(const std::string &body, bool wide, int n_outer) {
+std::string kernel_source(const std::string &loads, const std::string &body, bool wide, int vec, int n_outer, int n_inputs,
+                          int unroll) {
     std::string s = jit::ew_prelude_text();
-    char hdr[128];
-    snprintf(hdr, sizeof hdr, "\nEW_KERNEL_BEGIN(axb_ew, %d, %s, %d)\n", wide ? 4 : 8, wide ? "uint64_t" : "uint32_t", n_outer);
+    char hdr[160];
+    snprintf(hdr, sizeof hdr, "\nEW_KERNEL_BEGIN(axb_ew, %d, %s, %d, %d, %d)\n", vec, wide ? "uint64_t" : "uint32_t", n_outer,
+             n_inputs, unroll);
     s += hdr;
-    s += body;
+    s += "        EW_PRELOAD_BEGIN\n" + loads + "        EW_PRELOAD_END\n";
+    s += "        EW_COMPUTE_BEGIN\n" + body + "        EW_COMPUTE_END\n";
     s += "EW_KERNEL_END\n";
     return s;
 }
@@ -870,6 +880,7 @@ std::string kernel_source(const std::string &body, bool wide, int n_outer) {
 struct Prepared {
     Params p;
     std::string source;
+    int unroll = 1;
 };
 
 // Validates, plans the iteration space and generates the kernel text. No device needed.
@@ -913,14 +924,29 @@ axb_status prepare(const axb_instr *prog, int n_instr, const axb_tensor *inputs,
         return AXB_OK;
     Params &p = P->p;
     memset(&p, 0, sizeof(p));
-    const int vec = wide ? 4 : 8;
+    // elements per vector: 16 bytes of the widest element type that is streamed (so its access is ONE 128-bit
+    // instruction per thread and a warp covers a contiguous 512-byte span); narrower operands use 64/32-bit accesses
+    size_t widest = dtype_size(out->dtype);
+    for (int k = 0; k < n_inputs; ++k)
+        if (numel(inputs[k]) > 1)
+            widest = std::max(widest, dtype_size(inputs[k].dtype));
+    const int vec = wide ? 2 : (int)(16 / std::max<size_t>(widest, 1));
     AXB_TRY(plan_iteration(inputs, n_inputs, out, oshape, ondim, vec, p));
     int fdt = 0;
-    std::string body;
-    AXB_TRY(lower_program(prog, n_instr, inputs, n_inputs, wide, p, &fdt, true, &body));
+    std::string body, loads;
+    AXB_TRY(lower_program(prog, n_instr, inputs, n_inputs, wide, p, &fdt, true, &body, &loads));
     AXB_REQUIRE(fdt == out->dtype, AXB_ERR_INVALID, "axb_elementwise: last instruction yields dtype %d but out is %d", fdt,
                 out->dtype);
-    P->source = kernel_source(body, wide, (int)p.n_outer);
+    // loads in flight: U vectors per thread while the streamed (non-broadcast) operands fit the register budget
+    int streamed = 0;
+    for (int k = 0; k < n_inputs; ++k)
+        streamed += p.in[k].mode != MODE_BCAST;
+    // ~16 elements (8 for 64-bit words) per thread, fewer when many operands are streamed (register budget)
+    // measured on B200 (C2 chain: U=1 5.76, U=2 6.03, U=4 4.07 TB/s; single-input ops flat from U=1..8)
+    P->unroll = streamed <= 1 ? 4 : streamed <= 4 ? 2 : 1;
+    if (const char *env = getenv("AXB_EW_UNROLL")) // tuning knob (dev): overrides the vectors-per-thread heuristic
+        P->unroll = std::max(1, std::min(8, atoi(env)));
+    P->source = kernel_source(loads, body, wide, vec, (int)p.n_outer, n_inputs, P->unroll);
     return AXB_OK;
 }
 
@@ -945,10 +971,7 @@ axb_status axb_elementwise(const axb_instr *prog, int n_instr, const axb_tensor 
     jit::Kernel k;
     AXB_TRY(jit::get_kernel(P.source, "axb_ew", ctx->device, &k));
     const int threads = 256;
-    int64_t blocks = ((int64_t)P.p.total_vec + threads - 1) / threads;
-    const int64_t cap = (int64_t)ctx->sm_count * 16;
-    if (blocks > cap)
-        blocks = cap;
+    int64_t blocks = ((int64_t)P.p.total_vec + (int64_t)threads * P.unroll - 1) / ((int64_t)threads * P.unroll);
     if (blocks < 1)
         blocks = 1;
     void *args[] = {&P.p};

@@ -179,12 +179,25 @@ __device__ __forceinline__ void stg64(void *p, uint2 v) {
     asm volatile("st.global.L1::no_allocate.v2.u32 [%0], {%1,%2};" ::"l"(p), "r"(v.x), "r"(v.y) : "memory");
 }
 
+__device__ __forceinline__ uint32_t ldg32(const void *p) {
+    uint32_t r;
+    asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(r) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void stg32(void *p, uint32_t v) {
+    asm volatile("st.global.L1::no_allocate.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
 // Load VEC elements of operand `o` starting at element column `col` of the current run.
+// MODE_VEC: the VEC*sizeof(elem) bytes (4, 8, 16 or 32) are contiguous and aligned -> one (two for 32 B) streaming
+// vector load; consecutive threads own consecutive vectors, so a warp instruction covers one contiguous span.
 template <int VEC, typename W, int DT, int MODE>
 __device__ __forceinline__ void load_vec(const Operand &o, int64_t outer_off, uint32_t col, int valid,
                                          W (&r)[VEC]) {
     constexpr int dt = DT;
     constexpr int sz = dsize(dt);
+    constexpr int BYTES = VEC * sz;
+    constexpr int NW = BYTES >= 4 ? BYTES / 4 : 1;
     const char *base = o.ptr + outer_off;
     if (MODE == MODE_BCAST) {
         W v = canon<W>(ld_raw(base, sz), dt);
@@ -193,43 +206,38 @@ __device__ __forceinline__ void load_vec(const Operand &o, int64_t outer_off, ui
             r[i] = v;
         return;
     }
-    if (VEC == 8 && MODE == MODE_VEC && valid == VEC) {
+    if (MODE == MODE_VEC && valid == VEC && (BYTES == 4 || BYTES == 8 || BYTES == 16 || BYTES == 32)) {
         const char *p = base + (int64_t)col * sz;
-        if (sz == 4) {
+        uint32_t w[NW];
+        if (BYTES == 32) {
             uint4 a = ldg128(p), b = ldg128(p + 16);
-            r[0] = a.x; r[1] = a.y; r[2] = a.z; r[3] = a.w;
-            r[4 % VEC] = b.x; r[5 % VEC] = b.y; r[6 % VEC] = b.z; r[7 % VEC] = b.w;
-            return;
-        }
-        if (sz == 2) {
+            w[0] = a.x; w[1 % NW] = a.y; w[2 % NW] = a.z; w[3 % NW] = a.w;
+            w[4 % NW] = b.x; w[5 % NW] = b.y; w[6 % NW] = b.z; w[7 % NW] = b.w;
+        } else if (BYTES == 16) {
             uint4 a = ldg128(p);
-            uint32_t w[4] = {a.x, a.y, a.z, a.w};
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                r[(2 * i) % VEC] = canon<W>(w[i] & 0xFFFFu, dt);
-                r[(2 * i + 1) % VEC] = canon<W>(w[i] >> 16, dt);
-            }
-            return;
-        }
-        if (sz == 1) {
+            w[0] = a.x; w[1 % NW] = a.y; w[2 % NW] = a.z; w[3 % NW] = a.w;
+        } else if (BYTES == 8) {
             uint2 a = ldg64(p);
-            uint32_t w[2] = {a.x, a.y};
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-                r[i % VEC] = canon<W>((w[i >> 2] >> ((i & 3) * 8)) & 0xFFu, dt);
-            return;
+            w[0] = a.x; w[1 % NW] = a.y;
+        } else {
+            w[0] = ldg32(p);
         }
-    }
-    if (VEC == 4 && sizeof(W) == 8 && MODE == MODE_VEC && valid == VEC && sz == 8) {
-        const char *p = base + (int64_t)col * 8;
-        uint4 a = ldg128(p), b = ldg128(p + 16);
-        r[0] = (W)(((uint64_t)a.y << 32) | a.x);
-        r[1 % VEC] = (W)(((uint64_t)a.w << 32) | a.z);
-        r[2 % VEC] = (W)(((uint64_t)b.y << 32) | b.x);
-        r[3 % VEC] = (W)(((uint64_t)b.w << 32) | b.z);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+            uint64_t raw;
+            if (sz == 8)
+                raw = ((uint64_t)w[(2 * i + 1) % NW] << 32) | w[(2 * i) % NW];
+            else if (sz == 4)
+                raw = w[i % NW];
+            else if (sz == 2)
+                raw = (w[(i / 2) % NW] >> (16 * (i % 2))) & 0xFFFFu;
+            else
+                raw = (w[(i / 4) % NW] >> (8 * (i % 4))) & 0xFFu;
+            r[i] = canon<W>(raw, dt);
+        }
         return;
     }
-    const int64_t is = o.inner_stride;
+    const int64_t is = (MODE == MODE_VEC) ? (int64_t)sz : o.inner_stride;
 #pragma unroll
     for (int i = 0; i < VEC; ++i) {
         r[i] = 0;
@@ -243,42 +251,42 @@ __device__ __forceinline__ void store_vec(const Operand &o, int64_t outer_off, u
                                           const W (&r)[VEC]) {
     constexpr int dt = DT;
     constexpr int sz = dsize(dt);
+    constexpr int BYTES = VEC * sz;
+    constexpr int NW = BYTES >= 4 ? BYTES / 4 : 1;
     char *base = const_cast<char *>(o.ptr) + outer_off;
-    if (VEC == 8 && MODE == MODE_VEC && valid == VEC) {
+    if (MODE == MODE_VEC && valid == VEC && (BYTES == 4 || BYTES == 8 || BYTES == 16 || BYTES == 32)) {
         char *p = base + (int64_t)col * sz;
-        if (sz == 4) {
-            stg128(p, make_uint4((uint32_t)r[0], (uint32_t)r[1 % VEC], (uint32_t)r[2 % VEC], (uint32_t)r[3 % VEC]));
-            stg128(p + 16,
-                   make_uint4((uint32_t)r[4 % VEC], (uint32_t)r[5 % VEC], (uint32_t)r[6 % VEC], (uint32_t)r[7 % VEC]));
-            return;
-        }
-        if (sz == 2) {
-            uint32_t w[4];
+        uint32_t w[NW];
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
-                w[i] = (uint32_t)(decanon<W>(r[(2 * i) % VEC], dt) & 0xFFFFu) |
-                       ((uint32_t)(decanon<W>(r[(2 * i + 1) % VEC], dt) & 0xFFFFu) << 16);
-            stg128(p, make_uint4(w[0], w[1], w[2], w[3]));
-            return;
-        }
-        if (sz == 1) {
-            uint32_t w[2] = {0, 0};
+        for (int k = 0; k < NW; ++k)
+            w[k] = 0;
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
-                w[i >> 2] |= (uint32_t)(decanon<W>(r[i % VEC], dt) & 0xFFu) << ((i & 3) * 8);
-            stg64(p, make_uint2(w[0], w[1]));
-            return;
+        for (int i = 0; i < VEC; ++i) {
+            const uint64_t raw = decanon<W>(r[i], dt);
+            if (sz == 8) {
+                w[(2 * i) % NW] = (uint32_t)raw;
+                w[(2 * i + 1) % NW] = (uint32_t)(raw >> 32);
+            } else if (sz == 4) {
+                w[i % NW] = (uint32_t)raw;
+            } else if (sz == 2) {
+                w[(i / 2) % NW] |= ((uint32_t)raw & 0xFFFFu) << (16 * (i % 2));
+            } else {
+                w[(i / 4) % NW] |= ((uint32_t)raw & 0xFFu) << (8 * (i % 4));
+            }
         }
-    }
-    if (VEC == 4 && sizeof(W) == 8 && MODE == MODE_VEC && valid == VEC && sz == 8) {
-        char *p = base + (int64_t)col * 8;
-        stg128(p, make_uint4((uint32_t)r[0], (uint32_t)((uint64_t)r[0] >> 32), (uint32_t)r[1 % VEC],
-                             (uint32_t)((uint64_t)r[1 % VEC] >> 32)));
-        stg128(p + 16, make_uint4((uint32_t)r[2 % VEC], (uint32_t)((uint64_t)r[2 % VEC] >> 32), (uint32_t)r[3 % VEC],
-                                  (uint32_t)((uint64_t)r[3 % VEC] >> 32)));
+        if (BYTES == 32) {
+            stg128(p, make_uint4(w[0], w[1 % NW], w[2 % NW], w[3 % NW]));
+            stg128(p + 16, make_uint4(w[4 % NW], w[5 % NW], w[6 % NW], w[7 % NW]));
+        } else if (BYTES == 16) {
+            stg128(p, make_uint4(w[0], w[1 % NW], w[2 % NW], w[3 % NW]));
+        } else if (BYTES == 8) {
+            stg64(p, make_uint2(w[0], w[1 % NW]));
+        } else {
+            stg32(p, w[0]);
+        }
         return;
     }
-    const int64_t is = o.inner_stride;
+    const int64_t is = (MODE == MODE_VEC) ? (int64_t)sz : o.inner_stride;
 #pragma unroll
     for (int i = 0; i < VEC; ++i)
         if (i < valid)
@@ -482,9 +490,16 @@ __device__ __forceinline__ int64_t l_mod(int64_t a, int64_t b) { return b == 0 ?
 
 
 // ---- statements emitted by the host code generator (elementwise.cu) --------------------------------------
-// All of them run inside EW_KERNEL_BEGIN/END, which declares: p (Params), VEC, W, c[] (outer coordinates),
-// col, valid and the register arrays acc/t/u/s0..s3.
-#define EW_OUTER_OFF(o) outer_off<NOUT>((o), c)
+// A specialised kernel is two lambdas over a per-vector context `x` (outer coordinates, column, valid count and
+// the raw input vectors):  preload(x) issues every global load of one vector, compute(x) runs the chain and stores.
+// ew_run() calls preload for U vectors before the first compute, so U x (inputs) 128-bit loads are in flight per thread.
+template <typename W, int VEC, int NIN> struct Ctx {
+    uint32_t c[kMaxOuter];
+    uint32_t col;
+    int valid;
+    bool ok;
+    W in[NIN > 0 ? NIN : 1][VEC];
+};
 template <int NOUT> __device__ __forceinline__ int64_t outer_off(const Operand &o, const uint32_t (&c)[kMaxOuter]) {
     int64_t off = 0;
 #pragma unroll
@@ -492,8 +507,12 @@ template <int NOUT> __device__ __forceinline__ int64_t outer_off(const Operand &
         off += (int64_t)c[d] * o.stride[d];
     return off;
 }
-#define EW_LOAD(K, DT, MODE, DST) load_vec<VEC, W, DT, MODE>(p.in[K], EW_OUTER_OFF(p.in[K]), col, valid, DST);
-#define EW_STORE(DT, MODE) store_vec<VEC, W, DT, MODE>(p.out, EW_OUTER_OFF(p.out), col, valid, acc);
+#define EW_PRELOAD(K, DT, MODE) load_vec<VEC, W, DT, MODE>(p.in[K], outer_off<NOUT>(p.in[K], x.c), x.col, x.valid, x.in[K]);
+#define EW_USE(K, DST)                                                                                  \
+    {                                                                                                   \
+        _Pragma("unroll") for (int i = 0; i < VEC; ++i) DST[i] = x.in[K][i];                            \
+    }
+#define EW_STORE(DT, MODE) store_vec<VEC, W, DT, MODE>(p.out, outer_off<NOUT>(p.out, x.c), x.col, x.valid, acc);
 #define EW_IMM(K, DST)                                                                                  \
     {                                                                                                   \
         const W v_ = (W)p.imm[K];                                                                       \
@@ -534,37 +553,65 @@ template <int NOUT> __device__ __forceinline__ int64_t outer_off(const Operand &
         STMT                                                                                            \
     }
 
-// Grid-stride loop over the collapsed iteration space: one VEC-wide vector of one innermost run per iteration.
-#define EW_KERNEL_BEGIN(NAME, VEC_, WTYPE, NOUT_)                                                       \
+// One CTA owns 256*U consecutive vectors (VEC elements of one innermost run each): thread t handles vectors
+// t, t+256, ... so every warp-level access is one contiguous span, and all U x (inputs) loads are issued before the
+// first use. No grid-stride loop: a large grid of short CTAs measured faster than a persistent one on B200
+// (tools/stream_probe.cu, profiles/r1_stream_probe.txt: 6.8 TB/s vs 6.0 TB/s for y = relu(x)).
+template <int VEC, typename W, int NOUT, int NIN, int U, class FL, class FC>
+__device__ __forceinline__ void ew_run(const Params &p, FL &&preload, FC &&compute) {
+    const uint32_t v0 = blockIdx.x * (256u * U) + threadIdx.x;
+    Ctx<W, VEC, NIN> x[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const uint32_t vi = v0 + u * 256u;
+        x[u].ok = vi < p.total_vec;
+        if (x[u].ok) {
+            uint32_t row = (NOUT > 0) ? fastdiv(vi, p.div_m[0], p.div_s[0]) : 0u;
+            x[u].col = (vi - row * p.nvec_inner) * VEC;
+            x[u].valid = (int)min((uint32_t)VEC, p.inner_len - x[u].col);
+#pragma unroll
+            for (int d = 0; d < kMaxOuter; ++d) {
+                x[u].c[d] = 0;
+                if (d < NOUT) {
+                    if (d == NOUT - 1) {
+                        x[u].c[d] = row;
+                    } else {
+                        uint32_t q = fastdiv(row, p.div_m[1 + d], p.div_s[1 + d]);
+                        x[u].c[d] = row - q * p.outer_shape[d];
+                        row = q;
+                    }
+                }
+            }
+            preload(x[u]);
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+        if (x[u].ok)
+            compute(x[u]);
+}
+
+#define EW_KERNEL_BEGIN(NAME, VEC_, WTYPE, NOUT_, NIN_, U_)                                             \
     extern "C" __global__ void __launch_bounds__(256) NAME(const __grid_constant__ axb::ew::Params p) { \
         using namespace axb::ew;                                                                        \
-        constexpr int VEC = VEC_;                                                                       \
-        constexpr int NOUT = NOUT_;                                                                     \
+        constexpr int VEC = VEC_, NOUT = NOUT_, NIN = NIN_, U = U_;                                     \
         typedef WTYPE W;                                                                                \
-        const uint32_t stride_ = gridDim.x * blockDim.x;                                                \
-        for (uint32_t vi = blockIdx.x * blockDim.x + threadIdx.x; vi < p.total_vec; vi += stride_) {    \
-            uint32_t row = (NOUT > 0) ? fastdiv(vi, p.div_m[0], p.div_s[0]) : 0u;                       \
-            const uint32_t col = (vi - row * p.nvec_inner) * VEC;                                       \
-            const int valid = (int)min((uint32_t)VEC, p.inner_len - col);                               \
-            uint32_t c[kMaxOuter];                                                                      \
-            _Pragma("unroll") for (int d = 0; d < kMaxOuter; ++d) {                                     \
-                c[d] = 0;                                                                               \
-                if (d < NOUT) {                                                                         \
-                    if (d == NOUT - 1) {                                                                \
-                        c[d] = row;                                                                     \
-                    } else {                                                                            \
-                        uint32_t q = fastdiv(row, p.div_m[1 + d], p.div_s[1 + d]);                      \
-                        c[d] = row - q * p.outer_shape[d];                                              \
-                        row = q;                                                                        \
-                    }                                                                                   \
-                }                                                                                       \
-            }                                                                                           \
-            W acc[VEC], t[VEC], u[VEC], s0[VEC], s1[VEC], s2[VEC], s3[VEC];                             \
-            _Pragma("unroll") for (int i = 0; i < VEC; ++i) {                                           \
-                acc[i] = t[i] = u[i] = s0[i] = s1[i] = s2[i] = s3[i] = 0;                               \
-            }
+        typedef Ctx<W, VEC, NIN> X;
+#define EW_PRELOAD_BEGIN auto preload = [&](X &x) {
+#define EW_PRELOAD_END                                                                                  \
+    }                                                                                                   \
+    ;
+#define EW_COMPUTE_BEGIN                                                                                \
+    auto compute = [&](X &x) {                                                                          \
+        W acc[VEC], t[VEC], u[VEC], s0[VEC], s1[VEC], s2[VEC], s3[VEC];                                 \
+        _Pragma("unroll") for (int i = 0; i < VEC; ++i) {                                               \
+            acc[i] = t[i] = u[i] = s0[i] = s1[i] = s2[i] = s3[i] = 0;                                   \
+        }
+#define EW_COMPUTE_END                                                                                  \
+    }                                                                                                   \
+    ;
 #define EW_KERNEL_END                                                                                   \
-        }                                                                                               \
+        ew_run<VEC, W, NOUT, NIN, U>(p, preload, compute);                                              \
     }
 
 } // namespace ew

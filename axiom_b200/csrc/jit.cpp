@@ -27,7 +27,7 @@ const char kPrelude[] =
 #include "ew_prelude_embed.inc"
     ;
 
-const char kCacheTag[] = "axb-jit-v1 nvrtc sm_100a -std=c++17 --fmad=false";
+const char kCacheTag[] = "axb-jit-v3 nvrtc sm_100a -std=c++17 --fmad=false";
 
 uint64_t fnv1a(const void *data, size_t n, uint64_t h = 1469598103934665603ull) {
     const unsigned char *p = static_cast<const unsigned char *>(data);
@@ -220,6 +220,8 @@ axb_status get_kernel(const std::string &source, const char *name, int device, K
     r = d->ModuleGetFunction(&k.fn, mod, name);
     if (r != CUDA_SUCCESS)
         return fail(AXB_ERR_CUDA, "specialised kernel '%s' not found in module", name);
+    if (d->OccupancyMaxActiveBlocksPerMultiprocessor)
+        d->OccupancyMaxActiveBlocksPerMultiprocessor(&k.blocks_per_sm, k.fn, 256, 0);
     g_kernels[{h, device}] = k;
     *out = k;
     return AXB_OK;

@@ -16,6 +16,7 @@ namespace jit {
 
 struct Kernel {
     CUfunction fn = nullptr;
+    int blocks_per_sm = 0; // resident 256-thread CTAs per SM (occupancy query at load time)
 };
 
 // text of ew_prelude.cuh + hwy_math.cuh embedded at build time
