@@ -159,36 +159,52 @@ __global__ void __launch_bounds__(256) argreduce_rows_kernel(const __grid_consta
         const int64_t r0 = (int64_t)blockIdx.y * p.chunk;
         const int64_t r1 = min(p.n_red, r0 + p.chunk);
         if (CONTIG) {
+            // Each thread visits its elements in INCREASING index order, so "strictly better replaces" keeps the first
+            // extremum exactly like the reference's serial loop (cpu_operations.cpp:2213-2222) at 3 instructions per
+            // element (compare, select value, select 32-bit offset); NaN never compares better. Four independent scans
+            // (one per in-flight 128-bit load) are merged with the tie -> lower index rule. Offsets are 32-bit relative
+            // to a window start, windows of 2^30 elements keep them in range for any row length.
             constexpr int V = 16 / sizeof(In);
             const In *src = reinterpret_cast<const In *>(base);
-            const int64_t mis = (int64_t)((reinterpret_cast<uintptr_t>(src + r0) & 15) / sizeof(In));
-            const int64_t head_end = min(r1, mis ? r0 + (V - mis) : r0);
-            for (int64_t i = r0 + lane; i < head_end; i += TPR)
-                acc = Op::combine(acc, Op::make(load_as<In, Cmp>(src[i]), i));
-            const int64_t nvec = (r1 - head_end) / V;
-            const uint4 *v = reinterpret_cast<const uint4 *>(src + head_end);
-            int64_t i = lane;
-            for (; i + 3 * TPR < nvec; i += 4 * TPR) {
-                uint4 q[4] = {ldg_stream(v + i), ldg_stream(v + i + TPR), ldg_stream(v + i + 2 * TPR),
-                              ldg_stream(v + i + 3 * TPR)};
+            for (int64_t w0 = r0; w0 < r1; w0 += (int64_t)1 << 30) {
+                const int64_t w1 = min(r1, w0 + ((int64_t)1 << 30));
+                ArgScan<Cmp, IS_MAX> s0, s1, s2, s3;
+                s0.init(); s1.init(); s2.init(); s3.init();
+                const int64_t mis = (int64_t)((reinterpret_cast<uintptr_t>(src + w0) & 15) / sizeof(In));
+                const int64_t head_end = min(w1, mis ? w0 + (V - mis) : w0);
+                for (int64_t i = w0 + lane; i < head_end; i += TPR)
+                    s0.take(load_as<In, Cmp>(src[i]), (uint32_t)(i - w0));
+                const uint32_t hoff = (uint32_t)(head_end - w0);
+                const uint32_t nvec = (uint32_t)((w1 - head_end) / V);
+                const uint4 *v = reinterpret_cast<const uint4 *>(src + head_end);
+                uint32_t i = lane;
+                for (; i + 3 * TPR < nvec; i += 4 * TPR) {
+                    const uint4 q0 = ldg_stream(v + i), q1 = ldg_stream(v + i + TPR), q2 = ldg_stream(v + i + 2 * TPR),
+                                q3 = ldg_stream(v + i + 3 * TPR);
+                    const In *e0 = reinterpret_cast<const In *>(&q0), *e1 = reinterpret_cast<const In *>(&q1),
+                             *e2 = reinterpret_cast<const In *>(&q2), *e3 = reinterpret_cast<const In *>(&q3);
+                    const uint32_t o = hoff + i * V;
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const In *w = reinterpret_cast<const In *>(&q[u]);
-                    const int64_t e0 = head_end + (i + (int64_t)u * TPR) * V;
+                    for (int k = 0; k < V; ++k) {
+                        s0.take(load_as<In, Cmp>(e0[k]), o + k);
+                        s1.take(load_as<In, Cmp>(e1[k]), o + TPR * V + k);
+                        s2.take(load_as<In, Cmp>(e2[k]), o + 2 * TPR * V + k);
+                        s3.take(load_as<In, Cmp>(e3[k]), o + 3 * TPR * V + k);
+                    }
+                }
+                acc = Op::combine(acc, s0.pair(w0)); // head + stream 0 so far: all below the remainder in index order
+                s0.init();
+                for (; i < nvec; i += TPR) {
+                    const uint4 q = ldg_stream(v + i);
+                    const In *e = reinterpret_cast<const In *>(&q);
 #pragma unroll
                     for (int k = 0; k < V; ++k)
-                        acc = Op::combine(acc, Op::make(load_as<In, Cmp>(w[k]), e0 + k));
+                        s0.take(load_as<In, Cmp>(e[k]), hoff + i * V + k);
                 }
+                for (int64_t j = head_end + (int64_t)nvec * V + lane; j < w1; j += TPR)
+                    s0.take(load_as<In, Cmp>(src[j]), (uint32_t)(j - w0));
+                acc = Op::combine(acc, Op::combine(Op::combine(s0.pair(w0), s1.pair(w0)), Op::combine(s2.pair(w0), s3.pair(w0))));
             }
-            for (; i < nvec; i += TPR) {
-                uint4 q = ldg_stream(v + i);
-                const In *w = reinterpret_cast<const In *>(&q);
-#pragma unroll
-                for (int k = 0; k < V; ++k)
-                    acc = Op::combine(acc, Op::make(load_as<In, Cmp>(w[k]), head_end + i * V + k));
-            }
-            for (int64_t j = head_end + nvec * V + lane; j < r1; j += TPR)
-                acc = Op::combine(acc, Op::make(load_as<In, Cmp>(src[j]), j));
         } else {
             for (int64_t r = r0 + lane; r < r1; r += TPR) {
                 const In *e = reinterpret_cast<const In *>(base + reduced_offset(p, r));

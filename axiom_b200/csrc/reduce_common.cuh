@@ -263,6 +263,24 @@ template <typename C, bool IS_MAX> struct ArgOp {
         return take_b ? b : a;
     }
 };
+// Per-thread scan over elements presented in increasing index order (32-bit offsets relative to a window start).
+template <typename C, bool IS_MAX> struct ArgScan {
+    C best;
+    uint32_t off;
+    __device__ __forceinline__ void init() {
+        best = IS_MAX ? Limits<C>::lowest() : Limits<C>::highest();
+        off = 0;
+    }
+    __device__ __forceinline__ void take(C v, uint32_t o) {
+        const bool t = IS_MAX ? (v > best) : (v < best);
+        best = t ? v : best;
+        off = t ? o : off;
+    }
+    __device__ __forceinline__ ArgPair<C> pair(int64_t window_start) const {
+        const bool hit = IS_MAX ? (best > Limits<C>::lowest()) : (best < Limits<C>::highest());
+        return hit ? ArgPair<C>{best, window_start + (int64_t)off} : ArgOp<C, IS_MAX>::identity();
+    }
+};
 template <typename C, class Op, int TPR> __device__ __forceinline__ ArgPair<C> group_reduce_pair(ArgPair<C> a) {
 #pragma unroll
     for (int d = 16; d >= 1; d >>= 1) {

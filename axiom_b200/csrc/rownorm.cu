@@ -17,6 +17,8 @@
 // Half inputs: the CPU path rounds mean (layer_norm) and x*x, ms (rms_norm) to the half type because those steps run
 // in the input dtype (bfloat16.hpp:55-66, cpu_operations.cpp:1613-1614); mirrored here. Sums are trees, not the
 // reference's serial / lane-strided order: results agree to rounding (tests use the north_star's 1e-5 bound).
+#include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include "axb_internal.h"
@@ -43,6 +45,9 @@ struct RowParams {
     int32_t vec_ok;        // rows contiguous and suitably aligned -> vector accesses
     int32_t in_dtype, out_dtype, w_dtype, b_dtype;
     float eps;
+    // wide-row (TMA-staged) kernel only: row length in 16-byte vectors, vectors per warp, smem stages, weight/bias sweep
+    // order alternates between rows
+    int32_t nv, vpw, stages, wb_alternate;
 };
 
 __device__ __forceinline__ void row_offsets(const RowParams &p, int64_t row, int64_t *in_off, int64_t *out_off) {
@@ -276,11 +281,101 @@ __global__ void __launch_bounds__(THREADS == 32 ? 256 : THREADS) rownorm_kernel(
     }
 }
 
+} // namespace rown
+} // namespace axb
+#include "rownorm_wide.cuh"
+namespace axb {
+namespace rown {
+
 namespace {
+
+// Wide contiguous rows (>= 16 KiB, <= 32 values per lane of a 1024-thread CTA): persistent TMA-staged kernel.
+template <typename In, typename Out, typename W, int KIND>
+bool launch_wide_typed(RowParams p, DeviceCtx *ctx, cudaStream_t s, axb_status *st);
+
+template <typename In, typename Out, int KIND> bool try_launch_wide(const RowParams &p, DeviceCtx *ctx, cudaStream_t s, axb_status *st) {
+    // weight and bias must share one dtype class: the input's, or Float32 (what nn::LayerNorm holds for half inputs)
+    const int wdt = p.w ? p.w_dtype : (p.b ? p.b_dtype : p.in_dtype);
+    if (p.w && p.b && p.w_dtype != p.b_dtype)
+        return false;
+    if (wdt == p.in_dtype)
+        return launch_wide_typed<In, Out, In, KIND>(p, ctx, s, st);
+    if constexpr (KIND == K_LAYER_NORM || KIND == K_RMS_NORM) {
+        if (wdt == AXB_F32)
+            return launch_wide_typed<In, Out, float, KIND>(p, ctx, s, st);
+    }
+    return false;
+}
+
+template <typename In, typename Out, typename W, int KIND>
+bool launch_wide_typed(RowParams p, DeviceCtx *ctx, cudaStream_t s, axb_status *st) {
+    constexpr int E = 16 / (int)sizeof(In);
+    const int64_t isz = sizeof(In), osz = sizeof(Out);
+    if (p.in_es != isz || p.out_es != osz || ((int64_t)p.n * isz) % 16 != 0)
+        return false;
+    const int64_t nv = (int64_t)p.n * isz / 16;
+    if (nv < 1024 || nv > 1024 * (32 / E))
+        return false;
+    auto al16 = [](const void *q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
+    if (!al16(p.in) || !al16(p.out))
+        return false;
+    for (int d = 0; d < p.nk; ++d)
+        if (p.in_kstride[d] % 16 != 0 || p.out_kstride[d] % 16 != 0)
+            return false;
+    auto wb_ok = [&](const char *q, int64_t es, int dt) { return !q || (al16(q) && es == (int64_t)dtype_size(dt)); };
+    if (!wb_ok(p.w, p.w_es, p.w_dtype) || !wb_ok(p.b, p.b_es, p.b_dtype))
+        return false;
+    static const bool disabled = getenv("AXB_NO_WIDE_ROWS") != nullptr; // A/B switch for profiling
+    if (disabled)
+        return false;
+    p.nv = (int)nv;
+    p.vpw = (int)((nv + kWideWarps - 1) / kWideWarps);
+    const int j_need = (p.vpw + 31) / 32;
+    const size_t budget = ctx->smem_optin - 2048; // static: mbarriers + reduction scratch
+    const size_t row_bytes = (size_t)nv * 16;
+    p.stages = (int)std::min<size_t>(kWideMaxStages, budget / row_bytes);
+    if (p.stages < 1)
+        return false;
+    if (const char *e = getenv("AXB_WIDE_STAGES"))
+        p.stages = std::max(1, std::min(p.stages, atoi(e)));
+    static const bool no_alt = getenv("AXB_WB_NO_ALTERNATE") != nullptr;
+    p.wb_alternate = no_alt ? 0 : 1;
+    const size_t dyn = (size_t)p.stages * row_bytes;
+    const unsigned grid = (unsigned)std::min<int64_t>(p.rows, ctx->sm_count);
+    auto go = [&](auto kern) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+        if (e != cudaSuccess) {
+            *st = fail(AXB_ERR_CUDA, "wide row kernel: cannot reserve %zu bytes of shared memory: %s", dyn, cudaGetErrorString(e));
+            return;
+        }
+        kern<<<grid, kWideThreads, dyn, s>>>(p);
+        cudaError_t le = cudaGetLastError();
+        if (le != cudaSuccess) {
+            *st = fail(AXB_ERR_CUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(le), __FILE__, __LINE__);
+            return;
+        }
+        count_launch();
+        *st = AXB_OK;
+    };
+    constexpr int JMAX = 32 / E;
+    const bool exact = p.vpw == JMAX * 32 && nv == (int64_t)kWideWarps * p.vpw;
+    if (exact)
+        go(rowwide_kernel<In, Out, W, KIND, JMAX, true>);
+    else if (j_need * 4 <= JMAX && JMAX >= 4)
+        go(rowwide_kernel<In, Out, W, KIND, (JMAX >= 4 ? JMAX / 4 : 1), false>);
+    else if (j_need * 2 <= JMAX)
+        go(rowwide_kernel<In, Out, W, KIND, JMAX / 2, false>);
+    else
+        go(rowwide_kernel<In, Out, W, KIND, JMAX, false>);
+    return true;
+}
 
 template <typename In, typename Out, int KIND> axb_status launch_cfg(const RowParams &p, DeviceCtx *ctx, cudaStream_t s) {
     const int n = p.n;
     const int64_t max_ctas = (int64_t)ctx->sm_count * 32;
+    axb_status wst = AXB_OK;
+    if (try_launch_wide<In, Out, KIND>(p, ctx, s, &wst))
+        return wst;
     if (n <= 256) {
         int64_t g = std::min<int64_t>((p.rows + 7) / 8, max_ctas);
         rownorm_kernel<In, Out, 32, 8, KIND, true><<<(unsigned)g, 256, 0, s>>>(p);

@@ -1,0 +1,433 @@
+// rownorm_wide.cuh — TMA-staged persistent kernel for WIDE contiguous rows of softmax / log_softmax / layer_norm /
+// rms_norm (included by rownorm.cu; same numerics contract as the generic kernel there).
+//
+// Why a second kernel: at n = 32 768 a row is 128 KiB of fp32 — half an SM's register file — so only ONE CTA fits per
+// SM and the generic kernel's load -> reduce -> exp -> reduce -> store phases serialise (ncu r1: 36 % of HBM peak, 47
+// warp-instructions per element). Here one persistent 1024-thread CTA per SM keeps the NEXT rows in flight while the
+// current row is being computed:
+//   * each warp owns a fixed slice of the row; lane 0 fetches that slice with one 1-D bulk copy
+//     (cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes) into a per-stage shared-memory row buffer and
+//     the warp waits on its own mbarrier — no block-wide barrier on the load path;
+//   * the slice is moved to registers (conflict-free LDS.128), and the warp immediately re-arms the same buffer with the
+//     row `stages` iterations ahead, so HBM reads overlap all of the arithmetic and the stores of the current row;
+//   * block reductions: warp shuffles + one shared-memory hop, ping-pong scratch => ONE __syncthreads per reduction;
+//   * divisions are hoisted (one IEEE reciprocal per row), results leave through 128-bit streaming stores.
+// Algorithmic traffic stays in + out (+ weight/bias, which are re-read per row through L1/L2).
+#pragma once
+#include <type_traits>
+
+namespace axb {
+namespace rown {
+
+__device__ __forceinline__ uint32_t w_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void w_mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void w_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void w_mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done)
+                     : "r"(bar), "r"(parity)
+                     : "memory");
+    } while (!done);
+}
+// 1-D bulk copy global -> shared (TMA engine, no tensor map): 16-byte aligned addresses, size % 16 == 0
+__device__ __forceinline__ void w_bulk_load(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+                 "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ uint4 w_lds128(uint32_t addr) {
+    uint4 r;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
+    return r;
+}
+__device__ __forceinline__ float w_ex2(float x) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+__device__ __forceinline__ float w_max_nan(float a, float b) {
+    float r;
+    asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ float w_max3_nan(float a, float b, float c) {
+    float r;
+    asm("max.NaN.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+    return r;
+}
+// exp(d) for d <= 0 (softmax numerator), 6 instructions instead of expf's 9: t = fl(d*log2e); the rounding error of
+// that product is recovered exactly by one FMA and applied as a first-order correction, e = 2^t * (1 + r*ln2).
+// Error <= ~3 ulp (MUFU.EX2 2 ulp + log2e's own representation error |d|*1.9e-8*ln2), far inside the 1e-5 contract.
+// d is clamped (NaN-preserving) at -104: below that exp(d) < 2^-150 rounds to 0 anyway, and -inf (masked attention
+// scores) gives an exact 0 instead of inf - inf = NaN in the residual.
+__device__ __forceinline__ float w_exp_neg(float d) {
+    d = w_max_nan(d, -104.0f);
+    const float t = __fmul_rn(d, 1.4426950408889634f);
+    const float r = __fmaf_rn(d, 1.4426950408889634f, -t);
+    const float e = w_ex2(t);
+    return __fmaf_rn(__fmul_rn(e, r), 0.6931471805599453f, e);
+}
+
+// 16 bytes -> E floats
+template <typename T> struct Vec16;
+template <> struct Vec16<float> {
+    static constexpr int E = 4;
+    __device__ static void unpack(uint4 q, float *v) {
+        v[0] = __uint_as_float(q.x); v[1] = __uint_as_float(q.y); v[2] = __uint_as_float(q.z); v[3] = __uint_as_float(q.w);
+    }
+};
+template <> struct Vec16<bf16_t> {
+    static constexpr int E = 8;
+    __device__ static void unpack(uint4 q, float *v) {
+        v[0] = __uint_as_float(q.x << 16); v[1] = __uint_as_float(q.x & 0xFFFF0000u);
+        v[2] = __uint_as_float(q.y << 16); v[3] = __uint_as_float(q.y & 0xFFFF0000u);
+        v[4] = __uint_as_float(q.z << 16); v[5] = __uint_as_float(q.z & 0xFFFF0000u);
+        v[6] = __uint_as_float(q.w << 16); v[7] = __uint_as_float(q.w & 0xFFFF0000u);
+    }
+};
+template <> struct Vec16<f16_t> {
+    static constexpr int E = 8;
+    __device__ static void unpack(uint4 q, float *v) {
+        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            v[2 * i] = h2f((uint16_t)(w[i] & 0xFFFFu));
+            v[2 * i + 1] = h2f((uint16_t)(w[i] >> 16));
+        }
+    }
+};
+// two finite-or-not floats -> packed bf16 pair with the hardware converter (RNE). NaN comes out as 0x7FFF, so callers
+// only use it where a NaN cannot occur (softmax handles NaN rows separately); everything else goes through f2bf.
+__device__ __forceinline__ uint32_t pack_bf16x2_hw(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+// E floats -> E Out elements at dst (16-byte aligned), streaming stores
+template <typename Out, int E, bool HW> __device__ __forceinline__ void store_vec(char *dst, const float *v) {
+    if constexpr (sizeof(Out) == 4) {
+#pragma unroll
+        for (int i = 0; i < E; i += 4)
+            stg_stream(reinterpret_cast<uint4 *>(dst + i * 4), make_uint4(__float_as_uint(v[i]), __float_as_uint(v[i + 1]),
+                                                                       __float_as_uint(v[i + 2]), __float_as_uint(v[i + 3])));
+    } else {
+        uint32_t w[E / 2];
+#pragma unroll
+        for (int i = 0; i < E / 2; ++i) {
+            if constexpr (HW && sizeof(Out) == 2 && std::is_same<Out, bf16_t>::value) {
+                w[i] = pack_bf16x2_hw(v[2 * i], v[2 * i + 1]);
+            } else if constexpr (std::is_same<Out, bf16_t>::value) {
+                w[i] = (uint32_t)f2bf(v[2 * i]) | ((uint32_t)f2bf(v[2 * i + 1]) << 16);
+            } else {
+                w[i] = (uint32_t)f2h(v[2 * i]) | ((uint32_t)f2h(v[2 * i + 1]) << 16);
+            }
+        }
+        if constexpr (E == 8) {
+            stg_stream(reinterpret_cast<uint4 *>(dst), make_uint4(w[0], w[1], w[2], w[3]));
+        } else { // E == 4: fp32 input, half output
+            stg64_stream(dst, make_uint2(w[0], w[1]));
+        }
+    }
+}
+// E consecutive weight/bias values of type W (16-byte aligned vectors), cached loads: every row re-reads them, so they
+// should stay in L1/L2
+template <typename W, int E> __device__ __forceinline__ void load_wb(const char *base, int e0, float *v) {
+    if constexpr (sizeof(W) == 4) {
+#pragma unroll
+        for (int i = 0; i < E; i += 4) {
+            const float4 q = __ldg(reinterpret_cast<const float4 *>(base + (int64_t)(e0 + i) * 4));
+            v[i] = q.x; v[i + 1] = q.y; v[i + 2] = q.z; v[i + 3] = q.w;
+        }
+    } else if constexpr (E == 8) {
+        Vec16<W>::unpack(__ldg(reinterpret_cast<const uint4 *>(base + (int64_t)e0 * 2)), v);
+    } else {
+        const uint2 q = __ldg(reinterpret_cast<const uint2 *>(base + (int64_t)e0 * 2));
+        float t[8];
+        Vec16<W>::unpack(make_uint4(q.x, q.y, 0u, 0u), t);
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            v[i] = t[i];
+    }
+}
+
+template <int N, class F> __device__ __forceinline__ void static_for_up(F &f) {
+    if constexpr (N > 0) {
+        static_for_up<N - 1>(f);
+        f(std::integral_constant<int, N - 1>{});
+    }
+}
+template <int N, class F> __device__ __forceinline__ void static_for_down(F &f) {
+    if constexpr (N > 0) {
+        f(std::integral_constant<int, N - 1>{});
+        static_for_down<N - 1>(f);
+    }
+}
+
+constexpr int kWideThreads = 1024;
+constexpr int kWideWarps = kWideThreads / 32;
+constexpr int kWideMaxStages = 4;
+
+// block all-reduce over 1024 threads: one __syncthreads (scratch ping-pongs between consecutive reductions)
+template <class F> __device__ __forceinline__ float wide_allreduce(float v, float (*scratch)[kWideWarps], int &flip) {
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1)
+        v = F::apply(v, __shfl_xor_sync(0xFFFFFFFFu, v, d));
+    float *s = scratch[flip];
+    flip ^= 1;
+    if ((threadIdx.x & 31) == 0)
+        s[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float t = s[threadIdx.x & 31];
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1)
+        t = F::apply(t, __shfl_xor_sync(0xFFFFFFFFu, t, d));
+    return t;
+}
+
+// J = 16-byte vectors per lane (row length in vectors <= 1024 * J); EXACT: every lane owns exactly J valid vectors.
+template <typename In, typename Out, typename W, int KIND, int J, bool EXACT>
+__global__ void __launch_bounds__(kWideThreads, 1) rowwide_kernel(const __grid_constant__ RowParams p) {
+    constexpr int E = Vec16<In>::E;
+    constexpr int V = J * E;
+    extern __shared__ __align__(128) unsigned char wide_smem[];
+    __shared__ __align__(8) uint64_t full_bar[kWideMaxStages * kWideWarps];
+    __shared__ float scratch[2][kWideWarps];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int S = p.stages;
+    const uint32_t row_bytes = (uint32_t)p.nv * 16u;
+    const int v0 = warp * p.vpw;
+    const int v1 = min(v0 + p.vpw, p.nv);
+    const uint32_t chunk_bytes = v1 > v0 ? (uint32_t)(v1 - v0) * 16u : 0u;
+    const uint32_t smem_base = w_smem_u32(wide_smem);
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < S * kWideWarps; ++i)
+            w_mbar_init(w_smem_u32(&full_bar[i]), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    // rows of a 2-D (or collapsed) tensor need one multiply; only >= 2 outer dims pay for the div/mod walk
+    auto offsets = [&](int64_t row, int64_t *in_off, int64_t *out_off) {
+        if (p.nk <= 1) {
+            *in_off = row * p.in_kstride[0];
+            *out_off = row * p.out_kstride[0];
+        } else {
+            row_offsets(p, row, in_off, out_off);
+        }
+    };
+    auto issue = [&](int64_t row, int stage) { // one lane per warp
+        int64_t in_off, out_off;
+        offsets(row, &in_off, &out_off);
+        const uint32_t bar = w_smem_u32(&full_bar[stage * kWideWarps + warp]);
+        w_mbar_expect_tx(bar, chunk_bytes);
+        w_bulk_load(smem_base + (uint32_t)stage * row_bytes + (uint32_t)v0 * 16u, p.in + in_off + (int64_t)v0 * 16, chunk_bytes, bar);
+    };
+    if (lane == 0 && chunk_bytes) {
+        for (int s = 0; s < S; ++s) {
+            const int64_t r = (int64_t)blockIdx.x + (int64_t)s * gridDim.x;
+            if (r < p.rows)
+                issue(r, s);
+        }
+    }
+
+    const float n_f = (float)p.n;
+    int flip = 0;
+    uint32_t it = 0;
+    int stage = 0;
+    uint32_t parity = 0;
+    for (int64_t row = blockIdx.x; row < p.rows; row += gridDim.x) {
+        float x[V];
+        // ---- stage -> registers ---------------------------------------------------------------------------
+        if (chunk_bytes)
+            w_mbar_wait(w_smem_u32(&full_bar[stage * kWideWarps + warp]), parity);
+        const uint32_t buf = smem_base + (uint32_t)stage * row_bytes;
+#pragma unroll
+        for (int j = 0; j < J; ++j) {
+            const int vi = v0 + j * 32 + lane;
+            if (EXACT || vi < v1) {
+                Vec16<In>::unpack(w_lds128(buf + (uint32_t)vi * 16u), &x[j * E]);
+            } else {
+#pragma unroll
+                for (int k = 0; k < E; ++k)
+                    x[j * E + k] = (KIND == K_SOFTMAX || KIND == K_LOG_SOFTMAX) ? -INFINITY : 0.0f;
+            }
+        }
+        __syncwarp();
+        if (lane == 0 && chunk_bytes) {
+            const int64_t nr = row + (int64_t)S * gridDim.x;
+            if (nr < p.rows)
+                issue(nr, stage);
+        }
+        if (++stage == S) {
+            stage = 0;
+            parity ^= 1u;
+        }
+        int64_t in_off, out_off;
+        offsets(row, &in_off, &out_off);
+        char *dst = p.out + out_off;
+
+        if (KIND == K_SOFTMAX || KIND == K_LOG_SOFTMAX) {
+            float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+            for (int i = 0; i < V; i += 2) {
+                m0 = fmaxf(m0, x[i]);
+                m1 = fmaxf(m1, x[i + 1]);
+            }
+            const float m = wide_allreduce<FMax>(fmaxf(m0, m1), scratch, flip);
+            float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
+            if (KIND == K_SOFTMAX) {
+                if constexpr (sizeof(Out) == 4) { // fp32: e = exp(x - m) as the reference (cpu_operations.cpp:3132-3158)
+#pragma unroll
+                    for (int i = 0; i < V; i += 4) {
+                        x[i] = w_exp_neg(__fsub_rn(x[i], m)); s0 += x[i];
+                        x[i + 1] = w_exp_neg(__fsub_rn(x[i + 1], m)); s1 += x[i + 1];
+                        x[i + 2] = w_exp_neg(__fsub_rn(x[i + 2], m)); s2 += x[i + 2];
+                        x[i + 3] = w_exp_neg(__fsub_rn(x[i + 3], m)); s3 += x[i + 3];
+                    }
+                } else { // half output keeps 8-11 mantissa bits: 2^(x*log2e - m*log2e) in one FMA + MUFU.EX2
+                    const float ml = m * 1.4426950408889634f;
+#pragma unroll
+                    for (int i = 0; i < V; i += 4) {
+                        x[i] = w_ex2(fmaf(x[i], 1.4426950408889634f, -ml)); s0 += x[i];
+                        x[i + 1] = w_ex2(fmaf(x[i + 1], 1.4426950408889634f, -ml)); s1 += x[i + 1];
+                        x[i + 2] = w_ex2(fmaf(x[i + 2], 1.4426950408889634f, -ml)); s2 += x[i + 2];
+                        x[i + 3] = w_ex2(fmaf(x[i + 3], 1.4426950408889634f, -ml)); s3 += x[i + 3];
+                    }
+                }
+                const float s = wide_allreduce<FAdd>((s0 + s1) + (s2 + s3), scratch, flip);
+                const float inv = __fdiv_rn(1.0f, s);
+                const bool row_nan = !(s == s); // a NaN anywhere makes every output of the row NaN
+#pragma unroll
+                for (int j = 0; j < J; ++j) {
+                    const int vi = v0 + j * 32 + lane;
+                    if (EXACT || vi < v1) {
+                        float y[E];
+#pragma unroll
+                        for (int k = 0; k < E; ++k)
+                            y[k] = x[j * E + k] * inv;
+                        char *d = dst + (int64_t)vi * (E * sizeof(Out));
+                        if (row_nan)
+                            store_vec<Out, E, false>(d, y);
+                        else
+                            store_vec<Out, E, true>(d, y);
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < V; i += 4) {
+                    s0 += w_exp_neg(__fsub_rn(x[i], m));
+                    s1 += w_exp_neg(__fsub_rn(x[i + 1], m));
+                    s2 += w_exp_neg(__fsub_rn(x[i + 2], m));
+                    s3 += w_exp_neg(__fsub_rn(x[i + 3], m));
+                }
+                const float s = wide_allreduce<FAdd>((s0 + s1) + (s2 + s3), scratch, flip);
+                const float ls = logf(s);
+#pragma unroll
+                for (int j = 0; j < J; ++j) {
+                    const int vi = v0 + j * 32 + lane;
+                    if (EXACT || vi < v1) {
+                        float y[E];
+#pragma unroll
+                        for (int k = 0; k < E; ++k)
+                            y[k] = __fsub_rn(__fsub_rn(x[j * E + k], m), ls);
+                        store_vec<Out, E, false>(dst + (int64_t)vi * (E * sizeof(Out)), y);
+                    }
+                }
+            }
+        } else {
+            float scale; // multiplies the (centred) row
+            if (KIND == K_LAYER_NORM) {
+                float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
+#pragma unroll
+                for (int i = 0; i < V; i += 4) {
+                    s0 += x[i]; s1 += x[i + 1]; s2 += x[i + 2]; s3 += x[i + 3];
+                }
+                const float s = wide_allreduce<FAdd>((s0 + s1) + (s2 + s3), scratch, flip);
+                const float mean = round_to<In>(__fdiv_rn(s, n_f));
+                float q0 = 0.0f, q1 = 0.0f, q2 = 0.0f, q3 = 0.0f;
+#pragma unroll
+                for (int j = 0; j < J; ++j) {
+                    const bool ok = EXACT || (v0 + j * 32 + lane) < v1;
+#pragma unroll
+                    for (int k = 0; k < E; k += 4) {
+                        float *c = &x[j * E + k];
+                        c[0] = ok ? __fsub_rn(c[0], mean) : 0.0f; q0 += __fmul_rn(c[0], c[0]);
+                        c[1] = ok ? __fsub_rn(c[1], mean) : 0.0f; q1 += __fmul_rn(c[1], c[1]);
+                        c[2] = ok ? __fsub_rn(c[2], mean) : 0.0f; q2 += __fmul_rn(c[2], c[2]);
+                        c[3] = ok ? __fsub_rn(c[3], mean) : 0.0f; q3 += __fmul_rn(c[3], c[3]);
+                    }
+                }
+                const float q = wide_allreduce<FAdd>((q0 + q1) + (q2 + q3), scratch, flip);
+                scale = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(__fdiv_rn(q, n_f), p.eps)));
+            } else { // K_RMS_NORM
+                float q0 = 0.0f, q1 = 0.0f, q2 = 0.0f, q3 = 0.0f;
+#pragma unroll
+                for (int i = 0; i < V; i += 4) {
+                    q0 += round_to<In>(__fmul_rn(x[i], x[i]));
+                    q1 += round_to<In>(__fmul_rn(x[i + 1], x[i + 1]));
+                    q2 += round_to<In>(__fmul_rn(x[i + 2], x[i + 2]));
+                    q3 += round_to<In>(__fmul_rn(x[i + 3], x[i + 3]));
+                }
+                const float q = wide_allreduce<FAdd>((q0 + q1) + (q2 + q3), scratch, flip);
+                const float ms = round_to<In>(__fdiv_rn(q, n_f));
+                scale = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(ms, p.eps)));
+            }
+            // y = xc * (1/sd) * w + b. Alternate rows walk the weight/bias vectors in opposite order so that the tail
+            // of one row's sweep is still in L1 when the next row starts (they do not fit L1 as a whole at n = 32 768).
+            // bf16 results use the hardware converter (NaN -> 0x7FFF); the reference's conversion gives 0x7FC0
+            // (bfloat16.hpp:16-27), so NaNs are tracked with one NaN-propagating 3-input max per two results and a row
+            // that produced any is stored again through the exact software conversion.
+            constexpr bool HWPACK = std::is_same<Out, bf16_t>::value;
+            float nan_acc = 0.0f;
+            auto emit_as = [&](auto jc, auto hw) {
+                constexpr int j = decltype(jc)::value;
+                constexpr bool HW = decltype(hw)::value;
+                const int vi = v0 + j * 32 + lane;
+                if (EXACT || vi < v1) {
+                    float y[E], t[E];
+#pragma unroll
+                    for (int k = 0; k < E; ++k)
+                        y[k] = __fmul_rn(x[j * E + k], scale);
+                    if (p.w) {
+                        load_wb<W, E>(p.w, vi * E, t);
+#pragma unroll
+                        for (int k = 0; k < E; ++k)
+                            y[k] = __fmul_rn(y[k], t[k]);
+                    }
+                    if (KIND == K_LAYER_NORM && p.b) {
+                        load_wb<W, E>(p.b, vi * E, t);
+#pragma unroll
+                        for (int k = 0; k < E; ++k)
+                            y[k] = __fadd_rn(y[k], t[k]);
+                    }
+                    if constexpr (HW) {
+#pragma unroll
+                        for (int k = 0; k < E; k += 2)
+                            nan_acc = w_max3_nan(nan_acc, y[k], y[k + 1]);
+                    }
+                    store_vec<Out, E, HW>(dst + (int64_t)vi * (E * sizeof(Out)), y);
+                }
+            };
+            auto emit = [&](auto jc) { emit_as(jc, std::integral_constant<bool, HWPACK>{}); };
+            auto emit_exact = [&](auto jc) { emit_as(jc, std::false_type{}); };
+            if ((it & 1u) && p.wb_alternate)
+                static_for_down<J>(emit);
+            else
+                static_for_up<J>(emit);
+            if (HWPACK && __syncthreads_or(!(nan_acc == nan_acc))) // rare: redo the row with exact NaN encoding
+                static_for_up<J>(emit_exact);
+            ++it;
+        }
+    }
+}
+
+} // namespace rown
+} // namespace axb

@@ -67,8 +67,42 @@ def bmm_nt(nb=64, m=4096, iters=5):
     fl = 2.0*nb*m**3
     return dict(workload=f"bmm_nt_bf16_{nb}x{m}", ms_med=med, TFLOPs_med=fl/med/1e9, TFLOPs_best=fl/mn/1e9)
 
+def c3(kind, dt, rows=8192, n=32768):
+    x = dev.randn((rows, n), 7); isz = 4
+    if dt == "bf16":
+        x = dev.cast(x, capi.BF16); isz = 2
+    w, b = dev.randn((n,), 8, 1.0, 0.1), dev.randn((n,), 9, 0.0, 0.1)
+    by = ctypes.byref
+    xd, wd, bd = x.desc(), w.desc(), b.desc()
+    ax = (ctypes.c_int32 * 1)(1)
+    if kind in ("sum", "max"):
+        o = dev.DeviceArray.empty((rows,), x.dtype); od = o.desc(); nb = rows * n * isz + rows * isz
+        fn = lambda: capi.check(L.axb_reduce(capi.OP[kind], by(xd), ax, 1, 0, by(od), None))
+    elif kind == "argmax":
+        o = dev.DeviceArray.empty((rows,), capi.I64); od = o.desc(); nb = rows * n * isz + rows * 8
+        fn = lambda: capi.check(L.axb_argreduce(capi.OP["argmax"], by(xd), 1, 0, by(od), None))
+    else:
+        o = dev.DeviceArray.empty((rows, n), x.dtype); od = o.desc(); nb = 2 * rows * n * isz
+        if kind == "softmax":
+            fn = lambda: capi.check(L.axb_softmax(by(xd), -1, 0, by(od), None))
+        elif kind == "log_softmax":
+            fn = lambda: capi.check(L.axb_softmax(by(xd), -1, 1, by(od), None))
+        elif kind == "layer_norm":
+            fn = lambda: capi.check(L.axb_layer_norm(by(xd), by(wd), by(bd), -1, 1e-5, by(od), None))
+        elif kind == "layer_norm_noaffine":
+            fn = lambda: capi.check(L.axb_layer_norm(by(xd), None, None, -1, 1e-5, by(od), None))
+        else:
+            fn = lambda: capi.check(L.axb_rms_norm(by(xd), by(wd), -1, 1e-5, by(od), None))
+    med, mn = timeit(fn, iters=10, warm=3)
+    return dict(workload=f"c3_{kind}_{dt}_{rows}x{n}", ms_med=med, GBps_med=nb/med/1e6, GBps_best=nb/mn/1e6)
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["d2d", "relu", "exp", "gelu", "add", "c2"]
     for w in which:
+        if w.startswith("c3:"):
+            _, kind, dt = w.split(":")[:3]
+            extra = [int(v) for v in w.split(":")[3:]]
+            print(json.dumps(c3(kind, dt, *extra)), flush=True)
+            continue
         r = bmm() if w == "bmm" else bmm_nt() if w == "bmm_nt" else bmm(8, 4096) if w == "bmm8" else d2d() if w == "d2d" else c2() if w == "c2" else add() if w == "add" else simple(w)
         print(json.dumps(r), flush=True)

@@ -5,7 +5,7 @@ import numpy as np
 from axiom_b200 import capi, device as dev
 L = capi.lib(); capi.check(L.axb_set_device(0))
 which = sys.argv[1:] or ["c2", "sum", "argmax", "softmax", "layer_norm", "bmm"]
-reps = 3
+reps = int(os.environ.get("REPS", "3"))
 by = ctypes.byref
 if "c2" in which:
     import __graft_entry__ as g
