@@ -120,6 +120,41 @@ axb_status run_index(int mode, const axb_tensor *in, int dim, const axb_tensor *
     return AXB_OK;
 }
 
+// scatter (CPUScatterOperation src/backends/cpu/cpu_operations.cpp:2886-2960): out = copy(in);
+// out[.., idx[c], ..] = src[c] for every coordinate c of the index tensor. Duplicate targets: one of the writers wins
+// (the CPU loop keeps the last in C order; results only differ when the caller scatters two values to one slot).
+struct ScatterParams {
+    const char *idx, *src;
+    char *out;
+    int32_t ndim, dim, esize, idx_dtype;
+    uint32_t ishape[AXB_MAX_DIMS];                                   // index tensor shape, innermost first
+    int64_t idx_stride[AXB_MAX_DIMS], src_stride[AXB_MAX_DIMS], out_stride[AXB_MAX_DIMS];
+    int64_t dim_size, total;
+};
+
+__global__ void __launch_bounds__(256) scatter_kernel(const __grid_constant__ ScatterParams p) {
+    for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < p.total; o += (int64_t)gridDim.x * blockDim.x) {
+        int64_t rem = o, idx_off = 0, src_off = 0, out_off = 0;
+#pragma unroll 1
+        for (int d = 0; d < p.ndim; ++d) {
+            const int64_t q = rem / p.ishape[d];
+            const int64_t c = rem - q * p.ishape[d];
+            rem = q;
+            idx_off += c * p.idx_stride[d];
+            src_off += c * p.src_stride[d];
+            if (d != p.dim)
+                out_off += c * p.out_stride[d];
+        }
+        int64_t i = p.idx_dtype == AXB_I64 ? *reinterpret_cast<const int64_t *>(p.idx + idx_off)
+                                           : (int64_t) * reinterpret_cast<const int32_t *>(p.idx + idx_off);
+        if (i < 0)
+            i += p.dim_size;
+        if (i < 0 || i >= p.dim_size)
+            continue; // out-of-range targets are dropped instead of written out of bounds
+        copy_elem(p.out + out_off + i * p.out_stride[p.dim], p.src + src_off, p.esize);
+    }
+}
+
 } // namespace
 } // namespace axb
 
@@ -133,5 +168,54 @@ axb_status axb_gather(const axb_tensor *in, int dim, const axb_tensor *indices, 
 axb_status axb_index_select(const axb_tensor *in, int dim, const axb_tensor *indices, const axb_tensor *out,
                             axb_stream_t stream) {
     return run_index(1, in, dim, indices, out, stream, "axb_index_select");
+}
+
+axb_status axb_scatter(const axb_tensor *in, int dim, const axb_tensor *indices, const axb_tensor *src, const axb_tensor *out,
+                       axb_stream_t stream) {
+    const char *what = "axb_scatter";
+    AXB_TRY(validate_tensor(in, what));
+    AXB_TRY(validate_tensor(indices, what));
+    AXB_TRY(validate_tensor(src, what));
+    AXB_TRY(validate_tensor(out, what));
+    AXB_REQUIRE(in->dtype == out->dtype && src->dtype == in->dtype, AXB_ERR_INVALID, "%s: in, src and out must share one dtype", what);
+    AXB_REQUIRE(indices->dtype == AXB_I64 || indices->dtype == AXB_I32, AXB_ERR_UNSUPPORTED, "%s: indices must be Int64 or Int32", what);
+    if (dim < 0)
+        dim += in->ndim;
+    AXB_REQUIRE(dim >= 0 && dim < in->ndim, AXB_ERR_INVALID, "%s: dim out of range", what);
+    AXB_REQUIRE(indices->ndim == in->ndim && src->ndim == in->ndim && out->ndim == in->ndim, AXB_ERR_SHAPE,
+                "%s: in, indices, src and out must have the same rank", what);
+    for (int d = 0; d < in->ndim; ++d) {
+        AXB_REQUIRE(out->shape[d] == in->shape[d], AXB_ERR_SHAPE, "%s: out shape must equal the input shape", what);
+        AXB_REQUIRE(indices->shape[d] <= src->shape[d] && (d == dim || indices->shape[d] <= in->shape[d]), AXB_ERR_SHAPE,
+                    "%s: index extent %d exceeds src / input", what, d);
+    }
+    AXB_TRY(axb_gather_strided(in, out, stream)); // out = copy(in)
+    ScatterParams p;
+    memset(&p, 0, sizeof p);
+    p.total = numel(*indices);
+    if (p.total == 0 || numel(*out) == 0)
+        return AXB_OK;
+    p.idx = tensor_ptr(*indices);
+    p.src = tensor_ptr(*src);
+    p.out = tensor_ptr(*out);
+    p.ndim = in->ndim;
+    p.dim = in->ndim - 1 - dim;
+    p.esize = (int)dtype_size(in->dtype);
+    p.idx_dtype = indices->dtype;
+    p.dim_size = in->shape[dim];
+    for (int d = 0; d < in->ndim; ++d) {
+        const int s = in->ndim - 1 - d;
+        p.ishape[d] = (uint32_t)indices->shape[s];
+        p.idx_stride[d] = indices->strides[s];
+        p.src_stride[d] = src->strides[s];
+        p.out_stride[d] = out->strides[s];
+    }
+    cudaStream_t s;
+    DeviceCtx *ctx;
+    AXB_TRY(resolve_stream(stream, &s, &ctx));
+    const int64_t blocks = std::min<int64_t>((p.total + 255) / 256, (int64_t)ctx->sm_count * 16);
+    scatter_kernel<<<(unsigned)blocks, 256, 0, s>>>(p);
+    AXB_CHECK_LAUNCH();
+    return AXB_OK;
 }
 }

@@ -1,0 +1,510 @@
+// cuda_operations.cpp — seam 2: ops::Operation subclasses for Device::GPU, registered with the OperationRegistry
+// (include/axiom/operations.hpp:210-302), and the free functions the shared code calls on its GPU paths
+// (src/backends/metal/metal_operations.hpp:11-67). Every entry validates like the CPU operation it mirrors, allocates a
+// fresh GPU result and ends in one or a few axb_* launches on the backend stream; nothing is computed on the host and
+// nothing falls back to the CPU operation.
+#include <algorithm>
+#include <cmath>
+#include <numeric>
+
+#include "axiom/operations.hpp"
+#include "backends/metal/metal_operations.hpp"
+#include "cuda_backend.hpp"
+
+namespace axiom {
+namespace backends {
+namespace cuda {
+
+using ops::OpType;
+
+namespace {
+
+Shape shape_of(const int64_t *s, int n) {
+    Shape out(n);
+    for (int i = 0; i < n; ++i)
+        out[i] = static_cast<size_t>(s[i]);
+    return out;
+}
+
+Shape broadcast2(const Shape &a, const Shape &b) {
+    int64_t sa[AXB_MAX_DIMS], sb[AXB_MAX_DIMS], so[AXB_MAX_DIMS];
+    if (a.size() > AXB_MAX_DIMS || b.size() > AXB_MAX_DIMS)
+        throw ShapeError("CUDA backend supports at most 8 dimensions");
+    for (size_t i = 0; i < a.size(); ++i) sa[i] = (int64_t)a[i];
+    for (size_t i = 0; i < b.size(); ++i) sb[i] = (int64_t)b[i];
+    int n = 0;
+    if (axb_broadcast_shape(sa, (int)a.size(), sb, (int)b.size(), so, &n) != AXB_OK)
+        throw ShapeError::broadcast_incompatible(axb_last_error());
+    return shape_of(so, n);
+}
+
+// graph_registry.cpp:95-146 (normalises negative axes; all-reduced -> {1}, argmax/argmin -> rank 0)
+Shape reduced_shape(const Shape &in, std::vector<int> axes, bool keep_dims, bool is_arg) {
+    if (axes.empty())
+        return keep_dims ? Shape(in.size(), 1) : (is_arg ? Shape{} : Shape{1});
+    for (int &a : axes)
+        if (a < 0)
+            a += (int)in.size();
+    Shape out;
+    for (size_t i = 0; i < in.size(); ++i) {
+        const bool red = std::find(axes.begin(), axes.end(), (int)i) != axes.end();
+        if (!red)
+            out.push_back(in[i]);
+        else if (keep_dims)
+            out.push_back(1);
+    }
+    if (out.empty())
+        return is_arg ? Shape{} : Shape{1};
+    return out;
+}
+
+} // namespace
+
+Tensor gpu_unary(OpType op, const Tensor &x_in, double param) {
+    const Tensor x = on_gpu(x_in);
+    const int32_t rdt = axb_unary_result_dtype(to_axb_op(op), to_axb_dtype(x.dtype()));
+    if (rdt < 0)
+        throw TypeError::unsupported_dtype(x.dtype_name(), op_name(op) + " on GPU");
+    Tensor out = empty_gpu(x.shape(), static_cast<DType>(rdt));
+    if (out.size() == 0)
+        return out;
+    const axb_tensor xd = describe(x), od = describe(out);
+    check(axb_unary(to_axb_op(op), &xd, &od, param, nullptr), "axb_unary");
+    return out;
+}
+
+Tensor gpu_binary(OpType op, const Tensor &a_in, const Tensor &b_in) {
+    const Tensor a = on_gpu(a_in), b = on_gpu(b_in);
+    const int32_t rdt = axb_binary_result_dtype(to_axb_op(op), to_axb_dtype(a.dtype()), to_axb_dtype(b.dtype()));
+    if (rdt < 0)
+        throw TypeError::unsupported_dtype(a.dtype_name() + "/" + b.dtype_name(), op_name(op) + " on GPU");
+    Tensor out = empty_gpu(broadcast2(a.shape(), b.shape()), static_cast<DType>(rdt));
+    if (out.size() == 0)
+        return out;
+    const axb_tensor ad = describe(a), bd = describe(b), od = describe(out);
+    check(axb_binary(to_axb_op(op), &ad, &bd, &od, nullptr), "axb_binary");
+    return out;
+}
+
+Tensor gpu_where(const Tensor &c_in, const Tensor &a_in, const Tensor &b_in) {
+    const Tensor c = on_gpu(c_in), a = on_gpu(a_in), b = on_gpu(b_in);
+    const int32_t rdt = axb_promote_types(to_axb_dtype(a.dtype()), to_axb_dtype(b.dtype()));
+    if (rdt < 0)
+        throw TypeError("where: cannot promote " + a.dtype_name() + " and " + b.dtype_name());
+    Tensor out = empty_gpu(broadcast2(c.shape(), broadcast2(a.shape(), b.shape())), static_cast<DType>(rdt));
+    if (out.size() == 0)
+        return out;
+    const axb_tensor cd = describe(c), ad = describe(a), bd = describe(b), od = describe(out);
+    check(axb_where(&cd, &ad, &bd, &od, nullptr), "axb_where");
+    return out;
+}
+
+Tensor gpu_masked_fill(const Tensor &x_in, const Tensor &m_in, double value) {
+    const Tensor x = on_gpu(x_in), m = on_gpu(m_in);
+    Tensor out = empty_gpu(broadcast2(x.shape(), m.shape()), x.dtype());
+    if (out.size() == 0)
+        return out;
+    const axb_tensor xd = describe(x), md = describe(m), od = describe(out);
+    check(axb_masked_fill(&xd, &md, value, &od, nullptr), "axb_masked_fill");
+    return out;
+}
+
+Tensor gpu_cast(const Tensor &x_in, DType to) {
+    const Tensor x = on_gpu(x_in);
+    Tensor out = empty_gpu(x.shape(), to);
+    if (out.size() == 0)
+        return out;
+    const axb_tensor xd = describe(x), od = describe(out);
+    check(axb_cast(&xd, &od, nullptr), "axb_cast");
+    return out;
+}
+
+Tensor gpu_contiguous(const Tensor &x) {
+    if (x.is_contiguous())
+        return x;
+    Tensor out = empty_gpu(x.shape(), x.dtype());
+    if (out.size() == 0)
+        return out;
+    const axb_tensor xd = describe(x), od = describe(out);
+    check(axb_gather_strided(&xd, &od, nullptr), "axb_gather_strided");
+    return out;
+}
+
+Tensor gpu_reduce(OpType op, const Tensor &x_in, const std::vector<int> &axes_in, bool keep_dims) {
+    Tensor x = on_gpu(x_in);
+    const bool is_arg = op == OpType::ArgMax || op == OpType::ArgMin;
+    if (op == OpType::Softmax || op == OpType::LogSoftmax)
+        return gpu_softmax(x, axes_in.empty() ? -1 : axes_in[0], op == OpType::LogSoftmax);
+    if (is_arg) {
+        // cpu_operations.cpp:2240-2247: no axis, axis == -1 or several axes mean "flatten, then axis 0"
+        int ax = axes_in.empty() ? -1 : axes_in[0];
+        const bool flat = ax == -1 || axes_in.size() > 1;
+        if (!flat && (ax < -(int)x.ndim() || ax >= (int)x.ndim()))
+            throw ShapeError::invalid_axis(ax, (int)x.ndim());
+        if (!flat && ax < 0)
+            ax += (int)x.ndim();
+        if (x.size() == 0)
+            throw ValueError("argmax/argmin of an empty tensor");
+        Shape oshape;
+        if (flat) {
+            x = gpu_contiguous(x);
+            oshape = keep_dims ? Shape(x.ndim(), 1) : Shape{};
+        } else {
+            oshape = reduced_shape(x.shape(), {ax}, keep_dims, true);
+        }
+        Tensor out = empty_gpu(oshape, DType::Int64);
+        const axb_tensor xd = describe(x), od = describe(out);
+        check(axb_argreduce(to_axb_op(op), &xd, flat ? -1 : ax, keep_dims ? 1 : 0, &od, nullptr), "axb_argreduce");
+        return out;
+    }
+    std::vector<int32_t> axes;
+    for (int a : axes_in) {
+        if (a < -(int)x.ndim() || a >= (int)x.ndim())
+            throw ShapeError::invalid_axis(a, (int)x.ndim());
+        axes.push_back(a < 0 ? a + (int)x.ndim() : a);
+    }
+    std::sort(axes.begin(), axes.end());
+    axes.erase(std::unique(axes.begin(), axes.end()), axes.end());
+    const int32_t rdt = axb_reduce_result_dtype(to_axb_op(op), to_axb_dtype(x.dtype()));
+    if (rdt < 0)
+        throw TypeError::unsupported_dtype(x.dtype_name(), op_name(op) + " on GPU");
+    DType odt = static_cast<DType>(rdt);
+    Tensor out = empty_gpu(reduced_shape(x.shape(), axes_in, keep_dims, false), odt);
+    const axb_tensor xd = describe(x), od = describe(out);
+    check(axb_reduce(to_axb_op(op), &xd, axes.data(), (int)axes.size(), keep_dims ? 1 : 0, &od, nullptr), "axb_reduce");
+    // the graph declares Mean -> Float32 for every non-f64 input (graph_registry.cpp:278-287) and the executor upcasts
+    // half results (graph_executor.cpp:396-403); integer means arrive as Float32 from axb_reduce already
+    if (op == OpType::Mean && (out.dtype() == DType::Float16 || out.dtype() == DType::BFloat16))
+        return gpu_cast(out, DType::Float32);
+    return out;
+}
+
+Tensor gpu_softmax(const Tensor &x_in, int axis, bool is_log) {
+    const Tensor x = on_gpu(x_in);
+    if (axis < -(int)x.ndim() || axis >= (int)x.ndim())
+        throw ShapeError::invalid_axis(axis, (int)x.ndim());
+    Tensor out = empty_gpu(x.shape(), x.dtype());
+    if (out.size() == 0)
+        return out;
+    const axb_tensor xd = describe(x), od = describe(out);
+    check(axb_softmax(&xd, axis, is_log ? 1 : 0, &od, nullptr), "axb_softmax");
+    return out;
+}
+
+Tensor gpu_matmul(const Tensor &a_in, const Tensor &b_in, bool ta, bool tb, const Tensor *bias, OpType activation) {
+    const Tensor a = on_gpu(a_in), b = on_gpu(b_in);
+    const axb_tensor ad = describe(a), bd = describe(b);
+    int64_t oshape[AXB_MAX_DIMS];
+    int ond = 0;
+    check(axb_matmul_shape(&ad, &bd, ta ? 1 : 0, tb ? 1 : 0, oshape, &ond), "matmul");
+    const int32_t rdt = axb_promote_types(ad.dtype, bd.dtype);
+    if (rdt < 0)
+        throw TypeError("matmul: cannot promote " + a.dtype_name() + " and " + b.dtype_name());
+    Tensor out = empty_gpu(shape_of(oshape, ond), static_cast<DType>(rdt));
+    if (out.size() == 0)
+        return out;
+    const axb_tensor od = describe(out);
+    axb_matmul_epilogue epi{};
+    axb_tensor biasd{};
+    Tensor bias_gpu;
+    if (bias && bias->storage()) {
+        bias_gpu = on_gpu(*bias);
+        biasd = describe(bias_gpu);
+        epi.bias = &biasd;
+    }
+    if (activation != OpType::_Count)
+        epi.activation = to_axb_op(activation);
+    const bool use_epi = epi.bias || epi.activation;
+    check(axb_matmul(&ad, &bd, ta ? 1 : 0, tb ? 1 : 0, use_epi ? &epi : nullptr, &od, nullptr), "axb_matmul");
+    return out;
+}
+
+Tensor gpu_pad_constant(const Tensor &x_in, const std::vector<std::pair<size_t, size_t>> &pad, double value) {
+    const Tensor x = on_gpu(x_in);
+    if (pad.size() != x.ndim())
+        throw ShapeError("pad: pad_width must have one (before, after) pair per dimension");
+    Shape oshape(x.ndim());
+    int64_t lo[AXB_MAX_DIMS], hi[AXB_MAX_DIMS];
+    for (size_t d = 0; d < x.ndim(); ++d) {
+        lo[d] = (int64_t)pad[d].first;
+        hi[d] = (int64_t)pad[d].second;
+        oshape[d] = x.shape()[d] + pad[d].first + pad[d].second;
+    }
+    Tensor out = empty_gpu(oshape, x.dtype());
+    if (out.size() == 0)
+        return out;
+    const axb_tensor xd = describe(x), od = describe(out);
+    check(axb_pad_constant(&xd, lo, hi, value, &od, nullptr), "axb_pad_constant");
+    return out;
+}
+
+// conv1d = im2col (implicit zero padding) + one batched GEMM per group + bias broadcast along (N, :, L_out)
+Tensor gpu_conv1d_impl(const Tensor &x_in, const Tensor &w_in, const Tensor &b_in, int stride, int padding, int dilation,
+                       int groups) {
+    Tensor x = on_gpu(x_in);
+    const Tensor w = on_gpu(w_in);
+    const bool has_batch = x.ndim() == 3;
+    if (!has_batch)
+        x = x.reshape({1, x.shape()[0], x.shape()[1]});
+    const size_t N = x.shape()[0], C = x.shape()[1], L = x.shape()[2];
+    const size_t Cout = w.shape()[0], Cg = w.shape()[1], K = w.shape()[2];
+    if (C != Cg * (size_t)groups || Cout % (size_t)groups != 0)
+        throw ShapeError("conv1d: channel/group mismatch");
+    const size_t span = (size_t)dilation * (K - 1) + 1;
+    if (L + 2 * (size_t)padding < span)
+        throw ShapeError("conv1d: input length too small for given kernel/padding/dilation");
+    const size_t Lout = (L + 2 * (size_t)padding - span) / (size_t)stride + 1;
+    const DType dt = static_cast<DType>(axb_promote_types(to_axb_dtype(x.dtype()), to_axb_dtype(w.dtype())));
+    if (x.dtype() != dt)
+        x = gpu_cast(x, dt);
+    Tensor wq = w.dtype() == dt ? w : gpu_cast(w, dt);
+    Tensor col = empty_gpu({N, C * K, Lout}, dt);
+    {
+        const axb_tensor xd = describe(x), cd = describe(col);
+        check(axb_im2col_1d(&xd, (int)K, stride, padding, dilation, &cd, nullptr), "axb_im2col_1d");
+    }
+    Tensor out;
+    const Tensor w2d = gpu_contiguous(wq).reshape({Cout, Cg * K}); // (C_out, C_in/groups * K)
+    if (groups == 1) {
+        out = gpu_matmul(w2d, col, false, false); // {C_out, CK} x {N, CK, L_out} -> {N, C_out, L_out}
+    } else {
+        out = empty_gpu({N, Cout, Lout}, dt);
+        const size_t cog = Cout / (size_t)groups;
+        for (int g = 0; g < groups; ++g) {
+            Tensor wg = w2d.slice({Slice((int64_t)(g * cog), (int64_t)((g + 1) * cog)), Slice()});
+            Tensor cg = col.slice({Slice(), Slice((int64_t)(g * Cg * K), (int64_t)((g + 1) * Cg * K)), Slice()});
+            Tensor og = gpu_matmul(wg, cg, false, false);
+            Tensor dst = out.slice({Slice(), Slice((int64_t)(g * cog), (int64_t)((g + 1) * cog)), Slice()});
+            // strided store of the group's block: out_view = og (elementwise copy honours the view's strides)
+            const axb_tensor sd = describe(og), dd = describe(dst);
+            check(axb_gather_strided(&sd, &dd, nullptr), "conv1d group store");
+        }
+    }
+    if (b_in.storage() && b_in.size() > 0) {
+        Tensor b = on_gpu(b_in);
+        out = gpu_binary(OpType::Add, out, b.reshape({1, Cout, 1}));
+    }
+    return has_batch ? out : out.reshape({Cout, Lout});
+}
+
+// ---- Operation classes ---------------------------------------------------------------------------------------------
+namespace {
+
+class CudaOperation final : public ops::Operation {
+  public:
+    explicit CudaOperation(OpType t) : type_(t) {}
+    OpType type() const override { return type_; }
+    std::string name() const override { return "cuda_" + op_name(type_); }
+    Device device() const override { return Device::GPU; }
+
+    // broadcasting is handled in-kernel; returning false would send the eager path to the CPU op (operations.cpp:1122-1127)
+    bool supports_binary(const Tensor &lhs, const Tensor &rhs) const override {
+        return ops::are_broadcastable(lhs.shape(), rhs.shape());
+    }
+    Tensor execute_binary(const Tensor &lhs, const Tensor &rhs) const override { return gpu_binary(type_, lhs, rhs); }
+    Tensor execute_unary(const Tensor &input) const override {
+        return gpu_unary(type_, input, type_ == OpType::LeakyReLU ? 0.01 : 0.0);
+    }
+    Tensor execute_reduction(const Tensor &input, const std::vector<int> &axis, bool keep_dims) const override {
+        return gpu_reduce(type_, input, axis, keep_dims);
+    }
+    Tensor execute_matmul(const Tensor &a, const Tensor &b, bool ta, bool tb) const override {
+        return gpu_matmul(a, b, ta, tb);
+    }
+    Tensor execute_where(const Tensor &c, const Tensor &a, const Tensor &b) const override {
+        if (c.is_lazy() || a.is_lazy() || b.is_lazy())
+            return graph::fused_where(c, a, b); // lazy operand trees + select in one launch
+        return gpu_where(c, a, b);
+    }
+    Tensor execute_masked_fill(const Tensor &input, const Tensor &mask, const Tensor &value) const override {
+        // value is a one-element tensor (operations.cpp:1588-1590); a device scalar costs one 4/8-byte read back
+        Tensor v = value.device() == Device::CPU ? value : value.cpu();
+        const double val = v.astype(DType::Float64).item<double>({0});
+        return gpu_masked_fill(input, mask, val);
+    }
+    Tensor execute_gather(const Tensor &input, int dim, const Tensor &indices) const override {
+        const Tensor x = on_gpu(input), idx = on_gpu(indices);
+        Tensor out = empty_gpu(idx.shape(), x.dtype());
+        if (out.size() == 0)
+            return out;
+        const axb_tensor xd = describe(x), id = describe(idx), od = describe(out);
+        check(axb_gather(&xd, dim, &id, &od, nullptr), "axb_gather");
+        return out;
+    }
+    Tensor execute_index_select(const Tensor &input, int dim, const Tensor &indices) const override {
+        const Tensor x = on_gpu(input), idx = on_gpu(indices);
+        int d = dim < 0 ? dim + (int)x.ndim() : dim;
+        if (d < 0 || d >= (int)x.ndim())
+            throw ShapeError::invalid_axis(dim, (int)x.ndim());
+        Shape oshape = x.shape();
+        oshape[d] = idx.size();
+        Tensor out = empty_gpu(oshape, x.dtype());
+        if (out.size() == 0)
+            return out;
+        const axb_tensor xd = describe(x), id = describe(idx), od = describe(out);
+        check(axb_index_select(&xd, d, &id, &od, nullptr), "axb_index_select");
+        return out;
+    }
+    Tensor execute_scatter(const Tensor &input, int dim, const Tensor &indices, const Tensor &src) const override {
+        const Tensor x = on_gpu(input), idx = on_gpu(indices);
+        Tensor v = on_gpu(src);
+        if (v.dtype() != x.dtype())
+            v = gpu_cast(v, x.dtype());
+        Tensor out = empty_gpu(x.shape(), x.dtype());
+        if (out.size() == 0)
+            return out;
+        const axb_tensor xd = describe(x), id = describe(idx), vd = describe(v), od = describe(out);
+        check(axb_scatter(&xd, dim, &id, &vd, &od, nullptr), "axb_scatter");
+        return out;
+    }
+    Tensor execute_cast(const Tensor &input, DType target) const override { return gpu_cast(input, target); }
+    void execute_binary_inplace(Tensor &lhs, const Tensor &rhs) const override {
+        const Tensor r = on_gpu(rhs);
+        const int32_t rdt = axb_binary_result_dtype(to_axb_op(type_), to_axb_dtype(lhs.dtype()), to_axb_dtype(r.dtype()));
+        if (rdt != to_axb_dtype(lhs.dtype()) || broadcast2(lhs.shape(), r.shape()) != lhs.shape())
+            throw TypeError("in-place " + op_name(type_) + ": result does not fit the left operand");
+        const axb_tensor ld = describe(lhs), rd = describe(r);
+        check(axb_binary(to_axb_op(type_), &ld, &rd, &ld, nullptr), "axb_binary (in place)");
+    }
+
+  private:
+    OpType type_;
+};
+
+} // namespace
+
+void register_cuda_operations() {
+    static const OpType kOps[] = {
+        OpType::Add, OpType::Subtract, OpType::Multiply, OpType::Divide, OpType::Power, OpType::Modulo,
+        OpType::Equal, OpType::NotEqual, OpType::Less, OpType::LessEqual, OpType::Greater, OpType::GreaterEqual,
+        OpType::LogicalAnd, OpType::LogicalOr, OpType::LogicalXor, OpType::LogicalNot,
+        OpType::BitwiseAnd, OpType::BitwiseOr, OpType::BitwiseXor, OpType::LeftShift, OpType::RightShift,
+        OpType::Maximum, OpType::Minimum, OpType::Atan2, OpType::Hypot,
+        OpType::Negate, OpType::Abs, OpType::Sqrt, OpType::Exp, OpType::Log, OpType::Sin, OpType::Cos, OpType::Tan,
+        OpType::Erf, OpType::Sign, OpType::Floor, OpType::Ceil, OpType::Trunc, OpType::Round, OpType::Reciprocal,
+        OpType::Square, OpType::Cbrt, OpType::IsNaN, OpType::IsInf, OpType::IsFinite,
+        OpType::ReLU, OpType::LeakyReLU, OpType::SiLU, OpType::Sigmoid, OpType::Tanh, OpType::GELU,
+        OpType::Softmax, OpType::LogSoftmax,
+        OpType::Sum, OpType::Mean, OpType::Max, OpType::Min, OpType::ArgMax, OpType::ArgMin, OpType::Any, OpType::All,
+        OpType::Prod,
+        OpType::MatMul, OpType::BatchMatMul, OpType::Where, OpType::MaskedFill, OpType::Gather, OpType::Scatter,
+        OpType::IndexSelect,
+        OpType::Cast,
+    };
+    for (OpType t : kOps)
+        ops::OperationRegistry::register_operation(t, Device::GPU, std::make_unique<CudaOperation>(t));
+}
+
+} // namespace cuda
+
+// ---- free functions of the GPU seam (declared in src/backends/metal/metal_operations.hpp) --------------------------
+namespace metal {
+
+using cuda::check;
+using cuda::describe;
+using cuda::empty_gpu;
+using cuda::on_gpu;
+
+Tensor gpu_make_contiguous(const Tensor &tensor) { return cuda::gpu_contiguous(tensor); }
+
+Tensor gpu_layer_norm(const Tensor &input, const Tensor &weight, const Tensor &bias, int axis, float eps) {
+    const Tensor x = on_gpu(input);
+    Tensor out = empty_gpu(x.shape(), x.dtype()); // the lazy LayerNorm node declares the input dtype (graph_registry.cpp:625)
+    if (out.size() == 0)
+        return out;
+    const axb_tensor xd = describe(x), od = describe(out);
+    axb_tensor wd{}, bd{};
+    Tensor w, b;
+    const bool has_w = weight.storage() && weight.size() > 0, has_b = bias.storage() && bias.size() > 0;
+    if (has_w) { w = on_gpu(weight); wd = describe(w); }
+    if (has_b) { b = on_gpu(bias); bd = describe(b); }
+    check(axb_layer_norm(&xd, has_w ? &wd : nullptr, has_b ? &bd : nullptr, axis, eps, &od, nullptr), "axb_layer_norm");
+    return out;
+}
+
+Tensor gpu_rms_norm(const Tensor &input, const Tensor &weight, int axis, float eps) {
+    const Tensor x = on_gpu(input);
+    Tensor out = empty_gpu(x.shape(), x.dtype());
+    if (out.size() == 0)
+        return out;
+    const axb_tensor xd = describe(x), od = describe(out);
+    axb_tensor wd{};
+    Tensor w;
+    const bool has_w = weight.storage() && weight.size() > 0;
+    if (has_w) { w = on_gpu(weight); wd = describe(w); }
+    check(axb_rms_norm(&xd, has_w ? &wd : nullptr, axis, eps, &od, nullptr), "axb_rms_norm");
+    return out;
+}
+
+Tensor gpu_conv1d(const Tensor &input, const Tensor &weight, const Tensor &bias, int stride, int padding, int dilation,
+                  int groups) {
+    return cuda::gpu_conv1d_impl(input, weight, bias, stride, padding, dilation, groups);
+}
+
+// softmax(Q K^T * scale + mask) V as batched GEMM -> masked scale -> row softmax -> batched GEMM. Semantics follow
+// cpu_flash_attention (src/backends/cpu/flash_attention_cpu.cpp:73-105): causal masks kv > q, an explicit mask marks
+// positions to DROP (non-zero = masked out), both by -inf before the softmax.
+Tensor gpu_scaled_dot_product_attention(const Tensor &query, const Tensor &key, const Tensor &value, const Tensor &mask,
+                                        float scale, bool is_causal) {
+    const Tensor q = on_gpu(query), k = on_gpu(key), v = on_gpu(value);
+    Tensor s = cuda::gpu_matmul(q, k, false, true); // (B, H, Lq, Lk)
+    Tensor sc = Tensor::full({1}, scale, Device::CPU).astype(s.dtype()).to(Device::GPU);
+    s = cuda::gpu_binary(ops::OpType::Multiply, s, sc);
+    const size_t Lq = q.shape()[2], Lk = k.shape()[2];
+    if (is_causal) {
+        // kv position j is visible to query i iff j <= i (q_block_offset + i, flash_attention_cpu.cpp:76-89)
+        Tensor cm = Tensor::zeros({Lq, Lk}, DType::Bool, Device::CPU);
+        auto *p = cm.typed_data<bool>();
+        for (size_t i = 0; i < Lq; ++i)
+            for (size_t j = i + 1; j < Lk; ++j)
+                p[i * Lk + j] = true;
+        s = cuda::gpu_masked_fill(s, cm.to(Device::GPU), -INFINITY);
+    }
+    if (mask.storage() && mask.size() > 0) {
+        Tensor m = on_gpu(mask);
+        if (m.dtype() != DType::Bool)
+            m = cuda::gpu_binary(ops::OpType::NotEqual, m, Tensor::zeros({1}, m.dtype(), Device::CPU).to(Device::GPU));
+        s = cuda::gpu_masked_fill(s, m, -INFINITY);
+    }
+    Tensor p = cuda::gpu_softmax(s, -1, false);
+    return cuda::gpu_matmul(p, v, false, false); // (B, H, Lq, D)
+}
+
+Tensor gpu_pad(const Tensor &input, const std::vector<std::pair<size_t, size_t>> &pad_width, const std::string &mode,
+               double value) {
+    if (mode != "constant")
+        throw RuntimeError::not_implemented("GPU pad mode '" + mode + "' (constant only)");
+    return cuda::gpu_pad_constant(input, pad_width, value);
+}
+
+Tensor gpu_fill_constant(const Shape &shape, DType dtype, double value) {
+    Tensor out = empty_gpu(shape, dtype);
+    if (out.size() == 0)
+        return out;
+    const axb_tensor od = describe(out);
+    check(axb_fill(&od, value, nullptr), "axb_fill");
+    return out;
+}
+
+Tensor gpu_linear(const Tensor &input, const Tensor &weight, const Tensor &bias, bool has_bias) {
+    return cuda::gpu_matmul(input, weight, false, true, has_bias ? &bias : nullptr);
+}
+
+// outside the named hot path (SURVEY.md §8 out-of-scope list): explicit error instead of a silent CPU detour
+Tensor gpu_conv2d(const Tensor &, const Tensor &, const Tensor &, std::array<int, 2>, std::array<int, 2>, std::array<int, 2>, int) {
+    throw RuntimeError::not_implemented("conv2d on the CUDA backend");
+}
+Tensor gpu_conv_transpose1d(const Tensor &, const Tensor &, const Tensor &, int, int, int, int, int) {
+    throw RuntimeError::not_implemented("conv_transpose1d on the CUDA backend");
+}
+Tensor gpu_conv_transpose2d(const Tensor &, const Tensor &, const Tensor &, std::array<int, 2>, std::array<int, 2>,
+                            std::array<int, 2>, std::array<int, 2>, int) {
+    throw RuntimeError::not_implemented("conv_transpose2d on the CUDA backend");
+}
+Tensor gpu_interpolate(const Tensor &, const std::vector<size_t> &, ops::InterpolateMode, bool) {
+    throw RuntimeError::not_implemented("interpolate on the CUDA backend");
+}
+
+} // namespace metal
+} // namespace backends
+} // namespace axiom

@@ -273,6 +273,19 @@ axb_status axb_gather(const axb_tensor *in, int dim, const axb_tensor *indices, 
                       axb_stream_t stream);
 axb_status axb_index_select(const axb_tensor *in, int dim, const axb_tensor *indices, const axb_tensor *out,
                             axb_stream_t stream);
+/* CPUScatterOperation (cpu_operations.cpp:2886-2960): out = copy(in); out[.., indices[c], ..] = src[c] along dim */
+axb_status axb_scatter(const axb_tensor *in, int dim, const axb_tensor *indices, const axb_tensor *src,
+                       const axb_tensor *out, axb_stream_t stream);
+
+/* ---- convolution / padding data movement ("next" row: conv1d as GEMM) ------------------------------------------
+ * Replaces the reference's naive conv1d loops (src/tensor/operations.cpp:3046-3135) together with axb_matmul:
+ * col = im2col(x) with implicit zero padding, then W2d{C_out, C_in*K} x col{N, C_in*K, L_out}.
+ * axb_pad_constant is OpType::Pad in constant mode (src/tensor/operations.cpp:2150-2260, lazy node
+ * src/graph/graph_registry.cpp:707-722). in may be strided; out must be contiguous. */
+axb_status axb_im2col_1d(const axb_tensor *in /* (N, C, L) */, int kernel_size, int stride, int padding, int dilation,
+                         const axb_tensor *out /* (N, C*K, L_out) */, axb_stream_t stream);
+axb_status axb_pad_constant(const axb_tensor *in, const int64_t *pad_lo, const int64_t *pad_hi, double value,
+                            const axb_tensor *out, axb_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Host-buffer entry points (what `Tensor::gpu()` ... `.cpu()` does end to end: H2D, launch, D2H, sync).
