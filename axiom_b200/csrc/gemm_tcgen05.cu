@@ -21,6 +21,7 @@
 #include <cuda.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include "driver.h"
@@ -53,7 +54,15 @@ struct TcParams {
     int32_t bias_dtype, act, out_dtype;
     int32_t a_bmult, b_bmult;       // 0 when the operand is broadcast over the batch
     uint32_t idesc;
+    // fp32-accurate mode (see try_split_f32): operands are [rows, 3*Kp] bf16 (hi | mid | lo pieces), the K loop walks
+    // six (A piece, B piece) combinations of kbp k-blocks each
+    int32_t split, kbp;
+    int64_t Kp;
 };
+
+// piece (0 = hi, 1 = mid, 2 = lo) of A and B for combination c, smallest products first
+__device__ __forceinline__ int split_piece_a(int c) { return (0x001120 >> (4 * c)) & 0xF; } // c = 0..5: 0,2,1,1,0,0
+__device__ __forceinline__ int split_piece_b(int c) { return (0x010102 >> (4 * c)) & 0xF; } // c = 0..5: 2,0,1,0,1,0
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -161,7 +170,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
-    const int num_kb = (int)((p.K + BK - 1) / BK);
+    const int num_kb = p.split ? 6 * p.kbp : (int)((p.K + BK - 1) / BK);
     const int64_t tiles_per_batch = (int64_t)p.tiles_m * p.tiles_n;
 
     if (warp == 0) {
@@ -177,7 +186,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                     mbar_wait(empty_bar(stage), phase ^ 1u);
                     mbar_expect_tx(full_bar(stage), STAGE_BYTES);
                     const uint32_t sa = smem + stage * STAGE_BYTES, sb = sa + A_BYTES;
-                    const int k0 = kb * BK;
+                    int k0 = kb * BK, k0b = k0;
+                    if (p.split) { // K coordinate inside the piece each operand contributes to this combination
+                        const int c = kb / p.kbp, kk = (kb - c * p.kbp) * BK;
+                        k0 = split_piece_a(c) * (int)p.Kp + kk;
+                        k0b = split_piece_b(c) * (int)p.Kp + kk;
+                    }
                     if (!A_MN) {
                         tma_load_3d(sa, &tma_a, full_bar(stage), k0, m0, ba); // box {64 k, 128 m}
                     } else {
@@ -186,11 +200,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                             tma_load_3d(sa + j * (64 * BK * 2), &tma_a, full_bar(stage), m0 + 64 * j, k0, ba);
                     }
                     if (!B_MN) {
-                        tma_load_3d(sb, &tma_b, full_bar(stage), k0, n0, bb); // box {64 k, 256 n}
+                        tma_load_3d(sb, &tma_b, full_bar(stage), k0b, n0, bb); // box {64 k, 256 n}
                     } else {
 #pragma unroll
                         for (int j = 0; j < BN / 64; ++j)
-                            tma_load_3d(sb + j * (64 * BK * 2), &tma_b, full_bar(stage), n0 + 64 * j, k0, bb);
+                            tma_load_3d(sb + j * (64 * BK * 2), &tma_b, full_bar(stage), n0 + 64 * j, k0b, bb);
                     }
                     if (++stage == STAGES) {
                         stage = 0;
@@ -238,7 +252,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         const int q = warp & 3;
         int acc = 0;
         uint32_t acc_phase = 0;
-        const bool c_vec = (p.c_cs == 2) && ((reinterpret_cast<uintptr_t>(p.c) | (uintptr_t)p.c_rs | (uintptr_t)p.c_bs) % 16 == 0);
+        const bool out_f32 = p.out_dtype == AXB_F32;
+        const bool c_vec = (p.c_cs == (out_f32 ? 4 : 2)) && ((reinterpret_cast<uintptr_t>(p.c) | (uintptr_t)p.c_rs | (uintptr_t)p.c_bs) % 16 == 0);
         for (int64_t t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
             const int64_t b = t / tiles_per_batch;
             const int r = (int)(t - b * tiles_per_batch);
@@ -260,6 +275,30 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
 #pragma unroll
                     for (int i = 0; i < 32; ++i)
                         f[i] = __uint_as_float(v[i]);
+                    if (out_f32) { // fp32 result: bias / activation are separate fp32 ops in the reference, nothing to re-round
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            float x = f[i];
+                            if (p.bias && nbase + i < p.N)
+                                x = __fadd_rn(x, ld_bias(brow + (nbase + i) * p.bias_cs, p.bias_dtype));
+                            if (p.act)
+                                x = act_f(x, p.act);
+                            f[i] = x;
+                        }
+                        if (c_vec && nbase + 32 <= p.N) {
+                            uint4 *dst = reinterpret_cast<uint4 *>(crow + nbase * 4);
+#pragma unroll
+                            for (int i = 0; i < 8; ++i)
+                                dst[i] = make_uint4(__float_as_uint(f[4 * i]), __float_as_uint(f[4 * i + 1]), __float_as_uint(f[4 * i + 2]),
+                                                    __float_as_uint(f[4 * i + 3]));
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i)
+                                if (nbase + i < p.N)
+                                    *reinterpret_cast<float *>(crow + (nbase + i) * p.c_cs) = f[i];
+                        }
+                        continue;
+                    }
                     if (p.bias || p.act) {
                         // separate ops in the reference: each intermediate is rounded to the output dtype
 #pragma unroll
@@ -379,6 +418,175 @@ axb_status make_map(CUtensorMap *map, const drv::Api *api, int dtype, const void
     return AXB_OK;
 }
 
+
+// ---- fp32 matmul on the bf16 tensor pipe: exact 3-way operand split -------------------------------------------------
+// An fp32 value is the exact sum of three bf16 values: hi = bf16(x), mid = bf16(x - hi), lo = bf16(x - hi - mid)
+// (8 significand bits each, same exponent range). A.B then needs the six products whose weight is >= 2^-24 of the
+// result: hi.hi, hi.mid, mid.hi, hi.lo, lo.hi, mid.mid — every one an ordinary bf16 MMA accumulated in the SAME fp32 TMEM
+// accumulator. Dropped terms (mid.lo, lo.mid, lo.lo) are <= 3 * 2^-24 relative, i.e. the result is as accurate as an fp32
+// FMA chain (the reference's sgemm), at 6 bf16 MMAs per fp32 MAC: ~1/6 of the bf16 tensor peak instead of the CUDA-core
+// rate. tcgen05 has no IEEE-fp32 MMA; kind::tf32 truncates operands to 10 bits and would need the same 3-term split at
+// half the bf16 rate, so bf16 x 6 costs the same and reuses the bf16 data path unchanged.
+struct SplitParams {
+    const char *src;
+    uint16_t *dst;
+    int64_t rows, K, Kp;
+    int64_t rs, cs; // bytes: element (r, k) of the logical [rows][K] operand
+    int32_t nb;
+    int64_t bshape[kMaxBatchDims], bs[kMaxBatchDims];
+};
+
+__device__ __forceinline__ void split3(float x, uint16_t &hi, uint16_t &mid, uint16_t &lo) {
+    hi = red::f2bf(x);
+    const float r1 = x - red::bf2f(hi); // exact
+    mid = red::f2bf(r1);
+    const float r2 = r1 - red::bf2f(mid); // exact
+    lo = red::f2bf(r2);
+}
+
+// grid (Kp / 64, ceil(rows / 32), batch), block (32, 8). ROWS_CONTIG: the operand's row dim is the unit-stride one
+// (a transposed view): the 32x64 tile is read along rows and turned in shared memory so that writes stay k-contiguous.
+template <bool ROWS_CONTIG> __global__ void __launch_bounds__(256) split_f32_kernel(const __grid_constant__ SplitParams p) {
+    __shared__ float tile[64][33];
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int64_t k0 = (int64_t)blockIdx.x * 64, r0 = (int64_t)blockIdx.y * 32;
+    int64_t boff = 0, rem = blockIdx.z;
+#pragma unroll 1
+    for (int i = 0; i < p.nb; ++i) {
+        const int64_t q = rem / p.bshape[i];
+        boff += (rem - q * p.bshape[i]) * p.bs[i];
+        rem = q;
+    }
+    const char *src = p.src + boff;
+    uint16_t *dst = p.dst + (int64_t)blockIdx.z * p.rows * 3 * p.Kp;
+    if (ROWS_CONTIG) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { // k = k0 + ty + 8 i, r = r0 + tx
+            const int64_t k = k0 + ty + 8 * i, r = r0 + tx;
+            tile[ty + 8 * i][tx] = (k < p.K && r < p.rows) ? *reinterpret_cast<const float *>(src + r * p.rs + k * p.cs) : 0.0f;
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int64_t r = r0 + ty + 8 * i;
+        if (r >= p.rows)
+            continue;
+        const int64_t k = k0 + 2 * tx;
+        float v0, v1;
+        if (ROWS_CONTIG) {
+            v0 = tile[2 * tx][ty + 8 * i];
+            v1 = tile[2 * tx + 1][ty + 8 * i];
+        } else {
+            v0 = k < p.K ? *reinterpret_cast<const float *>(src + r * p.rs + k * p.cs) : 0.0f;
+            v1 = k + 1 < p.K ? *reinterpret_cast<const float *>(src + r * p.rs + (k + 1) * p.cs) : 0.0f;
+        }
+        uint16_t h0, m0, l0, h1, m1, l1;
+        split3(v0, h0, m0, l0);
+        split3(v1, h1, m1, l1);
+        uint16_t *row = dst + r * 3 * p.Kp + k; // k even, Kp % 64 == 0: 4-byte aligned
+        *reinterpret_cast<uint32_t *>(row) = (uint32_t)h0 | ((uint32_t)h1 << 16);
+        *reinterpret_cast<uint32_t *>(row + p.Kp) = (uint32_t)m0 | ((uint32_t)m1 << 16);
+        *reinterpret_cast<uint32_t *>(row + 2 * p.Kp) = (uint32_t)l0 | ((uint32_t)l1 << 16);
+    }
+}
+
+axb_status run_split(const Desc &d, const char *src, int64_t rows, int64_t rs, int64_t cs, const int64_t *bs, bool batched,
+                     int64_t Kp, uint16_t *dst, cudaStream_t s) {
+    SplitParams sp;
+    memset(&sp, 0, sizeof sp);
+    sp.src = src; sp.dst = dst; sp.rows = rows; sp.K = d.K; sp.Kp = Kp; sp.rs = rs; sp.cs = cs;
+    sp.nb = batched ? d.nb : 0;
+    for (int i = 0; i < sp.nb; ++i) {
+        sp.bshape[i] = d.bshape[i];
+        sp.bs[i] = bs[i];
+    }
+    const int64_t nbatch = batched ? d.batch : 1;
+    AXB_REQUIRE(nbatch <= 65535 && (rows + 31) / 32 <= 65535, AXB_ERR_UNSUPPORTED, "fp32 tensor-core matmul: operand too large to split");
+    dim3 grid((unsigned)(Kp / 64), (unsigned)((rows + 31) / 32), (unsigned)nbatch), block(32, 8);
+    if (rs == 4 && cs != 4)
+        split_f32_kernel<true><<<grid, block, 0, s>>>(sp);
+    else
+        split_f32_kernel<false><<<grid, block, 0, s>>>(sp);
+    AXB_CHECK_LAUNCH();
+    return AXB_OK;
+}
+
+axb_status launch_ff(const CUtensorMap &ma, const CUtensorMap &mb, const TcParams &p, int sm_count, cudaStream_t s);
+
+axb_status try_split_f32(const Desc &d, DeviceCtx *ctx, cudaStream_t s, bool *done) {
+    static const bool disabled = getenv("AXB_F32_MATMUL_SIMT") != nullptr; // A/B switch
+    if (disabled)
+        return AXB_OK;
+    const double flops = 2.0 * (double)d.M * (double)d.N * (double)d.K * (double)d.batch;
+    if (flops < 1.0e8 || d.M < 64 || d.N < 64 || d.K < 32 || d.M >= (1ll << 31) || d.N >= (1ll << 31) || d.K >= (1ll << 28) ||
+        d.batch > 65535)
+        return AXB_OK; // small problems: the split passes and the 128x256 tile would dominate
+    int64_t c_bs, bias_bs = 0;
+    int c_mult, bias_mult = 0;
+    if (!collapse_batch(d, d.c_bs, &c_bs, &c_mult) || (d.batch > 1 && !c_mult))
+        return AXB_OK;
+    if (d.bias && !collapse_batch(d, d.bias_bs, &bias_bs, &bias_mult))
+        return AXB_OK;
+    if (d.c_rs < 0 || d.c_cs < 0)
+        return AXB_OK;
+    auto batched = [&](const int64_t *bs) {
+        for (int i = 0; i < d.nb; ++i)
+            if (d.bshape[i] != 1 && bs[i] != 0)
+                return true;
+        return false;
+    };
+    const bool a_b = d.batch > 1 && batched(d.a_bs), b_b = d.batch > 1 && batched(d.b_bs);
+    const int64_t Kp = (d.K + 63) / 64 * 64;
+    const size_t a_bytes = (size_t)(a_b ? d.batch : 1) * d.M * 3 * Kp * 2, b_bytes = (size_t)(b_b ? d.batch : 1) * d.N * 3 * Kp * 2;
+    const drv::Api *api = drv::api();
+    if (!api)
+        return AXB_ERR_CUDA;
+    void *wa = nullptr, *wb = nullptr;
+    AXB_TRY(axb_alloc(a_bytes, s, &wa));
+    axb_status st = axb_alloc(b_bytes, s, &wb);
+    if (st != AXB_OK) {
+        axb_free(wa, s);
+        return st;
+    }
+    auto cleanup = [&]() {
+        axb_free(wa, s);
+        axb_free(wb, s);
+    };
+    // A is [M][K] with strides (a_rs, a_cs); B is used as [N][K] with strides (b_cs, b_rs)
+    st = run_split(d, d.a, d.M, d.a_rs, d.a_cs, d.a_bs, a_b, Kp, static_cast<uint16_t *>(wa), s);
+    if (st == AXB_OK)
+        st = run_split(d, d.b, d.N, d.b_cs, d.b_rs, d.b_bs, b_b, Kp, static_cast<uint16_t *>(wb), s);
+    CUtensorMap ma, mb;
+    if (st == AXB_OK)
+        st = make_map(&ma, api, AXB_BF16, wa, (uint64_t)(3 * Kp), (uint64_t)d.M, a_b ? (uint64_t)d.batch : 1, (uint64_t)(3 * Kp * 2),
+                      (uint64_t)d.M * 3 * Kp * 2, BK, BM);
+    if (st == AXB_OK)
+        st = make_map(&mb, api, AXB_BF16, wb, (uint64_t)(3 * Kp), (uint64_t)d.N, b_b ? (uint64_t)d.batch : 1, (uint64_t)(3 * Kp * 2),
+                      (uint64_t)d.N * 3 * Kp * 2, BK, BN);
+    if (st != AXB_OK) {
+        cleanup();
+        return st;
+    }
+    TcParams p;
+    memset(&p, 0, sizeof p);
+    p.M = d.M; p.N = d.N; p.K = d.K; p.batch = d.batch;
+    p.tiles_m = (int)((d.M + BM - 1) / BM);
+    p.tiles_n = (int)((d.N + BN - 1) / BN);
+    p.num_tiles = (int64_t)p.tiles_m * p.tiles_n * d.batch;
+    p.c = d.c; p.c_rs = d.c_rs; p.c_cs = d.c_cs; p.c_bs = c_bs;
+    p.bias = d.bias; p.bias_rs = d.bias_rs; p.bias_cs = d.bias_cs; p.bias_bs = bias_mult ? bias_bs : 0;
+    p.bias_dtype = d.bias_dtype; p.act = d.act; p.out_dtype = AXB_F32;
+    p.a_bmult = a_b ? 1 : 0; p.b_bmult = b_b ? 1 : 0;
+    p.split = 1; p.kbp = (int)(Kp / BK); p.Kp = Kp;
+    p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    st = launch_ff(ma, mb, p, ctx->sm_count, s);
+    cleanup(); // stream-ordered: the blocks return to the pool after the GEMM in stream order
+    if (st == AXB_OK)
+        *done = true;
+    return st;
+}
+
 template <bool A_MN, bool B_MN>
 axb_status launch(const CUtensorMap &ma, const CUtensorMap &mb, const TcParams &p, int sm_count, cudaStream_t s) {
     static bool configured = false; // per instantiation; benign race (same value)
@@ -392,10 +600,16 @@ axb_status launch(const CUtensorMap &ma, const CUtensorMap &mb, const TcParams &
     return AXB_OK;
 }
 
+axb_status launch_ff(const CUtensorMap &ma, const CUtensorMap &mb, const TcParams &p, int sm_count, cudaStream_t s) {
+    return launch<false, false>(ma, mb, p, sm_count, s);
+}
+
 } // namespace
 
 axb_status try_tcgen05(const Desc &d, int adt, int bdt, int cdt, DeviceCtx *ctx, cudaStream_t s, bool *done) {
     *done = false;
+    if (adt == AXB_F32 && bdt == AXB_F32 && cdt == AXB_F32)
+        return try_split_f32(d, ctx, s, done);
     if (!((adt == AXB_BF16 || adt == AXB_F16) && adt == bdt && cdt == adt))
         return AXB_OK;
     if (d.M * d.N * d.K < 64 * 64 * 64 || d.M >= (1ll << 31) || d.N >= (1ll << 31) || d.K >= (1ll << 31) || d.batch >= (1ll << 31))

@@ -380,7 +380,32 @@ def extras(L, capi, dev, timed, hbm_peak, tf_peak):
         dev.reduce("sum", p, [1])
 
     run("c1_readme_chain_f32_1024", readme, k=10)
+    ex["axiom_cpp_api"] = cpp_api_extras()
     return ex
+
+
+def cpp_api_extras():
+    """BASELINE configs 1, 2 and 5 through the reference's OWN C++ API (Tensor / nn / lazy graph) on Device::GPU:
+    axiom_b200/host/_build holds the unmodified reference library linked with the CUDA glue (built by build(); the
+    binaries travel to the GPU box). Wall-clock per call including graph construction, kernels and the final sync;
+    the CPU numbers are the same call on Device::CPU of the same binary (config 5: one sample)."""
+    import subprocess
+    bdir = os.path.join(ROOT, "axiom_b200", "host", "_build")
+    out = {}
+    for name, cmd in (("chains", ["axiom_chains", "4096", "16384", "20"]),
+                      ("whisper_encoder_b8", ["whisper_encoder", "8", "5", "1"]),
+                      ("whisper_encoder_b32", ["whisper_encoder", "32", "3", "0"])):
+        exe = os.path.join(bdir, cmd[0])
+        if not os.path.exists(exe):
+            out[name] = {"unavailable": "axiom_b200/host/_build not built (needs /root/reference at build time)"}
+            continue
+        try:
+            r = subprocess.run([exe] + cmd[1:], capture_output=True, text=True, timeout=600)
+            line = [l for l in r.stdout.splitlines() if l.startswith("{")][-1]
+            out[name] = json.loads(line)
+        except Exception as e:  # noqa: BLE001
+            out[name] = {"error": repr(e)}
+    return out
 
 
 if __name__ == "__main__":

@@ -160,3 +160,42 @@ def test_bf16_batched_config4_subbatch(gpu):
         exp = np.matmul(ao.bf16_to_f32(ar).astype(np.float64), ao.bf16_to_f32(bc).astype(np.float64))
         got = ao.bf16_to_f32(cc)
         assert np.all(np.abs(got - exp) <= 1e-2 * np.abs(exp) + 2e-2), float(np.max(np.abs(got - exp)))
+
+
+# ---- fp32 matmul on the tensor cores (bf16 x 6 exact split, gemm_tcgen05.cu try_split_f32) --------------------------
+@pytest.mark.parametrize("case", ["nn", "nt", "tn", "batched", "ragged", "bias_gelu", "wide_range"])
+def test_f32_tensor_core_split_is_fp32_accurate(gpu, case):
+    """Large fp32 problems run as six bf16 MMAs per product with fp32 accumulation. The result has to be as good as an
+    fp32 FMA chain: error <= 2e-6 * |A|.|B| (sgemm itself sits at ~1e-6 for K ~ 1000), far inside the reference's own
+    CPU/GPU parity tolerance of 1e-4 (tests/test_cpu_gpu_parity.cpp:376-398)."""
+    rng = np.random.default_rng(77)
+    if case == "batched":
+        a, b = rand_f32(rng, (3, 256, 320)), rand_f32(rng, (3, 320, 384))
+        got = _mm(a, b)
+    elif case == "ragged":
+        a, b = rand_f32(rng, (517, 333)), rand_f32(rng, (333, 401))
+        got = _mm(a, b)
+    elif case == "nt":
+        a, bt = rand_f32(rng, (512, 384)), rand_f32(rng, (640, 384))
+        b = bt.T
+        got = _mm(a, bt, transpose_b=True)
+    elif case == "tn":
+        at, b = rand_f32(rng, (384, 512)), rand_f32(rng, (384, 640))
+        a = at.T
+        got = _mm(at, b, transpose_a=True)
+    elif case == "wide_range":
+        a = (rand_f32(rng, (512, 512)) * np.exp2(rng.integers(-20, 20, (512, 512)))).astype(np.float32)
+        b = (rand_f32(rng, (512, 512)) * np.exp2(rng.integers(-20, 20, (512, 512)))).astype(np.float32)
+        got = _mm(a, b)
+    elif case == "bias_gelu":
+        a, w, bias = rand_f32(rng, (1024, 384), 0.5), rand_f32(rng, (768, 384), 0.1), rand_f32(rng, (768,), 0.5)
+        got = dev.matmul(dev.DeviceArray.from_numpy(a), dev.DeviceArray.from_numpy(w), transpose_b=True,
+                         bias=dev.DeviceArray.from_numpy(bias), activation="gelu").numpy()
+        y = (np.matmul(a.astype(np.float64), w.T.astype(np.float64)) + bias).astype(np.float32)
+        exp, _ = ao.unary("gelu", np.ascontiguousarray(y), ao.F32)
+        assert np.allclose(got, exp, rtol=1e-5, atol=1e-5)
+        return
+    else:
+        a, b = rand_f32(rng, (512, 1024)), rand_f32(rng, (1024, 768))
+        got = _mm(a, b)
+    _close_f32(got, a, b, rtol=2e-6)

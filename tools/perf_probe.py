@@ -96,6 +96,16 @@ def c3(kind, dt, rows=8192, n=32768):
     med, mn = timeit(fn, iters=10, warm=3)
     return dict(workload=f"c3_{kind}_{dt}_{rows}x{n}", ms_med=med, GBps_med=nb/med/1e6, GBps_best=nb/mn/1e6)
 
+def mm(dt, M, N, K, bias=0, act=None, iters=10):
+    a = dev.randn((M, K), 21); w = dev.randn((N, K), 22, 0.0, 0.05)
+    bvec = dev.randn((N,), 23) if bias else None
+    if dt == "bf16":
+        a = dev.cast(a, capi.BF16); w = dev.cast(w, capi.BF16); bvec = dev.cast(bvec, capi.BF16) if bias else None
+    fn = lambda: dev.matmul(a, w, transpose_b=True, bias=bvec, activation=act)
+    med, mn = timeit(fn, iters=iters, warm=3)
+    fl = 2.0 * M * N * K
+    return dict(workload=f"linear_{dt}_{M}x{N}x{K}_bias{bias}_{act}", ms_med=med, TFLOPs_med=fl/med/1e9, TFLOPs_best=fl/mn/1e9)
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["d2d", "relu", "exp", "gelu", "add", "c2"]
     for w in which:
@@ -103,6 +113,10 @@ if __name__ == "__main__":
             _, kind, dt = w.split(":")[:3]
             extra = [int(v) for v in w.split(":")[3:]]
             print(json.dumps(c3(kind, dt, *extra)), flush=True)
+            continue
+        if w.startswith("mm:"):
+            f = w.split(":")
+            print(json.dumps(mm(f[1], int(f[2]), int(f[3]), int(f[4]), int(f[5]) if len(f) > 5 else 0, f[6] if len(f) > 6 else None)), flush=True)
             continue
         r = bmm() if w == "bmm" else bmm_nt() if w == "bmm_nt" else bmm(8, 4096) if w == "bmm8" else d2d() if w == "d2d" else c2() if w == "c2" else add() if w == "add" else simple(w)
         print(json.dumps(r), flush=True)
