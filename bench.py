@@ -93,6 +93,8 @@ class ClockSampler:
 def run_reference(args, rank):
     if rank != 0:
         return
+    # torchrun exports OMP_NUM_THREADS=1 for its workers; the reference arm is meant to use every host core
+    os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
     from oracle import ref
     if not ref.available():
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libaxiom_ref.so was not built"}))
