@@ -307,3 +307,175 @@ def test_config3_full_size(gpu, dt):
     lns = dev.DeviceArray(ln.storage, ln.dtype, (64, n), ln.strides, ln.offset + 4000 * ln.strides[0]).numpy()
     eln, _ = ao.layer_norm(hs, odt, w.numpy(), ao.F32, b.numpy(), ao.F32, -1, 1e-5)
     assert np.allclose(lns, eln, rtol=1e-5, atol=3e-5)
+
+
+# ---- wide-row (TMA-staged) and cluster (SM-pair, DSMEM) kernels: shapes that select them, edge cases ----------------
+def _f64_softmax(x, log=False):
+    x64 = x.astype(np.float64)
+    z = x64 - x64.max(axis=-1, keepdims=True)
+    lse = np.log(np.exp(z).sum(axis=-1, keepdims=True))
+    return (z - lse) if log else np.exp(z - lse)
+
+
+@pytest.mark.parametrize("shape", [(300, 4096), (37, 5000), (150, 8192), (149, 12288), (3, 32768), (200, 16388), (9, 32764)])
+@pytest.mark.parametrize("log", [False, True])
+def test_softmax_wide_rows_f32(gpu, shape, log):
+    """Rows of 16 KiB..128 KiB take rownorm_wide.cuh (every J template, exact and masked lane maps, 1..4 stages, more
+    and fewer rows than SMs, ragged vector counts)."""
+    rng = np.random.default_rng(41)
+    x = rand_f32(rng, shape, 3.0)
+    got = dev.softmax(dev.DeviceArray.from_numpy(x), -1, log).numpy()
+    truth = _f64_softmax(x, log)
+    assert np.allclose(got, truth, rtol=1e-5, atol=1e-12 if not log else 1e-5), (shape, log)
+    if not log:
+        assert np.allclose(got.astype(np.float64).sum(axis=-1), 1.0, atol=1e-5)
+
+
+def test_softmax_wide_rows_masked_inf_nan(gpu):
+    """-inf entries (masked attention scores) give exact zeros; a NaN anywhere or an all -inf row gives an all-NaN row
+    as in the reference loop (x - max = NaN); other rows are unaffected. bf16 NaNs carry the reference encoding 0x7FC0."""
+    rng = np.random.default_rng(42)
+    x = rand_f32(rng, (160, 8192), 2.0)
+    x[:, 4000:] = -np.inf           # masked tail
+    x[7, 13] = np.nan
+    x[9, :] = -np.inf
+    got = dev.softmax(dev.DeviceArray.from_numpy(x), -1).numpy()
+    ok = np.ones(160, bool)
+    ok[[7, 9]] = False
+    assert np.all(got[ok][:, 4000:] == 0.0) and np.all(np.isnan(got[~ok]))
+    assert np.allclose(got[ok], _f64_softmax(x[ok]), rtol=1e-5, atol=1e-12)
+    xb = as_bf16(x)
+    gb = dev.softmax(dev.DeviceArray.from_numpy(xb, bf16=True), -1).numpy()
+    assert np.all(gb[~ok] == 0x7FC0), "NaN rows must use the reference's bf16 NaN encoding"
+    assert np.all(gb[ok][:, 4000:] == 0)
+    eb = ao.softmax(xb[ok], ao.BF16, -1)
+    assert np.max(np.abs(ao.bf16_to_f32(gb[ok]) - ao.bf16_to_f32(eb))) <= 2 ** -8 * ao.bf16_to_f32(eb).max()
+
+
+@pytest.mark.parametrize("dt", ["bf16", "f16"])
+@pytest.mark.parametrize("shape", [(200, 8192), (33, 32768), (150, 20000)])
+def test_softmax_wide_rows_half(gpu, dt, shape):
+    rng = np.random.default_rng(43)
+    x = rand_f32(rng, shape, 2.0)
+    if dt == "bf16":
+        xh = as_bf16(x)
+        got = ao.bf16_to_f32(dev.softmax(dev.DeviceArray.from_numpy(xh, bf16=True), -1).numpy())
+        truth = _f64_softmax(ao.bf16_to_f32(xh))
+        ulp = 2.0 ** -8
+    else:
+        xh = x.astype(np.float16)
+        got = dev.softmax(dev.DeviceArray.from_numpy(xh), -1).numpy().astype(np.float32)
+        truth = _f64_softmax(xh.astype(np.float32))
+        ulp = 2.0 ** -11
+    assert np.all(np.abs(got - truth) <= ulp * truth + 1e-7), float(np.max(np.abs(got - truth) / (truth + 1e-30)))
+
+
+def _ln_truth(x, w, b, eps, rms=False):
+    x64 = x.astype(np.float64)
+    if rms:
+        y = x64 / np.sqrt((x64 * x64).mean(axis=-1, keepdims=True) + eps)
+        return y * w if w is not None else y
+    xc = x64 - x64.mean(axis=-1, keepdims=True)
+    y = xc / np.sqrt((xc * xc).mean(axis=-1, keepdims=True) + eps)
+    if w is not None:
+        y = y * w
+    if b is not None:
+        y = y + b
+    return y
+
+
+@pytest.mark.parametrize("shape", [(600, 8192), (1200, 16384), (593, 8320), (700, 32768), (1201, 12288)])
+@pytest.mark.parametrize("affine", ["wb", "w", "none"])
+def test_layer_and_rms_norm_wide_and_cluster_f32(gpu, shape, affine):
+    """>= 4 x SM-count rows of >= 8192 elements with weight/bias select the SM-pair cluster kernel (parameters resident in
+    shared memory, DSMEM exchange of the row statistics); without parameters the single-CTA wide kernel runs. Odd row
+    counts exercise the ragged last pass, 8320 / 12288 the masked lane maps."""
+    rng = np.random.default_rng(51)
+    x = rand_f32(rng, shape, 2.0) + np.float32(0.75)
+    n = shape[-1]
+    w = (1 + 0.1 * rng.standard_normal(n)).astype(np.float32) if affine != "none" else None
+    b = (0.1 * rng.standard_normal(n)).astype(np.float32) if affine == "wb" else None
+    dx = dev.DeviceArray.from_numpy(x)
+    dw = dev.DeviceArray.from_numpy(w) if w is not None else None
+    db = dev.DeviceArray.from_numpy(b) if b is not None else None
+    got = dev.layer_norm(dx, dw, db, -1, 1e-5).numpy()
+    assert np.allclose(got, _ln_truth(x, w, b, 1e-5), rtol=1e-5, atol=2e-5), (shape, affine)
+    if w is not None:
+        got_r = dev.rms_norm(dx, dw, -1, 1e-5).numpy()
+        assert np.allclose(got_r, _ln_truth(x, w, None, 1e-5, rms=True), rtol=1e-5, atol=2e-5), (shape, affine)
+    # a 32-row sample against the oracle (the reference's own op sequence)
+    sl = slice(100, 132)
+    e, _ = ao.layer_norm(x[sl], ao.F32, w if w is not None else np.ones(n, np.float32), ao.F32,
+                         b if b is not None else np.zeros(n, np.float32), ao.F32, -1, 1e-5)
+    assert np.allclose(got[sl], e, rtol=1e-5, atol=2e-5)
+
+
+@pytest.mark.parametrize("wdt", ["f32", "bf16"])
+@pytest.mark.parametrize("shape", [(1200, 16384), (601, 32768), (800, 8192)])
+def test_layer_norm_cluster_bf16_rows(gpu, shape, wdt):
+    """bf16 rows, Float32 or bf16 parameters, bf16 and Float32 outputs (two rows per pass in the cluster kernel)."""
+    rng = np.random.default_rng(52)
+    n = shape[-1]
+    xb = as_bf16(rand_f32(rng, shape, 2.0) + np.float32(0.5))
+    w = (1 + 0.1 * rng.standard_normal(n)).astype(np.float32)
+    b = (0.1 * rng.standard_normal(n)).astype(np.float32)
+    if wdt == "bf16":
+        wq, bq = as_bf16(w), as_bf16(b)
+        dw, db = dev.DeviceArray.from_numpy(wq, bf16=True), dev.DeviceArray.from_numpy(bq, bf16=True)
+        w, b = ao.bf16_to_f32(wq), ao.bf16_to_f32(bq)
+    else:
+        dw, db = dev.DeviceArray.from_numpy(w), dev.DeviceArray.from_numpy(b)
+    dx = dev.DeviceArray.from_numpy(xb, bf16=True)
+    got32 = dev.layer_norm(dx, dw, db, -1, 1e-5, out_dtype=capi.F32).numpy()
+    # mean is rounded to bf16 by the CPU path (SURVEY App. A.4): compare against the oracle on a sample, and against
+    # the exact result with a tolerance that covers that rounding (|mean| ~ 0.5 -> 2^-9 absolute on xc / sd ~ 2)
+    sl = slice(50, 82)
+    e, _ = ao.layer_norm(xb[sl], ao.BF16, w, ao.F32, b, ao.F32, -1, 1e-5)
+    assert np.allclose(got32[sl], e, rtol=1e-5, atol=3e-5)
+    assert np.allclose(got32, _ln_truth(ao.bf16_to_f32(xb), w, b, 1e-5), rtol=1e-2, atol=5e-3)
+    got16 = dev.layer_norm(dx, dw, db, -1, 1e-5).numpy()
+    assert np.array_equal(got16, ao.f32_to_bf16(got32)), "bf16 output must be the rounded Float32 output"
+
+
+def test_layer_norm_cluster_nan_rows_and_strided_rows(gpu):
+    """A NaN / inf input row gives an all-NaN output row with the reference's bf16 NaN encoding (hardware conversion is
+    bypassed for those rows); rows that are slices of a wider tensor (outer stride != row length) take the same path."""
+    rng = np.random.default_rng(53)
+    n = 8192
+    base = rand_f32(rng, (640, n + 64), 1.5)
+    base[5, 10] = np.nan
+    base[6, 11] = np.inf
+    w = (1 + 0.1 * rng.standard_normal(n)).astype(np.float32)
+    b = (0.1 * rng.standard_normal(n)).astype(np.float32)
+    dbase = dev.DeviceArray.from_numpy(base)
+    view = dev.DeviceArray(dbase.storage, dbase.dtype, (640, n), dbase.strides, dbase.offset)  # row stride (n + 64) * 4
+    got = dev.layer_norm(view, dev.DeviceArray.from_numpy(w), dev.DeviceArray.from_numpy(b), -1, 1e-5).numpy()
+    x = base[:, :n]
+    ok = np.ones(640, bool)
+    ok[[5, 6]] = False
+    assert np.all(np.isnan(got[~ok]))
+    assert np.allclose(got[ok], _ln_truth(x[ok], w, b, 1e-5), rtol=1e-5, atol=2e-5)
+    xb = as_bf16(np.ascontiguousarray(x))
+    gb = dev.layer_norm(dev.DeviceArray.from_numpy(xb, bf16=True), dev.DeviceArray.from_numpy(w), dev.DeviceArray.from_numpy(b),
+                        -1, 1e-5).numpy()
+    assert np.all(gb[~ok] == 0x7FC0)
+
+
+@pytest.mark.parametrize("op", ["argmax", "argmin"])
+def test_argreduce_long_rows_with_heavy_ties(gpu, op):
+    """Rows drawn from 9 distinct values: thousands of exact ties per row, so any lapse in 'first occurrence wins' shows.
+    {64, 300001}: the split (multi-CTA) path; {4096, 4096} / {2100, 33000}: one CTA / one warp per row."""
+    rng = np.random.default_rng(61)
+    for shape in ((64, 300001), (4096, 4096), (2100, 33000), (5, 1 << 20)):
+        x = rng.integers(-4, 5, size=shape).astype(np.float32)
+        x[0, :] = 3.0
+        x[1, ::2] = np.nan
+        got = dev.argreduce(op, dev.DeviceArray.from_numpy(x), 1).numpy()
+        exp = (np.nanargmax if op == "argmax" else np.nanargmin)(x, axis=1)
+        assert np.array_equal(got, exp), (op, shape)
+        xb = as_bf16(np.nan_to_num(x))
+        gb = dev.argreduce(op, dev.DeviceArray.from_numpy(xb, bf16=True), 1).numpy()
+        eb = (np.argmax if op == "argmax" else np.argmin)(np.nan_to_num(x), axis=1)
+        assert np.array_equal(gb, eb), (op, shape, "bf16")
+        xi = np.nan_to_num(x).astype(np.int32)
+        assert np.array_equal(dev.argreduce(op, dev.DeviceArray.from_numpy(xi), 1).numpy(), eb), (op, shape, "i32")
