@@ -29,5 +29,8 @@ for dt in ("f32", "bf16"):
 if "bmm" in which:
     A = dev.cast(dev.randn((8, 4096, 4096), 11), capi.BF16); B = dev.cast(dev.randn((8, 4096, 4096), 12, 0.0, 1 / 64), capi.BF16)
     for _ in range(reps): dev.matmul(A, B)
+if "mm32" in which:
+    A = dev.randn((4096, 4096), 31); B = dev.randn((4096, 4096), 32, 0.0, 1 / 64)
+    for _ in range(reps): dev.matmul(A, B)
 dev.synchronize()
 print("ok")
