@@ -11,8 +11,8 @@
 //   warp 1      MMA issuer   : one elected thread issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=256, K=16),
 //                              A/B straight from shared memory through UMMA descriptors, fp32 accumulators in TMEM;
 //                              tcgen05.commit releases ring slots / publishes finished accumulators
-//   warps 2..5  epilogue     : tcgen05.ld (32 lanes x 32 columns per warp) -> bias / activation -> one rounding ->
-//                              128-bit global stores. TMEM holds TWO 128x256 fp32 accumulators (all 512 columns), so the
+//   warps 2..9  epilogue     : tcgen05.ld (32 lanes x 32 columns per warp) -> bias / activation -> one rounding ->
+//                              128-bit global stores (two warps per TMEM lane quarter, alternate column chunks). TMEM holds TWO 128x256 fp32 accumulators (all 512 columns), so the
 //                              epilogue of tile i overlaps the MMAs of tile i+1.
 // Transposes are never materialised: an operand whose contraction dim is contiguous is fed K-major, one whose M/N dim
 // is contiguous is fed MN-major (instruction-descriptor major bits + the matching UMMA canonical layout), which covers
@@ -40,7 +40,7 @@ constexpr int A_BYTES = BM * BK * 2;        // 16 KiB
 constexpr int B_BYTES = BN * BK * 2;        // 32 KiB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_THREADS = 320; // TMA producer, MMA issuer, 8 epilogue warps
 constexpr uint32_t TMEM_COLS = 512;
 
 struct TcParams {
@@ -158,7 +158,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(tfull_bar(a), 1);
-            mbar_init(tempty_bar(a), 4); // one arrive per epilogue warp
+            mbar_init(tempty_bar(a), 8); // one arrive per epilogue warp
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -248,12 +248,35 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             }
         }
     } else {
-        // epilogue: warp w may only touch TMEM lanes [32*(w%4), 32*(w%4)+32)
-        const int q = warp & 3;
+        // epilogue: EIGHT warps. Warp w may only touch TMEM lanes [32*(w%4), 32*(w%4)+32); warps 2..5 and 6..9 cover the
+        // four lane quarters twice and take alternate 32-column chunks, so every SM sub-partition runs two epilogue warps.
+        // (The first version had four warps, per-element bias loads / dtype branches / software bf16 rounding: ~240
+        // instructions per 32 outputs and ~25 us per 128x256 tile — as long as the MMAs of a K = 4096 tile, and 10x the
+        // MMAs of a K = 384 Linear layer. ncu: tensor pipe 9-20 % active on whisper's layers.)
+        const int q = warp & 3, half = (warp - 2) >> 2;
         int acc = 0;
         uint32_t acc_phase = 0;
-        const bool out_f32 = p.out_dtype == AXB_F32;
-        const bool c_vec = (p.c_cs == (out_f32 ? 4 : 2)) && ((reinterpret_cast<uintptr_t>(p.c) | (uintptr_t)p.c_rs | (uintptr_t)p.c_bs) % 16 == 0);
+        const bool out_f32 = p.out_dtype == AXB_F32, out_bf16 = p.out_dtype == AXB_BF16;
+        const int osz = out_f32 ? 4 : 2;
+        const bool c_vec = (p.c_cs == osz) && ((reinterpret_cast<uintptr_t>(p.c) | (uintptr_t)p.c_rs | (uintptr_t)p.c_bs) % 16 == 0);
+        // bias as a row vector shared by all rows (nn::Linear): read once per chunk with vector loads
+        const int bsz = p.bias_dtype == AXB_F32 ? 4 : 2;
+        const bool bias_vec = p.bias && p.bias_rs == 0 && p.bias_cs == bsz && ((reinterpret_cast<uintptr_t>(p.bias) | (uintptr_t)p.bias_bs) % 16 == 0);
+        auto round_out = [&](float (&f)[32]) { // round to the half output type and come back (hardware converters)
+            if (out_bf16) {
+#pragma unroll
+                for (int i = 0; i < 32; i += 2) {
+                    uint32_t h;
+                    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(f[i + 1]), "f"(f[i]));
+                    f[i] = __uint_as_float(h << 16);
+                    f[i + 1] = __uint_as_float(h & 0xFFFF0000u);
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                    f[i] = red::h2f(red::f2h(f[i]));
+            }
+        };
         for (int64_t t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
             const int64_t b = t / tiles_per_batch;
             const int r = (int)(t - b * tiles_per_batch);
@@ -265,75 +288,130 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             char *crow = p.c + b * p.c_bs + m * p.c_rs;
             const char *brow = p.bias ? p.bias + b * p.bias_bs + m * p.bias_rs : nullptr;
 #pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
+            for (int c = half; c < BN / 32; c += 2) {
+                const int64_t nbase = n0 + c * 32;
+                if (nbase >= p.N)
+                    break; // warp-uniform
                 uint32_t v[32];
                 tc_ld32(taddr + c * 32, v);
                 tc_wait_ld();
-                const int64_t nbase = n0 + c * 32;
-                if (m < p.M && nbase < p.N) {
-                    float f[32];
+                if (m >= p.M)
+                    continue;
+                float f[32];
 #pragma unroll
-                    for (int i = 0; i < 32; ++i)
-                        f[i] = __uint_as_float(v[i]);
-                    if (out_f32) { // fp32 result: bias / activation are separate fp32 ops in the reference, nothing to re-round
+                for (int i = 0; i < 32; ++i)
+                    f[i] = __uint_as_float(v[i]);
+                const bool full = nbase + 32 <= p.N;
+                // ---- bias: a separate op in the reference, applied to the matmul result rounded to its dtype ----------
+                if (p.bias) {
+                    if (!out_f32)
+                        round_out(f);
+                    if (bias_vec && full) {
+                        const char *bp = p.bias + b * p.bias_bs + nbase * bsz;
+                        if (bsz == 4) {
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) {
-                            float x = f[i];
-                            if (p.bias && nbase + i < p.N)
-                                x = __fadd_rn(x, ld_bias(brow + (nbase + i) * p.bias_cs, p.bias_dtype));
-                            if (p.act)
-                                x = act_f(x, p.act);
-                            f[i] = x;
-                        }
-                        if (c_vec && nbase + 32 <= p.N) {
-                            uint4 *dst = reinterpret_cast<uint4 *>(crow + nbase * 4);
-#pragma unroll
-                            for (int i = 0; i < 8; ++i)
-                                dst[i] = make_uint4(__float_as_uint(f[4 * i]), __float_as_uint(f[4 * i + 1]), __float_as_uint(f[4 * i + 2]),
-                                                    __float_as_uint(f[4 * i + 3]));
+                            for (int i = 0; i < 32; i += 4) {
+                                const float4 w = __ldg(reinterpret_cast<const float4 *>(bp) + (i >> 2));
+                                f[i] += w.x; f[i + 1] += w.y; f[i + 2] += w.z; f[i + 3] += w.w;
+                            }
                         } else {
 #pragma unroll
-                            for (int i = 0; i < 32; ++i)
-                                if (nbase + i < p.N)
-                                    *reinterpret_cast<float *>(crow + (nbase + i) * p.c_cs) = f[i];
-                        }
-                        continue;
-                    }
-                    if (p.bias || p.act) {
-                        // separate ops in the reference: each intermediate is rounded to the output dtype
+                            for (int i = 0; i < 32; i += 8) {
+                                const uint4 w = __ldg(reinterpret_cast<const uint4 *>(bp) + (i >> 3));
+                                const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) {
-                            float x = f[i];
-                            if (p.bias && nbase + i < p.N) {
-                                x = p.out_dtype == AXB_BF16 ? red::bf2f(red::f2bf(x)) : red::h2f(red::f2h(x));
-                                x += ld_bias(brow + (nbase + i) * p.bias_cs, p.bias_dtype);
+                                for (int k = 0; k < 4; ++k) {
+                                    if (p.bias_dtype == AXB_BF16) {
+                                        f[i + 2 * k] += __uint_as_float(ww[k] << 16);
+                                        f[i + 2 * k + 1] += __uint_as_float(ww[k] & 0xFFFF0000u);
+                                    } else {
+                                        f[i + 2 * k] += red::h2f((uint16_t)(ww[k] & 0xFFFFu));
+                                        f[i + 2 * k + 1] += red::h2f((uint16_t)(ww[k] >> 16));
+                                    }
+                                }
                             }
-                            if (p.act) {
-                                x = p.out_dtype == AXB_BF16 ? red::bf2f(red::f2bf(x)) : red::h2f(red::f2h(x));
-                                x = act_f(x, p.act);
-                            }
-                            f[i] = x;
                         }
-                    }
-                    uint32_t h[16];
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        const uint32_t lo = p.out_dtype == AXB_BF16 ? red::f2bf(f[2 * i]) : red::f2h(f[2 * i]);
-                        const uint32_t hi = p.out_dtype == AXB_BF16 ? red::f2bf(f[2 * i + 1]) : red::f2h(f[2 * i + 1]);
-                        h[i] = lo | (hi << 16);
-                    }
-                    if (c_vec && nbase + 32 <= p.N) {
-                        uint4 *dst = reinterpret_cast<uint4 *>(crow + nbase * 2);
-#pragma unroll
-                        for (int i = 0; i < 4; ++i)
-                            dst[i] = make_uint4(h[4 * i], h[4 * i + 1], h[4 * i + 2], h[4 * i + 3]);
                     } else {
 #pragma unroll
                         for (int i = 0; i < 32; ++i)
                             if (nbase + i < p.N)
-                                *reinterpret_cast<uint16_t *>(crow + (nbase + i) * p.c_cs) =
-                                    (uint16_t)((i & 1) ? (h[i >> 1] >> 16) : (h[i >> 1] & 0xFFFFu));
+                                f[i] += ld_bias(brow + (nbase + i) * p.bias_cs, p.bias_dtype);
                     }
+                }
+                // ---- activation (also a separate op: its input is rounded to the output dtype first) -----------------
+                if (p.act) {
+                    if (!out_f32)
+                        round_out(f);
+                    switch (p.act) {
+                    case AXB_OP_RELU:
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) f[i] = f[i] > 0.0f ? f[i] : 0.0f;
+                        break;
+                    case AXB_OP_GELU:
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) f[i] = hwym::Gelu(f[i]);
+                        break;
+                    case AXB_OP_SILU:
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) f[i] = hwym::Silu(f[i]);
+                        break;
+                    case AXB_OP_SIGMOID:
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) f[i] = hwym::Sigmoid(f[i]);
+                        break;
+                    default:
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) f[i] = hwym::Tanh(f[i]);
+                        break;
+                    }
+                }
+                // ---- store -----------------------------------------------------------------------------------------
+                if (out_f32) {
+                    if (c_vec && full) {
+                        uint4 *dst = reinterpret_cast<uint4 *>(crow + nbase * 4);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i)
+                            dst[i] = make_uint4(__float_as_uint(f[4 * i]), __float_as_uint(f[4 * i + 1]), __float_as_uint(f[4 * i + 2]),
+                                                __float_as_uint(f[4 * i + 3]));
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i)
+                            if (nbase + i < p.N)
+                                *reinterpret_cast<float *>(crow + (nbase + i) * p.c_cs) = f[i];
+                    }
+                    continue;
+                }
+                uint32_t h[16];
+                if (out_bf16) {
+                    // hardware pack (NaN -> 0x7FFF); the reference encodes NaN as 0x7FC0 (bfloat16.hpp:16-27): chunks that
+                    // contain a NaN are re-packed in software (rare)
+                    float nan_acc = 0.0f;
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(h[i]) : "f"(f[2 * i + 1]), "f"(f[2 * i]));
+                        asm("max.NaN.f32 %0, %0, %1, %2;" : "+f"(nan_acc) : "f"(f[2 * i]), "f"(f[2 * i + 1]));
+                    }
+                    if (nan_acc != nan_acc) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i)
+                            h[i] = (uint32_t)red::f2bf(f[2 * i]) | ((uint32_t)red::f2bf(f[2 * i + 1]) << 16);
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i)
+                        h[i] = (uint32_t)red::f2h(f[2 * i]) | ((uint32_t)red::f2h(f[2 * i + 1]) << 16);
+                }
+                if (c_vec && full) {
+                    uint4 *dst = reinterpret_cast<uint4 *>(crow + nbase * 2);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        dst[i] = make_uint4(h[4 * i], h[4 * i + 1], h[4 * i + 2], h[4 * i + 3]);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i)
+                        if (nbase + i < p.N)
+                            *reinterpret_cast<uint16_t *>(crow + (nbase + i) * p.c_cs) =
+                                (uint16_t)((i & 1) ? (h[i >> 1] >> 16) : (h[i >> 1] & 0xFFFFu));
                 }
             }
             tc_fence_before();
