@@ -522,12 +522,13 @@ __device__ __forceinline__ void split3(float x, uint16_t &hi, uint16_t &mid, uin
     lo = red::f2bf(r2);
 }
 
-// grid (Kp / 64, ceil(rows / 32), batch), block (32, 8). ROWS_CONTIG: the operand's row dim is the unit-stride one
-// (a transposed view): the 32x64 tile is read along rows and turned in shared memory so that writes stay k-contiguous.
+// ROWS_CONTIG = false (the common case: K is the unit-stride dim): grid (ceil(Kp / 256), ceil(rows / 8), batch), block
+// (32, 8): a thread converts 8 consecutive k of one row — two 128-bit loads, three 128-bit stores.
+// ROWS_CONTIG = true (a transposed view: rows are unit-stride): grid (Kp / 64, ceil(rows / 32), batch): the 32x64 tile is
+// read along rows and turned in shared memory so that writes stay k-contiguous.
 template <bool ROWS_CONTIG> __global__ void __launch_bounds__(256) split_f32_kernel(const __grid_constant__ SplitParams p) {
-    __shared__ float tile[64][33];
+    __shared__ float tile[ROWS_CONTIG ? 64 : 1][33];
     const int tx = threadIdx.x, ty = threadIdx.y;
-    const int64_t k0 = (int64_t)blockIdx.x * 64, r0 = (int64_t)blockIdx.y * 32;
     int64_t boff = 0, rem = blockIdx.z;
 #pragma unroll 1
     for (int i = 0; i < p.nb; ++i) {
@@ -537,28 +538,50 @@ template <bool ROWS_CONTIG> __global__ void __launch_bounds__(256) split_f32_ker
     }
     const char *src = p.src + boff;
     uint16_t *dst = p.dst + (int64_t)blockIdx.z * p.rows * 3 * p.Kp;
-    if (ROWS_CONTIG) {
+    if (!ROWS_CONTIG) {
+        const int64_t r = (int64_t)blockIdx.y * 8 + ty, k = ((int64_t)blockIdx.x * 32 + tx) * 8;
+        if (r >= p.rows || k >= p.Kp)
+            return;
+        float v[8];
+        const char *rp = src + r * p.rs;
+        if (p.cs == 4 && k + 8 <= p.K && ((reinterpret_cast<uintptr_t>(rp) + k * 4) & 15) == 0) {
+            const float4 a = *reinterpret_cast<const float4 *>(rp + k * 4), b = *reinterpret_cast<const float4 *>(rp + k * 4 + 16);
+            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+        } else {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) { // k = k0 + ty + 8 i, r = r0 + tx
-            const int64_t k = k0 + ty + 8 * i, r = r0 + tx;
-            tile[ty + 8 * i][tx] = (k < p.K && r < p.rows) ? *reinterpret_cast<const float *>(src + r * p.rs + k * p.cs) : 0.0f;
+            for (int i = 0; i < 8; ++i)
+                v[i] = k + i < p.K ? *reinterpret_cast<const float *>(rp + (k + i) * p.cs) : 0.0f;
         }
-        __syncthreads();
+        uint32_t h[4], m[4], l[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            uint16_t h0, m0, l0, h1, m1, l1;
+            split3(v[2 * i], h0, m0, l0);
+            split3(v[2 * i + 1], h1, m1, l1);
+            h[i] = (uint32_t)h0 | ((uint32_t)h1 << 16);
+            m[i] = (uint32_t)m0 | ((uint32_t)m1 << 16);
+            l[i] = (uint32_t)l0 | ((uint32_t)l1 << 16);
+        }
+        uint16_t *row = dst + r * 3 * p.Kp + k; // k % 8 == 0 and Kp % 64 == 0: 16-byte aligned
+        *reinterpret_cast<uint4 *>(row) = make_uint4(h[0], h[1], h[2], h[3]);
+        *reinterpret_cast<uint4 *>(row + p.Kp) = make_uint4(m[0], m[1], m[2], m[3]);
+        *reinterpret_cast<uint4 *>(row + 2 * p.Kp) = make_uint4(l[0], l[1], l[2], l[3]);
+        return;
     }
+    const int64_t k0 = (int64_t)blockIdx.x * 64, r0 = (int64_t)blockIdx.y * 32;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { // k = k0 + ty + 8 i, r = r0 + tx
+        const int64_t k = k0 + ty + 8 * i, r = r0 + tx;
+        tile[ROWS_CONTIG ? ty + 8 * i : 0][tx] = (k < p.K && r < p.rows) ? *reinterpret_cast<const float *>(src + r * p.rs + k * p.cs) : 0.0f;
+    }
+    __syncthreads();
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const int64_t r = r0 + ty + 8 * i;
         if (r >= p.rows)
             continue;
         const int64_t k = k0 + 2 * tx;
-        float v0, v1;
-        if (ROWS_CONTIG) {
-            v0 = tile[2 * tx][ty + 8 * i];
-            v1 = tile[2 * tx + 1][ty + 8 * i];
-        } else {
-            v0 = k < p.K ? *reinterpret_cast<const float *>(src + r * p.rs + k * p.cs) : 0.0f;
-            v1 = k + 1 < p.K ? *reinterpret_cast<const float *>(src + r * p.rs + (k + 1) * p.cs) : 0.0f;
-        }
+        const float v0 = tile[ROWS_CONTIG ? 2 * tx : 0][ty + 8 * i], v1 = tile[ROWS_CONTIG ? 2 * tx + 1 : 0][ty + 8 * i];
         uint16_t h0, m0, l0, h1, m1, l1;
         split3(v0, h0, m0, l0);
         split3(v1, h1, m1, l1);
@@ -580,12 +603,14 @@ axb_status run_split(const Desc &d, const char *src, int64_t rows, int64_t rs, i
         sp.bs[i] = bs[i];
     }
     const int64_t nbatch = batched ? d.batch : 1;
-    AXB_REQUIRE(nbatch <= 65535 && (rows + 31) / 32 <= 65535, AXB_ERR_UNSUPPORTED, "fp32 tensor-core matmul: operand too large to split");
-    dim3 grid((unsigned)(Kp / 64), (unsigned)((rows + 31) / 32), (unsigned)nbatch), block(32, 8);
-    if (rs == 4 && cs != 4)
-        split_f32_kernel<true><<<grid, block, 0, s>>>(sp);
+    const bool rows_contig = rs == 4 && cs != 4;
+    const int64_t gy = rows_contig ? (rows + 31) / 32 : (rows + 7) / 8;
+    AXB_REQUIRE(nbatch <= 65535 && gy <= 65535, AXB_ERR_UNSUPPORTED, "fp32 tensor-core matmul: operand too large to split");
+    dim3 block(32, 8);
+    if (rows_contig)
+        split_f32_kernel<true><<<dim3((unsigned)(Kp / 64), (unsigned)gy, (unsigned)nbatch), block, 0, s>>>(sp);
     else
-        split_f32_kernel<false><<<grid, block, 0, s>>>(sp);
+        split_f32_kernel<false><<<dim3((unsigned)((Kp + 255) / 256), (unsigned)gy, (unsigned)nbatch), block, 0, s>>>(sp);
     AXB_CHECK_LAUNCH();
     return AXB_OK;
 }

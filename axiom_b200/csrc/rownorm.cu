@@ -111,17 +111,21 @@ __global__ void __launch_bounds__(THREADS == 32 ? 256 : THREADS) rownorm_kernel(
             m = row_allreduce<THREADS, FMax>(m, smem);
             float s = 0.0f;
             if (KIND == K_SOFTMAX) {
-                if (RESIDENT) { // e = exp(x - m) kept in registers, y = e / s
-                    sweep([&](int, float &v) { v = expf(__fsub_rn(v, m)); s += v; }, false, false);
+                // one IEEE reciprocal per row instead of a division per element, and the 6-instruction exp of the wide
+                // kernel (rownorm_wide.cuh w_exp_neg): both inside the 1e-5 contract the tests state
+                if (RESIDENT) { // e = exp(x - m) kept in registers, y = e * (1 / s)
+                    sweep([&](int, float &v) { v = w_exp_neg(__fsub_rn(v, m)); s += v; }, false, false);
                     s = row_allreduce<THREADS, FAdd>(s, smem);
-                    sweep([&](int, float &v) { v = __fdiv_rn(v, s); }, false, true);
+                    const float inv = __fdiv_rn(1.0f, s);
+                    sweep([&](int, float &v) { v = __fmul_rn(v, inv); }, false, true);
                 } else {
-                    sweep([&](int, float &v) { s += expf(__fsub_rn(v, m)); }, true, false);
+                    sweep([&](int, float &v) { s += w_exp_neg(__fsub_rn(v, m)); }, true, false);
                     s = row_allreduce<THREADS, FAdd>(s, smem);
-                    sweep([&](int, float &v) { v = __fdiv_rn(expf(__fsub_rn(v, m)), s); }, true, true);
+                    const float inv = __fdiv_rn(1.0f, s);
+                    sweep([&](int, float &v) { v = __fmul_rn(w_exp_neg(__fsub_rn(v, m)), inv); }, true, true);
                 }
             } else {
-                sweep([&](int, float &v) { s += expf(__fsub_rn(v, m)); }, !RESIDENT, false);
+                sweep([&](int, float &v) { s += w_exp_neg(__fsub_rn(v, m)); }, !RESIDENT, false);
                 s = row_allreduce<THREADS, FAdd>(s, smem);
                 const float ls = logf(s);
                 sweep([&](int, float &v) { v = __fsub_rn(__fsub_rn(v, m), ls); }, !RESIDENT, true);
@@ -134,10 +138,10 @@ __global__ void __launch_bounds__(THREADS == 32 ? 256 : THREADS) rownorm_kernel(
             float q = 0.0f;
             sweep([&](int, float &v) { v = __fsub_rn(v, mean); q += __fmul_rn(v, v); }, !RESIDENT, false);
             q = row_allreduce<THREADS, FAdd>(q, smem);
-            const float sd = __fsqrt_rn(__fadd_rn(__fdiv_rn(q, (float)n), p.eps));
+            const float rsd = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(__fdiv_rn(q, (float)n), p.eps)));
             sweep([&](int e, float &v) {
                 float xc = RESIDENT ? v : __fsub_rn(v, mean);
-                float y = __fdiv_rn(xc, sd);
+                float y = __fmul_rn(xc, rsd);
                 if (p.w)
                     y = __fmul_rn(y, ld_dyn(p.w + (int64_t)e * p.w_es, p.w_dtype));
                 if (p.b)
@@ -149,9 +153,9 @@ __global__ void __launch_bounds__(THREADS == 32 ? 256 : THREADS) rownorm_kernel(
             sweep([&](int, float &v) { q += round_to<In>(__fmul_rn(v, v)); }, true, false);
             q = row_allreduce<THREADS, FAdd>(q, smem);
             const float ms = round_to<In>(__fdiv_rn(q, (float)n));
-            const float rms = __fsqrt_rn(__fadd_rn(ms, p.eps));
+            const float rrms = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(ms, p.eps)));
             sweep([&](int e, float &v) {
-                float y = __fdiv_rn(v, rms);
+                float y = __fmul_rn(v, rrms);
                 if (p.w)
                     y = __fmul_rn(y, ld_dyn(p.w + (int64_t)e * p.w_es, p.w_dtype));
                 v = y;
@@ -256,6 +260,9 @@ template <typename In, typename Out, int KIND> axb_status launch_cfg(const RowPa
     } else if (n <= 1024) {
         int64_t g = std::min<int64_t>((p.rows + 7) / 8, max_ctas);
         rownorm_kernel<In, Out, 32, 32, KIND, true><<<(unsigned)g, 256, 0, s>>>(p);
+    } else if (n <= 2048) { // e.g. attention rows of 1500: 8 values per thread keep the unrolled sweeps short
+        int64_t g = std::min<int64_t>(p.rows, max_ctas);
+        rownorm_kernel<In, Out, 256, 8, KIND, true><<<(unsigned)g, 256, 0, s>>>(p);
     } else if (n <= 8192) {
         int64_t g = std::min<int64_t>(p.rows, max_ctas);
         rownorm_kernel<In, Out, 256, 32, KIND, true><<<(unsigned)g, 256, 0, s>>>(p);

@@ -447,9 +447,9 @@ Tensor gpu_conv1d(const Tensor &input, const Tensor &weight, const Tensor &bias,
 Tensor gpu_scaled_dot_product_attention(const Tensor &query, const Tensor &key, const Tensor &value, const Tensor &mask,
                                         float scale, bool is_causal) {
     const Tensor q = on_gpu(query), k = on_gpu(key), v = on_gpu(value);
-    Tensor s = cuda::gpu_matmul(q, k, false, true); // (B, H, Lq, Lk)
-    Tensor sc = Tensor::full({1}, scale, Device::CPU).astype(s.dtype()).to(Device::GPU);
-    s = cuda::gpu_binary(ops::OpType::Multiply, s, sc);
+    // scale the (B, H, Lq, D) queries, not the (B, H, Lq, Lk) scores: Lk / D times less data through the kernel
+    Tensor sc = Tensor::full({1}, scale, Device::CPU).astype(q.dtype()).to(Device::GPU);
+    Tensor s = cuda::gpu_matmul(cuda::gpu_binary(ops::OpType::Multiply, q, sc), k, false, true); // (B, H, Lq, Lk)
     const size_t Lq = q.shape()[2], Lk = k.shape()[2];
     if (is_causal) {
         // kv position j is visible to query i iff j <= i (q_block_offset + i, flash_attention_cpu.cpp:76-89)
