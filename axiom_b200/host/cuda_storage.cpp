@@ -85,9 +85,11 @@ void CudaStorage::copy_from(const Storage &other) {
     if (n == 0)
         return;
     if (other.device() == Device::CPU) {
-        // pageable host memory: the copy is staged by the driver and complete with respect to the host buffer on return
+        // The reference's host tensors are pageable memory: cudaMemcpyAsync stages such a source through the driver's
+        // pinned buffer and returns once the HOST buffer has been consumed, so the caller may free or overwrite it
+        // immediately; the device side stays ordered on the backend stream. No stream sync here — scalar operands
+        // (`x + 1.0f` uploads a one-element tensor, tensor_operators.hpp) would otherwise serialise host and GPU.
         check(axb_memcpy_h2d(ptr_, other.data(), n, nullptr), "axb_memcpy_h2d");
-        check(axb_stream_sync(nullptr), "axb_stream_sync");
     } else {
         auto *src = dynamic_cast<const CudaStorage *>(&other);
         if (!src)
