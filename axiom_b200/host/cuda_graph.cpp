@@ -212,6 +212,49 @@ struct Lowering {
             const auto &cp = get_params<ConvParams>(n->params);
             r = backends::cuda::gpu_conv1d_impl(input(n, 0), input(n, 1), input(n, 2), cp.stride.at(0), cp.padding.at(0),
                                                 cp.dilation.at(0), cp.groups);
+        } else if (op == OpType::BatchNorm1D) {
+            // inference batch norm over the channel axis 1 (nn/normalization.cpp:88-106, lazy node graph_registry.cpp:637-655):
+            // (x - running_mean) * 1/sqrt(running_var + eps) * weight + bias as ONE elementwise program in fp32
+            Tensor x = input(n, 0), w = input(n, 1), b = input(n, 2), mean = input(n, 3), var = input(n, 4);
+            if (x.ndim() < 2 || !mean.storage() || !var.storage())
+                throw ShapeError("batch_norm: expected (N, C, ...) input and running statistics");
+            Shape ps(x.ndim(), 1);
+            ps[1] = x.shape()[1];
+            auto chan = [&](const Tensor &t) { return backends::cuda::gpu_contiguous(t).reshape(ps); };
+            std::vector<Tensor> ops_t{x, chan(mean), chan(var)};
+            const int32_t F = AXB_F32;
+            auto mk = [&](int32_t opc, int32_t s0, int32_t s1, double imm = 0.0) {
+                axb_instr in{};
+                in.op = opc; in.dtype = F; in.src[0] = s0; in.src[1] = s1; in.src[2] = AXB_SRC_NONE; in.imm = imm;
+                return in;
+            };
+            std::vector<axb_instr> pr;
+            pr.push_back(mk(AXB_OP_ADD, 2, AXB_SRC_IMM, (double)get_params<NormParams>(n->params).eps)); // var + eps
+            pr.push_back(mk(AXB_OP_SQRT, AXB_SRC_VALUE(0), AXB_SRC_NONE));
+            pr.push_back(mk(AXB_OP_RECIPROCAL, AXB_SRC_VALUE(1), AXB_SRC_NONE));
+            pr.push_back(mk(AXB_OP_SUB, 0, 1));                                                            // x - mean
+            pr.push_back(mk(AXB_OP_MUL, AXB_SRC_VALUE(3), AXB_SRC_VALUE(2)));
+            if (w.storage() && w.size() > 0) {
+                ops_t.push_back(chan(w));
+                pr.push_back(mk(AXB_OP_MUL, AXB_SRC_VALUE((int32_t)pr.size() - 1), (int32_t)ops_t.size() - 1));
+            }
+            if (b.storage() && b.size() > 0) {
+                ops_t.push_back(chan(b));
+                pr.push_back(mk(AXB_OP_ADD, AXB_SRC_VALUE((int32_t)pr.size() - 1), (int32_t)ops_t.size() - 1));
+            }
+            if (n->output_dtype != DType::Float32) {
+                axb_instr c = mk(AXB_OP_CAST, AXB_SRC_VALUE((int32_t)pr.size() - 1), AXB_SRC_NONE);
+                c.dtype = to_axb_dtype(n->output_dtype);
+                pr.push_back(c);
+            }
+            r = empty_gpu(n->output_shape, n->output_dtype);
+            if (r.size() != 0) {
+                std::vector<axb_tensor> ins;
+                for (auto &t : ops_t)
+                    ins.push_back(describe(t));
+                const axb_tensor od = describe(r);
+                check(axb_elementwise(pr.data(), (int)pr.size(), ins.data(), (int)ins.size(), &od, nullptr), "axb_elementwise (batch_norm)");
+            }
         } else if (op == OpType::Reshape) {
             Tensor x = input(n, 0);
             const Shape &ns = get_params<ReshapeParams>(n->params).new_shape;

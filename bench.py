@@ -255,6 +255,10 @@ def main():
         exp = np.where(hc > 0, (np.maximum(ha, 0) + np.float32(1)) * hb, np.float32(0))
         assert np.array_equal(ho, exp), "e2e result differs from the closed form"
 
+    multi = None
+    if dist is not None and not args.no_extras:
+        multi = sharded_full_reduction(L, capi, dev, dist, world, local_rank, barrier, max_over_ranks)
+
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -285,6 +289,8 @@ def main():
         "clocks": clocks,
     }
 
+    if multi is not None:
+        result["extras"] = {"c3_full_sum_row_sharded": multi}
     if world == 1:
         result["cpu_baseline"] = cpu_baseline()
         if not args.no_extras:
@@ -295,6 +301,42 @@ def main():
     print(json.dumps(result))
     if dist is not None:
         dist.destroy_process_group()
+
+
+def sharded_full_reduction(L, capi, dev, dist, world, local_rank, barrier, max_over_ranks):
+    """the one exchange step of the path. Every rank owns a {8192, 32768} fp32 block of rows of a
+    {8192 * world, 32768} tensor, reduces it to one scalar with axb_reduce (full sum, one pass over HBM) and the per-shard
+    scalars are combined with ONE NCCL all-reduce (axiom_b200/shard.py combine_full_reduction). Timed end to end on the
+    device (kernel + collective), max over ranks; checked against the sum of the per-rank partials."""
+    import torch
+    from axiom_b200 import shard
+    rows, n = 8192, 32768
+    x = dev.randn((rows, n), 70 + local_rank)
+    out = dev.DeviceArray.empty((1,), capi.F32)
+    xd, od = x.desc(), out.desc()
+    ax = (ctypes.c_int32 * 2)(0, 1)
+    devname = f"cuda:{local_rank}"
+
+    def step():
+        capi.check(L.axb_reduce(capi.OP["sum"], ctypes.byref(xd), ax, 2, 0, ctypes.byref(od), None))
+        part = out.numpy()  # D2H of 4 bytes: also orders the collective after the kernel
+        return part, shard.combine_full_reduction("sum", part, rows * n, device=devname)
+
+    for _ in range(3):
+        part, total = step()
+    barrier()
+    k = 20
+    t0 = time.perf_counter()
+    for _ in range(k):
+        part, total = step()
+    torch.cuda.synchronize()
+    ms = max_over_ranks((time.perf_counter() - t0) / k * 1e3)
+    parts = [torch.zeros(1, dtype=torch.float32, device=devname) for _ in range(world)]
+    dist.all_gather(parts, torch.from_numpy(part.copy()).to(devname))
+    expect = float(sum(p.double().item() for p in parts))
+    ok = abs(float(total[0]) - expect) <= 1e-6 * max(1.0, abs(expect)) * world
+    return {"ms": ms, "GBps_total": world * rows * n * 4 / ms / 1e6, "shards": world, "per_gpu_shape": [rows, n],
+            "collective": "one NCCL all-reduce of the per-shard scalar", "matches_sum_of_partials": bool(ok)}
 
 
 def cpu_baseline():

@@ -24,12 +24,21 @@ GPU_SUITES = ["test_cpu_gpu_parity", "test_fusion", "test_fusion_extended", "tes
               "test_conv1d", "test_flash_attention", "test_transformer_ops", "test_lazy_evaluation", "test_graph_compiler",
               "test_nn_attention", "test_nn_layers", "test_embedding", "test_tensor_operations",
               "test_tensor_unary_operations", "test_tensor_comparisons", "test_tensor_logical_bitwise", "test_broadcast",
-              "test_tensor_views", "test_tensor_shape_ops", "test_tensor_gather_scatter", "test_tensor_basic"]
+              "test_tensor_views", "test_tensor_shape_ops", "test_tensor_gather_scatter", "test_tensor_basic",
+              "test_custom_functors", "test_nn_activation_modules", "test_nn_ergonomics", "test_nn_groupnorm",
+              "test_nn_positional", "test_tensor_numpy_ops", "test_tensor_random", "test_nn_module", "test_tensor_indexing",
+              "test_shape_ops_extended", "test_conv_transpose", "test_interpolate"]
 
 # Known divergence, kept on purpose: TensorOperations.UnsupportedGpuOpFallback expects pow(3, 4) == 81 within 1e-6 (what
 # MPSGraph returns). The reference's CPU backend itself returns 81.00000763 on same-shape contiguous operands (Highway
 # exp(b * log a), src/backends/cpu/cpu_operations.cpp:229-262) and this backend reproduces the CPU backend bit for bit.
-KNOWN_DIVERGENT = {"test_tensor_operations": {"TensorOperations.UnsupportedGpuOpFallback"}}
+KNOWN_DIVERGENT = {
+    "test_tensor_operations": {"TensorOperations.UnsupportedGpuOpFallback"},
+    # outside the named hot path (SURVEY.md §8 "next" row 4 / out of scope): these ops raise RuntimeError::not_implemented
+    # on the CUDA backend instead of silently running on the CPU, so the reference's GPU variants of the tests fail loudly
+    "test_conv_transpose": {"ConvTranspose.Conv1dGPU", "ConvTranspose.Conv2dGPU"},
+    "test_interpolate": {"Interpolate.BilinearGPU", "Interpolate.NearestGPU"},
+}
 
 
 def _need_build():
