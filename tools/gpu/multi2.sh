@@ -1,6 +1,3 @@
 set -x
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus 2 --steps 50 --warmup 5 > gpurun_out/bench_n2.json 2> gpurun_out/bench_n2.err; tail -3 gpurun_out/bench_n2.err; cat gpurun_out/bench_n2.json
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29518 bench.py --impl reference --gpus 2 --steps 3 --warmup 3 > gpurun_out/bench_ref_n2.json 2>> gpurun_out/bench_n2.err; cat gpurun_out/bench_ref_n2.json
-# whisper encoder, one process per GPU (batch sharded: 8 samples per rank), both at once
-cd axiom_b200/host/_build
-(LOCAL_RANK=0 ./whisper_encoder 8 5 0 > /root/repo/gpurun_out/w0.json 2>&1 &) ; LOCAL_RANK=1 ./whisper_encoder 8 5 0 > /root/repo/gpurun_out/w1.json 2>&1; sleep 2; cat /root/repo/gpurun_out/w0.json /root/repo/gpurun_out/w1.json
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus 2 --steps 50 --warmup 5 > gpurun_out/bench_n2.json 2> gpurun_out/bench_n2.err; tail -3 gpurun_out/bench_n2.err | cut -c1-300; cat gpurun_out/bench_n2.json
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29518 bench.py --impl reference --gpus 2 --steps 3 --warmup 3 > gpurun_out/bench_ref_n2.json 2>> gpurun_out/bench_n2.err; cat gpurun_out/bench_ref_n2.json | cut -c1-400
