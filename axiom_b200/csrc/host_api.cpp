@@ -77,6 +77,164 @@ axb_status copy_back_and_release(const axb_tensor &h, Staged &o, std::vector<Sta
     return st;
 }
 
+// ---- pipelined variant --------------------------------------------------------------------------------------------
+// A large elementwise group is PCIe-bound end to end (config 2: 268 MB up, 268 MB down, 0.09 ms of kernel). PCIe is
+// full duplex, so the rows of the result are cut into chunks: chunk i+1 uploads on one stream while chunk i computes on
+// the backend stream and chunk i-1 downloads on a third — uploads and downloads then overlap and the step costs
+// max(up, down) instead of up + down. Operands that do not have the result's leading extent (broadcast rows, scalars,
+// small vectors) are staged whole once.
+struct SideStreams {
+    cudaStream_t in = nullptr, out = nullptr;
+};
+SideStreams *side_streams(int device) {
+    static SideStreams per_dev[64];
+    if (device < 0 || device >= 64)
+        return nullptr;
+    SideStreams &ss = per_dev[device];
+    if (!ss.in) {
+        if (cudaStreamCreateWithFlags(&ss.in, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaStreamCreateWithFlags(&ss.out, cudaStreamNonBlocking) != cudaSuccess)
+            return nullptr;
+    }
+    return &ss;
+}
+
+constexpr int kMaxChunks = 16;
+constexpr int64_t kPipelineMinBytes = 32ll << 20, kSmallOperandBytes = 1ll << 20;
+
+// true when operand `h` can be cut along the result's leading dim into non-overlapping host spans
+bool row_sliceable(const axb_tensor &h, const axb_tensor &out) {
+    if (h.ndim != out.ndim || h.ndim < 1 || h.shape[0] != out.shape[0])
+        return false;
+    int64_t inner_hi = (int64_t)dtype_size(h.dtype);
+    for (int d = 0; d < h.ndim; ++d) {
+        if (h.strides[d] < 0)
+            return false;
+        if (d > 0)
+            inner_hi += (h.shape[d] - 1) * h.strides[d];
+    }
+    return h.shape[0] <= 1 || h.strides[0] >= inner_hi; // rows do not interleave
+}
+
+// returns AXB_OK and sets *handled when the pipelined path ran
+axb_status pipelined_elementwise(const axb_instr *prog, int n_instr, const axb_tensor *hin, int n_in, const axb_tensor *hout,
+                                 cudaStream_t s, DeviceCtx *ctx, bool *handled) {
+    *handled = false;
+    const int64_t out_bytes = numel(*hout) * (int64_t)dtype_size(hout->dtype);
+    if (!is_contiguous(*hout) || hout->ndim < 2 || out_bytes < kPipelineMinBytes || hout->shape[0] < 2 * kMaxChunks)
+        return AXB_OK;
+    bool sliced[AXB_MAX_INPUTS];
+    for (int k = 0; k < n_in; ++k) {
+        int64_t lo, hi;
+        view_span(hin[k], &lo, &hi);
+        sliced[k] = (hi - lo) > kSmallOperandBytes;
+        if (sliced[k] && !row_sliceable(hin[k], *hout))
+            return AXB_OK; // a large operand that is broadcast along rows or oddly strided: plain path
+    }
+    SideStreams *ss = side_streams(ctx->device);
+    if (!ss)
+        return AXB_OK;
+    *handled = true;
+
+    std::vector<Staged> ins(n_in);
+    Staged o;
+    std::vector<cudaEvent_t> events;
+    auto new_event = [&](cudaEvent_t *e) {
+        cudaError_t r = cudaEventCreateWithFlags(e, cudaEventDisableTiming);
+        if (r == cudaSuccess)
+            events.push_back(*e);
+        return r;
+    };
+    axb_status st = AXB_OK;
+    auto cuda_ok = [&](cudaError_t e, const char *what) {
+        if (e != cudaSuccess && st == AXB_OK)
+            st = fail(AXB_ERR_CUDA, "axb_elementwise_host (pipelined): %s failed: %s", what, cudaGetErrorString(e));
+        return e == cudaSuccess;
+    };
+    // device blocks for everything (full size), small operands uploaded right away on the backend stream
+    for (int k = 0; k < n_in && st == AXB_OK; ++k) {
+        if (!sliced[k]) {
+            st = stage_in(hin[k], s, &ins[k]);
+        } else {
+            int64_t lo, hi;
+            view_span(hin[k], &lo, &hi);
+            st = axb_alloc((size_t)(hi - lo), s, &ins[k].dev);
+            ins[k].desc = hin[k];
+            ins[k].desc.base = ins[k].dev;
+            ins[k].desc.byte_offset = -lo; // lo == 0 here (non-negative strides)
+        }
+    }
+    if (st == AXB_OK)
+        st = alloc_out(*hout, s, &o);
+    cudaEvent_t ready = nullptr;
+    if (st == AXB_OK && cuda_ok(new_event(&ready), "cudaEventCreate")) {
+        cuda_ok(cudaEventRecord(ready, s), "cudaEventRecord");
+        cuda_ok(cudaStreamWaitEvent(ss->in, ready, 0), "cudaStreamWaitEvent");  // allocator blocks are ordered on s
+        cuda_ok(cudaStreamWaitEvent(ss->out, ready, 0), "cudaStreamWaitEvent");
+    }
+    const int64_t rows = hout->shape[0];
+    const int chunks = (int)std::min<int64_t>(kMaxChunks, rows);
+    const int64_t out_row_bytes = out_bytes / rows;
+    for (int c = 0; c < chunks && st == AXB_OK; ++c) {
+        const int64_t r0 = rows * c / chunks, r1 = rows * (c + 1) / chunks;
+        std::vector<axb_tensor> d(std::max(n_in, 1));
+        for (int k = 0; k < n_in; ++k) {
+            d[k] = ins[k].desc;
+            // every operand that has the result's leading extent is VIEWED per chunk (a {rows, 1} column as well as the
+            // big {rows, cols} operand); operands with fewer dims or extent 1 broadcast along rows and stay whole
+            if (hin[k].ndim == hout->ndim && hin[k].shape[0] == rows && rows > 1) {
+                d[k].shape[0] = r1 - r0;
+                d[k].byte_offset += r0 * hin[k].strides[0];
+            }
+            if (!sliced[k])
+                continue;
+            axb_tensor hv = hin[k];
+            hv.shape[0] = r1 - r0;
+            int64_t lo, hi;
+            view_span(hv, &lo, &hi);
+            cuda_ok(cudaMemcpyAsync(static_cast<char *>(ins[k].dev) + r0 * hin[k].strides[0], tensor_ptr(hin[k]) + r0 * hin[k].strides[0],
+                                    (size_t)(hi - lo), cudaMemcpyHostToDevice, ss->in),
+                    "H2D");
+        }
+        cudaEvent_t up = nullptr, done = nullptr;
+        if (!cuda_ok(new_event(&up), "cudaEventCreate") || !cuda_ok(new_event(&done), "cudaEventCreate"))
+            break;
+        cuda_ok(cudaEventRecord(up, ss->in), "cudaEventRecord");
+        cuda_ok(cudaStreamWaitEvent(s, up, 0), "cudaStreamWaitEvent");
+        axb_tensor od = o.desc;
+        od.shape[0] = r1 - r0;
+        od.byte_offset = r0 * out_row_bytes;
+        if (st == AXB_OK)
+            st = axb_elementwise(prog, n_instr, d.data(), n_in, &od, s);
+        cuda_ok(cudaEventRecord(done, s), "cudaEventRecord");
+        cuda_ok(cudaStreamWaitEvent(ss->out, done, 0), "cudaStreamWaitEvent");
+        if (st == AXB_OK)
+            cuda_ok(cudaMemcpyAsync(tensor_ptr(*hout) + r0 * out_row_bytes, static_cast<char *>(o.dev) + r0 * out_row_bytes,
+                                    (size_t)((r1 - r0) * out_row_bytes), cudaMemcpyDeviceToHost, ss->out),
+                    "D2H");
+    }
+    // the blocks go back to the pool in backend-stream order: that stream first waits for both side streams
+    cudaEvent_t in_done = nullptr, out_done = nullptr;
+    if (new_event(&in_done) == cudaSuccess && new_event(&out_done) == cudaSuccess) {
+        cudaEventRecord(in_done, ss->in);
+        cudaEventRecord(out_done, ss->out);
+        cudaStreamWaitEvent(s, in_done, 0);
+        cudaStreamWaitEvent(s, out_done, 0);
+    } else {
+        cudaStreamSynchronize(ss->in);
+        cudaStreamSynchronize(ss->out);
+    }
+    for (auto &i : ins)
+        if (i.dev)
+            axb_free(i.dev, s);
+    if (o.dev)
+        axb_free(o.dev, s);
+    cuda_ok(cudaStreamSynchronize(s), "cudaStreamSynchronize");
+    for (cudaEvent_t e : events)
+        cudaEventDestroy(e);
+    return st;
+}
+
 } // namespace
 
 extern "C" {
@@ -86,7 +244,14 @@ axb_status axb_elementwise_host(const axb_instr *prog, int n_instr, const axb_te
     AXB_REQUIRE(n_inputs >= 0 && n_inputs <= AXB_MAX_INPUTS, AXB_ERR_INVALID, "axb_elementwise_host: bad input count");
     AXB_TRY(validate_tensor(host_out, "axb_elementwise_host(out)"));
     cudaStream_t s;
-    AXB_TRY(resolve_stream(nullptr, &s));
+    DeviceCtx *ctx;
+    AXB_TRY(resolve_stream(nullptr, &s, &ctx));
+    for (int k = 0; k < n_inputs; ++k)
+        AXB_TRY(validate_tensor(&host_inputs[k], "axb_elementwise_host(input)"));
+    bool handled = false;
+    axb_status pst = pipelined_elementwise(prog, n_instr, host_inputs, n_inputs, host_out, s, ctx, &handled);
+    if (handled)
+        return pst;
     std::vector<Staged> ins(n_inputs);
     std::vector<axb_tensor> descs(std::max(n_inputs, 1));
     axb_status st = AXB_OK;

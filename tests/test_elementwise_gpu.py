@@ -377,3 +377,43 @@ def test_allocator_reuses_blocks(gpu):
     assert s1.n_allocs - s0.n_allocs == 8
     assert s1.n_cuda_malloc - s0.n_cuda_malloc <= 1, "freed blocks must be served from the cache"
     assert s1.n_cache_hits - s0.n_cache_hits >= 7
+
+
+# ---- host-buffer entry point (what bench.py's e2e leg calls) ------------------------------------------------------
+def _host_chain_config2(a, b, c):
+    F, B = capi.F32, capi.BOOL
+    prog = [capi.make_instr(capi.OP["relu"], F, 0), capi.make_instr(capi.OP["add"], F, capi.SRC_VALUE(0), 1),
+            capi.make_instr(capi.OP["mul"], F, capi.SRC_VALUE(1), 2), capi.make_instr(capi.OP["gt"], B, 3, 4),
+            capi.make_instr(capi.OP["where"], F, capi.SRC_VALUE(3), capi.SRC_VALUE(2), 5)]
+    P = (capi.AxbInstr * len(prog))(*prog)
+    hins = [a, np.array([1.0], np.float32), b, c, np.array([0], np.int32), np.array([0.0], np.float32)]
+
+    def desc(t):
+        return capi.make_tensor(t.ctypes.data, dev._NP2AXB[t.dtype], t.shape, [int(s) for s in t.strides])
+
+    I = (capi.AxbTensor * len(hins))(*[desc(t) for t in hins])
+    out = np.empty(np.broadcast_shapes(a.shape, b.shape, c.shape), np.float32)
+    O = desc(out)
+    capi.check(capi.lib().axb_elementwise_host(P, len(prog), I, len(hins), ctypes.byref(O)))
+    return out
+
+
+@pytest.mark.parametrize("shape,c_view", [((2048, 8192), "contig"), ((1000, 9000), "contig"), ((2048, 8192), "row_padded"),
+                                          ((2048, 8192), "transposed"), ((300, 500), "contig")])
+def test_elementwise_host_entry_pipelined_and_plain(gpu, shape, c_view):
+    """axb_elementwise_host on HOST buffers: results >= 32 MiB are cut into row chunks whose uploads, kernels and
+    downloads overlap on three streams (the {rows,1} column operand is viewed per chunk, the {1,cols} row operand stays
+    whole); small results, and large operands whose rows cannot be sliced (a transposed view), take the plain path. All
+    must equal the closed form bit for bit."""
+    rng = np.random.default_rng(91)
+    rows, cols = shape
+    a, b = rand_f32(rng, (rows, 1)), rand_f32(rng, (1, cols))
+    if c_view == "contig":
+        c = rand_f32(rng, shape)
+    elif c_view == "row_padded":
+        c = rand_f32(rng, (rows, cols + 64))[:, :cols]        # row stride > row length: still sliceable
+    else:
+        c = rand_f32(rng, (cols, rows)).T                      # rows interleave in memory: not sliceable
+    got = _host_chain_config2(a, b, c)
+    exp = np.where(c > 0, (np.maximum(a, 0) + np.float32(1)) * b, np.float32(0))
+    assert bits_equal(got, exp), (shape, c_view)
