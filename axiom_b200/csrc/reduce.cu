@@ -184,13 +184,18 @@ __global__ void __launch_bounds__(256) argreduce_rows_kernel(const __grid_consta
                     const In *e0 = reinterpret_cast<const In *>(&q0), *e1 = reinterpret_cast<const In *>(&q1),
                              *e2 = reinterpret_cast<const In *>(&q2), *e3 = reinterpret_cast<const In *>(&q3);
                     const uint32_t o = hoff + i * V;
+                    Cmp c0[V], c1[V], c2[V], c3[V];
 #pragma unroll
                     for (int k = 0; k < V; ++k) {
-                        s0.take(load_as<In, Cmp>(e0[k]), o + k);
-                        s1.take(load_as<In, Cmp>(e1[k]), o + TPR * V + k);
-                        s2.take(load_as<In, Cmp>(e2[k]), o + 2 * TPR * V + k);
-                        s3.take(load_as<In, Cmp>(e3[k]), o + 3 * TPR * V + k);
+                        c0[k] = load_as<In, Cmp>(e0[k]);
+                        c1[k] = load_as<In, Cmp>(e1[k]);
+                        c2[k] = load_as<In, Cmp>(e2[k]);
+                        c3[k] = load_as<In, Cmp>(e3[k]);
                     }
+                    s0.take_vec(c0, o);
+                    s1.take_vec(c1, o + TPR * V);
+                    s2.take_vec(c2, o + 2 * TPR * V);
+                    s3.take_vec(c3, o + 3 * TPR * V);
                 }
                 acc = Op::combine(acc, s0.pair(w0)); // head + stream 0 so far: all below the remainder in index order
                 s0.init();

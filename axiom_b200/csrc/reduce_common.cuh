@@ -276,6 +276,19 @@ template <typename C, bool IS_MAX> struct ArgScan {
         best = t ? v : best;
         off = t ? o : off;
     }
+    // V consecutive elements starting at offset `base`: the value chain is the same, but only a lane-local position
+    // (a select between immediates) is tracked per element; the offset is formed once per vector. `best` only ever
+    // improves, so the LAST improving element of the vector is the vector's first extremum.
+    template <int V> __device__ __forceinline__ void take_vec(const C (&v)[V], uint32_t base) {
+        int kk = -1;
+#pragma unroll
+        for (int k = 0; k < V; ++k) {
+            const bool t = IS_MAX ? (v[k] > best) : (v[k] < best);
+            best = t ? v[k] : best;
+            kk = t ? k : kk;
+        }
+        off = kk >= 0 ? base + (uint32_t)kk : off;
+    }
     __device__ __forceinline__ ArgPair<C> pair(int64_t window_start) const {
         const bool hit = IS_MAX ? (best > Limits<C>::lowest()) : (best < Limits<C>::highest());
         return hit ? ArgPair<C>{best, window_start + (int64_t)off} : ArgOp<C, IS_MAX>::identity();
