@@ -139,12 +139,20 @@ __global__ void __launch_bounds__(THREADS == 32 ? 256 : THREADS) rownorm_kernel(
             sweep([&](int, float &v) { v = __fsub_rn(v, mean); q += __fmul_rn(v, v); }, !RESIDENT, false);
             q = row_allreduce<THREADS, FAdd>(q, smem);
             const float rsd = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(__fdiv_rn(q, (float)n), p.eps)));
+            // contiguous Float32 parameters (nn::LayerNorm): plain indexed loads instead of the dtype switch + 64-bit
+            // stride arithmetic per element
+            const bool w_fast = p.w && p.w_dtype == AXB_F32 && p.w_es == 4, b_fast = p.b && p.b_dtype == AXB_F32 && p.b_es == 4;
+            const float *wf = reinterpret_cast<const float *>(p.w), *bf = reinterpret_cast<const float *>(p.b);
             sweep([&](int e, float &v) {
                 float xc = RESIDENT ? v : __fsub_rn(v, mean);
                 float y = __fmul_rn(xc, rsd);
-                if (p.w)
+                if (w_fast)
+                    y = __fmul_rn(y, __ldg(wf + e));
+                else if (p.w)
                     y = __fmul_rn(y, ld_dyn(p.w + (int64_t)e * p.w_es, p.w_dtype));
-                if (p.b)
+                if (b_fast)
+                    y = __fadd_rn(y, __ldg(bf + e));
+                else if (p.b)
                     y = __fadd_rn(y, ld_dyn(p.b + (int64_t)e * p.b_es, p.b_dtype));
                 v = y;
             }, !RESIDENT, true);
@@ -154,9 +162,13 @@ __global__ void __launch_bounds__(THREADS == 32 ? 256 : THREADS) rownorm_kernel(
             q = row_allreduce<THREADS, FAdd>(q, smem);
             const float ms = round_to<In>(__fdiv_rn(q, (float)n));
             const float rrms = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(ms, p.eps)));
+            const bool w_fast = p.w && p.w_dtype == AXB_F32 && p.w_es == 4;
+            const float *wf = reinterpret_cast<const float *>(p.w);
             sweep([&](int e, float &v) {
                 float y = __fmul_rn(v, rrms);
-                if (p.w)
+                if (w_fast)
+                    y = __fmul_rn(y, __ldg(wf + e));
+                else if (p.w)
                     y = __fmul_rn(y, ld_dyn(p.w + (int64_t)e * p.w_es, p.w_dtype));
                 v = y;
             }, !RESIDENT, true);
@@ -192,7 +204,9 @@ bool launch_wide_typed(RowParams p, DeviceCtx *ctx, cudaStream_t s, axb_status *
     if (p.in_es != isz || p.out_es != osz || ((int64_t)p.n * isz) % 16 != 0)
         return false;
     const int64_t nv = (int64_t)p.n * isz / 16;
-    if (nv < 1024 || nv > 1024 * (32 / E))
+    // rows of 32 KiB .. 128 KiB; shorter rows run several register-resident CTAs per SM (generic kernel), which hides
+    // the reduction round trips better than one persistent CTA (measured: {32768, 4096} fp32 softmax 4.96 vs 3.09 TB/s)
+    if (nv < 2048 || nv > 1024 * (32 / E))
         return false;
     auto al16 = [](const void *q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
     if (!al16(p.in) || !al16(p.out))
@@ -209,17 +223,24 @@ bool launch_wide_typed(RowParams p, DeviceCtx *ctx, cudaStream_t s, axb_status *
     p.nv = (int)nv;
     p.vpw = (int)((nv + kWideWarps - 1) / kWideWarps);
     const int j_need = (p.vpw + 31) / 32;
-    const size_t budget = ctx->smem_optin - 2048; // static: mbarriers + reduction scratch
+    const size_t budget = ctx->smem_optin - 4096; // static: mbarriers + reduction scratch
     const size_t row_bytes = (size_t)nv * 16;
-    p.stages = (int)std::min<size_t>(kWideMaxStages, budget / row_bytes);
-    if (p.stages < 1)
+    constexpr int JMAX = 32 / E;
+    // one row per pass. (A variant that covered R = 2..8 medium rows per pass with shared block reductions measured
+    // SLOWER on B200 — {16384, 8192} fp32 softmax 4.96 vs 5.30 TB/s, {16384, 16384} 5.71 vs 6.23 — and was removed.)
+    constexpr int R = 1;
+    const size_t per_stage = row_bytes * R;
+    p.stages = (int)std::min<size_t>(kWideMaxStages, std::max<size_t>(1, budget / per_stage));
+    if (per_stage > budget)
         return false;
+    p.stages = (int)std::min<size_t>(p.stages, std::max<size_t>(1, (64 * 1024 + per_stage - 1) / per_stage)); // ~64 KiB in flight
     if (const char *e = getenv("AXB_WIDE_STAGES"))
         p.stages = std::max(1, std::min(p.stages, atoi(e)));
     static const bool no_alt = getenv("AXB_WB_NO_ALTERNATE") != nullptr;
     p.wb_alternate = no_alt ? 0 : 1;
-    const size_t dyn = (size_t)p.stages * row_bytes;
-    const unsigned grid = (unsigned)std::min<int64_t>(p.rows, ctx->sm_count);
+    const size_t dyn = (size_t)p.stages * per_stage;
+    const int64_t n_groups = (p.rows + R - 1) / R;
+    const unsigned grid = (unsigned)std::min<int64_t>(n_groups, ctx->sm_count);
     auto go = [&](auto kern) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
         if (e != cudaSuccess) {
@@ -235,7 +256,6 @@ bool launch_wide_typed(RowParams p, DeviceCtx *ctx, cudaStream_t s, axb_status *
         count_launch();
         *st = AXB_OK;
     };
-    constexpr int JMAX = 32 / E;
     const bool exact = p.vpw == JMAX * 32 && nv == (int64_t)kWideWarps * p.vpw;
     if (exact)
         go(rowwide_kernel<In, Out, W, KIND, JMAX, true>);
@@ -263,6 +283,12 @@ template <typename In, typename Out, int KIND> axb_status launch_cfg(const RowPa
     } else if (n <= 2048) { // e.g. attention rows of 1500: 8 values per thread keep the unrolled sweeps short
         int64_t g = std::min<int64_t>(p.rows, max_ctas);
         rownorm_kernel<In, Out, 256, 8, KIND, true><<<(unsigned)g, 256, 0, s>>>(p);
+    } else if (n <= 4096 && !getenv("AXB_ROWS_OLD_MEDIUM")) { // 8 values per thread keep several CTAs resident per SM
+        int64_t g = std::min<int64_t>(p.rows, max_ctas);
+        rownorm_kernel<In, Out, 512, 8, KIND, true><<<(unsigned)g, 512, 0, s>>>(p);
+    } else if (n <= 8192 && !getenv("AXB_ROWS_OLD_MEDIUM")) {
+        int64_t g = std::min<int64_t>(p.rows, max_ctas);
+        rownorm_kernel<In, Out, 1024, 8, KIND, true><<<(unsigned)g, 1024, 0, s>>>(p);
     } else if (n <= 8192) {
         int64_t g = std::min<int64_t>(p.rows, max_ctas);
         rownorm_kernel<In, Out, 256, 32, KIND, true><<<(unsigned)g, 256, 0, s>>>(p);
