@@ -58,6 +58,7 @@ struct TcParams {
     // six (A piece, B piece) combinations of kbp k-blocks each
     int32_t split, kbp;
     int64_t Kp;
+    int32_t bn; // tile width in N (64 / 128 / 256)
 };
 
 // piece (0 = hi, 1 = mid, 2 = lo) of A and B for combination c, smallest products first
@@ -135,7 +136,9 @@ __device__ __forceinline__ float ld_bias(const char *p, int dt) {
 }
 
 // A_MN / B_MN: operand is MN-major (its M / N dim is the contiguous one) instead of K-major.
-template <bool A_MN, bool B_MN>
+// BN_: tile width in N (64 / 128 / 256). The shared-memory ring keeps the 256-wide stage stride; narrower tiles simply
+// load and multiply less of it (N = 64 attention values, N = 384 Linear layers: 3 exact 128-wide tiles instead of 2 x 256).
+template <bool A_MN, bool B_MN, int BN_>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                const __grid_constant__ TcParams p) {
@@ -180,11 +183,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             for (int64_t t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
                 const int64_t b = t / tiles_per_batch;
                 const int r = (int)(t - b * tiles_per_batch);
-                const int m0 = (r / p.tiles_n) * BM, n0 = (r % p.tiles_n) * BN;
+                const int m0 = (r / p.tiles_n) * BM, n0 = (r % p.tiles_n) * BN_;
                 const int ba = (int)b * p.a_bmult, bb = (int)b * p.b_bmult;
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(empty_bar(stage), phase ^ 1u);
-                    mbar_expect_tx(full_bar(stage), STAGE_BYTES);
+                    mbar_expect_tx(full_bar(stage), A_BYTES + BN_ * BK * 2);
                     const uint32_t sa = smem + stage * STAGE_BYTES, sb = sa + A_BYTES;
                     int k0 = kb * BK, k0b = k0;
                     if (p.split) { // K coordinate inside the piece each operand contributes to this combination
@@ -203,7 +206,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                         tma_load_3d(sb, &tma_b, full_bar(stage), k0b, n0, bb); // box {64 k, 256 n}
                     } else {
 #pragma unroll
-                        for (int j = 0; j < BN / 64; ++j)
+                        for (int j = 0; j < BN_ / 64; ++j)
                             tma_load_3d(sb + j * (64 * BK * 2), &tma_b, full_bar(stage), n0 + 64 * j, k0b, bb);
                     }
                     if (++stage == STAGES) {
@@ -220,7 +223,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             for (int64_t t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
                 mbar_wait(tempty_bar(acc), acc_phase ^ 1u); // epilogue has drained this accumulator
                 tc_fence_after();
-                const uint32_t tmem_d = tmem_base + (uint32_t)acc * BN;
+                const uint32_t tmem_d = tmem_base + (uint32_t)acc * BN;  // accumulators sit 256 columns apart for every BN_
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(full_bar(stage), phase);
                     tc_fence_after();
@@ -280,15 +283,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         for (int64_t t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
             const int64_t b = t / tiles_per_batch;
             const int r = (int)(t - b * tiles_per_batch);
-            const int m0 = (r / p.tiles_n) * BM, n0 = (r % p.tiles_n) * BN;
+            const int m0 = (r / p.tiles_n) * BM, n0 = (r % p.tiles_n) * BN_;
             const int64_t m = m0 + q * 32 + lane;
             mbar_wait(tfull_bar(acc), acc_phase);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * BN;
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * BN;  // accumulators sit 256 columns apart for every BN_
             char *crow = p.c + b * p.c_bs + m * p.c_rs;
             const char *brow = p.bias ? p.bias + b * p.bias_bs + m * p.bias_rs : nullptr;
 #pragma unroll 1
-            for (int c = half; c < BN / 32; c += 2) {
+            for (int c = half; c < BN_ / 32; c += 2) {
                 const int64_t nbase = n0 + c * 32;
                 if (nbase >= p.N)
                     break; // warp-uniform
@@ -616,6 +619,7 @@ axb_status run_split(const Desc &d, const char *src, int64_t rows, int64_t rs, i
 }
 
 axb_status launch_ff(const CUtensorMap &ma, const CUtensorMap &mb, const TcParams &p, int sm_count, cudaStream_t s);
+int pick_bn(int64_t N);
 
 axb_status try_split_f32(const Desc &d, DeviceCtx *ctx, cudaStream_t s, bool *done) {
     static const bool disabled = getenv("AXB_F32_MATMUL_SIMT") != nullptr; // A/B switch
@@ -660,13 +664,14 @@ axb_status try_split_f32(const Desc &d, DeviceCtx *ctx, cudaStream_t s, bool *do
     st = run_split(d, d.a, d.M, d.a_rs, d.a_cs, d.a_bs, a_b, Kp, static_cast<uint16_t *>(wa), s);
     if (st == AXB_OK)
         st = run_split(d, d.b, d.N, d.b_cs, d.b_rs, d.b_bs, b_b, Kp, static_cast<uint16_t *>(wb), s);
+    const int bn = pick_bn(d.N);
     CUtensorMap ma, mb;
     if (st == AXB_OK)
         st = make_map(&ma, api, AXB_BF16, wa, (uint64_t)(3 * Kp), (uint64_t)d.M, a_b ? (uint64_t)d.batch : 1, (uint64_t)(3 * Kp * 2),
                       (uint64_t)d.M * 3 * Kp * 2, BK, BM);
     if (st == AXB_OK)
         st = make_map(&mb, api, AXB_BF16, wb, (uint64_t)(3 * Kp), (uint64_t)d.N, b_b ? (uint64_t)d.batch : 1, (uint64_t)(3 * Kp * 2),
-                      (uint64_t)d.N * 3 * Kp * 2, BK, BN);
+                      (uint64_t)d.N * 3 * Kp * 2, BK, (uint32_t)bn);
     if (st != AXB_OK) {
         cleanup();
         return st;
@@ -675,14 +680,15 @@ axb_status try_split_f32(const Desc &d, DeviceCtx *ctx, cudaStream_t s, bool *do
     memset(&p, 0, sizeof p);
     p.M = d.M; p.N = d.N; p.K = d.K; p.batch = d.batch;
     p.tiles_m = (int)((d.M + BM - 1) / BM);
-    p.tiles_n = (int)((d.N + BN - 1) / BN);
+    p.bn = bn;
+    p.tiles_n = (int)((d.N + bn - 1) / bn);
     p.num_tiles = (int64_t)p.tiles_m * p.tiles_n * d.batch;
     p.c = d.c; p.c_rs = d.c_rs; p.c_cs = d.c_cs; p.c_bs = c_bs;
     p.bias = d.bias; p.bias_rs = d.bias_rs; p.bias_cs = d.bias_cs; p.bias_bs = bias_mult ? bias_bs : 0;
     p.bias_dtype = d.bias_dtype; p.act = d.act; p.out_dtype = AXB_F32;
     p.a_bmult = a_b ? 1 : 0; p.b_bmult = b_b ? 1 : 0;
     p.split = 1; p.kbp = (int)(Kp / BK); p.Kp = Kp;
-    p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
     st = launch_ff(ma, mb, p, ctx->sm_count, s);
     cleanup(); // stream-ordered: the blocks return to the pool after the GEMM in stream order
     if (st == AXB_OK)
@@ -690,17 +696,41 @@ axb_status try_split_f32(const Desc &d, DeviceCtx *ctx, cudaStream_t s, bool *do
     return st;
 }
 
-template <bool A_MN, bool B_MN>
-axb_status launch(const CUtensorMap &ma, const CUtensorMap &mb, const TcParams &p, int sm_count, cudaStream_t s) {
+template <bool A_MN, bool B_MN, int BN_>
+axb_status launch_bn(const CUtensorMap &ma, const CUtensorMap &mb, const TcParams &p, int sm_count, cudaStream_t s) {
     static bool configured = false; // per instantiation; benign race (same value)
     if (!configured) {
-        AXB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        AXB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<A_MN, B_MN, BN_>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         configured = true;
     }
     const unsigned grid = (unsigned)std::min<int64_t>(p.num_tiles, sm_count);
-    gemm_tc_kernel<A_MN, B_MN><<<grid, NUM_THREADS, SMEM_BYTES, s>>>(ma, mb, p);
+    gemm_tc_kernel<A_MN, B_MN, BN_><<<grid, NUM_THREADS, SMEM_BYTES, s>>>(ma, mb, p);
     AXB_CHECK_LAUNCH();
     return AXB_OK;
+}
+template <bool A_MN, bool B_MN>
+axb_status launch(const CUtensorMap &ma, const CUtensorMap &mb, const TcParams &p, int sm_count, cudaStream_t s) {
+    switch (p.bn) {
+    case 64: return launch_bn<A_MN, B_MN, 64>(ma, mb, p, sm_count, s);
+    case 128: return launch_bn<A_MN, B_MN, 128>(ma, mb, p, sm_count, s);
+    default: return launch_bn<A_MN, B_MN, 256>(ma, mb, p, sm_count, s);
+    }
+}
+// tile width: the narrowest of 64 / 128 / 256 that wastes the least of the last tile (ties -> wider)
+int pick_bn(int64_t N) {
+    static const char *force = getenv("AXB_GEMM_BN");
+    if (force)
+        return atoi(force) == 64 ? 64 : atoi(force) == 128 ? 128 : 256;
+    int best = 256;
+    int64_t best_pad = (N + 255) / 256 * 256;
+    for (int bn : {128, 64}) {
+        const int64_t pad = (N + bn - 1) / bn * bn;
+        if (pad < best_pad) {
+            best = bn;
+            best_pad = pad;
+        }
+    }
+    return best;
 }
 
 axb_status launch_ff(const CUtensorMap &ma, const CUtensorMap &mb, const TcParams &p, int sm_count, cudaStream_t s) {
@@ -742,20 +772,22 @@ axb_status try_tcgen05(const Desc &d, int adt, int bdt, int cdt, DeviceCtx *ctx,
     const uint64_t a_ld = (uint64_t)std::max<int64_t>(oa.ld, 16), b_ld = (uint64_t)std::max<int64_t>(ob.ld, 16);
     const uint64_t a_b = (uint64_t)std::max<int64_t>(a_bs, 16), b_b = (uint64_t)std::max<int64_t>(b_bs, 16);
     const uint64_t abatch = a_mult ? (uint64_t)d.batch : 1, bbatch = b_mult ? (uint64_t)d.batch : 1;
+    const int bn = pick_bn(d.N);
     CUtensorMap ma, mb;
     if (!oa.mn_major)
         AXB_TRY(make_map(&ma, api, adt, d.a, (uint64_t)d.K, (uint64_t)d.M, abatch, a_ld, a_b, BK, BM));
     else
         AXB_TRY(make_map(&ma, api, adt, d.a, (uint64_t)d.M, (uint64_t)d.K, abatch, a_ld, a_b, 64, BK));
     if (!ob.mn_major)
-        AXB_TRY(make_map(&mb, api, bdt, d.b, (uint64_t)d.K, (uint64_t)d.N, bbatch, b_ld, b_b, BK, BN));
+        AXB_TRY(make_map(&mb, api, bdt, d.b, (uint64_t)d.K, (uint64_t)d.N, bbatch, b_ld, b_b, BK, (uint32_t)bn));
     else
         AXB_TRY(make_map(&mb, api, bdt, d.b, (uint64_t)d.N, (uint64_t)d.K, bbatch, b_ld, b_b, 64, BK));
     TcParams p;
     memset(&p, 0, sizeof p);
     p.M = d.M; p.N = d.N; p.K = d.K; p.batch = d.batch;
     p.tiles_m = (int)((d.M + BM - 1) / BM);
-    p.tiles_n = (int)((d.N + BN - 1) / BN);
+    p.bn = bn;
+    p.tiles_n = (int)((d.N + bn - 1) / bn);
     p.num_tiles = (int64_t)p.tiles_m * p.tiles_n * d.batch;
     p.c = d.c; p.c_rs = d.c_rs; p.c_cs = d.c_cs; p.c_bs = c_bs;
     p.bias = d.bias; p.bias_rs = d.bias_rs; p.bias_cs = d.bias_cs; p.bias_bs = bias_mult ? bias_bs : 0;
@@ -765,7 +797,7 @@ axb_status try_tcgen05(const Desc &d, int adt, int bdt, int cdt, DeviceCtx *ctx,
     // BF16 = 1) @7/@10, a/b major (MN = 1) @15/@16, N>>3 @17, M>>4 @24
     const uint32_t fmt = adt == AXB_BF16 ? 1u : 0u;
     p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((oa.mn_major ? 1u : 0u) << 15) | ((ob.mn_major ? 1u : 0u) << 16) |
-              ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+              ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
     axb_status st;
     if (!oa.mn_major && !ob.mn_major)
         st = launch<false, false>(ma, mb, p, ctx->sm_count, s);
