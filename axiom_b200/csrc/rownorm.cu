@@ -143,6 +143,30 @@ __global__ void __launch_bounds__(THREADS == 32 ? 256 : THREADS) rownorm_kernel(
             // stride arithmetic per element
             const bool w_fast = p.w && p.w_dtype == AXB_F32 && p.w_es == 4, b_fast = p.b && p.b_dtype == AXB_F32 && p.b_es == 4;
             const float *wf = reinterpret_cast<const float *>(p.w), *bf = reinterpret_cast<const float *>(p.b);
+            if (RESIDENT && p.vec_ok && (w_fast || !p.w) && (b_fast || !p.b) && (n & 3) == 0 &&
+                ((reinterpret_cast<uintptr_t>(p.w) | reinterpret_cast<uintptr_t>(p.b)) & 15) == 0) {
+                // final pass with 128-bit parameter loads: the per-element scalar loads of weight and bias were the
+                // largest L1 client of this kernel on transformer-width rows (2 x 32-bit loads per output element)
+#pragma unroll
+                for (int j = 0; j < NCH; ++j) {
+                    const int e0 = (j * THREADS + tid) * 4;
+                    if (e0 < n && row_ok) {
+                        float y[4];
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            y[k] = __fmul_rn(x[(RESIDENT ? j * 4 : 0) + k], rsd);
+                        if (p.w) {
+                            const float4 wv = __ldg(reinterpret_cast<const float4 *>(wf + e0));
+                            y[0] = __fmul_rn(y[0], wv.x); y[1] = __fmul_rn(y[1], wv.y); y[2] = __fmul_rn(y[2], wv.z); y[3] = __fmul_rn(y[3], wv.w);
+                        }
+                        if (p.b) {
+                            const float4 bv = __ldg(reinterpret_cast<const float4 *>(bf + e0));
+                            y[0] = __fadd_rn(y[0], bv.x); y[1] = __fadd_rn(y[1], bv.y); y[2] = __fadd_rn(y[2], bv.z); y[3] = __fadd_rn(y[3], bv.w);
+                        }
+                        store_chunk(e0, y);
+                    }
+                }
+            } else {
             sweep([&](int e, float &v) {
                 float xc = RESIDENT ? v : __fsub_rn(v, mean);
                 float y = __fmul_rn(xc, rsd);
@@ -156,6 +180,7 @@ __global__ void __launch_bounds__(THREADS == 32 ? 256 : THREADS) rownorm_kernel(
                     y = __fadd_rn(y, ld_dyn(p.b + (int64_t)e * p.b_es, p.b_dtype));
                 v = y;
             }, !RESIDENT, true);
+            }
         } else { // K_RMS_NORM
             float q = 0.0f;
             sweep([&](int, float &v) { q += round_to<In>(__fmul_rn(v, v)); }, true, false);
@@ -277,6 +302,12 @@ template <typename In, typename Out, int KIND> axb_status launch_cfg(const RowPa
     if (n <= 256) {
         int64_t g = std::min<int64_t>((p.rows + 7) / 8, max_ctas);
         rownorm_kernel<In, Out, 32, 8, KIND, true><<<(unsigned)g, 256, 0, s>>>(p);
+    } else if (n <= 512) { // e.g. whisper's 384-wide layer norms: one warp per row, 16 values per lane
+        int64_t g = std::min<int64_t>((p.rows + 7) / 8, max_ctas);
+        rownorm_kernel<In, Out, 32, 16, KIND, true><<<(unsigned)g, 256, 0, s>>>(p);
+    } else if (n <= 1024 && !getenv("AXB_ROWS_OLD_MEDIUM")) { // four warps per row, 8 values per thread
+        int64_t g = std::min<int64_t>(p.rows, max_ctas * 2);
+        rownorm_kernel<In, Out, 128, 8, KIND, true><<<(unsigned)g, 128, 0, s>>>(p);
     } else if (n <= 1024) {
         int64_t g = std::min<int64_t>((p.rows + 7) / 8, max_ctas);
         rownorm_kernel<In, Out, 32, 32, KIND, true><<<(unsigned)g, 256, 0, s>>>(p);
