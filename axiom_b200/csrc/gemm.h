@@ -28,6 +28,15 @@ struct Desc {
     int64_t a_bs[kMaxBatchDims], b_bs[kMaxBatchDims], c_bs[kMaxBatchDims], bias_bs[kMaxBatchDims];
 };
 
+// Hint for the NEXT fp32 matmul issued by this thread: operand A has already been written in the three-piece bf16 layout
+// [batch][M][3 * kp] (see gemm_tcgen05.cu try_split_f32), so its split pass is skipped and the tensor-core path is
+// mandatory (the A tensor passed to axb_matmul only carries shape / batch information). Consumed by that call.
+struct PresplitA {
+    const uint16_t *ptr = nullptr;
+    int64_t kp = 0;
+};
+PresplitA &presplit_a_hint();
+
 // Runs the tensor-core path when the problem qualifies (sets *done), otherwise leaves it to the SIMT kernel.
 axb_status try_tcgen05(const Desc &d, int adt, int bdt, int cdt, DeviceCtx *ctx, cudaStream_t s, bool *done);
 

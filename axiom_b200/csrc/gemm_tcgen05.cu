@@ -622,21 +622,24 @@ axb_status launch_ff(const CUtensorMap &ma, const CUtensorMap &mb, const TcParam
 int pick_bn(int64_t N);
 
 axb_status try_split_f32(const Desc &d, DeviceCtx *ctx, cudaStream_t s, bool *done) {
+    const PresplitA pre = presplit_a_hint();
+    presplit_a_hint() = PresplitA{};
     static const bool disabled = getenv("AXB_F32_MATMUL_SIMT") != nullptr; // A/B switch
-    if (disabled)
+    if (disabled && !pre.ptr)
         return AXB_OK;
     const double flops = 2.0 * (double)d.M * (double)d.N * (double)d.K * (double)d.batch;
-    if (flops < 1.0e8 || d.M < 64 || d.N < 64 || d.K < 32 || d.M >= (1ll << 31) || d.N >= (1ll << 31) || d.K >= (1ll << 28) ||
-        d.batch > 65535)
+    const bool small = flops < 1.0e8 || d.M < 64 || d.N < 64 || d.K < 32;
+    if ((small && !pre.ptr) || d.M >= (1ll << 31) || d.N >= (1ll << 31) || d.K >= (1ll << 28) || d.batch > 65535) {
+        AXB_REQUIRE(!pre.ptr, AXB_ERR_UNSUPPORTED, "fp32 matmul with a pre-split operand: problem outside the tensor-core path");
         return AXB_OK; // small problems: the split passes and the 128x256 tile would dominate
+    }
     int64_t c_bs, bias_bs = 0;
     int c_mult, bias_mult = 0;
-    if (!collapse_batch(d, d.c_bs, &c_bs, &c_mult) || (d.batch > 1 && !c_mult))
+    if (!collapse_batch(d, d.c_bs, &c_bs, &c_mult) || (d.batch > 1 && !c_mult) ||
+        (d.bias && !collapse_batch(d, d.bias_bs, &bias_bs, &bias_mult)) || d.c_rs < 0 || d.c_cs < 0) {
+        AXB_REQUIRE(!pre.ptr, AXB_ERR_UNSUPPORTED, "fp32 matmul with a pre-split operand: output layout outside the tensor-core path");
         return AXB_OK;
-    if (d.bias && !collapse_batch(d, d.bias_bs, &bias_bs, &bias_mult))
-        return AXB_OK;
-    if (d.c_rs < 0 || d.c_cs < 0)
-        return AXB_OK;
+    }
     auto batched = [&](const int64_t *bs) {
         for (int i = 0; i < d.nb; ++i)
             if (d.bshape[i] != 1 && bs[i] != 0)
@@ -645,23 +648,31 @@ axb_status try_split_f32(const Desc &d, DeviceCtx *ctx, cudaStream_t s, bool *do
     };
     const bool a_b = d.batch > 1 && batched(d.a_bs), b_b = d.batch > 1 && batched(d.b_bs);
     const int64_t Kp = (d.K + 63) / 64 * 64;
+    AXB_REQUIRE(!pre.ptr || pre.kp == Kp, AXB_ERR_INVALID, "fp32 matmul with a pre-split operand: piece width %lld, expected %lld",
+                (long long)pre.kp, (long long)Kp);
     const size_t a_bytes = (size_t)(a_b ? d.batch : 1) * d.M * 3 * Kp * 2, b_bytes = (size_t)(b_b ? d.batch : 1) * d.N * 3 * Kp * 2;
     const drv::Api *api = drv::api();
     if (!api)
         return AXB_ERR_CUDA;
     void *wa = nullptr, *wb = nullptr;
-    AXB_TRY(axb_alloc(a_bytes, s, &wa));
+    if (pre.ptr)
+        wa = const_cast<uint16_t *>(pre.ptr);
+    else
+        AXB_TRY(axb_alloc(a_bytes, s, &wa));
     axb_status st = axb_alloc(b_bytes, s, &wb);
     if (st != AXB_OK) {
-        axb_free(wa, s);
+        if (!pre.ptr)
+            axb_free(wa, s);
         return st;
     }
     auto cleanup = [&]() {
-        axb_free(wa, s);
+        if (!pre.ptr)
+            axb_free(wa, s);
         axb_free(wb, s);
     };
     // A is [M][K] with strides (a_rs, a_cs); B is used as [N][K] with strides (b_cs, b_rs)
-    st = run_split(d, d.a, d.M, d.a_rs, d.a_cs, d.a_bs, a_b, Kp, static_cast<uint16_t *>(wa), s);
+    if (!pre.ptr)
+        st = run_split(d, d.a, d.M, d.a_rs, d.a_cs, d.a_bs, a_b, Kp, static_cast<uint16_t *>(wa), s);
     if (st == AXB_OK)
         st = run_split(d, d.b, d.N, d.b_cs, d.b_rs, d.b_bs, b_b, Kp, static_cast<uint16_t *>(wb), s);
     const int bn = pick_bn(d.N);
@@ -738,6 +749,11 @@ axb_status launch_ff(const CUtensorMap &ma, const CUtensorMap &mb, const TcParam
 }
 
 } // namespace
+
+PresplitA &presplit_a_hint() {
+    static thread_local PresplitA h;
+    return h;
+}
 
 axb_status try_tcgen05(const Desc &d, int adt, int bdt, int cdt, DeviceCtx *ctx, cudaStream_t s, bool *done) {
     *done = false;

@@ -447,6 +447,24 @@ Tensor gpu_conv1d(const Tensor &input, const Tensor &weight, const Tensor &bias,
 Tensor gpu_scaled_dot_product_attention(const Tensor &query, const Tensor &key, const Tensor &value, const Tensor &mask,
                                         float scale, bool is_causal) {
     const Tensor q = on_gpu(query), k = on_gpu(key), v = on_gpu(value);
+    if (q.dtype() == DType::Float32 && k.dtype() == DType::Float32 && v.dtype() == DType::Float32) {
+        // one C-ABI call: Q K^T, fused scale + mask + softmax writing pre-split probabilities, P V (csrc/attention.cu)
+        Tensor out = empty_gpu({q.shape()[0], q.shape()[1], q.shape()[2], v.shape()[3]}, DType::Float32);
+        if (out.size() == 0)
+            return out;
+        Tensor m;
+        axb_tensor md{};
+        const bool has_mask = mask.storage() && mask.size() > 0;
+        if (has_mask) {
+            m = on_gpu(mask);
+            if (m.itemsize() != 1)
+                m = cuda::gpu_binary(ops::OpType::NotEqual, m, Tensor::zeros({1}, m.dtype(), Device::CPU).to(Device::GPU));
+            md = describe(m);
+        }
+        const axb_tensor qd = describe(q), kd = describe(k), vd = describe(v), od = describe(out);
+        check(axb_sdpa(&qd, &kd, &vd, has_mask ? &md : nullptr, scale, is_causal ? 1 : 0, &od, nullptr), "axb_sdpa");
+        return out;
+    }
     // scale the (B, H, Lq, D) queries, not the (B, H, Lq, Lk) scores: Lk / D times less data through the kernel
     Tensor sc = Tensor::full({1}, scale, Device::CPU).astype(q.dtype()).to(Device::GPU);
     Tensor s = cuda::gpu_matmul(cuda::gpu_binary(ops::OpType::Multiply, q, sc), k, false, true); // (B, H, Lq, Lk)

@@ -277,6 +277,15 @@ axb_status axb_index_select(const axb_tensor *in, int dim, const axb_tensor *ind
 axb_status axb_scatter(const axb_tensor *in, int dim, const axb_tensor *indices, const axb_tensor *src,
                        const axb_tensor *out, axb_stream_t stream);
 
+/* ---- scaled dot-product attention ("next" row 1) ---------------------------------------------------------------
+ * ops::scaled_dot_product_attention (src/tensor/operations.cpp:3979-4044) / cpu_flash_attention
+ * (src/backends/cpu/flash_attention_cpu.cpp:18-131): q {B,H,Lq,D}, k {B,H,Lk,D}, v {B,H,Lk,Dv}, out {B,H,Lq,Dv}, Float32.
+ * mask (may be NULL): Bool / 8-bit, broadcastable to {B,H,Lq,Lk}, NON-ZERO = position masked out; is_causal masks kv > q;
+ * scale <= 0 means 1/sqrt(D). Three launches: Q K^T, fused scale+mask+softmax (probabilities written directly in the
+ * pre-split bf16 layout of the next GEMM), P V. */
+axb_status axb_sdpa(const axb_tensor *q, const axb_tensor *k, const axb_tensor *v, const axb_tensor *mask /* may be NULL */,
+                    float scale, int is_causal, const axb_tensor *out, axb_stream_t stream);
+
 /* ---- convolution / padding data movement ("next" row: conv1d as GEMM) ------------------------------------------
  * Replaces the reference's naive conv1d loops (src/tensor/operations.cpp:3046-3135) together with axb_matmul:
  * col = im2col(x) with implicit zero padding, then W2d{C_out, C_in*K} x col{N, C_in*K, L_out}.

@@ -1,0 +1,3 @@
+timeout 900 python -m pytest tests/test_attention_gpu.py -m gpu -x -q 2>&1 | tail -12
+cd axiom_b200/host/_build; timeout 300 ./whisper_encoder 8 5 1 | tail -1; timeout 300 ./whisper_encoder 32 3 0 | tail -1
+for t in reftest_test_flash_attention reftest_test_nn_attention reftest_test_transformer_ops; do timeout 300 ./$t | grep -E "SUMMARY|FAILED  \] [A-Z]"; done
