@@ -138,14 +138,9 @@ template <int VPT, bool RESIDENT> __global__ void __launch_bounds__(256) attn_so
                 if (prow && (k0 + 8 <= p.lk || k0 >= p.lk)) { // a full run (or pure K padding): 3 x 128-bit stores
                     uint32_t hh[4], mm[4], ll[4];
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        uint16_t h0, m0, l0, h1, m1, l1;
-                        attn_split3(k0 < p.lk ? x[c * 8 + 2 * i] * inv : 0.0f, h0, m0, l0);
-                        attn_split3(k0 < p.lk ? x[c * 8 + 2 * i + 1] * inv : 0.0f, h1, m1, l1);
-                        hh[i] = (uint32_t)h0 | ((uint32_t)h1 << 16);
-                        mm[i] = (uint32_t)m0 | ((uint32_t)m1 << 16);
-                        ll[i] = (uint32_t)l0 | ((uint32_t)l1 << 16);
-                    }
+                    for (int i = 0; i < 4; ++i)
+                        red::split3_pair(k0 < p.lk ? x[c * 8 + 2 * i] * inv : 0.0f, k0 < p.lk ? x[c * 8 + 2 * i + 1] * inv : 0.0f,
+                                         hh[i], mm[i], ll[i]);
                     *reinterpret_cast<uint4 *>(prow + k0) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
                     *reinterpret_cast<uint4 *>(prow + p.kp + k0) = make_uint4(mm[0], mm[1], mm[2], mm[3]);
                     *reinterpret_cast<uint4 *>(prow + 2 * p.kp + k0) = make_uint4(ll[0], ll[1], ll[2], ll[3]);

@@ -557,14 +557,8 @@ template <bool ROWS_CONTIG> __global__ void __launch_bounds__(256) split_f32_ker
         }
         uint32_t h[4], m[4], l[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            uint16_t h0, m0, l0, h1, m1, l1;
-            split3(v[2 * i], h0, m0, l0);
-            split3(v[2 * i + 1], h1, m1, l1);
-            h[i] = (uint32_t)h0 | ((uint32_t)h1 << 16);
-            m[i] = (uint32_t)m0 | ((uint32_t)m1 << 16);
-            l[i] = (uint32_t)l0 | ((uint32_t)l1 << 16);
-        }
+        for (int i = 0; i < 4; ++i)
+            red::split3_pair(v[2 * i], v[2 * i + 1], h[i], m[i], l[i]);
         uint16_t *row = dst + r * 3 * p.Kp + k; // k % 8 == 0 and Kp % 64 == 0: 16-byte aligned
         *reinterpret_cast<uint4 *>(row) = make_uint4(h[0], h[1], h[2], h[3]);
         *reinterpret_cast<uint4 *>(row + p.Kp) = make_uint4(m[0], m[1], m[2], m[3]);

@@ -98,6 +98,17 @@ __device__ __forceinline__ uint16_t f2bf(float f) {
 }
 __device__ __forceinline__ float bf2f(uint16_t b) { return __uint_as_float((uint32_t)b << 16); }
 
+// Exact three-way bf16 split of TWO floats with the hardware converter: x = hi + mid + lo, each piece packed as
+// (b in the upper half, a in the lower half). 11 instructions per pair instead of ~40 through the software rounding.
+// NaN / inf inputs give NaN pieces either way (inf - inf), so the NaN encoding of the converter does not matter here.
+__device__ __forceinline__ void split3_pair(float a, float b, uint32_t &hi, uint32_t &mid, uint32_t &lo) {
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(b), "f"(a));
+    const float a1 = a - __uint_as_float(hi << 16), b1 = b - __uint_as_float(hi & 0xFFFF0000u); // exact
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(mid) : "f"(b1), "f"(a1));
+    const float a2 = a1 - __uint_as_float(mid << 16), b2 = b1 - __uint_as_float(mid & 0xFFFF0000u); // exact
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(b2), "f"(a2));
+}
+
 // storage element -> compute type
 template <typename In, typename T> __device__ __forceinline__ T load_as(In v) { return (T)v; }
 template <> __device__ __forceinline__ float load_as<bf16_t, float>(bf16_t v) { return bf2f(v.bits); }
