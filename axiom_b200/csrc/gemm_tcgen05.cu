@@ -39,7 +39,8 @@ constexpr int STAGES = 4;
 constexpr int A_BYTES = BM * BK * 2;        // 16 KiB
 constexpr int B_BYTES = BN * BK * 2;        // 32 KiB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
+constexpr int STAGING_BYTES = 8 * 4096;   // one 32 x 32-word tile per epilogue warp (row <-> column exchange for the stores)
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/ + STAGING_BYTES;
 constexpr int NUM_THREADS = 320; // TMA producer, MMA issuer, 8 epilogue warps
 constexpr uint32_t TMEM_COLS = 512;
 
@@ -151,6 +152,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
     auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
     const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
+    const uint32_t staging_base = bar_base + 256u; // 16-byte aligned: bar_base is 1024-aligned
     uint32_t *tmem_slot_ptr = reinterpret_cast<uint32_t *>(smem_raw + (tmem_slot - raw));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -298,13 +300,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                 uint32_t v[32];
                 tc_ld32(taddr + c * 32, v);
                 tc_wait_ld();
-                if (m >= p.M)
-                    continue;
+                const bool full = nbase + 32 <= p.N;
+                if (m >= p.M && !(c_vec && full))
+                    continue; // (the exchange-based store below needs the whole warp)
                 float f[32];
 #pragma unroll
                 for (int i = 0; i < 32; ++i)
                     f[i] = __uint_as_float(v[i]);
-                const bool full = nbase + 32 <= p.N;
                 // ---- bias: a separate op in the reference, applied to the matmul result rounded to its dtype ----------
                 if (p.bias) {
                     if (!out_f32)
@@ -371,11 +373,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                 // ---- store -----------------------------------------------------------------------------------------
                 if (out_f32) {
                     if (c_vec && full) {
-                        uint4 *dst = reinterpret_cast<uint4 *>(crow + nbase * 4);
+                        // Each lane owns one ROW of the 32 x 32 chunk; written straight out, a warp store would touch 32
+                        // different 128-byte lines with 16 bytes each. The chunk goes through a swizzled shared-memory
+                        // tile instead so that 8 lanes cover one row: every store instruction writes 4 full lines.
+                        const uint32_t tile = staging_base + (uint32_t)(warp - 2) * 4096u;
 #pragma unroll
                         for (int i = 0; i < 8; ++i)
-                            dst[i] = make_uint4(__float_as_uint(f[4 * i]), __float_as_uint(f[4 * i + 1]), __float_as_uint(f[4 * i + 2]),
-                                                __float_as_uint(f[4 * i + 3]));
+                            asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(tile + lane * 128u + ((i ^ (lane & 7)) << 4)),
+                                         "r"(__float_as_uint(f[4 * i])), "r"(__float_as_uint(f[4 * i + 1])), "r"(__float_as_uint(f[4 * i + 2])),
+                                         "r"(__float_as_uint(f[4 * i + 3]))
+                                         : "memory");
+                        __syncwarp();
+                        const int cw = lane & 7;
+#pragma unroll
+                        for (int it = 0; it < 8; ++it) {
+                            const int rr = it * 4 + (lane >> 3);
+                            uint4 w;
+                            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(w.x), "=r"(w.y), "=r"(w.z), "=r"(w.w)
+                                         : "r"(tile + rr * 128u + ((cw ^ (rr & 7)) << 4)));
+                            const int64_t mm = (int64_t)m0 + q * 32 + rr;
+                            if (mm < p.M)
+                                *reinterpret_cast<uint4 *>(p.c + b * p.c_bs + mm * p.c_rs + (nbase + cw * 4) * 4) = w;
+                        }
+                        __syncwarp();
                     } else {
 #pragma unroll
                         for (int i = 0; i < 32; ++i)
@@ -405,10 +425,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                         h[i] = (uint32_t)red::f2h(f[2 * i]) | ((uint32_t)red::f2h(f[2 * i + 1]) << 16);
                 }
                 if (c_vec && full) {
-                    uint4 *dst = reinterpret_cast<uint4 *>(crow + nbase * 2);
+                    // same exchange for 64-byte rows: 4 lanes per row, 8 rows (4 full lines) per store instruction
+                    const uint32_t tile = staging_base + (uint32_t)(warp - 2) * 4096u;
 #pragma unroll
                     for (int i = 0; i < 4; ++i)
-                        dst[i] = make_uint4(h[4 * i], h[4 * i + 1], h[4 * i + 2], h[4 * i + 3]);
+                        asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(tile + lane * 64u + ((i ^ ((lane >> 1) & 3)) << 4)),
+                                     "r"(h[4 * i]), "r"(h[4 * i + 1]), "r"(h[4 * i + 2]), "r"(h[4 * i + 3])
+                                     : "memory");
+                    __syncwarp();
+                    const int cw = lane & 3;
+#pragma unroll
+                    for (int it = 0; it < 4; ++it) {
+                        const int rr = it * 8 + (lane >> 2);
+                        uint4 w;
+                        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(w.x), "=r"(w.y), "=r"(w.z), "=r"(w.w)
+                                     : "r"(tile + rr * 64u + ((cw ^ ((rr >> 1) & 3)) << 4)));
+                        const int64_t mm = (int64_t)m0 + q * 32 + rr;
+                        if (mm < p.M)
+                            *reinterpret_cast<uint4 *>(p.c + b * p.c_bs + mm * p.c_rs + (nbase + cw * 8) * 2) = w;
+                    }
+                    __syncwarp();
                 } else {
 #pragma unroll
                     for (int i = 0; i < 32; ++i)
