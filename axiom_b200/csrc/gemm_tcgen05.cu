@@ -175,7 +175,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
-    const int num_kb = p.split ? 6 * p.kbp : (int)((p.K + BK - 1) / BK);
+    // split == 2 ("grouped", K-major split buffers, BN_ <= 128): stages of 3 A pieces + 3 B pieces, kbp k-blocks per tile
+    constexpr int G_STAGE = 3 * A_BYTES + 3 * BN_ * BK * 2;
+    constexpr int G_STAGES = (STAGES * STAGE_BYTES) / G_STAGE >= 2 ? 2 : 1;
+    const bool grouped = p.split == 2 && !A_MN && !B_MN && BN_ <= 128;
+    const int num_kb = grouped ? p.kbp : p.split ? 6 * p.kbp : (int)((p.K + BK - 1) / BK);
     const int64_t tiles_per_batch = (int64_t)p.tiles_m * p.tiles_n;
 
     if (warp == 0) {
@@ -187,6 +191,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                 const int r = (int)(t - b * tiles_per_batch);
                 const int m0 = (r / p.tiles_n) * BM, n0 = (r % p.tiles_n) * BN_;
                 const int ba = (int)b * p.a_bmult, bb = (int)b * p.b_bmult;
+                if (grouped) {
+                    // fp32 split, narrow tiles: ONE stage carries all three pieces of A and of B for a k-block and the MMA
+                    // warp runs the six piece combinations out of it — every operand byte enters shared memory once per
+                    // k-block instead of once per combination (PV of attention, N = 64: the A pieces are the traffic)
+                    for (int kb = 0; kb < num_kb; ++kb) {
+                        mbar_wait(empty_bar(stage), phase ^ 1u);
+                        mbar_expect_tx(full_bar(stage), G_STAGE);
+                        const uint32_t sa = smem + stage * G_STAGE, sb = sa + 3 * A_BYTES;
+#pragma unroll
+                        for (int pc = 0; pc < 3; ++pc) {
+                            tma_load_3d(sa + pc * A_BYTES, &tma_a, full_bar(stage), pc * (int)p.Kp + kb * BK, m0, ba);
+                            tma_load_3d(sb + pc * (BN_ * BK * 2), &tma_b, full_bar(stage), pc * (int)p.Kp + kb * BK, n0, bb);
+                        }
+                        if (++stage == G_STAGES) {
+                            stage = 0;
+                            phase ^= 1u;
+                        }
+                    }
+                    continue;
+                }
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(empty_bar(stage), phase ^ 1u);
                     mbar_expect_tx(full_bar(stage), A_BYTES + BN_ * BK * 2);
@@ -226,6 +250,31 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                 mbar_wait(tempty_bar(acc), acc_phase ^ 1u); // epilogue has drained this accumulator
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + (uint32_t)acc * BN;  // accumulators sit 256 columns apart for every BN_
+                if (grouped) {
+                    for (int kb = 0; kb < num_kb; ++kb) {
+                        mbar_wait(full_bar(stage), phase);
+                        tc_fence_after();
+                        const uint32_t sa = smem + stage * G_STAGE, sb = sa + 3 * A_BYTES;
+#pragma unroll
+                        for (int c = 0; c < 6; ++c) { // smallest products first, as in the streamed variant
+                            const uint32_t pa = sa + split_piece_a(c) * A_BYTES, pb = sb + split_piece_b(c) * (BN_ * BK * 2);
+#pragma unroll
+                            for (int k = 0; k < BK / 16; ++k)
+                                tc_mma(tmem_d, umma_desc(pa + k * 32, 16, 1024), umma_desc(pb + k * 32, 16, 1024), p.idesc, (kb | c | k) != 0);
+                        }
+                        tc_commit(empty_bar(stage));
+                        if (++stage == G_STAGES) {
+                            stage = 0;
+                            phase ^= 1u;
+                        }
+                    }
+                    tc_commit(tfull_bar(acc));
+                    if (++acc == 2) {
+                        acc = 0;
+                        acc_phase ^= 1u;
+                    }
+                    continue;
+                }
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(full_bar(stage), phase);
                     tc_fence_after();
@@ -728,7 +777,8 @@ axb_status try_split_f32(const Desc &d, DeviceCtx *ctx, cudaStream_t s, bool *do
     p.bias = d.bias; p.bias_rs = d.bias_rs; p.bias_cs = d.bias_cs; p.bias_bs = bias_mult ? bias_bs : 0;
     p.bias_dtype = d.bias_dtype; p.act = d.act; p.out_dtype = AXB_F32;
     p.a_bmult = a_b ? 1 : 0; p.b_bmult = b_b ? 1 : 0;
-    p.split = 1; p.kbp = (int)(Kp / BK); p.Kp = Kp;
+    static const bool no_group = getenv("AXB_SPLIT_NO_GROUP") != nullptr; // A/B switch
+    p.split = (bn <= 128 && !no_group) ? 2 : 1; p.kbp = (int)(Kp / BK); p.Kp = Kp;
     p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
     st = launch_ff(ma, mb, p, ctx->sm_count, s);
     cleanup(); // stream-ordered: the blocks return to the pool after the GEMM in stream order
