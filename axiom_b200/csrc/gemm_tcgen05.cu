@@ -256,11 +256,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                         tc_fence_after();
                         const uint32_t sa = smem + stage * G_STAGE, sb = sa + 3 * A_BYTES;
 #pragma unroll
-                        for (int c = 0; c < 6; ++c) { // smallest products first, as in the streamed variant
+                        for (int c = 0; c < 6; ++c) {
+                            // hi.hi (c == 5) accumulates in the tile's main accumulator; the five small products go to a
+                            // SECOND accumulator in the unused upper half of the tile's 256 TMEM columns and meet the big
+                            // sum only once, in the epilogue: interleaving them per k-block into one fp32 accumulator
+                            // lost their low bits against the running hi.hi sum (3.9e-6 |A||B| on the wide-range test).
                             const uint32_t pa = sa + split_piece_a(c) * A_BYTES, pb = sb + split_piece_b(c) * (BN_ * BK * 2);
+                            const uint32_t dst = c == 5 ? tmem_d : tmem_d + 128u;
 #pragma unroll
                             for (int k = 0; k < BK / 16; ++k)
-                                tc_mma(tmem_d, umma_desc(pa + k * 32, 16, 1024), umma_desc(pb + k * 32, 16, 1024), p.idesc, (kb | c | k) != 0);
+                                tc_mma(dst, umma_desc(pa + k * 32, 16, 1024), umma_desc(pb + k * 32, 16, 1024), p.idesc,
+                                       c == 5 ? (kb | k) != 0 : (kb | c | k) != 0);
                         }
                         tc_commit(empty_bar(stage));
                         if (++stage == G_STAGES) {
@@ -349,6 +355,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                 uint32_t v[32];
                 tc_ld32(taddr + c * 32, v);
                 tc_wait_ld();
+                if (grouped) { // main (hi.hi) + small-products accumulator
+                    uint32_t w[32];
+                    tc_ld32(taddr + 128u + c * 32, w);
+                    tc_wait_ld();
+#pragma unroll
+                    for (int i = 0; i < 32; ++i)
+                        v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(w[i]));
+                }
                 const bool full = nbase + 32 <= p.N;
                 if (m >= p.M && !(c_vec && full))
                     continue; // (the exchange-based store below needs the whole warp)
@@ -754,7 +768,10 @@ axb_status try_split_f32(const Desc &d, DeviceCtx *ctx, cudaStream_t s, bool *do
         st = run_split(d, d.a, d.M, d.a_rs, d.a_cs, d.a_bs, a_b, Kp, static_cast<uint16_t *>(wa), s);
     if (st == AXB_OK)
         st = run_split(d, d.b, d.N, d.b_cs, d.b_rs, d.b_bs, b_b, Kp, static_cast<uint16_t *>(wb), s);
-    const int bn = pick_bn(d.N);
+    // grouped stages need BN <= 128; they also carry more flops per loaded byte (131 vs 87 flop/B for the streamed 256-wide
+    // tile), so the split path prefers 128-wide tiles whenever N > 64
+    static const bool wide_split = getenv("AXB_SPLIT_BN256") != nullptr; // A/B switch
+    const int bn = wide_split ? pick_bn(d.N) : (d.N <= 64 ? 64 : 128);
     CUtensorMap ma, mb;
     if (st == AXB_OK)
         st = make_map(&ma, api, AXB_BF16, wa, (uint64_t)(3 * Kp), (uint64_t)d.M, a_b ? (uint64_t)d.batch : 1, (uint64_t)(3 * Kp * 2),
