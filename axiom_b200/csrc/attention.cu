@@ -176,6 +176,70 @@ template <int VPT, bool RESIDENT> __global__ void __launch_bounds__(256) attn_so
     }
 }
 
+// Rows of up to 256 * RUNS / ... keys with ONE WARP per row (8 rows per CTA): each lane owns RUNS runs of 8 consecutive kv
+// positions, the two row statistics need shuffles only — no block barrier at all (the 256-thread variant above spends two
+// __syncthreads per 6 KB row; whisper's 1500-key rows: 295 -> see profiles). Pre-split output only.
+template <int RUNS> __global__ void __launch_bounds__(256) attn_softmax_warp_kernel(const __grid_constant__ AttnParams p) {
+    const float L2E = 1.4426950408889634f;
+    const int lane = threadIdx.x & 31;
+    const bool vec = (p.lk & 3) == 0 && (reinterpret_cast<uintptr_t>(p.s) & 15) == 0;
+    for (int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); row < p.rows; row += (int64_t)gridDim.x * 8) {
+        const int64_t q = row % p.lq, bh = row / p.lq, h = bh % p.heads, b = bh / p.heads;
+        const float *srow = p.s + row * p.lk;
+        const uint8_t *mrow = p.mask ? p.mask + b * p.m_sb + h * p.m_sh + q * p.m_sq : nullptr;
+        const int64_t kmax = p.causal ? min(p.lk, q + 1) : p.lk;
+        auto masked = [&](int64_t k) { return k >= kmax || (mrow && mrow[k * p.m_sk]); };
+        float x[RUNS * 8];
+        float m = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < RUNS; ++c) {
+            const int64_t k0 = ((int64_t)c * 32 + lane) * 8;
+            if (vec && k0 + 8 <= p.lk) {
+                const float4 a = *reinterpret_cast<const float4 *>(srow + k0), d = *reinterpret_cast<const float4 *>(srow + k0 + 4);
+                const float v[8] = {a.x, a.y, a.z, a.w, d.x, d.y, d.z, d.w};
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    x[c * 8 + i] = masked(k0 + i) ? -INFINITY : v[i] * p.scale;
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    x[c * 8 + i] = (k0 + i < p.lk && !masked(k0 + i)) ? srow[k0 + i] * p.scale : -INFINITY;
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                m = fmaxf(m, x[c * 8 + i]);
+        }
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1)
+            m = fmaxf(m, __shfl_xor_sync(0xFFFFFFFFu, m, d));
+        const float ml = m * L2E;
+        float s = 0.0f;
+#pragma unroll
+        for (int i = 0; i < RUNS * 8; ++i) {
+            x[i] = attn_ex2(fmaf(x[i], L2E, -ml));
+            s += x[i];
+        }
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1)
+            s += __shfl_xor_sync(0xFFFFFFFFu, s, d);
+        const float inv = __fdiv_rn(1.0f, s);
+        uint16_t *prow = p.pieces + row * 3 * p.kp;
+#pragma unroll
+        for (int c = 0; c < RUNS; ++c) {
+            const int64_t k0 = ((int64_t)c * 32 + lane) * 8;
+            if (k0 >= p.kp)
+                continue;
+            uint32_t hh[4], mm[4], ll[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) // positions >= lk carry exp(-inf) = 0: the K padding comes out as zeros
+                red::split3_pair(x[c * 8 + 2 * i] * inv, x[c * 8 + 2 * i + 1] * inv, hh[i], mm[i], ll[i]);
+            *reinterpret_cast<uint4 *>(prow + k0) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
+            *reinterpret_cast<uint4 *>(prow + p.kp + k0) = make_uint4(mm[0], mm[1], mm[2], mm[3]);
+            *reinterpret_cast<uint4 *>(prow + 2 * p.kp + k0) = make_uint4(ll[0], ll[1], ll[2], ll[3]);
+        }
+    }
+}
+
 } // namespace
 } // namespace axb
 
@@ -243,7 +307,12 @@ axb_status axb_sdpa(const axb_tensor *q, const axb_tensor *k, const axb_tensor *
         p.scale = scale;
         p.causal = is_causal ? 1 : 0;
         const unsigned grid = (unsigned)std::min<int64_t>(rows, (int64_t)ctx->sm_count * 16);
-        if (Lk <= 256 * 8)
+        static const bool no_warp_rows = getenv("AXB_SDPA_NO_WARP_ROWS") != nullptr; // A/B switch
+        if (presplit && kp <= 256 * 6 && !no_warp_rows)
+            attn_softmax_warp_kernel<6><<<(unsigned)std::min<int64_t>((rows + 7) / 8, (int64_t)ctx->sm_count * 16), 256, 0, s>>>(p);
+        else if (presplit && kp <= 256 * 8 && !no_warp_rows)
+            attn_softmax_warp_kernel<8><<<(unsigned)std::min<int64_t>((rows + 7) / 8, (int64_t)ctx->sm_count * 16), 256, 0, s>>>(p);
+        else if (Lk <= 256 * 8)
             attn_softmax_kernel<8, true><<<grid, 256, 0, s>>>(p);
         else if (Lk <= 256 * 32)
             attn_softmax_kernel<32, true><<<grid, 256, 0, s>>>(p);
