@@ -147,6 +147,7 @@ def main():
     capi.check(L.axb_set_device(local_rank))
     dist = None
     if world > 1:
+        os.environ["NCCL_DEBUG"] = "WARN"  # NCCL_DEBUG=VERSION/INFO would put a banner on stdout next to the one JSON line
         import torch
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
@@ -256,8 +257,10 @@ def main():
         assert np.array_equal(ho, exp), "e2e result differs from the closed form"
 
     multi = None
+    multi_c5 = None
     if dist is not None and not args.no_extras:
         multi = sharded_full_reduction(L, capi, dev, dist, world, local_rank, barrier, max_over_ranks)
+        multi_c5 = sharded_whisper(dist, world, local_rank, barrier, max_over_ranks)
 
     if rank != 0:
         if dist is not None:
@@ -290,7 +293,7 @@ def main():
     }
 
     if multi is not None:
-        result["extras"] = {"c3_full_sum_row_sharded": multi}
+        result["extras"] = {"c3_full_sum_row_sharded": multi, "c5_whisper_encoder_batch_sharded": multi_c5}
     if world == 1:
         result["cpu_baseline"] = cpu_baseline()
         if not args.no_extras:
@@ -337,6 +340,29 @@ def sharded_full_reduction(L, capi, dev, dist, world, local_rank, barrier, max_o
     ok = abs(float(total[0]) - expect) <= 1e-6 * max(1.0, abs(expect)) * world
     return {"ms": ms, "GBps_total": world * rows * n * 4 / ms / 1e6, "shards": world, "per_gpu_shape": [rows, n],
             "collective": "one NCCL all-reduce of the per-shard scalar", "matches_sum_of_partials": bool(ok)}
+
+
+def sharded_whisper(dist, world, local_rank, barrier, max_over_ranks, per_gpu_batch=8):
+    """BASELINE config 5 at N GPUs: the whisper_poc encoder (reference model code, this backend) with the batch sharded
+    across the ranks — every rank runs `per_gpu_batch` samples on its own GPU (weights replicated, no collective). All
+    ranks start together; the aggregate is N * batch / max-over-ranks forward time."""
+    import subprocess
+    exe = os.path.join(ROOT, "axiom_b200", "host", "_build", "whisper_encoder")
+    if not os.path.exists(exe):
+        return {"unavailable": "axiom_b200/host/_build not built"}
+    barrier()
+    try:
+        env = dict(os.environ, AXIOM_CUDA_DEVICE=str(local_rank))
+        r = subprocess.run([exe, str(per_gpu_batch), "5", "0"], capture_output=True, text=True, timeout=600, env=env)
+        j = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+        ms = float(j["gpu_ms"])
+    except Exception as e:  # noqa: BLE001
+        ms = float("nan")
+        j = {"error": repr(e)}
+    barrier()
+    ms_max = max_over_ranks(ms)
+    return {"per_gpu_batch": per_gpu_batch, "ms_per_forward_max": ms_max, "samples_per_s_total": world * per_gpu_batch / ms_max * 1e3,
+            "shards": world, "collective": "none (batch-sharded, weights replicated)", "rank0": j}
 
 
 def cpu_baseline():
