@@ -150,6 +150,7 @@ def lib() -> ctypes.CDLL:
         "axb_elementwise_reduce": (i32, [I, i32, T, i32, i32, T, vp]),
         "axb_matmul": (i32, [T, T, i32, i32, ctypes.POINTER(AxbMatmulEpilogue), T, vp]),
         "axb_matmul_shape": (i32, [T, T, i32, i32, pi64, pi32]),
+        "axb_matmul_last_path": (i32, []),
         "axb_gather": (i32, [T, i32, T, T, vp]),
         "axb_index_select": (i32, [T, i32, T, T, vp]),
         "axb_elementwise_host": (i32, [I, i32, T, i32, T]),

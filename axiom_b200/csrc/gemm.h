@@ -37,6 +37,8 @@ struct PresplitA {
 };
 PresplitA &presplit_a_hint();
 
+int &last_path(); // per thread, see axb_matmul_last_path
+
 // Runs the tensor-core path when the problem qualifies (sets *done), otherwise leaves it to the SIMT kernel.
 axb_status try_tcgen05(const Desc &d, int adt, int bdt, int cdt, DeviceCtx *ctx, cudaStream_t s, bool *done);
 

@@ -136,6 +136,207 @@ __device__ __forceinline__ float ld_bias(const char *p, int dt) {
                                           : red::h2f(*reinterpret_cast<const uint16_t *>(p));
 }
 
+// One 128 x BN_ accumulator tile: TMEM -> bias / activation -> one rounding -> global memory. Shared by the one-CTA and
+// the CTA-pair kernel (q = TMEM lane quarter of the warp, half = which alternate 32-column chunks it takes, ewarp = index
+// of the warp's staging tile).
+template <int BN_>
+__device__ __forceinline__ void epilogue_tile(const TcParams &p, int64_t b, int m0, int n0, uint32_t taddr, bool grouped, int q,
+                                              int half, int lane, int ewarp, uint32_t staging_base) {
+    const bool out_f32 = p.out_dtype == AXB_F32, out_bf16 = p.out_dtype == AXB_BF16;
+    const int osz = out_f32 ? 4 : 2;
+    const bool c_vec = (p.c_cs == osz) && ((reinterpret_cast<uintptr_t>(p.c) | (uintptr_t)p.c_rs | (uintptr_t)p.c_bs) % 16 == 0);
+    // bias as a row vector shared by all rows (nn::Linear): read once per chunk with vector loads
+    const int bsz = p.bias_dtype == AXB_F32 ? 4 : 2;
+    const bool bias_vec = p.bias && p.bias_rs == 0 && p.bias_cs == bsz && ((reinterpret_cast<uintptr_t>(p.bias) | (uintptr_t)p.bias_bs) % 16 == 0);
+    auto round_out = [&](float (&f)[32]) { // round to the half output type and come back (hardware converters)
+        if (out_bf16) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+                uint32_t h;
+                asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(f[i + 1]), "f"(f[i]));
+                f[i] = __uint_as_float(h << 16);
+                f[i + 1] = __uint_as_float(h & 0xFFFF0000u);
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+                f[i] = red::h2f(red::f2h(f[i]));
+        }
+    };
+    const int64_t m = m0 + q * 32 + lane;
+    char *crow = p.c + b * p.c_bs + m * p.c_rs;
+    const char *brow = p.bias ? p.bias + b * p.bias_bs + m * p.bias_rs : nullptr;
+#pragma unroll 1
+    for (int c = half; c < BN_ / 32; c += 2) {
+        const int64_t nbase = n0 + c * 32;
+        if (nbase >= p.N)
+            break; // warp-uniform
+        uint32_t v[32];
+        tc_ld32(taddr + c * 32, v);
+        tc_wait_ld();
+        if (grouped) { // main (hi.hi) + small-products accumulator
+            uint32_t w[32];
+            tc_ld32(taddr + 128u + c * 32, w);
+            tc_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+                v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(w[i]));
+        }
+        const bool full = nbase + 32 <= p.N;
+        if (m >= p.M && !(c_vec && full))
+            continue; // (the exchange-based store below needs the whole warp)
+        float f[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+            f[i] = __uint_as_float(v[i]);
+        // ---- bias: a separate op in the reference, applied to the matmul result rounded to its dtype ----------
+        if (p.bias) {
+            if (!out_f32)
+                round_out(f);
+            if (bias_vec && full) {
+                const char *bp = p.bias + b * p.bias_bs + nbase * bsz;
+                if (bsz == 4) {
+#pragma unroll
+                    for (int i = 0; i < 32; i += 4) {
+                        const float4 w = __ldg(reinterpret_cast<const float4 *>(bp) + (i >> 2));
+                        f[i] += w.x; f[i + 1] += w.y; f[i + 2] += w.z; f[i + 3] += w.w;
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; i += 8) {
+                        const uint4 w = __ldg(reinterpret_cast<const uint4 *>(bp) + (i >> 3));
+                        const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            if (p.bias_dtype == AXB_BF16) {
+                                f[i + 2 * k] += __uint_as_float(ww[k] << 16);
+                                f[i + 2 * k + 1] += __uint_as_float(ww[k] & 0xFFFF0000u);
+                            } else {
+                                f[i + 2 * k] += red::h2f((uint16_t)(ww[k] & 0xFFFFu));
+                                f[i + 2 * k + 1] += red::h2f((uint16_t)(ww[k] >> 16));
+                            }
+                        }
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                    if (nbase + i < p.N)
+                        f[i] += ld_bias(brow + (nbase + i) * p.bias_cs, p.bias_dtype);
+            }
+        }
+        // ---- activation (also a separate op: its input is rounded to the output dtype first) -----------------
+        if (p.act) {
+            if (!out_f32)
+                round_out(f);
+            switch (p.act) {
+            case AXB_OP_RELU:
+#pragma unroll
+                for (int i = 0; i < 32; ++i) f[i] = f[i] > 0.0f ? f[i] : 0.0f;
+                break;
+            case AXB_OP_GELU:
+#pragma unroll
+                for (int i = 0; i < 32; ++i) f[i] = hwym::Gelu(f[i]);
+                break;
+            case AXB_OP_SILU:
+#pragma unroll
+                for (int i = 0; i < 32; ++i) f[i] = hwym::Silu(f[i]);
+                break;
+            case AXB_OP_SIGMOID:
+#pragma unroll
+                for (int i = 0; i < 32; ++i) f[i] = hwym::Sigmoid(f[i]);
+                break;
+            default:
+#pragma unroll
+                for (int i = 0; i < 32; ++i) f[i] = hwym::Tanh(f[i]);
+                break;
+            }
+        }
+        // ---- store -----------------------------------------------------------------------------------------
+        if (out_f32) {
+            if (c_vec && full) {
+                // Each lane owns one ROW of the 32 x 32 chunk; written straight out, a warp store would touch 32
+                // different 128-byte lines with 16 bytes each. The chunk goes through a swizzled shared-memory
+                // tile instead so that 8 lanes cover one row: every store instruction writes 4 full lines.
+                const uint32_t tile = staging_base + (uint32_t)ewarp * 4096u;
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(tile + lane * 128u + ((i ^ (lane & 7)) << 4)),
+                                 "r"(__float_as_uint(f[4 * i])), "r"(__float_as_uint(f[4 * i + 1])), "r"(__float_as_uint(f[4 * i + 2])),
+                                 "r"(__float_as_uint(f[4 * i + 3]))
+                                 : "memory");
+                __syncwarp();
+                const int cw = lane & 7;
+#pragma unroll
+                for (int it = 0; it < 8; ++it) {
+                    const int rr = it * 4 + (lane >> 3);
+                    uint4 w;
+                    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(w.x), "=r"(w.y), "=r"(w.z), "=r"(w.w)
+                                 : "r"(tile + rr * 128u + ((cw ^ (rr & 7)) << 4)));
+                    const int64_t mm = (int64_t)m0 + q * 32 + rr;
+                    if (mm < p.M)
+                        *reinterpret_cast<uint4 *>(p.c + b * p.c_bs + mm * p.c_rs + (nbase + cw * 4) * 4) = w;
+                }
+                __syncwarp();
+            } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                    if (nbase + i < p.N)
+                        *reinterpret_cast<float *>(crow + (nbase + i) * p.c_cs) = f[i];
+            }
+            continue;
+        }
+        uint32_t h[16];
+        if (out_bf16) {
+            // hardware pack (NaN -> 0x7FFF); the reference encodes NaN as 0x7FC0 (bfloat16.hpp:16-27): chunks that
+            // contain a NaN are re-packed in software (rare)
+            float nan_acc = 0.0f;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(h[i]) : "f"(f[2 * i + 1]), "f"(f[2 * i]));
+                asm("max.NaN.f32 %0, %0, %1, %2;" : "+f"(nan_acc) : "f"(f[2 * i]), "f"(f[2 * i + 1]));
+            }
+            if (nan_acc != nan_acc) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i)
+                    h[i] = (uint32_t)red::f2bf(f[2 * i]) | ((uint32_t)red::f2bf(f[2 * i + 1]) << 16);
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+                h[i] = (uint32_t)red::f2h(f[2 * i]) | ((uint32_t)red::f2h(f[2 * i + 1]) << 16);
+        }
+        if (c_vec && full) {
+            // same exchange for 64-byte rows: 4 lanes per row, 8 rows (4 full lines) per store instruction
+            const uint32_t tile = staging_base + (uint32_t)ewarp * 4096u;
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(tile + lane * 64u + ((i ^ ((lane >> 1) & 3)) << 4)),
+                             "r"(h[4 * i]), "r"(h[4 * i + 1]), "r"(h[4 * i + 2]), "r"(h[4 * i + 3])
+                             : "memory");
+            __syncwarp();
+            const int cw = lane & 3;
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {
+                const int rr = it * 8 + (lane >> 2);
+                uint4 w;
+                asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(w.x), "=r"(w.y), "=r"(w.z), "=r"(w.w)
+                             : "r"(tile + rr * 64u + ((cw ^ ((rr >> 1) & 3)) << 4)));
+                const int64_t mm = (int64_t)m0 + q * 32 + rr;
+                if (mm < p.M)
+                    *reinterpret_cast<uint4 *>(p.c + b * p.c_bs + mm * p.c_rs + (nbase + cw * 8) * 2) = w;
+            }
+            __syncwarp();
+        } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+                if (nbase + i < p.N)
+                    *reinterpret_cast<uint16_t *>(crow + (nbase + i) * p.c_cs) =
+                        (uint16_t)((i & 1) ? (h[i >> 1] >> 16) : (h[i >> 1] & 0xFFFFu));
+        }
+    }
+}
+
 // A_MN / B_MN: operand is MN-major (its M / N dim is the contiguous one) instead of K-major.
 // BN_: tile width in N (64 / 128 / 256). The shared-memory ring keeps the 256-wide stage stride; narrower tiles simply
 // load and multiply less of it (N = 64 attention values, N = 384 Linear layers: 3 exact 128-wide tiles instead of 2 x 256).
@@ -316,206 +517,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         const int q = warp & 3, half = (warp - 2) >> 2;
         int acc = 0;
         uint32_t acc_phase = 0;
-        const bool out_f32 = p.out_dtype == AXB_F32, out_bf16 = p.out_dtype == AXB_BF16;
-        const int osz = out_f32 ? 4 : 2;
-        const bool c_vec = (p.c_cs == osz) && ((reinterpret_cast<uintptr_t>(p.c) | (uintptr_t)p.c_rs | (uintptr_t)p.c_bs) % 16 == 0);
-        // bias as a row vector shared by all rows (nn::Linear): read once per chunk with vector loads
-        const int bsz = p.bias_dtype == AXB_F32 ? 4 : 2;
-        const bool bias_vec = p.bias && p.bias_rs == 0 && p.bias_cs == bsz && ((reinterpret_cast<uintptr_t>(p.bias) | (uintptr_t)p.bias_bs) % 16 == 0);
-        auto round_out = [&](float (&f)[32]) { // round to the half output type and come back (hardware converters)
-            if (out_bf16) {
-#pragma unroll
-                for (int i = 0; i < 32; i += 2) {
-                    uint32_t h;
-                    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(f[i + 1]), "f"(f[i]));
-                    f[i] = __uint_as_float(h << 16);
-                    f[i + 1] = __uint_as_float(h & 0xFFFF0000u);
-                }
-            } else {
-#pragma unroll
-                for (int i = 0; i < 32; ++i)
-                    f[i] = red::h2f(red::f2h(f[i]));
-            }
-        };
         for (int64_t t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
             const int64_t b = t / tiles_per_batch;
             const int r = (int)(t - b * tiles_per_batch);
             const int m0 = (r / p.tiles_n) * BM, n0 = (r % p.tiles_n) * BN_;
-            const int64_t m = m0 + q * 32 + lane;
             mbar_wait(tfull_bar(acc), acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * BN;  // accumulators sit 256 columns apart for every BN_
-            char *crow = p.c + b * p.c_bs + m * p.c_rs;
-            const char *brow = p.bias ? p.bias + b * p.bias_bs + m * p.bias_rs : nullptr;
-#pragma unroll 1
-            for (int c = half; c < BN_ / 32; c += 2) {
-                const int64_t nbase = n0 + c * 32;
-                if (nbase >= p.N)
-                    break; // warp-uniform
-                uint32_t v[32];
-                tc_ld32(taddr + c * 32, v);
-                tc_wait_ld();
-                if (grouped) { // main (hi.hi) + small-products accumulator
-                    uint32_t w[32];
-                    tc_ld32(taddr + 128u + c * 32, w);
-                    tc_wait_ld();
-#pragma unroll
-                    for (int i = 0; i < 32; ++i)
-                        v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(w[i]));
-                }
-                const bool full = nbase + 32 <= p.N;
-                if (m >= p.M && !(c_vec && full))
-                    continue; // (the exchange-based store below needs the whole warp)
-                float f[32];
-#pragma unroll
-                for (int i = 0; i < 32; ++i)
-                    f[i] = __uint_as_float(v[i]);
-                // ---- bias: a separate op in the reference, applied to the matmul result rounded to its dtype ----------
-                if (p.bias) {
-                    if (!out_f32)
-                        round_out(f);
-                    if (bias_vec && full) {
-                        const char *bp = p.bias + b * p.bias_bs + nbase * bsz;
-                        if (bsz == 4) {
-#pragma unroll
-                            for (int i = 0; i < 32; i += 4) {
-                                const float4 w = __ldg(reinterpret_cast<const float4 *>(bp) + (i >> 2));
-                                f[i] += w.x; f[i + 1] += w.y; f[i + 2] += w.z; f[i + 3] += w.w;
-                            }
-                        } else {
-#pragma unroll
-                            for (int i = 0; i < 32; i += 8) {
-                                const uint4 w = __ldg(reinterpret_cast<const uint4 *>(bp) + (i >> 3));
-                                const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
-#pragma unroll
-                                for (int k = 0; k < 4; ++k) {
-                                    if (p.bias_dtype == AXB_BF16) {
-                                        f[i + 2 * k] += __uint_as_float(ww[k] << 16);
-                                        f[i + 2 * k + 1] += __uint_as_float(ww[k] & 0xFFFF0000u);
-                                    } else {
-                                        f[i + 2 * k] += red::h2f((uint16_t)(ww[k] & 0xFFFFu));
-                                        f[i + 2 * k + 1] += red::h2f((uint16_t)(ww[k] >> 16));
-                                    }
-                                }
-                            }
-                        }
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 32; ++i)
-                            if (nbase + i < p.N)
-                                f[i] += ld_bias(brow + (nbase + i) * p.bias_cs, p.bias_dtype);
-                    }
-                }
-                // ---- activation (also a separate op: its input is rounded to the output dtype first) -----------------
-                if (p.act) {
-                    if (!out_f32)
-                        round_out(f);
-                    switch (p.act) {
-                    case AXB_OP_RELU:
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) f[i] = f[i] > 0.0f ? f[i] : 0.0f;
-                        break;
-                    case AXB_OP_GELU:
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) f[i] = hwym::Gelu(f[i]);
-                        break;
-                    case AXB_OP_SILU:
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) f[i] = hwym::Silu(f[i]);
-                        break;
-                    case AXB_OP_SIGMOID:
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) f[i] = hwym::Sigmoid(f[i]);
-                        break;
-                    default:
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) f[i] = hwym::Tanh(f[i]);
-                        break;
-                    }
-                }
-                // ---- store -----------------------------------------------------------------------------------------
-                if (out_f32) {
-                    if (c_vec && full) {
-                        // Each lane owns one ROW of the 32 x 32 chunk; written straight out, a warp store would touch 32
-                        // different 128-byte lines with 16 bytes each. The chunk goes through a swizzled shared-memory
-                        // tile instead so that 8 lanes cover one row: every store instruction writes 4 full lines.
-                        const uint32_t tile = staging_base + (uint32_t)(warp - 2) * 4096u;
-#pragma unroll
-                        for (int i = 0; i < 8; ++i)
-                            asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(tile + lane * 128u + ((i ^ (lane & 7)) << 4)),
-                                         "r"(__float_as_uint(f[4 * i])), "r"(__float_as_uint(f[4 * i + 1])), "r"(__float_as_uint(f[4 * i + 2])),
-                                         "r"(__float_as_uint(f[4 * i + 3]))
-                                         : "memory");
-                        __syncwarp();
-                        const int cw = lane & 7;
-#pragma unroll
-                        for (int it = 0; it < 8; ++it) {
-                            const int rr = it * 4 + (lane >> 3);
-                            uint4 w;
-                            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(w.x), "=r"(w.y), "=r"(w.z), "=r"(w.w)
-                                         : "r"(tile + rr * 128u + ((cw ^ (rr & 7)) << 4)));
-                            const int64_t mm = (int64_t)m0 + q * 32 + rr;
-                            if (mm < p.M)
-                                *reinterpret_cast<uint4 *>(p.c + b * p.c_bs + mm * p.c_rs + (nbase + cw * 4) * 4) = w;
-                        }
-                        __syncwarp();
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 32; ++i)
-                            if (nbase + i < p.N)
-                                *reinterpret_cast<float *>(crow + (nbase + i) * p.c_cs) = f[i];
-                    }
-                    continue;
-                }
-                uint32_t h[16];
-                if (out_bf16) {
-                    // hardware pack (NaN -> 0x7FFF); the reference encodes NaN as 0x7FC0 (bfloat16.hpp:16-27): chunks that
-                    // contain a NaN are re-packed in software (rare)
-                    float nan_acc = 0.0f;
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(h[i]) : "f"(f[2 * i + 1]), "f"(f[2 * i]));
-                        asm("max.NaN.f32 %0, %0, %1, %2;" : "+f"(nan_acc) : "f"(f[2 * i]), "f"(f[2 * i + 1]));
-                    }
-                    if (nan_acc != nan_acc) {
-#pragma unroll
-                        for (int i = 0; i < 16; ++i)
-                            h[i] = (uint32_t)red::f2bf(f[2 * i]) | ((uint32_t)red::f2bf(f[2 * i + 1]) << 16);
-                    }
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 16; ++i)
-                        h[i] = (uint32_t)red::f2h(f[2 * i]) | ((uint32_t)red::f2h(f[2 * i + 1]) << 16);
-                }
-                if (c_vec && full) {
-                    // same exchange for 64-byte rows: 4 lanes per row, 8 rows (4 full lines) per store instruction
-                    const uint32_t tile = staging_base + (uint32_t)(warp - 2) * 4096u;
-#pragma unroll
-                    for (int i = 0; i < 4; ++i)
-                        asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(tile + lane * 64u + ((i ^ ((lane >> 1) & 3)) << 4)),
-                                     "r"(h[4 * i]), "r"(h[4 * i + 1]), "r"(h[4 * i + 2]), "r"(h[4 * i + 3])
-                                     : "memory");
-                    __syncwarp();
-                    const int cw = lane & 3;
-#pragma unroll
-                    for (int it = 0; it < 4; ++it) {
-                        const int rr = it * 8 + (lane >> 2);
-                        uint4 w;
-                        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(w.x), "=r"(w.y), "=r"(w.z), "=r"(w.w)
-                                     : "r"(tile + rr * 64u + ((cw ^ ((rr >> 1) & 3)) << 4)));
-                        const int64_t mm = (int64_t)m0 + q * 32 + rr;
-                        if (mm < p.M)
-                            *reinterpret_cast<uint4 *>(p.c + b * p.c_bs + mm * p.c_rs + (nbase + cw * 8) * 2) = w;
-                    }
-                    __syncwarp();
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 32; ++i)
-                        if (nbase + i < p.N)
-                            *reinterpret_cast<uint16_t *>(crow + (nbase + i) * p.c_cs) =
-                                (uint16_t)((i & 1) ? (h[i >> 1] >> 16) : (h[i >> 1] & 0xFFFFu));
-                }
-            }
+            epilogue_tile<BN_>(p, b, m0, n0, taddr, grouped, q, half, lane, warp - 2, staging_base);
             tc_fence_before();
             __syncwarp();
             if (lane == 0)
@@ -532,6 +541,204 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         __syncwarp();
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+// ---- CTA-pair variant: tcgen05.mma.cta_group::2 --------------------------------------------------------------------
+// What bounds the one-CTA kernel on C4 is the operand bytes every SM has to take in per flop: 48 KiB per
+// 128x256x64 k-block. Here a CLUSTER OF TWO CTAs (an SM pair) owns one 256x256 tile: each CTA loads its own 128 rows of A
+// and only HALF of the B tile (128 of the 256 columns), the leader CTA issues one M = 256 MMA that reads both halves out
+// of both shared memories, and each CTA ends up with its 128 rows of the accumulator in its own TMEM. 32 KiB per k-block
+// and SM instead of 48, which also leaves room for a 6-deep ring.
+//   producer (both CTAs)  : waits on its OWN empty barrier, signals the LEADER's full barrier (TMA .cta_group::2)
+//   MMA issuer (leader)   : tcgen05.commit ... multicast::cluster releases the ring slot / publishes the accumulator in
+//                           BOTH CTAs with one instruction
+//   epilogue (both CTAs)  : same code as the one-CTA kernel on the CTA's 128 rows; arrives remotely on the leader's
+//                           "accumulator drained" barrier (count = 16 warps)
+constexpr int P_STAGES = 6;
+constexpr int PB_BYTES = 128 * BK * 2;            // this CTA's half of the 256-wide B tile
+constexpr int P_STAGE_BYTES = A_BYTES + PB_BYTES; // 32 KiB
+constexpr int P_SMEM_BYTES = P_STAGES * P_STAGE_BYTES + 1024 + 256 + STAGING_BYTES;
+static_assert(P_SMEM_BYTES <= 232448, "CTA-pair GEMM: shared memory");
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t map_shared_rank(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done)
+                     : "r"(bar), "r"(parity)
+                     : "memory");
+    } while (!done);
+}
+// destination = this CTA's shared memory, completion = the barrier at `cluster_bar` (the leader's)
+__device__ __forceinline__ void tma_load_3d_pair(uint32_t dst, const CUtensorMap *map, uint32_t cluster_bar, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"(dst), "l"(map), "r"(cluster_bar), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
+__device__ __forceinline__ void tc_commit_pair(uint32_t bar) { // arrives on the barrier at this offset in both CTAs
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+                 "h"((uint16_t)3)
+                 : "memory");
+}
+__device__ __forceinline__ void tc_mma_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+                 : "memory");
+}
+
+template <bool A_MN, bool B_MN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+                    const __grid_constant__ TcParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t smem = (raw + 1023u) & ~1023u;
+    const uint32_t bar_base = smem + P_STAGES * P_STAGE_BYTES;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (P_STAGES + s); };
+    auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * P_STAGES + a); };
+    auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * P_STAGES + 2 + a); };
+    const uint32_t tmem_slot = bar_base + 8u * (2 * P_STAGES + 4);
+    const uint32_t staging_base = bar_base + 256u;
+    uint32_t *tmem_slot_ptr = reinterpret_cast<uint32_t *>(smem_raw + (tmem_slot - raw));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank(); // 0 = leader
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < P_STAGES; ++s) {
+            mbar_init(full_bar(s), 1);  // the leader's arrive.expect_tx (covers the bytes of both CTAs)
+            mbar_init(empty_bar(s), 1); // one multicast commit
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(tfull_bar(a), 1);
+            mbar_init(tempty_bar(a), 16); // eight epilogue warps in each of the two CTAs (leader's copy is the one used)
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) { // the same warp of both CTAs: the allocation is collective over the pair
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    cluster_sync_all(); // barriers of BOTH CTAs exist before anyone signals across the pair
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+    const int num_kb = (int)((p.K + BK - 1) / BK);
+    const int64_t tiles_per_batch = (int64_t)p.tiles_m * p.tiles_n;
+    const int64_t first = blockIdx.x >> 1, step = gridDim.x >> 1;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int64_t t = first; t < p.num_tiles; t += step) {
+                const int64_t b = t / tiles_per_batch;
+                const int r = (int)(t - b * tiles_per_batch);
+                const int m0 = (r / p.tiles_n) * 256 + (int)rank * 128, n0 = (r % p.tiles_n) * 256 + (int)rank * 128;
+                const int ba = (int)b * p.a_bmult, bb = (int)b * p.b_bmult;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(empty_bar(stage), phase ^ 1u);
+                    if (rank == 0)
+                        mbar_expect_tx(full_bar(stage), 2 * P_STAGE_BYTES);
+                    const uint32_t lfull = map_shared_rank(full_bar(stage), 0);
+                    const uint32_t sa = smem + stage * P_STAGE_BYTES, sb = sa + A_BYTES;
+                    const int k0 = kb * BK;
+                    if (!A_MN) {
+                        tma_load_3d_pair(sa, &tma_a, lfull, k0, m0, ba); // box {64 k, 128 m}
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 2; ++j) // box {64 m, 64 k}
+                            tma_load_3d_pair(sa + j * (64 * BK * 2), &tma_a, lfull, m0 + 64 * j, k0, ba);
+                    }
+                    if (!B_MN) {
+                        tma_load_3d_pair(sb, &tma_b, lfull, k0, n0, bb); // box {64 k, 128 n}
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 2; ++j)
+                            tma_load_3d_pair(sb + j * (64 * BK * 2), &tma_b, lfull, n0 + 64 * j, k0, bb);
+                    }
+                    if (++stage == P_STAGES) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && rank == 0) {
+            int stage = 0, acc = 0;
+            uint32_t phase = 0, acc_phase = 0;
+            for (int64_t t = first; t < p.num_tiles; t += step) {
+                mbar_wait_cluster(tempty_bar(acc), acc_phase ^ 1u); // both epilogues have drained this accumulator
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + (uint32_t)acc * 256u;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(full_bar(stage), phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem + stage * P_STAGE_BYTES, sb = sa + A_BYTES;
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k) {
+                        const uint64_t ad = A_MN ? umma_desc(sa + k * 2048, 64 * BK * 2, 1024) : umma_desc(sa + k * 32, 16, 1024);
+                        const uint64_t bd = B_MN ? umma_desc(sb + k * 2048, 64 * BK * 2, 1024) : umma_desc(sb + k * 32, 16, 1024);
+                        tc_mma_pair(tmem_d, ad, bd, p.idesc, (kb | k) != 0);
+                    }
+                    tc_commit_pair(empty_bar(stage));
+                    if (++stage == P_STAGES) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
+                }
+                tc_commit_pair(tfull_bar(acc));
+                if (++acc == 2) {
+                    acc = 0;
+                    acc_phase ^= 1u;
+                }
+            }
+        }
+    } else {
+        const int q = warp & 3, half = (warp - 2) >> 2;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int64_t t = first; t < p.num_tiles; t += step) {
+            const int64_t b = t / tiles_per_batch;
+            const int r = (int)(t - b * tiles_per_batch);
+            const int m0 = (r / p.tiles_n) * 256 + (int)rank * 128, n0 = (r % p.tiles_n) * 256;
+            mbar_wait(tfull_bar(acc), acc_phase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * 256u;
+            epilogue_tile<256>(p, b, m0, n0, taddr, false, q, half, lane, warp - 2, staging_base);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0)
+                mbar_arrive_remote(map_shared_rank(tempty_bar(acc), 0));
+            if (++acc == 2) {
+                acc = 0;
+                acc_phase ^= 1u;
+            }
+        }
+    }
+    tc_fence_before();
+    cluster_sync_all(); // the peer's shared memory and TMEM stay alive until the leader's last MMA and commit have landed
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
     }
 }
 
@@ -799,8 +1006,10 @@ axb_status try_split_f32(const Desc &d, DeviceCtx *ctx, cudaStream_t s, bool *do
     p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
     st = launch_ff(ma, mb, p, ctx->sm_count, s);
     cleanup(); // stream-ordered: the blocks return to the pool after the GEMM in stream order
-    if (st == AXB_OK)
+    if (st == AXB_OK) {
         *done = true;
+        last_path() = 3;
+    }
     return st;
 }
 
@@ -845,8 +1054,38 @@ axb_status launch_ff(const CUtensorMap &ma, const CUtensorMap &mb, const TcParam
     return launch<false, false>(ma, mb, p, sm_count, s);
 }
 
+template <bool A_MN, bool B_MN>
+axb_status launch_pair(const CUtensorMap &ma, const CUtensorMap &mb, const TcParams &p, int sm_count, cudaStream_t s) {
+    static bool configured = false;
+    if (!configured) {
+        AXB_CUDA(cudaFuncSetAttribute(gemm_tc_pair_kernel<A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_BYTES));
+        configured = true;
+    }
+    const unsigned grid = 2u * (unsigned)std::min<int64_t>(p.num_tiles, sm_count / 2); // one cluster (SM pair) per 256x256 tile
+    gemm_tc_pair_kernel<A_MN, B_MN><<<grid, NUM_THREADS, P_SMEM_BYTES, s>>>(ma, mb, p);
+    AXB_CHECK_LAUNCH();
+    return AXB_OK;
+}
+// The CTA-pair kernel takes every problem whose 256x256 tiles fill the 74 SM pairs at least twice; AXB_GEMM_PAIR=0/1 forces it.
+bool use_pair(const Desc &d, int bn, int sm_count) {
+    static const char *force = getenv("AXB_GEMM_PAIR");
+    if (bn != 256 || d.M <= 128)
+        return false;
+    if (force)
+        return atoi(force) != 0;
+    const int64_t pad256 = (d.M + 255) / 256 * 256, pad128 = (d.M + 127) / 128 * 128;
+    if ((double)pad256 > 1.04 * (double)pad128)
+        return false; // a ragged last tile whose second half would be all padding
+    const int64_t tiles = (pad256 / 256) * ((d.N + 255) / 256) * d.batch;
+    return tiles >= 2 * (sm_count / 2);
+}
+
 } // namespace
 
+int &last_path() {
+    static thread_local int v = 0;
+    return v;
+}
 PresplitA &presplit_a_hint() {
     static thread_local PresplitA h;
     return h;
@@ -886,19 +1125,20 @@ axb_status try_tcgen05(const Desc &d, int adt, int bdt, int cdt, DeviceCtx *ctx,
     const uint64_t a_b = (uint64_t)std::max<int64_t>(a_bs, 16), b_b = (uint64_t)std::max<int64_t>(b_bs, 16);
     const uint64_t abatch = a_mult ? (uint64_t)d.batch : 1, bbatch = b_mult ? (uint64_t)d.batch : 1;
     const int bn = pick_bn(d.N);
+    const bool pair = use_pair(d, bn, ctx->sm_count);
     CUtensorMap ma, mb;
     if (!oa.mn_major)
         AXB_TRY(make_map(&ma, api, adt, d.a, (uint64_t)d.K, (uint64_t)d.M, abatch, a_ld, a_b, BK, BM));
     else
         AXB_TRY(make_map(&ma, api, adt, d.a, (uint64_t)d.M, (uint64_t)d.K, abatch, a_ld, a_b, 64, BK));
     if (!ob.mn_major)
-        AXB_TRY(make_map(&mb, api, bdt, d.b, (uint64_t)d.K, (uint64_t)d.N, bbatch, b_ld, b_b, BK, (uint32_t)bn));
+        AXB_TRY(make_map(&mb, api, bdt, d.b, (uint64_t)d.K, (uint64_t)d.N, bbatch, b_ld, b_b, BK, pair ? 128u : (uint32_t)bn));
     else
         AXB_TRY(make_map(&mb, api, bdt, d.b, (uint64_t)d.N, (uint64_t)d.K, bbatch, b_ld, b_b, 64, BK));
     TcParams p;
     memset(&p, 0, sizeof p);
     p.M = d.M; p.N = d.N; p.K = d.K; p.batch = d.batch;
-    p.tiles_m = (int)((d.M + BM - 1) / BM);
+    p.tiles_m = pair ? (int)((d.M + 255) / 256) : (int)((d.M + BM - 1) / BM);
     p.bn = bn;
     p.tiles_n = (int)((d.N + bn - 1) / bn);
     p.num_tiles = (int64_t)p.tiles_m * p.tiles_n * d.batch;
@@ -910,9 +1150,18 @@ axb_status try_tcgen05(const Desc &d, int adt, int bdt, int cdt, DeviceCtx *ctx,
     // BF16 = 1) @7/@10, a/b major (MN = 1) @15/@16, N>>3 @17, M>>4 @24
     const uint32_t fmt = adt == AXB_BF16 ? 1u : 0u;
     p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((oa.mn_major ? 1u : 0u) << 15) | ((ob.mn_major ? 1u : 0u) << 16) |
-              ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+              ((uint32_t)(bn >> 3) << 17) | ((uint32_t)((pair ? 256 : BM) >> 4) << 24);
     axb_status st;
-    if (!oa.mn_major && !ob.mn_major)
+    if (pair) {
+        if (!oa.mn_major && !ob.mn_major)
+            st = launch_pair<false, false>(ma, mb, p, ctx->sm_count, s);
+        else if (!oa.mn_major && ob.mn_major)
+            st = launch_pair<false, true>(ma, mb, p, ctx->sm_count, s);
+        else if (oa.mn_major && !ob.mn_major)
+            st = launch_pair<true, false>(ma, mb, p, ctx->sm_count, s);
+        else
+            st = launch_pair<true, true>(ma, mb, p, ctx->sm_count, s);
+    } else if (!oa.mn_major && !ob.mn_major)
         st = launch<false, false>(ma, mb, p, ctx->sm_count, s);
     else if (!oa.mn_major && ob.mn_major)
         st = launch<false, true>(ma, mb, p, ctx->sm_count, s);
@@ -920,8 +1169,10 @@ axb_status try_tcgen05(const Desc &d, int adt, int bdt, int cdt, DeviceCtx *ctx,
         st = launch<true, false>(ma, mb, p, ctx->sm_count, s);
     else
         st = launch<true, true>(ma, mb, p, ctx->sm_count, s);
-    if (st == AXB_OK)
+    if (st == AXB_OK) {
         *done = true;
+        last_path() = pair ? 2 : 1;
+    }
     return st;
 }
 

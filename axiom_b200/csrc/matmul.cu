@@ -346,7 +346,10 @@ axb_status axb_matmul(const axb_tensor *a, const axb_tensor *b, int transpose_a,
     AXB_TRY(try_tcgen05(d, a->dtype, b->dtype, cdt, ctx, s, &done));
     if (done)
         return AXB_OK;
+    last_path() = 0;
     return simt_dispatch(d, a->dtype, b->dtype, cdt, s);
 }
+
+int axb_matmul_last_path(void) { return axb::gemm::last_path(); }
 
 } // extern "C"

@@ -262,6 +262,10 @@ typedef struct axb_matmul_epilogue {
 axb_status axb_matmul(const axb_tensor *a, const axb_tensor *b, int transpose_a, int transpose_b,
                       const axb_matmul_epilogue *epilogue /* may be NULL */, const axb_tensor *out,
                       axb_stream_t stream);
+/* Which kernel the LAST axb_matmul of the calling thread ran on (tests assert the path instead of trusting a heuristic):
+ * 0 = CUDA-core (SIMT) kernel, 1 = tcgen05 one-CTA tiles, 2 = tcgen05 CTA-pair tiles (cta_group::2, 256x256),
+ * 3 = fp32 on the tensor cores (three-way bf16 split). */
+int axb_matmul_last_path(void);
 /* result shape per matmul rules (graph_registry.cpp:147-220) */
 axb_status axb_matmul_shape(const axb_tensor *a, const axb_tensor *b, int transpose_a, int transpose_b,
                             int64_t *out_shape, int *out_ndim);

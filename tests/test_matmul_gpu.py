@@ -143,6 +143,44 @@ def test_half_matmul_vs_fp32_reference(gpu, dt, shape):
         assert np.all(np.abs(gf - exp) <= 1e-2 * np.maximum(np.abs(exp), 0) + 4e-3 * mag / np.sqrt(k) + 1e-6), (dt, shape, variant)
 
 
+@pytest.mark.parametrize("dt", ["bf16", "f16"])
+@pytest.mark.parametrize("shape", [(1, 2304, 192, 4352), (1, 2248, 200, 4328), (1, 4200, 64, 2304), (5, 768, 136, 2560)])
+def test_half_matmul_cta_pair_tiles(gpu, dt, shape):
+    """Problems with >= 148 tiles of 256x256 run on the CTA-pair kernel (tcgen05.mma.cta_group::2: an SM pair shares one
+    B tile). Covers exact tiles, ragged M / N / K, a last tile whose second CTA is entirely out of bounds (M = 4200) and a
+    batch; nn / nt / tn operand layouts; the bias + activation epilogue. The path is asserted, not assumed."""
+    nb, m, k, n = shape
+    rng = np.random.default_rng(m + n + k)
+    a, b = rand_f32(rng, (nb, m, k), 1.0), rand_f32(rng, (nb, k, n), 1.0 / np.sqrt(k))
+    bias = rand_f32(rng, (n,), 0.5)
+    if dt == "bf16":
+        ha, hb, hbias = as_bf16(a), as_bf16(b), as_bf16(bias)
+        fa, fb, fbias = ao.bf16_to_f32(ha), ao.bf16_to_f32(hb), ao.bf16_to_f32(hbias)
+    else:
+        ha, hb, hbias = a.astype(np.float16), b.astype(np.float16), bias.astype(np.float16)
+        fa, fb, fbias = ha.astype(np.float32), hb.astype(np.float32), hbias.astype(np.float32)
+    up = lambda x: dev.DeviceArray.from_numpy(np.ascontiguousarray(x), bf16=(dt == "bf16"))
+    da, db = up(ha), up(hb)
+    exp = np.matmul(fa.astype(np.float64), fb.astype(np.float64))
+    mag = np.matmul(np.abs(fa.astype(np.float64)), np.abs(fb.astype(np.float64)))
+    tol = lambda e: 1e-2 * np.abs(e) + 4e-3 * mag / np.sqrt(k) + 1e-6
+    to_f = lambda g: ao.bf16_to_f32(g) if dt == "bf16" else g.astype(np.float32)
+    for variant in ("nn", "nt", "tn"):
+        if variant == "nn":
+            got = dev.matmul(da, db)
+        elif variant == "nt":
+            got = dev.matmul(da, up(hb.swapaxes(-1, -2)), transpose_b=True)
+        else:
+            got = dev.matmul(up(ha.swapaxes(-1, -2)), db, transpose_a=True)
+        assert capi.lib().axb_matmul_last_path() == 2, (variant, "expected the CTA-pair kernel")
+        assert np.all(np.abs(to_f(got.numpy()) - exp) <= tol(exp)), (dt, shape, variant)
+    got = dev.matmul(da, db, bias=up(hbias), activation="relu")
+    assert capi.lib().axb_matmul_last_path() == 2
+    # reference op order: matmul result rounded to the half type, + bias rounded, then the activation
+    ref = np.maximum(exp + fbias.astype(np.float64), 0.0)
+    assert np.all(np.abs(to_f(got.numpy()) - ref) <= tol(exp) + 1e-2 * np.abs(ref) + 8e-3 * (np.abs(exp) + np.abs(fbias))), (dt, shape)
+
+
 def test_bf16_batched_config4_subbatch(gpu):
     """BASELINE config 4 at parity size: bf16 {2,4096,4096} x {2,4096,4096}; sampled 128x128 output tiles are checked
     against an fp64 product of the same bf16 inputs."""
@@ -150,6 +188,7 @@ def test_bf16_batched_config4_subbatch(gpu):
     a = dev.cast(dev.randn((nb, n, n), 11, 0.0, 1.0), capi.BF16)
     b = dev.cast(dev.randn((nb, n, n), 12, 0.0, 1.0 / 64.0), capi.BF16)
     c = dev.matmul(a, b)
+    assert capi.lib().axb_matmul_last_path() == 2  # 512 tiles of 256x256: the CTA-pair kernel
     assert c.shape == (nb, n, n) and c.dtype == capi.BF16
     rng = np.random.default_rng(0)
     for _ in range(6):

@@ -37,6 +37,14 @@ def simple(op, n=1<<28):
     med, mn = timeit(fn)
     return dict(workload="unary_"+op, ms_med=med, GBps_med=n*8/med/1e6, GBps_min=n*8/mn/1e6)
 
+def simple_bf16(op, n=1<<28):
+    x = dev.cast(dev.randn((n,), 5), capi.BF16); out = dev.DeviceArray.empty((n,), capi.BF16)
+    o = capi.OP[op]
+    xd, od = x.desc(), out.desc()
+    fn = lambda: capi.check(L.axb_unary(o, ctypes.byref(xd), ctypes.byref(od), 0.0, None))
+    med, mn = timeit(fn)
+    return dict(workload="unary_bf16_"+op, ms_med=med, GBps_med=n*4/med/1e6, GBps_min=n*4/mn/1e6)
+
 def add(n=1<<27):
     x = dev.randn((n,), 5); y = dev.randn((n,), 6); out = dev.DeviceArray.empty((n,), capi.F32)
     fn = lambda: capi.check(L.axb_binary(0, ctypes.byref(x.desc()), ctypes.byref(y.desc()), ctypes.byref(out.desc()), None))
@@ -113,6 +121,9 @@ if __name__ == "__main__":
             _, kind, dt = w.split(":")[:3]
             extra = [int(v) for v in w.split(":")[3:]]
             print(json.dumps(c3(kind, dt, *extra)), flush=True)
+            continue
+        if w.startswith("bf16:"):
+            print(json.dumps(simple_bf16(w.split(":")[1])), flush=True)
             continue
         if w.startswith("mm:"):
             f = w.split(":")
