@@ -603,6 +603,19 @@ __device__ __forceinline__ void tc_mma_pair(uint32_t tmem_d, uint64_t adesc, uin
                  : "memory");
 }
 
+// Tile order inside one matrix: bands of GROUP_M tile rows, walked column by column, so the 74 tiles in flight cover about
+// 8 x 9 tiles (A: 2048 rows, B: 2304 columns) instead of 2.3 full tile rows — operands larger than L2 (8192^3: B alone
+// is 128 MiB) are then re-read from HBM once per band instead of once per 2.3 tile rows.
+constexpr int GROUP_M = 8;
+__device__ __forceinline__ void pair_tile_coords(int r, int tiles_m, int tiles_n, int &tm, int &tn) {
+    const int band = r / (GROUP_M * tiles_n);
+    const int first_m = band * GROUP_M;
+    const int rows = min(GROUP_M, tiles_m - first_m);
+    const int in_band = r - band * GROUP_M * tiles_n;
+    tm = first_m + in_band % rows;
+    tn = in_band / rows;
+}
+
 template <bool A_MN, bool B_MN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
@@ -651,7 +664,9 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
             for (int64_t t = first; t < p.num_tiles; t += step) {
                 const int64_t b = t / tiles_per_batch;
                 const int r = (int)(t - b * tiles_per_batch);
-                const int m0 = (r / p.tiles_n) * 256 + (int)rank * 128, n0 = (r % p.tiles_n) * 256 + (int)rank * 128;
+                int tm, tn;
+                pair_tile_coords(r, p.tiles_m, p.tiles_n, tm, tn);
+                const int m0 = tm * 256 + (int)rank * 128, n0 = tn * 256 + (int)rank * 128;
                 const int ba = (int)b * p.a_bmult, bb = (int)b * p.b_bmult;
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(empty_bar(stage), phase ^ 1u);
@@ -719,7 +734,9 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
         for (int64_t t = first; t < p.num_tiles; t += step) {
             const int64_t b = t / tiles_per_batch;
             const int r = (int)(t - b * tiles_per_batch);
-            const int m0 = (r / p.tiles_n) * 256 + (int)rank * 128, n0 = (r % p.tiles_n) * 256;
+            int tm, tn;
+            pair_tile_coords(r, p.tiles_m, p.tiles_n, tm, tn);
+            const int m0 = tm * 256 + (int)rank * 128, n0 = tn * 256;
             mbar_wait(tfull_bar(acc), acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * 256u;
