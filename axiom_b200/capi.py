@@ -153,6 +153,9 @@ def lib() -> ctypes.CDLL:
         "axb_matmul_last_path": (i32, []),
         "axb_gather": (i32, [T, i32, T, T, vp]),
         "axb_index_select": (i32, [T, i32, T, T, vp]),
+        "axb_conv2d": (i32, [T, T, T, pi32, pi32, pi32, i32, T, vp]),
+        "axb_conv_transpose": (i32, [T, T, T, i32, pi32, pi32, pi32, i32, T, vp]),
+        "axb_interpolate": (i32, [T, i32, i32, T, vp]),
         "axb_elementwise_host": (i32, [I, i32, T, i32, T]),
         "axb_reduce_host": (i32, [i32, T, pi32, i32, i32, T]),
         "axb_matmul_host": (i32, [T, T, i32, i32, T]),

@@ -212,6 +212,10 @@ struct Lowering {
             const auto &cp = get_params<ConvParams>(n->params);
             r = backends::cuda::gpu_conv1d_impl(input(n, 0), input(n, 1), input(n, 2), cp.stride.at(0), cp.padding.at(0),
                                                 cp.dilation.at(0), cp.groups);
+        } else if (op == OpType::Conv2D) {
+            const auto &cp = get_params<ConvParams>(n->params);
+            r = backends::metal::gpu_conv2d(input(n, 0), input(n, 1), input(n, 2), {cp.stride.at(0), cp.stride.at(1)},
+                                            {cp.padding.at(0), cp.padding.at(1)}, {cp.dilation.at(0), cp.dilation.at(1)}, cp.groups);
         } else if (op == OpType::BatchNorm1D) {
             // inference batch norm over the channel axis 1 (nn/normalization.cpp:88-106, lazy node graph_registry.cpp:637-655):
             // (x - running_mean) * 1/sqrt(running_var + eps) * weight + bias as ONE elementwise program in fp32

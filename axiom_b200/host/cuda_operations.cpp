@@ -508,19 +508,119 @@ Tensor gpu_linear(const Tensor &input, const Tensor &weight, const Tensor &bias,
     return cuda::gpu_matmul(input, weight, false, true, has_bias ? &bias : nullptr);
 }
 
-// outside the named hot path (SURVEY.md §8 out-of-scope list): explicit error instead of a silent CPU detour
-Tensor gpu_conv2d(const Tensor &, const Tensor &, const Tensor &, std::array<int, 2>, std::array<int, 2>, std::array<int, 2>, int) {
-    throw RuntimeError::not_implemented("conv2d on the CUDA backend");
+// ---- spatial operators next to the path: csrc/spatial.cu ------------------------------------------
+namespace {
+// common dtype of input / weight / bias; tensors moved to the device and cast where needed
+struct ConvArgs {
+    Tensor x, w, b;
+    bool has_bias = false, has_batch = true;
+};
+ConvArgs conv_args(const Tensor &input, const Tensor &weight, const Tensor &bias, size_t batched_ndim, const char *what) {
+    ConvArgs a;
+    a.x = cuda::on_gpu(input);
+    a.w = cuda::on_gpu(weight);
+    if (a.x.ndim() + 1 == batched_ndim) {
+        a.has_batch = false;
+        Shape s{1};
+        for (auto d : a.x.shape())
+            s.push_back(d);
+        a.x = a.x.reshape(s);
+    }
+    if (a.x.ndim() != batched_ndim || a.w.ndim() != batched_ndim)
+        throw ShapeError(std::string(what) + ": unexpected input / weight rank");
+    const DType dt = static_cast<DType>(axb_promote_types(cuda::to_axb_dtype(a.x.dtype()), cuda::to_axb_dtype(a.w.dtype())));
+    if (a.x.dtype() != dt)
+        a.x = cuda::gpu_cast(a.x, dt);
+    if (a.w.dtype() != dt)
+        a.w = cuda::gpu_cast(a.w, dt);
+    a.has_bias = bias.storage() && bias.ndim() > 0 && bias.size() > 0;
+    if (a.has_bias) {
+        a.b = cuda::on_gpu(bias);
+        if (a.b.dtype() != dt)
+            a.b = cuda::gpu_cast(a.b, dt);
+    }
+    return a;
 }
-Tensor gpu_conv_transpose1d(const Tensor &, const Tensor &, const Tensor &, int, int, int, int, int) {
-    throw RuntimeError::not_implemented("conv_transpose1d on the CUDA backend");
+Tensor drop_batch(const Tensor &out, bool has_batch) {
+    if (has_batch)
+        return out;
+    Shape s(out.shape().begin() + 1, out.shape().end());
+    return out.reshape(s);
 }
-Tensor gpu_conv_transpose2d(const Tensor &, const Tensor &, const Tensor &, std::array<int, 2>, std::array<int, 2>,
-                            std::array<int, 2>, std::array<int, 2>, int) {
-    throw RuntimeError::not_implemented("conv_transpose2d on the CUDA backend");
+} // namespace
+
+// ops::conv2d on the GPU arrives as a lazy OpType::Conv2D node (operations.cpp:3211-3220) and is lowered here
+Tensor gpu_conv2d(const Tensor &input, const Tensor &weight, const Tensor &bias, std::array<int, 2> stride, std::array<int, 2> padding,
+                  std::array<int, 2> dilation, int groups) {
+    ConvArgs a = conv_args(input, weight, bias, 4, "conv2d");
+    const size_t H = a.x.shape()[2], W = a.x.shape()[3], KH = a.w.shape()[2], KW = a.w.shape()[3];
+    const size_t dkh = (size_t)dilation[0] * (KH - 1) + 1, dkw = (size_t)dilation[1] * (KW - 1) + 1;
+    if (H + 2 * (size_t)padding[0] < dkh || W + 2 * (size_t)padding[1] < dkw)
+        throw ShapeError("conv2d: input too small for given kernel/padding/dilation");
+    const size_t OH = (H + 2 * (size_t)padding[0] - dkh) / (size_t)stride[0] + 1;
+    const size_t OW = (W + 2 * (size_t)padding[1] - dkw) / (size_t)stride[1] + 1;
+    Tensor out = cuda::empty_gpu({a.x.shape()[0], a.w.shape()[0], OH, OW}, a.x.dtype());
+    if (out.size() > 0) {
+        const axb_tensor xd = cuda::describe(a.x), wd = cuda::describe(a.w), od = cuda::describe(out);
+        axb_tensor bd{};
+        if (a.has_bias)
+            bd = cuda::describe(a.b);
+        const int32_t st[2] = {stride[0], stride[1]}, pd[2] = {padding[0], padding[1]}, dl[2] = {dilation[0], dilation[1]};
+        cuda::check(axb_conv2d(&xd, &wd, a.has_bias ? &bd : nullptr, st, pd, dl, groups, &od, nullptr), "axb_conv2d");
+    }
+    return drop_batch(out, a.has_batch);
 }
-Tensor gpu_interpolate(const Tensor &, const std::vector<size_t> &, ops::InterpolateMode, bool) {
-    throw RuntimeError::not_implemented("interpolate on the CUDA backend");
+
+Tensor gpu_conv_transpose2d(const Tensor &input, const Tensor &weight, const Tensor &bias, std::array<int, 2> stride,
+                            std::array<int, 2> padding, std::array<int, 2> output_padding, std::array<int, 2> dilation, int groups) {
+    ConvArgs a = conv_args(input, weight, bias, 4, "conv_transpose2d");
+    const size_t H = a.x.shape()[2], W = a.x.shape()[3], KH = a.w.shape()[2], KW = a.w.shape()[3];
+    // output extent exactly as the reference computes it (operations.cpp:3546-3553)
+    const size_t OH = (H - 1) * (size_t)stride[0] - 2 * (size_t)padding[0] + (size_t)dilation[0] * (KH - 1) + (size_t)output_padding[0] + 1;
+    const size_t OW = (W - 1) * (size_t)stride[1] - 2 * (size_t)padding[1] + (size_t)dilation[1] * (KW - 1) + (size_t)output_padding[1] + 1;
+    Tensor out = cuda::empty_gpu({a.x.shape()[0], a.w.shape()[1] * (size_t)groups, OH, OW}, a.x.dtype());
+    if (out.size() > 0) {
+        const axb_tensor xd = cuda::describe(a.x), wd = cuda::describe(a.w), od = cuda::describe(out);
+        axb_tensor bd{};
+        if (a.has_bias)
+            bd = cuda::describe(a.b);
+        const int32_t st[2] = {stride[0], stride[1]}, pd[2] = {padding[0], padding[1]}, dl[2] = {dilation[0], dilation[1]};
+        cuda::check(axb_conv_transpose(&xd, &wd, a.has_bias ? &bd : nullptr, 2, st, pd, dl, groups, &od, nullptr), "axb_conv_transpose");
+    }
+    return drop_batch(out, a.has_batch);
+}
+
+Tensor gpu_conv_transpose1d(const Tensor &input, const Tensor &weight, const Tensor &bias, int stride, int padding, int output_padding,
+                            int dilation, int groups) {
+    ConvArgs a = conv_args(input, weight, bias, 3, "conv_transpose1d");
+    const size_t L = a.x.shape()[2], K = a.w.shape()[2];
+    const size_t OL = (L - 1) * (size_t)stride - 2 * (size_t)padding + (size_t)dilation * (K - 1) + (size_t)output_padding + 1; // :3386-3389
+    Tensor out = cuda::empty_gpu({a.x.shape()[0], a.w.shape()[1] * (size_t)groups, OL}, a.x.dtype());
+    if (out.size() > 0) {
+        const axb_tensor xd = cuda::describe(a.x), wd = cuda::describe(a.w), od = cuda::describe(out);
+        axb_tensor bd{};
+        if (a.has_bias)
+            bd = cuda::describe(a.b);
+        const int32_t st = stride, pd = padding, dl = dilation;
+        cuda::check(axb_conv_transpose(&xd, &wd, a.has_bias ? &bd : nullptr, 1, &st, &pd, &dl, groups, &od, nullptr), "axb_conv_transpose");
+    }
+    return drop_batch(out, a.has_batch);
+}
+
+Tensor gpu_interpolate(const Tensor &input, const std::vector<size_t> &size, ops::InterpolateMode mode, bool align_corners) {
+    const Tensor x = cuda::on_gpu(input);
+    if (x.ndim() != 3 && x.ndim() != 4)
+        throw ValueError("interpolate: only 1D and 2D spatial interpolation supported, got " + std::to_string(x.ndim() - 2) + "D");
+    Shape os{x.shape()[0], x.shape()[1]};
+    for (auto v : size)
+        os.push_back(v);
+    Tensor out = cuda::empty_gpu(os, x.dtype());
+    if (out.size() > 0) {
+        const axb_tensor xd = cuda::describe(x), od = cuda::describe(out);
+        const int m = mode == ops::InterpolateMode::Nearest ? 0 : mode == ops::InterpolateMode::Bilinear ? 1 : 2;
+        cuda::check(axb_interpolate(&xd, m, align_corners ? 1 : 0, &od, nullptr), "axb_interpolate");
+    }
+    return out;
 }
 
 } // namespace metal

@@ -301,6 +301,26 @@ axb_status axb_pad_constant(const axb_tensor *in, const int64_t *pad_lo, const i
                             const axb_tensor *out, axb_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Spatial operators next to the path. Replace the reference's scalar CPU loops / MPSGraph calls:
+ *   axb_conv2d          ops::conv2d (src/tensor/operations.cpp:3141-3330; lazy OpType::Conv2D on the GPU, :3211-3220):
+ *                       in (N, C_in, H, W), weight (C_out, C_in/groups, KH, KW), bias {C_out} or NULL, out (N, C_out, OH, OW)
+ *   axb_conv_transpose  ops::conv_transpose1d / 2d (:3340-3690, hook backends::metal::gpu_conv_transpose1d/2d :3395, :3563):
+ *                       spatial_dims 1: in (N, C_in, L), weight (C_in, C_out/groups, K); 2: the 4-d forms. The output
+ *                       shape (which carries output_padding) is the caller's, as in the reference.
+ *   axb_interpolate     ops::interpolate (:3694-3975, hook gpu_interpolate :3742): in (N, C, L) or (N, C, H, W);
+ *                       mode 0 nearest, 1 linear / bilinear, 2 bicubic (1-d inputs: every non-nearest mode is linear)
+ * Inputs and weights may be strided views; outputs are contiguous; floating dtypes; fp32 results are bit-identical to the
+ * CPU loops (same accumulation type and term order).
+ * ---------------------------------------------------------------------------------------------- */
+axb_status axb_conv2d(const axb_tensor *in, const axb_tensor *weight, const axb_tensor *bias /* may be NULL */,
+                      const int32_t stride[2], const int32_t padding[2], const int32_t dilation[2], int groups,
+                      const axb_tensor *out, axb_stream_t stream);
+axb_status axb_conv_transpose(const axb_tensor *in, const axb_tensor *weight, const axb_tensor *bias /* may be NULL */,
+                              int spatial_dims, const int32_t *stride, const int32_t *padding, const int32_t *dilation,
+                              int groups, const axb_tensor *out, axb_stream_t stream);
+axb_status axb_interpolate(const axb_tensor *in, int mode, int align_corners, const axb_tensor *out, axb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Host-buffer entry points (what `Tensor::gpu()` ... `.cpu()` does end to end: H2D, launch, D2H, sync).
  * Inputs/outputs are HOST tensors (base = host pointer, contiguous or strided); used by bench.py's
  * `e2e` leg and by callers that hold no device memory. Staging goes through the caching allocator and

@@ -34,10 +34,6 @@ GPU_SUITES = ["test_cpu_gpu_parity", "test_fusion", "test_fusion_extended", "tes
 # exp(b * log a), src/backends/cpu/cpu_operations.cpp:229-262) and this backend reproduces the CPU backend bit for bit.
 KNOWN_DIVERGENT = {
     "test_tensor_operations": {"TensorOperations.UnsupportedGpuOpFallback"},
-    # outside the named hot path (SURVEY.md §8 "next" row 4 / out of scope): these ops raise RuntimeError::not_implemented
-    # on the CUDA backend instead of silently running on the CPU, so the reference's GPU variants of the tests fail loudly
-    "test_conv_transpose": {"ConvTranspose.Conv1dGPU", "ConvTranspose.Conv2dGPU"},
-    "test_interpolate": {"Interpolate.BilinearGPU", "Interpolate.NearestGPU"},
 }
 
 
@@ -113,3 +109,20 @@ def test_config5_whisper_encoder_matches_cpu_backend(gpu):
     j = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
     assert r.returncode == 0 and j["parity_ok"], j
     assert j["max_abs_diff"] <= 1e-3
+
+
+@pytest.mark.gpu
+def test_spatial_ops_match_cpu_backend(gpu):
+    """conv2d (lazy OpType::Conv2D), conv_transpose1d/2d and interpolate (SURVEY.md §8f row 4) through the reference API on
+    Device::GPU against the same call on Device::CPU: strides / paddings / dilations / output paddings / groups / bias /
+    unbatched and strided inputs / three interpolate modes x align_corners / four float dtypes. fp32 is bit-identical."""
+    _need_build()
+    exe = os.path.join(BUILD, "spatial_parity")
+    if not os.path.exists(exe):
+        pytest.skip("spatial_parity not built")
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=900)
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert lines, r.stdout[-2000:] + r.stderr[-2000:]
+    j = json.loads(lines[-1])
+    assert j["failed"] == 0 and r.returncode == 0, j
+    assert j["cases"] >= 200 and j["bit_exact_f32"] == j["f32_cases"], j
