@@ -106,7 +106,29 @@ struct Builder {
                 line(s);
                 return; // conversions carry no rounding flag
             }
-            s = std::string("EW_OP(") + ((fl & FL_SWAP) ? "true" : "false") + ", AXB_" + d->kind + "(" + d->expr + "))";
+            std::string expr = d->expr;
+            if ((fl & 3u) == RND_BF16 || (fl & 3u) == RND_F16) {
+                // half-type transcendentals: fp32 evaluation + exact fallback near rounding boundaries (ew_prelude.cuh hfast::)
+                const char *fast = nullptr;
+                switch (op) {
+                case M_FA_EXP: fast = "Exp"; break;
+                case M_FA_LOG: fast = "Log"; break;
+                case M_FA_SIN: fast = "Sin"; break;
+                case M_FA_COS: fast = "Cos"; break;
+                case M_FA_TAN: fast = "Tan"; break;
+                case M_FA_ERF: fast = "Erf"; break;
+                case M_FA_CBRT: fast = "Cbrt"; break;
+                case M_FA_TANH: fast = "Tanh"; break;
+                case M_FA_SIGMOID: fast = "Sigmoid"; break;
+                case M_FA_SILU: fast = "Silu"; break;
+                case M_FA_GELU: fast = "Gelu"; break;
+                case M_FA_SQRT: expr = "__fsqrt_rn(a)"; break; // float(sqrt(double)) == correctly rounded fp32 sqrt
+                default: break;
+                }
+                if (fast)
+                    expr = std::string("hfast::") + fast + ((fl & 3u) == RND_BF16 ? "<16>(a)" : "<13>(a)");
+            }
+            s = std::string("EW_OP(") + ((fl & FL_SWAP) ? "true" : "false") + ", AXB_" + d->kind + "(" + expr + "))";
             line(s);
             break;
         }
