@@ -650,6 +650,7 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
+    __syncthreads();    // (the CTA-level barrier is what compute-sanitizer's racecheck tracks for the TMEM-slot read below)
     cluster_sync_all(); // barriers of BOTH CTAs exist before anyone signals across the pair
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;

@@ -299,3 +299,41 @@ def index_select(x: DeviceArray, dim: int, idx: DeviceArray) -> DeviceArray:
     check(lib().axb_index_select(ctypes.byref(x.desc()), dim, ctypes.byref(idx.desc()), ctypes.byref(out.desc()),
                                  None))
     return out
+
+
+# ---- spatial operators next to the path (csrc/spatial.cu; ops::conv2d / conv_transpose1d,2d / interpolate) ------------
+def _i32s(v, n):
+    v = [int(v)] * n if isinstance(v, int) else [int(t) for t in v]
+    return (ctypes.c_int32 * n)(*v)
+
+
+def conv2d(x: DeviceArray, w: DeviceArray, bias: Optional[DeviceArray] = None, stride=1, padding=0, dilation=1,
+           groups: int = 1) -> DeviceArray:
+    st, pd, dl = _i32s(stride, 2), _i32s(padding, 2), _i32s(dilation, 2)
+    n, _, h, wd = x.shape
+    cout, _, kh, kw = w.shape
+    oh = (h + 2 * pd[0] - dl[0] * (kh - 1) - 1) // st[0] + 1
+    ow = (wd + 2 * pd[1] - dl[1] * (kw - 1) - 1) // st[1] + 1
+    out = DeviceArray.empty((n, cout, oh, ow), x.dtype)
+    check(lib().axb_conv2d(ctypes.byref(x.desc()), ctypes.byref(w.desc()), ctypes.byref(bias.desc()) if bias else None,
+                           st, pd, dl, groups, ctypes.byref(out.desc()), None))
+    return out
+
+
+def conv_transpose(x: DeviceArray, w: DeviceArray, bias: Optional[DeviceArray] = None, stride=1, padding=0,
+                   output_padding=0, dilation=1, groups: int = 1) -> DeviceArray:
+    nsp = len(x.shape) - 2
+    st, pd, op, dl = _i32s(stride, nsp), _i32s(padding, nsp), _i32s(output_padding, nsp), _i32s(dilation, nsp)
+    sp = [(x.shape[2 + i] - 1) * st[i] - 2 * pd[i] + dl[i] * (w.shape[2 + i] - 1) + op[i] + 1 for i in range(nsp)]
+    out = DeviceArray.empty((x.shape[0], w.shape[1] * groups, *sp), x.dtype)
+    check(lib().axb_conv_transpose(ctypes.byref(x.desc()), ctypes.byref(w.desc()),
+                                   ctypes.byref(bias.desc()) if bias else None, nsp, st, pd, dl, groups,
+                                   ctypes.byref(out.desc()), None))
+    return out
+
+
+def interpolate(x: DeviceArray, size: Sequence[int], mode: str = "nearest", align_corners: bool = False) -> DeviceArray:
+    out = DeviceArray.empty((x.shape[0], x.shape[1], *size), x.dtype)
+    m = {"nearest": 0, "linear": 1, "bilinear": 1, "bicubic": 2}[mode]
+    check(lib().axb_interpolate(ctypes.byref(x.desc()), m, int(align_corners), ctypes.byref(out.desc()), None))
+    return out

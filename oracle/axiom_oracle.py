@@ -489,3 +489,116 @@ def matmul(a: np.ndarray, adt: int, b: np.ndarray, bdt: int, ta: bool = False, t
     if rdt in (BF16, F16):
         return cast(np.asarray(r, np.float32), F32, rdt), rdt
     return np.asarray(r).astype(NP_OF[rdt]), rdt
+
+
+# ---- spatial operators (small-case restatements in plain loops; fp32) ---------------------------------------------------
+def conv2d_f32(x, w, bias=None, stride=(1, 1), padding=(0, 0), dilation=(1, 1), groups=1):
+    """ops::conv2d CPU loop (src/tensor/operations.cpp:3263-3318): fp64 accumulator over (ic, fh, fw), + bias, one rounding."""
+    n, cin, h, wd = x.shape
+    cout, cg, kh, kw = w.shape
+    oh = (h + 2 * padding[0] - dilation[0] * (kh - 1) - 1) // stride[0] + 1
+    ow = (wd + 2 * padding[1] - dilation[1] * (kw - 1) - 1) // stride[1] + 1
+    out = np.zeros((n, cout, oh, ow), np.float32)
+    cog = cout // groups
+    xd, wdd = x.astype(np.float64), w.astype(np.float64)
+    for b in range(n):
+        for oc in range(cout):
+            g = oc // cog
+            for i in range(oh):
+                for j in range(ow):
+                    acc = 0.0
+                    for ic in range(cg):
+                        for fh in range(kh):
+                            ih = i * stride[0] - padding[0] + fh * dilation[0]
+                            if ih < 0 or ih >= h:
+                                continue
+                            for fw in range(kw):
+                                iw = j * stride[1] - padding[1] + fw * dilation[1]
+                                if 0 <= iw < wd:
+                                    acc += xd[b, g * cg + ic, ih, iw] * wdd[oc, ic, fh, fw]
+                    if bias is not None:
+                        acc += float(bias[oc])
+                    out[b, oc, i, j] = np.float32(acc)
+    return out
+
+
+def conv_transpose2d_f32(x, w, bias=None, stride=(1, 1), padding=(0, 0), output_padding=(0, 0), dilation=(1, 1), groups=1):
+    """ops::conv_transpose2d CPU loop (src/tensor/operations.cpp:3590-3690; 1-d: :3425-3486 with H = 1): scatter of
+    out += float(double(in) * double(w)) in fp32, order (ic, ih, iw, oc, fh, fw); bias added last in fp32."""
+    n, cin, h, wd = x.shape
+    _, cog, kh, kw = w.shape
+    cout = cog * groups
+    cig = cin // groups
+    oh = (h - 1) * stride[0] - 2 * padding[0] + dilation[0] * (kh - 1) + output_padding[0] + 1
+    ow = (wd - 1) * stride[1] - 2 * padding[1] + dilation[1] * (kw - 1) + output_padding[1] + 1
+    out = np.zeros((n, cout, oh, ow), np.float32)
+    for b in range(n):
+        for g in range(groups):
+            for ic in range(g * cig, (g + 1) * cig):
+                for ih in range(h):
+                    for iw in range(wd):
+                        v = float(x[b, ic, ih, iw])
+                        for oc in range(cog):
+                            for fh in range(kh):
+                                o_h = ih * stride[0] - padding[0] + fh * dilation[0]
+                                if o_h < 0 or o_h >= oh:
+                                    continue
+                                for fw in range(kw):
+                                    o_w = iw * stride[1] - padding[1] + fw * dilation[1]
+                                    if 0 <= o_w < ow:
+                                        out[b, g * cog + oc, o_h, o_w] += np.float32(v * float(w[ic, oc, fh, fw]))
+    if bias is not None:
+        out += bias.astype(np.float32).reshape(1, cout, 1, 1)
+    return out
+
+
+def interpolate2d_f32(x, size, mode="nearest", align_corners=False):
+    """ops::interpolate CPU loop (src/tensor/operations.cpp:3826-3955): coordinates and weights in fp32, every product
+    and sum rounded on its own (no FMA contraction in the reference's x86-64 build)."""
+    f = np.float32
+    n, c, h, w = x.shape
+    oh, ow = size
+    out = np.zeros((n, c, oh, ow), np.float32)
+
+    def src(o, i, t):
+        if align_corners and t > 1:
+            return f(f(o) * f(i - 1)) / f(t - 1)
+        return f(f(f(f(o) + f(0.5)) * f(i)) / f(t)) - f(0.5)
+
+    def cubic(v):
+        v = f(abs(v))
+        if v <= 1:
+            return f(f(f(f(f(f(1.25) * v) * v) * v) - f(f(f(2.25) * v) * v)) + f(1))
+        if v < 2:
+            return f(f(f(f(f(f(-0.75) * v) * v) * v) - f(f(f(-3.75) * v) * v)) + f(f(-6) * v)) - f(-3)
+        return f(0)
+
+    for i in range(oh):
+        for j in range(ow):
+            if mode == "nearest":
+                sh = min(int(f(f(i) * f(h)) / f(oh)), h - 1)
+                sw = min(int(f(f(j) * f(w)) / f(ow)), w - 1)
+                out[:, :, i, j] = x[:, :, sh, sw]
+                continue
+            fh, fw = src(i, h, oh), src(j, w, ow)
+            if mode == "bilinear":
+                fh, fw = max(f(0), min(fh, f(h - 1))), max(f(0), min(fw, f(w - 1)))
+                h0, w0 = int(fh), int(fw)
+                h1, w1 = min(h0 + 1, h - 1), min(w0 + 1, w - 1)
+                wh, ww = f(fh - f(h0)), f(fw - f(w0))
+                ah, aw = f(f(1) - wh), f(f(1) - ww)
+                val = f(f(ah * aw) * x[:, :, h0, w0]) + f(f(ah * ww) * x[:, :, h0, w1])
+                val = f(val) + f(f(wh * aw) * x[:, :, h1, w0])
+                out[:, :, i, j] = f(val) + f(f(wh * ww) * x[:, :, h1, w1])
+            else:
+                hf, wf = int(np.floor(fh)), int(np.floor(fw))
+                val = np.zeros((n, c), np.float32)
+                for dh in range(-1, 3):
+                    sh = max(0, min(hf + dh, h - 1))
+                    a = cubic(f(fh - f(hf + dh)))
+                    for dw in range(-1, 3):
+                        sw = max(0, min(wf + dw, w - 1))
+                        bq = cubic(f(fw - f(wf + dw)))
+                        val = (val + (f(a * bq) * x[:, :, sh, sw]).astype(np.float32)).astype(np.float32)
+                out[:, :, i, j] = val
+    return out

@@ -15,5 +15,15 @@ x = f(33, 70001); dev.argreduce("argmax", x, 1); dev.reduce("sum", x, [1]); dev.
 a = f(512, 320); bt = f(384, 320); dev.matmul(a, bt, transpose_b=True, bias=f(384), activation="gelu")   # fp32 split GEMM
 ab = dev.cast(f(300, 200), capi.BF16); bb = dev.cast(f(200, 260), capi.BF16); dev.matmul(ab, bb)
 a3 = f(3, 200, 96); b3 = f(3, 96, 300); dev.matmul(a3, b3)
+# CTA-pair GEMM (153 tiles of 256x256, ragged M / N, one k-block and three): cluster barriers, remote arrives, multicast commits
+ap = dev.cast(f(2250, 64), capi.BF16); bp = dev.cast(f(64, 4330 // 8 * 8), capi.BF16); dev.matmul(ap, bp); assert capi.lib().axb_matmul_last_path() == 2
+ap = dev.cast(f(2304, 192), capi.BF16); bp = dev.cast(f(4352, 192), capi.BF16); dev.matmul(ap, bp, transpose_b=True, bias=dev.cast(f(4352), capi.BF16), activation="relu")
+# half-type transcendentals (fp32 evaluation + double fallback), bf16 pair rounding / PRMT store, ragged tail
+xh = dev.cast(f(1000, 37), capi.BF16); dev.unary("gelu", xh); dev.unary("exp", xh); dev.unary("relu", xh)
+# spatial operators
+xs = f(2, 4, 9, 10); dev.conv2d(xs, f(8, 2, 3, 2), f(8), stride=(2, 1), padding=(1, 2), dilation=(1, 2), groups=2)
+dev.conv_transpose(f(2, 4, 5, 6), f(4, 3, 3, 2), f(6), stride=(2, 3), padding=(1, 0), output_padding=(1, 2), groups=2)
+dev.conv_transpose(f(3, 4, 11), f(4, 2, 5), None, stride=3, padding=2, output_padding=1, dilation=2, groups=2)
+for m in ("nearest", "bilinear", "bicubic"): dev.interpolate(xs, (7, 13), m, True)
 dev.synchronize()
 print("sanitize targets ok")
