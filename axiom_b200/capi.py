@@ -156,6 +156,13 @@ def lib() -> ctypes.CDLL:
         "axb_conv2d": (i32, [T, T, T, pi32, pi32, pi32, i32, T, vp]),
         "axb_conv_transpose": (i32, [T, T, T, i32, pi32, pi32, pi32, i32, T, vp]),
         "axb_interpolate": (i32, [T, i32, i32, T, vp]),
+        "axb_peer_mailbox_create": (i32, [pvp, ctypes.c_char_p]),
+        "axb_peer_mailbox_open": (i32, [ctypes.c_char_p, pvp]),
+        "axb_peer_mailbox_close": (i32, [vp]),
+        "axb_peer_mailbox_destroy": (i32, [vp]),
+        "axb_peer_group_create": (i32, [i32, i32, pvp, pvp]),
+        "axb_peer_group_destroy": (i32, [vp]),
+        "axb_reduce_sharded": (i32, [i32, T, i64, vp, T, vp]),
         "axb_elementwise_host": (i32, [I, i32, T, i32, T]),
         "axb_reduce_host": (i32, [i32, T, pi32, i32, i32, T]),
         "axb_matmul_host": (i32, [T, T, i32, i32, T]),

@@ -16,6 +16,7 @@
 // extreme, NaN (and values equal to lowest()/max()) never win, so an all-NaN row yields 0 (:2211-2228).
 #include <algorithm>
 #include <cstring>
+#include <type_traits>
 #include <vector>
 
 #include "axb_internal.h"
@@ -77,7 +78,7 @@ __global__ void __launch_bounds__(256) reduce_rows_kernel(const __grid_constant_
     }
     acc = group_reduce<Acc, Op, TPR>(acc);
     if (row_ok && lane == 0) {
-        if (p.split > 1)
+        if (p.split > 1 || p.peer_world > 1)
             reinterpret_cast<Acc *>(p.ws)[row * p.split + blockIdx.y] = acc;
         else
             finalize<Acc, Op>(p, row, acc);
@@ -125,7 +126,7 @@ __global__ void __launch_bounds__(256) reduce_cols_kernel(const __grid_constant_
 #pragma unroll
             for (int y = 1; y < 8; ++y)
                 a = Op::combine(a, sm[y][tx * VEC + k]);
-            if (p.split > 1)
+            if (p.split > 1 || p.peer_world > 1)
                 reinterpret_cast<Acc *>(p.ws)[(o0 + k) * p.split + blockIdx.y] = a;
             else
                 finalize<Acc, Op>(p, o0 + k, a);
@@ -134,7 +135,64 @@ __global__ void __launch_bounds__(256) reduce_cols_kernel(const __grid_constant_
 }
 
 // second pass of split reductions: one thread per output over `split` partials
+// Sharded full reduction (the one exchange step of the path), fused into the finish kernel: thread 0 folds
+// this GPU's split partials, then thread t < world STORES the shard's value into rank t's mailbox over NVLink and polls
+// slot t of the own mailbox; thread 0 combines the `world` values in rank order (every rank computes the identical
+// result) and finalises. One 64-bit word carries (call counter, fp32 value), so a reader never sees a torn pair; two
+// banks selected by the counter's parity make the mailbox reusable without a reset: a rank can only reach call k + 2
+// (which overwrites bank k & 1) after every rank has delivered call k + 1, i.e. after every rank has finished reading
+// call k. No collective library call, no host round trip: the exchange costs one NVLink store + one polled load.
+__device__ __forceinline__ void peer_store(uint64_t *addr, uint64_t v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(addr), "l"(v) : "memory");
+}
+__device__ __forceinline__ uint64_t peer_load(const uint64_t *addr) {
+    uint64_t v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(addr) : "memory");
+    return v;
+}
+template <typename Acc, class Op> __device__ __forceinline__ void peer_finish(const Params &p) {
+    if constexpr (sizeof(Acc) == 4 && std::is_floating_point<Acc>::value) {
+        __shared__ float mine, vals[kMaxPeers];
+        if (threadIdx.x == 0) {
+            const Acc *w = reinterpret_cast<const Acc *>(p.ws);
+            Acc a = Op::template identity<Acc>();
+            for (int s = 0; s < p.split; ++s)
+                a = Op::combine(a, w[s]);
+            mine = a;
+        }
+        __syncthreads();
+        const int t = threadIdx.x;
+        if (t < p.peer_world) {
+            const uint32_t bank = (p.peer_seq & 1u) * kMaxPeers;
+            peer_store(p.peer_box[t] + bank + p.peer_rank, ((uint64_t)p.peer_seq << 32) | __float_as_uint(mine));
+            const uint64_t *slot = p.peer_box[p.peer_rank] + bank + t;
+            uint64_t w = peer_load(slot);
+            const long long t0 = clock64();
+            while ((uint32_t)(w >> 32) != p.peer_seq) {
+                if (clock64() - t0 > 6000000000ll) { // ~3 s: a rank never arrived — poison the result instead of hanging
+                    w = 0x7FC00000ull;
+                    break;
+                }
+                __nanosleep(64);
+                w = peer_load(slot);
+            }
+            vals[t] = __uint_as_float((uint32_t)w);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            Acc tot = vals[0];
+            for (int r = 1; r < p.peer_world; ++r)
+                tot = Op::combine(tot, (Acc)vals[r]);
+            finalize<Acc, Op>(p, 0, tot);
+        }
+    }
+}
+
 template <typename Acc, class Op> __global__ void reduce_finish_kernel(const __grid_constant__ Params p) {
+    if (p.peer_world > 1) {
+        peer_finish<Acc, Op>(p);
+        return;
+    }
     const int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (o >= p.n_out)
         return;
@@ -360,7 +418,7 @@ template <typename In, typename Acc, class Op>
 axb_status run_typed(Params &p, DeviceCtx *ctx, cudaStream_t s) {
     Launch L = choose(p, sizeof(In), ctx->sm_count, true);
     void *ws = nullptr;
-    if (p.split > 1) {
+    if (p.split > 1 || p.peer_world > 1) {
         AXB_TRY(axb_alloc((size_t)p.n_out * p.split * sizeof(Acc), s, &ws));
         p.ws = static_cast<char *>(ws);
     }
@@ -396,7 +454,7 @@ axb_status run_typed(Params &p, DeviceCtx *ctx, cudaStream_t s) {
         }
         count_launch();
     }
-    if (p.split > 1) {
+    if (p.split > 1 || p.peer_world > 1) {
         reduce_finish_kernel<Acc, Op><<<(unsigned)((p.n_out + 127) / 128), 128, 0, s>>>(p);
         cudaError_t e = cudaGetLastError();
         axb_free(ws, s); // stream-ordered: reusable only by later work on `s`
@@ -467,6 +525,18 @@ template <typename In, typename Cmp> axb_status run_arg(bool is_max, Params &p, 
 using namespace axb;
 using namespace axb::red;
 
+// ---- sharded full reductions: peer mailboxes -------------------------------------------------------------------------
+struct axb_peer_group {
+    int rank = 0, world = 1;
+    uint64_t *box[axb::red::kMaxPeers] = {};
+    uint32_t seq = 0;          // calls issued so far; every rank issues the same sequence of sharded reductions
+    int64_t global_count = 0;  // divisor of a sharded Mean (set per call)
+};
+static const axb_peer_group *&pending_peer_group() {
+    static thread_local const axb_peer_group *g = nullptr;
+    return g;
+}
+
 extern "C" {
 
 // What the caller of the reference's CPU op observes (execute_reduction_typed keeps the input dtype; the graph
@@ -518,6 +588,18 @@ axb_status axb_reduce(int32_t op, const axb_tensor *in, const int32_t *axes, int
                 (long long)numel(*out), (long long)p.n_out);
     (void)keep_dims;
     p.count = p.n_red;
+    if (const axb_peer_group *g = pending_peer_group()) { // set by axb_reduce_sharded for exactly this call
+        pending_peer_group() = nullptr;
+        AXB_REQUIRE(p.n_out == 1 && (op == AXB_OP_SUM || op == AXB_OP_MEAN || op == AXB_OP_MAX || op == AXB_OP_MIN) &&
+                        (in->dtype == AXB_F32 || in->dtype == AXB_BF16 || in->dtype == AXB_F16),
+                    AXB_ERR_UNSUPPORTED, "axb_reduce_sharded: full sum / mean / max / min of f32, bf16 or f16 shards only");
+        for (int r = 0; r < g->world; ++r)
+            p.peer_box[r] = g->box[r];
+        p.peer_rank = g->rank;
+        p.peer_world = g->world;
+        p.peer_seq = g->seq;
+        p.count = g->global_count;
+    }
     switch (in->dtype) {
     case AXB_F32: return run_op<float, float>(op, p, ctx, s);
     case AXB_BF16: return run_op<bf16_t, float>(op, p, ctx, s);
@@ -582,6 +664,77 @@ axb_status axb_argreduce(int32_t op, const axb_tensor *in, int axis, int keep_di
     case AXB_U64: return run_arg<uint64_t, uint64_t>(mx, p, ctx, s);
     default: return fail(AXB_ERR_UNSUPPORTED, "axb_argreduce: dtype %d unsupported", in->dtype);
     }
+}
+
+// Mailbox = 2 banks x kMaxPeers 64-bit words in DEVICE memory of the calling rank's GPU, allocated with cudaMalloc (the
+// caching pool sub-allocates, and an IPC handle names a whole allocation). The handle travels to the other ranks through
+// the host plumbing (torch.distributed in axiom_b200/shard.py) and is opened there with axb_peer_mailbox_open.
+axb_status axb_peer_mailbox_create(void **mailbox, unsigned char ipc_handle[64]) {
+    AXB_REQUIRE(mailbox && ipc_handle, AXB_ERR_INVALID, "axb_peer_mailbox_create: null argument");
+    cudaStream_t s;
+    AXB_TRY(resolve_stream(nullptr, &s));
+    void *ptr = nullptr;
+    AXB_CUDA(cudaMalloc(&ptr, 2 * axb::red::kMaxPeers * sizeof(uint64_t)));
+    AXB_CUDA(cudaMemset(ptr, 0, 2 * axb::red::kMaxPeers * sizeof(uint64_t)));
+    AXB_CUDA(cudaDeviceSynchronize());
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    cudaIpcMemHandle_t h;
+    AXB_CUDA(cudaIpcGetMemHandle(&h, ptr));
+    memcpy(ipc_handle, &h, 64);
+    *mailbox = ptr;
+    return AXB_OK;
+}
+axb_status axb_peer_mailbox_open(const unsigned char ipc_handle[64], void **peer_mailbox) {
+    AXB_REQUIRE(ipc_handle && peer_mailbox, AXB_ERR_INVALID, "axb_peer_mailbox_open: null argument");
+    cudaStream_t s;
+    AXB_TRY(resolve_stream(nullptr, &s));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, ipc_handle, 64);
+    AXB_CUDA(cudaIpcOpenMemHandle(peer_mailbox, h, cudaIpcMemLazyEnablePeerAccess));
+    return AXB_OK;
+}
+axb_status axb_peer_mailbox_close(void *peer_mailbox) {
+    AXB_CUDA(cudaIpcCloseMemHandle(peer_mailbox));
+    return AXB_OK;
+}
+axb_status axb_peer_mailbox_destroy(void *mailbox) {
+    AXB_CUDA(cudaFree(mailbox));
+    return AXB_OK;
+}
+axb_status axb_peer_group_create(int rank, int world, void *const *mailboxes, axb_peer_group **group) {
+    AXB_REQUIRE(group && mailboxes && world >= 1 && world <= axb::red::kMaxPeers && rank >= 0 && rank < world, AXB_ERR_INVALID,
+                "axb_peer_group_create: need 1 <= world <= %d and 0 <= rank < world", axb::red::kMaxPeers);
+    axb_peer_group *g = new axb_peer_group();
+    g->rank = rank;
+    g->world = world;
+    for (int r = 0; r < world; ++r) {
+        if (!mailboxes[r]) {
+            delete g;
+            return fail(AXB_ERR_INVALID, "axb_peer_group_create: mailbox %d is null", r);
+        }
+        g->box[r] = static_cast<uint64_t *>(mailboxes[r]);
+    }
+    *group = g;
+    return AXB_OK;
+}
+axb_status axb_peer_group_destroy(axb_peer_group *group) {
+    delete group;
+    return AXB_OK;
+}
+axb_status axb_reduce_sharded(int32_t op, const axb_tensor *in_shard, int64_t global_count, axb_peer_group *group,
+                              const axb_tensor *out, axb_stream_t stream) {
+    AXB_REQUIRE(group, AXB_ERR_INVALID, "axb_reduce_sharded: null group");
+    AXB_REQUIRE(in_shard && numel(*in_shard) > 0, AXB_ERR_INVALID, "axb_reduce_sharded: every rank must own a non-empty shard");
+    if (group->world == 1)
+        return axb_reduce(op, in_shard, nullptr, 0, 0, out, stream);
+    ++group->seq;
+    if (group->seq == 0) // 0 is the mailbox's initial tag
+        ++group->seq;
+    group->global_count = global_count;
+    pending_peer_group() = group;
+    const axb_status st = axb_reduce(op, in_shard, nullptr, 0, 0, out, stream);
+    pending_peer_group() = nullptr;
+    return st;
 }
 
 } // extern "C"

@@ -17,6 +17,7 @@ struct f16_t {
     uint16_t bits;
 };
 
+constexpr int kMaxPeers = 16;
 struct Params {
     const char *in;
     char *out;
@@ -30,6 +31,11 @@ struct Params {
     int64_t chunk;     // reduced elements per split
     int32_t split;
     int32_t op, in_dtype, out_dtype;
+    // sharded FULL reduction (axb_reduce_sharded): the finish kernel also exchanges the shard's partial with the other
+    // ranks through their mailboxes in peer (NVLink / NVSwitch) memory — see peer exchange in reduce.cu
+    uint64_t *peer_box[kMaxPeers]; // mailbox of every rank (own included), mapped into this process
+    int32_t peer_rank, peer_world; // peer_world <= 1: not sharded
+    uint32_t peer_seq;             // call counter, identical on all ranks; selects the bank and tags every word
 };
 
 __device__ __forceinline__ uint32_t fastdiv32(uint32_t n, uint32_t m, uint32_t s) { return (__umulhi(n, m) + n) >> s; }

@@ -70,3 +70,72 @@ def combine_argreduce(op: str, value: float, local_index: int, shard_offset: int
         if (op == "argmax" and v > best_val) or (op == "argmin" and v < best_val):
             best_val, best_idx = v, i
     return best_idx
+
+
+class PeerGroup:
+    """Mailboxes in peer memory for axb_reduce_sharded (include/axb.h): the per-shard partials of a full reduction are
+    exchanged by the reduction's own finish kernel over NVLink instead of by a collective call. torch.distributed only
+    carries the 64-byte IPC handles once, at construction (`local_boxes` builds a group from mailboxes of this process —
+    used by the single-GPU test of the protocol)."""
+
+    def __init__(self, rank: int, world: int, boxes, opened=(), own=None):
+        import ctypes
+        from . import capi
+        self._capi, self.rank, self.world = capi, rank, world
+        self._opened, self._own = list(opened), own
+        arr = (ctypes.c_void_p * world)(*[ctypes.c_void_p(b) for b in boxes])
+        g = ctypes.c_void_p()
+        capi.check(capi.lib().axb_peer_group_create(rank, world, arr, ctypes.byref(g)))
+        self.handle = g
+
+    @staticmethod
+    def create_mailbox():
+        import ctypes
+        from . import capi
+        box, h = ctypes.c_void_p(), ctypes.create_string_buffer(64)
+        capi.check(capi.lib().axb_peer_mailbox_create(ctypes.byref(box), h))
+        return box.value, h.raw
+
+    @classmethod
+    def from_process_group(cls, device: str) -> "PeerGroup":
+        """One process per GPU: all-gather the IPC handles over the default process group and map every peer's mailbox."""
+        import ctypes
+        import torch
+        from . import capi
+        dist = _dist()
+        rank, world = dist.get_rank(), dist.get_world_size()
+        own, handle = cls.create_mailbox()
+        mine = torch.tensor(list(handle), dtype=torch.uint8, device=device)
+        gathered = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(gathered, mine)
+        boxes, opened = [], []
+        for r in range(world):
+            if r == rank:
+                boxes.append(own)
+                continue
+            p = ctypes.c_void_p()
+            capi.check(capi.lib().axb_peer_mailbox_open(bytes(gathered[r].cpu().tolist()), ctypes.byref(p)))
+            boxes.append(p.value)
+            opened.append(p.value)
+        dist.barrier()
+        return cls(rank, world, boxes, opened, own)
+
+    def reduce(self, op: str, shard, global_count: int, out, stream=None) -> None:
+        """Full `op` over all shards; `out` ({1}, device) receives the combined value on every rank."""
+        import ctypes
+        capi = self._capi
+        capi.check(capi.lib().axb_reduce_sharded(capi.OP[op], ctypes.byref(shard.desc()), int(global_count), self.handle,
+                                                 ctypes.byref(out.desc()), stream))
+
+    def close(self) -> None:
+        import ctypes
+        L = self._capi.lib()
+        if self.handle:
+            L.axb_peer_group_destroy(self.handle)
+            self.handle = None
+        for p in self._opened:
+            L.axb_peer_mailbox_close(ctypes.c_void_p(p))
+        self._opened = []
+        if self._own:
+            L.axb_peer_mailbox_destroy(ctypes.c_void_p(self._own))
+            self._own = None

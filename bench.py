@@ -308,9 +308,12 @@ def main():
 
 def sharded_full_reduction(L, capi, dev, dist, world, local_rank, barrier, max_over_ranks):
     """the one exchange step of the path. Every rank owns a {8192, 32768} fp32 block of rows of a
-    {8192 * world, 32768} tensor, reduces it to one scalar with axb_reduce (full sum, one pass over HBM) and the per-shard
-    scalars are combined with ONE NCCL all-reduce (axiom_b200/shard.py combine_full_reduction). Timed end to end on the
-    device (kernel + collective), max over ranks; checked against the sum of the per-rank partials."""
+    {8192 * world, 32768} tensor. `ms` is axb_reduce_sharded: the shard's full sum AND the combine across ranks in one
+    pass — the reduction's finish kernel exchanges the per-shard partials through mailboxes in peer memory (NVLink stores +
+    polled loads, axiom_b200/shard.py PeerGroup) and every rank ends with the identical total; K calls are enqueued back
+    to back and timed on the device (CUDA events, max over ranks). `nccl_ms` is the same work with the combine done by one
+    NCCL all-reduce of the per-shard scalar (shard.combine_full_reduction), timed by wall clock as before. Both are
+    checked against the sum of the per-rank partials."""
     import torch
     from axiom_b200 import shard
     rows, n = 8192, 32768
@@ -333,13 +336,41 @@ def sharded_full_reduction(L, capi, dev, dist, world, local_rank, barrier, max_o
     for _ in range(k):
         part, total = step()
     torch.cuda.synchronize()
-    ms = max_over_ranks((time.perf_counter() - t0) / k * 1e3)
+    nccl_ms = max_over_ranks((time.perf_counter() - t0) / k * 1e3)
     parts = [torch.zeros(1, dtype=torch.float32, device=devname) for _ in range(world)]
     dist.all_gather(parts, torch.from_numpy(part.copy()).to(devname))
     expect = float(sum(p.double().item() for p in parts))
     ok = abs(float(total[0]) - expect) <= 1e-6 * max(1.0, abs(expect)) * world
+
+    # fused: partial reduce + cross-GPU combine inside the finish kernel
+    group = shard.PeerGroup.from_process_group(devname)
+    fused = dev.DeviceArray.empty((1,), capi.F32)
+    for _ in range(3):
+        group.reduce("sum", x, rows * n * world, fused)
+    dev.synchronize()
+    e0, e1 = ctypes.c_void_p(), ctypes.c_void_p()
+    capi.check(L.axb_event_create(ctypes.byref(e0)))
+    capi.check(L.axb_event_create(ctypes.byref(e1)))
+    barrier()
+    capi.check(L.axb_event_record(e0, None))
+    for _ in range(k):
+        group.reduce("sum", x, rows * n * world, fused)
+    capi.check(L.axb_event_record(e1, None))
+    capi.check(L.axb_event_sync(e1))
+    msf = ctypes.c_float()
+    capi.check(L.axb_event_elapsed_ms(e0, e1, ctypes.byref(msf)))
+    ms = max_over_ranks(msf.value / k)
+    got = float(fused.numpy()[0])
+    ok_fused = abs(got - expect) <= 1e-6 * max(1.0, abs(expect)) * world
+    allv = [torch.zeros(1, dtype=torch.float32, device=devname) for _ in range(world)]
+    dist.all_gather(allv, torch.tensor([got], dtype=torch.float32, device=devname))
+    identical = len({float(v.item()) for v in allv}) == 1
+    barrier()
+    group.close()
     return {"ms": ms, "GBps_total": world * rows * n * 4 / ms / 1e6, "shards": world, "per_gpu_shape": [rows, n],
-            "collective": "one NCCL all-reduce of the per-shard scalar", "matches_sum_of_partials": bool(ok)}
+            "collective": "none: per-shard partials exchanged by the finish kernel through peer-memory mailboxes (axb_reduce_sharded)",
+            "matches_sum_of_partials": bool(ok_fused), "identical_on_all_ranks": bool(identical),
+            "nccl_ms": nccl_ms, "nccl_GBps_total": world * rows * n * 4 / nccl_ms / 1e6, "nccl_matches_sum_of_partials": bool(ok)}
 
 
 def sharded_whisper(dist, world, local_rank, barrier, max_over_ranks, per_gpu_batch=8):

@@ -236,6 +236,26 @@ axb_status axb_reduce(int32_t op, const axb_tensor *in, const int32_t *axes, int
  * all-NaN -> 0 (cpu_operations.cpp:2211-2228). */
 axb_status axb_argreduce(int32_t op, const axb_tensor *in, int axis, int keep_dims, const axb_tensor *out,
                          axb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Sharded FULL reductions (the one exchange step of the path). Every rank (one process per GPU) owns a
+ * shard of the tensor; axb_reduce_sharded reduces the shard and combines the per-rank partials INSIDE the reduction's
+ * finish kernel through mailboxes in peer memory (NVLink / NVSwitch stores + polled loads, rank-ordered combine, so
+ * every rank gets the identical value) — no collective-library call and no host round trip. sum / mean / max / min of
+ * f32 / bf16 / f16 shards; `global_count` = element count over all shards (the divisor of Mean). All ranks must issue
+ * the same sequence of sharded reductions. A mailbox is 256 bytes of device memory; its IPC handle is exchanged by the
+ * host plumbing (axiom_b200/shard.py over torch.distributed). world == 1 degenerates to axb_reduce.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct axb_peer_group axb_peer_group;
+axb_status axb_peer_mailbox_create(void **mailbox, unsigned char ipc_handle[64]);
+axb_status axb_peer_mailbox_open(const unsigned char ipc_handle[64], void **peer_mailbox);
+axb_status axb_peer_mailbox_close(void *peer_mailbox);
+axb_status axb_peer_mailbox_destroy(void *mailbox);
+axb_status axb_peer_group_create(int rank, int world, void *const *mailboxes /* world pointers, [rank] = own */,
+                                 axb_peer_group **group);
+axb_status axb_peer_group_destroy(axb_peer_group *group);
+axb_status axb_reduce_sharded(int32_t op, const axb_tensor *in_shard, int64_t global_count, axb_peer_group *group,
+                              const axb_tensor *out, axb_stream_t stream);
 /* softmax / log_softmax along `axis` (any axis; fp32/bf16/fp16/f64; half via fp32 round trip). */
 axb_status axb_softmax(const axb_tensor *in, int axis, int is_log, const axb_tensor *out, axb_stream_t stream);
 /* y = (x-mean)/sqrt(var+eps)*w + b over `axis` (biased variance). weight/bias may be NULL. */

@@ -479,3 +479,66 @@ def test_argreduce_long_rows_with_heavy_ties(gpu, op):
         assert np.array_equal(gb, eb), (op, shape, "bf16")
         xi = np.nan_to_num(x).astype(np.int32)
         assert np.array_equal(dev.argreduce(op, dev.DeviceArray.from_numpy(xi), 1).numpy(), eb), (op, shape, "i32")
+
+
+# ---- sharded full reduction: peer-mailbox exchange fused into the finish kernel (axb_reduce_sharded) ---------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("world", [2, 4])
+@pytest.mark.parametrize("op", ["sum", "mean", "max", "min"])
+def test_sharded_full_reduction_peer_mailboxes_single_gpu(gpu, op, world):
+    """The protocol of axb_reduce_sharded on ONE GPU: `world` ranks = `world` mailboxes and streams of this process. Every
+    rank's finish kernel stores its partial into all mailboxes and polls its own; all ranks must report the SAME value,
+    equal to the rank-ordered combine of the per-shard results, over repeated calls (bank alternation, counter tags)."""
+    import ctypes
+    from axiom_b200 import shard
+    rt = ctypes.CDLL("libcudart.so.12")
+    streams = []
+    for _ in range(world):
+        s = ctypes.c_void_p()
+        assert rt.cudaStreamCreateWithFlags(ctypes.byref(s), 1) == 0
+        streams.append(s)
+    boxes = [shard.PeerGroup.create_mailbox()[0] for _ in range(world)]
+    groups = [shard.PeerGroup(r, world, boxes) for r in range(world)]
+    rng = np.random.default_rng(5)
+    sizes = [(257, 1031), (64, 4096), (3, 70001), (1, 17)][:world]
+    dev.synchronize()
+    for call in range(5):
+        shards = [rng.standard_normal(sz).astype(np.float32) + np.float32(r) for r, sz in enumerate(sizes)]
+        total = sum(x.size for x in shards)
+        xs = [dev.DeviceArray.from_numpy(x) for x in shards]
+        outs = [dev.DeviceArray.empty((1,), capi.F32) for _ in range(world)]
+        if call == 0:
+            # one process plays all ranks here, so nothing on the host may wait for the device between the enqueues: warm
+            # each stream's allocator pool (a first-time workspace allocation is a device-synchronising cudaMalloc, which
+            # would wait for rank 0's polling kernel — a coupling separate processes do not have)
+            ax = (ctypes.c_int32 * 2)(0, 1)
+            for r in range(world):
+                capi.check(capi.lib().axb_reduce(capi.OP["sum"], ctypes.byref(xs[r].desc()), ax, 2, 0, ctypes.byref(outs[r].desc()), streams[r]))
+            for s in streams:
+                assert rt.cudaStreamSynchronize(s) == 0
+        dev.synchronize()
+        for r in range(world):  # every "rank" enqueues on its own stream; the finish kernels meet on the device
+            groups[r].reduce(op, xs[r], total, outs[r], streams[r])
+        for s in streams:
+            assert rt.cudaStreamSynchronize(s) == 0
+        got = [float(o.numpy()[0]) for o in outs]
+        assert len(set(got)) == 1, (op, call, got)  # bit-identical on every rank
+        parts = [float(dev.reduce({"mean": "sum"}.get(op, op), x, [0, 1]).numpy()[0]) for x in xs]
+        if op in ("sum", "mean"):
+            acc = np.float32(parts[0])
+            for v in parts[1:]:
+                acc = np.float32(acc + np.float32(v))
+            exp = float(acc / np.float32(total)) if op == "mean" else float(acc)
+            assert abs(got[0] - exp) <= 1e-6 * max(1.0, abs(exp)), (op, call, got[0], exp)
+            ref = float(np.concatenate([x.ravel() for x in shards]).astype(np.float64).sum()) / (total if op == "mean" else 1)
+            assert abs(got[0] - ref) <= 1e-5 * sum(float(np.abs(x).sum()) for x in shards) / (total if op == "mean" else 1)
+        else:
+            assert got[0] == (max(parts) if op == "max" else min(parts))
+    for g in groups:
+        g._own = None
+        g.close()
+    L = capi.lib()
+    for b in boxes:
+        capi.check(L.axb_peer_mailbox_destroy(ctypes.c_void_p(b)))
+    for s in streams:
+        rt.cudaStreamDestroy(s)
