@@ -98,26 +98,47 @@ class PeerGroup:
 
     @classmethod
     def from_process_group(cls, device: str) -> "PeerGroup":
-        """One process per GPU: all-gather the IPC handles over the default process group and map every peer's mailbox."""
+        """One process per GPU: all-gather the IPC handles over the default process group and map every peer's mailbox.
+        A failure on any rank (no peer access, IPC disabled) is agreed on collectively, so either every rank gets a group
+        or every rank raises — nobody is left waiting in a collective."""
         import ctypes
         import torch
         from . import capi
         dist = _dist()
         rank, world = dist.get_rank(), dist.get_world_size()
-        own, handle = cls.create_mailbox()
-        mine = torch.tensor(list(handle), dtype=torch.uint8, device=device)
+        own, handle, err = None, bytes(64), ""
+        try:
+            own, handle = cls.create_mailbox()
+        except Exception as ex:  # noqa: BLE001 — reported after the collective below
+            err = repr(ex)
+        mine = torch.tensor(list(handle) + [1 if own else 0], dtype=torch.uint8, device=device)
         gathered = [torch.empty_like(mine) for _ in range(world)]
         dist.all_gather(gathered, mine)
+        rows = [g.cpu().tolist() for g in gathered]
         boxes, opened = [], []
-        for r in range(world):
-            if r == rank:
-                boxes.append(own)
-                continue
-            p = ctypes.c_void_p()
-            capi.check(capi.lib().axb_peer_mailbox_open(bytes(gathered[r].cpu().tolist()), ctypes.byref(p)))
-            boxes.append(p.value)
-            opened.append(p.value)
-        dist.barrier()
+        if all(r[64] == 1 for r in rows):
+            try:
+                for r in range(world):
+                    if r == rank:
+                        boxes.append(own)
+                        continue
+                    p = ctypes.c_void_p()
+                    capi.check(capi.lib().axb_peer_mailbox_open(bytes(rows[r][:64]), ctypes.byref(p)))
+                    boxes.append(p.value)
+                    opened.append(p.value)
+            except Exception as ex:  # noqa: BLE001
+                err = repr(ex)
+        else:
+            err = err or "a peer could not create its mailbox"
+        flag = torch.tensor([0 if err else 1], dtype=torch.int32, device=device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0:
+            L = capi.lib()
+            for p in opened:
+                L.axb_peer_mailbox_close(ctypes.c_void_p(p))
+            if own:
+                L.axb_peer_mailbox_destroy(ctypes.c_void_p(own))
+            raise RuntimeError("peer mailboxes unavailable: " + (err or "failure on another rank"))
         return cls(rank, world, boxes, opened, own)
 
     def reduce(self, op: str, shard, global_count: int, out, stream=None) -> None:

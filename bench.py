@@ -342,8 +342,14 @@ def sharded_full_reduction(L, capi, dev, dist, world, local_rank, barrier, max_o
     expect = float(sum(p.double().item() for p in parts))
     ok = abs(float(total[0]) - expect) <= 1e-6 * max(1.0, abs(expect)) * world
 
+    nccl = {"nccl_ms": nccl_ms, "nccl_GBps_total": world * rows * n * 4 / nccl_ms / 1e6, "nccl_matches_sum_of_partials": bool(ok)}
     # fused: partial reduce + cross-GPU combine inside the finish kernel
-    group = shard.PeerGroup.from_process_group(devname)
+    try:
+        group = shard.PeerGroup.from_process_group(devname)  # raises on ALL ranks or on none
+    except RuntimeError as ex:
+        return {"ms": nccl_ms, "GBps_total": nccl["nccl_GBps_total"], "shards": world, "per_gpu_shape": [rows, n],
+                "collective": "one NCCL all-reduce of the per-shard scalar (peer mailboxes unavailable: %s)" % ex,
+                "matches_sum_of_partials": bool(ok), **nccl}
     fused = dev.DeviceArray.empty((1,), capi.F32)
     for _ in range(3):
         group.reduce("sum", x, rows * n * world, fused)
@@ -369,8 +375,7 @@ def sharded_full_reduction(L, capi, dev, dist, world, local_rank, barrier, max_o
     group.close()
     return {"ms": ms, "GBps_total": world * rows * n * 4 / ms / 1e6, "shards": world, "per_gpu_shape": [rows, n],
             "collective": "none: per-shard partials exchanged by the finish kernel through peer-memory mailboxes (axb_reduce_sharded)",
-            "matches_sum_of_partials": bool(ok_fused), "identical_on_all_ranks": bool(identical),
-            "nccl_ms": nccl_ms, "nccl_GBps_total": world * rows * n * 4 / nccl_ms / 1e6, "nccl_matches_sum_of_partials": bool(ok)}
+            "matches_sum_of_partials": bool(ok_fused), "identical_on_all_ranks": bool(identical), **nccl}
 
 
 def sharded_whisper(dist, world, local_rank, barrier, max_over_ranks, per_gpu_batch=8):

@@ -80,3 +80,39 @@ def test_full_reduction_combine_world2_gloo():
         assert np.allclose(r["mean"], clean.mean(), rtol=1e-5, atol=1e-7)
         assert r["any"][0] == 1.0 and r["all"][0] == 1.0
         assert r["argmax"] == 5 * 50 + 7  # first of the tied maxima, NaN ignored
+
+
+def _peer_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        try:
+            shard.PeerGroup.from_process_group("cpu")
+            q.put((rank, "created"))
+        except RuntimeError as ex:
+            q.put((rank, "raised: " + str(ex)[:80]))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_peer_group_failure_is_agreed_on_by_all_ranks_gloo():
+    """axb_reduce_sharded's mailboxes need a GPU. Without one, PeerGroup.from_process_group must fail on EVERY rank after
+    the same collectives (handle all-gather, status all-reduce) — no rank may raise early and leave the other one waiting.
+    With GPUs (not here) both ranks would report 'created'."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_peer_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = dict(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    kinds = {v.split(":")[0] for v in results.values()}
+    assert len(kinds) == 1, results  # both created or both raised
+    import torch
+    if not torch.cuda.is_available():
+        assert kinds == {"raised"}, results
