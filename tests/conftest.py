@@ -6,6 +6,10 @@ import sys
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+# One test plays several ranks of the peer-mailbox protocol on separate streams of ONE process; streams that share a
+# hardware work queue would serialise a polling kernel ahead of the kernel it is waiting for. 32 queues instead of the
+# default 8 (read when the CUDA context is created, i.e. before any test touches the device).
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
