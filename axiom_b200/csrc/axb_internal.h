@@ -148,4 +148,13 @@ inline FastDiv make_fastdiv(uint32_t d) {
     return f;
 }
 
+// elementwise.cu: chain + full reduction, first pass (one fp32 partial per CTA into a pooled block)
+namespace ew {
+axb_status launch_chain_reduce(const axb_instr *prog, int n_instr, const axb_tensor *inputs, int n_inputs,
+                               const axb_tensor *shape_desc, int reduce_opk, cudaStream_t s, DeviceCtx *ctx, void **partials,
+                               int64_t *n_partials);
+}
+// reduce.cu: divisor used by the NEXT Mean reduction of this thread instead of its own element count (the partials of a
+// fused chain + mean stand for `count` elements); consumed by that call
+int64_t &reduce_count_override();
 } // namespace axb

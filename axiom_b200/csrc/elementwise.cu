@@ -887,15 +887,19 @@ axb_status broadcast_all(const axb_tensor *inputs, int n_inputs, int64_t *oshape
 
 // Full translation unit of one specialised kernel.
 std::string kernel_source(const std::string &loads, const std::string &body, bool wide, int vec, int n_outer, int n_inputs,
-                          int unroll) {
+                          int unroll, int reduce_opk = -1) {
     std::string s = jit::ew_prelude_text();
-    char hdr[160];
-    snprintf(hdr, sizeof hdr, "\nEW_KERNEL_BEGIN(axb_ew, %d, %s, %d, %d, %d)\n", vec, wide ? "uint64_t" : "uint32_t", n_outer,
-             n_inputs, unroll);
+    char hdr[200];
+    if (reduce_opk < 0)
+        snprintf(hdr, sizeof hdr, "\nEW_KERNEL_BEGIN(axb_ew, %d, %s, %d, %d, %d)\n", vec, wide ? "uint64_t" : "uint32_t", n_outer,
+                 n_inputs, unroll);
+    else // chain + full reduction: the body ends in EW_RED, the kernel in a CTA reduce (ew_prelude.cuh)
+        snprintf(hdr, sizeof hdr, "\nEW_RKERNEL_BEGIN(axb_ew_red, %d, %s, %d, %d, %d, %d)\n", vec, wide ? "uint64_t" : "uint32_t",
+                 n_outer, n_inputs, unroll, reduce_opk);
     s += hdr;
     s += "        EW_PRELOAD_BEGIN\n" + loads + "        EW_PRELOAD_END\n";
     s += "        EW_COMPUTE_BEGIN\n" + body + "        EW_COMPUTE_END\n";
-    s += "EW_KERNEL_END\n";
+    s += reduce_opk < 0 ? "EW_KERNEL_END\n" : "EW_RKERNEL_END\n";
     return s;
 }
 
@@ -907,7 +911,7 @@ struct Prepared {
 
 // Validates, plans the iteration space and generates the kernel text. No device needed.
 axb_status prepare(const axb_instr *prog, int n_instr, const axb_tensor *inputs, int n_inputs, const axb_tensor *out,
-                   Prepared *P, bool *empty) {
+                   Prepared *P, bool *empty, int reduce_opk = -1) {
     AXB_REQUIRE(prog && n_instr > 0 && n_instr <= AXB_MAX_INSTRS, AXB_ERR_INVALID,
                 "axb_elementwise: need 1..%d instructions", AXB_MAX_INSTRS);
     AXB_REQUIRE(n_inputs >= 0 && n_inputs <= AXB_MAX_INPUTS, AXB_ERR_INVALID, "axb_elementwise: at most %d inputs",
@@ -956,9 +960,14 @@ axb_status prepare(const axb_instr *prog, int n_instr, const axb_tensor *inputs,
     AXB_TRY(plan_iteration(inputs, n_inputs, out, oshape, ondim, vec, p));
     int fdt = 0;
     std::string body, loads;
-    AXB_TRY(lower_program(prog, n_instr, inputs, n_inputs, wide, p, &fdt, true, &body, &loads));
+    AXB_TRY(lower_program(prog, n_instr, inputs, n_inputs, wide, p, &fdt, reduce_opk < 0, &body, &loads));
     AXB_REQUIRE(fdt == out->dtype, AXB_ERR_INVALID, "axb_elementwise: last instruction yields dtype %d but out is %d", fdt,
                 out->dtype);
+    if (reduce_opk >= 0) {
+        char line[64];
+        snprintf(line, sizeof line, "            EW_RED(%d)\n", reduce_opk);
+        body += line;
+    }
     // loads in flight: U vectors per thread while the streamed (non-broadcast) operands fit the register budget
     int streamed = 0;
     for (int k = 0; k < n_inputs; ++k)
@@ -968,7 +977,7 @@ axb_status prepare(const axb_instr *prog, int n_instr, const axb_tensor *inputs,
     P->unroll = streamed <= 1 ? 4 : streamed <= 4 ? 2 : 1;
     if (const char *env = getenv("AXB_EW_UNROLL")) // tuning knob (dev): overrides the vectors-per-thread heuristic
         P->unroll = std::max(1, std::min(8, atoi(env)));
-    P->source = kernel_source(loads, body, wide, vec, (int)p.n_outer, n_inputs, P->unroll);
+    P->source = kernel_source(loads, body, wide, vec, (int)p.n_outer, n_inputs, P->unroll, reduce_opk);
     return AXB_OK;
 }
 
@@ -1001,6 +1010,46 @@ axb_status axb_elementwise(const axb_instr *prog, int n_instr, const axb_tensor 
     count_launch();
     return AXB_OK;
 }
+
+} // extern "C"
+
+// Chain + full reduction, first pass (host_api.cpp axb_elementwise_reduce): `shape_desc` describes the chain's (never
+// materialised) fp32 value; one fp32 partial per CTA goes to a pooled workspace returned in *partials / *n_partials.
+namespace axb {
+namespace ew {
+axb_status launch_chain_reduce(const axb_instr *prog, int n_instr, const axb_tensor *inputs, int n_inputs,
+                               const axb_tensor *shape_desc, int reduce_opk, cudaStream_t s, DeviceCtx *ctx, void **partials,
+                               int64_t *n_partials) {
+    Prepared P;
+    bool empty = false;
+    axb_tensor od = *shape_desc;
+    od.base = reinterpret_cast<void *>(uintptr_t(256)); // never dereferenced: the kernel only writes the partials
+    AXB_TRY(prepare(prog, n_instr, inputs, n_inputs, &od, &P, &empty, reduce_opk));
+    AXB_REQUIRE(!empty, AXB_ERR_INVALID, "axb_elementwise_reduce: empty chain");
+    jit::Kernel k;
+    AXB_TRY(jit::get_kernel(P.source, "axb_ew_red", ctx->device, &k));
+    const int threads = 256;
+    int64_t blocks = ((int64_t)P.p.total_vec + (int64_t)threads * P.unroll - 1) / ((int64_t)threads * P.unroll);
+    if (blocks < 1)
+        blocks = 1;
+    void *ws = nullptr;
+    AXB_TRY(axb_alloc((size_t)blocks * sizeof(float), s, &ws));
+    P.p.out.ptr = static_cast<char *>(ws);
+    void *args[] = {&P.p};
+    axb_status st = jit::launch(k, (unsigned)blocks, threads, 0, s, args);
+    if (st != AXB_OK) {
+        axb_free(ws, s);
+        return st;
+    }
+    count_launch();
+    *partials = ws;
+    *n_partials = blocks;
+    return AXB_OK;
+}
+} // namespace ew
+} // namespace axb
+
+extern "C" {
 
 // Compile-only entry (no device needed): makes sure the specialised kernel of this program signature is in
 // the in-tree cubin cache. build() calls it for the BASELINE configs so the named hot path never JITs.

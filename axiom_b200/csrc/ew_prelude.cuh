@@ -722,5 +722,43 @@ __device__ __forceinline__ void ew_run(const Params &p, FL &&preload, FC &&compu
         ew_run<VEC, W, NOUT, NIN, U>(p, preload, compute);                                              \
     }
 
+// ---- chain + FULL reduction in one pass (FusedReductionStep, include/axiom/graph/compiled_graph.hpp:61-66) --------------
+// The last statement of the program is EW_RED instead of EW_STORE: every thread folds the fp32 values of its vectors into
+// one register, the CTA reduces (shuffles + one shared-memory hop) and writes ONE partial to p.out.ptr[blockIdx.x]; the
+// partials are combined by the reduction family's finish pass. The chain's value never reaches HBM.
+// OPK: 0 = sum (also mean), 1 = max, 2 = min — same combine rules as reduce_common.cuh SumOp / MaxOp / MinOp.
+template <int OPK> __device__ __forceinline__ float red_identity() {
+    return OPK == 0 ? 0.0f : OPK == 1 ? -3.402823466e+38f : 3.402823466e+38f;
+}
+template <int OPK> __device__ __forceinline__ float red_combine(float a, float b) {
+    return OPK == 0 ? __fadd_rn(a, b) : OPK == 1 ? ((a < b) ? b : a) : ((b < a) ? b : a);
+}
+#define EW_RED(OPK_)                                                                                    \
+    {                                                                                                   \
+        _Pragma("unroll") for (int i = 0; i < VEC; ++i) if (i < x.valid)                                \
+            racc = red_combine<OPK_>(racc, asF<W>(acc[i]));                                             \
+    }
+#define EW_RKERNEL_BEGIN(NAME, VEC_, WTYPE, NOUT_, NIN_, U_, OPK_)                                      \
+    extern "C" __global__ void __launch_bounds__(256) NAME(const __grid_constant__ axb::ew::Params p) { \
+        using namespace axb::ew;                                                                        \
+        constexpr int VEC = VEC_, NOUT = NOUT_, NIN = NIN_, U = U_, OPK = OPK_;                         \
+        typedef WTYPE W;                                                                                \
+        typedef Ctx<W, VEC, NIN> X;                                                                     \
+        float racc = red_identity<OPK>();
+#define EW_RKERNEL_END                                                                                  \
+        ew_run<VEC, W, NOUT, NIN, U>(p, preload, compute);                                              \
+        __shared__ float red_sm[8];                                                                     \
+        _Pragma("unroll") for (int d = 16; d >= 1; d >>= 1)                                             \
+            racc = red_combine<OPK>(racc, __shfl_xor_sync(0xFFFFFFFFu, racc, d));                       \
+        if ((threadIdx.x & 31) == 0)                                                                    \
+            red_sm[threadIdx.x >> 5] = racc;                                                            \
+        __syncthreads();                                                                                \
+        if (threadIdx.x == 0) {                                                                         \
+            float tot = red_sm[0];                                                                      \
+            _Pragma("unroll") for (int w = 1; w < 8; ++w) tot = red_combine<OPK>(tot, red_sm[w]);       \
+            reinterpret_cast<float *>(const_cast<char *>(p.out.ptr))[blockIdx.x] = tot;                 \
+        }                                                                                               \
+    }
+
 } // namespace ew
 } // namespace axb

@@ -305,8 +305,8 @@ axb_status axb_matmul_host(const axb_tensor *host_a, const axb_tensor *host_b, i
 }
 
 // FusedReductionStep (include/axiom/graph/compiled_graph.hpp:61-66): elementwise chain + FULL reduction.
-// Round 1: the chain's value is materialised once in a pooled scratch block and reduced by the row kernel (2 launches +
-// finish); folding the reduction into the chain kernel's epilogue is the next step for this entry point.
+// fp32 chains under sum / mean / max / min run in one pass over the operands (below); every other combination
+// materialises the chain's value once in a pooled scratch block and reduces it (2 launches + finish).
 axb_status axb_elementwise_reduce(const axb_instr *prog, int n_instr, const axb_tensor *inputs, int n_inputs,
                                   int32_t reduce_op, const axb_tensor *out, axb_stream_t stream) {
     AXB_REQUIRE(prog && n_instr > 0 && n_inputs > 0 && inputs, AXB_ERR_INVALID, "axb_elementwise_reduce: bad arguments");
@@ -326,9 +326,32 @@ axb_status axb_elementwise_reduce(const axb_instr *prog, int n_instr, const axb_
         nd = ncur;
     }
     cudaStream_t s;
-    AXB_TRY(resolve_stream(stream, &s));
+    DeviceCtx *ctx;
+    AXB_TRY(resolve_stream(stream, &s, &ctx));
     const int32_t vdt = prog[n_instr - 1].dtype;
     axb_tensor tmp = make_contiguous_desc(nullptr, vdt, shape, nd);
+    // One pass: fp32 chains under sum / mean / max / min fold every CTA's values into ONE partial inside the chain kernel
+    // (EW_RED, ew_prelude.cuh) and the reduction family combines the partials — the chain's value never reaches HBM
+    // (operands read once, 4 bytes written per CTA, instead of + one write and one read of the whole intermediate).
+    static const bool two_pass = getenv("AXB_EW_REDUCE_TWO_PASS") != nullptr; // A/B switch
+    bool wide = false;
+    for (int k = 0; k < n_inputs; ++k)
+        wide = wide || is_64bit_dtype(inputs[k].dtype);
+    for (int i = 0; i < n_instr; ++i)
+        wide = wide || is_64bit_dtype(prog[i].dtype);
+    const int opk = (reduce_op == AXB_OP_SUM || reduce_op == AXB_OP_MEAN) ? 0 : reduce_op == AXB_OP_MAX ? 1 : reduce_op == AXB_OP_MIN ? 2 : -1;
+    if (!two_pass && !wide && opk >= 0 && vdt == AXB_F32 && out->dtype == AXB_F32 && numel(*out) == 1 && numel(tmp) > 0) {
+        void *partials = nullptr;
+        int64_t n_partials = 0;
+        AXB_TRY(ew::launch_chain_reduce(prog, n_instr, inputs, n_inputs, &tmp, opk, s, ctx, &partials, &n_partials));
+        const axb_tensor pd = make_contiguous_desc(partials, AXB_F32, &n_partials, 1);
+        if (reduce_op == AXB_OP_MEAN)
+            reduce_count_override() = numel(tmp);
+        const axb_status st = axb_reduce(reduce_op, &pd, nullptr, 0, 0, out, s);
+        reduce_count_override() = 0;
+        axb_free(partials, s);
+        return st;
+    }
     void *buf = nullptr;
     AXB_TRY(axb_alloc((size_t)numel(tmp) * dtype_size(vdt), s, &buf));
     tmp.base = buf;

@@ -532,6 +532,12 @@ struct axb_peer_group {
     uint32_t seq = 0;          // calls issued so far; every rank issues the same sequence of sharded reductions
     int64_t global_count = 0;  // divisor of a sharded Mean (set per call)
 };
+namespace axb {
+int64_t &reduce_count_override() {
+    static thread_local int64_t v = 0;
+    return v;
+}
+} // namespace axb
 static const axb_peer_group *&pending_peer_group() {
     static thread_local const axb_peer_group *g = nullptr;
     return g;
@@ -588,6 +594,10 @@ axb_status axb_reduce(int32_t op, const axb_tensor *in, const int32_t *axes, int
                 (long long)numel(*out), (long long)p.n_out);
     (void)keep_dims;
     p.count = p.n_red;
+    if (int64_t &ov = axb::reduce_count_override(); ov > 0) {
+        p.count = ov;
+        ov = 0;
+    }
     if (const axb_peer_group *g = pending_peer_group()) { // set by axb_reduce_sharded for exactly this call
         pending_peer_group() = nullptr;
         AXB_REQUIRE(p.n_out == 1 && (op == AXB_OP_SUM || op == AXB_OP_MEAN || op == AXB_OP_MAX || op == AXB_OP_MIN) &&

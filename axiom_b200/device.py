@@ -337,3 +337,12 @@ def interpolate(x: DeviceArray, size: Sequence[int], mode: str = "nearest", alig
     m = {"nearest": 0, "linear": 1, "bilinear": 1, "bicubic": 2}[mode]
     check(lib().axb_interpolate(ctypes.byref(x.desc()), m, int(align_corners), ctypes.byref(out.desc()), None))
     return out
+
+
+def elementwise_reduce(prog: List[capi.AxbInstr], inputs: Sequence[DeviceArray], op: str) -> DeviceArray:
+    """FusedReductionStep: the chain's value under a FULL reduction (axb_elementwise_reduce); result shape {1}."""
+    P = (capi.AxbInstr * len(prog))(*prog)
+    I = (capi.AxbTensor * len(inputs))(*[t.desc() for t in inputs])
+    out = DeviceArray.empty((1,), prog[-1].dtype)
+    check(lib().axb_elementwise_reduce(P, len(prog), I, len(inputs), capi.OP[op], ctypes.byref(out.desc()), None))
+    return out

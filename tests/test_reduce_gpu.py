@@ -567,3 +567,35 @@ def test_sharded_full_reduction_peer_mailboxes_single_gpu(gpu, op, world):
     L = capi.lib()
     for b in boxes:
         capi.check(L.axb_peer_mailbox_destroy(ctypes.c_void_p(b)))
+
+
+# ---- chain + full reduction in ONE pass (FusedReductionStep; EW_RED in ew_prelude.cuh) -----------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("op", ["sum", "mean", "max", "min"])
+@pytest.mark.parametrize("shape", [(257, 1031), (1, 5), (64, 4096), (3, 70001)])
+def test_fused_chain_full_reduction_one_pass(gpu, op, shape):
+    """((a + b) * c).relu() under a full reduction: the chain kernel folds its values into one partial per CTA (the chain's
+    value is never written), the reduction family combines the partials. a is a {rows, 1} column (broadcast), sizes are
+    ragged (vector tails). max / min are exact against the op-by-op chain; sum / mean meet the 1e-5 reduction contract."""
+    rng = np.random.default_rng(9)
+    a = rng.standard_normal((shape[0], 1)).astype(np.float32)
+    b = rng.standard_normal(shape).astype(np.float32)
+    c = rng.standard_normal(shape).astype(np.float32)
+    F, V = capi.F32, capi.SRC_VALUE
+    prog = [capi.make_instr(capi.OP["add"], F, 0, 1), capi.make_instr(capi.OP["mul"], F, V(0), 2),
+            capi.make_instr(capi.OP["relu"], F, V(1))]
+    ins = [dev.DeviceArray.from_numpy(t) for t in (a, b, c)]
+    n0 = dev.launch_count()
+    got = float(dev.elementwise_reduce(prog, ins, op).numpy()[0])
+    assert dev.launch_count() - n0 <= 3  # chain+partials, (split) reduce, finish — no materialising launch
+    chain = np.maximum((a + b) * c, np.float32(0)).astype(np.float32)  # IEEE add / mul / relu: exact op by op
+    if op == "max":
+        assert got == float(chain.max())
+    elif op == "min":
+        assert got == float(chain.min())
+    else:
+        ref = float(chain.astype(np.float64).sum())
+        tol = 1e-5 * float(np.abs(chain).astype(np.float64).sum()) + 1e-30
+        if op == "mean":
+            ref, tol = ref / chain.size, tol / chain.size
+        assert abs(got - ref) <= tol, (op, shape, got, ref)
