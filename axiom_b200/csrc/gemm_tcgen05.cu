@@ -60,6 +60,7 @@ struct TcParams {
     int32_t split, kbp;
     int64_t Kp;
     int32_t bn; // tile width in N (64 / 128 / 256)
+    int32_t group_m; // CTA-pair kernel: tile rows per band (see pair_tile_coords)
 };
 
 // piece (0 = hi, 1 = mid, 2 = lo) of A and B for combination c, smallest products first
@@ -607,11 +608,11 @@ __device__ __forceinline__ void tc_mma_pair(uint32_t tmem_d, uint64_t adesc, uin
 // 8 x 9 tiles (A: 2048 rows, B: 2304 columns) instead of 2.3 full tile rows — operands larger than L2 (8192^3: B alone
 // is 128 MiB) are then re-read from HBM once per band instead of once per 2.3 tile rows.
 constexpr int GROUP_M = 8;
-__device__ __forceinline__ void pair_tile_coords(int r, int tiles_m, int tiles_n, int &tm, int &tn) {
-    const int band = r / (GROUP_M * tiles_n);
-    const int first_m = band * GROUP_M;
-    const int rows = min(GROUP_M, tiles_m - first_m);
-    const int in_band = r - band * GROUP_M * tiles_n;
+__device__ __forceinline__ void pair_tile_coords(int r, int tiles_m, int tiles_n, int group_m, int &tm, int &tn) {
+    const int band = r / (group_m * tiles_n);
+    const int first_m = band * group_m;
+    const int rows = min(group_m, tiles_m - first_m);
+    const int in_band = r - band * group_m * tiles_n;
     tm = first_m + in_band % rows;
     tn = in_band / rows;
 }
@@ -666,7 +667,7 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
                 const int64_t b = t / tiles_per_batch;
                 const int r = (int)(t - b * tiles_per_batch);
                 int tm, tn;
-                pair_tile_coords(r, p.tiles_m, p.tiles_n, tm, tn);
+                pair_tile_coords(r, p.tiles_m, p.tiles_n, p.group_m, tm, tn);
                 const int m0 = tm * 256 + (int)rank * 128, n0 = tn * 256 + (int)rank * 128;
                 const int ba = (int)b * p.a_bmult, bb = (int)b * p.b_bmult;
                 for (int kb = 0; kb < num_kb; ++kb) {
@@ -736,7 +737,7 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
             const int64_t b = t / tiles_per_batch;
             const int r = (int)(t - b * tiles_per_batch);
             int tm, tn;
-            pair_tile_coords(r, p.tiles_m, p.tiles_n, tm, tn);
+            pair_tile_coords(r, p.tiles_m, p.tiles_n, p.group_m, tm, tn);
             const int m0 = tm * 256 + (int)rank * 128, n0 = tn * 256;
             mbar_wait(tfull_bar(acc), acc_phase);
             tc_fence_after();
@@ -1164,6 +1165,8 @@ axb_status try_tcgen05(const Desc &d, int adt, int bdt, int cdt, DeviceCtx *ctx,
     p.bias = d.bias; p.bias_rs = d.bias_rs; p.bias_cs = d.bias_cs; p.bias_bs = bias_mult ? bias_bs : 0;
     p.bias_dtype = d.bias_dtype; p.act = d.act; p.out_dtype = cdt;
     p.a_bmult = a_mult; p.b_bmult = b_mult;
+    static const int group_m_env = getenv("AXB_GEMM_GROUP_M") ? std::max(1, atoi(getenv("AXB_GEMM_GROUP_M"))) : GROUP_M; // tuning knob
+    p.group_m = group_m_env;
     // instruction descriptor (cute/arch/mma_sm100_desc.hpp InstrDescriptor): c_format F32 = 1 @4, a/b format (F16 = 0,
     // BF16 = 1) @7/@10, a/b major (MN = 1) @15/@16, N>>3 @17, M>>4 @24
     const uint32_t fmt = adt == AXB_BF16 ? 1u : 0u;
