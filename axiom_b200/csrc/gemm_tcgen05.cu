@@ -974,11 +974,19 @@ axb_status try_split_f32(const Desc &d, DeviceCtx *ctx, cudaStream_t s, bool *do
     if (!api)
         return AXB_ERR_CUDA;
     void *wa = nullptr, *wb = nullptr;
+    // x.matmul(x.T()) (the README chain): B viewed as [N][K] is the very same strided matrix as A — one split serves both
+    bool same_operand = !pre.ptr && d.a == d.b && d.M == d.N && d.a_rs == d.b_cs && d.a_cs == d.b_rs && a_b == b_b;
+    for (int i = 0; i < d.nb && same_operand; ++i)
+        same_operand = d.a_bs[i] == d.b_bs[i];
     if (pre.ptr)
         wa = const_cast<uint16_t *>(pre.ptr);
     else
         AXB_TRY(axb_alloc(a_bytes, s, &wa));
-    axb_status st = axb_alloc(b_bytes, s, &wb);
+    axb_status st = AXB_OK;
+    if (same_operand)
+        wb = wa;
+    else
+        st = axb_alloc(b_bytes, s, &wb);
     if (st != AXB_OK) {
         if (!pre.ptr)
             axb_free(wa, s);
@@ -987,12 +995,13 @@ axb_status try_split_f32(const Desc &d, DeviceCtx *ctx, cudaStream_t s, bool *do
     auto cleanup = [&]() {
         if (!pre.ptr)
             axb_free(wa, s);
-        axb_free(wb, s);
+        if (!same_operand)
+            axb_free(wb, s);
     };
     // A is [M][K] with strides (a_rs, a_cs); B is used as [N][K] with strides (b_cs, b_rs)
     if (!pre.ptr)
         st = run_split(d, d.a, d.M, d.a_rs, d.a_cs, d.a_bs, a_b, Kp, static_cast<uint16_t *>(wa), s);
-    if (st == AXB_OK)
+    if (st == AXB_OK && !same_operand)
         st = run_split(d, d.b, d.N, d.b_cs, d.b_rs, d.b_bs, b_b, Kp, static_cast<uint16_t *>(wb), s);
     // grouped stages need BN <= 128; they also carry more flops per loaded byte (131 vs 87 flop/B for the streamed 256-wide
     // tile), so the split path prefers 128-wide tiles whenever N > 64

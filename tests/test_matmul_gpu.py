@@ -89,7 +89,10 @@ def test_batched_broadcast_random(gpu):
 def test_readme_chain_1024(gpu):
     """BASELINE config 1: x.matmul(x.T()).softmax(-1).sum({1}) on fp32 {1024,1024}; every row sums to 1."""
     x = dev.randn((1024, 1024), 1234)
+    n0 = dev.launch_count()
     s = dev.matmul(x, x.T())
+    # x.T() viewed as [N][K] is x itself: ONE split pass serves both operands of the fp32 tensor-core GEMM
+    assert capi.lib().axb_matmul_last_path() == 3 and dev.launch_count() - n0 == 2
     p = dev.softmax(s, -1)
     r = dev.reduce("sum", p, [1]).numpy()
     assert r.shape == (1024,) and np.allclose(r, 1.0, atol=1e-4)
