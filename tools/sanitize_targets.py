@@ -25,5 +25,10 @@ xs = f(2, 4, 9, 10); dev.conv2d(xs, f(8, 2, 3, 2), f(8), stride=(2, 1), padding=
 dev.conv_transpose(f(2, 4, 5, 6), f(4, 3, 3, 2), f(6), stride=(2, 3), padding=(1, 0), output_padding=(1, 2), groups=2)
 dev.conv_transpose(f(3, 4, 11), f(4, 2, 5), None, stride=3, padding=2, output_padding=1, dilation=2, groups=2)
 for m in ("nearest", "bilinear", "bicubic"): dev.interpolate(xs, (7, 13), m, True)
+# fused chain + full reduction (EW_RED: per-thread fold, CTA reduce, one partial per CTA), ragged sizes, broadcast column
+F_, V_ = capi.F32, capi.SRC_VALUE
+pr = [capi.make_instr(capi.OP["add"], F_, 0, 1), capi.make_instr(capi.OP["mul"], F_, V_(0), 2), capi.make_instr(capi.OP["relu"], F_, V_(1))]
+for shp in ((257, 1031), (1, 5), (3, 70001)):
+    for op in ("sum", "mean", "max"): dev.elementwise_reduce(pr, [f(shp[0], 1), f(*shp), f(*shp)], op)
 dev.synchronize()
 print("sanitize targets ok")
