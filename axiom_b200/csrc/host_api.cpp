@@ -352,6 +352,35 @@ axb_status axb_elementwise_reduce(const axb_instr *prog, int n_instr, const axb_
         axb_free(partials, s);
         return st;
     }
+    if (!two_pass && !wide && opk >= 0 && is_half_dtype(vdt) && numel(*out) == 1 && numel(tmp) > 0 &&
+        out->dtype == axb_reduce_result_dtype(reduce_op, vdt)) {
+        // half-type chains: same one-pass kernel (every value is already rounded to the half type, the fold is fp32 as in
+        // the reference's reduction, cpu_operations.cpp:1422-1424), then the reference's result conversion: one rounding to
+        // the half type (Mean: rounded to the half type, then widened to Float32 — graph_executor.cpp:396-403)
+        void *partials = nullptr, *scratch = nullptr;
+        int64_t n_partials = 0, one = 1;
+        AXB_TRY(ew::launch_chain_reduce(prog, n_instr, inputs, n_inputs, &tmp, opk, s, ctx, &partials, &n_partials));
+        axb_status st = axb_alloc(512, s, &scratch);
+        if (st == AXB_OK) {
+            const axb_tensor pd = make_contiguous_desc(partials, AXB_F32, &n_partials, 1);
+            const axb_tensor f32d = make_contiguous_desc(scratch, AXB_F32, &one, 1);
+            const axb_tensor halfd = make_contiguous_desc(static_cast<char *>(scratch) + 256, vdt, &one, 1);
+            if (reduce_op == AXB_OP_MEAN)
+                reduce_count_override() = numel(tmp);
+            st = axb_reduce(reduce_op, &pd, nullptr, 0, 0, &f32d, s);
+            reduce_count_override() = 0;
+            if (st == AXB_OK && out->dtype == vdt)
+                st = axb_cast(&f32d, out, s);
+            else if (st == AXB_OK) {
+                st = axb_cast(&f32d, &halfd, s);
+                if (st == AXB_OK)
+                    st = axb_cast(&halfd, out, s);
+            }
+            axb_free(scratch, s);
+        }
+        axb_free(partials, s);
+        return st;
+    }
     void *buf = nullptr;
     AXB_TRY(axb_alloc((size_t)numel(tmp) * dtype_size(vdt), s, &buf));
     tmp.base = buf;

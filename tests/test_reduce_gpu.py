@@ -599,3 +599,36 @@ def test_fused_chain_full_reduction_one_pass(gpu, op, shape):
         if op == "mean":
             ref, tol = ref / chain.size, tol / chain.size
         assert abs(got - ref) <= tol, (op, shape, got, ref)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("op", ["sum", "mean", "max", "min"])
+@pytest.mark.parametrize("shape", [(257, 1031), (3, 70001)])
+def test_fused_chain_full_reduction_bf16(gpu, op, shape):
+    """bf16 chain (a + b) * c under a full reduction, one pass: the chain values are the reference's (every op rounded to
+    bf16), the fold is fp32, the result is rounded once to bf16 (Mean: rounded to bf16, returned as Float32)."""
+    import ctypes
+    rng = np.random.default_rng(11)
+    a, b, c = (as_bf16(rand_f32(rng, shape, 1.0)) for _ in range(3))
+    BF, V = capi.BF16, capi.SRC_VALUE
+    prog = [capi.make_instr(capi.OP["add"], BF, 0, 1), capi.make_instr(capi.OP["mul"], BF, V(0), 2)]
+    ins = [dev.DeviceArray.from_numpy(t, bf16=True) for t in (a, b, c)]
+    P = (capi.AxbInstr * len(prog))(*prog)
+    I = (capi.AxbTensor * 3)(*[t.desc() for t in ins])
+    out_dt = capi.lib().axb_reduce_result_dtype(capi.OP[op], BF)
+    out = dev.DeviceArray.empty((1,), out_dt)
+    n0 = dev.launch_count()
+    capi.check(capi.lib().axb_elementwise_reduce(P, len(prog), I, 3, capi.OP[op], ctypes.byref(out.desc()), None))
+    assert dev.launch_count() - n0 <= 5
+    v, _ = ao.binary("add", a, ao.BF16, b, ao.BF16)
+    v, _ = ao.binary("mul", v, ao.BF16, c, ao.BF16)
+    chain = ao.bf16_to_f32(v).astype(np.float64)
+    got = out.numpy()
+    gotf = float(ao.bf16_to_f32(got)[0]) if out_dt == capi.BF16 else float(got[0])
+    if op in ("max", "min"):
+        assert gotf == float(chain.max() if op == "max" else chain.min())
+    else:
+        ref = chain.sum() / (chain.size if op == "mean" else 1)
+        # fp32 fold (1e-5 of the absolute sum) + one rounding to bf16 (2^-8 relative)
+        tol = 1e-5 * np.abs(chain).sum() / (chain.size if op == "mean" else 1) + 2.0 ** -8 * abs(ref) + 1e-30
+        assert abs(gotf - ref) <= tol, (op, shape, gotf, ref)
