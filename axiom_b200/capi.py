@@ -57,7 +57,13 @@ class AxbInstr(ctypes.Structure):
 
 class AxbAllocStats(ctypes.Structure):
     _fields_ = [(n, ctypes.c_uint64) for n in
-                ("bytes_in_use", "bytes_cached", "peak_bytes_in_use", "n_cuda_malloc", "n_cache_hits", "n_allocs")]
+                ("bytes_in_use", "bytes_cached", "peak_bytes_in_use", "n_cuda_malloc", "n_cache_hits", "n_allocs",
+                 "n_splits", "n_merges", "n_cross_stream")]
+
+
+class AxbTransferStats(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_uint64) for n in
+                ("h2d_bytes", "h2d_calls", "d2h_bytes", "d2h_calls", "d2d_bytes", "d2d_calls")]
 
 
 class AxbJitStats(ctypes.Structure):
@@ -119,8 +125,11 @@ def lib() -> ctypes.CDLL:
         "axb_free": (i32, [vp, vp]),
         "axb_empty_cache": (i32, []),
         "axb_get_alloc_stats": (i32, [ctypes.POINTER(AxbAllocStats)]),
+        "axb_get_transfer_stats": (i32, [ctypes.POINTER(AxbTransferStats)]),
+        "axb_pool_reserve": (i32, [sz]),
         "axb_host_alloc": (i32, [sz, pvp]),
         "axb_host_free": (i32, [vp]),
+        "axb_host_alloc_numa_node": (i32, []),
         "axb_memcpy_h2d": (i32, [vp, vp, sz, vp]),
         "axb_memcpy_d2h": (i32, [vp, vp, sz, vp, i32]),
         "axb_memcpy_d2d": (i32, [vp, vp, sz, vp]),
@@ -147,6 +156,7 @@ def lib() -> ctypes.CDLL:
         "axb_softmax": (i32, [T, i32, i32, T, vp]),
         "axb_layer_norm": (i32, [T, T, T, i32, f32, T, vp]),
         "axb_rms_norm": (i32, [T, T, i32, f32, T, vp]),
+        "axb_rownorm_last_path": (i32, []),
         "axb_elementwise_reduce": (i32, [I, i32, T, i32, i32, T, vp]),
         "axb_matmul": (i32, [T, T, i32, i32, ctypes.POINTER(AxbMatmulEpilogue), T, vp]),
         "axb_matmul_shape": (i32, [T, T, i32, i32, pi64, pi32]),
@@ -162,6 +172,7 @@ def lib() -> ctypes.CDLL:
         "axb_peer_mailbox_destroy": (i32, [vp]),
         "axb_peer_group_create": (i32, [i32, i32, pvp, pvp]),
         "axb_peer_group_destroy": (i32, [vp]),
+        "axb_peer_group_status": (i32, [vp]),
         "axb_reduce_sharded": (i32, [i32, T, i64, vp, T, vp]),
         "axb_elementwise_host": (i32, [I, i32, T, i32, T]),
         "axb_reduce_host": (i32, [i32, T, pi32, i32, i32, T]),

@@ -6,16 +6,26 @@
 // (src/graph/graph_executor.cpp:254-303, compiled_graph.hpp:121-141).
 //
 // Design (B200, 180 GB HBM3e):
-//  * sizes are rounded to classes (512 B granules below 1 MiB, 2 MiB granules above) so freed blocks
-//    are re-usable; cudaMalloc is only hit on a class miss.
-//  * free(ptr, stream) returns the block to the free list of THAT stream at once — later work on the
-//    same stream is ordered after everything that used the block, so no synchronisation is needed.
-//  * a block is handed to a different stream only through a cudaStreamWaitEvent on an event recorded
-//    at free time (device-side ordering, the host never blocks).
+//  * sizes are rounded to classes (512 B granules below 1 MiB, 2 MiB granules above). Small blocks are cached per exact
+//    class. Large blocks live inside SEGMENTS (one cudaMalloc each): a cached block that is larger than the request is
+//    SPLIT (the remainder stays cached), and a freed block is COALESCED with free neighbours of the same segment that
+//    were freed on the same stream — so a freed 2 GiB block can serve four 512 MiB requests and grow back.
+//  * free(ptr, stream) returns the block to the cache at once, owned by that stream: later work on the same stream is
+//    ordered after everything that used the block, so no synchronisation is needed. A block is handed to a different
+//    stream only through a cudaStreamWaitEvent on the event recorded at free time (device-side ordering, the host
+//    never blocks). The cache is ONE ordered index by (size, address); a lookup walks at most kScan candidates from the
+//    best fit, preferring the caller's stream — no scan of the whole cache.
+//  * every block remembers its DEVICE. A free with stream == NULL (the Storage destructor, called from arbitrary host
+//    threads whose current device may be another GPU) goes to the backend stream of the block's own device, and the
+//    event is recorded with that device current.
+//  * stream capture: while the stream is capturing, freed blocks are parked in a capture list that only later
+//    allocations of the SAME capture reuse; they never return to the general cache, because replays of the captured
+//    graph keep writing to them. Allocations made during capture never wait on events from outside the capture.
 //  * on cudaErrorMemoryAllocation the cache is drained (after a device sync) and the malloc retried.
-//  * one mutex per device; all entry points are thread-safe.
+//  * one mutex per device; all entry points are thread-safe. axb_pool_reserve pre-warms a segment.
 #include <map>
 #include <mutex>
+#include <set>
 #include <unordered_map>
 #include <vector>
 
@@ -27,6 +37,7 @@ namespace {
 constexpr size_t kSmallGranule = 512;
 constexpr size_t kLargeGranule = 2u << 20;
 constexpr size_t kSmallLimit = 1u << 20;
+constexpr int kScan = 32;
 
 size_t round_size(size_t n) {
     if (n < kSmallLimit)
@@ -34,89 +45,263 @@ size_t round_size(size_t n) {
     return (n + kLargeGranule - 1) / kLargeGranule * kLargeGranule;
 }
 
+// free-time event shared by the pieces of a block that was split while cached
+struct Ev {
+    cudaEvent_t e = nullptr;
+    int refs = 0;
+};
+
 struct Block {
     void *ptr = nullptr;
-    size_t size = 0;           // rounded size
-    cudaStream_t stream = nullptr; // stream that owns it while cached
-    cudaEvent_t freed = nullptr;   // recorded on `stream` when it was freed
+    size_t size = 0; // rounded size
+    int device = 0;
+    cudaStream_t stream = nullptr; // allocation stream while live, free stream while cached
+    Ev *freed = nullptr;           // recorded on `stream` when it was freed (nullptr: nothing to wait for)
+    Block *prev = nullptr, *next = nullptr; // neighbours inside the segment (large blocks only)
+    bool cached = false;
+    bool capture = false; // parked by a free during stream capture: never returns to the general cache
 };
+
+struct BySizeAddr {
+    bool operator()(const Block *a, const Block *b) const {
+        return a->size != b->size ? a->size < b->size : a->ptr < b->ptr;
+    }
+};
+
+bool is_capturing(cudaStream_t s) {
+    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(s, &st) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return st != cudaStreamCaptureStatusNone;
+}
 
 struct DevicePool {
     std::mutex mu;
-    // live allocations: ptr -> block
-    std::unordered_map<void *, Block> live;
-    // cached blocks: (stream, size) ordered so lower_bound finds best fit within a stream
-    std::multimap<std::pair<cudaStream_t, size_t>, Block> cached;
+    int device = 0;
+    std::unordered_map<void *, Block *> live;
+    std::set<Block *, BySizeAddr> cached;                         // general cache
+    std::multimap<std::pair<cudaStream_t, size_t>, Block *> park; // freed during capture, per capturing stream
     std::vector<cudaEvent_t> event_pool;
     axb_alloc_stats st{};
 
-    cudaEvent_t get_event() {
-        if (!event_pool.empty()) {
-            cudaEvent_t e = event_pool.back();
-            event_pool.pop_back();
-            return e;
-        }
+    Ev *new_event(cudaStream_t s) {
         cudaEvent_t e = nullptr;
-        cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
-        return e;
-    }
-    void put_event(cudaEvent_t e) {
-        if (e)
+        if (!event_pool.empty()) {
+            e = event_pool.back();
+            event_pool.pop_back();
+        } else if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) {
+            cudaGetLastError();
+            return nullptr;
+        }
+        if (cudaEventRecord(e, s) != cudaSuccess) {
+            cudaGetLastError();
             event_pool.push_back(e);
+            return nullptr;
+        }
+        Ev *ev = new Ev();
+        ev->e = e;
+        ev->refs = 1;
+        return ev;
+    }
+    void release(Ev *&ev) {
+        if (ev && --ev->refs == 0) {
+            event_pool.push_back(ev->e);
+            delete ev;
+        }
+        ev = nullptr;
     }
 
-    // returns true and fills b if a cached block fits
-    bool take_cached(size_t size, cudaStream_t stream, Block *b) {
-        // 1. same stream, best fit (allow up to 25% slack for large blocks, exact class for small ones)
-        auto it = cached.lower_bound({stream, size});
-        if (it != cached.end() && it->first.first == stream) {
-            size_t have = it->first.second;
-            if (have == size || (size >= kSmallLimit && have <= size + size / 4)) {
-                *b = it->second;
-                cached.erase(it);
-                put_event(b->freed);
-                b->freed = nullptr;
-                return true;
-            }
+    // hands a cached block to `stream`; false if the free point cannot be ordered (no event could be recorded)
+    void adopt(Block *b, cudaStream_t stream) {
+        if (b->stream != stream && b->freed) {
+            cudaStreamWaitEvent(stream, b->freed->e, 0);
+            st.n_cross_stream++;
         }
-        // 2. any other stream, exact class: order the new stream after the free point
-        for (auto jt = cached.begin(); jt != cached.end(); ++jt) {
-            if (jt->first.second == size && jt->first.first != stream) {
-                *b = jt->second;
-                cached.erase(jt);
-                if (b->freed) {
-                    cudaStreamWaitEvent(stream, b->freed, 0);
-                    put_event(b->freed);
-                    b->freed = nullptr;
-                }
-                b->stream = stream;
-                return true;
+        release(b->freed);
+        b->stream = stream;
+    }
+
+    Block *take_cached(size_t size, cudaStream_t stream, bool same_stream_only) {
+        Block key;
+        key.size = size;
+        key.ptr = nullptr;
+        auto it = cached.lower_bound(&key);
+        Block *other = nullptr, *pick = nullptr;
+        const bool small = size < kSmallLimit;
+        for (int n = 0; it != cached.end() && n < kScan; ++it, ++n) {
+            Block *b = *it;
+            if (small && b->size != size)
+                break; // small blocks: exact class only (never split)
+            if (!small && b->size < kSmallLimit)
+                continue;
+            if (b->stream == stream) {
+                pick = b;
+                break;
             }
+            // a block freed on another stream is ordered through its free event (none = the free point was synchronised)
+            if (!other && !same_stream_only)
+                other = b;
+            if (other && b->size > other->size)
+                break; // a larger same-stream block is not worth the extra split
         }
-        return false;
+        if (!pick)
+            pick = other;
+        if (!pick)
+            return nullptr;
+        cached.erase(pick);
+        pick->cached = false;
+        st.bytes_cached -= pick->size;
+        // split: keep the tail cached under the stream (and free point) it was freed on
+        if (!small && pick->size >= size + kLargeGranule) {
+            Block *rem = new Block();
+            rem->ptr = static_cast<char *>(pick->ptr) + size;
+            rem->size = pick->size - size;
+            rem->device = pick->device;
+            rem->stream = pick->stream;
+            rem->freed = pick->freed;
+            if (rem->freed)
+                rem->freed->refs++;
+            rem->prev = pick;
+            rem->next = pick->next;
+            if (pick->next)
+                pick->next->prev = rem;
+            pick->next = rem;
+            pick->size = size;
+            rem->cached = true;
+            cached.insert(rem);
+            st.bytes_cached += rem->size;
+            st.n_splits++;
+        }
+        adopt(pick, stream);
+        return pick;
+    }
+
+    Block *take_parked(size_t size, cudaStream_t stream) {
+        auto it = park.lower_bound({stream, size});
+        if (it == park.end() || it->first.first != stream)
+            return nullptr;
+        if (it->first.second != size && (size < kSmallLimit || it->first.second > size + size / 4))
+            return nullptr;
+        Block *b = it->second;
+        park.erase(it);
+        return b;
+    }
+
+    // merges b with a cached neighbour freed on the same stream; `b` is not in the index yet
+    void coalesce(Block *b) {
+        for (int side = 0; side < 2; ++side) {
+            Block *n = side == 0 ? b->next : b->prev;
+            if (!n || !n->cached || n->capture || n->stream != b->stream)
+                continue;
+            cached.erase(n);
+            st.bytes_cached -= n->size;
+            release(n->freed); // b's event is later on the same stream: it covers n's free point
+            if (side == 0) {
+                b->size += n->size;
+                b->next = n->next;
+                if (n->next)
+                    n->next->prev = b;
+            } else {
+                b->ptr = n->ptr;
+                b->size += n->size;
+                b->prev = n->prev;
+                if (n->prev)
+                    n->prev->next = b;
+            }
+            delete n;
+            st.n_merges++;
+        }
     }
 
     void drain_locked() {
         cudaDeviceSynchronize();
-        for (auto &kv : cached) {
-            cudaFree(kv.second.ptr);
-            st.bytes_cached -= kv.second.size;
-            put_event(kv.second.freed);
-        }
+        // everything queued has finished: free points no longer matter, neighbours merge across streams
+        std::vector<Block *> blocks(cached.begin(), cached.end());
         cached.clear();
+        std::set<Block *> dead;
+        for (Block *b : blocks) {
+            if (dead.count(b))
+                continue;
+            release(b->freed);
+            // forward merges on every surviving block cover every mergeable pair, whatever the visiting order
+            while (b->next && b->next->cached && !b->next->capture) {
+                Block *n = b->next;
+                release(n->freed);
+                b->size += n->size;
+                b->next = n->next;
+                if (n->next)
+                    n->next->prev = b;
+                dead.insert(n);
+            }
+        }
+        for (Block *b : blocks) {
+            if (dead.count(b))
+                continue;
+            if (!b->prev && !b->next) { // a whole segment
+                cudaFree(b->ptr);
+                st.bytes_cached -= b->size;
+                dead.insert(b);
+            } else {
+                cached.insert(b); // part of a segment that still has live blocks
+            }
+        }
+        for (Block *b : dead)
+            delete b;
     }
 };
 
 std::mutex g_pools_mu;
 std::vector<DevicePool *> g_pools;
+// which pool owns a live pointer (a free may come from a thread bound to another device)
+std::mutex g_owner_mu;
+std::unordered_map<void *, int> g_owner;
 
 DevicePool *pool_for(int dev) {
     std::lock_guard<std::mutex> lk(g_pools_mu);
     if ((int)g_pools.size() <= dev)
         g_pools.resize(dev + 1, nullptr);
-    if (!g_pools[dev])
+    if (!g_pools[dev]) {
         g_pools[dev] = new DevicePool();
+        g_pools[dev]->device = dev;
+    }
     return g_pools[dev];
+}
+
+struct DeviceGuard { // makes `dev` current for the scope (events must be recorded with their device current)
+    int prev = -1;
+    bool switched = false;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) == cudaSuccess && prev != dev)
+            switched = cudaSetDevice(dev) == cudaSuccess;
+    }
+    ~DeviceGuard() {
+        if (switched)
+            cudaSetDevice(prev);
+    }
+};
+
+axb_status new_segment(DevicePool *p, size_t size, Block **out) {
+    void *d = nullptr;
+    cudaError_t e = cudaMalloc(&d, size);
+    if (e == cudaErrorMemoryAllocation) {
+        cudaGetLastError(); // clear
+        p->drain_locked();
+        e = cudaMalloc(&d, size);
+    }
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(e == cudaErrorMemoryAllocation ? AXB_ERR_OOM : AXB_ERR_CUDA, "axb_alloc: cudaMalloc(%zu) failed: %s", size,
+                    cudaGetErrorString(e));
+    }
+    p->st.n_cuda_malloc++;
+    Block *b = new Block();
+    b->ptr = d;
+    b->size = size;
+    b->device = p->device;
+    *out = b;
+    return AXB_OK;
 }
 
 } // namespace
@@ -135,69 +320,104 @@ axb_status axb_alloc(size_t bytes, axb_stream_t stream, void **ptr) {
     DeviceCtx *ctx;
     AXB_TRY(resolve_stream(stream, &s, &ctx));
     DevicePool *p = pool_for(ctx->device);
-    size_t size = round_size(bytes);
+    const size_t size = round_size(bytes);
+    const bool capturing = is_capturing(s);
     std::lock_guard<std::mutex> lk(p->mu);
-    Block b;
     p->st.n_allocs++;
-    if (p->take_cached(size, s, &b)) {
+    Block *b = capturing ? p->take_parked(size, s) : nullptr;
+    if (!b)
+        b = p->take_cached(size, s, /*same_stream_only=*/capturing);
+    if (b) {
         p->st.n_cache_hits++;
-        p->st.bytes_cached -= b.size;
     } else {
-        void *d = nullptr;
-        cudaError_t e = cudaMalloc(&d, size);
-        if (e == cudaErrorMemoryAllocation) {
-            cudaGetLastError(); // clear
-            p->drain_locked();
-            e = cudaMalloc(&d, size);
-        }
-        if (e != cudaSuccess) {
-            cudaGetLastError();
-            return fail(e == cudaErrorMemoryAllocation ? AXB_ERR_OOM : AXB_ERR_CUDA,
-                        "axb_alloc: cudaMalloc(%zu) failed: %s", size, cudaGetErrorString(e));
-        }
-        p->st.n_cuda_malloc++;
-        b.ptr = d;
-        b.size = size;
-        b.stream = s;
+        AXB_TRY(new_segment(p, size, &b));
     }
-    b.stream = s;
-    p->live[b.ptr] = b;
-    p->st.bytes_in_use += b.size;
+    b->stream = s;
+    p->live[b->ptr] = b;
+    {
+        std::lock_guard<std::mutex> ol(g_owner_mu);
+        g_owner[b->ptr] = p->device;
+    }
+    p->st.bytes_in_use += b->size;
     if (p->st.bytes_in_use > p->st.peak_bytes_in_use)
         p->st.peak_bytes_in_use = p->st.bytes_in_use;
-    *ptr = b.ptr;
+    *ptr = b->ptr;
     return AXB_OK;
 }
 
 axb_status axb_free(void *ptr, axb_stream_t stream) {
     if (!ptr)
         return AXB_OK;
-    cudaStream_t s;
-    DeviceCtx *ctx;
-    AXB_TRY(resolve_stream(stream, &s, &ctx));
-    // the block may belong to another device's pool (multi-GPU host thread): search the owner
-    cudaPointerAttributes attr{};
-    int dev = ctx->device;
-    if (cudaPointerGetAttributes(&attr, ptr) == cudaSuccess && attr.type == cudaMemoryTypeDevice)
-        dev = attr.device;
-    else
-        cudaGetLastError();
+    int dev = -1;
+    {
+        std::lock_guard<std::mutex> ol(g_owner_mu);
+        auto it = g_owner.find(ptr);
+        if (it != g_owner.end()) {
+            dev = it->second;
+            g_owner.erase(it);
+        }
+    }
+    if (dev < 0)
+        return fail(AXB_ERR_INVALID, "axb_free: pointer %p was not allocated by axb_alloc", ptr);
     DevicePool *p = pool_for(dev);
+    // stream == NULL means "the backend stream of the block's OWN device" — the calling thread may be bound to another
+    // GPU or to none (Storage destructors run on arbitrary host threads)
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (!s) {
+        DeviceCtx *octx = ctx_of_device(dev);
+        if (!octx)
+            return fail(AXB_ERR_CUDA, "axb_free: device %d has no context", dev);
+        s = octx->stream;
+    }
+    DeviceGuard guard(dev);
+    const bool capturing = is_capturing(s);
     std::lock_guard<std::mutex> lk(p->mu);
     auto it = p->live.find(ptr);
     if (it == p->live.end())
-        return fail(AXB_ERR_INVALID, "axb_free: pointer %p was not allocated by axb_alloc", ptr);
-    Block b = it->second;
+        return fail(AXB_ERR_INVALID, "axb_free: pointer %p is not live on device %d", ptr, dev);
+    Block *b = it->second;
     p->live.erase(it);
-    p->st.bytes_in_use -= b.size;
-    // If the caller frees on a different stream than it allocated on, the free stream is the one whose
-    // queued work may still touch the block: cache it under that stream.
-    b.stream = s;
-    b.freed = p->get_event();
-    if (b.freed)
-        cudaEventRecord(b.freed, s);
-    p->cached.emplace(std::make_pair(b.stream, b.size), b);
-    p->st.bytes_cached += b.size;
+    p->st.bytes_in_use -= b->size;
+    // If the caller frees on a different stream than it allocated on, the free stream is the one whose queued work may
+    // still touch the block: cache it under that stream.
+    b->stream = s;
+    if (capturing) {
+        b->capture = true;
+        p->park.emplace(std::make_pair(s, b->size), b);
+        return AXB_OK;
+    }
+    if (b->capture) { // allocated from the capture list, freed after the capture ended: stays out of the general cache
+        p->park.emplace(std::make_pair(s, b->size), b);
+        return AXB_OK;
+    }
+    b->freed = p->new_event(s);
+    if (!b->freed) {
+        // no event could be recorded: make the free point explicit on the host instead of risking an unordered reuse
+        cudaStreamSynchronize(s);
+    }
+    if (b->size >= kSmallLimit)
+        p->coalesce(b);
+    b->cached = true;
+    p->cached.insert(b);
+    p->st.bytes_cached += b->size;
+    return AXB_OK;
+}
+
+axb_status axb_pool_reserve(size_t bytes) {
+    cudaStream_t s;
+    DeviceCtx *ctx;
+    AXB_TRY(resolve_stream(nullptr, &s, &ctx));
+    if (bytes < kSmallLimit)
+        return AXB_OK;
+    DevicePool *p = pool_for(ctx->device);
+    const size_t size = round_size(bytes);
+    std::lock_guard<std::mutex> lk(p->mu);
+    Block *b = nullptr;
+    AXB_TRY(new_segment(p, size, &b));
+    b->stream = s;
+    b->cached = true;
+    p->cached.insert(b);
+    p->st.bytes_cached += b->size;
     return AXB_OK;
 }
 

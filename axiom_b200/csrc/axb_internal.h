@@ -48,12 +48,23 @@ struct DeviceCtx {
 };
 // Context of the calling thread's current device (lazily created). nullptr + error set on failure.
 DeviceCtx *current_ctx();
+// Context of device `dev` if it has been created (never creates one, never touches the thread's current device).
+DeviceCtx *ctx_of_device(int dev);
 // Resolve a user stream handle: NULL -> backend stream of the current device.
 axb_status resolve_stream(axb_stream_t s, cudaStream_t *out, DeviceCtx **ctx = nullptr);
 
 // ---- launch accounting -----------------------------------------------------------------------------
 extern std::atomic<uint64_t> g_launches;
 inline void count_launch(uint64_t n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+// ---- host<->device transfer accounting (axb_get_transfer_stats) ------------------------------------
+struct TransferCounters {
+    std::atomic<uint64_t> h2d_bytes{0}, h2d_calls{0}, d2h_bytes{0}, d2h_calls{0}, d2d_bytes{0}, d2d_calls{0};
+};
+extern TransferCounters g_xfer;
+inline void count_h2d(size_t n) { g_xfer.h2d_bytes.fetch_add(n, std::memory_order_relaxed); g_xfer.h2d_calls.fetch_add(1, std::memory_order_relaxed); }
+inline void count_d2h(size_t n) { g_xfer.d2h_bytes.fetch_add(n, std::memory_order_relaxed); g_xfer.d2h_calls.fetch_add(1, std::memory_order_relaxed); }
+inline void count_d2d(size_t n) { g_xfer.d2d_bytes.fetch_add(n, std::memory_order_relaxed); g_xfer.d2d_calls.fetch_add(1, std::memory_order_relaxed); }
 
 #define AXB_CHECK_LAUNCH()                                                                              \
     do {                                                                                                \

@@ -40,7 +40,10 @@ axb_status stage_in(const axb_tensor &h, cudaStream_t s, Staged *out) {
     size_t bytes = (size_t)std::max<int64_t>(hi - lo, 0);
     AXB_TRY(axb_alloc(bytes, s, &out->dev));
     if (bytes)
+    {
         AXB_CUDA(cudaMemcpyAsync(out->dev, tensor_ptr(h) + lo, bytes, cudaMemcpyHostToDevice, s));
+        count_h2d(bytes);
+    }
     out->desc = h;
     out->desc.base = out->dev;
     out->desc.byte_offset = -lo;
@@ -64,6 +67,7 @@ axb_status copy_back_and_release(const axb_tensor &h, Staged &o, std::vector<Sta
         size_t bytes = (size_t)numel(h) * dtype_size(h.dtype);
         if (bytes) {
             cudaError_t e = cudaMemcpyAsync(tensor_ptr(h), o.dev, bytes, cudaMemcpyDeviceToHost, s);
+            count_d2h(bytes);
             if (e != cudaSuccess)
                 st = fail(AXB_ERR_CUDA, "D2H copy failed: %s", cudaGetErrorString(e));
         }
@@ -195,6 +199,7 @@ axb_status pipelined_elementwise(const axb_instr *prog, int n_instr, const axb_t
             cuda_ok(cudaMemcpyAsync(static_cast<char *>(ins[k].dev) + r0 * hin[k].strides[0], tensor_ptr(hin[k]) + r0 * hin[k].strides[0],
                                     (size_t)(hi - lo), cudaMemcpyHostToDevice, ss->in),
                     "H2D");
+            count_h2d((size_t)(hi - lo));
         }
         cudaEvent_t up = nullptr, done = nullptr;
         if (!cuda_ok(new_event(&up), "cudaEventCreate") || !cuda_ok(new_event(&done), "cudaEventCreate"))
@@ -208,10 +213,12 @@ axb_status pipelined_elementwise(const axb_instr *prog, int n_instr, const axb_t
             st = axb_elementwise(prog, n_instr, d.data(), n_in, &od, s);
         cuda_ok(cudaEventRecord(done, s), "cudaEventRecord");
         cuda_ok(cudaStreamWaitEvent(ss->out, done, 0), "cudaStreamWaitEvent");
-        if (st == AXB_OK)
+        if (st == AXB_OK) {
             cuda_ok(cudaMemcpyAsync(tensor_ptr(*hout) + r0 * out_row_bytes, static_cast<char *>(o.dev) + r0 * out_row_bytes,
                                     (size_t)((r1 - r0) * out_row_bytes), cudaMemcpyDeviceToHost, ss->out),
                     "D2H");
+            count_d2h((size_t)((r1 - r0) * out_row_bytes));
+        }
     }
     // the blocks go back to the pool in backend-stream order: that stream first waits for both side streams
     cudaEvent_t in_done = nullptr, out_done = nullptr;

@@ -14,6 +14,7 @@
 #include <cstring>
 #include <fstream>
 #include <map>
+#include <tuple>
 #include <mutex>
 #include <sstream>
 #include <vector>
@@ -160,28 +161,78 @@ void write_file_atomic(const std::string &path, const std::vector<char> &data) {
 }
 
 std::mutex g_mu;
-std::map<std::pair<uint64_t, int>, Kernel> g_kernels; // (source hash, device) -> function
+// Kernel identity = (FNV-1a of the source, a second independent hash, source length): a 64-bit collision alone can no longer
+// alias two programs, neither in memory nor on disk.
+struct SourceId {
+    uint64_t h1, h2, len;
+    bool operator<(const SourceId &o) const { return std::tie(h1, h2, len) < std::tie(o.h1, o.h2, o.len); }
+};
+std::map<std::pair<SourceId, int>, Kernel> g_kernels; // (source id, device) -> function
 Stats g_stats{0, 0, 0};
 
-uint64_t source_hash(const std::string &source) {
-    return fnv1a(source.data(), source.size(), fnv1a(kCacheTag, sizeof kCacheTag));
+SourceId source_id(const std::string &source) {
+    SourceId id;
+    id.h1 = fnv1a(source.data(), source.size(), fnv1a(kCacheTag, sizeof kCacheTag));
+    id.h2 = fnv1a(source.data(), source.size(), 0x9E3779B97F4A7C15ull ^ source.size());
+    id.len = source.size();
+    return id;
 }
-std::string cubin_path(uint64_t h) {
+std::string cache_path(const SourceId &id) {
     char name[64];
-    snprintf(name, sizeof name, "/%016llx.cubin", (unsigned long long)h);
+    snprintf(name, sizeof name, "/%016llx.axbk", (unsigned long long)id.h1);
     return cache_dir() + name;
 }
 
+// Cache file = header + cubin. The header names the source it was compiled from (length + second hash) and the payload
+// (length + hash), so a truncated, corrupt or colliding file is detected, deleted and recompiled instead of being loaded.
+struct CacheHeader {
+    char magic[8]; // "AXBKRN01"
+    uint64_t source_len, source_h2, cubin_len, cubin_hash;
+};
+const char kMagic[8] = {'A', 'X', 'B', 'K', 'R', 'N', '0', '1'};
+
+bool read_cached(const std::string &path, const SourceId &id, std::vector<char> *bin) {
+    std::vector<char> raw;
+    if (!read_file(path, &raw))
+        return false;
+    CacheHeader h;
+    bool ok = raw.size() > sizeof h;
+    if (ok) {
+        memcpy(&h, raw.data(), sizeof h);
+        ok = memcmp(h.magic, kMagic, 8) == 0 && h.source_len == id.len && h.source_h2 == id.h2 &&
+             h.cubin_len == raw.size() - sizeof h && h.cubin_hash == fnv1a(raw.data() + sizeof h, h.cubin_len, 0x1234567ull);
+    }
+    if (!ok) {
+        remove(path.c_str()); // evict: the next line recompiles and rewrites it
+        return false;
+    }
+    bin->assign(raw.begin() + sizeof h, raw.end());
+    return true;
+}
+
+void write_cached(const std::string &path, const SourceId &id, const std::vector<char> &bin) {
+    CacheHeader h;
+    memcpy(h.magic, kMagic, 8);
+    h.source_len = id.len;
+    h.source_h2 = id.h2;
+    h.cubin_len = bin.size();
+    h.cubin_hash = fnv1a(bin.data(), bin.size(), 0x1234567ull);
+    std::vector<char> raw(sizeof h + bin.size());
+    memcpy(raw.data(), &h, sizeof h);
+    memcpy(raw.data() + sizeof h, bin.data(), bin.size());
+    write_file_atomic(path, raw);
+}
+
 // cubin bytes for `source`: disk cache, else NVRTC (+ store)
-axb_status cubin_for(const std::string &source, uint64_t h, std::vector<char> *bin) {
-    const std::string path = cubin_path(h);
-    if (read_file(path, bin)) {
+axb_status cubin_for(const std::string &source, const SourceId &id, std::vector<char> *bin, bool force_compile = false) {
+    const std::string path = cache_path(id);
+    if (!force_compile && read_cached(path, id, bin)) {
         g_stats.disk_hits++;
         return AXB_OK;
     }
     AXB_TRY(compile_cubin(source, bin));
     g_stats.compiles++;
-    write_file_atomic(path, *bin);
+    write_cached(path, id, *bin);
     return AXB_OK;
 }
 
@@ -195,25 +246,30 @@ const std::string &ew_prelude_text() {
 axb_status precompile(const std::string &source) {
     std::lock_guard<std::mutex> lk(g_mu);
     std::vector<char> bin;
-    return cubin_for(source, source_hash(source), &bin);
+    return cubin_for(source, source_id(source), &bin);
 }
 
 axb_status get_kernel(const std::string &source, const char *name, int device, Kernel *out) {
-    const uint64_t h = source_hash(source);
+    const SourceId id = source_id(source);
     std::lock_guard<std::mutex> lk(g_mu);
-    auto it = g_kernels.find({h, device});
+    auto it = g_kernels.find({id, device});
     if (it != g_kernels.end()) {
         g_stats.mem_hits++;
         *out = it->second;
         return AXB_OK;
     }
     std::vector<char> bin;
-    AXB_TRY(cubin_for(source, h, &bin));
+    AXB_TRY(cubin_for(source, id, &bin));
     const drv::Api *d = drv::api();
     if (!d)
         return AXB_ERR_CUDA;
     CUmodule mod;
     CUresult r = d->ModuleLoadData(&mod, bin.data());
+    if (r != CUDA_SUCCESS) {
+        // a cache entry that passes its checksums but does not load (other driver / toolkit): compile afresh, once
+        AXB_TRY(cubin_for(source, id, &bin, /*force_compile=*/true));
+        r = d->ModuleLoadData(&mod, bin.data());
+    }
     if (r != CUDA_SUCCESS)
         return fail(AXB_ERR_CUDA, "cuModuleLoadData failed: %s", drv::err_str(r));
     Kernel k;
@@ -222,7 +278,7 @@ axb_status get_kernel(const std::string &source, const char *name, int device, K
         return fail(AXB_ERR_CUDA, "specialised kernel '%s' not found in module", name);
     if (d->OccupancyMaxActiveBlocksPerMultiprocessor)
         d->OccupancyMaxActiveBlocksPerMultiprocessor(&k.blocks_per_sm, k.fn, 256, 0);
-    g_kernels[{h, device}] = k;
+    g_kernels[{id, device}] = k;
     *out = k;
     return AXB_OK;
 }

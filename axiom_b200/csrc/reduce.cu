@@ -153,12 +153,14 @@ __device__ __forceinline__ uint64_t peer_load(const uint64_t *addr) {
 template <typename Acc, class Op> __device__ __forceinline__ void peer_finish(const Params &p) {
     if constexpr (sizeof(Acc) == 4 && std::is_floating_point<Acc>::value) {
         __shared__ float mine, vals[kMaxPeers];
+        __shared__ int timed_out;
         if (threadIdx.x == 0) {
             const Acc *w = reinterpret_cast<const Acc *>(p.ws);
             Acc a = Op::template identity<Acc>();
             for (int s = 0; s < p.split; ++s)
                 a = Op::combine(a, w[s]);
             mine = a;
+            timed_out = 0;
         }
         __syncthreads();
         const int t = threadIdx.x;
@@ -169,8 +171,14 @@ template <typename Acc, class Op> __device__ __forceinline__ void peer_finish(co
             uint64_t w = peer_load(slot);
             const long long t0 = clock64();
             while ((uint32_t)(w >> 32) != p.peer_seq) {
-                if (clock64() - t0 > 6000000000ll) { // ~3 s: a rank never arrived — poison the result instead of hanging
-                    w = 0x7FC00000ull;
+                // ~20 s (a late rank may still be compiling a kernel): a rank that never arrives must not hang the GPU.
+                // The failure is REPORTED, not hidden in the value: the group's host-mapped error word receives the call
+                // counter (the host turns it into AXB_ERR_CUDA on the next call / status query) and the result is NaN
+                // for every op — a NaN operand alone would be dropped by max / min.
+                if (clock64() - t0 > 40000000000ll) {
+                    timed_out = 1;
+                    if (p.peer_err)
+                        atomicExch(p.peer_err, p.peer_seq);
                     break;
                 }
                 __nanosleep(64);
@@ -183,6 +191,8 @@ template <typename Acc, class Op> __device__ __forceinline__ void peer_finish(co
             Acc tot = vals[0];
             for (int r = 1; r < p.peer_world; ++r)
                 tot = Op::combine(tot, (Acc)vals[r]);
+            if (timed_out)
+                tot = __uint_as_float(0x7FC00000u);
             finalize<Acc, Op>(p, 0, tot);
         }
     }
@@ -531,6 +541,7 @@ struct axb_peer_group {
     uint64_t *box[axb::red::kMaxPeers] = {};
     uint32_t seq = 0;          // calls issued so far; every rank issues the same sequence of sharded reductions
     int64_t global_count = 0;  // divisor of a sharded Mean (set per call)
+    uint32_t *err = nullptr;   // pinned, device-visible: call counter of the first exchange that timed out (0 = none)
 };
 namespace axb {
 int64_t &reduce_count_override() {
@@ -608,6 +619,7 @@ axb_status axb_reduce(int32_t op, const axb_tensor *in, const int32_t *axes, int
         p.peer_rank = g->rank;
         p.peer_world = g->world;
         p.peer_seq = g->seq;
+        p.peer_err = g->err;
         p.count = g->global_count;
     }
     switch (in->dtype) {
@@ -724,10 +736,28 @@ axb_status axb_peer_group_create(int rank, int world, void *const *mailboxes, ax
         }
         g->box[r] = static_cast<uint64_t *>(mailboxes[r]);
     }
+    void *e = nullptr;
+    if (cudaHostAlloc(&e, sizeof(uint32_t), cudaHostAllocPortable | cudaHostAllocMapped) != cudaSuccess) {
+        cudaGetLastError();
+        delete g;
+        return fail(AXB_ERR_CUDA, "axb_peer_group_create: cannot allocate the error word");
+    }
+    g->err = static_cast<uint32_t *>(e);
+    *g->err = 0;
     *group = g;
     return AXB_OK;
 }
+axb_status axb_peer_group_status(const axb_peer_group *group) {
+    AXB_REQUIRE(group, AXB_ERR_INVALID, "axb_peer_group_status: null group");
+    const uint32_t bad = group->err ? *(volatile uint32_t *)group->err : 0;
+    if (bad)
+        return fail(AXB_ERR_CUDA, "axb_reduce_sharded: exchange %u timed out on rank %d (a peer never delivered its partial); "
+                                  "the result of that call is NaN", bad, group->rank);
+    return AXB_OK;
+}
 axb_status axb_peer_group_destroy(axb_peer_group *group) {
+    if (group && group->err)
+        cudaFreeHost(group->err);
     delete group;
     return AXB_OK;
 }
@@ -737,6 +767,20 @@ axb_status axb_reduce_sharded(int32_t op, const axb_tensor *in_shard, int64_t gl
     AXB_REQUIRE(in_shard && numel(*in_shard) > 0, AXB_ERR_INVALID, "axb_reduce_sharded: every rank must own a non-empty shard");
     if (group->world == 1)
         return axb_reduce(op, in_shard, nullptr, 0, 0, out, stream);
+    AXB_TRY(axb_peer_group_status(group)); // an earlier exchange timed out: every later call fails loudly
+    // everything that can be rejected is checked BEFORE the call counter moves: a rank that fails validation must not
+    // leave its sequence one ahead of the others (they would time out on every later call)
+    AXB_TRY(validate_tensor(in_shard, "axb_reduce_sharded(in)"));
+    AXB_TRY(validate_tensor(out, "axb_reduce_sharded(out)"));
+    AXB_REQUIRE((op == AXB_OP_SUM || op == AXB_OP_MEAN || op == AXB_OP_MAX || op == AXB_OP_MIN) &&
+                    (in_shard->dtype == AXB_F32 || in_shard->dtype == AXB_BF16 || in_shard->dtype == AXB_F16),
+                AXB_ERR_UNSUPPORTED, "axb_reduce_sharded: full sum / mean / max / min of f32, bf16 or f16 shards only");
+    AXB_REQUIRE(numel(*out) == 1 && is_contiguous(*out) &&
+                    (out->dtype == in_shard->dtype || out->dtype == axb_reduce_result_dtype(op, in_shard->dtype)),
+                AXB_ERR_SHAPE, "axb_reduce_sharded: out must be one element of the reduction's result dtype");
+    AXB_REQUIRE(in_shard->ndim <= AXB_MAX_DIMS && global_count >= numel(*in_shard), AXB_ERR_INVALID,
+                "axb_reduce_sharded: global_count is smaller than the shard");
+    const uint32_t seq_before = group->seq;
     ++group->seq;
     if (group->seq == 0) // 0 is the mailbox's initial tag
         ++group->seq;
@@ -744,6 +788,8 @@ axb_status axb_reduce_sharded(int32_t op, const axb_tensor *in_shard, int64_t gl
     pending_peer_group() = group;
     const axb_status st = axb_reduce(op, in_shard, nullptr, 0, 0, out, stream);
     pending_peer_group() = nullptr;
+    if (st != AXB_OK)
+        group->seq = seq_before; // nothing was enqueued: the exchange did not happen on this rank
     return st;
 }
 

@@ -36,6 +36,7 @@ struct Params {
     uint64_t *peer_box[kMaxPeers]; // mailbox of every rank (own included), mapped into this process
     int32_t peer_rank, peer_world; // peer_world <= 1: not sharded
     uint32_t peer_seq;             // call counter, identical on all ranks; selects the bank and tags every word
+    uint32_t *peer_err;            // host-mapped error word of the group: a timed-out exchange stores its call counter here
 };
 
 __device__ __forceinline__ uint32_t fastdiv32(uint32_t n, uint32_t m, uint32_t s) { return (__umulhi(n, m) + n) >> s; }

@@ -202,6 +202,11 @@ __global__ void __launch_bounds__(THREADS == 32 ? 256 : THREADS) rownorm_kernel(
 }
 
 
+int &last_path() { // per thread: 0 generic (register-resident / streaming), 1 wide TMA-staged, 2 SM-pair cluster
+    static thread_local int v = -1;
+    return v;
+}
+
 namespace {
 
 // Wide contiguous rows (>= 16 KiB, <= 32 values per lane of a 1024-thread CTA): persistent TMA-staged kernel.
@@ -297,8 +302,11 @@ template <typename In, typename Out, int KIND> axb_status launch_cfg(const RowPa
     const int n = p.n;
     const int64_t max_ctas = (int64_t)ctx->sm_count * 32;
     axb_status wst = AXB_OK;
-    if (try_launch_wide<In, Out, KIND>(p, ctx, s, &wst))
+    if (try_launch_wide<In, Out, KIND>(p, ctx, s, &wst)) {
+        last_path() = 1;
         return wst;
+    }
+    last_path() = 0;
     if (n <= 256) {
         int64_t g = std::min<int64_t>((p.rows + 7) / 8, max_ctas);
         rownorm_kernel<In, Out, 32, 8, KIND, true><<<(unsigned)g, 256, 0, s>>>(p);
@@ -418,8 +426,10 @@ axb_status run(int kind, const axb_tensor *in, const axb_tensor *w, const axb_te
     DeviceCtx *ctx;
     AXB_TRY(resolve_stream(stream, &s, &ctx));
     axb_status cst = AXB_OK;
-    if (try_launch_cluster(kind, p, ctx, s, &cst)) // wide rows with affine parameters: SM-pair cluster kernel
+    if (try_launch_cluster(kind, p, ctx, s, &cst)) { // wide rows with affine parameters: SM-pair cluster kernel
+        last_path() = 2;
         return cst;
+    }
     switch (kind) {
     case K_SOFTMAX: return dispatch<K_SOFTMAX>(p, ctx, s);
     case K_LOG_SOFTMAX: return dispatch<K_LOG_SOFTMAX>(p, ctx, s);
@@ -452,5 +462,7 @@ axb_status axb_rms_norm(const axb_tensor *in, const axb_tensor *weight, int axis
                         axb_stream_t stream) {
     return rown::run(rown::K_RMS_NORM, in, weight, nullptr, axis, eps, out, stream, "axb_rms_norm");
 }
+
+int axb_rownorm_last_path(void) { return axb::rown::last_path(); }
 
 } // extern "C"

@@ -4,6 +4,8 @@
 // host synchronises only when it reads: src/backends/metal/metal_common.hpp:53-123,
 // metal_storage.mm:66-93) and of system::is_metal_available (src/tensor/system.cpp:12-29).
 #include <cstring>
+#include <sys/syscall.h>
+#include <unistd.h>
 #include <mutex>
 #include <vector>
 
@@ -12,6 +14,7 @@
 namespace axb {
 
 std::atomic<uint64_t> g_launches{0};
+TransferCounters g_xfer;
 
 std::string &last_error_ref() {
     thread_local std::string e;
@@ -71,6 +74,11 @@ DeviceCtx *current_ctx() {
         g_ctx[dev] = c;
     }
     return g_ctx[dev];
+}
+
+DeviceCtx *ctx_of_device(int dev) {
+    std::lock_guard<std::mutex> lk(g_ctx_mu);
+    return (dev >= 0 && dev < (int)g_ctx.size()) ? g_ctx[dev] : nullptr;
 }
 
 axb_status resolve_stream(axb_stream_t s, cudaStream_t *out, DeviceCtx **ctx) {
@@ -170,12 +178,63 @@ axb_status axb_event_elapsed_ms(axb_event_t start, axb_event_t end, float *ms) {
     return AXB_OK;
 }
 
+// Pinned staging memory is placed on the NUMA node the current GPU hangs off (sysfs numa_node of its PCI function):
+// cudaHostAlloc faults the pages in while pinning them, so a PREFERRED memory policy around the call decides the node.
+// Eight ranks that all stage through whichever node their Python process happened to start on push every transfer of
+// the remote GPUs across the socket interconnect. Best effort: a container without the syscall, or a single-node host,
+// changes nothing. AXB_HOST_NUMA=0 switches it off (A/B for the e2e ceiling probe).
+static int gpu_numa_node(int dev) {
+    char bus[32] = {0};
+    if (cudaDeviceGetPCIBusId(bus, sizeof bus, dev) != cudaSuccess) {
+        cudaGetLastError();
+        return -1;
+    }
+    for (char *c = bus; *c; ++c)
+        if (*c >= 'A' && *c <= 'F')
+            *c = (char)(*c - 'A' + 'a');
+    char path[96];
+    snprintf(path, sizeof path, "/sys/bus/pci/devices/%s/numa_node", bus);
+    FILE *f = fopen(path, "r");
+    if (!f)
+        return -1;
+    int node = -1;
+    if (fscanf(f, "%d", &node) != 1)
+        node = -1;
+    fclose(f);
+    return node;
+}
+static int &last_host_numa_node() {
+    static thread_local int v = -1;
+    return v;
+}
+int axb_host_alloc_numa_node(void) { return last_host_numa_node(); }
+
 axb_status axb_host_alloc(size_t bytes, void **ptr) {
     AXB_REQUIRE(ptr, AXB_ERR_INVALID, "axb_host_alloc: null out");
     *ptr = nullptr;
     if (bytes == 0)
         return AXB_OK;
-    AXB_CUDA(cudaHostAlloc(ptr, bytes, cudaHostAllocDefault));
+    last_host_numa_node() = -1;
+    bool policy_set = false;
+    static const bool numa_on = [] {
+        const char *e = getenv("AXB_HOST_NUMA");
+        return !(e && e[0] == '0');
+    }();
+    int dev = -1;
+    if (numa_on && cudaGetDevice(&dev) == cudaSuccess) {
+        const int node = gpu_numa_node(dev);
+        if (node >= 0 && node < 64) {
+            unsigned long mask = 1ul << node;
+            if (syscall(SYS_set_mempolicy, 1 /* MPOL_PREFERRED */, &mask, 65ul) == 0) {
+                policy_set = true;
+                last_host_numa_node() = node;
+            }
+        }
+    }
+    const cudaError_t e = cudaHostAlloc(ptr, bytes, cudaHostAllocDefault);
+    if (policy_set)
+        syscall(SYS_set_mempolicy, 0 /* MPOL_DEFAULT */, nullptr, 0ul);
+    AXB_CUDA(e);
     return AXB_OK;
 }
 axb_status axb_host_free(void *ptr) {
@@ -189,13 +248,16 @@ axb_status axb_memcpy_h2d(void *dst, const void *src, size_t bytes, axb_stream_t
     cudaStream_t s;
     AXB_TRY(resolve_stream(stream, &s));
     AXB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, s));
+    count_h2d(bytes);
     return AXB_OK;
 }
 axb_status axb_memcpy_d2h(void *dst, const void *src, size_t bytes, axb_stream_t stream, int sync) {
     cudaStream_t s;
     AXB_TRY(resolve_stream(stream, &s));
-    if (bytes)
+    if (bytes) {
         AXB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, s));
+        count_d2h(bytes);
+    }
     if (sync)
         AXB_CUDA(cudaStreamSynchronize(s));
     return AXB_OK;
@@ -206,6 +268,7 @@ axb_status axb_memcpy_d2d(void *dst, const void *src, size_t bytes, axb_stream_t
     cudaStream_t s;
     AXB_TRY(resolve_stream(stream, &s));
     AXB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, s));
+    count_d2d(bytes);
     return AXB_OK;
 }
 axb_status axb_memset(void *dst, int value, size_t bytes, axb_stream_t stream) {
@@ -214,6 +277,17 @@ axb_status axb_memset(void *dst, int value, size_t bytes, axb_stream_t stream) {
     cudaStream_t s;
     AXB_TRY(resolve_stream(stream, &s));
     AXB_CUDA(cudaMemsetAsync(dst, value, bytes, s));
+    return AXB_OK;
+}
+
+axb_status axb_get_transfer_stats(axb_transfer_stats *out) {
+    AXB_REQUIRE(out, AXB_ERR_INVALID, "axb_get_transfer_stats: null out");
+    out->h2d_bytes = g_xfer.h2d_bytes.load();
+    out->h2d_calls = g_xfer.h2d_calls.load();
+    out->d2h_bytes = g_xfer.d2h_bytes.load();
+    out->d2h_calls = g_xfer.d2h_calls.load();
+    out->d2d_bytes = g_xfer.d2d_bytes.load();
+    out->d2d_calls = g_xfer.d2d_calls.load();
     return AXB_OK;
 }
 

@@ -126,9 +126,13 @@ struct Lowering {
         } else {
             for (size_t i = 0; i < n->inputs.size() && i < 2; ++i)
                 in.src[i] = emit(n->inputs[i].get(), pg, tree_root);
-            if (n->op_type == OpType::LeakyReLU)
+            if (n->op_type == OpType::LeakyReLU) {
+                // lazy unary nodes carry NoParams (operations.cpp:1394 create_lazy_unary): the slope is the CPU functor's
+                // 0.01 (cpu_operations.hpp LeakyReLUFunc) unless the node has ActivationParams
+                in.imm = 0.01;
                 if (auto *ap = std::get_if<ActivationParams>(&n->params))
                     in.imm = (double)ap->alpha;
+            }
         }
         pg.instrs.push_back(in);
         return AXB_SRC_VALUE((int32_t)pg.instrs.size() - 1);
@@ -520,6 +524,8 @@ bool chain_program(const StepBase &step, const std::vector<OpType> &chain, std::
         axb_instr in{};
         in.op = to_axb_op(op);
         in.src[0] = in.src[1] = in.src[2] = AXB_SRC_NONE;
+        if (op == OpType::LeakyReLU)
+            in.imm = 0.01; // op chains carry no parameters; same default as the eager path and the CPU functor
         const auto &slots = step.input_slot_indices[i];
         int32_t dts[2] = {-1, -1};
         for (size_t k = 0; k < slots.size() && k < 2; ++k) {

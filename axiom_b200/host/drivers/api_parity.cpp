@@ -1,0 +1,96 @@
+// api_parity — small GPU-vs-CPU parity cases through the reference's Tensor API that the reference's own tests do not hold
+// (leaky_relu on the lazy GPU path silently became relu). Every case runs the SAME expression on Device::CPU
+// and Device::GPU of the same library and compares the results; fp32 elementwise is bit-exact, half types exact as well
+// (both sides compute in float and round once, bfloat16.hpp:55-66).
+// One JSON object on stdout; exit code 0 = all ok.
+#include <axiom/axiom.hpp>
+
+#include <cstdio>
+#include <cstring>
+#include <functional>
+#include <string>
+#include <vector>
+
+#include "axb.h"
+
+using namespace axiom;
+
+struct Case {
+    std::string name;
+    bool ok;
+    std::string why;
+};
+
+int main() {
+    ops::OperationRegistry::initialize_builtin_operations();
+    manual_seed(99);
+    std::vector<Case> cases;
+    auto check = [&](const std::string &name, const Tensor &x_cpu, const std::function<Tensor(const Tensor &)> &f) {
+        Case c{name, false, ""};
+        try {
+            Tensor ref = f(x_cpu);
+            ref.sync();
+            Tensor xg = x_cpu.gpu();
+            axb_transfer_stats t0{}, t1{};
+            axb_get_transfer_stats(&t0);
+            const uint64_t l0 = axb_launch_count();
+            Tensor got = f(xg);
+            got.sync();
+            axb_get_transfer_stats(&t1);
+            if (got.device() != Device::GPU)
+                c.why = "result is not on the GPU";
+            else if (axb_launch_count() == l0)
+                c.why = "no kernel launched";
+            else if (t1.d2h_bytes != t0.d2h_bytes)
+                c.why = "device->host traffic inside the GPU call (CPU fallback)";
+            else {
+                Tensor back = got.cpu().ascontiguousarray();
+                Tensor r = ref.ascontiguousarray();
+                if (back.shape() != r.shape() || back.dtype() != r.dtype())
+                    c.why = "shape / dtype differ";
+                else if (std::memcmp(back.data(), r.data(), r.nbytes()) != 0)
+                    c.why = "values differ from the CPU backend";
+                else
+                    c.ok = true;
+            }
+        } catch (const std::exception &e) {
+            c.why = e.what();
+        }
+        cases.push_back(c);
+    };
+
+    Tensor x = Tensor::randn({37, 129}) * 3.0f;
+    x.sync();
+    for (DType dt : {DType::Float32, DType::BFloat16, DType::Float16}) {
+        const std::string sfx = dt == DType::Float32 ? "f32" : dt == DType::BFloat16 ? "bf16" : "f16";
+        Tensor xd = x.astype(dt);
+        xd.sync();
+        // default slope through the LAZY unary node (operations.cpp:1391-1394: NoParams)
+        check("leaky_relu_default_" + sfx, xd, [](const Tensor &t) { return ops::leaky_relu(t); });
+        check("leaky_relu_method_" + sfx, xd, [](const Tensor &t) { return t.leaky_relu(); });
+        // custom slope: relu(x) - slope * relu(-x) (operations.cpp:1396-1400)
+        check("leaky_relu_0p2_" + sfx, xd, [](const Tensor &t) { return ops::leaky_relu(t, 0.2f); });
+        // inside a longer lazy chain, and under a full reduction (the chain + reduction fusion path)
+        check("leaky_relu_chain_" + sfx, xd, [](const Tensor &t) { return (ops::leaky_relu(t) + 1.0f) * t; });
+    }
+    // scalar-operand forms of where (the patched Tensor::where(cond, scalar) overloads, tensor.cpp:1340-1355)
+    Tensor y = Tensor::randn({5, 1, 33}), c = Tensor::randn({5, 7, 33});
+    y.sync();
+    c.sync();
+    auto with_c = [&](const Tensor &t) { return t.device() == Device::GPU ? c.gpu() : c; };
+    check("where_scalar_int", y, [&](const Tensor &t) { return t.where(with_c(t) > 0, 0); });
+    check("where_scalar_float", y, [&](const Tensor &t) { return t.where(with_c(t) > 0.5f, -2.5f); });
+    check("where_scalar_double", y, [&](const Tensor &t) { return t.where(with_c(t) <= 0.0, 7.0); });
+
+    bool all = true;
+    std::printf("{\"cases\": %zu, \"failed\": [", cases.size());
+    bool first = true;
+    for (auto &k : cases)
+        if (!k.ok) {
+            all = false;
+            std::printf("%s{\"name\": \"%s\", \"why\": \"%s\"}", first ? "" : ", ", k.name.c_str(), k.why.c_str());
+            first = false;
+        }
+    std::printf("], \"all_ok\": %s}\n", all ? "true" : "false");
+    return all ? 0 : 1;
+}

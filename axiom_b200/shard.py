@@ -148,6 +148,10 @@ class PeerGroup:
         capi.check(capi.lib().axb_reduce_sharded(capi.OP[op], ctypes.byref(shard.desc()), int(global_count), self.handle,
                                                  ctypes.byref(out.desc()), stream))
 
+    def status(self) -> None:
+        """Raises AxbError once any exchange of this group has timed out (a peer never delivered its partial)."""
+        self._capi.check(self._capi.lib().axb_peer_group_status(self.handle))
+
     def close(self) -> None:
         import ctypes
         L = self._capi.lib()

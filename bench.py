@@ -35,6 +35,15 @@ ALG_BYTES = ROWS * COLS * 4 * 2 + ROWS * 4 + COLS * 4  # 536 952 832
 WORKLOAD = "config2 fused chain ((a.relu()+1.0f)*b).where(c>0,0): a{4096,1} b{1,16384} c{4096,16384} fp32"
 
 
+def bench_config():
+    """`config` of the JSON line — IDENTICAL in both arms (the driver compares the dicts): it names the workload and how
+    it is laid out, nothing about how an arm runs it (that goes to the top-level `arm` key)."""
+    return {"workload": WORKLOAD, "per_gpu_rows": ROWS, "cols": COLS,
+            "sharding": "rows of the broadcast result; every rank runs {4096,16384}; no collective",
+            "l2": "512 MiB touched per step >> 126 MB L2 (inputs larger than L2, no flush needed)",
+            "algorithmic_bytes_per_step_per_gpu": ALG_BYTES}
+
+
 def _peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -45,18 +54,49 @@ def _peaks():
 
 
 class ClockSampler:
-    """nvidia-smi sampled DURING the timed region (B200_PROFILING.md clocks line)."""
+    """SM clock, power and throttle reasons sampled DURING a timed region (B200_PROFILING.md clocks line). NVML through
+    pynvml in a thread (first sample within a millisecond, so even a 0.4 s loop is covered); nvidia-smi -lms as a fallback."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    REASONS = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap"))
 
-    def __init__(self, index: int):
-        self.index, self.rows, self.proc = index, [], None
+    def __init__(self, index: int, interval_ms: int = 100, all_samples: bool = False):
+        self.index, self.rows, self.proc, self.interval_ms = index, [], None, interval_ms
+        self.all_samples = all_samples  # True: the sampler only lives during a loop, so every sample is under load
+        self._stop, self._thread, self.source = threading.Event(), None, None
+
+    def _nvml_loop(self, nv, h):
+        mx = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+        getr = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self._stop.is_set():
+            try:
+                sm = float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                pw = nv.nvmlDeviceGetPowerUsage(h) / 1000.0
+                bits = int(getr(h))
+                self.rows.append((sm, mx, pw, {n for b, n in self.REASONS if bits & b}))
+            except Exception:  # noqa: BLE001
+                pass
+            self._stop.wait(self.interval_ms / 1000.0)
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
-                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            import pynvml as nv
+            nv.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[self.index]) if vis and all(v.strip().isdigit() for v in vis.split(",")) else self.index
+            h = nv.nvmlDeviceGetHandleByIndex(idx)
+            self.source = "nvml"
+            self._thread = threading.Thread(target=self._nvml_loop, args=(nv, h), daemon=True)
+            self._thread.start()
+            return self
+        except Exception:  # noqa: BLE001
+            pass
+        try:
+            self.source = "nvidia-smi"
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms",
+                                          str(self.interval_ms), "-i", str(self.index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
@@ -64,29 +104,33 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            r = [c.strip() for c in line.split(",")]
+            try:
+                reasons = {n for n, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9])
+                           if v.lower().startswith("active")}
+                self.rows.append((float(r[1]), float(r[2]), float(r[3]), reasons))
+            except Exception:  # noqa: BLE001
+                continue
 
     def stop(self):
+        self._stop.set()
+        if self._thread:
+            self._thread.join(timeout=1)
         if self.proc:
             self.proc.terminate()
             try:
                 self.proc.wait(timeout=2)
             except Exception:
                 pass
-        sm, mx, reasons = [], 0.0, set()
-        for r in self.rows:
-            try:
-                sm.append(float(r[1]))
-                mx = max(mx, float(r[2]))
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
-            except Exception:
-                continue
+        sm = [r[0] for r in self.rows]
+        mx = max([r[1] for r in self.rows], default=0.0)
+        pw = [r[2] for r in self.rows]
+        reasons = set().union(*[r[3] for r in self.rows]) if self.rows else set()
         busy = sorted(s for s in sm if s > 0)
-        top = busy[len(busy) // 2:] if busy else []  # samples under load = upper half
+        top = busy if self.all_samples else (busy[len(busy) // 2:] if busy else [])  # else: under load = upper half
         return {"sm_mhz": float(np.median(top)) if top else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "power_w_median": float(np.median(pw)) if pw else None, "power_w_max": max(pw) if pw else None,
+                "source": self.source}
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -119,7 +163,9 @@ def run_reference(args, rank):
     out = {"impl": "reference", "metric": "fused_elementwise_chain_throughput", "value": val, "unit": "GB/s",
            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3,
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": {"workload": WORKLOAD, "backend": "reference CPU backend (Highway SIMD + native BLAS + OpenMP)"},
+           "config": bench_config(),
+           "arm": "reference CPU backend (Highway SIMD + native BLAS + OpenMP; OpenBLAS is not installed in this image, "
+                  "src/backends/cpu/blas/blas_openblas.cpp:58-68 — irrelevant for this elementwise chain)",
            "cpu_baseline": {"value": val, "unit": "GB/s", "cores": cores, "kind": "reference",
                             "sample": f"full config-2 chain per step, {args.steps} steps"},
            "e2e": {"value": val, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -147,7 +193,10 @@ def main():
     capi.check(L.axb_set_device(local_rank))
     dist = None
     if world > 1:
-        os.environ["NCCL_DEBUG"] = "WARN"  # NCCL_DEBUG=VERSION/INFO would put a banner on stdout next to the one JSON line
+        # NCCL_DEBUG is left as the launcher set it (the driver reads the communicator lines to check the rank count);
+        # when nobody set it, ask for the INIT lines ourselves. The JSON line is printed last, on its own line.
+        os.environ.setdefault("NCCL_DEBUG", "INFO")
+        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
         import torch
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
@@ -301,11 +350,33 @@ def main():
         exp = np.where(hc > 0, (np.maximum(ha, 0) + np.float32(1)) * hb, np.float32(0))
         assert np.array_equal(ho, exp), "e2e result differs from the closed form"
 
-    multi = None
-    multi_c5 = None
-    if dist is not None and not args.no_extras:
-        multi = sharded_full_reduction(L, capi, dev, dist, world, local_rank, barrier, max_over_ranks)
-        multi_c5 = sharded_whisper(dist, world, local_rank, barrier, max_over_ranks)
+    def timed_graph(fn, k, chunk=100):
+        """k calls replayed from CUDA graphs of <= `chunk` calls each (no host gaps between short kernels)."""
+        per = min(k, chunk)
+        g = capture(fn, per)
+        if g is None:
+            return timed(fn, k)
+        g()
+        dev.synchronize()
+        reps = max(1, (k + per - 1) // per)
+        return timed(g, reps) / per
+
+    ceiling = None
+    side = {}
+    if not args.no_extras:
+        try:
+            ceiling = pcie_ceiling_probe(L, capi, int(sum(int(t.nbytes) for t in hins)), int(ho.nbytes), barrier, max_over_ranks, world)
+        except Exception as ex:  # noqa: BLE001
+            ceiling = {"error": repr(ex)}
+        env = dict(L=L, capi=capi, dev=dev, timed=timed, timed_graph=timed_graph, world=world, rank=rank, local_rank=local_rank,
+                   barrier=barrier, max_over_ranks=max_over_ranks, peaks=_peaks())
+        try:
+            side = sharded_configs(env)  # C3 rows/N and C4 64/N per GPU: every rank takes part
+        except Exception as ex:  # noqa: BLE001 — the headline must still print
+            side = {"error": repr(ex)}
+        if dist is not None:
+            side["c3_full_sum_row_sharded"] = sharded_full_reduction(L, capi, dev, dist, world, local_rank, barrier, max_over_ranks)
+            side["c5_whisper_encoder_batch_sharded"] = sharded_whisper(dist, world, local_rank, barrier, max_over_ranks)
 
     if rank != 0:
         if dist is not None:
@@ -324,12 +395,10 @@ def main():
         "metric": "fused_elementwise_chain_throughput", "value": value, "unit": "GB/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "per_gpu_rows": ROWS, "cols": COLS,
-                   "sharding": "rows of the broadcast result; every rank runs {4096,16384}; no collective",
-                   "l2": "512 MiB touched per step >> 126 MB L2 (inputs larger than L2, no flush needed)",
-                   "launch": ("K steps captured in one CUDA graph on the backend stream, timed between two CUDA events"
-                              if graph is not None else "K steps enqueued one by one, timed between two CUDA events"),
-                   "algorithmic_bytes_per_step_per_gpu": ALG_BYTES},
+        "config": bench_config(),
+        "arm": ("libaxb.so through the C ABI; " +
+                ("K steps captured in one CUDA graph on the backend stream, timed between two CUDA events"
+                 if graph is not None else "K steps enqueued one by one, timed between two CUDA events")),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                      "traffic": traffic, "peak_source": peak_src + " (MEASURED_PEAKS.json hbm_gbs, copy kernel)",
                      "kernel": "axb_ew (specialised fused chain)"},
@@ -339,22 +408,19 @@ def main():
         "clocks": clocks,
     }
 
-    if multi is not None:
-        result["extras"] = {"c3_full_sum_row_sharded": multi, "c5_whisper_encoder_batch_sharded": multi_c5}
+    if ceiling is not None:
+        result["e2e"]["ceiling_GBps"] = ceiling.get("GBps_total")
+        result["e2e"]["frac_of_ceiling"] = (e2e_val / ceiling["GBps_total"]) if ceiling.get("GBps_total") else None
+        result["e2e"]["ceiling_probe"] = ceiling
     if world == 1:
         result["cpu_baseline"] = cpu_baseline()
-        if not args.no_extras:
+    if not args.no_extras:
+        if world == 1:
             try:
-                def timed_graph(fn, k):
-                    g = capture(fn, k)
-                    if g is None:
-                        return timed(fn, k)
-                    g()
-                    dev.synchronize()
-                    return timed(g, 1) / k
-                result["extras"] = extras(L, capi, dev, timed, hbm_peak, tf_peak, tf_sust, timed_graph)
-            except Exception as ex:  # the headline must still print
-                result["extras"] = {"error": repr(ex)}
+                side.update(single_gpu_extras(dev, timed))
+            except Exception as ex:  # noqa: BLE001
+                side["c1_error"] = repr(ex)
+        result["extras"] = side
     print(json.dumps(result))
     if dist is not None:
         dist.destroy_process_group()
@@ -481,30 +547,46 @@ def cpu_baseline():
         return {"value": None, "unit": "GB/s", "cores": 0, "kind": "reference", "sample": "failed: " + repr(ex)}
 
 
-def extras(L, capi, dev, timed, hbm_peak, tf_peak, tf_sust=None, timed_graph=None):
-    """Side measurements for the other BASELINE configs (CUDA events, inputs resident, >= 3 warm-ups each)."""
+def sharded_configs(env):
+    """BASELINE configs 3 and 4 at N GPUs (BASELINE.json configs[2..3]): the rows of the {8192, 32768} tensor
+    and the 64 matrices of the bf16 bmm are SHARDED along the leading dim — every rank runs rows 8192/N resp. 64/N
+    matrices, no collective — so the totals below are strong-scaling numbers: `GBps` / `TFLOPs` = work of ALL ranks over the
+    max-over-ranks device time; `frac_*` = one GPU's rate against the measured peak. Every entry is looped for at least
+    `min_s` seconds (C4: 2 s) between two CUDA events with nvidia-smi clocks and power sampled during that loop."""
+    import math
+    L, capi, dev = env["L"], env["capi"], env["dev"]
+    world, rank = env["world"], env["rank"]
+    hbm_peak, tf_peak, tf_sust, _ = env["peaks"]
     ex = {}
+    by = ctypes.byref
 
-    def run(name, fn, nbytes=None, flops=None, k=10, graph=True):
+    def run(name, fn, nbytes=None, flops=None, min_s=0.4, per_gpu=None):
         for _ in range(3):
             fn()
-        # single-kernel entries are timed like the headline: the k calls replayed from one CUDA graph (no host gaps
-        # between 80-370 us kernels); entries that allocate on the way (the README chain) are enqueued call by call
-        ms = timed_graph(fn, k) if (graph and timed_graph) else timed(fn, k)
-        r = {"ms": ms}
+        est = max(env["timed"](fn, 3), 1e-3)
+        k = int(max(10, min(20000, math.ceil(min_s * 1e3 / est))))
+        env["barrier"]()
+        sampler = ClockSampler(env["local_rank"], interval_ms=25, all_samples=True).start() if rank == 0 else None
+        ms = env["timed_graph"](fn, k)
+        clocks = sampler.stop() if sampler else None
+        env["barrier"]()
+        ms_max = env["max_over_ranks"](ms)
+        r = {"ms": ms_max, "calls": k, "loop_s": ms * k / 1e3, "shards": world, "clocks": clocks}
+        if per_gpu:
+            r.update(per_gpu)
         if nbytes:
-            r["GBps"] = nbytes / ms / 1e6
-            r["frac_hbm"] = r["GBps"] / hbm_peak
+            r["GBps"] = world * nbytes / ms_max / 1e6
+            r["frac_hbm"] = nbytes / ms_max / 1e6 / hbm_peak
         if flops:
-            r["TFLOPs"] = flops / ms / 1e9
-            r["frac_bf16_peak"] = r["TFLOPs"] / tf_peak  # MEASURED_PEAKS bf16_tflops: cuBLAS best-of-10 burst
-            if tf_sust:  # cuBLAS back to back for 4 s (power-limited clocks) - the regime a 6 ms x 3 timed loop runs in
-                r["frac_bf16_sustained"] = r["TFLOPs"] / tf_sust
+            r["TFLOPs"] = world * flops / ms_max / 1e9
+            r["TFLOPs_per_gpu"] = flops / ms_max / 1e9
+            r["frac_bf16_peak"] = r["TFLOPs_per_gpu"] / tf_peak  # MEASURED_PEAKS bf16_tflops: cuBLAS best-of-10 burst
+            r["frac_bf16_sustained"] = r["TFLOPs_per_gpu"] / tf_sust  # cuBLAS back to back for 4 s under the power cap
         ex[name] = r
 
-    rows, n = 8192, 32768
+    rows, n = 8192 // world, 32768
     for dt in ("f32", "bf16"):
-        x = dev.randn((rows, n), 7)
+        x = dev.randn((rows, n), 7 + 100 * rank)
         isz = 4
         if dt == "bf16":
             x = dev.cast(x, capi.BF16)
@@ -515,27 +597,35 @@ def extras(L, capi, dev, timed, hbm_peak, tf_peak, tf_sust=None, timed_graph=Non
         obig = dev.DeviceArray.empty((rows, n), x.dtype)
         xd, wd, bd = x.desc(), w.desc(), b.desc()
         ax = (ctypes.c_int32 * 1)(1)
-        by = ctypes.byref
+        pg = {"rows_per_gpu": rows}
         run(f"c3_sum_{dt}", lambda: capi.check(L.axb_reduce(capi.OP["sum"], by(xd), ax, 1, 0, by(osum.desc()), None)),
-            rows * n * isz + rows * isz)
+            rows * n * isz + rows * isz, per_gpu=pg)
         run(f"c3_max_{dt}", lambda: capi.check(L.axb_reduce(capi.OP["max"], by(xd), ax, 1, 0, by(osum.desc()), None)),
-            rows * n * isz + rows * isz)
+            rows * n * isz + rows * isz, per_gpu=pg)
         run(f"c3_argmax_{dt}", lambda: capi.check(L.axb_argreduce(capi.OP["argmax"], by(xd), 1, 0, by(oarg.desc()), None)),
-            rows * n * isz + rows * 8)
-        run(f"c3_softmax_{dt}", lambda: capi.check(L.axb_softmax(by(xd), -1, 0, by(obig.desc()), None)), 2 * rows * n * isz)
+            rows * n * isz + rows * 8, per_gpu=pg)
+        run(f"c3_softmax_{dt}", lambda: capi.check(L.axb_softmax(by(xd), -1, 0, by(obig.desc()), None)), 2 * rows * n * isz,
+            per_gpu=pg)
         run(f"c3_layer_norm_{dt}", lambda: capi.check(L.axb_layer_norm(by(xd), by(wd), by(bd), -1, 1e-5, by(obig.desc()), None)),
-            2 * rows * n * isz + 2 * n * 4)
+            2 * rows * n * isz + 2 * n * 4, per_gpu=pg)
         del x, obig
-    # C4: bf16 batched matmul {64,4096,4096}^2 (one GPU's share at N=1 is the whole batch)
-    nb, m = 64, 4096
-    A = dev.cast(dev.randn((nb, m, m), 11), capi.BF16)
-    Bm = dev.cast(dev.randn((nb, m, m), 12, 0.0, 1.0 / 64.0), capi.BF16)
+    # C4: bf16 batched matmul {64,4096,4096}^2, 64/N matrices per GPU, looped >= 2 s (power-limited steady state)
+    nb, m = 64 // world, 4096
+    A = dev.cast(dev.randn((nb, m, m), 11 + 100 * rank), capi.BF16)
+    Bm = dev.cast(dev.randn((nb, m, m), 12 + 100 * rank, 0.0, 1.0 / 64.0), capi.BF16)
     C = dev.DeviceArray.empty((nb, m, m), capi.BF16)
     ad, bd, cd = A.desc(), Bm.desc(), C.desc()
-    run("c4_bmm_bf16_64x4096", lambda: capi.check(L.axb_matmul(ctypes.byref(ad), ctypes.byref(bd), 0, 0, None, ctypes.byref(cd), None)),
-        flops=2.0 * nb * m ** 3, k=3)
+    run("c4_bmm_bf16_64x4096", lambda: capi.check(L.axb_matmul(by(ad), by(bd), 0, 0, None, by(cd), None)),
+        flops=2.0 * nb * m ** 3, min_s=2.0, per_gpu={"matrices_per_gpu": nb, "kernel_path": None})
+    ex["c4_bmm_bf16_64x4096"]["kernel_path"] = int(L.axb_matmul_last_path())
     del A, Bm, C
-    # C1: README chain fp32 1024^2 (launch/latency bound; reported, not graded against peak)
+    return ex
+
+
+def single_gpu_extras(dev, timed):
+    """N = 1 only: the C1 README chain through the C ABI (launch / latency bound; reported, not graded against a peak) and
+    configs 1, 2, 3, 4, 5 through the reference's OWN C++ API."""
+    ex = {}
     x = dev.randn((1024, 1024), 1234)
 
     def readme():
@@ -543,9 +633,71 @@ def extras(L, capi, dev, timed, hbm_peak, tf_peak, tf_sust=None, timed_graph=Non
         p = dev.softmax(s, -1)
         dev.reduce("sum", p, [1])
 
-    run("c1_readme_chain_f32_1024", readme, k=10, graph=False)
+    for _ in range(3):
+        readme()
+    ex["c1_readme_chain_f32_1024"] = {"ms": timed(readme, 10)}
     ex["axiom_cpp_api"] = cpp_api_extras()
     return ex
+
+
+def pcie_ceiling_probe(L, capi, h2d_bytes, d2h_bytes, barrier, max_over_ranks, world, reps=8):
+    """What bounds `e2e`: every rank moves the step's H2D bytes up and its D2H bytes down CONCURRENTLY (two streams, pinned
+    buffers, plain cudaMemcpyAsync — no kernel), all ranks at the same time. `GBps_total` is in the unit of `e2e.value`
+    (bytes moved per step over all ranks / max-over-ranks time), i.e. the ceiling the e2e figure can reach on this host."""
+    rt = ctypes.CDLL("libcudart.so.12")
+    vp = ctypes.c_void_p
+    rt.cudaStreamCreateWithFlags.argtypes = [ctypes.POINTER(vp), ctypes.c_uint]
+    rt.cudaStreamSynchronize.argtypes = [vp]
+    rt.cudaStreamDestroy.argtypes = [vp]
+    up, down = vp(), vp()
+    if rt.cudaStreamCreateWithFlags(ctypes.byref(up), 1) != 0 or rt.cudaStreamCreateWithFlags(ctypes.byref(down), 1) != 0:
+        raise RuntimeError("cudaStreamCreate failed")
+    hsrc, hdst, dsrc, ddst = vp(), vp(), vp(), vp()
+    capi.check(L.axb_host_alloc(h2d_bytes, ctypes.byref(hsrc)))
+    capi.check(L.axb_host_alloc(d2h_bytes, ctypes.byref(hdst)))
+    capi.check(L.axb_alloc(h2d_bytes, None, ctypes.byref(ddst)))
+    capi.check(L.axb_alloc(d2h_bytes, None, ctypes.byref(dsrc)))
+    ctypes.memset(hsrc.value, 1, h2d_bytes)
+    ctypes.memset(hdst.value, 0, d2h_bytes)
+    capi.check(L.axb_stream_sync(None))
+
+    def one(both=True, do_up=True):
+        if both or do_up:
+            capi.check(L.axb_memcpy_h2d(ddst, hsrc, h2d_bytes, up))
+        if both or not do_up:
+            capi.check(L.axb_memcpy_d2h(hdst, dsrc, d2h_bytes, down, 0))
+
+    def timed_loop(**kw):
+        for _ in range(2):
+            one(**kw)
+        rt.cudaStreamSynchronize(up)
+        rt.cudaStreamSynchronize(down)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            one(**kw)
+        rt.cudaStreamSynchronize(up)
+        rt.cudaStreamSynchronize(down)
+        dt = (time.perf_counter() - t0) / reps
+        barrier()
+        return max_over_ranks(dt)
+
+    t_both = timed_loop(both=True)
+    t_up = timed_loop(both=False, do_up=True)
+    t_down = timed_loop(both=False, do_up=False)
+    out = {"GBps_total": world * (h2d_bytes + d2h_bytes) / t_both / 1e9, "ms_per_step": t_both * 1e3,
+           "h2d_only_GBps_per_gpu": h2d_bytes / t_up / 1e9, "d2h_only_GBps_per_gpu": d2h_bytes / t_down / 1e9,
+           "bidirectional_GBps_per_gpu": (h2d_bytes + d2h_bytes) / t_both / 1e9, "ranks": world,
+           "pinned_numa_node": int(L.axb_host_alloc_numa_node()),
+           "how": "concurrent pinned cudaMemcpyAsync H2D + D2H of the step's byte counts on two streams, all ranks together, "
+                  f"{reps} repetitions, wall clock between barriers, max over ranks"}
+    capi.check(L.axb_free(ddst, None))
+    capi.check(L.axb_free(dsrc, None))
+    capi.check(L.axb_host_free(hsrc))
+    capi.check(L.axb_host_free(hdst))
+    rt.cudaStreamDestroy(up)
+    rt.cudaStreamDestroy(down)
+    return out
 
 
 def cpp_api_extras():
@@ -557,6 +709,7 @@ def cpp_api_extras():
     bdir = os.path.join(ROOT, "axiom_b200", "host", "_build")
     out = {}
     for name, cmd in (("chains", ["axiom_chains", "4096", "16384", "20"]),
+                      ("c3_c4", ["c3_c4_api"]),
                       ("whisper_encoder_b8", ["whisper_encoder", "8", "5", "1"]),
                       ("whisper_encoder_b32", ["whisper_encoder", "32", "3", "0"])):
         exe = os.path.join(bdir, cmd[0])

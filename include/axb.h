@@ -132,17 +132,32 @@ axb_status axb_free(void *ptr, axb_stream_t stream);
 axb_status axb_empty_cache(void);
 typedef struct axb_alloc_stats {
     uint64_t bytes_in_use, bytes_cached, peak_bytes_in_use, n_cuda_malloc, n_cache_hits, n_allocs;
+    uint64_t n_splits, n_merges, n_cross_stream; /* block splitting / coalescing / event-ordered hand-overs */
 } axb_alloc_stats;
 axb_status axb_get_alloc_stats(axb_alloc_stats *out);
 /* pinned host staging (H2D of randn()/weights, tensor.cpp:1884-1904) */
 axb_status axb_host_alloc(size_t bytes, void **ptr);
 axb_status axb_host_free(void *ptr);
+/* NUMA node the LAST axb_host_alloc of the calling thread was placed on (the node of the current GPU's PCI function), or
+ * -1 when no placement was applied (single-node host, syscall unavailable, AXB_HOST_NUMA=0). */
+int axb_host_alloc_numa_node(void);
 /* async copies on `stream`; d2h additionally synchronises the stream before returning when sync!=0
  * (MetalStorage::copy_to(CPU) synchronises first, metal_storage.mm:66-93) */
 axb_status axb_memcpy_h2d(void *dst_dev, const void *src_host, size_t bytes, axb_stream_t stream);
 axb_status axb_memcpy_d2h(void *dst_host, const void *src_dev, size_t bytes, axb_stream_t stream, int sync);
 axb_status axb_memcpy_d2d(void *dst_dev, const void *src_dev, size_t bytes, axb_stream_t stream);
 axb_status axb_memset(void *dst_dev, int value, size_t bytes, axb_stream_t stream);
+/* Host<->device traffic this library has issued since load (all devices, all entry points incl. the *_host calls).
+ * The fallback detector of the C++ glue and the tests: a GPU forward that silently dropped to the reference's CPU
+ * path (src/tensor/operations.cpp:913-917, src/graph/graph_executor.cpp:346-349) shows up as D2H bytes between two
+ * snapshots, exactly as axb_launch_count shows missing kernels. */
+typedef struct axb_transfer_stats {
+    uint64_t h2d_bytes, h2d_calls, d2h_bytes, d2h_calls, d2d_bytes, d2d_calls;
+} axb_transfer_stats;
+axb_status axb_get_transfer_stats(axb_transfer_stats *out);
+/* Pre-warms the caching allocator of the current device with one segment of `bytes` (split on demand), so a steady
+ * state that fits it never calls cudaMalloc. */
+axb_status axb_pool_reserve(size_t bytes);
 
 /* ------------------------------------------------------------------------------------------------
  * Family 1 — fused elementwise / broadcast / where chains (one launch per fusion group).
@@ -254,6 +269,9 @@ axb_status axb_peer_mailbox_destroy(void *mailbox);
 axb_status axb_peer_group_create(int rank, int world, void *const *mailboxes /* world pointers, [rank] = own */,
                                  axb_peer_group **group);
 axb_status axb_peer_group_destroy(axb_peer_group *group);
+/* AXB_ERR_CUDA once any exchange of this group has timed out (a peer never delivered its partial within ~20 s; that call's
+ * result is NaN on this rank whatever the op). Also checked at the start of every axb_reduce_sharded. Never blocks. */
+axb_status axb_peer_group_status(const axb_peer_group *group);
 axb_status axb_reduce_sharded(int32_t op, const axb_tensor *in_shard, int64_t global_count, axb_peer_group *group,
                               const axb_tensor *out, axb_stream_t stream);
 /* softmax / log_softmax along `axis` (any axis; fp32/bf16/fp16/f64; half via fp32 round trip). */
@@ -263,6 +281,10 @@ axb_status axb_layer_norm(const axb_tensor *in, const axb_tensor *weight, const 
                           float eps, const axb_tensor *out, axb_stream_t stream);
 axb_status axb_rms_norm(const axb_tensor *in, const axb_tensor *weight, int axis, float eps,
                         const axb_tensor *out, axb_stream_t stream);
+/* Which kernel the LAST softmax / layer_norm / rms_norm of the calling thread ran on: 0 = generic (register-resident or
+ * streaming rows), 1 = wide TMA-staged persistent kernel (rows of 32..128 KiB), 2 = SM-pair cluster kernel (wide rows
+ * with affine parameters resident in shared memory). -1 before the first call. */
+int axb_rownorm_last_path(void);
 /* elementwise prologue fused into a FULL reduction (FusedReductionStep, compiled_graph.hpp:61-66):
  * the program's last value is reduced with `op` instead of being stored. */
 axb_status axb_elementwise_reduce(const axb_instr *prog, int n_instr, const axb_tensor *inputs, int n_inputs,

@@ -98,8 +98,46 @@ def test_configs_1_and_2_through_the_axiom_api(gpu):
     j = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
     assert r.returncode == 0, r.stdout + r.stderr
     assert j["config1"]["parity_ok"] and j["config2"]["bit_exact"]
+    # config 2 is the LITERAL BASELINE expression ((a.relu()+1.0f)*b).where(c>0, 0): scalar operands, nothing pre-uploaded
     assert j["config2"]["gpu_launches"] == 1, "config 2 must lower to ONE fused kernel"
+    assert j["config2"]["d2h_bytes_per_call"] == 0
+    assert j["config2"]["h2d_bytes_per_call"] <= 64, "only the three scalar operands may be uploaded (no full-size constant)"
     assert j["config1"]["gpu_launches"] <= 6
+
+
+@pytest.mark.gpu
+def test_configs_3_and_4_through_the_axiom_api(gpu):
+    """C3 {8192,32768} fp32 + bf16 (sum / max / argmax / softmax / layer_norm) and C4 bf16 bmm {64,4096,4096} through the
+    Tensor API at the BASELINE sizes: zero device->host bytes inside every GPU call, the expected kernel family (wide
+    TMA-staged softmax, SM-pair cluster layer_norm, CTA-pair tcgen05 GEMM), parity against Device::CPU."""
+    _need_build()
+    exe = os.path.join(BUILD, "c3_c4_api")
+    if not os.path.exists(exe):
+        pytest.skip("c3_c4_api not built")
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=1500)
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert lines, r.stdout[-2000:] + r.stderr[-2000:]
+    j = json.loads(lines[-1])
+    bad = {k: v for k, v in j["calls"].items() if not v["ok"]}
+    assert not bad and r.returncode == 0, bad
+    assert j["calls"]["c3_softmax_f32"]["kernel_path"] == 1 and j["calls"]["c3_layer_norm_f32"]["kernel_path"] == 2
+    assert j["calls"]["c4_bmm_bf16"]["kernel_path"] == 2
+    assert all(v["d2h_bytes"] == 0 for v in j["calls"].values())
+
+
+@pytest.mark.gpu
+def test_api_parity_cases(gpu):
+    """leaky_relu (default slope through the lazy unary node, custom slope, inside a chain; fp32 / bf16 / fp16) and the
+    scalar forms of Tensor::where — GPU bit-identical to the CPU backend, no CPU fallback."""
+    _need_build()
+    exe = os.path.join(BUILD, "api_parity")
+    if not os.path.exists(exe):
+        pytest.skip("api_parity not built")
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=600)
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert lines, r.stdout[-2000:] + r.stderr[-2000:]
+    j = json.loads(lines[-1])
+    assert j["all_ok"] and r.returncode == 0, j["failed"]
 
 
 @pytest.mark.gpu

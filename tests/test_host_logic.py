@@ -70,7 +70,7 @@ def test_specialised_kernel_compiles_without_a_gpu_and_is_cached(tmp_path, monke
     assert (s1.compiles - s0.compiles) + (s1.disk_hits - s0.disk_hits) == 2
     assert s1.compiles - s0.compiles <= 1, "a shape change must not trigger a second compile"
     cache = os.path.join(os.path.dirname(capi.LIB_PATH), "kernel_cache")
-    assert any(f.endswith(".cubin") for f in os.listdir(cache))
+    assert any(f.endswith(".axbk") for f in os.listdir(cache))
 
 
 def test_program_validation_errors():
