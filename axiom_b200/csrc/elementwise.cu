@@ -11,6 +11,8 @@
 #include "axb_internal.h"
 #include "ew_micro_table.h"
 #include "ew_prelude.cuh"
+#include <cuda_fp16.h>
+
 #include "jit.h"
 
 namespace axb {
@@ -655,6 +657,8 @@ axb_status lower_program(const axb_instr *prog, int n_instr, const axb_tensor *i
                             uint64_t b = imm_bits(in.imm, AXB_BF16);
                             uint32_t bb = (uint32_t)b;
                             memcpy(&sl, &bb, 4);
+                        } else if (ct == AXB_F16) {
+                            sl = __half2float(__float2half_rn(sl)); // float16_t(float) rounds the slope first (float16.hpp:15)
                         }
                         uint32_t bits;
                         memcpy(&bits, &sl, 4);
@@ -885,10 +889,10 @@ axb_status broadcast_all(const axb_tensor *inputs, int n_inputs, int64_t *oshape
     return AXB_OK;
 }
 
-// Full translation unit of one specialised kernel.
+// Program-specific tail of the translation unit of one specialised kernel (jit.cpp prepends the shared prelude).
 std::string kernel_source(const std::string &loads, const std::string &body, bool wide, int vec, int n_outer, int n_inputs,
                           int unroll, int reduce_opk = -1) {
-    std::string s = jit::ew_prelude_text();
+    std::string s;
     char hdr[200];
     if (reduce_opk < 0)
         snprintf(hdr, sizeof hdr, "\nEW_KERNEL_BEGIN(axb_ew, %d, %s, %d, %d, %d)\n", vec, wide ? "uint64_t" : "uint32_t", n_outer,

@@ -170,11 +170,22 @@ struct SourceId {
 std::map<std::pair<SourceId, int>, Kernel> g_kernels; // (source id, device) -> function
 Stats g_stats{0, 0, 0};
 
-SourceId source_id(const std::string &source) {
+// `body` is the program-specific tail of the translation unit; the shared prelude (ew_prelude.cuh + hwy_math.cuh, ~45 KB)
+// is hashed ONCE per process and only seeds the per-call hashes, so a cache lookup costs a hash of ~1 KB, not of the
+// whole source (which dominated the host time of a fused-chain launch: two passes over 45 KB per call).
+SourceId source_id(const std::string &body) {
+    static const SourceId prelude = [] {
+        const std::string &p = ew_prelude_text();
+        SourceId id;
+        id.h1 = fnv1a(p.data(), p.size(), fnv1a(kCacheTag, sizeof kCacheTag));
+        id.h2 = fnv1a(p.data(), p.size(), 0x9E3779B97F4A7C15ull ^ p.size());
+        id.len = p.size();
+        return id;
+    }();
     SourceId id;
-    id.h1 = fnv1a(source.data(), source.size(), fnv1a(kCacheTag, sizeof kCacheTag));
-    id.h2 = fnv1a(source.data(), source.size(), 0x9E3779B97F4A7C15ull ^ source.size());
-    id.len = source.size();
+    id.h1 = fnv1a(body.data(), body.size(), prelude.h1);
+    id.h2 = fnv1a(body.data(), body.size(), prelude.h2 ^ body.size());
+    id.len = prelude.len + body.size();
     return id;
 }
 std::string cache_path(const SourceId &id) {
@@ -224,13 +235,13 @@ void write_cached(const std::string &path, const SourceId &id, const std::vector
 }
 
 // cubin bytes for `source`: disk cache, else NVRTC (+ store)
-axb_status cubin_for(const std::string &source, const SourceId &id, std::vector<char> *bin, bool force_compile = false) {
+axb_status cubin_for(const std::string &body, const SourceId &id, std::vector<char> *bin, bool force_compile = false) {
     const std::string path = cache_path(id);
     if (!force_compile && read_cached(path, id, bin)) {
         g_stats.disk_hits++;
         return AXB_OK;
     }
-    AXB_TRY(compile_cubin(source, bin));
+    AXB_TRY(compile_cubin(ew_prelude_text() + body, bin));
     g_stats.compiles++;
     write_cached(path, id, *bin);
     return AXB_OK;

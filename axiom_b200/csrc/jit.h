@@ -1,5 +1,5 @@
 // jit.h — kernel specialisation service: CUDA C++ text -> sm_100a cubin (NVRTC) -> CUfunction, with an
-// in-memory cache per device and an in-tree cubin cache on disk (axiom_b200/kernel_cache/<hash>.cubin).
+// in-memory cache per device and an in-tree cubin cache on disk (axiom_b200/kernel_cache/<hash>.axbk: header + cubin).
 //
 // B200 counterpart of the reference's per-signature MPSGraph caches (src/backends/metal/mpsgraph_fused.mm:373-377,
 // 256 entries; mpsgraph_graph_compiler.mm:756-765, 128 entries): there the Metal backend builds and compiles one
@@ -22,10 +22,11 @@ struct Kernel {
 // text of ew_prelude.cuh + hwy_math.cuh embedded at build time
 const std::string &ew_prelude_text();
 
-// Returns the kernel `name` of translation unit `source` for `device` (compiling / loading it on first use).
-axb_status get_kernel(const std::string &source, const char *name, int device, Kernel *out);
-// Compile-only: make sure the cubin of `source` is in the on-disk cache. Needs no GPU.
-axb_status precompile(const std::string &source);
+// Returns the kernel `name` of the translation unit  ew_prelude_text() + body  for `device` (compiling / loading it on
+// first use). The cache key is a hash of `body` seeded with the prelude's hash: a lookup never touches the prelude text.
+axb_status get_kernel(const std::string &body, const char *name, int device, Kernel *out);
+// Compile-only: make sure the cubin of  ew_prelude_text() + body  is in the on-disk cache. Needs no GPU.
+axb_status precompile(const std::string &body);
 axb_status launch(const Kernel &k, unsigned grid, unsigned block, unsigned smem, cudaStream_t s, void **args);
 
 struct Stats {

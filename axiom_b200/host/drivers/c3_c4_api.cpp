@@ -100,13 +100,6 @@ static double time_gpu(const std::function<Tensor()> &f, int iters) {
     return ms / iters;
 }
 
-static float bf16_to_f32(uint16_t b) {
-    uint32_t u = (uint32_t)b << 16;
-    float f;
-    std::memcpy(&f, &u, 4);
-    return f;
-}
-
 int main(int argc, char **argv) {
     const size_t R = argc > 2 ? std::strtoul(argv[1], nullptr, 10) : 8192;
     const size_t N = argc > 2 ? std::strtoul(argv[2], nullptr, 10) : 32768;
@@ -288,10 +281,12 @@ int main(int argc, char **argv) {
         double worst = 0;
         const size_t rows = std::min<size_t>(128, M);
         for (size_t bi : {(size_t)0, NB - 1}) {
-            Tensor As = A.slice({Slice((int64_t)bi, (int64_t)bi + 1), Slice(0, (int64_t)rows)}).cpu().astype(DType::Float32);
-            Tensor Bs = B.slice({Slice((int64_t)bi, (int64_t)bi + 1)}).cpu().astype(DType::Float32);
+            // NB: Tensor::to() copies a CONTIGUOUS view from the START of its storage (tensor.cpp:1626-1634 ignores offset_),
+            // so a slice of matrix 63 must become a fresh tensor on the device (Cast op) before it travels to the host
+            Tensor As = A.slice({Slice((int64_t)bi, (int64_t)bi + 1), Slice(0, (int64_t)rows)}).astype(DType::Float32).cpu();
+            Tensor Bs = B.slice({Slice((int64_t)bi, (int64_t)bi + 1)}).astype(DType::Float32).cpu();
             Tensor ref = As.matmul(Bs).ascontiguousarray();
-            Tensor got = C.slice({Slice((int64_t)bi, (int64_t)bi + 1), Slice(0, (int64_t)rows)}).cpu().astype(DType::Float32).ascontiguousarray();
+            Tensor got = C.slice({Slice((int64_t)bi, (int64_t)bi + 1), Slice(0, (int64_t)rows)}).astype(DType::Float32).cpu().ascontiguousarray();
             // norm-wise bound per element: |d| <= 1e-2 * (|ref| + row scale); the row scale guards cancellation
             const float *gp = got.typed_data<float>(), *rp = ref.typed_data<float>();
             double scale = 0;
