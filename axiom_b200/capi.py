@@ -71,7 +71,14 @@ class AxbJitStats(ctypes.Structure):
 
 
 class AxbMatmulEpilogue(ctypes.Structure):
-    _fields_ = [("bias", ctypes.POINTER(AxbTensor)), ("activation", ctypes.c_int32)]
+    _fields_ = [("bias", ctypes.POINTER(AxbTensor)), ("activation", ctypes.c_int32), ("flags", ctypes.c_int32)]
+
+
+class AxbConstCacheStats(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_uint64) for n in ("entries", "bytes", "hits", "misses", "invalidations")]
+
+
+MM_CONST_A, MM_CONST_B = 1, 2
 
 
 class AxbError(RuntimeError):
@@ -161,6 +168,10 @@ def lib() -> ctypes.CDLL:
         "axb_matmul": (i32, [T, T, i32, i32, ctypes.POINTER(AxbMatmulEpilogue), T, vp]),
         "axb_matmul_shape": (i32, [T, T, i32, i32, pi64, pi32]),
         "axb_matmul_last_path": (i32, []),
+        "axb_invalidate_cached": (i32, [vp, sz]),
+        "axb_get_const_cache_stats": (i32, [ctypes.POINTER(AxbConstCacheStats)]),
+        "axb_sdpa": (i32, [T, T, T, T, f32, i32, T, vp]),
+        "axb_sdpa_last_path": (i32, []),
         "axb_gather": (i32, [T, i32, T, T, vp]),
         "axb_index_select": (i32, [T, i32, T, T, vp]),
         "axb_conv2d": (i32, [T, T, T, pi32, pi32, pi32, i32, T, vp]),

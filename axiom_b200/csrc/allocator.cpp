@@ -30,6 +30,7 @@
 #include <vector>
 
 #include "axb_internal.h"
+#include "gemm.h"
 
 namespace axb {
 namespace {
@@ -368,6 +369,18 @@ axb_status axb_free(void *ptr, axb_stream_t stream) {
         if (!octx)
             return fail(AXB_ERR_CUDA, "axb_free: device %d has no context", dev);
         s = octx->stream;
+    }
+    // operand forms derived from this block (cached weight splits) die with it — before the block can be handed out again
+    if (gemm::const_cache_active()) {
+        size_t blk = 0;
+        {
+            std::lock_guard<std::mutex> lk(p->mu);
+            auto it = p->live.find(ptr);
+            if (it != p->live.end())
+                blk = it->second->size;
+        }
+        if (blk)
+            gemm::invalidate_const_cache(ptr, blk);
     }
     DeviceGuard guard(dev);
     const bool capturing = is_capturing(s);

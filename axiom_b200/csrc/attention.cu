@@ -22,6 +22,11 @@
 #include "reduce_common.cuh"
 
 namespace axb {
+namespace fa { // flash_attention.cu: the single-kernel path
+bool supported(int32_t dtype, int64_t D, int64_t Dv, int64_t BH, int64_t Lq, int64_t Lk);
+axb_status run(const axb_tensor *q, const axb_tensor *k, const axb_tensor *v, const uint8_t *mask, const int64_t mask_strides[4],
+               float scale, int is_causal, const axb_tensor *out, DeviceCtx *ctx, cudaStream_t s);
+} // namespace fa
 namespace {
 
 struct AttnParams {
@@ -245,7 +250,14 @@ template <int RUNS> __global__ void __launch_bounds__(256) attn_softmax_warp_ker
 
 using namespace axb;
 
+static int &sdpa_last_path() {
+    static thread_local int v = -1;
+    return v;
+}
+
 extern "C" {
+
+int axb_sdpa_last_path(void) { return sdpa_last_path(); }
 
 axb_status axb_sdpa(const axb_tensor *q, const axb_tensor *k, const axb_tensor *v, const axb_tensor *mask, float scale,
                     int is_causal, const axb_tensor *out, axb_stream_t stream) {
@@ -255,8 +267,9 @@ axb_status axb_sdpa(const axb_tensor *q, const axb_tensor *k, const axb_tensor *
     AXB_TRY(validate_tensor(v, what));
     AXB_TRY(validate_tensor(out, what));
     AXB_REQUIRE(q->ndim == 4 && k->ndim == 4 && v->ndim == 4 && out->ndim == 4, AXB_ERR_SHAPE, "%s: q, k, v, out must be 4-D (batch, heads, seq, dim)", what);
-    AXB_REQUIRE(q->dtype == AXB_F32 && k->dtype == AXB_F32 && v->dtype == AXB_F32 && out->dtype == AXB_F32, AXB_ERR_UNSUPPORTED,
-                "%s: Float32 only (other dtypes run as matmul + softmax + matmul)", what);
+    AXB_REQUIRE((q->dtype == AXB_F32 || q->dtype == AXB_BF16 || q->dtype == AXB_F16) && k->dtype == q->dtype && v->dtype == q->dtype &&
+                    out->dtype == q->dtype,
+                AXB_ERR_UNSUPPORTED, "%s: q, k, v, out must share one of Float32 / BFloat16 / Float16", what);
     const int64_t B = q->shape[0], H = q->shape[1], Lq = q->shape[2], D = q->shape[3], Lk = k->shape[2], Dv = v->shape[3];
     AXB_REQUIRE(k->shape[0] == B && v->shape[0] == B && k->shape[1] == H && v->shape[1] == H, AXB_ERR_SHAPE, "%s: batch / heads mismatch", what);
     AXB_REQUIRE(k->shape[3] == D && v->shape[2] == Lk, AXB_ERR_SHAPE, "%s: head_dim / kv length mismatch", what);
@@ -286,6 +299,16 @@ axb_status axb_sdpa(const axb_tensor *q, const axb_tensor *k, const axb_tensor *
         p.mask = reinterpret_cast<const uint8_t *>(tensor_ptr(*mask));
         p.m_sb = st[0]; p.m_sh = st[1]; p.m_sq = st[2]; p.m_sk = st[3];
     }
+    if (fa::supported(q->dtype, D, Dv, B * H, Lq, Lk)) { // one tcgen05 kernel, no materialised score matrix
+        const int64_t mst[4] = {p.m_sb, p.m_sh, p.m_sq, p.m_sk};
+        const axb_status fst = fa::run(q, k, v, p.mask, mst, scale, is_causal, out, ctx, s);
+        if (fst == AXB_OK)
+            sdpa_last_path() = 1;
+        return fst;
+    }
+    AXB_REQUIRE(q->dtype == AXB_F32, AXB_ERR_UNSUPPORTED,
+                "%s: head_dim > 64 is served by the three-kernel path, which is Float32 only (half types: matmul + softmax + matmul)", what);
+    sdpa_last_path() = 0;
     const int64_t rows = B * H * Lq;
     void *sbuf = nullptr, *pbuf = nullptr;
     AXB_TRY(axb_alloc((size_t)rows * Lk * 4, s, &sbuf));

@@ -23,7 +23,7 @@ struct Desc {
     int32_t nb;         // batch dims, index 0 = innermost
     int32_t act;        // 0 or a unary axb_op
     int32_t bias_dtype;
-    int32_t pad;
+    int32_t const_ops;  // AXB_MM_CONST_A / _B: the operand's derived forms may be cached (see split cache)
     int64_t bshape[kMaxBatchDims];
     int64_t a_bs[kMaxBatchDims], b_bs[kMaxBatchDims], c_bs[kMaxBatchDims], bias_bs[kMaxBatchDims];
 };
@@ -38,6 +38,13 @@ struct PresplitA {
 PresplitA &presplit_a_hint();
 
 int &last_path(); // per thread, see axb_matmul_last_path
+
+// Cache of operand forms derived from CONSTANT operands (today: the three-piece bf16 split of fp32 weights). Entries are
+// keyed by the operand's address and layout and dropped when the source memory is freed or written (allocator.cpp /
+// runtime.cpp call invalidate_const_cache; the glue announces in-place kernels through axb_invalidate_cached).
+void invalidate_const_cache(const void *ptr, size_t bytes);
+axb_const_cache_stats const_cache_stats();
+bool const_cache_active();
 
 // Runs the tensor-core path when the problem qualifies (sets *done), otherwise leaves it to the SIMT kernel.
 axb_status try_tcgen05(const Desc &d, int adt, int bdt, int cdt, DeviceCtx *ctx, cudaStream_t s, bool *done);

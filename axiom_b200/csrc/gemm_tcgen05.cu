@@ -23,6 +23,9 @@
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
+#include <mutex>
+#include <vector>
 
 #include "driver.h"
 #include "gemm.h"
@@ -940,6 +943,83 @@ axb_status run_split(const Desc &d, const char *src, int64_t rows, int64_t rs, i
 axb_status launch_ff(const CUtensorMap &ma, const CUtensorMap &mb, const TcParams &p, int sm_count, cudaStream_t s);
 int pick_bn(int64_t N);
 
+// ---- split cache: the pieces of a CONSTANT fp32 operand are computed once ----------------------------------------------
+// whisper's encoder re-split every Linear / conv weight on every forward (80 of its 164 launches, 12.6 % of the GPU time,
+// profiles/r1_launches_whisper_b8_s6.csv). An operand flagged AXB_MM_CONST_* keeps its [rows][3 * Kp] pieces in a device
+// buffer keyed by (address, layout); the entry dies when its source bytes are freed or overwritten.
+struct SplitKey {
+    const char *src;
+    int64_t rows, K, rs, cs, batch;
+    int64_t bs[kMaxBatchDims], bshape[kMaxBatchDims];
+    int32_t nb, device;
+    bool operator==(const SplitKey &o) const { return memcmp(this, &o, sizeof *this) == 0; }
+};
+struct SplitEntry {
+    SplitKey key;
+    const char *lo, *hi; // source byte range
+    void *pieces;
+    size_t bytes;
+    uint64_t tick;
+};
+std::mutex g_split_mu;
+std::vector<SplitEntry> g_split;
+std::atomic<int> g_split_n{0};
+axb_const_cache_stats g_split_stats{};
+uint64_t g_split_tick = 0;
+constexpr size_t kSplitCacheBytes = 4ull << 30;
+
+SplitKey split_key(const Desc &d, const char *src, int64_t rows, int64_t rs, int64_t cs, const int64_t *bs, bool batched, int device) {
+    SplitKey k;
+    memset(&k, 0, sizeof k);
+    k.src = src; k.rows = rows; k.K = d.K; k.rs = rs; k.cs = cs; k.device = device;
+    k.batch = batched ? d.batch : 1;
+    k.nb = batched ? d.nb : 0;
+    for (int i = 0; i < k.nb; ++i) {
+        k.bs[i] = bs[i];
+        k.bshape[i] = d.bshape[i];
+    }
+    return k;
+}
+// returns the cached pieces or nullptr
+void *split_cache_find(const SplitKey &k) {
+    if (g_split_n.load(std::memory_order_acquire) == 0)
+        return nullptr;
+    std::lock_guard<std::mutex> lk(g_split_mu);
+    for (auto &e : g_split)
+        if (e.key == k) {
+            e.tick = ++g_split_tick;
+            g_split_stats.hits++;
+            return e.pieces;
+        }
+    return nullptr;
+}
+void split_cache_insert(const SplitKey &k, void *pieces, size_t bytes, cudaStream_t s) {
+    // byte range the operand covers (non-negative strides only; others are never cached)
+    int64_t span = 4 + (k.rows - 1) * k.rs + (k.K - 1) * k.cs;
+    for (int i = 0; i < k.nb; ++i)
+        span += (k.bshape[i] - 1) * k.bs[i];
+    std::vector<void *> evict;
+    {
+        std::lock_guard<std::mutex> lk(g_split_mu);
+        g_split_stats.misses++;
+        g_split.push_back(SplitEntry{k, k.src, k.src + span, pieces, bytes, ++g_split_tick});
+        g_split_stats.bytes += bytes;
+        while (g_split_stats.bytes > kSplitCacheBytes && g_split.size() > 1) { // least recently used first
+            size_t v = 0;
+            for (size_t i = 1; i + 1 < g_split.size(); ++i)
+                if (g_split[i].tick < g_split[v].tick)
+                    v = i;
+            evict.push_back(g_split[v].pieces);
+            g_split_stats.bytes -= g_split[v].bytes;
+            g_split.erase(g_split.begin() + v);
+        }
+        g_split_stats.entries = g_split.size();
+        g_split_n.store((int)g_split.size(), std::memory_order_release);
+    }
+    for (void *q : evict)
+        axb_free(q, s);
+}
+
 axb_status try_split_f32(const Desc &d, DeviceCtx *ctx, cudaStream_t s, bool *done) {
     const PresplitA pre = presplit_a_hint();
     presplit_a_hint() = PresplitA{};
@@ -978,31 +1058,63 @@ axb_status try_split_f32(const Desc &d, DeviceCtx *ctx, cudaStream_t s, bool *do
     bool same_operand = !pre.ptr && d.a == d.b && d.M == d.N && d.a_rs == d.b_cs && d.a_cs == d.b_rs && a_b == b_b;
     for (int i = 0; i < d.nb && same_operand; ++i)
         same_operand = d.a_bs[i] == d.b_bs[i];
+    // constant operands (weights): pieces from the split cache; a miss computes them once and keeps them
+    auto cacheable = [&](int flag, int64_t rs, int64_t cs, const int64_t *bs, bool batched) {
+        if (!(d.const_ops & flag) || rs < 0 || cs < 0)
+            return false;
+        for (int i = 0; batched && i < d.nb; ++i)
+            if (bs[i] < 0)
+                return false;
+        return true;
+    };
+    const bool a_const = !pre.ptr && cacheable(AXB_MM_CONST_A, d.a_rs, d.a_cs, d.a_bs, a_b);
+    const bool b_const = !same_operand && cacheable(AXB_MM_CONST_B, d.b_cs, d.b_rs, d.b_bs, b_b);
+    SplitKey ka{}, kb{};
+    bool a_hit = false, b_hit = false;
+    if (a_const) {
+        ka = split_key(d, d.a, d.M, d.a_rs, d.a_cs, d.a_bs, a_b, ctx->device);
+        wa = split_cache_find(ka);
+        a_hit = wa != nullptr;
+    }
+    if (b_const) {
+        kb = split_key(d, d.b, d.N, d.b_cs, d.b_rs, d.b_bs, b_b, ctx->device);
+        wb = split_cache_find(kb);
+        b_hit = wb != nullptr;
+    }
     if (pre.ptr)
         wa = const_cast<uint16_t *>(pre.ptr);
-    else
+    else if (!wa)
         AXB_TRY(axb_alloc(a_bytes, s, &wa));
     axb_status st = AXB_OK;
     if (same_operand)
         wb = wa;
-    else
+    else if (!wb)
         st = axb_alloc(b_bytes, s, &wb);
     if (st != AXB_OK) {
-        if (!pre.ptr)
+        if (!pre.ptr && !a_hit)
             axb_free(wa, s);
         return st;
     }
+    bool a_keep = a_hit, b_keep = b_hit; // owned by the cache: not returned to the pool here
     auto cleanup = [&]() {
-        if (!pre.ptr)
+        if (!pre.ptr && !a_keep)
             axb_free(wa, s);
-        if (!same_operand)
+        if (!same_operand && !b_keep)
             axb_free(wb, s);
     };
     // A is [M][K] with strides (a_rs, a_cs); B is used as [N][K] with strides (b_cs, b_rs)
-    if (!pre.ptr)
+    if (!pre.ptr && !a_hit)
         st = run_split(d, d.a, d.M, d.a_rs, d.a_cs, d.a_bs, a_b, Kp, static_cast<uint16_t *>(wa), s);
-    if (st == AXB_OK && !same_operand)
+    if (st == AXB_OK && !same_operand && !b_hit)
         st = run_split(d, d.b, d.N, d.b_cs, d.b_rs, d.b_bs, b_b, Kp, static_cast<uint16_t *>(wb), s);
+    if (st == AXB_OK && a_const && !a_hit) {
+        split_cache_insert(ka, wa, a_bytes, s);
+        a_keep = true;
+    }
+    if (st == AXB_OK && b_const && !b_hit) {
+        split_cache_insert(kb, wb, b_bytes, s);
+        b_keep = true;
+    }
     // grouped stages need BN <= 128; they also carry more flops per loaded byte (131 vs 87 flop/B for the streamed 256-wide
     // tile), so the split path prefers 128-wide tiles whenever N > 64
     static const bool wide_split = getenv("AXB_SPLIT_BN256") != nullptr; // A/B switch
@@ -1113,6 +1225,35 @@ bool use_pair(const Desc &d, int bn, int sm_count) {
 int &last_path() {
     static thread_local int v = 0;
     return v;
+}
+
+void invalidate_const_cache(const void *ptr, size_t bytes) {
+    if (g_split_n.load(std::memory_order_acquire) == 0 || !ptr)
+        return;
+    const char *lo = static_cast<const char *>(ptr), *hi = lo + bytes;
+    std::vector<void *> dead;
+    {
+        std::lock_guard<std::mutex> lk(g_split_mu);
+        for (size_t i = 0; i < g_split.size();) {
+            if (g_split[i].lo < hi && lo < g_split[i].hi) {
+                dead.push_back(g_split[i].pieces);
+                g_split_stats.bytes -= g_split[i].bytes;
+                g_split_stats.invalidations++;
+                g_split.erase(g_split.begin() + i);
+            } else {
+                ++i;
+            }
+        }
+        g_split_stats.entries = g_split.size();
+        g_split_n.store((int)g_split.size(), std::memory_order_release);
+    }
+    for (void *q : dead)
+        axb_free(q, nullptr); // stream-ordered: GEMMs already queued on the backend stream still read valid pieces
+}
+bool const_cache_active() { return g_split_n.load(std::memory_order_acquire) != 0; }
+axb_const_cache_stats const_cache_stats() {
+    std::lock_guard<std::mutex> lk(g_split_mu);
+    return g_split_stats;
 }
 PresplitA &presplit_a_hint() {
     static thread_local PresplitA h;

@@ -313,6 +313,7 @@ axb_status axb_matmul(const axb_tensor *a, const axb_tensor *b, int transpose_a,
         return axb_fill(out, 0.0, stream);
     }
     if (epilogue) {
+        d.const_ops = epilogue->flags & (AXB_MM_CONST_A | AXB_MM_CONST_B);
         d.act = epilogue->activation;
         AXB_REQUIRE(d.act == 0 || d.act == AXB_OP_RELU || d.act == AXB_OP_GELU || d.act == AXB_OP_SILU ||
                         d.act == AXB_OP_SIGMOID || d.act == AXB_OP_TANH,
@@ -351,5 +352,14 @@ axb_status axb_matmul(const axb_tensor *a, const axb_tensor *b, int transpose_a,
 }
 
 int axb_matmul_last_path(void) { return axb::gemm::last_path(); }
+axb_status axb_invalidate_cached(const void *ptr, size_t bytes) {
+    axb::gemm::invalidate_const_cache(ptr, bytes);
+    return AXB_OK;
+}
+axb_status axb_get_const_cache_stats(axb_const_cache_stats *out) {
+    AXB_REQUIRE(out, AXB_ERR_INVALID, "axb_get_const_cache_stats: null out");
+    *out = axb::gemm::const_cache_stats();
+    return AXB_OK;
+}
 
 } // extern "C"

@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "axb_internal.h"
+#include "gemm.h"
 
 namespace axb {
 
@@ -247,6 +248,7 @@ axb_status axb_memcpy_h2d(void *dst, const void *src, size_t bytes, axb_stream_t
         return AXB_OK;
     cudaStream_t s;
     AXB_TRY(resolve_stream(stream, &s));
+    gemm::invalidate_const_cache(dst, bytes); // cached forms of overwritten constants
     AXB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, s));
     count_h2d(bytes);
     return AXB_OK;
@@ -267,6 +269,7 @@ axb_status axb_memcpy_d2d(void *dst, const void *src, size_t bytes, axb_stream_t
         return AXB_OK;
     cudaStream_t s;
     AXB_TRY(resolve_stream(stream, &s));
+    gemm::invalidate_const_cache(dst, bytes);
     AXB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, s));
     count_d2d(bytes);
     return AXB_OK;
@@ -276,6 +279,7 @@ axb_status axb_memset(void *dst, int value, size_t bytes, axb_stream_t stream) {
         return AXB_OK;
     cudaStream_t s;
     AXB_TRY(resolve_stream(stream, &s));
+    gemm::invalidate_const_cache(dst, bytes);
     AXB_CUDA(cudaMemsetAsync(dst, value, bytes, s));
     return AXB_OK;
 }

@@ -267,7 +267,7 @@ def rms_norm(x: DeviceArray, w: Optional[DeviceArray], axis: int = -1, eps: floa
 
 # ---- family 3 -------------------------------------------------------------------------------------
 def matmul(a: DeviceArray, b: DeviceArray, transpose_a: bool = False, transpose_b: bool = False,
-           bias: Optional[DeviceArray] = None, activation: Optional[str] = None) -> DeviceArray:
+           bias: Optional[DeviceArray] = None, activation: Optional[str] = None, const_ops: int = 0) -> DeviceArray:
     shape = (ctypes.c_int64 * capi.AXB_MAX_DIMS)()
     nd = ctypes.c_int32()
     ad, bd = a.desc(), b.desc()
@@ -275,8 +275,9 @@ def matmul(a: DeviceArray, b: DeviceArray, transpose_a: bool = False, transpose_
                                  ctypes.byref(nd)))
     out = DeviceArray.empty([shape[i] for i in range(nd.value)], lib().axb_promote_types(a.dtype, b.dtype))
     epi = None
-    if bias is not None or activation is not None:
+    if bias is not None or activation is not None or const_ops:
         e = capi.AxbMatmulEpilogue()
+        e.flags = const_ops
         bdesc = bias.desc() if bias is not None else None
         e.bias = ctypes.pointer(bdesc) if bdesc is not None else None
         e.activation = capi.OP[activation] if activation else 0

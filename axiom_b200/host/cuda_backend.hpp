@@ -74,8 +74,10 @@ inline int32_t to_axb_op(ops::OpType op) { return static_cast<int32_t>(op); } //
 Tensor gpu_unary(ops::OpType op, const Tensor &x, double param = 0.0);
 Tensor gpu_binary(ops::OpType op, const Tensor &a, const Tensor &b);
 Tensor gpu_reduce(ops::OpType op, const Tensor &x, const std::vector<int> &axes, bool keep_dims);
+// const_ops: AXB_MM_CONST_A / AXB_MM_CONST_B — the operand is a constant leaf of the graph (weights): libaxb may keep
+// derived forms of it (the fp32 three-piece split) until its storage is freed or written
 Tensor gpu_matmul(const Tensor &a, const Tensor &b, bool ta, bool tb, const Tensor *bias = nullptr,
-                  ops::OpType activation = ops::OpType::_Count);
+                  ops::OpType activation = ops::OpType::_Count, int const_ops = 0);
 Tensor gpu_softmax(const Tensor &x, int axis, bool is_log);
 Tensor gpu_where(const Tensor &c, const Tensor &a, const Tensor &b);
 Tensor gpu_masked_fill(const Tensor &x, const Tensor &mask, double value);

@@ -69,6 +69,20 @@ Tensor leaf_tensor(const GraphNode *n) {
     return Tensor();
 }
 
+// Which operands of a MatMul node are CONSTANT leaves of the graph in the weight position: 2-D tensors captured by value
+// (nn::Linear's weight, x.matmul(W)). Their storage only changes through paths that invalidate libaxb's caches (storage
+// release, copy_from, in-place ops), so the fp32 tensor-core path may keep their three-piece split across calls.
+int const_operands(const GraphNode *mm) {
+    int f = 0;
+    for (int i = 0; i < 2 && i < (int)mm->inputs.size(); ++i) {
+        const GraphNode *c = mm->inputs[i].get();
+        if (c && c->is_constant && c->constant_storage && c->output_shape.size() == 2 && c->output_dtype == DType::Float32 &&
+            c->constant_storage->device() == Device::GPU)
+            f |= i == 0 ? AXB_MM_CONST_A : AXB_MM_CONST_B;
+    }
+    return f;
+}
+
 struct Lowering;
 bool try_linear_epilogue(Lowering &L, const GraphNode *n);
 
@@ -206,7 +220,8 @@ struct Lowering {
         Tensor r;
         if (op == OpType::MatMul || op == OpType::BatchMatMul) {
             const auto &mp = get_params<MatMulParams>(n->params);
-            r = backends::cuda::gpu_matmul(input(n, 0), input(n, 1), mp.transpose_a, mp.transpose_b);
+            r = backends::cuda::gpu_matmul(input(n, 0), input(n, 1), mp.transpose_a, mp.transpose_b, nullptr, OpType::_Count,
+                                           const_operands(n));
         } else if (op == OpType::Softmax || op == OpType::LogSoftmax) {
             r = backends::cuda::gpu_softmax(input(n, 0), get_params<ActivationParams>(n->params).axis, op == OpType::LogSoftmax);
         } else if (op == OpType::LayerNorm) {
@@ -358,7 +373,7 @@ bool try_linear_epilogue(Lowering &L, const GraphNode *n) {
     const auto &mp = get_params<MatMulParams>(mm->params);
     Tensor a = L.input(mm, 0), b = L.input(mm, 1);
     Tensor bias_t = bias ? L.get(bias) : Tensor();
-    Tensor r = backends::cuda::gpu_matmul(a, b, mp.transpose_a, mp.transpose_b, bias ? &bias_t : nullptr, act);
+    Tensor r = backends::cuda::gpu_matmul(a, b, mp.transpose_a, mp.transpose_b, bias ? &bias_t : nullptr, act, const_operands(mm));
     if (r.shape() != n->output_shape)
         r = r.reshape(n->output_shape);
     L.value[n] = std::move(r);

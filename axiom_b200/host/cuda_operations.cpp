@@ -191,7 +191,7 @@ Tensor gpu_softmax(const Tensor &x_in, int axis, bool is_log) {
     return out;
 }
 
-Tensor gpu_matmul(const Tensor &a_in, const Tensor &b_in, bool ta, bool tb, const Tensor *bias, OpType activation) {
+Tensor gpu_matmul(const Tensor &a_in, const Tensor &b_in, bool ta, bool tb, const Tensor *bias, OpType activation, int const_ops) {
     const Tensor a = on_gpu(a_in), b = on_gpu(b_in);
     const axb_tensor ad = describe(a), bd = describe(b);
     int64_t oshape[AXB_MAX_DIMS];
@@ -214,7 +214,8 @@ Tensor gpu_matmul(const Tensor &a_in, const Tensor &b_in, bool ta, bool tb, cons
     }
     if (activation != OpType::_Count)
         epi.activation = to_axb_op(activation);
-    const bool use_epi = epi.bias || epi.activation;
+    epi.flags = const_ops;
+    const bool use_epi = epi.bias || epi.activation || epi.flags;
     check(axb_matmul(&ad, &bd, ta ? 1 : 0, tb ? 1 : 0, use_epi ? &epi : nullptr, &od, nullptr), "axb_matmul");
     return out;
 }
@@ -266,7 +267,9 @@ Tensor gpu_conv1d_impl(const Tensor &x_in, const Tensor &w_in, const Tensor &b_i
     Tensor out;
     const Tensor w2d = gpu_contiguous(wq).reshape({Cout, Cg * K}); // (C_out, C_in/groups * K)
     if (groups == 1) {
-        out = gpu_matmul(w2d, col, false, false); // {C_out, CK} x {N, CK, L_out} -> {N, C_out, L_out}
+        // the reshaped weight is a VIEW of the (constant) conv weight when that is contiguous: its split is cached
+        out = gpu_matmul(w2d, col, false, false, nullptr, OpType::_Count,
+                         w2d.storage() == w.storage() ? AXB_MM_CONST_A : 0); // {C_out, CK} x {N, CK, L_out} -> {N, C_out, L_out}
     } else {
         out = empty_gpu({N, Cout, Lout}, dt);
         const size_t cog = Cout / (size_t)groups;
@@ -364,6 +367,9 @@ class CudaOperation final : public ops::Operation {
         if (rdt != to_axb_dtype(lhs.dtype()) || broadcast2(lhs.shape(), r.shape()) != lhs.shape())
             throw TypeError("in-place " + op_name(type_) + ": result does not fit the left operand");
         const axb_tensor ld = describe(lhs), rd = describe(r);
+        // a kernel is about to overwrite lhs: cached forms of it (weight splits) are stale from here on
+        if (auto *cs = dynamic_cast<CudaStorage *>(lhs.storage().get()))
+            axb_invalidate_cached(cs->device_ptr(), cs->size_bytes());
         check(axb_binary(to_axb_op(type_), &ld, &rd, &ld, nullptr), "axb_binary (in place)");
     }
 
@@ -447,9 +453,13 @@ Tensor gpu_conv1d(const Tensor &input, const Tensor &weight, const Tensor &bias,
 Tensor gpu_scaled_dot_product_attention(const Tensor &query, const Tensor &key, const Tensor &value, const Tensor &mask,
                                         float scale, bool is_causal) {
     const Tensor q = on_gpu(query), k = on_gpu(key), v = on_gpu(value);
-    if (q.dtype() == DType::Float32 && k.dtype() == DType::Float32 && v.dtype() == DType::Float32) {
-        // one C-ABI call: Q K^T, fused scale + mask + softmax writing pre-split probabilities, P V (csrc/attention.cu)
-        Tensor out = empty_gpu({q.shape()[0], q.shape()[1], q.shape()[2], v.shape()[3]}, DType::Float32);
+    const bool f32 = q.dtype() == DType::Float32, half = q.dtype() == DType::BFloat16 || q.dtype() == DType::Float16;
+    const bool narrow = q.ndim() == 4 && v.ndim() == 4 && q.shape()[3] <= 64 && v.shape()[3] <= 64; // the flash kernel's head_dim range
+    if (k.dtype() == q.dtype() && v.dtype() == q.dtype() && (f32 || (half && narrow))) {
+        // one C-ABI call. head_dim <= 64: ONE tcgen05 kernel, online softmax, no score matrix (csrc/flash_attention.cu),
+        // fp32 through the exact three-piece split, bf16 / fp16 native; wider fp32 heads: Q K^T, fused scale + mask +
+        // softmax writing pre-split probabilities, P V (csrc/attention.cu)
+        Tensor out = empty_gpu({q.shape()[0], q.shape()[1], q.shape()[2], v.shape()[3]}, q.dtype());
         if (out.size() == 0)
             return out;
         Tensor m;

@@ -40,7 +40,7 @@ extern "C" {
 #endif
 
 #define AXB_MAX_DIMS 8
-#define AXB_ABI_VERSION 1
+#define AXB_ABI_VERSION 2
 
 typedef enum axb_status {
     AXB_OK = 0,
@@ -297,10 +297,22 @@ axb_status axb_elementwise_reduce(const axb_instr *prog, int n_instr, const axb_
  * (compiled_graph.hpp:54-58). NumPy batch broadcasting; transposes are folded into strides, never
  * materialised. out dtype == promote(a,b).
  * ---------------------------------------------------------------------------------------------- */
+#define AXB_MM_CONST_A 1 /* operand A is a constant (weights): derived operand forms may be cached */
+#define AXB_MM_CONST_B 2 /* operand B is a constant */
 typedef struct axb_matmul_epilogue {
     const axb_tensor *bias; /* NULL, or broadcastable to [.., M, N] (Linear: {N}) — nn/linear.cpp:22-25 */
     int32_t activation;     /* 0 = none, else a unary axb_op (RELU, GELU, SILU, SIGMOID, TANH) */
+    /* AXB_MM_CONST_*: the caller promises that the flagged operand's bytes only change through this library (axb_free of
+     * its block, axb_memcpy_* / axb_memset into it) or are announced with axb_invalidate_cached. The fp32 tensor-core path
+     * then keeps the operand's three-piece bf16 split (nn::Linear / conv weights) instead of re-splitting it per call. */
+    int32_t flags;
 } axb_matmul_epilogue;
+/* Drops every cached operand form derived from device memory overlapping [ptr, ptr + bytes) (in-place writes by kernels). */
+axb_status axb_invalidate_cached(const void *ptr, size_t bytes);
+typedef struct axb_const_cache_stats {
+    uint64_t entries, bytes, hits, misses, invalidations;
+} axb_const_cache_stats;
+axb_status axb_get_const_cache_stats(axb_const_cache_stats *out);
 axb_status axb_matmul(const axb_tensor *a, const axb_tensor *b, int transpose_a, int transpose_b,
                       const axb_matmul_epilogue *epilogue /* may be NULL */, const axb_tensor *out,
                       axb_stream_t stream);
@@ -327,10 +339,14 @@ axb_status axb_scatter(const axb_tensor *in, int dim, const axb_tensor *indices,
  * ops::scaled_dot_product_attention (src/tensor/operations.cpp:3979-4044) / cpu_flash_attention
  * (src/backends/cpu/flash_attention_cpu.cpp:18-131): q {B,H,Lq,D}, k {B,H,Lk,D}, v {B,H,Lk,Dv}, out {B,H,Lq,Dv}, Float32.
  * mask (may be NULL): Bool / 8-bit, broadcastable to {B,H,Lq,Lk}, NON-ZERO = position masked out; is_causal masks kv > q;
- * scale <= 0 means 1/sqrt(D). Three launches: Q K^T, fused scale+mask+softmax (probabilities written directly in the
- * pre-split bf16 layout of the next GEMM), P V. */
+ * scale <= 0 means 1/sqrt(D). head_dim <= 64: ONE tcgen05 kernel (flash_attention.cu: Q K^T and P V on the tensor cores, online
+ * softmax in registers, P handed to the second MMA through tensor memory, no score matrix in HBM) after a one-launch operand
+ * prologue; Float32 (exact three-piece bf16 split), BFloat16 and Float16 (native). Wider heads, Float32 only: three launches
+ * (Q K^T, fused scale+mask+softmax writing pre-split probabilities, P V). */
 axb_status axb_sdpa(const axb_tensor *q, const axb_tensor *k, const axb_tensor *v, const axb_tensor *mask /* may be NULL */,
                     float scale, int is_causal, const axb_tensor *out, axb_stream_t stream);
+/* Which path the LAST axb_sdpa of the calling thread took: 1 = single flash kernel, 0 = three-kernel path, -1 none yet. */
+int axb_sdpa_last_path(void);
 
 /* ---- convolution / padding data movement ("next" row: conv1d as GEMM) ------------------------------------------
  * Replaces the reference's naive conv1d loops (src/tensor/operations.cpp:3046-3135) together with axb_matmul:

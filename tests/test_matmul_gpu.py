@@ -241,3 +241,48 @@ def test_f32_tensor_core_split_is_fp32_accurate(gpu, case):
         a, b = rand_f32(rng, (512, 1024)), rand_f32(rng, (1024, 768))
         got = _mm(a, b)
     _close_f32(got, a, b, rtol=2e-6)
+
+
+def test_constant_operand_split_is_cached_and_invalidated(gpu):
+    """AXB_MM_CONST_B (nn::Linear weights): the fp32 three-piece split of B is computed once; overwriting B's bytes through
+    the library (or freeing its block) drops the cached pieces, so results always follow the CURRENT contents."""
+    import ctypes
+    L = capi.lib()
+    rng = np.random.default_rng(77)
+    x = rng.standard_normal((512, 384)).astype(np.float32)
+    w1 = rng.standard_normal((1536, 384)).astype(np.float32)
+    w2 = rng.standard_normal((1536, 384)).astype(np.float32)
+    dx, dw = dev.DeviceArray.from_numpy(x), dev.DeviceArray.from_numpy(w1)
+
+    def stats():
+        s = capi.AxbConstCacheStats()
+        capi.check(L.axb_get_const_cache_stats(ctypes.byref(s)))
+        return s
+
+    s0 = stats()
+    n0 = dev.launch_count()
+    y1 = dev.matmul(dx, dw, transpose_b=True, const_ops=capi.MM_CONST_B).numpy()
+    first = dev.launch_count() - n0
+    assert L.axb_matmul_last_path() == 3
+    s1 = stats()
+    assert s1.misses == s0.misses + 1 and s1.entries == s0.entries + 1
+    n0 = dev.launch_count()
+    y2 = dev.matmul(dx, dw, transpose_b=True, const_ops=capi.MM_CONST_B).numpy()
+    assert dev.launch_count() - n0 == first - 1, "the second call must skip the split of B"
+    s2 = stats()
+    assert s2.hits == s1.hits + 1
+    assert np.array_equal(y1, y2)
+    ref = x.astype(np.float64) @ w1.T.astype(np.float64)
+    assert np.allclose(y1, ref, rtol=1e-5, atol=1e-4)
+    # overwrite the weights in place (what Storage::copy_from does): the cached pieces must not survive
+    capi.check(L.axb_memcpy_h2d(ctypes.c_void_p(dw.storage.ptr), w2.ctypes.data_as(ctypes.c_void_p), w2.nbytes, None))
+    s3 = stats()
+    assert s3.invalidations == s2.invalidations + 1 and s3.entries == s2.entries - 1
+    y3 = dev.matmul(dx, dw, transpose_b=True, const_ops=capi.MM_CONST_B).numpy()
+    assert np.allclose(y3, x.astype(np.float64) @ w2.T.astype(np.float64), rtol=1e-5, atol=1e-4)
+    # releasing the operand's block drops its entry as well
+    e_before = stats().entries
+    del dw
+    import gc
+    gc.collect()
+    assert stats().entries == e_before - 1
