@@ -17,10 +17,11 @@
 //   warps 0..7    softmax      : two query tiles of 128 rows (warps 0-3 / 4-7), thread = row: tcgen05.ld of the 64 scores,
 //                                running max with LAZY rescaling (the accumulator is only rescaled when the max grows by
 //                                more than 2^8, so the TMEM round trip of O is rare), exp2, row sum, split of P into bf16
-//                                pieces written back to TMEM with tcgen05.st
-// TMEM per query tile (256 of the 512 columns): TWO score buffers of 64 columns, O 64, and the low pieces of P (2 x 32);
-// the hi / mid pieces of P(j) are written over the score buffer they were computed from, once its 64 scores sit in
-// registers. The MMA issuer runs two key blocks ahead of the softmax: Q K^T of block j+2 is issued right after P V of block
+//                                pieces written back to TMEM with tcgen05.st. P is carried as TWO pieces (hi + mid, 16
+//                                significand bits): its rounding errors are independent per key and average out over
+//                                the row (2^-17 / sqrt(keys) relative in O), so the P_lo . V_hi product is dropped
+// TMEM per query tile (256 of the 512 columns): TWO score buffers of 64 columns and O (64); the pieces of P(j) are
+// written over the score buffer they were computed from, once its 64 scores sit in registers. The MMA issuer runs two key blocks ahead of the softmax: Q K^T of block j+2 is issued right after P V of block
 // j (it reuses that score buffer; tcgen05.mma executes in issue order), so the softmax warps always find the next scores
 // ready and the tensor pipe never waits for one exp round trip (the first version was serialised per tile: softmax -> P V
 // -> Q K^T -> softmax, ncu: tensor pipe 39 % active, 0.229 ms on the whisper shape).
@@ -45,7 +46,7 @@ constexpr int NQT = 2;            // query tiles per CTA
 constexpr int KST = 2, VST = 2;   // ring depths
 constexpr int NUM_THREADS = 320;  // 8 softmax warps, TMA producer, MMA issuer
 constexpr uint32_t TMEM_COLS = 512;
-constexpr uint32_t COL_S = 0 /* + 64 * buf */, COL_PLO = 128 /* + 32 * buf */, COL_O = 192, COL_TILE = 256;
+constexpr uint32_t COL_S = 0 /* + 64 * buf */, COL_O = 192, COL_TILE = 256; // columns 128..191 of a tile are free
 constexpr int Q_PIECE = BQ * DP * 2;  // 16 KiB
 constexpr int KV_PIECE = BKV * DP * 2; // 8 KiB
 constexpr float LAZY = 8.0f;      // log2 units: P stays below 2^8
@@ -129,6 +130,14 @@ __device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sy
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
     return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
            ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46) | (2ull << 61);
+}
+// one lane of a fully converged warp (the warp runs the role's control flow uniformly, so descriptors and barrier addresses
+// stay in uniform registers; issuing from inside `if (lane == 0)` cost ~10 extra instructions per MMA: R2UR moves and an
+// ELECT retry loop per tcgen05.mma — more than the 32-48 cycles a 128x64x16 MMA takes to execute)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xFFFFFFFF;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred != 0;
 }
 __device__ __forceinline__ float ex2(float x) {
     float r;
@@ -274,70 +283,80 @@ fa_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUt
             }
         }
     } else if (warp == 9) {
-        // ===== MMA issuer =====
-        if (lane == 0) {
-            auto qk = [&](int t, int ks, int buf) { // S_t[buf] = Q_t K^T
+        // ===== MMA issuer: the whole warp walks the schedule, one elected lane issues =====
+        {
+            // descriptors: base + (byte offset >> 4) in the 14-bit start-address field (shared memory < 256 KiB: no carry)
+            const uint64_t qdesc0 = umma_desc(q_base, 16, 1024), kdesc0 = umma_desc(k_base, 16, 1024), vdesc0 = umma_desc(v_base, 8192, 1024);
+            auto qk = [&](int t, int ks, int buf, uint32_t bar_s, uint32_t bar_k /* 0: none */) { // S_t[buf] = Q_t K^T
                 const uint32_t d = tmem_base + t * COL_TILE + COL_S + buf * 64;
-                const uint32_t qa = q_base + t * Q_TILE, kb = k_base + ks * KV_STAGE;
+                const uint64_t qa = qdesc0 + (uint64_t)((t * Q_TILE) >> 4), kb = kdesc0 + (uint64_t)((ks * KV_STAGE) >> 4);
+                if (elect_one()) {
 #pragma unroll
-                for (int c = 0; c < NC; ++c) {
-                    const uint32_t pa = qa + (NP == 3 ? piece_a(c) : 0) * Q_PIECE, pb = kb + (NP == 3 ? piece_b(c) : 0) * KV_PIECE;
+                    for (int c = 0; c < NC; ++c) {
+                        const uint64_t pa = qa + (uint64_t)(((NP == 3 ? piece_a(c) : 0) * Q_PIECE) >> 4);
+                        const uint64_t pb = kb + (uint64_t)(((NP == 3 ? piece_b(c) : 0) * KV_PIECE) >> 4);
 #pragma unroll
-                    for (int k = 0; k < DP / 16; ++k)
-                        tc_mma_ss(d, umma_desc(pa + k * 32, 16, 1024), umma_desc(pb + k * 32, 16, 1024), p.idesc_qk, (c | k) != 0);
+                        for (int k = 0; k < DP / 16; ++k)
+                            tc_mma_ss(d, pa + (uint64_t)(k * 2), pb + (uint64_t)(k * 2), p.idesc_qk, (c | k) != 0);
+                    }
+                    tc_commit(bar_s);
+                    if (bar_k)
+                        tc_commit(bar_k);
                 }
+                __syncwarp();
             };
-            auto pv = [&](int t, int vs, int j) { // O_t += P_t(j) V   (A from tensor memory, B = V MN-major)
+            auto pv = [&](int t, int vs, int j, uint32_t bar_o, uint32_t bar_v /* 0: none */) { // O_t += P_t(j) V
                 const int buf = j & 1;
                 const uint32_t tb = tmem_base + t * COL_TILE, d = tb + COL_O;
-                // pieces of P(j): hi and mid over score buffer `buf`, lo in its own columns
-                const uint32_t ppc[3] = {tb + COL_S + buf * 64, tb + COL_S + buf * 64 + 32, tb + COL_PLO + buf * 32};
-                const uint32_t vb = v_base + vs * KV_STAGE;
+                // pieces of P(j) (hi, mid) sit over score buffer `buf`; five products, smallest first:
+                // P_hi V_lo, P_mid V_mid, P_mid V_hi, P_hi V_mid, P_hi V_hi   (P_lo V_hi is below the P rounding noise)
+                constexpr int NCP = NP == 3 ? 5 : 1;
+                const uint32_t pp0 = tb + COL_S + buf * 64;
+                const uint64_t vb = vdesc0 + (uint64_t)((vs * KV_STAGE) >> 4);
+                if (elect_one()) {
 #pragma unroll
-                for (int c = 0; c < NC; ++c) {
-                    const uint32_t pa = ppc[NP == 3 ? piece_a(c) : 0], pb = vb + (NP == 3 ? piece_b(c) : 0) * KV_PIECE;
+                    for (int c = 0; c < NCP; ++c) {
+                        const int ap = NP == 3 ? ((0x00110 >> (4 * c)) & 0xF) : 0; // c = 0..4: 0,1,1,0,0
+                        const int bp = NP == 3 ? ((0x01012 >> (4 * c)) & 0xF) : 0; // c = 0..4: 2,1,0,1,0
+                        const uint32_t pa = pp0 + ap * 32;
+                        const uint64_t pb = vb + (uint64_t)((bp * KV_PIECE) >> 4);
 #pragma unroll
-                    for (int k = 0; k < BKV / 16; ++k)
-                        tc_mma_ts(d, pa + k * 8, umma_desc(pb + k * 2048, 8192, 1024), p.idesc_pv, (j | c | k) != 0);
+                        for (int k = 0; k < BKV / 16; ++k)
+                            tc_mma_ts(d, pa + k * 8, pb + (uint64_t)(k * 128), p.idesc_pv, (j | c | k) != 0);
+                    }
+                    tc_commit(bar_o);
+                    if (bar_v)
+                        tc_commit(bar_v);
                 }
+                __syncwarp();
             };
+            const int last_tile = tile_on[1] ? 1 : 0;
             // scores of the first two key blocks, both tiles
             for (int jj = 0; jj < 2 && jj < nkv; ++jj) {
                 mbar_wait(k_full(jj % KST), 0);
-                for (int t = 0; t < NQT; ++t) {
-                    if (!tile_on[t])
-                        continue;
+                for (int t = 0; t <= last_tile; ++t) {
                     if (jj == 0)
                         mbar_wait(q_full(t), 0);
                     tc_fence_after();
-                    qk(t, jj % KST, jj & 1);
-                    tc_commit(s_full(t, jj & 1));
+                    qk(t, jj % KST, jj & 1, s_full(t, jj & 1), t == last_tile ? k_empty(jj % KST) : 0u);
                 }
-                tc_commit(k_empty(jj % KST));
             }
             for (int j = 0; j < nkv; ++j) {
                 const int vs = j % VST, ks2 = (j + 2) % KST;
                 const bool more = j + 2 < nkv;
-                for (int t = 0; t < NQT; ++t) {
-                    if (!tile_on[t])
-                        continue;
+                for (int t = 0; t <= last_tile; ++t) {
                     mbar_wait(p_full(t), (uint32_t)j & 1u); // P_t(j) written (over the scores of block j)
                     if (t == 0)
                         mbar_wait(v_full(vs), (uint32_t)(j / VST) & 1u);
                     tc_fence_after();
-                    pv(t, vs, j);
-                    tc_commit(o_done(t));
+                    pv(t, vs, j, o_done(t), t == last_tile ? v_empty(vs) : 0u);
                     if (more) { // scores of block j + 2 into the buffer P(j) is being read from: executes after P V above
                         if (t == 0)
                             mbar_wait(k_full(ks2), (uint32_t)((j + 2) / KST) & 1u);
                         tc_fence_after();
-                        qk(t, ks2, j & 1);
-                        tc_commit(s_full(t, j & 1));
+                        qk(t, ks2, j & 1, s_full(t, j & 1), t == last_tile ? k_empty(ks2) : 0u);
                     }
                 }
-                tc_commit(v_empty(vs));
-                if (more)
-                    tc_commit(k_empty(ks2));
             }
         }
     } else {
@@ -364,10 +383,11 @@ fa_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUt
                 float x[64];
                 float mx = -INFINITY;
                 const bool edge = kv0 + BKV > p.Lk || (p.causal && kv0 + BKV - 1 > q) || mrow != nullptr;
+                // x holds the RAW scores; the scale (> 0) is folded into the exponent: exp2(x * c - m), one FFMA per element
                 if (!edge) {
 #pragma unroll
                     for (int i = 0; i < 64; ++i) {
-                        x[i] = sr(i) * p.scale_log2;
+                        x[i] = sr(i);
                         mx = fmaxf(mx, x[i]);
                     }
                 } else {
@@ -377,10 +397,11 @@ fa_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUt
                         bool drop = kv >= p.Lk || (p.causal && kv > q);
                         if (mrow && kv < p.Lk)
                             drop = drop || mrow[(int64_t)kv * p.m_sk] != 0;
-                        x[i] = drop ? -INFINITY : sr(i) * p.scale_log2;
+                        x[i] = drop ? -INFINITY : sr(i);
                         mx = fmaxf(mx, x[i]);
                     }
                 }
+                mx *= p.scale_log2;
                 // lazy running max: keep the old reference point while the new maximum stays within 2^LAZY of it
                 const bool grow = mx > m_used + LAZY || (m_used == -INFINITY && mx > -INFINITY);
                 float alpha = 1.0f;
@@ -389,36 +410,20 @@ fa_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUt
                     m_used = mx;
                     l *= alpha;
                 }
-                // Every phase of o_done is consumed in order (a parity wait is only meaningful one phase ahead): P V of block
-                // j-1 has normally finished long before this point — it was issued when P(j-1) arrived and this warp has
-                // spent a whole score block since. Rare: the reference point moved -> rescale O_t (TMEM round trip).
-                if (j > 0) {
-                    mbar_wait(o_done(t), (uint32_t)(j - 1) & 1u);
-                    if (__any_sync(0xFFFFFFFFu, grow)) { // warp-uniform: tcgen05.ld / st are warp-collective
-                        tc_fence_after();
-#pragma unroll
-                        for (int hb = 0; hb < 2; ++hb) {
-                            uint32_t o[32];
-                            tc_ld32(lane_addr + COL_O + hb * 32, o);
-                            tc_wait_ld();
-#pragma unroll
-                            for (int i = 0; i < 32; ++i)
-                                o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-                            tc_st32(lane_addr + COL_O + hb * 32, o);
-                        }
-                    }
-                }
                 // exponentials, row sum, pieces of P -> tensor memory (column c of a piece holds kv = 2c, 2c + 1)
                 float sum = 0.0f;
 #pragma unroll
                 for (int hb = 0; hb < 2; ++hb) {
-                    uint32_t ph[16], pm[16], pl[16];
+                    uint32_t ph[16], pm[16];
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
-                        const float e0 = ex2(x[hb * 32 + 2 * i] - m_used), e1 = ex2(x[hb * 32 + 2 * i + 1] - m_used);
+                        const float e0 = ex2(fmaf(x[hb * 32 + 2 * i], p.scale_log2, -m_used)),
+                                    e1 = ex2(fmaf(x[hb * 32 + 2 * i + 1], p.scale_log2, -m_used));
                         sum += e0 + e1;
-                        if (NP == 3) {
-                            red::split3_pair(e0, e1, ph[i], pm[i], pl[i]);
+                        if (NP == 3) { // hi = bf16(e), mid = bf16(e - hi): the first two steps of the exact split
+                            asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(ph[i]) : "f"(e1), "f"(e0));
+                            const float r0 = e0 - __uint_as_float(ph[i] << 16), r1 = e1 - __uint_as_float(ph[i] & 0xFFFF0000u);
+                            asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(pm[i]) : "f"(r1), "f"(r0));
                         } else if (F16) {
                             ph[i] = (uint32_t)red::f2h(e0) | ((uint32_t)red::f2h(e1) << 16);
                         } else {
@@ -438,14 +443,29 @@ fa_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUt
                                        "r"(pm[5]), "r"(pm[6]), "r"(pm[7]), "r"(pm[8]), "r"(pm[9]), "r"(pm[10]), "r"(pm[11]), "r"(pm[12]),
                                        "r"(pm[13]), "r"(pm[14]), "r"(pm[15])
                                      : "memory");
-                        asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
-                                     ::"r"(lane_addr + COL_PLO + buf * 32 + hb * 16), "r"(pl[0]), "r"(pl[1]), "r"(pl[2]), "r"(pl[3]), "r"(pl[4]),
-                                       "r"(pl[5]), "r"(pl[6]), "r"(pl[7]), "r"(pl[8]), "r"(pl[9]), "r"(pl[10]), "r"(pl[11]), "r"(pl[12]),
-                                       "r"(pl[13]), "r"(pl[14]), "r"(pl[15])
-                                     : "memory");
                     }
                 }
                 l += sum;
+                // O_t: every phase of o_done is consumed in order (a parity wait is only meaningful one phase ahead), but as LATE
+                // as possible — P(j) went over score buffer j, which P V(j-1) does not touch, so only the rescale of O needs
+                // P V(j-1) to be complete, and by now it has had this whole score block of time (waiting here BEFORE the
+                // exponentials cost 45 % of the softmax warps' samples). Rare: the reference point moved -> TMEM round trip.
+                if (j > 0) {
+                    mbar_wait(o_done(t), (uint32_t)(j - 1) & 1u);
+                    if (__any_sync(0xFFFFFFFFu, grow)) { // warp-uniform: tcgen05.ld / st are warp-collective
+                        tc_fence_after();
+#pragma unroll
+                        for (int hb = 0; hb < 2; ++hb) {
+                            uint32_t o[32];
+                            tc_ld32(lane_addr + COL_O + hb * 32, o);
+                            tc_wait_ld();
+#pragma unroll
+                            for (int i = 0; i < 32; ++i)
+                                o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+                            tc_st32(lane_addr + COL_O + hb * 32, o);
+                        }
+                    }
+                }
                 tc_wait_st();
                 tc_fence_before();
                 __syncwarp();

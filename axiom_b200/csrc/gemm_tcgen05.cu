@@ -116,6 +116,15 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
                  : "memory");
 }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// One lane of a fully converged warp. The MMA-issuing warp runs its schedule warp-uniformly and only the tcgen05
+// instructions sit under this predicate: descriptors and barrier addresses then live in uniform registers. Issuing from
+// inside `if (lane == 0)` cost ~10 extra instructions per MMA (R2UR moves + an ELECT retry loop around every UTCHMMA,
+// profiles/r2_flash_attention_notes.txt) — as long as a 128x128x16 MMA runs.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xFFFFFFFF;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 
 // UMMA shared-memory descriptor (cute/arch/mma_sm100_desc.hpp SmemDescriptor): start>>4 [0,14), LBO>>4 [16,30),
 // SBO>>4 [32,46), version=1 [46,48), layout SWIZZLE_128B=2 [61,64).
@@ -448,7 +457,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        { // whole warp, one elected lane issues (see elect_one)
             int stage = 0, acc = 0;
             uint32_t phase = 0, acc_phase = 0;
             for (int64_t t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
@@ -460,26 +469,33 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                         mbar_wait(full_bar(stage), phase);
                         tc_fence_after();
                         const uint32_t sa = smem + stage * G_STAGE, sb = sa + 3 * A_BYTES;
+                        // descriptors: base + (byte offset >> 4) in the start-address field (shared memory < 256 KiB)
+                        const uint64_t da = umma_desc(sa, 16, 1024), db = umma_desc(sb, 16, 1024);
+                        if (elect_one()) {
 #pragma unroll
-                        for (int c = 0; c < 6; ++c) {
-                            // hi.hi (c == 5) accumulates in the tile's main accumulator; the five small products go to a
-                            // SECOND accumulator in the unused upper half of the tile's 256 TMEM columns and meet the big
-                            // sum only once, in the epilogue: interleaving them per k-block into one fp32 accumulator
-                            // lost their low bits against the running hi.hi sum (3.9e-6 |A||B| on the wide-range test).
-                            const uint32_t pa = sa + split_piece_a(c) * A_BYTES, pb = sb + split_piece_b(c) * (BN_ * BK * 2);
-                            const uint32_t dst = c == 5 ? tmem_d : tmem_d + 128u;
+                            for (int c = 0; c < 6; ++c) {
+                                // hi.hi (c == 5) accumulates in the tile's main accumulator; the five small products go to a
+                                // SECOND accumulator in the unused upper half of the tile's 256 TMEM columns and meet the big
+                                // sum only once, in the epilogue: interleaving them per k-block into one fp32 accumulator
+                                // lost their low bits against the running hi.hi sum (3.9e-6 |A||B| on the wide-range test).
+                                const uint64_t pa = da + (uint64_t)((split_piece_a(c) * A_BYTES) >> 4);
+                                const uint64_t pb = db + (uint64_t)((split_piece_b(c) * (BN_ * BK * 2)) >> 4);
+                                const uint32_t dst = c == 5 ? tmem_d : tmem_d + 128u;
 #pragma unroll
-                            for (int k = 0; k < BK / 16; ++k)
-                                tc_mma(dst, umma_desc(pa + k * 32, 16, 1024), umma_desc(pb + k * 32, 16, 1024), p.idesc,
-                                       c == 5 ? (kb | k) != 0 : (kb | c | k) != 0);
+                                for (int k = 0; k < BK / 16; ++k)
+                                    tc_mma(dst, pa + (uint64_t)(k * 2), pb + (uint64_t)(k * 2), p.idesc,
+                                           c == 5 ? (kb | k) != 0 : (kb | c | k) != 0);
+                            }
+                            tc_commit(empty_bar(stage));
+                            if (kb == num_kb - 1)
+                                tc_commit(tfull_bar(acc));
                         }
-                        tc_commit(empty_bar(stage));
+                        __syncwarp();
                         if (++stage == G_STAGES) {
                             stage = 0;
                             phase ^= 1u;
                         }
                     }
-                    tc_commit(tfull_bar(acc));
                     if (++acc == 2) {
                         acc = 0;
                         acc_phase ^= 1u;
@@ -490,22 +506,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                     mbar_wait(full_bar(stage), phase);
                     tc_fence_after();
                     const uint32_t sa = smem + stage * STAGE_BYTES, sb = sa + A_BYTES;
+                    // K-major SW128: rows of 128 B, 8-row groups 1024 B apart (SBO); a K step of 16 elements = +32 B.
+                    // MN-major SW128: 64-element MN chunks 8 KiB apart (LBO), 8-row K groups 1024 B apart (SBO);
+                    //                 a K step of 16 rows = +2048 B.
+                    const uint64_t da = A_MN ? umma_desc(sa, 64 * BK * 2, 1024) : umma_desc(sa, 16, 1024);
+                    const uint64_t db = B_MN ? umma_desc(sb, 64 * BK * 2, 1024) : umma_desc(sb, 16, 1024);
+                    if (elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < BK / 16; ++k) {
-                        // K-major SW128: rows of 128 B, 8-row groups 1024 B apart (SBO); a K step of 16 elements = +32 B.
-                        // MN-major SW128: 64-element MN chunks 8 KiB apart (LBO), 8-row K groups 1024 B apart (SBO);
-                        //                 a K step of 16 rows = +2048 B.
-                        const uint64_t ad = A_MN ? umma_desc(sa + k * 2048, 64 * BK * 2, 1024) : umma_desc(sa + k * 32, 16, 1024);
-                        const uint64_t bd = B_MN ? umma_desc(sb + k * 2048, 64 * BK * 2, 1024) : umma_desc(sb + k * 32, 16, 1024);
-                        tc_mma(tmem_d, ad, bd, p.idesc, (kb | k) != 0);
+                        for (int k = 0; k < BK / 16; ++k)
+                            tc_mma(tmem_d, da + (uint64_t)(k * (A_MN ? 128 : 2)), db + (uint64_t)(k * (B_MN ? 128 : 2)), p.idesc, (kb | k) != 0);
+                        tc_commit(empty_bar(stage)); // slot is free once these MMAs have read it
+                        if (kb == num_kb - 1)
+                            tc_commit(tfull_bar(acc)); // accumulator complete
                     }
-                    tc_commit(empty_bar(stage)); // slot is free once these MMAs have read it
+                    __syncwarp();
                     if (++stage == STAGES) {
                         stage = 0;
                         phase ^= 1u;
                     }
                 }
-                tc_commit(tfull_bar(acc)); // accumulator complete
                 if (++acc == 2) {
                     acc = 0;
                     acc_phase ^= 1u;
@@ -702,7 +721,7 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
             }
         }
     } else if (warp == 1) {
-        if (lane == 0 && rank == 0) {
+        if (rank == 0) { // whole warp of the leader CTA, one elected lane issues (see elect_one)
             int stage = 0, acc = 0;
             uint32_t phase = 0, acc_phase = 0;
             for (int64_t t = first; t < p.num_tiles; t += step) {
@@ -713,19 +732,22 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
                     mbar_wait(full_bar(stage), phase);
                     tc_fence_after();
                     const uint32_t sa = smem + stage * P_STAGE_BYTES, sb = sa + A_BYTES;
+                    const uint64_t da = A_MN ? umma_desc(sa, 64 * BK * 2, 1024) : umma_desc(sa, 16, 1024);
+                    const uint64_t db = B_MN ? umma_desc(sb, 64 * BK * 2, 1024) : umma_desc(sb, 16, 1024);
+                    if (elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < BK / 16; ++k) {
-                        const uint64_t ad = A_MN ? umma_desc(sa + k * 2048, 64 * BK * 2, 1024) : umma_desc(sa + k * 32, 16, 1024);
-                        const uint64_t bd = B_MN ? umma_desc(sb + k * 2048, 64 * BK * 2, 1024) : umma_desc(sb + k * 32, 16, 1024);
-                        tc_mma_pair(tmem_d, ad, bd, p.idesc, (kb | k) != 0);
+                        for (int k = 0; k < BK / 16; ++k)
+                            tc_mma_pair(tmem_d, da + (uint64_t)(k * (A_MN ? 128 : 2)), db + (uint64_t)(k * (B_MN ? 128 : 2)), p.idesc, (kb | k) != 0);
+                        tc_commit_pair(empty_bar(stage));
+                        if (kb == num_kb - 1)
+                            tc_commit_pair(tfull_bar(acc));
                     }
-                    tc_commit_pair(empty_bar(stage));
+                    __syncwarp();
                     if (++stage == P_STAGES) {
                         stage = 0;
                         phase ^= 1u;
                     }
                 }
-                tc_commit_pair(tfull_bar(acc));
                 if (++acc == 2) {
                     acc = 0;
                     acc_phase ^= 1u;
