@@ -66,6 +66,10 @@ class AxbTransferStats(ctypes.Structure):
                 ("h2d_bytes", "h2d_calls", "d2h_bytes", "d2h_calls", "d2d_bytes", "d2d_calls")]
 
 
+class AxbPlanCacheStats(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_uint64) for n in ("entries", "hits", "misses", "evictions")]
+
+
 class AxbJitStats(ctypes.Structure):
     _fields_ = [(n, ctypes.c_uint64) for n in ("mem_hits", "disk_hits", "compiles")]
 
@@ -144,6 +148,8 @@ def lib() -> ctypes.CDLL:
         "axb_elementwise": (i32, [I, i32, T, i32, T, vp]),
         "axb_elementwise_precompile": (i32, [I, i32, T, i32, T]),
         "axb_get_jit_stats": (i32, [ctypes.POINTER(AxbJitStats)]),
+        "axb_get_plan_cache_stats": (i32, [ctypes.POINTER(AxbPlanCacheStats)]),
+        "axb_plan_cache_clear": (i32, []),
         "axb_promote_types": (i32, [i32, i32]),
         "axb_binary_result_dtype": (i32, [i32, i32, i32]),
         "axb_unary_result_dtype": (i32, [i32, i32]),

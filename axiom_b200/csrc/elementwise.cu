@@ -4,6 +4,8 @@
 //
 // Semantics follow the reference op by op (file:line in each rule below); see include/axb.h.
 #include <algorithm>
+#include <unordered_map>
+#include <mutex>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -985,6 +987,133 @@ axb_status prepare(const axb_instr *prog, int n_instr, const axb_tensor *inputs,
     return AXB_OK;
 }
 
+
+// ---- launch-plan cache -------------------------------------------------------------------------------------------------
+// A fused-chain launch is fully determined by the program (ops, dtypes, operand selectors, immediates) and by the LAYOUT
+// of every operand (dtype, shape, byte strides, 16-byte alignment class of its address) — never by the addresses
+// themselves. prepare() (validation, iteration-space collapse, statement generation, kernel lookup by source hash) costs
+// tens of microseconds per call, as much as the kernels the graph lowering launches; the plan cache keeps its result
+// (kernel handle + Params with stale pointers + grid) under a hash of exactly those inputs, and a hit only patches the
+// operand pointers. This is the per-launch half of the plan cache of SURVEY.md §8 a3 (the graph-level half lives in the
+// C++ glue, host/cuda_graph.cpp); reference counterpart: the per-signature MPSGraph cache, mpsgraph_fused.mm:373-377.
+struct PlanKeyOperand {
+    int32_t dtype, ndim;
+    uint32_t align; // address & 15
+    int64_t shape[AXB_MAX_DIMS], strides[AXB_MAX_DIMS];
+};
+struct PlanEntry {
+    std::vector<unsigned char> key;
+    Params p;
+    jit::Kernel kernel;
+    int unroll, device;
+    uint64_t tick;
+};
+std::mutex g_plan_mu;
+std::unordered_map<uint64_t, std::vector<PlanEntry>> g_plans; // hash -> entries (full key compared)
+size_t g_plan_count = 0;
+uint64_t g_plan_tick = 0;
+axb_plan_cache_stats g_plan_stats{};
+constexpr size_t kMaxPlans = 4096;
+
+void plan_key(const axb_instr *prog, int n_instr, const axb_tensor *inputs, int n_inputs, const axb_tensor *out, int reduce_opk,
+              int device, std::vector<unsigned char> *key, uint64_t *hash) {
+    key->clear();
+    auto put = [&](const void *q, size_t n) {
+        const unsigned char *b = static_cast<const unsigned char *>(q);
+        key->insert(key->end(), b, b + n);
+    };
+    const int32_t head[4] = {n_instr, n_inputs, reduce_opk, device};
+    put(head, sizeof head);
+    for (int i = 0; i < n_instr; ++i) {
+        put(&prog[i].op, 4);
+        put(&prog[i].dtype, 4);
+        put(prog[i].src, 12);
+        put(&prog[i].imm, 8);
+    }
+    for (int k = 0; k <= n_inputs; ++k) {
+        const axb_tensor &t = k < n_inputs ? inputs[k] : *out;
+        const int32_t h2[2] = {t.dtype, t.ndim};
+        put(h2, sizeof h2);
+        const uint32_t al = (uint32_t)(reinterpret_cast<uintptr_t>(tensor_ptr(t)) & 15u);
+        put(&al, 4);
+        put(t.shape, sizeof(int64_t) * (size_t)std::max(t.ndim, 0));
+        put(t.strides, sizeof(int64_t) * (size_t)std::max(t.ndim, 0));
+    }
+    uint64_t h = 1469598103934665603ull;
+    for (unsigned char c : *key) {
+        h ^= c;
+        h *= 1099511628211ull;
+    }
+    *hash = h;
+}
+
+// Looks the launch up (or prepares and inserts it). On return P holds Params with CURRENT pointers, *k the kernel.
+axb_status plan_lookup(const axb_instr *prog, int n_instr, const axb_tensor *inputs, int n_inputs, const axb_tensor *out,
+                       int reduce_opk, const char *name, int device, Prepared *P, jit::Kernel *k, bool *empty) {
+    *empty = false;
+    static const bool off = getenv("AXB_NO_PLAN_CACHE") != nullptr; // A/B switch
+    bool sane = !off && prog && out && n_instr > 0 && n_instr <= AXB_MAX_INSTRS && n_inputs >= 0 && n_inputs <= AXB_MAX_INPUTS &&
+                (n_inputs == 0 || inputs) && out->ndim >= 0 && out->ndim <= AXB_MAX_DIMS && out->base;
+    for (int i = 0; sane && i < n_inputs; ++i)
+        sane = inputs[i].ndim >= 0 && inputs[i].ndim <= AXB_MAX_DIMS && inputs[i].base;
+    std::vector<unsigned char> key;
+    uint64_t h = 0;
+    if (sane) {
+        plan_key(prog, n_instr, inputs, n_inputs, out, reduce_opk, device, &key, &h);
+        std::lock_guard<std::mutex> lk(g_plan_mu);
+        auto it = g_plans.find(h);
+        if (it != g_plans.end())
+            for (auto &e : it->second)
+                if (e.key == key) {
+                    e.tick = ++g_plan_tick;
+                    g_plan_stats.hits++;
+                    P->p = e.p;
+                    P->unroll = e.unroll;
+                    for (int i = 0; i < n_inputs; ++i)
+                        P->p.in[i].ptr = tensor_ptr(inputs[i]);
+                    P->p.out.ptr = tensor_ptr(*out);
+                    *k = e.kernel;
+                    return AXB_OK;
+                }
+    }
+    // miss (or an argument set the validation inside prepare() has to reject with its own message)
+    AXB_TRY(prepare(prog, n_instr, inputs, n_inputs, out, P, empty, reduce_opk));
+    if (*empty)
+        return AXB_OK;
+    AXB_TRY(jit::get_kernel(P->source, name, device, k));
+    if (sane) {
+        std::lock_guard<std::mutex> lk(g_plan_mu);
+        g_plan_stats.misses++;
+        if (g_plan_count >= kMaxPlans) { // full: drop the least recently used half
+            std::vector<uint64_t> ticks;
+            for (auto &kv : g_plans)
+                for (auto &e : kv.second)
+                    ticks.push_back(e.tick);
+            std::nth_element(ticks.begin(), ticks.begin() + ticks.size() / 2, ticks.end());
+            const uint64_t cut = ticks[ticks.size() / 2];
+            for (auto it = g_plans.begin(); it != g_plans.end();) {
+                auto &v = it->second;
+                v.erase(std::remove_if(v.begin(), v.end(), [&](const PlanEntry &e) { return e.tick < cut; }), v.end());
+                it = v.empty() ? g_plans.erase(it) : std::next(it);
+            }
+            g_plan_count = 0;
+            for (auto &kv : g_plans)
+                g_plan_count += kv.second.size();
+            g_plan_stats.evictions++;
+        }
+        PlanEntry e;
+        e.key = std::move(key);
+        e.p = P->p;
+        e.kernel = *k;
+        e.unroll = P->unroll;
+        e.device = device;
+        e.tick = ++g_plan_tick;
+        g_plans[h].push_back(std::move(e));
+        g_plan_stats.entries = ++g_plan_count;
+    }
+    return AXB_OK;
+}
+
 } // namespace ew
 } // namespace axb
 
@@ -995,16 +1124,15 @@ extern "C" {
 
 axb_status axb_elementwise(const axb_instr *prog, int n_instr, const axb_tensor *inputs, int n_inputs,
                            const axb_tensor *out, axb_stream_t stream) {
-    Prepared P;
-    bool empty = false;
-    AXB_TRY(prepare(prog, n_instr, inputs, n_inputs, out, &P, &empty));
-    if (empty)
-        return AXB_OK;
     cudaStream_t s;
     DeviceCtx *ctx;
     AXB_TRY(resolve_stream(stream, &s, &ctx));
+    Prepared P;
+    bool empty = false;
     jit::Kernel k;
-    AXB_TRY(jit::get_kernel(P.source, "axb_ew", ctx->device, &k));
+    AXB_TRY(plan_lookup(prog, n_instr, inputs, n_inputs, out, -1, "axb_ew", ctx->device, &P, &k, &empty));
+    if (empty)
+        return AXB_OK;
     const int threads = 256;
     int64_t blocks = ((int64_t)P.p.total_vec + (int64_t)threads * P.unroll - 1) / ((int64_t)threads * P.unroll);
     if (blocks < 1)
@@ -1012,6 +1140,20 @@ axb_status axb_elementwise(const axb_instr *prog, int n_instr, const axb_tensor 
     void *args[] = {&P.p};
     AXB_TRY(jit::launch(k, (unsigned)blocks, threads, 0, s, args));
     count_launch();
+    return AXB_OK;
+}
+
+axb_status axb_get_plan_cache_stats(axb_plan_cache_stats *out) {
+    AXB_REQUIRE(out, AXB_ERR_INVALID, "axb_get_plan_cache_stats: null out");
+    std::lock_guard<std::mutex> lk(g_plan_mu);
+    *out = g_plan_stats;
+    return AXB_OK;
+}
+axb_status axb_plan_cache_clear(void) {
+    std::lock_guard<std::mutex> lk(g_plan_mu);
+    g_plans.clear();
+    g_plan_count = 0;
+    g_plan_stats = axb_plan_cache_stats{};
     return AXB_OK;
 }
 
@@ -1028,10 +1170,9 @@ axb_status launch_chain_reduce(const axb_instr *prog, int n_instr, const axb_ten
     bool empty = false;
     axb_tensor od = *shape_desc;
     od.base = reinterpret_cast<void *>(uintptr_t(256)); // never dereferenced: the kernel only writes the partials
-    AXB_TRY(prepare(prog, n_instr, inputs, n_inputs, &od, &P, &empty, reduce_opk));
-    AXB_REQUIRE(!empty, AXB_ERR_INVALID, "axb_elementwise_reduce: empty chain");
     jit::Kernel k;
-    AXB_TRY(jit::get_kernel(P.source, "axb_ew_red", ctx->device, &k));
+    AXB_TRY(plan_lookup(prog, n_instr, inputs, n_inputs, &od, reduce_opk, "axb_ew_red", ctx->device, &P, &k, &empty));
+    AXB_REQUIRE(!empty, AXB_ERR_INVALID, "axb_elementwise_reduce: empty chain");
     const int threads = 256;
     int64_t blocks = ((int64_t)P.p.total_vec + (int64_t)threads * P.unroll - 1) / ((int64_t)threads * P.unroll);
     if (blocks < 1)

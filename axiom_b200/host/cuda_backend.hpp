@@ -30,6 +30,9 @@ namespace cuda {
 class CudaStorage : public Storage {
   public:
     explicit CudaStorage(size_t size_bytes);
+    // takes ownership of a block that came from axb_alloc on the current device (plan replay, cuda_plan.cpp)
+    struct Adopt {};
+    CudaStorage(void *adopted, size_t size_bytes, Adopt);
     ~CudaStorage() override;
     CudaStorage(const CudaStorage &) = delete;
     CudaStorage &operator=(const CudaStorage &) = delete;

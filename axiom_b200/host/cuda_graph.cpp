@@ -27,10 +27,12 @@
 #include "axiom/graph/graph_node.hpp"
 #include "backends/metal/metal_operations.hpp"
 #include "cuda_backend.hpp"
+#include "cuda_plan.hpp"
 
 namespace axiom {
 namespace graph {
 
+namespace plan = backends::cuda::plan;
 using backends::cuda::check;
 using backends::cuda::describe;
 using backends::cuda::empty_gpu;
@@ -181,11 +183,10 @@ struct Lowering {
         for (size_t i = 0; i < pg.inputs.size(); ++i)
             ins[i] = describe(get(pg.inputs[i]));
         if (reduce_op < 0)
-            check(axb_elementwise(pg.instrs.data(), (int)pg.instrs.size(), ins.data(), (int)ins.size(), &out, nullptr),
+            check(plan::elementwise(pg.instrs.data(), (int)pg.instrs.size(), ins.data(), (int)ins.size(), &out),
                   "axb_elementwise");
         else
-            check(axb_elementwise_reduce(pg.instrs.data(), (int)pg.instrs.size(), ins.data(), (int)ins.size(), reduce_op, &out,
-                                         nullptr),
+            check(plan::elementwise_reduce(pg.instrs.data(), (int)pg.instrs.size(), ins.data(), (int)ins.size(), reduce_op, &out),
                   "axb_elementwise_reduce");
     }
 
@@ -276,7 +277,7 @@ struct Lowering {
                 for (auto &t : ops_t)
                     ins.push_back(describe(t));
                 const axb_tensor od = describe(r);
-                check(axb_elementwise(pr.data(), (int)pr.size(), ins.data(), (int)ins.size(), &od, nullptr), "axb_elementwise (batch_norm)");
+                check(plan::elementwise(pr.data(), (int)pr.size(), ins.data(), (int)ins.size(), &od), "axb_elementwise (batch_norm)");
             }
         } else if (op == OpType::Reshape) {
             Tensor x = input(n, 0);
@@ -311,7 +312,7 @@ struct Lowering {
             r = empty_gpu(n->output_shape, n->output_dtype);
             const axb_tensor ins[2] = {describe(a), describe(b)}, od = describe(r);
             if (r.size() != 0)
-                check(axb_elementwise(pr, 2, ins, 2, &od, nullptr), "axb_elementwise (glu)");
+                check(plan::elementwise(pr, 2, ins, 2, &od), "axb_elementwise (glu)");
         } else if (is_reduction_op(op)) {
             const auto &rp = get_params<ReductionParams>(n->params);
             const GraphNode *c = n->inputs.at(0).get();
@@ -415,19 +416,30 @@ void materialize_gpu_graph(GraphNode *root) {
         return;
     backends::cuda::ensure_initialized();
     materialize_shared_below(root); // 1. shared sub-DAGs first: their results stay available to other consumers
-    // 2. lower the remaining tree
-    Lowering L;
-    L.eval(root);
-    Tensor out = L.get(root);
-    // 3. the node caches (storage, shape, strides) with offset 0 (graph_registry.cpp:323-331): views that start inside
-    //    another tensor's storage are gathered into a fresh one
-    if (out.offset() != 0) {
-        Tensor c = empty_gpu(out.shape(), out.dtype());
-        if (c.size() != 0) {
-            const axb_tensor sd = describe(out), dd = describe(c);
-            check(axb_gather_strided(&sd, &dd, nullptr), "axb_gather_strided");
+    // 2. plan cache (cuda_plan.hpp): signature + leaf layout -> recorded C-ABI call sequence. A hit replays it with the
+    //    current leaf pointers; a miss lowers the remaining tree with the recorder on.
+    Tensor out;
+    if (!plan::try_replay(root, &out)) {
+        plan::begin_record(root);
+        try {
+            Lowering L;
+            L.eval(root);
+            out = L.get(root);
+            // 3. the node caches (storage, shape, strides) with offset 0 (graph_registry.cpp:323-331): views that start
+            //    inside another tensor's storage are gathered into a fresh one
+            if (out.offset() != 0) {
+                Tensor c = empty_gpu(out.shape(), out.dtype());
+                if (c.size() != 0) {
+                    const axb_tensor sd = describe(out), dd = describe(c);
+                    check(plan::gather_strided(&sd, &dd), "axb_gather_strided");
+                }
+                out = c;
+            }
+        } catch (...) {
+            plan::end_record(nullptr, false);
+            throw;
         }
-        out = c;
+        plan::end_record(&out, true);
     }
     root->cached_result_ = out.storage();
     root->cached_shape_ = out.shape();
@@ -597,7 +609,7 @@ bool execute_gpu_fused_chain(const StepBase &step, const std::vector<ops::OpType
         for (size_t i = 0; i < inputs.size(); ++i)
             ins[i] = describe(inputs[i]);
         const axb_tensor od = describe(out);
-        check(axb_elementwise(prog.data(), (int)prog.size(), ins.data(), (int)ins.size(), &od, nullptr), "axb_elementwise");
+        check(plan::elementwise(prog.data(), (int)prog.size(), ins.data(), (int)ins.size(), &od), "axb_elementwise");
     }
     buffers[step.output_slot] = out;
     return true;
@@ -622,7 +634,7 @@ bool execute_gpu_fused_reduction(const FusedReductionStep &step, std::vector<Ten
     for (size_t i = 0; i < inputs.size(); ++i)
         ins[i] = describe(inputs[i]);
     const axb_tensor od = describe(out);
-    check(axb_elementwise_reduce(prog.data(), (int)prog.size(), ins.data(), (int)ins.size(), to_axb_op(rop), &od, nullptr),
+    check(plan::elementwise_reduce(prog.data(), (int)prog.size(), ins.data(), (int)ins.size(), to_axb_op(rop), &od),
           "axb_elementwise_reduce");
     buffers[step.output_slot] = out;
     return true;

@@ -10,6 +10,7 @@
 #include "axiom/operations.hpp"
 #include "backends/metal/metal_operations.hpp"
 #include "cuda_backend.hpp"
+#include "cuda_plan.hpp"
 
 namespace axiom {
 namespace backends {
@@ -69,7 +70,7 @@ Tensor gpu_unary(OpType op, const Tensor &x_in, double param) {
     if (out.size() == 0)
         return out;
     const axb_tensor xd = describe(x), od = describe(out);
-    check(axb_unary(to_axb_op(op), &xd, &od, param, nullptr), "axb_unary");
+    check(plan::unary(to_axb_op(op), &xd, &od, param), "axb_unary");
     return out;
 }
 
@@ -82,7 +83,7 @@ Tensor gpu_binary(OpType op, const Tensor &a_in, const Tensor &b_in) {
     if (out.size() == 0)
         return out;
     const axb_tensor ad = describe(a), bd = describe(b), od = describe(out);
-    check(axb_binary(to_axb_op(op), &ad, &bd, &od, nullptr), "axb_binary");
+    check(plan::binary(to_axb_op(op), &ad, &bd, &od), "axb_binary");
     return out;
 }
 
@@ -95,7 +96,7 @@ Tensor gpu_where(const Tensor &c_in, const Tensor &a_in, const Tensor &b_in) {
     if (out.size() == 0)
         return out;
     const axb_tensor cd = describe(c), ad = describe(a), bd = describe(b), od = describe(out);
-    check(axb_where(&cd, &ad, &bd, &od, nullptr), "axb_where");
+    check(plan::where(&cd, &ad, &bd, &od), "axb_where");
     return out;
 }
 
@@ -105,7 +106,7 @@ Tensor gpu_masked_fill(const Tensor &x_in, const Tensor &m_in, double value) {
     if (out.size() == 0)
         return out;
     const axb_tensor xd = describe(x), md = describe(m), od = describe(out);
-    check(axb_masked_fill(&xd, &md, value, &od, nullptr), "axb_masked_fill");
+    check(plan::masked_fill(&xd, &md, value, &od), "axb_masked_fill");
     return out;
 }
 
@@ -115,7 +116,7 @@ Tensor gpu_cast(const Tensor &x_in, DType to) {
     if (out.size() == 0)
         return out;
     const axb_tensor xd = describe(x), od = describe(out);
-    check(axb_cast(&xd, &od, nullptr), "axb_cast");
+    check(plan::cast(&xd, &od), "axb_cast");
     return out;
 }
 
@@ -126,7 +127,7 @@ Tensor gpu_contiguous(const Tensor &x) {
     if (out.size() == 0)
         return out;
     const axb_tensor xd = describe(x), od = describe(out);
-    check(axb_gather_strided(&xd, &od, nullptr), "axb_gather_strided");
+    check(plan::gather_strided(&xd, &od), "axb_gather_strided");
     return out;
 }
 
@@ -154,7 +155,7 @@ Tensor gpu_reduce(OpType op, const Tensor &x_in, const std::vector<int> &axes_in
         }
         Tensor out = empty_gpu(oshape, DType::Int64);
         const axb_tensor xd = describe(x), od = describe(out);
-        check(axb_argreduce(to_axb_op(op), &xd, flat ? -1 : ax, keep_dims ? 1 : 0, &od, nullptr), "axb_argreduce");
+        check(plan::argreduce(to_axb_op(op), &xd, flat ? -1 : ax, keep_dims ? 1 : 0, &od), "axb_argreduce");
         return out;
     }
     std::vector<int32_t> axes;
@@ -171,7 +172,7 @@ Tensor gpu_reduce(OpType op, const Tensor &x_in, const std::vector<int> &axes_in
     DType odt = static_cast<DType>(rdt);
     Tensor out = empty_gpu(reduced_shape(x.shape(), axes_in, keep_dims, false), odt);
     const axb_tensor xd = describe(x), od = describe(out);
-    check(axb_reduce(to_axb_op(op), &xd, axes.data(), (int)axes.size(), keep_dims ? 1 : 0, &od, nullptr), "axb_reduce");
+    check(plan::reduce(to_axb_op(op), &xd, axes.data(), (int)axes.size(), keep_dims ? 1 : 0, &od), "axb_reduce");
     // the graph declares Mean -> Float32 for every non-f64 input (graph_registry.cpp:278-287) and the executor upcasts
     // half results (graph_executor.cpp:396-403); integer means arrive as Float32 from axb_reduce already
     if (op == OpType::Mean && (out.dtype() == DType::Float16 || out.dtype() == DType::BFloat16))
@@ -187,7 +188,7 @@ Tensor gpu_softmax(const Tensor &x_in, int axis, bool is_log) {
     if (out.size() == 0)
         return out;
     const axb_tensor xd = describe(x), od = describe(out);
-    check(axb_softmax(&xd, axis, is_log ? 1 : 0, &od, nullptr), "axb_softmax");
+    check(plan::softmax(&xd, axis, is_log ? 1 : 0, &od), "axb_softmax");
     return out;
 }
 
@@ -216,7 +217,7 @@ Tensor gpu_matmul(const Tensor &a_in, const Tensor &b_in, bool ta, bool tb, cons
         epi.activation = to_axb_op(activation);
     epi.flags = const_ops;
     const bool use_epi = epi.bias || epi.activation || epi.flags;
-    check(axb_matmul(&ad, &bd, ta ? 1 : 0, tb ? 1 : 0, use_epi ? &epi : nullptr, &od, nullptr), "axb_matmul");
+    check(plan::matmul(&ad, &bd, ta ? 1 : 0, tb ? 1 : 0, use_epi ? &epi : nullptr, &od), "axb_matmul");
     return out;
 }
 
@@ -235,7 +236,7 @@ Tensor gpu_pad_constant(const Tensor &x_in, const std::vector<std::pair<size_t, 
     if (out.size() == 0)
         return out;
     const axb_tensor xd = describe(x), od = describe(out);
-    check(axb_pad_constant(&xd, lo, hi, value, &od, nullptr), "axb_pad_constant");
+    check(plan::pad_constant(&xd, lo, hi, value, &od), "axb_pad_constant");
     return out;
 }
 
@@ -262,7 +263,7 @@ Tensor gpu_conv1d_impl(const Tensor &x_in, const Tensor &w_in, const Tensor &b_i
     Tensor col = empty_gpu({N, C * K, Lout}, dt);
     {
         const axb_tensor xd = describe(x), cd = describe(col);
-        check(axb_im2col_1d(&xd, (int)K, stride, padding, dilation, &cd, nullptr), "axb_im2col_1d");
+        check(plan::im2col_1d(&xd, (int)K, stride, padding, dilation, &cd), "axb_im2col_1d");
     }
     Tensor out;
     const Tensor w2d = gpu_contiguous(wq).reshape({Cout, Cg * K}); // (C_out, C_in/groups * K)
@@ -280,7 +281,7 @@ Tensor gpu_conv1d_impl(const Tensor &x_in, const Tensor &w_in, const Tensor &b_i
             Tensor dst = out.slice({Slice(), Slice((int64_t)(g * cog), (int64_t)((g + 1) * cog)), Slice()});
             // strided store of the group's block: out_view = og (elementwise copy honours the view's strides)
             const axb_tensor sd = describe(og), dd = describe(dst);
-            check(axb_gather_strided(&sd, &dd, nullptr), "conv1d group store");
+            check(plan::gather_strided(&sd, &dd), "conv1d group store");
         }
     }
     if (b_in.storage() && b_in.size() > 0) {
@@ -405,6 +406,7 @@ void register_cuda_operations() {
 
 // ---- free functions of the GPU seam (declared in src/backends/metal/metal_operations.hpp) --------------------------
 namespace metal {
+namespace plan = cuda::plan;
 
 using cuda::check;
 using cuda::describe;
@@ -424,7 +426,7 @@ Tensor gpu_layer_norm(const Tensor &input, const Tensor &weight, const Tensor &b
     const bool has_w = weight.storage() && weight.size() > 0, has_b = bias.storage() && bias.size() > 0;
     if (has_w) { w = on_gpu(weight); wd = describe(w); }
     if (has_b) { b = on_gpu(bias); bd = describe(b); }
-    check(axb_layer_norm(&xd, has_w ? &wd : nullptr, has_b ? &bd : nullptr, axis, eps, &od, nullptr), "axb_layer_norm");
+    check(plan::layer_norm(&xd, has_w ? &wd : nullptr, has_b ? &bd : nullptr, axis, eps, &od), "axb_layer_norm");
     return out;
 }
 
@@ -438,7 +440,7 @@ Tensor gpu_rms_norm(const Tensor &input, const Tensor &weight, int axis, float e
     Tensor w;
     const bool has_w = weight.storage() && weight.size() > 0;
     if (has_w) { w = on_gpu(weight); wd = describe(w); }
-    check(axb_rms_norm(&xd, has_w ? &wd : nullptr, axis, eps, &od, nullptr), "axb_rms_norm");
+    check(plan::rms_norm(&xd, has_w ? &wd : nullptr, axis, eps, &od), "axb_rms_norm");
     return out;
 }
 
@@ -510,7 +512,7 @@ Tensor gpu_fill_constant(const Shape &shape, DType dtype, double value) {
     if (out.size() == 0)
         return out;
     const axb_tensor od = describe(out);
-    check(axb_fill(&od, value, nullptr), "axb_fill");
+    check(plan::fill(&od, value), "axb_fill");
     return out;
 }
 
@@ -576,7 +578,7 @@ Tensor gpu_conv2d(const Tensor &input, const Tensor &weight, const Tensor &bias,
         if (a.has_bias)
             bd = cuda::describe(a.b);
         const int32_t st[2] = {stride[0], stride[1]}, pd[2] = {padding[0], padding[1]}, dl[2] = {dilation[0], dilation[1]};
-        cuda::check(axb_conv2d(&xd, &wd, a.has_bias ? &bd : nullptr, st, pd, dl, groups, &od, nullptr), "axb_conv2d");
+        cuda::check(plan::conv2d(&xd, &wd, a.has_bias ? &bd : nullptr, st, pd, dl, groups, &od), "axb_conv2d");
     }
     return drop_batch(out, a.has_batch);
 }

@@ -1,6 +1,7 @@
 // cuda_storage.cpp — seam 1: Storage on device memory, the make_storage factory, and the stream / availability
 // symbols the shared code calls (see cuda_backend.hpp for the map of reference call sites).
 #include "cuda_backend.hpp"
+#include "cuda_plan.hpp"
 
 #include <cstring>
 #include <mutex>
@@ -53,8 +54,14 @@ void ensure_initialized() {
 CudaStorage::CudaStorage(size_t size_bytes) : size_bytes_(size_bytes) {
     ensure_initialized();
     check(axb_get_device(&device_index_), "axb_get_device");
-    if (size_bytes_ > 0) // size 0 is legal (tests/test_tensor_basic.cpp: empty tensors)
+    if (size_bytes_ > 0) { // size 0 is legal (tests/test_tensor_basic.cpp: empty tensors)
         check(axb_alloc(size_bytes_, nullptr, &ptr_), "axb_alloc");
+        plan::note_alloc(ptr_, size_bytes_); // a temporary of the lowering being recorded (no-op otherwise)
+    }
+}
+
+CudaStorage::CudaStorage(void *adopted, size_t size_bytes, Adopt) : ptr_(adopted), size_bytes_(size_bytes) {
+    check(axb_get_device(&device_index_), "axb_get_device");
 }
 
 CudaStorage::~CudaStorage() {
@@ -71,6 +78,7 @@ void CudaStorage::copy_to(Storage &other) const {
         return;
     if (other.device() == Device::CPU) {
         // synchronous: the caller reads the host bytes as soon as this returns (metal_storage.mm:69-70)
+        plan::note_foreign("device->host copy inside a lowering");
         check(axb_memcpy_d2h(other.data(), ptr_, n, nullptr, /*sync=*/1), "axb_memcpy_d2h");
     } else {
         auto *dst = dynamic_cast<CudaStorage *>(&other);
@@ -90,6 +98,7 @@ void CudaStorage::copy_from(const Storage &other) {
         // immediately; the device side stays ordered on the backend stream. No stream sync here — scalar operands
         // (`x + 1.0f` uploads a one-element tensor, tensor_operators.hpp) would otherwise serialise host and GPU.
         check(axb_memcpy_h2d(ptr_, other.data(), n, nullptr), "axb_memcpy_h2d");
+        plan::note_upload(ptr_, other.data(), n);
     } else {
         auto *src = dynamic_cast<const CudaStorage *>(&other);
         if (!src)

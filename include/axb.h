@@ -200,6 +200,15 @@ axb_status axb_elementwise(const axb_instr *prog, int n_instr, const axb_tensor 
  * use (the analogue of the reference's per-signature MPSGraph cache, mpsgraph_fused.mm:373-377). */
 axb_status axb_elementwise_precompile(const axb_instr *prog, int n_instr, const axb_tensor *inputs, int n_inputs,
                                       const axb_tensor *out);
+/* Launch-plan cache of the fused-chain family: program + operand LAYOUTS (dtype, shape, byte strides, alignment class —
+ * never addresses) -> specialised kernel + launch parameters. A hit skips validation, iteration-space planning, statement
+ * generation and the kernel lookup; only the operand pointers are patched. (Graph-level counterpart in the C++ glue:
+ * signature -> lowering plan, reference src/graph/graph_cache.cpp:12-52.) */
+typedef struct axb_plan_cache_stats {
+    uint64_t entries, hits, misses, evictions;
+} axb_plan_cache_stats;
+axb_status axb_get_plan_cache_stats(axb_plan_cache_stats *out);
+axb_status axb_plan_cache_clear(void);
 typedef struct axb_jit_stats {
     uint64_t mem_hits, disk_hits, compiles;
 } axb_jit_stats;

@@ -16,7 +16,7 @@ def test_library_loads_and_exports_every_declared_symbol():
     assert len(declared) >= 40
     missing = [s for s in declared if not hasattr(L, s)]
     assert not missing, f"declared in include/axb.h but not exported by libaxb.so: {missing}"
-    assert L.axb_abi_version() == 1
+    assert L.axb_abi_version() == 2
 
 
 def test_ctypes_signatures_cover_header():

@@ -164,3 +164,21 @@ def test_spatial_ops_match_cpu_backend(gpu):
     j = json.loads(lines[-1])
     assert j["failed"] == 0 and r.returncode == 0, j
     assert j["cases"] >= 200 and j["bit_exact_f32"] == j["f32_cases"], j
+
+
+@pytest.mark.gpu
+def test_plan_cache_hits_and_misses(gpu):
+    """Graph-level plan cache of the CUDA lowering (host/cuda_plan.cpp), tested the way the reference tests
+    its own cache (tests/test_graph_compiler.cpp CacheHit / CacheMissOnShapeChange): same expression + same leaf layouts ->
+    hit (new data and new scalar operands still give the CPU backend's bytes); strided / transposed / offset views, shape,
+    dtype and aliasing changes -> their own plans; a replay launches what the recording launched, no device->host bytes."""
+    _need_build()
+    exe = os.path.join(BUILD, "plan_cache")
+    if not os.path.exists(exe):
+        pytest.skip("plan_cache not built")
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=600)
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert lines, r.stdout[-2000:] + r.stderr[-2000:]
+    j = json.loads(lines[-1])
+    assert j["all_ok"] and r.returncode == 0, j["failed"]
+    assert j["cases"] >= 30
