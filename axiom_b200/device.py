@@ -340,6 +340,47 @@ def interpolate(x: DeviceArray, size: Sequence[int], mode: str = "nearest", alig
     return out
 
 
+def pool(x: DeviceArray, mode: str, kernel, stride=None, padding=0, count_include_pad: bool = True) -> DeviceArray:
+    """ops::max_pool{1,2,3}d / avg_pool{1,2,3}d on (N, C, spatial...) (axb_pool). stride None = kernel (operations.cpp:2369)."""
+    nsp = len(x.shape) - 2
+    k = _i32s(kernel, nsp)
+    st = _i32s(kernel if stride is None else stride, nsp)
+    pd = _i32s(padding, nsp)
+    sp = [(x.shape[2 + i] + 2 * pd[i] - k[i]) // st[i] + 1 for i in range(nsp)]
+    out = DeviceArray.empty((x.shape[0], x.shape[1], *sp), x.dtype)
+    check(lib().axb_pool(ctypes.byref(x.desc()), 1 if mode == "avg" else 0, nsp, k, st, pd, int(count_include_pad),
+                         ctypes.byref(out.desc()), None))
+    return out
+
+
+def sort(x: DeviceArray, axis: int = -1, descending: bool = False, k: Optional[int] = None, want_values: bool = True,
+         want_indices: bool = True):
+    """ops::sort / argsort / topk (axb_sort): (values, indices) with extent k (default: all) along `axis`."""
+    ax = axis + len(x.shape) if axis < 0 else axis
+    oshape = list(x.shape)
+    if k is not None:
+        oshape[ax] = int(k)
+    v = DeviceArray.empty(oshape, x.dtype) if want_values else None
+    i = DeviceArray.empty(oshape, capi.I64) if want_indices else None
+    check(lib().axb_sort(ctypes.byref(x.desc()), axis, int(descending), ctypes.byref(v.desc()) if v else None,
+                         ctypes.byref(i.desc()) if i else None, None))
+    return v, i
+
+
+class _AdoptedStorage(Storage):
+    def __init__(self, ptr: int, nbytes: int):  # a block that came out of axb_alloc inside the library
+        self.nbytes, self.ptr = int(nbytes), int(ptr)
+
+
+def masked_select(x: DeviceArray, mask: DeviceArray) -> DeviceArray:
+    """ops::masked_select (axb_masked_select): 1-D result of the input's dtype."""
+    p, n = ctypes.c_void_p(), ctypes.c_int64()
+    check(lib().axb_masked_select(ctypes.byref(x.desc()), ctypes.byref(mask.desc()), ctypes.byref(p), ctypes.byref(n), None))
+    if n.value == 0:
+        return DeviceArray.empty((0,), x.dtype)
+    return DeviceArray(_AdoptedStorage(p.value, n.value * x.itemsize), x.dtype, (n.value,), (x.itemsize,))
+
+
 def elementwise_reduce(prog: List[capi.AxbInstr], inputs: Sequence[DeviceArray], op: str) -> DeviceArray:
     """FusedReductionStep: the chain's value under a FULL reduction (axb_elementwise_reduce); result shape {1}."""
     P = (capi.AxbInstr * len(prog))(*prog)

@@ -86,9 +86,17 @@ Tensor gpu_where(const Tensor &c, const Tensor &a, const Tensor &b);
 Tensor gpu_masked_fill(const Tensor &x, const Tensor &mask, double value);
 Tensor gpu_cast(const Tensor &x, DType to);
 Tensor gpu_contiguous(const Tensor &x);
+Tensor gpu_compact(const Tensor &x); // always a fresh, offset-free storage (patched Tensor::to)
 Tensor gpu_conv1d_impl(const Tensor &x, const Tensor &w, const Tensor &b, int stride, int padding, int dilation,
                        int groups);
 Tensor gpu_pad_constant(const Tensor &x, const std::vector<std::pair<size_t, size_t>> &pad, double value);
+// Entry points of the patched ops::max_pool*/avg_pool*/sort/argsort/topk (patches/apply.py; the reference has no device
+// branch for them, operations.cpp:2367-2880, :4199-4257). `out_shape` is the shape the reference computed (without the
+// batch dim when the input has none). Results live on the GPU.
+Tensor gpu_pool(const Tensor &input, bool is_avg, const std::vector<int> &kernel, const std::vector<int> &stride,
+                const std::vector<int> &padding, bool count_include_pad, const Shape &out_shape);
+Tensor gpu_sort(const Tensor &input, int axis, bool descending, bool want_indices);
+std::pair<Tensor, Tensor> gpu_topk(const Tensor &input, int k, int axis, bool largest);
 
 } // namespace cuda
 } // namespace backends

@@ -131,6 +131,16 @@ Tensor gpu_contiguous(const Tensor &x) {
     return out;
 }
 
+// fresh storage holding exactly the view's elements (the patched Tensor::to compacts offset views before a transfer)
+Tensor gpu_compact(const Tensor &x) {
+    Tensor out = empty_gpu(x.shape(), x.dtype());
+    if (out.size() == 0)
+        return out;
+    const axb_tensor xd = describe(x), od = describe(out);
+    check(plan::gather_strided(&xd, &od), "axb_gather_strided");
+    return out;
+}
+
 Tensor gpu_reduce(OpType op, const Tensor &x_in, const std::vector<int> &axes_in, bool keep_dims) {
     Tensor x = on_gpu(x_in);
     const bool is_arg = op == OpType::ArgMax || op == OpType::ArgMin;
@@ -361,6 +371,20 @@ class CudaOperation final : public ops::Operation {
         check(axb_scatter(&xd, dim, &id, &vd, &od, nullptr), "axb_scatter");
         return out;
     }
+    Tensor execute_masked_select(const Tensor &input, const Tensor &mask) const override {
+        // CPU rule (cpu_operations.cpp:2719-2776): broadcast, first byte of the mask element, row-major, 1-D result.
+        // The element count decides the result's shape: 8 bytes come back inside axb_masked_select, nothing else.
+        const Tensor x = on_gpu(input), m = on_gpu(mask);
+        const axb_tensor xd = describe(x), md = describe(m);
+        void *data = nullptr;
+        int64_t count = 0;
+        check(axb_masked_select(&xd, &md, &data, &count, nullptr), "axb_masked_select");
+        if (count == 0)
+            return empty_gpu({0}, x.dtype());
+        const size_t bytes = (size_t)count * dtype_size(x.dtype());
+        auto st = std::make_shared<CudaStorage>(data, bytes, CudaStorage::Adopt{});
+        return Tensor(st, Shape{(size_t)count}, Strides{(int64_t)dtype_size(x.dtype())}, x.dtype(), 0);
+    }
     Tensor execute_cast(const Tensor &input, DType target) const override { return gpu_cast(input, target); }
     void execute_binary_inplace(Tensor &lhs, const Tensor &rhs) const override {
         const Tensor r = on_gpu(rhs);
@@ -380,6 +404,78 @@ class CudaOperation final : public ops::Operation {
 
 } // namespace
 
+// ---- pooling / sort / topk: called from the patched ops::max_pool*/avg_pool*/sort/argsort/topk (patches/apply.py), which
+// otherwise copy a GPU tensor to the host, run scalar loops and upload the result (operations.cpp:2367-2880, :4199-4257) --
+Tensor gpu_pool(const Tensor &input, bool is_avg, const std::vector<int> &kernel, const std::vector<int> &stride,
+                const std::vector<int> &padding, bool count_include_pad, const Shape &out_shape) {
+    const int nsp = (int)kernel.size();
+    Tensor x = on_gpu(input);
+    if (!is_floating_dtype(x.dtype())) // dispatch_float (include/axiom/dispatch.hpp:151-156)
+        throw TypeError::unsupported_dtype(dtype_name(x.dtype()), is_avg ? "avg_pool" : "max_pool");
+    const bool has_batch = (int)x.ndim() == nsp + 2;
+    if (!has_batch)
+        x = x.unsqueeze(0);
+    Shape oshape = out_shape;
+    if (!has_batch)
+        oshape.insert(oshape.begin(), 1);
+    Tensor out = empty_gpu(oshape, x.dtype());
+    if (out.size() != 0) {
+        int32_t k[3], s[3], p[3];
+        for (int d = 0; d < nsp; ++d) {
+            k[d] = kernel[d];
+            s[d] = stride[d];
+            p[d] = padding[d];
+        }
+        const axb_tensor xd = describe(x), od = describe(out);
+        check(plan::pool(&xd, is_avg ? 1 : 0, nsp, k, s, p, count_include_pad ? 1 : 0, &od), "axb_pool");
+    }
+    return has_batch ? out : out.squeeze(0);
+}
+
+namespace {
+// keys the kernels sort: float32 / float64 / int32 / int64; everything else becomes float32 first (operations.cpp:4199-4257)
+Tensor sort_keys(const Tensor &input) {
+    Tensor x = gpu_contiguous(on_gpu(input));
+    switch (x.dtype()) {
+    case DType::Float32: case DType::Float64: case DType::Int32: case DType::Int64: return x;
+    default: return gpu_cast(x, DType::Float32);
+    }
+}
+int sort_axis(const Tensor &x, int axis) {
+    const int nd = (int)x.ndim();
+    const int a = axis < 0 ? axis + nd : axis;
+    if (a < 0 || a >= nd)
+        throw ShapeError::invalid_axis(axis, nd);
+    return a;
+}
+} // namespace
+
+Tensor gpu_sort(const Tensor &input, int axis, bool descending, bool want_indices) {
+    const Tensor x = sort_keys(input);
+    const int a = sort_axis(x, axis);
+    Tensor out = empty_gpu(x.shape(), want_indices ? DType::Int64 : x.dtype());
+    if (out.size() == 0)
+        return out;
+    const axb_tensor xd = describe(x), od = describe(out);
+    check(plan::sort(&xd, a, descending ? 1 : 0, want_indices ? nullptr : &od, want_indices ? &od : nullptr), "axb_sort");
+    return out;
+}
+
+std::pair<Tensor, Tensor> gpu_topk(const Tensor &input, int k, int axis, bool largest) {
+    const Tensor x = sort_keys(input);
+    const int a = sort_axis(x, axis);
+    if (k < 0 || (size_t)k > x.shape()[a])
+        throw ValueError("topk: k = " + std::to_string(k) + " out of range for an axis of " + std::to_string(x.shape()[a]));
+    Shape oshape = x.shape();
+    oshape[a] = (size_t)k;
+    Tensor values = empty_gpu(oshape, x.dtype()), indices = empty_gpu(oshape, DType::Int64);
+    if (values.size() != 0) {
+        const axb_tensor xd = describe(x), vd = describe(values), id = describe(indices);
+        check(plan::sort(&xd, a, largest ? 1 : 0, &vd, &id), "axb_sort (topk)");
+    }
+    return {values, indices};
+}
+
 void register_cuda_operations() {
     static const OpType kOps[] = {
         OpType::Add, OpType::Subtract, OpType::Multiply, OpType::Divide, OpType::Power, OpType::Modulo,
@@ -395,7 +491,7 @@ void register_cuda_operations() {
         OpType::Sum, OpType::Mean, OpType::Max, OpType::Min, OpType::ArgMax, OpType::ArgMin, OpType::Any, OpType::All,
         OpType::Prod,
         OpType::MatMul, OpType::BatchMatMul, OpType::Where, OpType::MaskedFill, OpType::Gather, OpType::Scatter,
-        OpType::IndexSelect,
+        OpType::IndexSelect, OpType::MaskedSelect,
         OpType::Cast,
     };
     for (OpType t : kOps)

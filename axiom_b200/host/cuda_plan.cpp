@@ -20,7 +20,7 @@ using graph::GraphNode;
 
 enum Fn : int32_t {
     F_ELEMENTWISE, F_ELEMENTWISE_REDUCE, F_MATMUL, F_SOFTMAX, F_LAYER_NORM, F_RMS_NORM, F_REDUCE, F_ARGREDUCE, F_CAST,
-    F_GATHER_STRIDED, F_IM2COL, F_BINARY, F_UNARY, F_WHERE, F_MASKED_FILL, F_PAD, F_CONV2D, F_FILL
+    F_GATHER_STRIDED, F_IM2COL, F_BINARY, F_UNARY, F_WHERE, F_MASKED_FILL, F_PAD, F_CONV2D, F_FILL, F_POOL, F_SORT
 };
 enum Kind : int8_t { K_NONE = 0, K_LEAF = 1, K_TEMP = 2 };
 
@@ -229,6 +229,16 @@ axb_status invoke(const Call &c, axb_tensor *T) {
         return axb_conv2d(&T[0], &T[1], tp(2), st, pd, dl, (int)c.iv[6], &T[3], nullptr);
     }
     case F_FILL: return axb_fill(&T[0], c.dv[0], nullptr);
+    case F_POOL: {
+        int32_t k[3], st[3], pd[3];
+        for (int d = 0; d < 3; ++d) {
+            k[d] = (int32_t)c.iv[3 + d];
+            st[d] = (int32_t)c.iv[6 + d];
+            pd[d] = (int32_t)c.iv[9 + d];
+        }
+        return axb_pool(&T[0], (int)c.iv[0], (int)c.iv[1], k, st, pd, (int)c.iv[2], &T[1], nullptr);
+    }
+    case F_SORT: return axb_sort(&T[0], (int)c.iv[0], (int)c.iv[1], tp(1), tp(2), nullptr);
     }
     return AXB_ERR_INVALID;
 }
@@ -622,6 +632,26 @@ axb_status conv2d(const axb_tensor *in, const axb_tensor *w, const axb_tensor *b
     c->iv[0] = stride[0]; c->iv[1] = stride[1]; c->iv[2] = padding[0]; c->iv[3] = padding[1];
     c->iv[4] = dilation[0]; c->iv[5] = dilation[1]; c->iv[6] = groups;
     c->t[0] = resolve(in); c->t[1] = resolve(w); c->t[2] = resolve(b); c->t[3] = resolve(out);
+    return st_;
+}
+axb_status pool(const axb_tensor *in, int is_avg, int nsp, const int32_t *kernel, const int32_t *stride, const int32_t *padding,
+                int count_include_pad, const axb_tensor *out) {
+    AXB_PLAN_CALL(axb_pool(in, is_avg, nsp, kernel, stride, padding, count_include_pad, out, nullptr))
+    Call *c = sc.open(F_POOL);
+    c->iv[0] = is_avg; c->iv[1] = nsp; c->iv[2] = count_include_pad;
+    for (int d = 0; d < nsp && d < 3; ++d) {
+        c->iv[3 + d] = kernel[d];
+        c->iv[6 + d] = stride[d];
+        c->iv[9 + d] = padding[d];
+    }
+    c->t[0] = resolve(in); c->t[1] = resolve(out);
+    return st_;
+}
+axb_status sort(const axb_tensor *in, int axis, int descending, const axb_tensor *values, const axb_tensor *indices) {
+    AXB_PLAN_CALL(axb_sort(in, axis, descending, values, indices, nullptr))
+    Call *c = sc.open(F_SORT);
+    c->iv[0] = axis; c->iv[1] = descending;
+    c->t[0] = resolve(in); c->t[1] = resolve(values); c->t[2] = resolve(indices);
     return st_;
 }
 axb_status fill(const axb_tensor *out, double value) {

@@ -73,6 +73,9 @@ axb_status pad_constant(const axb_tensor *in, const int64_t *lo, const int64_t *
 axb_status conv2d(const axb_tensor *in, const axb_tensor *w, const axb_tensor *b, const int32_t stride[2], const int32_t padding[2],
                   const int32_t dilation[2], int groups, const axb_tensor *out);
 axb_status fill(const axb_tensor *out, double value);
+axb_status pool(const axb_tensor *in, int is_avg, int nsp, const int32_t *kernel, const int32_t *stride, const int32_t *padding,
+                int count_include_pad, const axb_tensor *out);
+axb_status sort(const axb_tensor *in, int axis, int descending, const axb_tensor *values, const axb_tensor *indices);
 
 } // namespace plan
 } // namespace cuda

@@ -21,6 +21,68 @@ RULES = {
         (r"Tensor::full\(shape_, other, device\(\)\)", "Tensor::full({1}, other, device())", 1),
         (r"Tensor::full\(shape_, static_cast<float>\(other\), device\(\)\)",
          "Tensor::full({1}, static_cast<float>(other), device())", 2),
+        # Tensor::to(Device) hands the WHOLE storage of a contiguous view to Storage::copy_from (src/tensor/tensor.cpp:1625-
+        # 1636): a contiguous view that starts inside its storage (`x.slice({Slice(1, 2)})`, a batch slice) arrives on the
+        # other device with the bytes of offset 0. On Apple silicon the unified-memory branch above it (:1600-1622) keeps the
+        # offset, so the reference never takes this branch with a GPU; a discrete GPU always does. The view is compacted on
+        # its own device first (host memcpy / device gather), then copied as before.
+        (r"\n    const Tensor &src = is_contiguous\(\) \? \*this : ascontiguousarray\(\);\n",
+         "\n    Tensor compact_;\n"
+         "    if (is_contiguous() && offset_ != 0 && size() > 0 && memory_order_ == MemoryOrder::RowMajor) {\n"
+         "        if (device() == Device::CPU) {\n"
+         "            compact_ = Tensor(shape_, dtype_, Device::CPU, memory_order_);\n"
+         "            std::memcpy(compact_.data(), data(), nbytes());\n"
+         "        } else {\n"
+         "            compact_ = backends::cuda::gpu_compact(*this);\n"
+         "        }\n"
+         "    }\n"
+         "    const Tensor &src = compact_.storage_ ? compact_ : (is_contiguous() ? *this : ascontiguousarray());\n", 1),
+        (r"\nnamespace axiom \{\n\ntemplate <typename T> std::string vec_to_string",
+         "\nnamespace axiom { namespace backends { namespace cuda { Tensor gpu_compact(const Tensor &); }}}\n"
+         "\nnamespace axiom {\n\ntemplate <typename T> std::string vec_to_string", 1),
+    ],
+    # Pooling, sort, argsort and topk have NO device branch in the reference: a GPU tensor is copied to the host, processed by
+    # scalar loops and (pooling only) uploaded again (src/tensor/operations.cpp:2367-2880, :4199-4257). The rules below add
+    # the branch the other spatial operators already have (cf. gpu_conv_transpose1d at :3395, gpu_interpolate at :3742):
+    # on Device::GPU the call goes to the CUDA backend (host/cuda_operations.cpp gpu_pool / gpu_sort / gpu_topk) AFTER the
+    # reference's own argument checks and shape computation, so errors and result shapes are the reference's.
+    "src/tensor/operations.cpp": [
+        # declarations, placed in front of the first namespace block
+        (r"\nnamespace axiom \{\nnamespace ops \{\n",
+         "\nnamespace axiom { namespace backends { namespace cuda {\n"
+         "Tensor gpu_pool(const Tensor &, bool, const std::vector<int> &, const std::vector<int> &, const std::vector<int> &, bool, const Shape &);\n"
+         "Tensor gpu_sort(const Tensor &, int, bool, bool);\n"
+         "std::pair<Tensor, Tensor> gpu_topk(const Tensor &, int, int, bool);\n"
+         "}}} // namespace axiom::backends::cuda\n"
+         "\nnamespace axiom {\nnamespace ops {\n", 1),
+    ],
+}
+
+# Function-scoped insertions: (file, regex matching the START of a function definition, regex of the anchor line inside it,
+# text inserted in front of the anchor). The anchor is the first match after the function start.
+_POOL_ANCHOR = r"    Tensor input_cpu = input\.device\(\) == Device::CPU \? input : input\.cpu\(\);\n"
+_SORT_ANCHOR = r"    auto src = input\.is_contiguous\(\) \? input : input\.ascontiguousarray\(\);\n"
+
+
+def _pool_call(is_avg, k, s, p, inc):
+    return ("    if (input.device() == Device::GPU)\n"
+            f"        return backends::cuda::gpu_pool(input, {is_avg}, {k}, {s}, {p}, {inc}, out_shape);\n")
+
+
+INSERTIONS = {
+    "src/tensor/operations.cpp": [
+        (r"\nTensor max_pool1d\(", _POOL_ANCHOR, _pool_call("false", "{kernel_size}", "{stride}", "{padding}", "false")),
+        (r"\nTensor avg_pool1d\(", _POOL_ANCHOR, _pool_call("true", "{kernel_size}", "{stride}", "{padding}", "count_include_pad")),
+        (r"\nTensor max_pool2d\(", _POOL_ANCHOR, _pool_call("false", "kernel_size", "actual_stride", "actual_padding", "false")),
+        (r"\nTensor avg_pool2d\(", _POOL_ANCHOR, _pool_call("true", "kernel_size", "actual_stride", "actual_padding", "count_include_pad")),
+        (r"\nTensor max_pool3d\(", _POOL_ANCHOR, _pool_call("false", "kernel_size", "actual_stride", "actual_padding", "false")),
+        (r"\nTensor avg_pool3d\(", _POOL_ANCHOR, _pool_call("true", "kernel_size", "actual_stride", "actual_padding", "count_include_pad")),
+        (r"\nTensor sort\(const Tensor &input, int axis, bool descending\) \{\n", _SORT_ANCHOR,
+         "    if (input.device() == Device::GPU)\n        return backends::cuda::gpu_sort(input, axis, descending, false);\n"),
+        (r"\nTensor argsort\(const Tensor &input, int axis, bool descending\) \{\n", _SORT_ANCHOR,
+         "    if (input.device() == Device::GPU)\n        return backends::cuda::gpu_sort(input, axis, descending, true);\n"),
+        (r"\nstd::pair<Tensor, Tensor> topk\(const Tensor &input, int k, int axis,\n", _SORT_ANCHOR,
+         "    if (input.device() == Device::GPU)\n        return backends::cuda::gpu_topk(input, k, axis, largest);\n"),
     ],
 }
 
@@ -33,11 +95,22 @@ def main() -> int:
         return 2
     text = open(src).read()
     for pattern, repl, count in RULES[key]:
-        text, n = re.subn(pattern, repl, text)
+        text, n = re.subn(pattern, lambda m, r=repl: r, text)
         if n != count:
             print(f"apply.py: {key}: pattern {pattern!r} matched {n} times, expected {count} — upstream changed, "
                   "re-examine the patch", file=sys.stderr)
             return 1
+    for start, anchor, insertion in INSERTIONS.get(key, []):
+        heads = list(re.finditer(start, text))
+        if len(heads) != 1:
+            print(f"apply.py: {key}: function start {start!r} matched {len(heads)} times, expected 1", file=sys.stderr)
+            return 1
+        m = re.compile(anchor).search(text, heads[0].end())
+        nxt = re.compile(r"\n}\n").search(text, heads[0].end())  # end of that function (first closing brace in column 0)
+        if m is None or nxt is None or m.start() > nxt.start():
+            print(f"apply.py: {key}: anchor {anchor!r} not found inside the function starting at {start!r}", file=sys.stderr)
+            return 1
+        text = text[:m.start()] + insertion + text[m.start():]
     with open(dst, "w") as f:
         f.write(text)
     return 0

@@ -388,6 +388,30 @@ axb_status axb_conv_transpose(const axb_tensor *in, const axb_tensor *weight, co
 axb_status axb_interpolate(const axb_tensor *in, int mode, int align_corners, const axb_tensor *out, axb_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Pooling, sorting, masked_select. The reference has no device branch for these: a GPU tensor is
+ * copied to the host, processed by scalar loops and (pooling) uploaded again.
+ *   axb_pool           ops::max_pool1d/2d/3d, avg_pool1d/2d/3d (src/tensor/operations.cpp:2367-2880; the adaptive forms
+ *                      :2883-2962 call them): in (N, C, spatial...), out contiguous (N, C, out...) with
+ *                      out = (in + 2*padding - kernel) / stride + 1 (:2360-2363). fp64 accumulation in the CPU loops' order:
+ *                      bit-identical for every float dtype. Input may be a strided view.
+ *   axb_sort           ops::sort / argsort / topk (:4053-4257): contiguous keys of float32 / float64 / int32 / int64 (the
+ *                      reference converts every other dtype to float32 first), sorted along `axis`. `values` / `indices`
+ *                      (either may be NULL) are contiguous with extent k <= n along `axis`: k == n is sort / argsort, k < n
+ *                      the first k of the order = topk (largest: descending = 1). Equal keys keep ascending positions (the
+ *                      reference's std::sort leaves their order unspecified).
+ *   axb_masked_select  ops::masked_select (src/backends/cpu/cpu_operations.cpp:2719-2789): broadcasts input and mask, selects
+ *                      where the FIRST BYTE of the mask element is non-zero, row-major order. The result block comes from
+ *                      axb_alloc (release it with axb_free); *out_count elements of the input's dtype (NULL when 0). The
+ *                      count is read back inside the call (8 bytes device->host, one stream synchronisation).
+ * ---------------------------------------------------------------------------------------------- */
+axb_status axb_pool(const axb_tensor *in, int is_avg, int spatial_dims, const int32_t *kernel, const int32_t *stride,
+                    const int32_t *padding, int count_include_pad, const axb_tensor *out, axb_stream_t stream);
+axb_status axb_sort(const axb_tensor *in, int axis, int descending, const axb_tensor *values /* may be NULL */,
+                    const axb_tensor *indices /* int64, may be NULL */, axb_stream_t stream);
+axb_status axb_masked_select(const axb_tensor *in, const axb_tensor *mask, void **out_data, int64_t *out_count,
+                             axb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Host-buffer entry points (what `Tensor::gpu()` ... `.cpu()` does end to end: H2D, launch, D2H, sync).
  * Inputs/outputs are HOST tensors (base = host pointer, contiguous or strided); used by bench.py's
  * `e2e` leg and by callers that hold no device memory. Staging goes through the caching allocator and

@@ -602,3 +602,88 @@ def interpolate2d_f32(x, size, mode="nearest", align_corners=False):
                         val = (val + (f(a * bq) * x[:, :, sh, sw]).astype(np.float32)).astype(np.float32)
                 out[:, :, i, j] = val
     return out
+
+
+# ---- pooling / sort / topk / masked_select ---------------------------------------------------------
+def _from_f64(v: np.ndarray, dt: int) -> np.ndarray:
+    """static_cast<T>(double) of the reference's element types: half types go through float (bfloat16.hpp:29,
+    float16.hpp:16)."""
+    if dt == F64:
+        return v.astype(np.float64)
+    f = v.astype(np.float32)
+    if dt == F32:
+        return f
+    if dt == BF16:
+        return f32_to_bf16(f)
+    return f.astype(np.float16)
+
+
+def pool(x: np.ndarray, dt: int, mode: str, kernel: Sequence[int], stride: Optional[Sequence[int]] = None,
+         padding: Optional[Sequence[int]] = None, count_include_pad: bool = True) -> np.ndarray:
+    """ops::max_pool{1,2,3}d / avg_pool{1,2,3}d on (N, C, spatial...) (src/tensor/operations.cpp:2367-2880): the window is
+    walked kd, kh, kw ascending; max starts at -inf in double and takes `val > max` (NaN never wins); avg sums in double,
+    counts in-bounds taps (+ padded ones with count_include_pad) and divides once; one cast to the element type."""
+    nsp = x.ndim - 2
+    k = list(kernel)
+    s = list(stride) if stride else list(k)
+    p = list(padding) if padding else [0] * nsp
+    xf = to_f32(x, dt).astype(np.float64) if dt != F64 else x.astype(np.float64)
+    k3, s3, p3 = [1] * (3 - nsp) + k, [1] * (3 - nsp) + s, [0] * (3 - nsp) + p
+    x5 = xf.reshape(x.shape[:2] + (1,) * (3 - nsp) + x.shape[2:])
+    insz = x5.shape[2:]
+    osz = [(insz[d] + 2 * p3[d] - k3[d]) // s3[d] + 1 for d in range(3)]  # pool_output_size, :2360-2363
+    acc = np.full(x5.shape[:2] + tuple(osz), -np.inf if mode == "max" else 0.0, np.float64)
+    cnt = np.zeros(tuple(osz), np.int64)
+    grids = [np.arange(osz[d]) * s3[d] - p3[d] for d in range(3)]
+    for kd in range(k3[0]):
+        for kh in range(k3[1]):
+            for kw in range(k3[2]):
+                pos = [grids[0] + kd, grids[1] + kh, grids[2] + kw]
+                ok = [(pos[d] >= 0) & (pos[d] < insz[d]) for d in range(3)]
+                valid = ok[0][:, None, None] & ok[1][None, :, None] & ok[2][None, None, :]
+                cl = [np.clip(pos[d], 0, insz[d] - 1) for d in range(3)]
+                v = x5[:, :, cl[0][:, None, None], cl[1][None, :, None], cl[2][None, None, :]]
+                if mode == "max":
+                    with np.errstate(invalid="ignore"):
+                        acc = np.where(valid[None, None] & (v > acc), v, acc)
+                else:
+                    acc = np.where(valid[None, None], acc + v, acc)
+                    cnt += valid.astype(np.int64) if not count_include_pad else 1
+    if mode != "max":
+        with np.errstate(invalid="ignore", divide="ignore"):
+            acc = np.where(cnt[None, None] > 0, acc / np.maximum(cnt, 1)[None, None], 0.0)
+    out = _from_f64(acc, dt)
+    return out.reshape(x.shape[:2] + tuple(osz[3 - nsp:]))
+
+
+def sort_order(x: np.ndarray, axis: int = -1, descending: bool = False) -> np.ndarray:
+    """Positions that sort `x` along `axis` (ops::argsort, src/tensor/operations.cpp:4088-4127, std::sort by `<` or `>` on
+    float32 / float64 / int32 / int64 keys; every other dtype is converted to float32 first, :4218-4234). std::sort leaves
+    the order of EQUAL keys unspecified; the restatement (and the CUDA kernel) fix it as ascending position — compare
+    indices only where keys are distinct, values everywhere."""
+    if descending:
+        # stable ascending order of the reversed slice, mapped back: largest first, ties by ascending position
+        n = x.shape[axis]
+        r = np.argsort(np.flip(x, axis), axis=axis, kind="stable")
+        return np.flip(n - 1 - r, axis)
+    return np.argsort(x, axis=axis, kind="stable")
+
+
+def sort(x: np.ndarray, axis: int = -1, descending: bool = False, k: Optional[int] = None) -> Tuple[np.ndarray, np.ndarray]:
+    """(values, indices) of ops::sort / argsort / topk (:4053-4257); k limits the result to the first k along `axis`
+    (std::partial_sort + the first k copied out, :4148-4193 — they come out sorted whether or not `sorted` is set)."""
+    key = x if x.dtype in (np.float32, np.float64, np.int32, np.int64) else x.astype(np.float32)
+    order = sort_order(key, axis, descending)
+    if k is not None:
+        order = np.take(order, np.arange(k), axis=axis)
+    return np.take_along_axis(key, order, axis=axis), order.astype(np.int64)
+
+
+def masked_select(x: np.ndarray, mask: np.ndarray) -> np.ndarray:
+    """ops::masked_select (src/backends/cpu/cpu_operations.cpp:2719-2776): operands broadcast together, an element is
+    selected when the FIRST BYTE of its mask element is non-zero (:2738-2741 reads a uint8 whatever the mask dtype),
+    row-major order, 1-D result of the input's dtype."""
+    shape = np.broadcast_shapes(x.shape, mask.shape)
+    xb, mb = np.broadcast_to(x, shape), np.broadcast_to(mask, shape)
+    first = np.ascontiguousarray(mb).view(np.uint8).reshape(shape + (mask.dtype.itemsize,))[..., 0] != 0
+    return np.ascontiguousarray(xb)[first]

@@ -86,6 +86,9 @@ def lib() -> ctypes.CDLL:
             "axref_index_select": (vp, [vp, i32, vp]),
             "axref_conv1d": (vp, [vp, vp, vp, i32, i32, i32, i32]),
             "axref_sdpa": (vp, [vp, vp, vp, vp, f32, i32]),
+            "axref_pool": (vp, [vp, i32, i32, pi32, pi32, pi32, i32]),
+            "axref_sort": (vp, [vp, i32, i32, i32, i32]),
+            "axref_masked_select": (vp, [vp, vp]),
             "axref_time_sync": (ctypes.c_double, [vp]),
         }
         for name, (res, args) in sig.items():
@@ -254,6 +257,29 @@ def conv1d(x: RefTensor, w: RefTensor, b: Optional[RefTensor], stride=1, padding
 def sdpa(q: RefTensor, k: RefTensor, v: RefTensor, mask: Optional[RefTensor] = None, scale: float = -1.0,
          is_causal: bool = False):
     return RefTensor(lib().axref_sdpa(q.h, k.h, v.h, mask.h if mask else None, scale, int(is_causal)))
+
+
+def pool(x: RefTensor, mode: str, kernel, stride, padding, count_include_pad: bool = True) -> RefTensor:
+    n = len(kernel)
+    arr = lambda v: (ctypes.c_int * n)(*[int(t) for t in v])  # noqa: E731
+    return RefTensor(lib().axref_pool(x.h, 1 if mode == "avg" else 0, n, arr(kernel), arr(stride), arr(padding),
+                                      int(count_include_pad)))
+
+
+def sort(x: RefTensor, axis: int = -1, descending: bool = False) -> RefTensor:
+    return RefTensor(lib().axref_sort(x.h, 0, axis, int(descending), 0))
+
+
+def argsort(x: RefTensor, axis: int = -1, descending: bool = False) -> RefTensor:
+    return RefTensor(lib().axref_sort(x.h, 1, axis, int(descending), 0))
+
+
+def topk(x: RefTensor, k: int, axis: int = -1, largest: bool = True):
+    return (RefTensor(lib().axref_sort(x.h, 2, axis, int(largest), k)), RefTensor(lib().axref_sort(x.h, 3, axis, int(largest), k)))
+
+
+def masked_select(x: RefTensor, mask: RefTensor) -> RefTensor:
+    return RefTensor(lib().axref_masked_select(x.h, mask.h))
 
 
 def num_threads() -> int:

@@ -42,7 +42,7 @@ template <typename F> void *guard(F &&f) {
 
 extern "C" {
 
-int axref_version(void) { return 2; }
+int axref_version(void) { return 3; }
 const char *axref_last_error(void) { return g_err.c_str(); }
 
 int axref_num_threads(void) {
@@ -324,6 +324,34 @@ void *axref_sdpa(void *q, void *k, void *v, void *mask, float scale, int is_caus
         Tensor m = mask ? H(mask)->t : Tensor();
         return ops::scaled_dot_product_attention(H(q)->t, H(k)->t, H(v)->t, m, scale, is_causal != 0);
     });
+}
+
+// pooling / sort / topk / masked_select (operations.cpp:2367-2880, :4199-4257, :1631-1656)
+void *axref_pool(void *x, int is_avg, int nsp, const int *kernel, const int *stride, const int *padding, int include_pad) {
+    return guard([&] {
+        const Tensor &X = H(x)->t;
+        std::vector<int> k(kernel, kernel + nsp), s(stride, stride + nsp), p(padding, padding + nsp);
+        if (nsp == 1)
+            return is_avg ? ops::avg_pool1d(X, k[0], s[0], p[0], include_pad != 0) : ops::max_pool1d(X, k[0], s[0], p[0]);
+        if (nsp == 2)
+            return is_avg ? ops::avg_pool2d(X, k, s, p, include_pad != 0) : ops::max_pool2d(X, k, s, p);
+        return is_avg ? ops::avg_pool3d(X, k, s, p, include_pad != 0) : ops::max_pool3d(X, k, s, p);
+    });
+}
+// what: 0 sort values, 1 argsort, 2 topk values, 3 topk indices (descending doubles as `largest`)
+void *axref_sort(void *x, int what, int axis, int descending, int k) {
+    return guard([&] {
+        const Tensor &X = H(x)->t;
+        if (what == 0)
+            return ops::sort(X, axis, descending != 0);
+        if (what == 1)
+            return ops::argsort(X, axis, descending != 0);
+        auto r = ops::topk(X, k, axis, descending != 0, true);
+        return what == 2 ? r.first : r.second;
+    });
+}
+void *axref_masked_select(void *x, void *mask) {
+    return guard([&] { return ops::masked_select(H(x)->t, H(mask)->t); });
 }
 
 // Wall-clock helper for the CPU baseline: runs `iters` x (build lazy op + force) for a small menu of

@@ -27,7 +27,8 @@ GPU_SUITES = ["test_cpu_gpu_parity", "test_fusion", "test_fusion_extended", "tes
               "test_tensor_views", "test_tensor_shape_ops", "test_tensor_gather_scatter", "test_tensor_basic",
               "test_custom_functors", "test_nn_activation_modules", "test_nn_ergonomics", "test_nn_groupnorm",
               "test_nn_positional", "test_tensor_numpy_ops", "test_tensor_random", "test_nn_module", "test_tensor_indexing",
-              "test_shape_ops_extended", "test_conv_transpose", "test_interpolate"]
+              "test_shape_ops_extended", "test_conv_transpose", "test_interpolate", "test_pooling", "test_sort_topk",
+              "test_nn_pooling_modules", "test_conv2d"]
 
 # Known divergence, kept on purpose: TensorOperations.UnsupportedGpuOpFallback expects pow(3, 4) == 81 within 1e-6 (what
 # MPSGraph returns). The reference's CPU backend itself returns 81.00000763 on same-shape contiguous operands (Highway
@@ -182,3 +183,20 @@ def test_plan_cache_hits_and_misses(gpu):
     j = json.loads(lines[-1])
     assert j["all_ok"] and r.returncode == 0, j["failed"]
     assert j["cases"] >= 30
+
+
+@pytest.mark.gpu
+def test_pool_sort_masked_select_match_cpu_backend(gpu):
+    """Pooling (max / avg, 1-3 d, adaptive, four float dtypes), sort / argsort / topk and masked_select
+    through the reference API on Device::GPU against the same call on Device::CPU: bit-identical values (and positions, for
+    distinct keys), results on the GPU, zero device->host bytes inside the call (masked_select: the 8-byte count)."""
+    _need_build()
+    exe = os.path.join(BUILD, "op_surface_parity")
+    if not os.path.exists(exe):
+        pytest.skip("op_surface_parity not built")
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=900)
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert lines, r.stdout[-2000:] + r.stderr[-2000:]
+    j = json.loads(lines[-1])
+    assert j["all_ok"] and r.returncode == 0, j["failed"]
+    assert j["cases"] >= 90
