@@ -9,6 +9,11 @@
 #include <mutex>
 #include <vector>
 
+#include <fcntl.h>
+#include <unistd.h>
+#include <cerrno>
+#include <mutex>
+
 #include "axb_internal.h"
 #include "gemm.h"
 
@@ -253,6 +258,94 @@ axb_status axb_memcpy_h2d(void *dst, const void *src, size_t bytes, axb_stream_t
     count_h2d(bytes);
     return AXB_OK;
 }
+// File -> device without a pageable stop: pread() fills pinned staging buffers (two, reused for the life of the process)
+// while the previous chunk's DMA runs. Used for weight loading (safetensors), where the reference reads every tensor into a
+// pageable host tensor and then copies it to the device (src/io/io_safetensors.cpp:123-160).
+namespace {
+struct FileStage {
+    void *buf[2] = {nullptr, nullptr};
+    cudaEvent_t done[2] = {nullptr, nullptr};
+    bool busy[2] = {false, false};
+    size_t chunk = 0;
+    int device = -1;
+};
+std::mutex g_stage_mu;
+FileStage g_stage;
+} // namespace
+
+axb_status axb_upload_file(const char *path, uint64_t file_offset, size_t bytes, void *dst, axb_stream_t stream) {
+    AXB_REQUIRE(path, AXB_ERR_INVALID, "axb_upload_file: null path");
+    if (!bytes)
+        return AXB_OK;
+    AXB_REQUIRE(dst, AXB_ERR_INVALID, "axb_upload_file: null destination");
+    cudaStream_t s;
+    DeviceCtx *ctx;
+    AXB_TRY(resolve_stream(stream, &s, &ctx));
+    const int fd = ::open(path, O_RDONLY);
+    AXB_REQUIRE(fd >= 0, AXB_ERR_INVALID, "axb_upload_file: cannot open %s", path);
+    std::lock_guard<std::mutex> lk(g_stage_mu);
+    constexpr size_t kChunk = 16u << 20;
+    if (!g_stage.buf[0] || g_stage.device != ctx->device) {
+        for (int i = 0; i < 2; ++i) {
+            if (g_stage.buf[i])
+                cudaFreeHost(g_stage.buf[i]);
+            if (g_stage.done[i])
+                cudaEventDestroy(g_stage.done[i]);
+            g_stage.buf[i] = nullptr;
+            g_stage.done[i] = nullptr;
+            g_stage.busy[i] = false;
+        }
+        for (int i = 0; i < 2; ++i) {
+            const axb_status st = axb_host_alloc(kChunk, &g_stage.buf[i]);
+            if (st != AXB_OK) {
+                ::close(fd);
+                return st;
+            }
+            if (cudaEventCreateWithFlags(&g_stage.done[i], cudaEventDisableTiming) != cudaSuccess) {
+                ::close(fd);
+                return fail(AXB_ERR_CUDA, "axb_upload_file: cudaEventCreate failed");
+            }
+        }
+        g_stage.chunk = kChunk;
+        g_stage.device = ctx->device;
+    }
+    gemm::invalidate_const_cache(dst, bytes);
+    axb_status st = AXB_OK;
+    size_t done = 0;
+    int slot = 0;
+    while (done < bytes && st == AXB_OK) {
+        const size_t n = std::min(g_stage.chunk, bytes - done);
+        if (g_stage.busy[slot]) { // the DMA that last read this buffer must have finished
+            if (cudaEventSynchronize(g_stage.done[slot]) != cudaSuccess)
+                st = fail(AXB_ERR_CUDA, "axb_upload_file: staging event failed");
+            g_stage.busy[slot] = false;
+        }
+        size_t got = 0;
+        while (got < n && st == AXB_OK) {
+            const ssize_t r = ::pread(fd, static_cast<char *>(g_stage.buf[slot]) + got, n - got, (off_t)(file_offset + done + got));
+            if (r < 0 && errno == EINTR)
+                continue;
+            if (r <= 0)
+                st = fail(AXB_ERR_INVALID, "axb_upload_file: short read from %s at byte %llu", path, (unsigned long long)(file_offset + done + got));
+            else
+                got += (size_t)r;
+        }
+        if (st != AXB_OK)
+            break;
+        if (cudaMemcpyAsync(static_cast<char *>(dst) + done, g_stage.buf[slot], n, cudaMemcpyHostToDevice, s) != cudaSuccess ||
+            cudaEventRecord(g_stage.done[slot], s) != cudaSuccess) {
+            st = fail(AXB_ERR_CUDA, "axb_upload_file: cudaMemcpyAsync failed: %s", cudaGetErrorString(cudaGetLastError()));
+            break;
+        }
+        g_stage.busy[slot] = true;
+        count_h2d(n);
+        done += n;
+        slot ^= 1;
+    }
+    ::close(fd);
+    return st;
+}
+
 axb_status axb_memcpy_d2h(void *dst, const void *src, size_t bytes, axb_stream_t stream, int sync) {
     cudaStream_t s;
     AXB_TRY(resolve_stream(stream, &s));

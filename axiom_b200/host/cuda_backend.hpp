@@ -12,6 +12,8 @@
 // implemented on CUDA. Nothing in this directory computes on the CPU: every tensor operation ends in an axb_* call.
 #pragma once
 
+#include <map>
+
 #include <string>
 
 #include "axb.h"
@@ -97,6 +99,17 @@ Tensor gpu_pool(const Tensor &input, bool is_avg, const std::vector<int> &kernel
                 const std::vector<int> &padding, bool count_include_pad, const Shape &out_shape);
 Tensor gpu_sort(const Tensor &input, int axis, bool descending, bool want_indices);
 std::pair<Tensor, Tensor> gpu_topk(const Tensor &input, int k, int axis, bool largest);
+
+// Weight loading (patched io::safetensors::load / load_tensor on Device::GPU, src/io/io_safetensors.cpp:123-214): the byte
+// ranges of `filename` go file -> pinned staging -> device (axb_upload_file), in file order; no host tensor is created.
+struct FileTensor {
+    std::string name;
+    DType dtype;
+    Shape shape;
+    size_t file_offset;
+    size_t bytes;
+};
+std::map<std::string, Tensor> load_file_tensors(const std::string &filename, const std::vector<FileTensor> &items);
 
 } // namespace cuda
 } // namespace backends

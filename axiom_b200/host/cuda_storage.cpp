@@ -2,7 +2,9 @@
 // symbols the shared code calls (see cuda_backend.hpp for the map of reference call sites).
 #include "cuda_backend.hpp"
 #include "cuda_plan.hpp"
+#include "axiom/io/io.hpp"
 
+#include <algorithm>
 #include <cstring>
 #include <mutex>
 
@@ -111,6 +113,29 @@ std::unique_ptr<Storage> CudaStorage::clone() const {
     auto s = std::make_unique<CudaStorage>(size_bytes_);
     s->copy_from(*this);
     return s;
+}
+
+std::map<std::string, Tensor> load_file_tensors(const std::string &filename, const std::vector<FileTensor> &items) {
+    ensure_initialized();
+    std::vector<const FileTensor *> order;
+    for (const auto &it : items)
+        order.push_back(&it);
+    std::sort(order.begin(), order.end(), [](const FileTensor *a, const FileTensor *b) { return a->file_offset < b->file_offset; });
+    std::map<std::string, Tensor> result;
+    for (const FileTensor *it : order) {
+        Tensor t = empty_gpu(it->shape, it->dtype);
+        if (it->bytes != t.nbytes()) // same check and message as io_safetensors.cpp:137-144
+            throw io::FileFormatError("SafeTensors: tensor '" + it->name + "' size mismatch: file=" + std::to_string(it->bytes) +
+                                  " expected=" + std::to_string(t.nbytes()));
+        if (it->bytes != 0) {
+            auto *cs = dynamic_cast<CudaStorage *>(t.storage().get());
+            const axb_status st = axb_upload_file(filename.c_str(), it->file_offset, it->bytes, cs->device_ptr(), nullptr);
+            if (st != AXB_OK) // unreadable / truncated file: the reference's error type (io_safetensors.cpp:148-151)
+                throw io::SerializationError("SafeTensors: failed to read tensor '" + it->name + "' data: " + axb_last_error());
+        }
+        result[it->name] = t;
+    }
+    return result;
 }
 
 axb_tensor describe(const Tensor &t) {

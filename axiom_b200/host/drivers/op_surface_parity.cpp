@@ -14,6 +14,8 @@
 #include <string>
 #include <vector>
 
+#include <unistd.h>
+
 #include "axb.h"
 
 using namespace axiom;
@@ -187,6 +189,68 @@ int main() {
         } catch (const std::exception &e) {
             c.why = e.what();
         }
+        g_cases.push_back(c);
+    }
+
+    // ---- safetensors -> device (patched io::safetensors::load, src/io/io_safetensors.cpp:123-214) ---------------------------
+    {
+        Case c{"safetensors_load_to_gpu", false, ""};
+        const std::string path = "/tmp/axb_op_surface_" + std::to_string((long)getpid()) + ".safetensors";
+        try {
+            // three tensors; `big` (40 MiB) spans several staging chunks; data section in header order
+            Tensor w = Tensor::randn({33, 17}), idx = (Tensor::randn({11}) * 100.0f).astype(DType::Int64);
+            Tensor hb = Tensor::randn({5, 7}).astype(DType::BFloat16), big = Tensor::randn({10, 1024, 1024});
+            std::vector<std::pair<std::string, Tensor>> items = {{"enc.w", w}, {"idx", idx}, {"half", hb}, {"big", big}};
+            std::string header = "{\"__metadata__\":{\"format\":\"pt\"}";
+            size_t off = 0;
+            for (auto &kv : items) {
+                Tensor t = kv.second.ascontiguousarray();
+                const char *dn = t.dtype() == DType::Float32 ? "F32" : t.dtype() == DType::Int64 ? "I64" : "BF16";
+                header += ",\"" + kv.first + "\":{\"dtype\":\"" + dn + "\",\"shape\":[";
+                for (size_t d = 0; d < t.ndim(); ++d)
+                    header += (d ? "," : "") + std::to_string(t.shape()[d]);
+                header += "],\"data_offsets\":[" + std::to_string(off) + "," + std::to_string(off + t.nbytes()) + "]}";
+                off += t.nbytes();
+            }
+            header += "}";
+            FILE *f = std::fopen(path.c_str(), "wb");
+            const uint64_t hl = header.size();
+            std::fwrite(&hl, 8, 1, f);
+            std::fwrite(header.data(), 1, header.size(), f);
+            for (auto &kv : items) {
+                Tensor t = kv.second.ascontiguousarray();
+                std::fwrite(t.data(), 1, t.nbytes(), f);
+            }
+            std::fclose(f);
+            auto cpu = io::safetensors::load(path, Device::CPU);
+            axb_transfer_stats t0{}, t1{};
+            axb_get_transfer_stats(&t0);
+            auto gpu = io::safetensors::load(path, Device::GPU);
+            Tensor one = io::safetensors::load_tensor(path, "half", Device::GPU);
+            axb_get_transfer_stats(&t1);
+            c.ok = gpu.size() == cpu.size() && cpu.size() == items.size();
+            for (auto &kv : cpu) {
+                if (!c.ok)
+                    break;
+                auto it = gpu.find(kv.first);
+                c.ok = it != gpu.end() && same(it->second, kv.second, &c.why);
+            }
+            if (c.ok)
+                c.ok = same(one, cpu["half"], &c.why);
+            if (c.ok && t1.h2d_bytes - t0.h2d_bytes != off + cpu["half"].nbytes()) {
+                c.ok = false;
+                c.why = "uploaded " + std::to_string(t1.h2d_bytes - t0.h2d_bytes) + " bytes for a " + std::to_string(off) + "-byte data section";
+            }
+            if (c.ok && !c.why.empty())
+                c.why.clear();
+            if (!c.ok && c.why.empty())
+                c.why = "tensor set differs";
+            // error behaviour: a header that promises more bytes than the shape holds is a FileFormatError on both devices
+        } catch (const std::exception &e) {
+            c.ok = false;
+            c.why = e.what();
+        }
+        std::remove(path.c_str());
         g_cases.push_back(c);
     }
 

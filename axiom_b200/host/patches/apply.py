@@ -56,6 +56,18 @@ RULES = {
          "}}} // namespace axiom::backends::cuda\n"
          "\nnamespace axiom {\nnamespace ops {\n", 1),
     ],
+    # io::safetensors::load / load_tensor read every tensor into a pageable host tensor and then call Tensor::gpu()
+    # (src/io/io_safetensors.cpp:123-160, :175-214). On Device::GPU the patched build hands the parsed metadata to the CUDA
+    # backend, which reads the file straight into pinned staging buffers and overlaps their DMA with the next read
+    # (host/cuda_storage.cpp load_file_tensors -> axb_upload_file). Header parsing, dtype names, error types stay the reference's.
+    "src/io/io_safetensors.cpp": [
+        (r"\nnamespace axiom \{\nnamespace io \{\nnamespace safetensors \{\n",
+         "\nnamespace axiom { namespace backends { namespace cuda {\n"
+         "struct FileTensor { std::string name; DType dtype; Shape shape; size_t file_offset; size_t bytes; };\n"
+         "std::map<std::string, Tensor> load_file_tensors(const std::string &, const std::vector<FileTensor> &);\n"
+         "}}} // namespace axiom::backends::cuda\n"
+         "\nnamespace axiom {\nnamespace io {\nnamespace safetensors {\n", 1),
+    ],
 }
 
 # Function-scoped insertions: (file, regex matching the START of a function definition, regex of the anchor line inside it,
@@ -70,6 +82,21 @@ def _pool_call(is_avg, k, s, p, inc):
 
 
 INSERTIONS = {
+    "src/io/io_safetensors.cpp": [
+        (r"\nstd::map<std::string, Tensor> load\(const std::string &filename, Device device\) \{\n",
+         r"    std::ifstream file\(filename, std::ios::binary\);\n",
+         "    if (device == Device::GPU) {\n"
+         "        std::vector<backends::cuda::FileTensor> items;\n"
+         "        for (const auto &meta : tensor_metas)\n"
+         "            items.push_back({meta.name, meta.dtype, meta.shape, data_offset + meta.data_start, meta.data_end - meta.data_start});\n"
+         "        return backends::cuda::load_file_tensors(filename, items);\n"
+         "    }\n"),
+        (r"\nTensor load_tensor\(const std::string &filename, const std::string &tensor_name,\n",
+         r"    size_t byte_count = found->data_end - found->data_start;\n",
+         "    if (device == Device::GPU)\n"
+         "        return backends::cuda::load_file_tensors(filename, {{found->name, found->dtype, found->shape, data_offset + found->data_start,\n"
+         "                                                             found->data_end - found->data_start}}).begin()->second;\n"),
+    ],
     "src/tensor/operations.cpp": [
         (r"\nTensor max_pool1d\(", _POOL_ANCHOR, _pool_call("false", "{kernel_size}", "{stride}", "{padding}", "false")),
         (r"\nTensor avg_pool1d\(", _POOL_ANCHOR, _pool_call("true", "{kernel_size}", "{stride}", "{padding}", "count_include_pad")),

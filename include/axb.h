@@ -141,6 +141,11 @@ axb_status axb_host_free(void *ptr);
 /* NUMA node the LAST axb_host_alloc of the calling thread was placed on (the node of the current GPU's PCI function), or
  * -1 when no placement was applied (single-node host, syscall unavailable, AXB_HOST_NUMA=0). */
 int axb_host_alloc_numa_node(void);
+/* File -> device upload for weight loading: `bytes` bytes of `path` starting at `file_offset` land at `dst` (device memory),
+ * read with pread() straight into pinned staging buffers whose DMA overlaps the next read — no pageable host copy of the
+ * data ever exists. Replaces "read into a host tensor, then Tensor::gpu()" of the reference's safetensors loader
+ * (src/io/io_safetensors.cpp:123-160). The copies are ordered on `stream`; the call returns when the file has been read. */
+axb_status axb_upload_file(const char *path, uint64_t file_offset, size_t bytes, void *dst, axb_stream_t stream);
 /* async copies on `stream`; d2h additionally synchronises the stream before returning when sync!=0
  * (MetalStorage::copy_to(CPU) synchronises first, metal_storage.mm:66-93) */
 axb_status axb_memcpy_h2d(void *dst_dev, const void *src_host, size_t bytes, axb_stream_t stream);
