@@ -70,6 +70,10 @@ class AxbPlanCacheStats(ctypes.Structure):
     _fields_ = [(n, ctypes.c_uint64) for n in ("entries", "hits", "misses", "evictions")]
 
 
+class AxbHalfLutStats(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_uint64) for n in ("tables", "builds", "hits", "launches")]
+
+
 class AxbJitStats(ctypes.Structure):
     _fields_ = [(n, ctypes.c_uint64) for n in ("mem_hits", "disk_hits", "compiles")]
 
@@ -148,6 +152,7 @@ def lib() -> ctypes.CDLL:
         "axb_elementwise": (i32, [I, i32, T, i32, T, vp]),
         "axb_elementwise_precompile": (i32, [I, i32, T, i32, T]),
         "axb_get_jit_stats": (i32, [ctypes.POINTER(AxbJitStats)]),
+        "axb_get_half_lut_stats": (i32, [ctypes.POINTER(AxbHalfLutStats)]),
         "axb_get_plan_cache_stats": (i32, [ctypes.POINTER(AxbPlanCacheStats)]),
         "axb_plan_cache_clear": (i32, []),
         "axb_promote_types": (i32, [i32, i32]),

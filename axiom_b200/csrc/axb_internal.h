@@ -165,6 +165,11 @@ axb_status launch_chain_reduce(const axb_instr *prog, int n_instr, const axb_ten
                                const axb_tensor *shape_desc, int reduce_opk, cudaStream_t s, DeviceCtx *ctx, void **partials,
                                int64_t *n_partials);
 }
+// half_lut.cu: table-lookup evaluation of a chain over one half-precision tensor (*done = false: not applicable)
+namespace lut {
+axb_status try_run(const axb_instr *prog, int n_instr, const axb_tensor *inputs, int n_inputs, const axb_tensor *out, cudaStream_t s,
+                   DeviceCtx *ctx, bool *done);
+}
 // reduce.cu: divisor used by the NEXT Mean reduction of this thread instead of its own element count (the partials of a
 // fused chain + mean stand for `count` elements); consumed by that call
 int64_t &reduce_count_override();

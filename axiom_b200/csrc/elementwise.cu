@@ -1127,6 +1127,12 @@ axb_status axb_elementwise(const axb_instr *prog, int n_instr, const axb_tensor 
     cudaStream_t s;
     DeviceCtx *ctx;
     AXB_TRY(resolve_stream(stream, &s, &ctx));
+    {
+        bool via_table = false; // one half-precision tensor through a transcendental: 65 536-entry lookup (half_lut.cu)
+        AXB_TRY(lut::try_run(prog, n_instr, inputs, n_inputs, out, s, ctx, &via_table));
+        if (via_table)
+            return AXB_OK;
+    }
     Prepared P;
     bool empty = false;
     jit::Kernel k;

@@ -214,6 +214,13 @@ typedef struct axb_plan_cache_stats {
 } axb_plan_cache_stats;
 axb_status axb_get_plan_cache_stats(axb_plan_cache_stats *out);
 axb_status axb_plan_cache_clear(void);
+/* Table-lookup path of the family (csrc/half_lut.cu): a chain over ONE contiguous bf16 / fp16 tensor (>= 2 Mi elements, a
+ * transcendental in it, 2-byte result) is evaluated once on all 65 536 input patterns by the chain kernel itself and then
+ * streamed through a shared-memory lookup — bit-identical by construction, bandwidth-bound instead of instruction-bound. */
+typedef struct axb_half_lut_stats {
+    uint64_t tables, builds, hits, launches;
+} axb_half_lut_stats;
+axb_status axb_get_half_lut_stats(axb_half_lut_stats *out);
 typedef struct axb_jit_stats {
     uint64_t mem_hits, disk_hits, compiles;
 } axb_jit_stats;

@@ -449,3 +449,63 @@ def test_elementwise_host_entry_pipelined_and_plain(gpu, shape, c_view):
     got = _host_chain_config2(a, b, c)
     exp = np.where(c > 0, (np.maximum(a, 0) + np.float32(1)) * b, np.float32(0))
     assert bits_equal(got, exp), (shape, c_view)
+
+
+@pytest.mark.parametrize("dt", ["bf16", "f16"])
+@pytest.mark.parametrize("op", ["exp", "log", "sin", "erf", "tanh", "sigmoid", "silu", "gelu", "cbrt"])
+def test_half_table_path_equals_the_chain_kernel(gpu, op, dt):
+    """Large half-precision tensors under a transcendental go through the 65 536-entry table (csrc/half_lut.cu). The table is
+    the chain kernel's own output on every input pattern, so the two paths must agree bit for bit — checked on a tensor that
+    holds every pattern (NaN payloads, subnormals, infinities included) many times over, with a ragged tail."""
+    import ctypes
+    from axiom_b200 import capi
+    reps = 40
+    bits = np.tile(np.arange(65536, dtype=np.uint16), reps)
+    rng = np.random.default_rng(5)
+    bits = np.concatenate([rng.permutation(bits), np.arange(7, dtype=np.uint16) * 9001])  # 2 621 447 elements, not a multiple of 8
+    small = np.arange(65536, dtype=np.uint16)  # below the table threshold: the chain kernel
+    st0, st1 = capi.AxbHalfLutStats(), capi.AxbHalfLutStats()
+    capi.check(capi.lib().axb_get_half_lut_stats(ctypes.byref(st0)))
+    if dt == "bf16":
+        got = dev.unary(op, dev.DeviceArray.from_numpy(bits, bf16=True)).numpy()
+        ref_tab = dev.unary(op, dev.DeviceArray.from_numpy(small, bf16=True)).numpy()
+    else:
+        got = dev.unary(op, dev.DeviceArray.from_numpy(bits.view(np.float16))).numpy().view(np.uint16)
+        ref_tab = dev.unary(op, dev.DeviceArray.from_numpy(small.view(np.float16))).numpy().view(np.uint16)
+    capi.check(capi.lib().axb_get_half_lut_stats(ctypes.byref(st1)))
+    assert st1.launches == st0.launches + 1, "the large call did not take the table path"
+    assert np.array_equal(got, ref_tab[bits]), (op, dt)
+
+
+def test_half_table_path_for_a_chain_with_immediates_and_fallbacks(gpu):
+    """gelu(x) * 1.5 + 0.25 over one bf16 tensor is still a function of 16 bits -> table; two tensor operands, a cheap chain
+    or a strided operand stay on the chain kernel. Results equal the oracle either way."""
+    import ctypes
+    from axiom_b200 import capi
+    rng = np.random.default_rng(6)
+    x = as_bf16(rand_f32(rng, (2048, 1100), 3.0))
+    dx = dev.DeviceArray.from_numpy(x, bf16=True)
+    B = capi.BF16
+    prog = [capi.make_instr(capi.OP["gelu"], B, 0),
+            capi.make_instr(capi.OP["mul"], B, capi.SRC_VALUE(0), capi.SRC_IMM, imm=1.5),
+            capi.make_instr(capi.OP["add"], B, capi.SRC_VALUE(1), capi.SRC_IMM, imm=0.25)]
+
+    def launches():
+        st = capi.AxbHalfLutStats()
+        capi.check(capi.lib().axb_get_half_lut_stats(ctypes.byref(st)))
+        return st.launches
+
+    n0 = launches()
+    got = dev.elementwise(prog, [dx]).numpy()
+    assert launches() == n0 + 1
+    v, _ = ao.unary("gelu", x, ao.BF16)
+    v, _ = ao.binary("mul", v, ao.BF16, as_bf16(np.array([1.5], np.float32)), ao.BF16)
+    v, _ = ao.binary("add", v, ao.BF16, as_bf16(np.array([0.25], np.float32)), ao.BF16)
+    assert np.array_equal(got, v)
+    n1 = launches()
+    dev.unary("relu", dx)                                   # cheap: stays bandwidth-bound on the chain kernel
+    dev.binary("mul", dev.unary("exp", dx.T()), dx.T())     # strided operand / two tensors
+    assert launches() == n1
+    got_t = dev.unary("exp", dx.T()).numpy()
+    e, _ = ao.unary("exp", np.ascontiguousarray(x.T), ao.BF16)
+    assert np.array_equal(got_t, e)
