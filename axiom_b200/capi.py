@@ -186,6 +186,7 @@ def lib() -> ctypes.CDLL:
         "axb_gather": (i32, [T, i32, T, T, vp]),
         "axb_index_select": (i32, [T, i32, T, T, vp]),
         "axb_conv2d": (i32, [T, T, T, pi32, pi32, pi32, i32, T, vp]),
+        "axb_conv": (i32, [T, T, T, i32, pi32, pi32, pi32, i32, i32, T, vp]),
         "axb_conv_transpose": (i32, [T, T, T, i32, pi32, pi32, pi32, i32, T, vp]),
         "axb_interpolate": (i32, [T, i32, i32, T, vp]),
         "axb_upload_file": (i32, [ctypes.c_char_p, u64, sz, vp, vp]),

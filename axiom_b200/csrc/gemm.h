@@ -46,6 +46,20 @@ void invalidate_const_cache(const void *ptr, size_t bytes);
 axb_const_cache_stats const_cache_stats();
 bool const_cache_active();
 
+// Convolution as an implicit GEMM on the tensor cores (gemm_tcgen05.cu conv_tc): NC(H)W input, (C_out, C_in, KH, KW) weights,
+// contiguous (N, C_out, OH, OW) output of the same dtype (float32 via the exact three-piece bf16 split, bf16, fp16),
+// groups == 1. 1-D convolutions pass H = KH = OH = 1. Sets *done when it ran; small / unsupported problems are left alone.
+struct ConvDesc {
+    const char *x, *w, *bias;
+    char *out;
+    int32_t dtype, bias_dtype, act;
+    int64_t N, Cin, H, W, Cout, KH, KW, OH, OW;
+    int64_t x_s[4], w_s[4]; // byte strides
+    int64_t bias_s;
+    int32_t sh, sw, ph, pw, dh, dw;
+};
+axb_status conv_tc(const ConvDesc &d, DeviceCtx *ctx, cudaStream_t s, bool *done);
+
 // Runs the tensor-core path when the problem qualifies (sets *done), otherwise leaves it to the SIMT kernel.
 axb_status try_tcgen05(const Desc &d, int adt, int bdt, int cdt, DeviceCtx *ctx, cudaStream_t s, bool *done);
 

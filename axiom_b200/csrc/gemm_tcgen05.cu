@@ -47,6 +47,7 @@ constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256
 constexpr int NUM_THREADS = 320; // TMA producer, MMA issuer, 8 epilogue warps
 constexpr uint32_t TMEM_COLS = 512;
 
+constexpr int kMaxTaps = 64;
 struct TcParams {
     int64_t M, N, K, batch;
     int32_t tiles_m, tiles_n;
@@ -64,6 +65,14 @@ struct TcParams {
     int64_t Kp;
     int32_t bn; // tile width in N (64 / 128 / 256)
     int32_t group_m; // CTA-pair kernel: tile rows per band (see pair_tile_coords)
+    // implicit-GEMM convolution (see conv_tc): conv_taps > 0 turns the K loop into (filter tap, 64-channel block) steps.
+    // A is [tap][C_out][pieces * Cp] (3-D map, tap in the batch coordinate), B the phase-split channels-last input
+    // [image * phases + phase][H'][W'][pieces * Cp] (4-D map); tap t reads B at column n0 + conv_qw[t], row oh + conv_qh[t],
+    // plane image * conv_phases + conv_ph[t] — out-of-range coordinates are zero-filled by TMA, which IS the padding.
+    // "batch" counts (image, output row) pairs: b = image * conv_oh + oh; c_hs is the byte stride of an output row.
+    int32_t conv_taps, conv_cblocks, conv_oh, conv_phases;
+    int64_t c_hs;
+    int16_t conv_qw[kMaxTaps], conv_qh[kMaxTaps], conv_ph[kMaxTaps];
 };
 
 // piece (0 = hi, 1 = mid, 2 = lo) of A and B for combination c, smallest products first
@@ -93,6 +102,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1, int c2) {
     asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
                  ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
+                 "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
                  : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -157,7 +171,9 @@ __device__ __forceinline__ void epilogue_tile(const TcParams &p, int64_t b, int 
                                               int half, int lane, int ewarp, uint32_t staging_base) {
     const bool out_f32 = p.out_dtype == AXB_F32, out_bf16 = p.out_dtype == AXB_BF16;
     const int osz = out_f32 ? 4 : 2;
-    const bool c_vec = (p.c_cs == osz) && ((reinterpret_cast<uintptr_t>(p.c) | (uintptr_t)p.c_rs | (uintptr_t)p.c_bs) % 16 == 0);
+    // convolution: b = image * conv_oh + output row (see TcParams)
+    const int64_t cbase = p.conv_taps ? (b / p.conv_oh) * p.c_bs + (b % p.conv_oh) * p.c_hs : b * p.c_bs;
+    const bool c_vec = (p.c_cs == osz) && ((reinterpret_cast<uintptr_t>(p.c) | (uintptr_t)p.c_rs | (uintptr_t)p.c_bs | (uintptr_t)p.c_hs) % 16 == 0);
     // bias as a row vector shared by all rows (nn::Linear): read once per chunk with vector loads
     const int bsz = p.bias_dtype == AXB_F32 ? 4 : 2;
     const bool bias_vec = p.bias && p.bias_rs == 0 && p.bias_cs == bsz && ((reinterpret_cast<uintptr_t>(p.bias) | (uintptr_t)p.bias_bs) % 16 == 0);
@@ -177,7 +193,7 @@ __device__ __forceinline__ void epilogue_tile(const TcParams &p, int64_t b, int 
         }
     };
     const int64_t m = m0 + q * 32 + lane;
-    char *crow = p.c + b * p.c_bs + m * p.c_rs;
+    char *crow = p.c + cbase + m * p.c_rs;
     const char *brow = p.bias ? p.bias + b * p.bias_bs + m * p.bias_rs : nullptr;
 #pragma unroll 1
     for (int c = half; c < BN_ / 32; c += 2) {
@@ -288,7 +304,7 @@ __device__ __forceinline__ void epilogue_tile(const TcParams &p, int64_t b, int 
                                  : "r"(tile + rr * 128u + ((cw ^ (rr & 7)) << 4)));
                     const int64_t mm = (int64_t)m0 + q * 32 + rr;
                     if (mm < p.M)
-                        *reinterpret_cast<uint4 *>(p.c + b * p.c_bs + mm * p.c_rs + (nbase + cw * 4) * 4) = w;
+                        *reinterpret_cast<uint4 *>(p.c + cbase + mm * p.c_rs + (nbase + cw * 4) * 4) = w;
                 }
                 __syncwarp();
             } else {
@@ -337,7 +353,7 @@ __device__ __forceinline__ void epilogue_tile(const TcParams &p, int64_t b, int 
                              : "r"(tile + rr * 64u + ((cw ^ ((rr >> 1) & 3)) << 4)));
                 const int64_t mm = (int64_t)m0 + q * 32 + rr;
                 if (mm < p.M)
-                    *reinterpret_cast<uint4 *>(p.c + b * p.c_bs + mm * p.c_rs + (nbase + cw * 8) * 2) = w;
+                    *reinterpret_cast<uint4 *>(p.c + cbase + mm * p.c_rs + (nbase + cw * 8) * 2) = w;
             }
             __syncwarp();
         } else {
@@ -413,10 +429,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                         mbar_wait(empty_bar(stage), phase ^ 1u);
                         mbar_expect_tx(full_bar(stage), G_STAGE);
                         const uint32_t sa = smem + stage * G_STAGE, sb = sa + 3 * A_BYTES;
+                        if (p.conv_taps) { // implicit-GEMM convolution: k-block = (tap, channel block)
+                            const int tap = kb / p.conv_cblocks, c0 = (kb - tap * p.conv_cblocks) * BK;
+                            const int img = (int)(b / p.conv_oh), oh = (int)(b - (int64_t)img * p.conv_oh);
 #pragma unroll
-                        for (int pc = 0; pc < 3; ++pc) {
-                            tma_load_3d(sa + pc * A_BYTES, &tma_a, full_bar(stage), pc * (int)p.Kp + kb * BK, m0, ba);
-                            tma_load_3d(sb + pc * (BN_ * BK * 2), &tma_b, full_bar(stage), pc * (int)p.Kp + kb * BK, n0, bb);
+                            for (int pc = 0; pc < 3; ++pc) {
+                                tma_load_3d(sa + pc * A_BYTES, &tma_a, full_bar(stage), pc * (int)p.Kp + c0, m0, tap);
+                                tma_load_4d(sb + pc * (BN_ * BK * 2), &tma_b, full_bar(stage), pc * (int)p.Kp + c0, n0 + p.conv_qw[tap],
+                                            oh + p.conv_qh[tap], img * p.conv_phases + p.conv_ph[tap]);
+                            }
+                        } else {
+#pragma unroll
+                            for (int pc = 0; pc < 3; ++pc) {
+                                tma_load_3d(sa + pc * A_BYTES, &tma_a, full_bar(stage), pc * (int)p.Kp + kb * BK, m0, ba);
+                                tma_load_3d(sb + pc * (BN_ * BK * 2), &tma_b, full_bar(stage), pc * (int)p.Kp + kb * BK, n0, bb);
+                            }
                         }
                         if (++stage == G_STAGES) {
                             stage = 0;
@@ -434,6 +461,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                         const int c = kb / p.kbp, kk = (kb - c * p.kbp) * BK;
                         k0 = split_piece_a(c) * (int)p.Kp + kk;
                         k0b = split_piece_b(c) * (int)p.Kp + kk;
+                    }
+                    if (!A_MN && !B_MN && p.conv_taps) { // implicit-GEMM convolution, half-precision operands
+                        const int tap = kb / p.conv_cblocks, c0 = (kb - tap * p.conv_cblocks) * BK;
+                        const int img = (int)(b / p.conv_oh), oh = (int)(b - (int64_t)img * p.conv_oh);
+                        tma_load_3d(sa, &tma_a, full_bar(stage), c0, m0, tap);
+                        tma_load_4d(sb, &tma_b, full_bar(stage), c0, n0 + p.conv_qw[tap], oh + p.conv_qh[tap],
+                                    img * p.conv_phases + p.conv_ph[tap]);
+                        if (++stage == STAGES) {
+                            stage = 0;
+                            phase ^= 1u;
+                        }
+                        continue;
                     }
                     if (!A_MN) {
                         tma_load_3d(sa, &tma_a, full_bar(stage), k0, m0, ba); // box {64 k, 128 m}
@@ -1242,7 +1281,220 @@ bool use_pair(const Desc &d, int bn, int sm_count) {
     return tiles >= 2 * (sm_count / 2);
 }
 
+
+// ---- implicit-GEMM convolution --------------------------------------------------------------------------------------------
+// out[n, co, oh, ow] = sum over (kh, kw, ci) of w[co, ci, kh, kw] * x[n, ci, oh*sh + kh*dh - ph, ow*sw + kw*dw - pw]
+// is, for one output row (n, oh), the GEMM  C[co][ow] = sum over taps t = (kh, kw) of  W_t[co][ci] . X_t[ci][ow]  where X_t is
+// the input row shifted by the tap. Nothing is gathered into an im2col matrix: the K loop of gemm_tc_kernel walks (tap,
+// 64-channel block) steps and the TMA load of the B tile simply starts at the shifted coordinate — columns / rows that fall
+// outside the image come back as zeros (TMA out-of-bounds fill), which is exactly the convolution's zero padding.
+// Two preparation passes put the operands into the K-major form the kernel consumes:
+//   conv_prep_x   NC(H)W -> channels-last, de-interleaved by stride phase: [image * sh*sw + rh*sw + rw][H'][W'][pieces * Cp]
+//                 (h = h'*sh + rh, w = w'*sw + rw), so a strided convolution also reads unit-stride rows; fp32 inputs are
+//                 written as their three bf16 pieces (the exact split of try_split_f32), half inputs are transposed as is
+//   conv_prep_w   (C_out, C_in, KH, KW) -> [tap][C_out][pieces * Cp]
+// Reference being replaced: the scalar loops of ops::conv1d / conv2d (src/tensor/operations.cpp:2968-3330) and the MPSGraph
+// lowering (src/backends/metal/mpsgraph_graph_compiler.mm:365-405).
+struct ConvPrepX {
+    const char *x;
+    uint16_t *dst;
+    int64_t xs[4];     // byte strides of (N, C, H, W)
+    int64_t C, H, W, Cp, Hq, Wq;
+    int32_t sh, sw, pieces, src_f32;
+    int32_t wtiles;
+};
+// block (32, 8): a 32 (channels) x 32 (w') tile is read along w' and written along channels
+__global__ void __launch_bounds__(256) conv_prep_x_kernel(const __grid_constant__ ConvPrepX q) {
+    __shared__ float tile[32][33];
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int wt = blockIdx.x % q.wtiles, ct = blockIdx.x / q.wtiles;
+    const int64_t hq = blockIdx.y, plane = blockIdx.z;
+    const int phases = q.sh * q.sw;
+    const int64_t n = plane / phases;
+    const int ph = (int)(plane - n * phases), rh = ph / q.sw, rw = ph - rh * q.sw;
+    const int64_t ih = hq * q.sh + rh;
+    const int64_t c0 = (int64_t)ct * 32, w0 = (int64_t)wt * 32;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { // c = c0 + ty + 8 i, w' = w0 + tx
+        const int64_t c = c0 + ty + 8 * i, wq = w0 + tx, iw = wq * q.sw + rw;
+        float v = 0.0f;
+        if (c < q.C && ih < q.H && wq < q.Wq && iw < q.W) {
+            const char *sp = q.x + n * q.xs[0] + c * q.xs[1] + ih * q.xs[2] + iw * q.xs[3];
+            v = q.src_f32 ? *reinterpret_cast<const float *>(sp) : __uint_as_float((uint32_t) * reinterpret_cast<const uint16_t *>(sp));
+        }
+        tile[ty + 8 * i][tx] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { // w' = w0 + ty + 8 i, c = c0 + tx
+        const int64_t wq = w0 + ty + 8 * i, c = c0 + tx;
+        if (wq >= q.Wq || c >= q.Cp)
+            continue;
+        const float v = tile[tx][ty + 8 * i];
+        uint16_t *row = q.dst + (((plane * q.Hq + hq) * q.Wq + wq) * q.pieces) * q.Cp + c;
+        if (q.src_f32) {
+            uint16_t h, m, l;
+            split3(v, h, m, l);
+            row[0] = h;
+            row[q.Cp] = m;
+            row[2 * q.Cp] = l;
+        } else {
+            row[0] = (uint16_t)__float_as_uint(v); // the 16 raw bits travelled in the low half
+        }
+    }
+}
+struct ConvPrepW {
+    const char *w;
+    uint16_t *dst;
+    int64_t ws[4]; // byte strides of (C_out, C_in, KH, KW)
+    int64_t Cout, Cin, Cp, KH, KW;
+    int32_t pieces, src_f32;
+    int64_t total; // taps * Cout * Cp
+};
+__global__ void __launch_bounds__(256) conv_prep_w_kernel(const __grid_constant__ ConvPrepW q) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < q.total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t c = i % q.Cp, t1 = i / q.Cp, co = t1 % q.Cout, tap = t1 / q.Cout;
+        const int64_t kh = tap / q.KW, kw = tap - kh * q.KW;
+        uint16_t *row = q.dst + ((tap * q.Cout + co) * q.pieces) * q.Cp + c;
+        if (q.src_f32) {
+            const float v = c < q.Cin ? *reinterpret_cast<const float *>(q.w + co * q.ws[0] + c * q.ws[1] + kh * q.ws[2] + kw * q.ws[3]) : 0.0f;
+            uint16_t h, m, l;
+            split3(v, h, m, l);
+            row[0] = h;
+            row[q.Cp] = m;
+            row[2 * q.Cp] = l;
+        } else {
+            row[0] = c < q.Cin ? *reinterpret_cast<const uint16_t *>(q.w + co * q.ws[0] + c * q.ws[1] + kh * q.ws[2] + kw * q.ws[3]) : (uint16_t)0;
+        }
+    }
+}
+
+axb_status make_map4(CUtensorMap *map, const drv::Api *api, int dtype, const void *base, const uint64_t dims[4], const uint64_t strides[3],
+                     uint32_t b0, uint32_t b1) {
+    cuuint64_t gdim[4] = {dims[0], dims[1], dims[2], dims[3]};
+    cuuint64_t gstr[3] = {strides[0], strides[1], strides[2]};
+    cuuint32_t box[4] = {b0, b1, 1, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = api->TensorMapEncodeTiled(map, dtype == AXB_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4,
+                                           const_cast<void *>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+        return fail(AXB_ERR_CUDA, "cuTensorMapEncodeTiled (4-D) failed: %s", drv::err_str(r));
+    return AXB_OK;
+}
+
 } // namespace
+
+axb_status conv_tc(const ConvDesc &d, DeviceCtx *ctx, cudaStream_t s, bool *done) {
+    *done = false;
+    static const bool off = getenv("AXB_CONV_NO_TC") != nullptr; // A/B switch
+    if (off)
+        return AXB_OK;
+    const bool f32 = d.dtype == AXB_F32;
+    if (!(f32 || d.dtype == AXB_BF16 || d.dtype == AXB_F16))
+        return AXB_OK;
+    const int64_t taps = d.KH * d.KW;
+    const double flops = 2.0 * (double)d.N * (double)d.Cout * (double)d.OH * (double)d.OW * (double)d.Cin * (double)taps;
+    if (taps < 1 || taps > kMaxTaps || flops < 1.0e8 || d.Cout < 32 || d.OW < 16 || d.Cin < 8 || d.N * d.OH >= (1ll << 31))
+        return AXB_OK; // small problems: the preparation passes and the 128-row tile would dominate (gather kernel / im2col path)
+    if (d.sh < 1 || d.sw < 1 || d.sh * d.sw > 64 || d.N * d.sh * d.sw > 65535 || (d.H + d.sh - 1) / d.sh > 65535)
+        return AXB_OK;
+    const drv::Api *api = drv::api();
+    if (!api)
+        return AXB_ERR_CUDA;
+    const int pieces = f32 ? 3 : 1;
+    const int esz = f32 ? 4 : 2;
+    const int64_t Cp = (d.Cin + 63) / 64 * 64, cblocks = Cp / 64;
+    const int64_t Hq = (d.H + d.sh - 1) / d.sh, Wq = (d.W + d.sw - 1) / d.sw, planes = d.N * d.sh * d.sw;
+    int16_t qw[kMaxTaps], qh[kMaxTaps], phs[kMaxTaps];
+    for (int64_t kh = 0; kh < d.KH; ++kh)
+        for (int64_t kw = 0; kw < d.KW; ++kw) {
+            auto floor_split = [](int64_t t, int64_t stride, int64_t *q, int64_t *r) {
+                *r = ((t % stride) + stride) % stride;
+                *q = (t - *r) / stride;
+            };
+            int64_t q_h, r_h, q_w, r_w;
+            floor_split(kh * d.dh - d.ph, d.sh, &q_h, &r_h);
+            floor_split(kw * d.dw - d.pw, d.sw, &q_w, &r_w);
+            if (q_h < -30000 || q_h > 30000 || q_w < -30000 || q_w > 30000)
+                return AXB_OK;
+            const int64_t t = kh * d.KW + kw;
+            qh[t] = (int16_t)q_h;
+            qw[t] = (int16_t)q_w;
+            phs[t] = (int16_t)(r_h * d.sw + r_w);
+        }
+    const size_t x_bytes = (size_t)planes * Hq * Wq * pieces * Cp * 2, w_bytes = (size_t)taps * d.Cout * pieces * Cp * 2;
+    void *xq = nullptr, *wq = nullptr;
+    AXB_TRY(axb_alloc(x_bytes, s, &xq));
+    axb_status st = axb_alloc(w_bytes, s, &wq);
+    if (st != AXB_OK) {
+        axb_free(xq, s);
+        return st;
+    }
+    auto body = [&]() -> axb_status {
+        ConvPrepX px;
+        memset(&px, 0, sizeof px);
+        px.x = d.x; px.dst = static_cast<uint16_t *>(xq);
+        for (int i = 0; i < 4; ++i)
+            px.xs[i] = d.x_s[i];
+        px.C = d.Cin; px.H = d.H; px.W = d.W; px.Cp = Cp; px.Hq = Hq; px.Wq = Wq;
+        px.sh = d.sh; px.sw = d.sw; px.pieces = pieces; px.src_f32 = f32 ? 1 : 0;
+        px.wtiles = (int)((Wq + 31) / 32);
+        const int64_t gx = (int64_t)px.wtiles * (Cp / 32);
+        AXB_REQUIRE(gx < (1ll << 31), AXB_ERR_UNSUPPORTED, "conv: input too wide for the preparation pass");
+        conv_prep_x_kernel<<<dim3((unsigned)gx, (unsigned)Hq, (unsigned)planes), dim3(32, 8), 0, s>>>(px);
+        AXB_CHECK_LAUNCH();
+        ConvPrepW pw;
+        memset(&pw, 0, sizeof pw);
+        pw.w = d.w; pw.dst = static_cast<uint16_t *>(wq);
+        for (int i = 0; i < 4; ++i)
+            pw.ws[i] = d.w_s[i];
+        pw.Cout = d.Cout; pw.Cin = d.Cin; pw.Cp = Cp; pw.KH = d.KH; pw.KW = d.KW; pw.pieces = pieces; pw.src_f32 = f32 ? 1 : 0;
+        pw.total = taps * d.Cout * Cp;
+        conv_prep_w_kernel<<<(unsigned)std::min<int64_t>((pw.total + 255) / 256, (int64_t)ctx->sm_count * 16), 256, 0, s>>>(pw);
+        AXB_CHECK_LAUNCH();
+
+        const int mdt = d.dtype == AXB_F16 ? AXB_F16 : AXB_BF16;
+        const int bn = f32 ? (d.OW <= 64 ? 64 : 128) : pick_bn(d.OW);
+        const uint64_t rowb = (uint64_t)pieces * Cp * 2;
+        CUtensorMap ma, mb;
+        AXB_TRY(make_map(&ma, api, mdt, wq, (uint64_t)pieces * Cp, (uint64_t)d.Cout, (uint64_t)taps, rowb, (uint64_t)d.Cout * rowb, BK, BM));
+        const uint64_t dims[4] = {(uint64_t)pieces * Cp, (uint64_t)Wq, (uint64_t)Hq, (uint64_t)planes};
+        const uint64_t strides[3] = {rowb, (uint64_t)Wq * rowb, (uint64_t)Hq * Wq * rowb};
+        AXB_TRY(make_map4(&mb, api, mdt, xq, dims, strides, BK, (uint32_t)bn));
+        TcParams p;
+        memset(&p, 0, sizeof p);
+        p.M = d.Cout; p.N = d.OW; p.batch = d.N * d.OH;
+        p.K = taps * cblocks * BK; // the plain (half-precision) path derives its k-block count from K
+        p.tiles_m = (int)((d.Cout + BM - 1) / BM);
+        p.bn = bn;
+        p.tiles_n = (int)((d.OW + bn - 1) / bn);
+        p.num_tiles = (int64_t)p.tiles_m * p.tiles_n * p.batch;
+        p.c = d.out;
+        p.c_rs = d.OH * d.OW * esz; p.c_cs = esz; p.c_bs = d.Cout * d.OH * d.OW * esz; p.c_hs = d.OW * esz;
+        p.bias = d.bias; p.bias_rs = d.bias ? d.bias_s : 0; p.bias_cs = 0; p.bias_bs = 0;
+        p.bias_dtype = d.bias_dtype; p.act = d.act; p.out_dtype = d.dtype;
+        p.split = f32 ? 2 : 0; p.kbp = (int)(taps * cblocks); p.Kp = Cp;
+        p.conv_taps = (int)taps; p.conv_cblocks = (int)cblocks; p.conv_oh = (int)d.OH; p.conv_phases = d.sh * d.sw;
+        for (int64_t t = 0; t < taps; ++t) {
+            p.conv_qw[t] = qw[t];
+            p.conv_qh[t] = qh[t];
+            p.conv_ph[t] = phs[t];
+        }
+        const uint32_t fmt = mdt == AXB_BF16 ? 1u : 0u;
+        p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+        return launch_ff(ma, mb, p, ctx->sm_count, s);
+    };
+    st = body();
+    axb_free(xq, s); // stream-ordered: reusable after the GEMM
+    axb_free(wq, s);
+    if (st == AXB_OK) {
+        *done = true;
+        last_path() = 4;
+    }
+    return st;
+}
 
 int &last_path() {
     static thread_local int v = 0;

@@ -15,6 +15,7 @@
 #include <cstring>
 
 #include "axb_internal.h"
+#include "gemm.h"
 #include "reduce_common.cuh"
 
 namespace axb {
@@ -225,7 +226,7 @@ unsigned grid_for(int64_t total, const DeviceCtx *ctx) {
 // shared argument handling of conv2d / conv_transpose: 3-D (N, C, L) tensors are the 1-D case (H = KH = 1)
 axb_status run_conv(bool transposed, const axb_tensor *in, const axb_tensor *weight, const axb_tensor *bias, int spatial_dims,
                     const int32_t *stride, const int32_t *padding, const int32_t *dilation, int groups, const axb_tensor *out,
-                    axb_stream_t stream) {
+                    axb_stream_t stream, int activation = 0) {
     const char *what = transposed ? "conv_transpose" : "conv2d";
     AXB_TRY(validate_tensor(in, what));
     AXB_TRY(validate_tensor(weight, what));
@@ -276,6 +277,27 @@ axb_status run_conv(bool transposed, const axb_tensor *in, const axb_tensor *wei
     cudaStream_t s;
     DeviceCtx *ctx;
     AXB_TRY(resolve_stream(stream, &s, &ctx));
+    if (!transposed && groups == 1) {
+        // large problems: implicit GEMM on the tensor cores (gemm_tcgen05.cu conv_tc) — fp32 through the exact three-piece
+        // bf16 split (as accurate as an fp32 FMA chain, NOT bit-identical to the fp64 accumulation of the gather kernel)
+        gemm::ConvDesc cd;
+        memset(&cd, 0, sizeof cd);
+        cd.x = p.in; cd.w = p.w; cd.bias = p.bias; cd.out = p.out;
+        cd.dtype = in->dtype; cd.bias_dtype = in->dtype; cd.act = activation;
+        cd.N = p.N; cd.Cin = p.Cin; cd.H = p.H; cd.W = p.W; cd.Cout = p.Cout; cd.KH = p.KH; cd.KW = p.KW; cd.OH = p.OH; cd.OW = p.OW;
+        for (int i = 0; i < 4; ++i) {
+            cd.x_s[i] = p.in_s[i];
+            cd.w_s[i] = p.w_s[i];
+        }
+        cd.bias_s = p.bias_s;
+        cd.sh = p.sh; cd.sw = p.sw; cd.ph = p.ph; cd.pw = p.pw; cd.dh = p.dh; cd.dw = p.dw;
+        bool done = false;
+        AXB_TRY(gemm::conv_tc(cd, ctx, s, &done));
+        if (done)
+            return AXB_OK;
+    }
+    AXB_REQUIRE(activation == 0, AXB_ERR_UNSUPPORTED, "%s: a fused activation needs the tensor-core path (groups == 1, >= 1e8 flop)", what);
+    gemm::last_path() = 0;
     const unsigned grid = grid_for(p.total, ctx);
     if (transposed) {
         AXB_DISPATCH_FLOAT(in->dtype, conv_transpose_kernel, grid, s, p)
@@ -296,6 +318,13 @@ extern "C" {
 axb_status axb_conv2d(const axb_tensor *in, const axb_tensor *weight, const axb_tensor *bias, const int32_t stride[2],
                       const int32_t padding[2], const int32_t dilation[2], int groups, const axb_tensor *out, axb_stream_t stream) {
     return run_conv(false, in, weight, bias, 2, stride, padding, dilation, groups, out, stream);
+}
+
+axb_status axb_conv(const axb_tensor *in, const axb_tensor *weight, const axb_tensor *bias, int spatial_dims, const int32_t *stride,
+                    const int32_t *padding, const int32_t *dilation, int groups, int activation, const axb_tensor *out,
+                    axb_stream_t stream) {
+    AXB_REQUIRE(stride && padding && dilation, AXB_ERR_INVALID, "axb_conv: null stride / padding / dilation");
+    return run_conv(false, in, weight, bias, spatial_dims, stride, padding, dilation, groups, out, stream, activation);
 }
 
 axb_status axb_conv_transpose(const axb_tensor *in, const axb_tensor *weight, const axb_tensor *bias, int spatial_dims,

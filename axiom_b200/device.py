@@ -321,6 +321,18 @@ def conv2d(x: DeviceArray, w: DeviceArray, bias: Optional[DeviceArray] = None, s
     return out
 
 
+def conv(x: DeviceArray, w: DeviceArray, bias: Optional[DeviceArray] = None, stride=1, padding=0, dilation=1, groups: int = 1,
+         activation: Optional[str] = None) -> DeviceArray:
+    """axb_conv: 1-D / 2-D forward convolution; the tensor-core implicit GEMM when the problem qualifies (matmul_last_path() == 4)."""
+    nsp = len(x.shape) - 2
+    st, pd, dl = _i32s(stride, nsp), _i32s(padding, nsp), _i32s(dilation, nsp)
+    sp = [(x.shape[2 + i] + 2 * pd[i] - dl[i] * (w.shape[2 + i] - 1) - 1) // st[i] + 1 for i in range(nsp)]
+    out = DeviceArray.empty((x.shape[0], w.shape[0], *sp), x.dtype)
+    check(lib().axb_conv(ctypes.byref(x.desc()), ctypes.byref(w.desc()), ctypes.byref(bias.desc()) if bias else None, nsp, st, pd, dl,
+                         groups, capi.OP[activation] if activation else 0, ctypes.byref(out.desc()), None))
+    return out
+
+
 def conv_transpose(x: DeviceArray, w: DeviceArray, bias: Optional[DeviceArray] = None, stride=1, padding=0,
                    output_padding=0, dilation=1, groups: int = 1) -> DeviceArray:
     nsp = len(x.shape) - 2

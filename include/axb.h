@@ -394,6 +394,17 @@ axb_status axb_pad_constant(const axb_tensor *in, const int64_t *pad_lo, const i
 axb_status axb_conv2d(const axb_tensor *in, const axb_tensor *weight, const axb_tensor *bias /* may be NULL */,
                       const int32_t stride[2], const int32_t padding[2], const int32_t dilation[2], int groups,
                       const axb_tensor *out, axb_stream_t stream);
+/* Forward convolution, 1-D ((N, C, L) / (C_out, C_in/groups, K)) or 2-D, optional fused activation (0 or a unary axb_op).
+ * groups == 1 and >= 1e8 flop, float32 / bf16 / fp16: IMPLICIT GEMM on the tensor cores — no im2col matrix exists; the K loop
+ * of the tcgen05 GEMM walks (filter tap, 64-channel block) steps and the TMA load of each input tile starts at the tap's
+ * shifted coordinate, out-of-image rows / columns zero-filled by TMA (= the padding); strides read a phase-de-interleaved
+ * copy; bias and activation run in the GEMM epilogue. float32 uses the exact three-piece bf16 split (fp32-FMA accuracy,
+ * tolerance-based parity); axb_matmul_last_path() reports 4. Everything else runs the gather kernel of axb_conv2d (fp64
+ * accumulation, bit-identical to the CPU loops; no fused activation). Replaces ops::conv1d / conv2d
+ * (src/tensor/operations.cpp:2968-3330) and the MPSGraph convolution lowering (mpsgraph_graph_compiler.mm:365-405). */
+axb_status axb_conv(const axb_tensor *in, const axb_tensor *weight, const axb_tensor *bias /* may be NULL */, int spatial_dims,
+                    const int32_t *stride, const int32_t *padding, const int32_t *dilation, int groups, int activation,
+                    const axb_tensor *out, axb_stream_t stream);
 axb_status axb_conv_transpose(const axb_tensor *in, const axb_tensor *weight, const axb_tensor *bias /* may be NULL */,
                               int spatial_dims, const int32_t *stride, const int32_t *padding, const int32_t *dilation,
                               int groups, const axb_tensor *out, axb_stream_t stream);

@@ -687,3 +687,28 @@ def masked_select(x: np.ndarray, mask: np.ndarray) -> np.ndarray:
     xb, mb = np.broadcast_to(x, shape), np.broadcast_to(mask, shape)
     first = np.ascontiguousarray(mb).view(np.uint8).reshape(shape + (mask.dtype.itemsize,))[..., 0] != 0
     return np.ascontiguousarray(xb)[first]
+
+
+def conv2d_f64(x, w, bias=None, stride=(1, 1), padding=(0, 0), dilation=(1, 1)):
+    """The same sum as conv2d_f32 (groups == 1), accumulated in float64 tap by tap with whole-array operations, for problems
+    too large for the scalar loops; returned in float64 together with sum |x| |w| per output (the scale of the rounding
+    error of any fp32 evaluation order). Pinned against conv2d_f32 on a small case in tests/test_spatial_gpu.py."""
+    n, cin, h, wd = x.shape
+    cout, cg, kh, kw = w.shape
+    oh = (h + 2 * padding[0] - dilation[0] * (kh - 1) - 1) // stride[0] + 1
+    ow = (wd + 2 * padding[1] - dilation[1] * (kw - 1) - 1) // stride[1] + 1
+    xp = np.zeros((n, cin, h + 2 * padding[0], wd + 2 * padding[1]), np.float64)
+    xp[:, :, padding[0]:padding[0] + h, padding[1]:padding[1] + wd] = x
+    wd64 = w.astype(np.float64)
+    out = np.zeros((n, cout, oh, ow), np.float64)
+    mag = np.zeros((n, cout, oh, ow), np.float64)
+    for fh in range(kh):
+        for fw in range(kw):
+            h0, w0 = fh * dilation[0], fw * dilation[1]
+            win = xp[:, :, h0:h0 + (oh - 1) * stride[0] + 1:stride[0], w0:w0 + (ow - 1) * stride[1] + 1:stride[1]]
+            out += np.einsum("oc,nchw->nohw", wd64[:, :, fh, fw], win, optimize=True)
+            mag += np.einsum("oc,nchw->nohw", np.abs(wd64[:, :, fh, fw]), np.abs(win), optimize=True)
+    if bias is not None:
+        out += np.asarray(bias, np.float64).reshape(1, -1, 1, 1)
+        mag += np.abs(np.asarray(bias, np.float64)).reshape(1, -1, 1, 1)
+    return out, mag

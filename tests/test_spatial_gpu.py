@@ -96,3 +96,110 @@ def test_spatial_errors_are_reported(gpu):
         dev.conv2d(x, w)
     with pytest.raises(Exception):
         dev.interpolate(dev.DeviceArray.from_numpy(np.zeros((4, 4), np.float32).reshape(1, 1, 1, 4, 4)), (2, 2, 2))
+
+
+# ---- convolution as an implicit GEMM on the tensor cores (gemm_tcgen05.cu conv_tc) ----------------------------------------
+def test_oracle_fast_conv_matches_the_loops():
+    rng = np.random.default_rng(41)
+    x = rng.standard_normal((2, 3, 7, 9)).astype(np.float32)
+    w = rng.standard_normal((4, 3, 3, 2)).astype(np.float32)
+    b = rng.standard_normal(4).astype(np.float32)
+    for cfg in (dict(stride=(1, 1), padding=(0, 0), dilation=(1, 1)), dict(stride=(2, 1), padding=(1, 2), dilation=(1, 2))):
+        fast, mag = ao.conv2d_f64(x, w, b, **cfg)
+        assert np.array_equal(fast.astype(np.float32), ao.conv2d_f32(x, w, b, **cfg)) and np.all(mag >= np.abs(fast) - 1e-12)
+
+
+def _check_conv_tc(x, w, b, dt, cfg, activation=None, expect_path=4):
+    from axiom_b200 import capi
+    xs, ws = (x, w) if x.ndim == 4 else (x[:, :, None, :], w[:, :, None, :])
+    c2 = {k: ((1, v) if k != "padding" else (0, v)) if x.ndim == 3 else v for k, v in cfg.items()}
+    if dt == "f32":
+        dx, dw, db = dev.DeviceArray.from_numpy(x), dev.DeviceArray.from_numpy(w), dev.DeviceArray.from_numpy(b) if b is not None else None
+        xe, we, be = xs, ws, b
+        tol = 4e-6  # the three-piece bf16 split is as accurate as an fp32 FMA chain: error <= a few 2^-24 of sum |x||w|
+    else:
+        cv = ao.f32_to_bf16 if dt == "bf16" else (lambda a: a.astype(np.float16))
+        back = ao.bf16_to_f32 if dt == "bf16" else (lambda a: a.astype(np.float32))
+        xh, wh, bh = cv(x), cv(w), cv(b) if b is not None else None
+        dx, dw = dev.DeviceArray.from_numpy(xh, bf16=dt == "bf16"), dev.DeviceArray.from_numpy(wh, bf16=dt == "bf16")
+        db = dev.DeviceArray.from_numpy(bh, bf16=dt == "bf16") if b is not None else None
+        xe, we = (back(xh), back(wh)) if x.ndim == 4 else (back(xh)[:, :, None, :], back(wh)[:, :, None, :])
+        be = back(bh) if b is not None else None
+        tol = 1e-2 if dt == "bf16" else 2e-3  # north_star: fp32 accumulate, one rounding, <= 1e-2 relative
+    got = dev.conv(dx, dw, db, activation=activation, **cfg)
+    assert capi.lib().axb_matmul_last_path() == expect_path, "unexpected kernel path"
+    got = got.numpy()
+    gotf = got if dt == "f32" else (ao.bf16_to_f32(got) if dt == "bf16" else got.astype(np.float32))
+    exp, mag = ao.conv2d_f64(xe, we, be, **c2)
+    if x.ndim == 3:
+        exp, mag = exp[:, :, 0, :], mag[:, :, 0, :]
+    if activation == "relu":
+        exp = np.maximum(exp, 0)
+    elif activation == "gelu":
+        from scipy.special import erf
+        exp = 0.5 * exp * (1 + erf(exp / np.sqrt(2)))
+    assert gotf.shape == exp.shape
+    err = np.abs(gotf.astype(np.float64) - exp)
+    bound = tol * mag + (1e-6 if activation == "gelu" else 0)
+    assert np.all(err <= bound), (float((err / np.maximum(mag, 1e-30)).max()), dt, cfg)
+
+
+CONV_TC_2D = [((2, 64, 56, 56), (128, 64, 3, 3), dict(stride=(1, 1), padding=(1, 1), dilation=(1, 1))),
+              ((2, 64, 57, 61), (96, 64, 3, 3), dict(stride=(2, 2), padding=(1, 1), dilation=(1, 1))),
+              ((1, 48, 40, 70), (130, 48, 5, 3), dict(stride=(1, 2), padding=(2, 0), dilation=(1, 1))),
+              ((2, 80, 33, 64), (64, 80, 3, 3), dict(stride=(1, 1), padding=(2, 2), dilation=(2, 2))),
+              ((3, 200, 28, 40), (256, 200, 1, 1), dict(stride=(1, 1), padding=(0, 0), dilation=(1, 1))),
+              ((1, 32, 64, 64), (64, 32, 7, 7), dict(stride=(2, 2), padding=(3, 3), dilation=(1, 1))),
+              ((2, 64, 60, 96), (64, 64, 3, 3), dict(stride=(3, 2), padding=(0, 1), dilation=(2, 1)))]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("xs,ws,cfg", CONV_TC_2D)
+@pytest.mark.parametrize("dt", ["f32", "bf16", "f16"])
+def test_conv2d_implicit_gemm(gpu, xs, ws, cfg, dt):
+    rng = np.random.default_rng(43)
+    x = rng.standard_normal(xs).astype(np.float32)
+    w = (rng.standard_normal(ws) / np.sqrt(ws[1] * ws[2] * ws[3])).astype(np.float32)
+    b = rng.standard_normal(ws[0]).astype(np.float32)
+    _check_conv_tc(x, w, b, dt, cfg)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dt", ["f32", "bf16"])
+def test_conv1d_implicit_gemm_whisper_shapes(gpu, dt):
+    """The two convolutions of the whisper encoder (examples/whisper_poc.cpp:57-60): 80 -> 384, k 3, pad 1 and 384 -> 384,
+    k 3, stride 2, pad 1, with the bias and a fused GELU in the GEMM epilogue."""
+    rng = np.random.default_rng(44)
+    x = rng.standard_normal((2, 80, 3000)).astype(np.float32)
+    w = (rng.standard_normal((384, 80, 3)) / 15).astype(np.float32)
+    b = rng.standard_normal(384).astype(np.float32)
+    _check_conv_tc(x, w, b, dt, dict(stride=1, padding=1, dilation=1))
+    _check_conv_tc(x, w, b, dt, dict(stride=1, padding=1, dilation=1), activation="gelu")
+    x2 = rng.standard_normal((2, 384, 3000)).astype(np.float32)
+    w2 = (rng.standard_normal((384, 384, 3)) / 34).astype(np.float32)
+    _check_conv_tc(x2, w2, b, dt, dict(stride=2, padding=1, dilation=1), activation="gelu")
+    _check_conv_tc(x2, w2, None, dt, dict(stride=2, padding=0, dilation=3))
+
+
+@pytest.mark.gpu
+def test_conv_implicit_gemm_views_and_small_fallback(gpu):
+    from axiom_b200 import capi
+    rng = np.random.default_rng(45)
+    # input as a strided view (channels-last storage seen as NCHW) and a sliced weight: the preparation pass reads strides
+    xl = rng.standard_normal((2, 40, 50, 64)).astype(np.float32)          # N H W C
+    x = xl.transpose(0, 3, 1, 2)                                          # N C H W view
+    wbig = (rng.standard_normal((96, 64, 3, 5)) / 30).astype(np.float32)
+    w = wbig[:, :, :, ::2]                                                # (96, 64, 3, 3) view
+    got = dev.conv(dev.DeviceArray.from_numpy(x), dev.DeviceArray.from_numpy(w), None, stride=(1, 1), padding=(1, 1), dilation=(1, 1))
+    assert capi.lib().axb_matmul_last_path() == 4
+    exp, mag = ao.conv2d_f64(np.ascontiguousarray(x), np.ascontiguousarray(w), None, (1, 1), (1, 1), (1, 1))
+    assert np.all(np.abs(got.numpy() - exp) <= 4e-6 * mag)
+    # a small problem stays on the gather kernel and is bit-identical to the CPU loops
+    xs = rng.standard_normal((1, 3, 9, 9)).astype(np.float32)
+    wsm = rng.standard_normal((4, 3, 3, 3)).astype(np.float32)
+    got = dev.conv(dev.DeviceArray.from_numpy(xs), dev.DeviceArray.from_numpy(wsm), None, stride=(1, 1), padding=(1, 1), dilation=(1, 1))
+    assert capi.lib().axb_matmul_last_path() == 0
+    assert np.array_equal(got.numpy(), ao.conv2d_f32(xs, wsm, None, (1, 1), (1, 1), (1, 1)))
+    with pytest.raises(capi.AxbError):  # a fused activation exists only in the GEMM epilogue
+        dev.conv(dev.DeviceArray.from_numpy(xs), dev.DeviceArray.from_numpy(wsm), None, stride=(1, 1), padding=(1, 1), dilation=(1, 1),
+                 activation="relu")
