@@ -296,7 +296,6 @@ axb_status run_conv(bool transposed, const axb_tensor *in, const axb_tensor *wei
         if (done)
             return AXB_OK;
     }
-    AXB_REQUIRE(activation == 0, AXB_ERR_UNSUPPORTED, "%s: a fused activation needs the tensor-core path (groups == 1, >= 1e8 flop)", what);
     gemm::last_path() = 0;
     const unsigned grid = grid_for(p.total, ctx);
     if (transposed) {
@@ -305,6 +304,8 @@ axb_status run_conv(bool transposed, const axb_tensor *in, const axb_tensor *wei
         AXB_DISPATCH_FLOAT(in->dtype, conv2d_kernel, grid, s, p)
     }
     AXB_CHECK_LAUNCH();
+    if (activation) // the gather kernel has no epilogue: the activation runs in place on the result (same rounding order as
+        AXB_TRY(axb_unary(activation, out, out, activation == AXB_OP_LEAKY_RELU ? 0.01 : 0.0, stream)); // conv followed by the op)
     return AXB_OK;
 }
 

@@ -91,6 +91,8 @@ Tensor gpu_contiguous(const Tensor &x);
 Tensor gpu_compact(const Tensor &x); // always a fresh, offset-free storage (patched Tensor::to)
 Tensor gpu_conv1d_impl(const Tensor &x, const Tensor &w, const Tensor &b, int stride, int padding, int dilation,
                        int groups);
+Tensor gpu_conv_nd(const Tensor &x, const Tensor &w, const Tensor &b, int nsp, const int *stride, const int *padding,
+                   const int *dilation, int groups, ops::OpType activation);
 Tensor gpu_pad_constant(const Tensor &x, const std::vector<std::pair<size_t, size_t>> &pad, double value);
 // Entry points of the patched ops::max_pool*/avg_pool*/sort/argsort/topk (patches/apply.py; the reference has no device
 // branch for them, operations.cpp:2367-2880, :4199-4257). `out_shape` is the shape the reference computed (without the

@@ -352,6 +352,23 @@ bool try_linear_epilogue(Lowering &L, const GraphNode *n) {
         act = n->op_type;
         add = n->inputs[0].get();
     }
+    if (act != OpType::_Count && (add->op_type == OpType::Conv1D || add->op_type == OpType::Conv2D) &&
+        add->output_dtype == n->output_dtype && add->ref_count <= 1) {
+        // act(conv(x, w, b)): the convolution's GEMM epilogue applies bias and activation (whisper_poc.cpp:121-124 gelu(conv))
+        const auto &cp = get_params<ConvParams>(add->params);
+        const int nsp = add->op_type == OpType::Conv1D ? 1 : 2;
+        int st[2] = {1, 1}, pd[2] = {0, 0}, dl[2] = {1, 1};
+        for (int d = 0; d < nsp; ++d) {
+            st[d] = cp.stride.at(d);
+            pd[d] = cp.padding.at(d);
+            dl[d] = cp.dilation.at(d);
+        }
+        Tensor r = backends::cuda::gpu_conv_nd(L.input(add, 0), L.input(add, 1), L.input(add, 2), nsp, st, pd, dl, cp.groups, act);
+        if (r.shape() != n->output_shape)
+            r = r.reshape(n->output_shape);
+        L.value[n] = std::move(r);
+        return true;
+    }
     const GraphNode *mm = nullptr, *bias = nullptr;
     if (add->op_type == OpType::Add && add->inputs.size() == 2) {
         for (int s = 0; s < 2; ++s) {

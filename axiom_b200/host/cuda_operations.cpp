@@ -250,55 +250,70 @@ Tensor gpu_pad_constant(const Tensor &x_in, const std::vector<std::pair<size_t, 
     return out;
 }
 
-// conv1d = im2col (implicit zero padding) + one batched GEMM per group + bias broadcast along (N, :, L_out)
-Tensor gpu_conv1d_impl(const Tensor &x_in, const Tensor &w_in, const Tensor &b_in, int stride, int padding, int dilation,
-                       int groups) {
+// Forward convolution, 1-D or 2-D (axb_conv): implicit GEMM on the tensor cores for groups == 1 and >= 1e8 flop (bias and
+// `activation` in the GEMM epilogue), the fp64-accumulating gather kernel otherwise (bit-identical to the CPU loops of
+// operations.cpp:3054-3130 / :3263-3318). x: (N, C, spatial...) or unbatched; operands are promoted to one float dtype.
+Tensor gpu_conv_nd(const Tensor &x_in, const Tensor &w_in, const Tensor &b_in, int nsp, const int *stride, const int *padding,
+                   const int *dilation, int groups, OpType activation) {
+    const char *what = nsp == 1 ? "conv1d" : "conv2d";
     Tensor x = on_gpu(x_in);
-    const Tensor w = on_gpu(w_in);
-    const bool has_batch = x.ndim() == 3;
-    if (!has_batch)
-        x = x.reshape({1, x.shape()[0], x.shape()[1]});
-    const size_t N = x.shape()[0], C = x.shape()[1], L = x.shape()[2];
-    const size_t Cout = w.shape()[0], Cg = w.shape()[1], K = w.shape()[2];
-    if (C != Cg * (size_t)groups || Cout % (size_t)groups != 0)
-        throw ShapeError("conv1d: channel/group mismatch");
-    const size_t span = (size_t)dilation * (K - 1) + 1;
-    if (L + 2 * (size_t)padding < span)
-        throw ShapeError("conv1d: input length too small for given kernel/padding/dilation");
-    const size_t Lout = (L + 2 * (size_t)padding - span) / (size_t)stride + 1;
+    Tensor w = on_gpu(w_in);
+    const bool has_batch = (int)x.ndim() == nsp + 2;
+    if (!has_batch) {
+        Shape sh{1};
+        for (auto d : x.shape())
+            sh.push_back(d);
+        x = x.reshape(sh);
+    }
+    if ((int)x.ndim() != nsp + 2 || (int)w.ndim() != nsp + 2)
+        throw ShapeError(std::string(what) + ": unexpected input / weight rank");
+    const size_t N = x.shape()[0], C = x.shape()[1], Cout = w.shape()[0], Cg = w.shape()[1];
+    if (groups <= 0 || C != Cg * (size_t)groups || Cout % (size_t)groups != 0)
+        throw ShapeError(std::string(what) + ": channel/group mismatch");
+    Shape oshape{N, Cout};
+    for (int d = 0; d < nsp; ++d) {
+        const size_t L = x.shape()[2 + d], K = w.shape()[2 + d];
+        const size_t span = (size_t)dilation[d] * (K - 1) + 1;
+        if (stride[d] <= 0 || dilation[d] <= 0 || padding[d] < 0 || L + 2 * (size_t)padding[d] < span)
+            throw ShapeError(std::string(what) + ": input too small for given kernel/padding/dilation");
+        oshape.push_back((L + 2 * (size_t)padding[d] - span) / (size_t)stride[d] + 1);
+    }
     const DType dt = static_cast<DType>(axb_promote_types(to_axb_dtype(x.dtype()), to_axb_dtype(w.dtype())));
     if (x.dtype() != dt)
         x = gpu_cast(x, dt);
-    Tensor wq = w.dtype() == dt ? w : gpu_cast(w, dt);
-    Tensor col = empty_gpu({N, C * K, Lout}, dt);
-    {
-        const axb_tensor xd = describe(x), cd = describe(col);
-        check(plan::im2col_1d(&xd, (int)K, stride, padding, dilation, &cd), "axb_im2col_1d");
+    if (w.dtype() != dt)
+        w = gpu_cast(w, dt);
+    const bool has_bias = b_in.storage() && b_in.ndim() > 0 && b_in.size() > 0;
+    Tensor b;
+    if (has_bias) {
+        b = on_gpu(b_in);
+        if (b.dtype() != dt)
+            b = gpu_cast(b, dt);
     }
-    Tensor out;
-    const Tensor w2d = gpu_contiguous(wq).reshape({Cout, Cg * K}); // (C_out, C_in/groups * K)
-    if (groups == 1) {
-        // the reshaped weight is a VIEW of the (constant) conv weight when that is contiguous: its split is cached
-        out = gpu_matmul(w2d, col, false, false, nullptr, OpType::_Count,
-                         w2d.storage() == w.storage() ? AXB_MM_CONST_A : 0); // {C_out, CK} x {N, CK, L_out} -> {N, C_out, L_out}
-    } else {
-        out = empty_gpu({N, Cout, Lout}, dt);
-        const size_t cog = Cout / (size_t)groups;
-        for (int g = 0; g < groups; ++g) {
-            Tensor wg = w2d.slice({Slice((int64_t)(g * cog), (int64_t)((g + 1) * cog)), Slice()});
-            Tensor cg = col.slice({Slice(), Slice((int64_t)(g * Cg * K), (int64_t)((g + 1) * Cg * K)), Slice()});
-            Tensor og = gpu_matmul(wg, cg, false, false);
-            Tensor dst = out.slice({Slice(), Slice((int64_t)(g * cog), (int64_t)((g + 1) * cog)), Slice()});
-            // strided store of the group's block: out_view = og (elementwise copy honours the view's strides)
-            const axb_tensor sd = describe(og), dd = describe(dst);
-            check(plan::gather_strided(&sd, &dd), "conv1d group store");
+    Tensor out = empty_gpu(oshape, dt);
+    if (out.size() != 0) {
+        const axb_tensor xd = describe(x), wd = describe(w), od = describe(out);
+        axb_tensor bd{};
+        if (has_bias)
+            bd = describe(b);
+        int32_t st[2], pd[2], dl[2];
+        for (int d = 0; d < nsp; ++d) {
+            st[d] = stride[d];
+            pd[d] = padding[d];
+            dl[d] = dilation[d];
         }
+        check(plan::conv(&xd, &wd, has_bias ? &bd : nullptr, nsp, st, pd, dl, groups,
+                         activation == OpType::_Count ? 0 : to_axb_op(activation), &od),
+              "axb_conv");
     }
-    if (b_in.storage() && b_in.size() > 0) {
-        Tensor b = on_gpu(b_in);
-        out = gpu_binary(OpType::Add, out, b.reshape({1, Cout, 1}));
-    }
-    return has_batch ? out : out.reshape({Cout, Lout});
+    if (has_batch)
+        return out;
+    Shape s1(out.shape().begin() + 1, out.shape().end());
+    return out.reshape(s1);
+}
+
+Tensor gpu_conv1d_impl(const Tensor &x, const Tensor &w, const Tensor &b, int stride, int padding, int dilation, int groups) {
+    return gpu_conv_nd(x, w, b, 1, &stride, &padding, &dilation, groups, OpType::_Count);
 }
 
 // ---- Operation classes ---------------------------------------------------------------------------------------------
@@ -660,23 +675,7 @@ Tensor drop_batch(const Tensor &out, bool has_batch) {
 // ops::conv2d on the GPU arrives as a lazy OpType::Conv2D node (operations.cpp:3211-3220) and is lowered here
 Tensor gpu_conv2d(const Tensor &input, const Tensor &weight, const Tensor &bias, std::array<int, 2> stride, std::array<int, 2> padding,
                   std::array<int, 2> dilation, int groups) {
-    ConvArgs a = conv_args(input, weight, bias, 4, "conv2d");
-    const size_t H = a.x.shape()[2], W = a.x.shape()[3], KH = a.w.shape()[2], KW = a.w.shape()[3];
-    const size_t dkh = (size_t)dilation[0] * (KH - 1) + 1, dkw = (size_t)dilation[1] * (KW - 1) + 1;
-    if (H + 2 * (size_t)padding[0] < dkh || W + 2 * (size_t)padding[1] < dkw)
-        throw ShapeError("conv2d: input too small for given kernel/padding/dilation");
-    const size_t OH = (H + 2 * (size_t)padding[0] - dkh) / (size_t)stride[0] + 1;
-    const size_t OW = (W + 2 * (size_t)padding[1] - dkw) / (size_t)stride[1] + 1;
-    Tensor out = cuda::empty_gpu({a.x.shape()[0], a.w.shape()[0], OH, OW}, a.x.dtype());
-    if (out.size() > 0) {
-        const axb_tensor xd = cuda::describe(a.x), wd = cuda::describe(a.w), od = cuda::describe(out);
-        axb_tensor bd{};
-        if (a.has_bias)
-            bd = cuda::describe(a.b);
-        const int32_t st[2] = {stride[0], stride[1]}, pd[2] = {padding[0], padding[1]}, dl[2] = {dilation[0], dilation[1]};
-        cuda::check(plan::conv2d(&xd, &wd, a.has_bias ? &bd : nullptr, st, pd, dl, groups, &od), "axb_conv2d");
-    }
-    return drop_batch(out, a.has_batch);
+    return cuda::gpu_conv_nd(input, weight, bias, 2, stride.data(), padding.data(), dilation.data(), groups, ops::OpType::_Count);
 }
 
 Tensor gpu_conv_transpose2d(const Tensor &input, const Tensor &weight, const Tensor &bias, std::array<int, 2> stride,

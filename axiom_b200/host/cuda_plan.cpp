@@ -226,7 +226,7 @@ axb_status invoke(const Call &c, axb_tensor *T) {
     case F_CONV2D: {
         const int32_t st[2] = {(int32_t)c.iv[0], (int32_t)c.iv[1]}, pd[2] = {(int32_t)c.iv[2], (int32_t)c.iv[3]},
                       dl[2] = {(int32_t)c.iv[4], (int32_t)c.iv[5]};
-        return axb_conv2d(&T[0], &T[1], tp(2), st, pd, dl, (int)c.iv[6], &T[3], nullptr);
+        return axb_conv(&T[0], &T[1], tp(2), (int)c.iv[7], st, pd, dl, (int)c.iv[6], (int)c.iv[8], &T[3], nullptr);
     }
     case F_FILL: return axb_fill(&T[0], c.dv[0], nullptr);
     case F_POOL: {
@@ -625,12 +625,12 @@ axb_status pad_constant(const axb_tensor *in, const int64_t *lo, const int64_t *
     c->t[0] = resolve(in); c->t[1] = resolve(out);
     return st_;
 }
-axb_status conv2d(const axb_tensor *in, const axb_tensor *w, const axb_tensor *b, const int32_t stride[2], const int32_t padding[2],
-                  const int32_t dilation[2], int groups, const axb_tensor *out) {
-    AXB_PLAN_CALL(axb_conv2d(in, w, b, stride, padding, dilation, groups, out, nullptr))
+axb_status conv(const axb_tensor *in, const axb_tensor *w, const axb_tensor *b, int nsp, const int32_t *stride, const int32_t *padding,
+                const int32_t *dilation, int groups, int activation, const axb_tensor *out) {
+    AXB_PLAN_CALL(axb_conv(in, w, b, nsp, stride, padding, dilation, groups, activation, out, nullptr))
     Call *c = sc.open(F_CONV2D);
-    c->iv[0] = stride[0]; c->iv[1] = stride[1]; c->iv[2] = padding[0]; c->iv[3] = padding[1];
-    c->iv[4] = dilation[0]; c->iv[5] = dilation[1]; c->iv[6] = groups;
+    c->iv[0] = stride[0]; c->iv[1] = nsp > 1 ? stride[1] : 1; c->iv[2] = padding[0]; c->iv[3] = nsp > 1 ? padding[1] : 0;
+    c->iv[4] = dilation[0]; c->iv[5] = nsp > 1 ? dilation[1] : 1; c->iv[6] = groups; c->iv[7] = nsp; c->iv[8] = activation;
     c->t[0] = resolve(in); c->t[1] = resolve(w); c->t[2] = resolve(b); c->t[3] = resolve(out);
     return st_;
 }

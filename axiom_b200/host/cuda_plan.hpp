@@ -70,8 +70,8 @@ axb_status unary(int32_t op, const axb_tensor *in, const axb_tensor *out, double
 axb_status where(const axb_tensor *c, const axb_tensor *a, const axb_tensor *b, const axb_tensor *out);
 axb_status masked_fill(const axb_tensor *in, const axb_tensor *mask, double value, const axb_tensor *out);
 axb_status pad_constant(const axb_tensor *in, const int64_t *lo, const int64_t *hi, double value, const axb_tensor *out);
-axb_status conv2d(const axb_tensor *in, const axb_tensor *w, const axb_tensor *b, const int32_t stride[2], const int32_t padding[2],
-                  const int32_t dilation[2], int groups, const axb_tensor *out);
+axb_status conv(const axb_tensor *in, const axb_tensor *w, const axb_tensor *b, int nsp, const int32_t *stride, const int32_t *padding,
+                const int32_t *dilation, int groups, int activation, const axb_tensor *out);
 axb_status fill(const axb_tensor *out, double value);
 axb_status pool(const axb_tensor *in, int is_avg, int nsp, const int32_t *kernel, const int32_t *stride, const int32_t *padding,
                 int count_include_pad, const axb_tensor *out);

@@ -400,7 +400,7 @@ axb_status axb_conv2d(const axb_tensor *in, const axb_tensor *weight, const axb_
  * shifted coordinate, out-of-image rows / columns zero-filled by TMA (= the padding); strides read a phase-de-interleaved
  * copy; bias and activation run in the GEMM epilogue. float32 uses the exact three-piece bf16 split (fp32-FMA accuracy,
  * tolerance-based parity); axb_matmul_last_path() reports 4. Everything else runs the gather kernel of axb_conv2d (fp64
- * accumulation, bit-identical to the CPU loops; no fused activation). Replaces ops::conv1d / conv2d
+ * accumulation, bit-identical to the CPU loops; an activation runs as a second, in-place launch). Replaces ops::conv1d / conv2d
  * (src/tensor/operations.cpp:2968-3330) and the MPSGraph convolution lowering (mpsgraph_graph_compiler.mm:365-405). */
 axb_status axb_conv(const axb_tensor *in, const axb_tensor *weight, const axb_tensor *bias /* may be NULL */, int spatial_dims,
                     const int32_t *stride, const int32_t *padding, const int32_t *dilation, int groups, int activation,

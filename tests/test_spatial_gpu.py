@@ -200,6 +200,7 @@ def test_conv_implicit_gemm_views_and_small_fallback(gpu):
     got = dev.conv(dev.DeviceArray.from_numpy(xs), dev.DeviceArray.from_numpy(wsm), None, stride=(1, 1), padding=(1, 1), dilation=(1, 1))
     assert capi.lib().axb_matmul_last_path() == 0
     assert np.array_equal(got.numpy(), ao.conv2d_f32(xs, wsm, None, (1, 1), (1, 1), (1, 1)))
-    with pytest.raises(capi.AxbError):  # a fused activation exists only in the GEMM epilogue
-        dev.conv(dev.DeviceArray.from_numpy(xs), dev.DeviceArray.from_numpy(wsm), None, stride=(1, 1), padding=(1, 1), dilation=(1, 1),
-                 activation="relu")
+    # off the tensor-core path the activation is a second, in-place launch: conv (bit-exact) followed by the exact relu
+    got = dev.conv(dev.DeviceArray.from_numpy(xs), dev.DeviceArray.from_numpy(wsm), None, stride=(1, 1), padding=(1, 1), dilation=(1, 1),
+                   activation="relu")
+    assert np.array_equal(got.numpy(), np.maximum(ao.conv2d_f32(xs, wsm, None, (1, 1), (1, 1), (1, 1)), 0))
