@@ -899,13 +899,16 @@ std::string kernel_source(const std::string &loads, const std::string &body, boo
     if (reduce_opk < 0)
         snprintf(hdr, sizeof hdr, "\nEW_KERNEL_BEGIN(axb_ew, %d, %s, %d, %d, %d)\n", vec, wide ? "uint64_t" : "uint32_t", n_outer,
                  n_inputs, unroll);
-    else // chain + full reduction: the body ends in EW_RED, the kernel in a CTA reduce (ew_prelude.cuh)
+    else if (reduce_opk < 4) // chain + full reduction: the body ends in EW_RED, the kernel in a CTA reduce (ew_prelude.cuh)
         snprintf(hdr, sizeof hdr, "\nEW_RKERNEL_BEGIN(axb_ew_red, %d, %s, %d, %d, %d, %d)\n", vec, wide ? "uint64_t" : "uint32_t",
                  n_outer, n_inputs, unroll, reduce_opk);
+    else // chain + last-axis reduction: reduce_opk = 4 * mode + op, mode 1 = one CTA per row, 2 = one warp per row
+        snprintf(hdr, sizeof hdr, "\nEW_ROWKERNEL_BEGIN(axb_ew_rowred, %d, %s, %d, %d, %d, %d, %d)\n", vec, wide ? "uint64_t" : "uint32_t",
+                 n_outer, n_inputs, unroll, reduce_opk & 3, (reduce_opk >> 2) == 1 ? 256 : 32);
     s += hdr;
     s += "        EW_PRELOAD_BEGIN\n" + loads + "        EW_PRELOAD_END\n";
     s += "        EW_COMPUTE_BEGIN\n" + body + "        EW_COMPUTE_END\n";
-    s += reduce_opk < 0 ? "EW_KERNEL_END\n" : "EW_RKERNEL_END\n";
+    s += reduce_opk < 0 ? "EW_KERNEL_END\n" : reduce_opk < 4 ? "EW_RKERNEL_END\n" : "EW_ROWKERNEL_END\n";
     return s;
 }
 
@@ -971,7 +974,7 @@ axb_status prepare(const axb_instr *prog, int n_instr, const axb_tensor *inputs,
                 out->dtype);
     if (reduce_opk >= 0) {
         char line[64];
-        snprintf(line, sizeof line, "            EW_RED(%d)\n", reduce_opk);
+        snprintf(line, sizeof line, "            EW_RED(%d)\n", reduce_opk & 3);
         body += line;
     }
     // loads in flight: U vectors per thread while the streamed (non-broadcast) operands fit the register budget
@@ -1197,6 +1200,52 @@ axb_status launch_chain_reduce(const axb_instr *prog, int n_instr, const axb_ten
     *n_partials = blocks;
     return AXB_OK;
 }
+
+// Chain + reduction over the LAST axis of the chain's value in one pass (host_api.cpp axb_elementwise_reduce_axis): `out`
+// holds one fp32 per row of `shape_desc`. *done = false leaves the call to the unfused path (the planner could not keep the
+// reduced axis as the innermost run on its own, or the row count does not fit a grid).
+axb_status launch_chain_rowreduce(const axb_instr *prog, int n_instr, const axb_tensor *inputs, int n_inputs,
+                                  const axb_tensor *shape_desc, int opk, bool is_mean, float *out, cudaStream_t s, DeviceCtx *ctx,
+                                  bool *done) {
+    *done = false;
+    const int nd = shape_desc->ndim;
+    if (nd < 1 || shape_desc->shape[nd - 1] < 2)
+        return AXB_OK;
+    // a descriptor of the (never written) chain value whose rows are PADDED: no operand set is dense across the last two
+    // dims any more, so plan_iteration keeps the reduced axis as the innermost run while outer dims still collapse
+    axb_tensor od = *shape_desc;
+    od.base = reinterpret_cast<void *>(uintptr_t(256));
+    od.byte_offset = 0;
+    const int64_t esz = (int64_t)dtype_size(od.dtype);
+    int64_t pitch = od.shape[nd - 1] * esz + 16;
+    od.strides[nd - 1] = esz;
+    for (int d = nd - 2; d >= 0; --d) {
+        od.strides[d] = pitch;
+        pitch *= std::max<int64_t>(od.shape[d], 1);
+    }
+    const int64_t len = od.shape[nd - 1];
+    int64_t rows = 1;
+    for (int d = 0; d < nd - 1; ++d)
+        rows *= od.shape[d];
+    if (rows == 0 || rows >= (1ll << 31))
+        return AXB_OK;
+    Prepared P;
+    bool empty = false;
+    jit::Kernel k;
+    // one warp per row while a warp covers the row in at most two trips (VEC = 4 for fp32 chains, U <= 4)
+    const int mode = len <= 1024 ? 2 : 1;
+    AXB_TRY(plan_lookup(prog, n_instr, inputs, n_inputs, &od, 4 * mode + opk, "axb_ew_rowred", ctx->device, &P, &k, &empty));
+    if (empty || (int64_t)P.p.inner_len != len || (int64_t)(P.p.total_vec / P.p.nvec_inner) != rows)
+        return AXB_OK;
+    P.p.reduce_op = is_mean ? AXB_OP_MEAN : 0;
+    P.p.reduce_ws = out;
+    const int64_t blocks = mode == 1 ? rows : (rows + 7) / 8;
+    void *args[] = {&P.p};
+    AXB_TRY(jit::launch(k, (unsigned)blocks, 256, 0, s, args));
+    count_launch();
+    *done = true;
+    return AXB_OK;
+}
 } // namespace ew
 } // namespace axb
 
@@ -1209,6 +1258,33 @@ axb_status axb_elementwise_precompile(const axb_instr *prog, int n_instr, const 
     Prepared P;
     bool empty = false;
     AXB_TRY(prepare(prog, n_instr, inputs, n_inputs, out, &P, &empty));
+    if (empty)
+        return AXB_OK;
+    return jit::precompile(P.source);
+}
+
+// Same for the chain + reduction kernels: reduce_kind 0 = full reduction (axb_elementwise_reduce), 1 = last axis with one CTA per
+// row, 2 = last axis with one warp per row (axb_elementwise_reduce_axis); reduce_op sum / mean / max / min.
+axb_status axb_elementwise_reduce_precompile(const axb_instr *prog, int n_instr, const axb_tensor *inputs, int n_inputs,
+                                             const axb_tensor *shape_desc, int32_t reduce_op, int reduce_kind) {
+    AXB_REQUIRE(shape_desc && reduce_kind >= 0 && reduce_kind <= 2, AXB_ERR_INVALID, "axb_elementwise_reduce_precompile: bad arguments");
+    const int opk = (reduce_op == AXB_OP_SUM || reduce_op == AXB_OP_MEAN) ? 0 : reduce_op == AXB_OP_MAX ? 1 : reduce_op == AXB_OP_MIN ? 2 : -1;
+    AXB_REQUIRE(opk >= 0, AXB_ERR_UNSUPPORTED, "axb_elementwise_reduce_precompile: sum / mean / max / min only");
+    axb_tensor od = *shape_desc;
+    od.base = reinterpret_cast<void *>(uintptr_t(256));
+    od.byte_offset = 0;
+    if (reduce_kind > 0 && od.ndim >= 1) { // padded rows, exactly as launch_chain_rowreduce plans them
+        const int64_t esz = (int64_t)dtype_size(od.dtype);
+        int64_t pitch = od.shape[od.ndim - 1] * esz + 16;
+        od.strides[od.ndim - 1] = esz;
+        for (int d = od.ndim - 2; d >= 0; --d) {
+            od.strides[d] = pitch;
+            pitch *= std::max<int64_t>(od.shape[d], 1);
+        }
+    }
+    Prepared P;
+    bool empty = false;
+    AXB_TRY(prepare(prog, n_instr, inputs, n_inputs, &od, &P, &empty, 4 * reduce_kind + opk));
     if (empty)
         return AXB_OK;
     return jit::precompile(P.source);

@@ -760,5 +760,86 @@ template <int OPK> __device__ __forceinline__ float red_combine(float a, float b
         }                                                                                               \
     }
 
+
+// ---- chain + LAST-AXIS reduction in one pass (the reference fuses elementwise producers into ANY reduction,
+// src/graph/graph_compiler.cpp:376-478; `(a * b).sum({1})`, `x.square().mean({-1})`) ------------------------------------------
+// The iteration space is planned so that the innermost run IS the reduced axis (elementwise.cu launch_chain_rowreduce). A
+// group of G threads owns one output row: G = 256 (one CTA per row) for long rows, G = 32 (one warp per row, 8 rows per CTA,
+// no block barrier) for rows of at most 32 * U vectors. Thread t folds vectors t, t + G, ... of the row through the same
+// EW_RED statement as the full reduction, the group combines, and ONE fp32 result per row is written (Mean divides by the
+// row length in fp32, like reduce_common.cuh finalize). The chain's value never reaches HBM.
+template <int VEC, typename W, int NOUT, int NIN, int U, int G, class FL, class FC>
+__device__ __forceinline__ void ew_run_row(const Params &p, uint32_t row, uint32_t t, FL &&preload, FC &&compute) {
+    uint32_t c[kMaxOuter];
+    {
+        uint32_t r = row;
+#pragma unroll
+        for (int d = 0; d < kMaxOuter; ++d) {
+            c[d] = 0;
+            if (d < NOUT) {
+                if (d == NOUT - 1) {
+                    c[d] = r;
+                } else {
+                    uint32_t q = fastdiv(r, p.div_m[1 + d], p.div_s[1 + d]);
+                    c[d] = r - q * p.outer_shape[d];
+                    r = q;
+                }
+            }
+        }
+    }
+    for (uint32_t v0 = t; v0 < p.nvec_inner; v0 += (uint32_t)(G * U)) {
+        Ctx<W, VEC, NIN> x[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const uint32_t vi = v0 + (uint32_t)(u * G);
+            x[u].ok = vi < p.nvec_inner;
+            if (x[u].ok) {
+                x[u].col = vi * VEC;
+                x[u].valid = (int)min((uint32_t)VEC, p.inner_len - x[u].col);
+#pragma unroll
+                for (int d = 0; d < kMaxOuter; ++d)
+                    x[u].c[d] = c[d];
+                preload(x[u]);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if (x[u].ok)
+                compute(x[u]);
+    }
+}
+#define EW_ROWKERNEL_BEGIN(NAME, VEC_, WTYPE, NOUT_, NIN_, U_, OPK_, G_)                                \
+    extern "C" __global__ void __launch_bounds__(256) NAME(const __grid_constant__ axb::ew::Params p) { \
+        using namespace axb::ew;                                                                        \
+        constexpr int VEC = VEC_, NOUT = NOUT_, NIN = NIN_, U = U_, OPK = OPK_, G = G_;                 \
+        typedef WTYPE W;                                                                                \
+        typedef Ctx<W, VEC, NIN> X;                                                                     \
+        float racc = red_identity<OPK>();
+#define EW_ROWKERNEL_END                                                                                \
+        const uint32_t rows = p.total_vec / p.nvec_inner;                                               \
+        const uint32_t row = G == 256 ? blockIdx.x : blockIdx.x * 8u + (threadIdx.x >> 5);              \
+        const uint32_t tig = G == 256 ? threadIdx.x : (threadIdx.x & 31u);                              \
+        if (row < rows)                                                                                 \
+            ew_run_row<VEC, W, NOUT, NIN, U, G>(p, row, tig, preload, compute);                         \
+        _Pragma("unroll") for (int d = 16; d >= 1; d >>= 1)                                             \
+            racc = red_combine<OPK>(racc, __shfl_xor_sync(0xFFFFFFFFu, racc, d));                       \
+        float *rout = reinterpret_cast<float *>(p.reduce_ws);                                           \
+        if (G == 256) {                                                                                 \
+            __shared__ float red_sm[8];                                                                 \
+            if ((threadIdx.x & 31) == 0)                                                                \
+                red_sm[threadIdx.x >> 5] = racc;                                                        \
+            __syncthreads();                                                                            \
+            if (threadIdx.x == 0) {                                                                     \
+                float tot = red_sm[0];                                                                  \
+                _Pragma("unroll") for (int w = 1; w < 8; ++w) tot = red_combine<OPK>(tot, red_sm[w]);   \
+                if (p.reduce_op == 57 /* AXB_OP_MEAN */)                                                         \
+                    tot = __fdiv_rn(tot, (float)p.inner_len);                                           \
+                rout[row] = tot;                                                                        \
+            }                                                                                           \
+        } else if (tig == 0 && row < rows) {                                                            \
+            rout[row] = p.reduce_op == 57 /* AXB_OP_MEAN */ ? __fdiv_rn(racc, (float)p.inner_len) : racc;        \
+        }                                                                                               \
+    }
+
 } // namespace ew
 } // namespace axb

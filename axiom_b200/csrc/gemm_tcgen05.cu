@@ -1396,7 +1396,7 @@ axb_status conv_tc(const ConvDesc &d, DeviceCtx *ctx, cudaStream_t s, bool *done
         return AXB_OK;
     const int64_t taps = d.KH * d.KW;
     const double flops = 2.0 * (double)d.N * (double)d.Cout * (double)d.OH * (double)d.OW * (double)d.Cin * (double)taps;
-    if (taps < 1 || taps > kMaxTaps || flops < 1.0e8 || d.Cout < 32 || d.OW < 16 || d.Cin < 8 || d.N * d.OH >= (1ll << 31))
+    if (taps < 1 || taps > kMaxTaps || flops < 1.0e8 || d.Cout < 32 || d.OW < 8 || d.Cin < 8 || d.N * d.OH >= (1ll << 31))
         return AXB_OK; // small problems: the preparation passes and the 128-row tile would dominate (gather kernel / im2col path)
     if (d.sh < 1 || d.sw < 1 || d.sh * d.sw > 64 || d.N * d.sh * d.sw > 65535 || (d.H + d.sh - 1) / d.sh > 65535)
         return AXB_OK;

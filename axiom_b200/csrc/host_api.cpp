@@ -398,4 +398,62 @@ axb_status axb_elementwise_reduce(const axb_instr *prog, int n_instr, const axb_
     return st;
 }
 
+// Chain + reduction over ONE axis. The fused single-pass kernel covers fp32 chains reduced over their LAST axis by sum / mean /
+// max / min into a contiguous fp32 result; every other case runs the chain and the reduction as two launches.
+axb_status axb_elementwise_reduce_axis(const axb_instr *prog, int n_instr, const axb_tensor *inputs, int n_inputs, int32_t reduce_op,
+                                       int axis, int keep_dims, const axb_tensor *out, axb_stream_t stream) {
+    AXB_REQUIRE(prog && n_instr > 0 && n_inputs > 0 && inputs, AXB_ERR_INVALID, "axb_elementwise_reduce_axis: bad arguments");
+    AXB_TRY(validate_tensor(out, "axb_elementwise_reduce_axis(out)"));
+    int64_t shape[AXB_MAX_DIMS];
+    int nd = inputs[0].ndim;
+    memcpy(shape, inputs[0].shape, sizeof(int64_t) * nd);
+    for (int k = 1; k < n_inputs; ++k) {
+        int64_t nxt[AXB_MAX_DIMS];
+        int nn = 0;
+        AXB_TRY(axb_broadcast_shape(shape, nd, inputs[k].shape, inputs[k].ndim, nxt, &nn));
+        memcpy(shape, nxt, sizeof(int64_t) * nn);
+        nd = nn;
+    }
+    if (axis < 0)
+        axis += nd;
+    AXB_REQUIRE(axis >= 0 && axis < nd, AXB_ERR_INVALID, "axb_elementwise_reduce_axis: axis out of range");
+    cudaStream_t s;
+    DeviceCtx *ctx;
+    AXB_TRY(resolve_stream(stream, &s, &ctx));
+    const int32_t vdt = prog[n_instr - 1].dtype;
+    axb_tensor tmp = make_contiguous_desc(nullptr, vdt, shape, nd);
+    const int opk = (reduce_op == AXB_OP_SUM || reduce_op == AXB_OP_MEAN) ? 0 : reduce_op == AXB_OP_MAX ? 1 : reduce_op == AXB_OP_MIN ? 2 : -1;
+    static const bool two_pass = getenv("AXB_EW_REDUCE_TWO_PASS") != nullptr; // A/B switch
+    bool wide = false;
+    for (int k = 0; k < n_inputs; ++k)
+        wide = wide || is_64bit_dtype(inputs[k].dtype);
+    for (int i = 0; i < n_instr; ++i)
+        wide = wide || is_64bit_dtype(prog[i].dtype);
+    int64_t rows = 1;
+    for (int d = 0; d < nd - 1; ++d)
+        rows *= shape[d];
+    if (!two_pass && !wide && opk >= 0 && axis == nd - 1 && vdt == AXB_F32 && out->dtype == AXB_F32 && is_contiguous(*out) &&
+        numel(*out) == rows && numel(tmp) > 0) {
+        bool done = false;
+        AXB_TRY(ew::launch_chain_rowreduce(prog, n_instr, inputs, n_inputs, &tmp, opk, reduce_op == AXB_OP_MEAN,
+                                           reinterpret_cast<float *>(tensor_ptr(*out)), s, ctx, &done));
+        if (done)
+            return AXB_OK;
+    }
+    if (numel(tmp) == 0) {
+        const int32_t ax = axis;
+        tmp.base = reinterpret_cast<void *>(uintptr_t(256));
+        return axb_reduce(reduce_op, &tmp, &ax, 1, keep_dims, out, s);
+    }
+    void *buf = nullptr;
+    AXB_TRY(axb_alloc((size_t)numel(tmp) * dtype_size(vdt), s, &buf));
+    tmp.base = buf;
+    axb_status st = axb_elementwise(prog, n_instr, inputs, n_inputs, &tmp, s);
+    const int32_t ax = axis;
+    if (st == AXB_OK)
+        st = axb_reduce(reduce_op, &tmp, &ax, 1, keep_dims, out, s);
+    axb_free(buf, s);
+    return st;
+}
+
 } // extern "C"

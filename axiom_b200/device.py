@@ -400,3 +400,18 @@ def elementwise_reduce(prog: List[capi.AxbInstr], inputs: Sequence[DeviceArray],
     out = DeviceArray.empty((1,), prog[-1].dtype)
     check(lib().axb_elementwise_reduce(P, len(prog), I, len(inputs), capi.OP[op], ctypes.byref(out.desc()), None))
     return out
+
+
+def elementwise_reduce_axis(prog: List[capi.AxbInstr], inputs: Sequence[DeviceArray], op: str, axis: int,
+                            keep_dims: bool = False) -> DeviceArray:
+    """The chain's value reduced over one axis (axb_elementwise_reduce_axis): one kernel for fp32 chains over the last axis."""
+    P = (capi.AxbInstr * len(prog))(*prog)
+    I = (capi.AxbTensor * len(inputs))(*[t.desc() for t in inputs])
+    shape = list(_bshape(*[x.shape for x in inputs]))
+    ax = axis + len(shape) if axis < 0 else axis
+    oshape = shape[:ax] + ([1] if keep_dims else []) + shape[ax + 1:]
+    odt = lib().axb_reduce_result_dtype(capi.OP[op], prog[-1].dtype)
+    out = DeviceArray.empty(tuple(oshape), odt)
+    check(lib().axb_elementwise_reduce_axis(P, len(prog), I, len(inputs), capi.OP[op], axis, int(keep_dims),
+                                            ctypes.byref(out.desc()), None))
+    return out

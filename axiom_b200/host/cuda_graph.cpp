@@ -324,6 +324,21 @@ struct Lowering {
                 Program pg = build_program(c);
                 r = empty_gpu(n->output_shape, n->output_dtype);
                 run_program(pg, describe(r), to_axb_op(op));
+            } else if (!full && rp.axes.size() == 1 && (op == OpType::Sum || op == OpType::Max || op == OpType::Min || op == OpType::Mean) &&
+                       !is_leaf(c) && !value.count(c) && is_fusable(c) && c->output_dtype == DType::Float32 &&
+                       n->output_dtype == DType::Float32 && ShapeUtils::size(c->output_shape) > 0 &&
+                       (rp.axes[0] == (int)c->output_shape.size() - 1 || rp.axes[0] == -1)) {
+                // elementwise tree + reduction over its LAST axis in one pass (graph_compiler.cpp:376-478 fuses producers
+                // into any reduction): one CTA / warp per output row folds the chain's values as it computes them
+                Program pg = build_program(c);
+                r = empty_gpu(n->output_shape, n->output_dtype);
+                std::vector<axb_tensor> ins(pg.inputs.size());
+                for (size_t i = 0; i < pg.inputs.size(); ++i)
+                    ins[i] = describe(get(pg.inputs[i]));
+                const axb_tensor od = describe(r);
+                check(plan::elementwise_reduce_axis(pg.instrs.data(), (int)pg.instrs.size(), ins.data(), (int)ins.size(), to_axb_op(op),
+                                                    (int)c->output_shape.size() - 1, rp.keep_dims ? 1 : 0, &od),
+                      "axb_elementwise_reduce_axis");
             } else {
                 r = backends::cuda::gpu_reduce(op, input(n, 0), rp.axes, rp.keep_dims);
             }

@@ -20,7 +20,7 @@ using graph::GraphNode;
 
 enum Fn : int32_t {
     F_ELEMENTWISE, F_ELEMENTWISE_REDUCE, F_MATMUL, F_SOFTMAX, F_LAYER_NORM, F_RMS_NORM, F_REDUCE, F_ARGREDUCE, F_CAST,
-    F_GATHER_STRIDED, F_IM2COL, F_BINARY, F_UNARY, F_WHERE, F_MASKED_FILL, F_PAD, F_CONV2D, F_FILL, F_POOL, F_SORT
+    F_GATHER_STRIDED, F_IM2COL, F_BINARY, F_UNARY, F_WHERE, F_MASKED_FILL, F_PAD, F_CONV2D, F_FILL, F_POOL, F_SORT, F_ELEMENTWISE_REDUCE_AXIS
 };
 enum Kind : int8_t { K_NONE = 0, K_LEAF = 1, K_TEMP = 2 };
 
@@ -196,6 +196,11 @@ axb_status invoke(const Call &c, axb_tensor *T) {
     case F_ELEMENTWISE_REDUCE: {
         const int n_in = (int)c.iv[0];
         return axb_elementwise_reduce(c.prog.data(), (int)c.prog.size(), T, n_in, (int32_t)c.iv[1], &T[n_in], nullptr);
+    }
+    case F_ELEMENTWISE_REDUCE_AXIS: {
+        const int n_in = (int)c.iv[0];
+        return axb_elementwise_reduce_axis(c.prog.data(), (int)c.prog.size(), T, n_in, (int32_t)c.iv[1], (int)c.iv[2], (int)c.iv[3], &T[n_in],
+                                           nullptr);
     }
     case F_MATMUL: {
         axb_matmul_epilogue e{};
@@ -512,6 +517,20 @@ axb_status elementwise_reduce(const axb_instr *prog, int n_instr, const axb_tens
     c->prog.assign(prog, prog + n_instr);
     c->iv[0] = n_inputs;
     c->iv[1] = reduce_op;
+    for (int i = 0; i < n_inputs; ++i)
+        c->t[i] = resolve(&inputs[i]);
+    c->t[n_inputs] = resolve(out);
+    return st_;
+}
+axb_status elementwise_reduce_axis(const axb_instr *prog, int n_instr, const axb_tensor *inputs, int n_inputs, int32_t reduce_op,
+                                   int axis, int keep_dims, const axb_tensor *out) {
+    AXB_PLAN_CALL(axb_elementwise_reduce_axis(prog, n_instr, inputs, n_inputs, reduce_op, axis, keep_dims, out, nullptr))
+    Call *c = sc.open(F_ELEMENTWISE_REDUCE_AXIS);
+    c->prog.assign(prog, prog + n_instr);
+    c->iv[0] = n_inputs;
+    c->iv[1] = reduce_op;
+    c->iv[2] = axis;
+    c->iv[3] = keep_dims;
     for (int i = 0; i < n_inputs; ++i)
         c->t[i] = resolve(&inputs[i]);
     c->t[n_inputs] = resolve(out);

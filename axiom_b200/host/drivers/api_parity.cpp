@@ -73,6 +73,45 @@ int main() {
         // inside a longer lazy chain, and under a full reduction (the chain + reduction fusion path)
         check("leaky_relu_chain_" + sfx, xd, [](const Tensor &t) { return (ops::leaky_relu(t) + 1.0f) * t; });
     }
+    // elementwise producer + reduction over the last axis: ONE kernel (the reference fuses producers into reductions,
+    // graph_compiler.cpp:376-478); sums within the 1e-5 contract, max / min exact
+    {
+        Tensor p = Tensor::randn({257, 1500}), q = Tensor::randn({1, 1500}), sm = Tensor::randn({600, 200});
+        p.sync(); q.sync(); sm.sync();
+        auto fused = [&](const std::string &name, const Tensor &a_cpu, const std::function<Tensor(const Tensor &)> &f, bool exact) {
+            Case c{name, false, ""};
+            try {
+                Tensor ref = f(a_cpu);
+                ref.sync();
+                Tensor ag = a_cpu.gpu();
+                const uint64_t l0 = axb_launch_count();
+                Tensor got = f(ag);
+                got.sync();
+                const uint64_t launches = axb_launch_count() - l0;
+                Tensor back = got.cpu();
+                if (got.device() != Device::GPU)
+                    c.why = "result is not on the GPU";
+                else if (launches != 1)
+                    c.why = "expected one fused kernel, launched " + std::to_string(launches);
+                else if (back.shape() != ref.shape())
+                    c.why = "shape differs";
+                else if (exact ? std::memcmp(back.ascontiguousarray().data(), ref.ascontiguousarray().data(), ref.nbytes()) != 0
+                               : !ref.allclose(back, 1e-4, 1e-4))
+                    c.why = "values differ from the CPU backend";
+                else
+                    c.ok = true;
+            } catch (const std::exception &e) {
+                c.why = e.what();
+            }
+            cases.push_back(c);
+        };
+        Tensor qg = q.gpu();
+        auto Q = [&](const Tensor &t) { return t.device() == Device::GPU ? qg : q; };
+        fused("chain_sum_last_axis", p, [&](const Tensor &t) { return (t * Q(t) + 1.0f).sum({1}); }, false);
+        fused("chain_mean_last_axis_keepdims", p, [&](const Tensor &t) { return t.square().mean({1}, true); }, false);
+        fused("chain_max_last_axis", p, [&](const Tensor &t) { return (t * Q(t)).abs().max(1); }, true);
+        fused("chain_min_short_rows", sm, [&](const Tensor &t) { return (t.relu() - 0.5f).min(1); }, true);
+    }
     // scalar-operand forms of where (the patched Tensor::where(cond, scalar) overloads, tensor.cpp:1340-1355)
     Tensor y = Tensor::randn({5, 1, 33}), c = Tensor::randn({5, 7, 33});
     y.sync();

@@ -205,6 +205,8 @@ axb_status axb_elementwise(const axb_instr *prog, int n_instr, const axb_tensor 
  * use (the analogue of the reference's per-signature MPSGraph cache, mpsgraph_fused.mm:373-377). */
 axb_status axb_elementwise_precompile(const axb_instr *prog, int n_instr, const axb_tensor *inputs, int n_inputs,
                                       const axb_tensor *out);
+axb_status axb_elementwise_reduce_precompile(const axb_instr *prog, int n_instr, const axb_tensor *inputs, int n_inputs,
+                                             const axb_tensor *shape_desc, int32_t reduce_op, int reduce_kind);
 /* Launch-plan cache of the fused-chain family: program + operand LAYOUTS (dtype, shape, byte strides, alignment class —
  * never addresses) -> specialised kernel + launch parameters. A hit skips validation, iteration-space planning, statement
  * generation and the kernel lookup; only the operand pointers are patched. (Graph-level counterpart in the C++ glue:
@@ -310,6 +312,12 @@ int axb_rownorm_last_path(void);
  * the program's last value is reduced with `op` instead of being stored. */
 axb_status axb_elementwise_reduce(const axb_instr *prog, int n_instr, const axb_tensor *inputs, int n_inputs,
                                   int32_t reduce_op, const axb_tensor *out, axb_stream_t stream);
+/* The chain's value under a reduction over ONE axis (the reference fuses elementwise producers into any reduction,
+ * src/graph/graph_compiler.cpp:376-478): fp32 chains reduced over their LAST axis by sum / mean / max / min into a
+ * contiguous fp32 `out` run as ONE kernel (a CTA or a warp per output row folds the chain's values as it computes them);
+ * every other combination runs the chain and axb_reduce as two launches. `out` has the shape axb_reduce would produce. */
+axb_status axb_elementwise_reduce_axis(const axb_instr *prog, int n_instr, const axb_tensor *inputs, int n_inputs,
+                                       int32_t reduce_op, int axis, int keep_dims, const axb_tensor *out, axb_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Family 3 — matmul / batched matmul (tcgen05 + TMEM + TMA for bf16/fp16; fp32 via 3xTF32 or FFMA).

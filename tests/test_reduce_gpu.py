@@ -632,3 +632,56 @@ def test_fused_chain_full_reduction_bf16(gpu, op, shape):
         # fp32 fold (1e-5 of the absolute sum) + one rounding to bf16 (2^-8 relative)
         tol = 1e-5 * np.abs(chain).sum() / (chain.size if op == "mean" else 1) + 2.0 ** -8 * abs(ref) + 1e-30
         assert abs(gotf - ref) <= tol, (op, shape, gotf, ref)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("op", ["sum", "mean", "max", "min"])
+@pytest.mark.parametrize("shape", [(37, 5000), (1000, 300), (4, 33, 1025), (5, 2), (3, 1, 70001)])
+def test_fused_chain_last_axis_reduction_one_kernel(gpu, op, shape):
+    """((a + b) * c).relu() reduced over its LAST axis (axb_elementwise_reduce_axis): ONE launch — a CTA (rows > 1024 elements) or
+    a warp per output row folds the chain's values as it computes them; a is a broadcast column, b a broadcast row. max / min are
+    exact against the op-by-op chain, sum / mean meet the 1e-5 reduction contract of the plain reductions."""
+    rng = np.random.default_rng(19)
+    a = rng.standard_normal(shape[:-1] + (1,)).astype(np.float32)
+    b = rng.standard_normal((shape[-1],)).astype(np.float32)
+    c = rng.standard_normal(shape).astype(np.float32)
+    F, V = capi.F32, capi.SRC_VALUE
+    prog = [capi.make_instr(capi.OP["add"], F, 0, 1), capi.make_instr(capi.OP["mul"], F, V(0), 2),
+            capi.make_instr(capi.OP["relu"], F, V(1))]
+    ins = [dev.DeviceArray.from_numpy(t) for t in (a, b, c)]
+    for keep in (False, True):
+        n0 = dev.launch_count()
+        got = dev.elementwise_reduce_axis(prog, ins, op, -1, keep).numpy()
+        assert dev.launch_count() - n0 == 1, "chain + last-axis reduction must be one kernel"
+        chain = np.maximum((a + b) * c, np.float32(0)).astype(np.float32)
+        assert got.shape == (chain.max(axis=-1, keepdims=keep)).shape
+        if op in ("max", "min"):
+            assert np.array_equal(got, chain.max(axis=-1, keepdims=keep) if op == "max" else chain.min(axis=-1, keepdims=keep))
+        else:
+            ref = chain.astype(np.float64).sum(axis=-1, keepdims=keep)
+            tol = 1e-5 * np.abs(chain).astype(np.float64).sum(axis=-1, keepdims=keep) + 1e-30
+            if op == "mean":
+                ref, tol = ref / shape[-1], tol / shape[-1] + 2.0 ** -23 * np.abs(ref / shape[-1])
+            assert np.all(np.abs(got - ref) <= tol), (op, shape)
+
+
+@pytest.mark.gpu
+def test_chain_axis_reduction_unfused_cases_agree(gpu):
+    """Everything outside the one-kernel case (another axis, a bf16 chain, prod) runs chain + reduction as two launches and gives
+    exactly what the separate calls give."""
+    rng = np.random.default_rng(20)
+    x = rng.standard_normal((33, 70, 129)).astype(np.float32)
+    y = rng.standard_normal((70, 1)).astype(np.float32)
+    F, V = capi.F32, capi.SRC_VALUE
+    prog = [capi.make_instr(capi.OP["mul"], F, 0, 1), capi.make_instr(capi.OP["abs"], F, V(0))]
+    dx, dy = dev.DeviceArray.from_numpy(x), dev.DeviceArray.from_numpy(y)
+    chain = dev.elementwise(prog, [dx, dy])
+    for op, axis in (("sum", 1), ("max", 0), ("prod", 2), ("mean", -2)):
+        got = dev.elementwise_reduce_axis(prog, [dx, dy], op, axis).numpy()
+        assert np.array_equal(got, dev.reduce(op, chain, [axis % 3]).numpy()), (op, axis)
+    xb, yb = as_bf16(x), as_bf16(np.broadcast_to(y, (70, 129)).copy())
+    BF = capi.BF16
+    progb = [capi.make_instr(capi.OP["mul"], BF, 0, 1)]
+    dxb, dyb = dev.DeviceArray.from_numpy(xb, bf16=True), dev.DeviceArray.from_numpy(yb, bf16=True)
+    got = dev.elementwise_reduce_axis(progb, [dxb, dyb], "sum", -1).numpy()
+    assert np.array_equal(got, dev.reduce("sum", dev.elementwise(progb, [dxb, dyb]), [2]).numpy())

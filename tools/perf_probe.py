@@ -114,6 +114,21 @@ def mm(dt, M, N, K, bias=0, act=None, iters=10):
     fl = 2.0 * M * N * K
     return dict(workload=f"linear_{dt}_{M}x{N}x{K}_bias{bias}_{act}", ms_med=med, TFLOPs_med=fl/med/1e9, TFLOPs_best=fl/mn/1e9)
 
+def conv(dt, xs, ws, stride, padding, act=None, iters=10):
+    """conv:<dt>:<N,C,H,W>:<Cout,Cin,KH,KW>:<stride>:<padding>[:act] — 1-D when the shapes are 3-D"""
+    x = dev.randn(tuple(xs), 31); w = dev.randn(tuple(ws), 32, 0.0, 0.05); b = dev.randn((ws[0],), 33)
+    if dt != "f32":
+        code = capi.BF16 if dt == "bf16" else capi.F16
+        x, w, b = dev.cast(x, code), dev.cast(w, code), dev.cast(b, code)
+    nsp = len(xs) - 2
+    fn = lambda: dev.conv(x, w, b, stride=stride, padding=padding, dilation=1, activation=act)
+    out = fn()
+    path = L.axb_matmul_last_path()
+    med, mn = timeit(fn, iters=iters, warm=3)
+    fl = 2.0 * np.prod(out.shape) * ws[1] * np.prod(ws[2:])
+    return dict(workload=f"conv{nsp}d_{dt}_{'x'.join(map(str, xs))}_{'x'.join(map(str, ws))}_s{stride}_p{padding}_{act}", path=int(path),
+                ms_med=med, TFLOPs_med=fl/med/1e9, TFLOPs_best=fl/mn/1e9)
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["d2d", "relu", "exp", "gelu", "add", "c2"]
     for w in which:
@@ -124,6 +139,11 @@ if __name__ == "__main__":
             continue
         if w.startswith("bf16:"):
             print(json.dumps(simple_bf16(w.split(":")[1])), flush=True)
+            continue
+        if w.startswith("conv:"):
+            f = w.split(":")
+            print(json.dumps(conv(f[1], [int(v) for v in f[2].split(",")], [int(v) for v in f[3].split(",")], int(f[4]), int(f[5]),
+                                  f[6] if len(f) > 6 else None)), flush=True)
             continue
         if w.startswith("mm:"):
             f = w.split(":")
