@@ -55,7 +55,8 @@ def _run_suite(name, extra=()):
     return s, failed, r.stdout
 
 
-@pytest.mark.parametrize("suite", ["test_tensor_reductions", "test_fusion", "test_tensor_matmul", "test_lazy_evaluation"])
+@pytest.mark.parametrize("suite", ["test_tensor_reductions", "test_fusion", "test_tensor_matmul", "test_lazy_evaluation", "test_pooling",
+                                   "test_sort_topk", "test_io_safetensors"])
 def test_reference_suites_on_cpu_build(suite):
     """CPU half: the rebuilt library (own make_storage, seam TUs compiled with the GPU hooks) still passes the reference's
     CPU tests; GPU tests skip themselves when no device is visible."""
