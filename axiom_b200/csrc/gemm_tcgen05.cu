@@ -69,8 +69,11 @@ struct TcParams {
     // A is [tap][C_out][pieces * Cp] (3-D map, tap in the batch coordinate), B the phase-split channels-last input
     // [image * phases + phase][H'][W'][pieces * Cp] (4-D map); tap t reads B at column n0 + conv_qw[t], row oh + conv_qh[t],
     // plane image * conv_phases + conv_ph[t] — out-of-range coordinates are zero-filled by TMA, which IS the padding.
-    // "batch" counts (image, output row) pairs: b = image * conv_oh + oh; c_hs is the byte stride of an output row.
-    int32_t conv_taps, conv_cblocks, conv_oh, conv_phases;
+    // "batch" counts (image, output row group) pairs: b = image * conv_oh + group; a group is conv_rows consecutive output
+    // rows, each filling one 64-column chunk of the tile (images narrower than 64 columns: a 256-wide tile holds four rows,
+    // so the weights are fetched once per four rows instead of once per row); c_hs is the byte stride of an output row,
+    // conv_ohs the number of output rows of an image.
+    int32_t conv_taps, conv_cblocks, conv_oh, conv_phases, conv_rows, conv_ohs;
     int64_t c_hs;
     int16_t conv_qw[kMaxTaps], conv_qh[kMaxTaps], conv_ph[kMaxTaps];
 };
@@ -172,7 +175,8 @@ __device__ __forceinline__ void epilogue_tile(const TcParams &p, int64_t b, int 
     const bool out_f32 = p.out_dtype == AXB_F32, out_bf16 = p.out_dtype == AXB_BF16;
     const int osz = out_f32 ? 4 : 2;
     // convolution: b = image * conv_oh + output row (see TcParams)
-    const int64_t cbase = p.conv_taps ? (b / p.conv_oh) * p.c_bs + (b % p.conv_oh) * p.c_hs : b * p.c_bs;
+    const int64_t conv_oh0 = p.conv_taps ? (b % p.conv_oh) * p.conv_rows : 0; // first output row of this tile's group
+    const int64_t cbase0 = p.conv_taps ? (b / p.conv_oh) * p.c_bs + conv_oh0 * p.c_hs : b * p.c_bs;
     const bool c_vec = (p.c_cs == osz) && ((reinterpret_cast<uintptr_t>(p.c) | (uintptr_t)p.c_rs | (uintptr_t)p.c_bs | (uintptr_t)p.c_hs) % 16 == 0);
     // bias as a row vector shared by all rows (nn::Linear): read once per chunk with vector loads
     const int bsz = p.bias_dtype == AXB_F32 ? 4 : 2;
@@ -193,13 +197,20 @@ __device__ __forceinline__ void epilogue_tile(const TcParams &p, int64_t b, int 
         }
     };
     const int64_t m = m0 + q * 32 + lane;
-    char *crow = p.c + cbase + m * p.c_rs;
     const char *brow = p.bias ? p.bias + b * p.bias_bs + m * p.bias_rs : nullptr;
 #pragma unroll 1
     for (int c = half; c < BN_ / 32; c += 2) {
-        const int64_t nbase = n0 + c * 32;
-        if (nbase >= p.N)
+        int64_t nbase = n0 + c * 32, cbase = cbase0;
+        if (p.conv_rows > 1) { // 64-column chunk r of the tile is output row conv_oh0 + r
+            const int r = c >> 1;
+            nbase = (c & 1) * 32;
+            if (conv_oh0 + r >= p.conv_ohs || nbase >= p.N)
+                continue; // warp-uniform
+            cbase += r * p.c_hs;
+        } else if (nbase >= p.N) {
             break; // warp-uniform
+        }
+        char *crow = p.c + cbase + m * p.c_rs;
         uint32_t v[32];
         tc_ld32(taddr + c * 32, v);
         tc_wait_ld();
@@ -212,7 +223,10 @@ __device__ __forceinline__ void epilogue_tile(const TcParams &p, int64_t b, int 
                 v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(w[i]));
         }
         const bool full = nbase + 32 <= p.N;
-        if (m >= p.M && !(c_vec && full))
+        // a ragged last chunk still takes the 128-bit exchange store when N is a whole number of 16-byte segments (the
+        // segments past N are simply not written): N = 56 bf16 columns would otherwise leave 24 of them to 2-byte stores
+        const bool vec_store = c_vec && (full || (p.N * osz) % 16 == 0);
+        if (m >= p.M && !vec_store)
             continue; // (the exchange-based store below needs the whole warp)
         float f[32];
 #pragma unroll
@@ -283,7 +297,7 @@ __device__ __forceinline__ void epilogue_tile(const TcParams &p, int64_t b, int 
         }
         // ---- store -----------------------------------------------------------------------------------------
         if (out_f32) {
-            if (c_vec && full) {
+            if (vec_store) {
                 // Each lane owns one ROW of the 32 x 32 chunk; written straight out, a warp store would touch 32
                 // different 128-byte lines with 16 bytes each. The chunk goes through a swizzled shared-memory
                 // tile instead so that 8 lanes cover one row: every store instruction writes 4 full lines.
@@ -303,7 +317,7 @@ __device__ __forceinline__ void epilogue_tile(const TcParams &p, int64_t b, int 
                     asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(w.x), "=r"(w.y), "=r"(w.z), "=r"(w.w)
                                  : "r"(tile + rr * 128u + ((cw ^ (rr & 7)) << 4)));
                     const int64_t mm = (int64_t)m0 + q * 32 + rr;
-                    if (mm < p.M)
+                    if (mm < p.M && nbase + cw * 4 < p.N)
                         *reinterpret_cast<uint4 *>(p.c + cbase + mm * p.c_rs + (nbase + cw * 4) * 4) = w;
                 }
                 __syncwarp();
@@ -335,7 +349,7 @@ __device__ __forceinline__ void epilogue_tile(const TcParams &p, int64_t b, int 
             for (int i = 0; i < 16; ++i)
                 h[i] = (uint32_t)red::f2h(f[2 * i]) | ((uint32_t)red::f2h(f[2 * i + 1]) << 16);
         }
-        if (c_vec && full) {
+        if (vec_store) {
             // same exchange for 64-byte rows: 4 lanes per row, 8 rows (4 full lines) per store instruction
             const uint32_t tile = staging_base + (uint32_t)ewarp * 4096u;
 #pragma unroll
@@ -352,7 +366,7 @@ __device__ __forceinline__ void epilogue_tile(const TcParams &p, int64_t b, int 
                 asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(w.x), "=r"(w.y), "=r"(w.z), "=r"(w.w)
                              : "r"(tile + rr * 64u + ((cw ^ ((rr >> 1) & 3)) << 4)));
                 const int64_t mm = (int64_t)m0 + q * 32 + rr;
-                if (mm < p.M)
+                if (mm < p.M && nbase + cw * 8 < p.N)
                     *reinterpret_cast<uint4 *>(p.c + cbase + mm * p.c_rs + (nbase + cw * 8) * 2) = w;
             }
             __syncwarp();
@@ -431,12 +445,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                         const uint32_t sa = smem + stage * G_STAGE, sb = sa + 3 * A_BYTES;
                         if (p.conv_taps) { // implicit-GEMM convolution: k-block = (tap, channel block)
                             const int tap = kb / p.conv_cblocks, c0 = (kb - tap * p.conv_cblocks) * BK;
-                            const int img = (int)(b / p.conv_oh), oh = (int)(b - (int64_t)img * p.conv_oh);
+                            const int img = (int)(b / p.conv_oh), oh = (int)(b - (int64_t)img * p.conv_oh) * p.conv_rows;
 #pragma unroll
                             for (int pc = 0; pc < 3; ++pc) {
                                 tma_load_3d(sa + pc * A_BYTES, &tma_a, full_bar(stage), pc * (int)p.Kp + c0, m0, tap);
-                                tma_load_4d(sb + pc * (BN_ * BK * 2), &tma_b, full_bar(stage), pc * (int)p.Kp + c0, n0 + p.conv_qw[tap],
-                                            oh + p.conv_qh[tap], img * p.conv_phases + p.conv_ph[tap]);
+                                if (p.conv_rows == 1) {
+                                    tma_load_4d(sb + pc * (BN_ * BK * 2), &tma_b, full_bar(stage), pc * (int)p.Kp + c0, n0 + p.conv_qw[tap],
+                                                oh + p.conv_qh[tap], img * p.conv_phases + p.conv_ph[tap]);
+                                } else { // one 64-column box per output row of the group
+                                    for (int r = 0; r < BN_ / 64; ++r)
+                                        tma_load_4d(sb + pc * (BN_ * BK * 2) + r * (64 * BK * 2), &tma_b, full_bar(stage), pc * (int)p.Kp + c0,
+                                                    p.conv_qw[tap], oh + r + p.conv_qh[tap], img * p.conv_phases + p.conv_ph[tap]);
+                                }
                             }
                         } else {
 #pragma unroll
@@ -464,10 +484,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                     }
                     if (!A_MN && !B_MN && p.conv_taps) { // implicit-GEMM convolution, half-precision operands
                         const int tap = kb / p.conv_cblocks, c0 = (kb - tap * p.conv_cblocks) * BK;
-                        const int img = (int)(b / p.conv_oh), oh = (int)(b - (int64_t)img * p.conv_oh);
+                        const int img = (int)(b / p.conv_oh), oh = (int)(b - (int64_t)img * p.conv_oh) * p.conv_rows;
                         tma_load_3d(sa, &tma_a, full_bar(stage), c0, m0, tap);
-                        tma_load_4d(sb, &tma_b, full_bar(stage), c0, n0 + p.conv_qw[tap], oh + p.conv_qh[tap],
-                                    img * p.conv_phases + p.conv_ph[tap]);
+                        if (p.conv_rows == 1) {
+                            tma_load_4d(sb, &tma_b, full_bar(stage), c0, n0 + p.conv_qw[tap], oh + p.conv_qh[tap],
+                                        img * p.conv_phases + p.conv_ph[tap]);
+                        } else { // one 64-column box per output row of the group
+                            for (int r = 0; r < BN_ / 64; ++r)
+                                tma_load_4d(sb + r * (64 * BK * 2), &tma_b, full_bar(stage), c0, p.conv_qw[tap], oh + r + p.conv_qh[tap],
+                                            img * p.conv_phases + p.conv_ph[tap]);
+                        }
                         if (++stage == STAGES) {
                             stage = 0;
                             phase ^= 1u;
@@ -1456,27 +1482,37 @@ axb_status conv_tc(const ConvDesc &d, DeviceCtx *ctx, cudaStream_t s, bool *done
         AXB_CHECK_LAUNCH();
 
         const int mdt = d.dtype == AXB_F16 ? AXB_F16 : AXB_BF16;
-        const int bn = f32 ? (d.OW <= 64 ? 64 : 128) : pick_bn(d.OW);
+        int bn = f32 ? (d.OW <= 64 ? 64 : 128) : pick_bn(d.OW);
+        // images at most 64 columns wide: a tile holds bn / 64 consecutive output rows (one 64-column chunk each), so the
+        // weight tile is fetched once per group of rows instead of once per row (L2 -> SM traffic per flop halves / quarters)
+        static const bool no_rows = getenv("AXB_CONV_ONE_ROW") != nullptr; // A/B switch
+        int rows_per_tile = 1;
+        if (!no_rows && d.OW <= 64 && d.OH >= 2) {
+            bn = (f32 || d.OH < 4) ? 128 : 256;
+            rows_per_tile = bn / 64;
+        }
+        const int64_t groups = (d.OH + rows_per_tile - 1) / rows_per_tile;
         const uint64_t rowb = (uint64_t)pieces * Cp * 2;
         CUtensorMap ma, mb;
         AXB_TRY(make_map(&ma, api, mdt, wq, (uint64_t)pieces * Cp, (uint64_t)d.Cout, (uint64_t)taps, rowb, (uint64_t)d.Cout * rowb, BK, BM));
         const uint64_t dims[4] = {(uint64_t)pieces * Cp, (uint64_t)Wq, (uint64_t)Hq, (uint64_t)planes};
         const uint64_t strides[3] = {rowb, (uint64_t)Wq * rowb, (uint64_t)Hq * Wq * rowb};
-        AXB_TRY(make_map4(&mb, api, mdt, xq, dims, strides, BK, (uint32_t)bn));
+        AXB_TRY(make_map4(&mb, api, mdt, xq, dims, strides, BK, rows_per_tile > 1 ? 64u : (uint32_t)bn));
         TcParams p;
         memset(&p, 0, sizeof p);
-        p.M = d.Cout; p.N = d.OW; p.batch = d.N * d.OH;
+        p.M = d.Cout; p.N = d.OW; p.batch = d.N * groups;
         p.K = taps * cblocks * BK; // the plain (half-precision) path derives its k-block count from K
         p.tiles_m = (int)((d.Cout + BM - 1) / BM);
         p.bn = bn;
-        p.tiles_n = (int)((d.OW + bn - 1) / bn);
+        p.tiles_n = rows_per_tile > 1 ? 1 : (int)((d.OW + bn - 1) / bn);
         p.num_tiles = (int64_t)p.tiles_m * p.tiles_n * p.batch;
         p.c = d.out;
         p.c_rs = d.OH * d.OW * esz; p.c_cs = esz; p.c_bs = d.Cout * d.OH * d.OW * esz; p.c_hs = d.OW * esz;
         p.bias = d.bias; p.bias_rs = d.bias ? d.bias_s : 0; p.bias_cs = 0; p.bias_bs = 0;
         p.bias_dtype = d.bias_dtype; p.act = d.act; p.out_dtype = d.dtype;
         p.split = f32 ? 2 : 0; p.kbp = (int)(taps * cblocks); p.Kp = Cp;
-        p.conv_taps = (int)taps; p.conv_cblocks = (int)cblocks; p.conv_oh = (int)d.OH; p.conv_phases = d.sh * d.sw;
+        p.conv_taps = (int)taps; p.conv_cblocks = (int)cblocks; p.conv_oh = (int)groups; p.conv_phases = d.sh * d.sw;
+        p.conv_rows = rows_per_tile; p.conv_ohs = (int)d.OH;
         for (int64_t t = 0; t < taps; ++t) {
             p.conv_qw[t] = qw[t];
             p.conv_qh[t] = qh[t];

@@ -641,6 +641,61 @@ def sharded_configs(env):
         run(f"c3_layer_norm_{dt}", lambda: capi.check(L.axb_layer_norm(by(xd), by(wd), by(bd), -1, 1e-5, by(obig.desc()), None)),
             2 * rows * n * isz + 2 * n * 4, per_gpu=pg)
         del x, obig
+
+    # ---- round 2: the kernels either side of the path, same two regimes, sharded along the leading dim at N GPUs -------------
+    try:
+        # bf16 / fp32 gelu: 2^28 / N elements (bf16: 65 536-entry shared-memory table, csrc/half_lut.cu; fp32: chain kernel)
+        ne = (1 << 28) // world
+        xf = dev.randn((ne,), 21 + 100 * rank)
+        of = dev.DeviceArray.empty((ne,), capi.F32)
+        xfd, ofd = xf.desc(), of.desc()
+        run("ew_gelu_f32", lambda: capi.check(L.axb_unary(capi.OP["gelu"], by(xfd), by(ofd), 0.0, None)), ne * 8)
+        xh = dev.cast(xf, capi.BF16)
+        oh = dev.DeviceArray.empty((ne,), capi.BF16)
+        xhd, ohd = xh.desc(), oh.desc()
+        run("ew_gelu_bf16", lambda: capi.check(L.axb_unary(capi.OP["gelu"], by(xhd), by(ohd), 0.0, None)), ne * 4)
+        del xf, of, xh, oh
+        # elementwise producer + last-axis reduction in one kernel: (a * b).sum(axis 1), a {8192/N, 32768}, b {1, 32768}
+        a2, b2 = dev.randn((rows, n), 31 + 100 * rank), dev.randn((1, n), 32)
+        o2 = dev.DeviceArray.empty((rows,), capi.F32)
+        prog = [capi.make_instr(capi.OP["mul"], capi.F32, 0, 1)]
+        P = (capi.AxbInstr * 1)(*prog)
+        I2 = (capi.AxbTensor * 2)(a2.desc(), b2.desc())
+        o2d = o2.desc()
+        run("chain_rowsum_f32", lambda: capi.check(L.axb_elementwise_reduce_axis(P, 1, I2, 2, capi.OP["sum"], 1, 0, by(o2d), None)),
+            rows * n * 4 + n * 4 + rows * 4, per_gpu=pg)
+        del a2, b2, o2
+        # convolution as an implicit GEMM (gemm_tcgen05.cu conv_tc): bf16 3x3, 256 channels, {32/N,256,56,56}; the whisper
+        # encoder's second conv in fp32 (stride 2, + bias + gelu in the epilogue), batch 8/N
+        nbc = max(1, 32 // world)
+        xc = dev.cast(dev.randn((nbc, 256, 56, 56), 41 + 100 * rank), capi.BF16)
+        wc = dev.cast(dev.randn((256, 256, 3, 3), 42, 0.0, 0.02), capi.BF16)
+        bc = dev.cast(dev.randn((256,), 43), capi.BF16)
+        run("conv2d_bf16_256c_3x3", lambda: dev.conv(xc, wc, bc, stride=(1, 1), padding=(1, 1), dilation=(1, 1)),
+            flops=2.0 * nbc * 256 * 56 * 56 * 256 * 9, per_gpu={"images_per_gpu": nbc})
+        ex["conv2d_bf16_256c_3x3"]["kernel_path"] = int(L.axb_matmul_last_path())
+        del xc, wc, bc
+        nbw = max(1, 8 // world)
+        xw, ww, bw = dev.randn((nbw, 384, 3000), 44 + 100 * rank), dev.randn((384, 384, 3), 45, 0.0, 0.03), dev.randn((384,), 46)
+        run("conv1d_f32_whisper_conv2_gelu", lambda: dev.conv(xw, ww, bw, stride=2, padding=1, dilation=1, activation="gelu"),
+            flops=2.0 * nbw * 384 * 1500 * 384 * 3, per_gpu={"samples_per_gpu": nbw})
+        ex["conv1d_f32_whisper_conv2_gelu"]["kernel_path"] = int(L.axb_matmul_last_path())
+        ex["conv1d_f32_whisper_conv2_gelu"]["note"] = "fp32 through the three-piece bf16 split: 6 bf16 MMAs per fp32 MAC"
+        del xw, ww, bw
+        # flash attention at the whisper shape {8/N, 6, 1500, 64}, fp32 (three-piece) and bf16
+        for dt in ("f32", "bf16"):
+            q, k, v = (dev.randn((nbw, 6, 1500, 64), 50 + i + 100 * rank) for i in range(3))
+            code = capi.F32
+            if dt == "bf16":
+                q, k, v = (dev.cast(t, capi.BF16) for t in (q, k, v))
+                code = capi.BF16
+            o = dev.DeviceArray.empty((nbw, 6, 1500, 64), code)
+            qd, kd, vd, od = q.desc(), k.desc(), v.desc(), o.desc()
+            run(f"sdpa_{dt}_whisper", lambda: capi.check(L.axb_sdpa(by(qd), by(kd), by(vd), None, ctypes.c_float(-1.0), 0, by(od), None)),
+                flops=4.0 * nbw * 6 * 1500 * 1500 * 64, per_gpu={"samples_per_gpu": nbw})
+            del q, k, v, o
+    except Exception as exn:  # noqa: BLE001 — the BASELINE entries above must still be reported
+        ex["round2_extras_error"] = repr(exn)
     return ex
 
 

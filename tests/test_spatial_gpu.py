@@ -150,7 +150,10 @@ CONV_TC_2D = [((2, 64, 56, 56), (128, 64, 3, 3), dict(stride=(1, 1), padding=(1,
               ((2, 80, 33, 64), (64, 80, 3, 3), dict(stride=(1, 1), padding=(2, 2), dilation=(2, 2))),
               ((3, 200, 28, 40), (256, 200, 1, 1), dict(stride=(1, 1), padding=(0, 0), dilation=(1, 1))),
               ((1, 32, 64, 64), (64, 32, 7, 7), dict(stride=(2, 2), padding=(3, 3), dilation=(1, 1))),
-              ((2, 64, 60, 96), (64, 64, 3, 3), dict(stride=(3, 2), padding=(0, 1), dilation=(2, 1)))]
+              ((2, 64, 60, 96), (64, 64, 3, 3), dict(stride=(3, 2), padding=(0, 1), dilation=(2, 1))),
+              ((1, 64, 21, 200), (72, 64, 3, 3), dict(stride=(1, 1), padding=(1, 1), dilation=(1, 1))),   # wider than a tile: one row per tile
+              ((8, 64, 3, 64), (64, 64, 3, 3), dict(stride=(1, 1), padding=(1, 1), dilation=(1, 1))),     # OH = 3: two-row groups, ragged
+              ((4, 128, 14, 14), (256, 128, 3, 3), dict(stride=(1, 1), padding=(1, 1), dilation=(1, 1)))] # 14 x 14 feature map
 
 
 @pytest.mark.gpu
