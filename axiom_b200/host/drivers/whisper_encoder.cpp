@@ -10,6 +10,7 @@
 
 #include "axb.h"
 #include "backends/metal/metal_common.hpp"
+#include "cuda_plan.hpp"
 
 static void gpu_sync() { backends::metal::MetalExecutionStream::instance().synchronize(); }
 
@@ -76,13 +77,26 @@ int main(int argc, char **argv) {
     }
     gpu_sync();
     const uint64_t l0 = axb_launch_count();
+    // three clocks: wall time of the whole loop (host + device, what a caller sees), the HOST time to build, lower and enqueue
+    // the forwards (the loop body never waits for the device), and the DEVICE time between two events on the backend stream
+    axb_event_t ev0 = nullptr, ev1 = nullptr;
+    axb_event_create(&ev0);
+    axb_event_create(&ev1);
+    const auto plan0 = backends::cuda::plan::stats();
+    axb_event_record(ev0, nullptr);
     auto t0 = Clock::now();
     for (int i = 0; i < iters; ++i) {
         out = enc.forward(mel_g);
         out.sync();
     }
+    const double host_ms = std::chrono::duration<double, std::milli>(Clock::now() - t0).count() / iters;
+    axb_event_record(ev1, nullptr);
     gpu_sync();
     const double gpu_ms = std::chrono::duration<double, std::milli>(Clock::now() - t0).count() / iters;
+    float dev_total = 0.0f;
+    axb_event_elapsed_ms(ev0, ev1, &dev_total);
+    const double device_ms = dev_total / iters;
+    const auto plan1 = backends::cuda::plan::stats();
     const uint64_t launches = (axb_launch_count() - l0) / (uint64_t)iters;
 
     if (cpu_check) {
@@ -99,8 +113,12 @@ int main(int argc, char **argv) {
     const double gflop_per_sample = 36.9;
     std::printf("{\"workload\": \"whisper_poc encoder forward, random-init, mel {%zu,80,3000}\", \"batch\": %zu, \"gpu_ms\": %.3f,"
                 " \"samples_per_s\": %.2f, \"gpu_TFLOPs\": %.2f, \"gpu_launches_per_forward\": %llu, \"cpu_ms_one_sample\": %.1f,"
+                " \"host_enqueue_ms\": %.3f, \"device_ms\": %.3f, \"host_over_device\": %.3f, \"plan_cache_hits\": %llu,"
+                " \"plan_cache_misses\": %llu,"
                 " \"parity_checked\": %s, \"max_abs_diff\": %.3e, \"max_abs_ref\": %.3e, \"parity_ok\": %s}\n",
-                B, B, gpu_ms, B / gpu_ms * 1e3, gflop_per_sample * B / gpu_ms, (unsigned long long)launches, cpu_ms,
+                B, B, gpu_ms, B / gpu_ms * 1e3, gflop_per_sample * B / gpu_ms, (unsigned long long)launches, cpu_ms, host_ms, device_ms,
+                device_ms > 0 ? host_ms / device_ms : 0.0, (unsigned long long)(plan1.hits - plan0.hits),
+                (unsigned long long)(plan1.misses - plan0.misses),
                 cpu_check ? "true" : "false", max_abs, max_ref, ok ? "true" : "false");
     return ok ? 0 : 1;
 }
