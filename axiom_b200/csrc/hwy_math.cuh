@@ -147,7 +147,7 @@ __device__ __forceinline__ float Erf(float x) {
                 a5 = 1.061405429f;
     float sign = copysignf(1.0f, x);
     float ax = fabsf(x);
-    float t = __fdiv_rn(1.0f, fma_(p, ax, 1.0f));
+    float t = __frcp_rn(fma_(p, ax, 1.0f)); // == Div(1, d): both are the correctly rounded 1 / d; rcp.rn is the shorter sequence
     float poly = fma_(t, a5, a4);
     poly = fma_(t, poly, a3);
     poly = fma_(t, poly, a2);
@@ -167,12 +167,12 @@ __device__ __forceinline__ float Gelu(float x) {
 __device__ __forceinline__ float Sigmoid(float x) {
     float e = Exp(-fabsf(x));
     float denom = add(1.0f, e);
-    return (x >= 0.0f) ? __fdiv_rn(1.0f, denom) : __fdiv_rn(e, denom);
+    return __fdiv_rn((x >= 0.0f) ? 1.0f : e, denom); // IfThenElse(x >= 0, 1 / d, e / d): ONE division of the selected numerator
 }
 __device__ __forceinline__ float Silu(float x) {
     float e = Exp(-fabsf(x));
     float denom = add(1.0f, e);
-    return (x >= 0.0f) ? __fdiv_rn(x, denom) : __fdiv_rn(mul(x, e), denom);
+    return __fdiv_rn((x >= 0.0f) ? x : mul(x, e), denom); // one division of the selected numerator (same values as two)
 }
 // reference pow (hwy_kernels-inl.h:142-161): exp(b * log(a))
 __device__ __forceinline__ float Pow(float a, float b) { return Exp(mul(b, Log(a))); }

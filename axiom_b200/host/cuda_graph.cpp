@@ -81,6 +81,12 @@ int const_operands(const GraphNode *mm) {
         if (c && c->is_constant && c->constant_storage && c->output_shape.size() == 2 && c->output_dtype == DType::Float32 &&
             c->constant_storage->device() == Device::GPU)
             f |= i == 0 ? AXB_MM_CONST_A : AXB_MM_CONST_B;
+        // an ACTIVATION that several matmuls consume (the q / k / v projections of one layer-norm output,
+        // examples/whisper_poc.cpp:63-75): it was materialised as a shared sub-graph, so every consumer sees the same storage;
+        // its split is kept until that storage is released or written, and the second and third projection reuse it
+        else if (i == 0 && c && !c->is_constant && c->is_materialized_ && c->cached_result_ && c->ref_count > 0 &&
+                 c->output_dtype == DType::Float32 && c->cached_result_->device() == Device::GPU)
+            f |= AXB_MM_CONST_A;
     }
     return f;
 }
