@@ -167,6 +167,9 @@ axb_status launch_chain_reduce(const axb_instr *prog, int n_instr, const axb_ten
 axb_status launch_chain_rowreduce(const axb_instr *prog, int n_instr, const axb_tensor *inputs, int n_inputs,
                                   const axb_tensor *shape_desc, int opk, bool is_mean, float *out, cudaStream_t s, DeviceCtx *ctx,
                                   bool *done);
+axb_status launch_chain_softmax(const axb_instr *prog, int n_instr, const axb_tensor *inputs, int n_inputs,
+                                const axb_tensor *shape_desc, bool is_log, int epilogue, float *out, cudaStream_t s, DeviceCtx *ctx,
+                                bool *done);
 }
 // half_lut.cu: table-lookup evaluation of a chain over one half-precision tensor (*done = false: not applicable)
 namespace lut {

@@ -902,13 +902,18 @@ std::string kernel_source(const std::string &loads, const std::string &body, boo
     else if (reduce_opk < 4) // chain + full reduction: the body ends in EW_RED, the kernel in a CTA reduce (ew_prelude.cuh)
         snprintf(hdr, sizeof hdr, "\nEW_RKERNEL_BEGIN(axb_ew_red, %d, %s, %d, %d, %d, %d)\n", vec, wide ? "uint64_t" : "uint32_t",
                  n_outer, n_inputs, unroll, reduce_opk);
-    else // chain + last-axis reduction: reduce_opk = 4 * mode + op, mode 1 = one CTA per row, 2 = one warp per row
+    else if (reduce_opk < 64) // chain + last-axis reduction: reduce_opk = 4 * mode + op, mode 1 = one CTA per row, 2 = one warp per row
         snprintf(hdr, sizeof hdr, "\nEW_ROWKERNEL_BEGIN(axb_ew_rowred, %d, %s, %d, %d, %d, %d, %d)\n", vec, wide ? "uint64_t" : "uint32_t",
                  n_outer, n_inputs, unroll, reduce_opk & 3, (reduce_opk >> 2) == 1 ? 256 : 32);
+    else { // chain + softmax over the last axis: 64 + (NV - 1) + 8 * (G == 256) + 16 * log + 32 * epilogue
+        const int k = reduce_opk - 64;
+        snprintf(hdr, sizeof hdr, "\nEW_SMKERNEL_BEGIN(axb_ew_softmax, %d, %s, %d, %d, %d, %d, %d, %d)\n", vec, wide ? "uint64_t" : "uint32_t",
+                 n_outer, n_inputs, (k & 7) + 1, (k & 8) ? 256 : 32, (k >> 4) & 1, (k >> 5) & 3);
+    }
     s += hdr;
     s += "        EW_PRELOAD_BEGIN\n" + loads + "        EW_PRELOAD_END\n";
     s += "        EW_COMPUTE_BEGIN\n" + body + "        EW_COMPUTE_END\n";
-    s += reduce_opk < 0 ? "EW_KERNEL_END\n" : reduce_opk < 4 ? "EW_RKERNEL_END\n" : "EW_ROWKERNEL_END\n";
+    s += reduce_opk < 0 ? "EW_KERNEL_END\n" : reduce_opk < 4 ? "EW_RKERNEL_END\n" : reduce_opk < 64 ? "EW_ROWKERNEL_END\n" : "EW_SMKERNEL_END\n";
     return s;
 }
 
@@ -972,7 +977,9 @@ axb_status prepare(const axb_instr *prog, int n_instr, const axb_tensor *inputs,
     AXB_TRY(lower_program(prog, n_instr, inputs, n_inputs, wide, p, &fdt, reduce_opk < 0, &body, &loads));
     AXB_REQUIRE(fdt == out->dtype, AXB_ERR_INVALID, "axb_elementwise: last instruction yields dtype %d but out is %d", fdt,
                 out->dtype);
-    if (reduce_opk >= 0) {
+    if (reduce_opk >= 64) {
+        body += "            EW_KEEP\n";
+    } else if (reduce_opk >= 0) {
         char line[64];
         snprintf(line, sizeof line, "            EW_RED(%d)\n", reduce_opk & 3);
         body += line;
@@ -1201,6 +1208,59 @@ axb_status launch_chain_reduce(const axb_instr *prog, int n_instr, const axb_ten
     return AXB_OK;
 }
 
+// Padded-pitch descriptor of a chain value that is never written: no operand set is dense across its last two dims any more, so
+// plan_iteration keeps the last axis as the innermost run while the outer dims still collapse.
+static axb_tensor row_desc(const axb_tensor &shape_desc) {
+    axb_tensor od = shape_desc;
+    od.base = reinterpret_cast<void *>(uintptr_t(256));
+    od.byte_offset = 0;
+    const int nd = od.ndim;
+    const int64_t esz = (int64_t)dtype_size(od.dtype);
+    int64_t pitch = od.shape[nd - 1] * esz + 16;
+    od.strides[nd - 1] = esz;
+    for (int d = nd - 2; d >= 0; --d) {
+        od.strides[d] = pitch;
+        pitch *= std::max<int64_t>(od.shape[d], 1);
+    }
+    return od;
+}
+
+// Chain + softmax / log_softmax over the last axis [+ row sum / mean / max of the result] in one pass
+// (axb_elementwise_softmax): rows of at most 256 * 8 vectors; `out` holds the fp32 rows (epilogue 0) or one fp32 per row.
+axb_status launch_chain_softmax(const axb_instr *prog, int n_instr, const axb_tensor *inputs, int n_inputs,
+                                const axb_tensor *shape_desc, bool is_log, int epilogue, float *out, cudaStream_t s, DeviceCtx *ctx,
+                                bool *done) {
+    *done = false;
+    const int nd = shape_desc->ndim;
+    if (nd < 1 || shape_desc->shape[nd - 1] < 2 || dtype_size(shape_desc->dtype) != 4)
+        return AXB_OK;
+    const int64_t len = shape_desc->shape[nd - 1];
+    int64_t rows = 1;
+    for (int d = 0; d < nd - 1; ++d)
+        rows *= shape_desc->shape[d];
+    const int64_t nvec = (len + 3) / 4; // fp32 chains: 4 elements per vector
+    if (rows == 0 || rows >= (1ll << 31) || nvec > 256 * 8)
+        return AXB_OK;
+    const bool cta = nvec > 32 * 8 || (nvec > 64 && rows < 4096); // one warp per row while 8 vectors per lane cover it
+    const int g = cta ? 256 : 32;
+    const int nv = (int)((nvec + g - 1) / g);
+    const axb_tensor od = row_desc(*shape_desc);
+    Prepared P;
+    bool empty = false;
+    jit::Kernel k;
+    const int code = 64 + (nv - 1) + (cta ? 8 : 0) + (is_log ? 16 : 0) + 32 * epilogue;
+    AXB_TRY(plan_lookup(prog, n_instr, inputs, n_inputs, &od, code, "axb_ew_softmax", ctx->device, &P, &k, &empty));
+    if (empty || (int64_t)P.p.inner_len != len || (int64_t)(P.p.total_vec / P.p.nvec_inner) != rows || (int64_t)P.p.nvec_inner != nvec)
+        return AXB_OK;
+    P.p.reduce_ws = out;
+    const int64_t blocks = cta ? rows : (rows + 7) / 8;
+    void *args[] = {&P.p};
+    AXB_TRY(jit::launch(k, (unsigned)blocks, 256, 0, s, args));
+    count_launch();
+    *done = true;
+    return AXB_OK;
+}
+
 // Chain + reduction over the LAST axis of the chain's value in one pass (host_api.cpp axb_elementwise_reduce_axis): `out`
 // holds one fp32 per row of `shape_desc`. *done = false leaves the call to the unfused path (the planner could not keep the
 // reduced axis as the innermost run on its own, or the row count does not fit a grid).
@@ -1267,7 +1327,15 @@ axb_status axb_elementwise_precompile(const axb_instr *prog, int n_instr, const 
 // row, 2 = last axis with one warp per row (axb_elementwise_reduce_axis); reduce_op sum / mean / max / min.
 axb_status axb_elementwise_reduce_precompile(const axb_instr *prog, int n_instr, const axb_tensor *inputs, int n_inputs,
                                              const axb_tensor *shape_desc, int32_t reduce_op, int reduce_kind) {
-    AXB_REQUIRE(shape_desc && reduce_kind >= 0 && reduce_kind <= 2, AXB_ERR_INVALID, "axb_elementwise_reduce_precompile: bad arguments");
+    AXB_REQUIRE(shape_desc && reduce_kind >= 0, AXB_ERR_INVALID, "axb_elementwise_reduce_precompile: bad arguments");
+    if (reduce_kind >= 64) { // a chain + softmax kernel code (see launch_chain_softmax), for build-time checks
+        const axb_tensor od = row_desc(*shape_desc);
+        Prepared P;
+        bool empty = false;
+        AXB_TRY(prepare(prog, n_instr, inputs, n_inputs, &od, &P, &empty, reduce_kind));
+        return empty ? AXB_OK : jit::precompile(P.source);
+    }
+    AXB_REQUIRE(reduce_kind <= 2, AXB_ERR_INVALID, "axb_elementwise_reduce_precompile: bad reduce_kind");
     const int opk = (reduce_op == AXB_OP_SUM || reduce_op == AXB_OP_MEAN) ? 0 : reduce_op == AXB_OP_MAX ? 1 : reduce_op == AXB_OP_MIN ? 2 : -1;
     AXB_REQUIRE(opk >= 0, AXB_ERR_UNSUPPORTED, "axb_elementwise_reduce_precompile: sum / mean / max / min only");
     axb_tensor od = *shape_desc;

@@ -841,5 +841,142 @@ __device__ __forceinline__ void ew_run_row(const Params &p, uint32_t row, uint32
         }                                                                                               \
     }
 
+
+// ---- chain -> softmax / log_softmax over the LAST axis [-> row sum / mean / max] in one pass ("softmax
+// with elementwise prologue / epilogue"; `(x * s + m).softmax(-1)`, and the README chain's `.softmax(-1).sum({1})`) -----------
+// Same row ownership as EW_ROWKERNEL (G = 256: one CTA per row, G = 32: one warp per row), but the chain's values STAY in
+// registers: thread t computes vectors t, t + G, ..., t + (NV - 1) G of its row (NV <= 8, i.e. rows of at most G * NV * VEC
+// elements; longer rows run chain and softmax as two launches), the group reduces max and sum(exp(x - max)) and the thread
+// writes exp(x - max) / sum — or (x - max) - log(sum) — for its own elements. EPI: 0 = store the row, 1 = sum, 2 = mean,
+// 3 = max of the softmax values, one fp32 per row. Numerics = the reference's op sequence (cpu_operations.cpp:3132-3158:
+// max, exp(x - max), sum, divide) with expf / logf and a tree instead of the serial sum, inside the 1e-5 contract of the
+// stand-alone softmax kernels.
+#define EW_KEEP                                                                                         \
+    {                                                                                                   \
+        _Pragma("unroll") for (int i = 0; i < VEC; ++i) if (i < x.valid) kv[i] = asF<W>(acc[i]);        \
+    }
+template <int G> __device__ __forceinline__ float group_max(float v, float *sm) {
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1)
+        v = fmaxf(v, __shfl_xor_sync(0xFFFFFFFFu, v, d));
+    if (G == 256) {
+        __syncthreads(); // the scratch may still be read by the previous reduction
+        if ((threadIdx.x & 31) == 0)
+            sm[threadIdx.x >> 5] = v;
+        __syncthreads();
+        v = sm[0];
+#pragma unroll
+        for (int w = 1; w < 8; ++w)
+            v = fmaxf(v, sm[w]);
+    }
+    return v;
+}
+template <int G> __device__ __forceinline__ float group_sum(float v, float *sm) {
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1)
+        v = __fadd_rn(v, __shfl_xor_sync(0xFFFFFFFFu, v, d));
+    if (G == 256) {
+        __syncthreads();
+        if ((threadIdx.x & 31) == 0)
+            sm[threadIdx.x >> 5] = v;
+        __syncthreads();
+        v = sm[0];
+#pragma unroll
+        for (int w = 1; w < 8; ++w)
+            v = __fadd_rn(v, sm[w]);
+    }
+    return v;
+}
+#define EW_SMKERNEL_BEGIN(NAME, VEC_, WTYPE, NOUT_, NIN_, NV_, G_, LOG_, EPI_)                          \
+    extern "C" __global__ void __launch_bounds__(256) NAME(const __grid_constant__ axb::ew::Params p) { \
+        using namespace axb::ew;                                                                        \
+        constexpr int VEC = VEC_, NOUT = NOUT_, NIN = NIN_, NV = NV_, G = G_, LOG = LOG_, EPI = EPI_;   \
+        typedef WTYPE W;                                                                                \
+        typedef Ctx<W, VEC, NIN> X;                                                                     \
+        float keep[NV][VEC];                                                                            \
+        float *kv = keep[0];
+#define EW_SMKERNEL_END                                                                                 \
+        __shared__ float red_sm[8];                                                                     \
+        const float ninf = __int_as_float(0xff800000);                                                  \
+        const uint32_t rows = p.total_vec / p.nvec_inner;                                               \
+        const uint32_t row = G == 256 ? blockIdx.x : blockIdx.x * 8u + (threadIdx.x >> 5);              \
+        const uint32_t tig = G == 256 ? threadIdx.x : (threadIdx.x & 31u);                              \
+        const bool active = row < rows;                                                                 \
+        uint32_t rc[kMaxOuter];                                                                         \
+        {                                                                                               \
+            uint32_t r = row;                                                                           \
+            _Pragma("unroll") for (int d = 0; d < kMaxOuter; ++d) {                                     \
+                rc[d] = 0;                                                                              \
+                if (d < NOUT) {                                                                         \
+                    if (d == NOUT - 1) {                                                                \
+                        rc[d] = r;                                                                      \
+                    } else {                                                                            \
+                        uint32_t q = fastdiv(r, p.div_m[1 + d], p.div_s[1 + d]);                        \
+                        rc[d] = r - q * p.outer_shape[d];                                               \
+                        r = q;                                                                          \
+                    }                                                                                   \
+                }                                                                                       \
+            }                                                                                           \
+        }                                                                                               \
+        _Pragma("unroll") for (int j = 0; j < NV; ++j) {                                                \
+            _Pragma("unroll") for (int i = 0; i < VEC; ++i) keep[j][i] = ninf;                          \
+            const uint32_t vi = tig + (uint32_t)(j * G);                                                \
+            if (active && vi < p.nvec_inner) {                                                          \
+                X x;                                                                                    \
+                x.ok = true;                                                                            \
+                x.col = vi * VEC;                                                                       \
+                x.valid = (int)min((uint32_t)VEC, p.inner_len - x.col);                                 \
+                _Pragma("unroll") for (int d = 0; d < kMaxOuter; ++d) x.c[d] = rc[d];                   \
+                kv = keep[j];                                                                           \
+                preload(x);                                                                             \
+                compute(x);                                                                             \
+            }                                                                                           \
+        }                                                                                               \
+        float m = ninf;                                                                                 \
+        _Pragma("unroll") for (int j = 0; j < NV; ++j)                                                  \
+            _Pragma("unroll") for (int i = 0; i < VEC; ++i) m = fmaxf(m, keep[j][i]);                   \
+        m = group_max<G>(m, red_sm);                                                                    \
+        float ssum = 0.0f;                                                                              \
+        _Pragma("unroll") for (int j = 0; j < NV; ++j)                                                  \
+            _Pragma("unroll") for (int i = 0; i < VEC; ++i) {                                           \
+                const float d_ = __fsub_rn(keep[j][i], m);                                              \
+                const float e_ = expf(d_);                                                              \
+                ssum = __fadd_rn(ssum, e_);                                                             \
+                keep[j][i] = LOG ? d_ : e_;                                                             \
+            }                                                                                           \
+        ssum = group_sum<G>(ssum, red_sm);                                                              \
+        const float lg = LOG ? logf(ssum) : 0.0f;                                                       \
+        float racc = EPI == 3 ? ninf : 0.0f;                                                            \
+        float *rout = reinterpret_cast<float *>(p.reduce_ws);                                           \
+        _Pragma("unroll") for (int j = 0; j < NV; ++j) {                                                \
+            const uint32_t vi = tig + (uint32_t)(j * G);                                                \
+            if (!(active && vi < p.nvec_inner))                                                         \
+                continue;                                                                               \
+            const uint32_t col = vi * VEC;                                                              \
+            const int valid = (int)min((uint32_t)VEC, p.inner_len - col);                               \
+            float o_[VEC];                                                                              \
+            _Pragma("unroll") for (int i = 0; i < VEC; ++i)                                             \
+                o_[i] = LOG ? __fsub_rn(keep[j][i], lg) : __fdiv_rn(keep[j][i], ssum);                  \
+            if (EPI == 0) {                                                                             \
+                float *dst = rout + (size_t)row * p.inner_len + col;                                    \
+                if (VEC == 4 && valid == 4 && (p.inner_len & 3u) == 0 && (reinterpret_cast<size_t>(rout) & 15) == 0) { \
+                    *reinterpret_cast<float4 *>(dst) = make_float4(o_[0], o_[1], o_[2], o_[3]);         \
+                } else {                                                                                \
+                    _Pragma("unroll") for (int i = 0; i < VEC; ++i) if (i < valid) dst[i] = o_[i];      \
+                }                                                                                       \
+            } else {                                                                                    \
+                _Pragma("unroll") for (int i = 0; i < VEC; ++i) if (i < valid)                          \
+                    racc = EPI == 3 ? fmaxf(racc, o_[i]) : __fadd_rn(racc, o_[i]);                      \
+            }                                                                                           \
+        }                                                                                               \
+        if (EPI != 0) {                                                                                 \
+            racc = EPI == 3 ? group_max<G>(racc, red_sm) : group_sum<G>(racc, red_sm);                  \
+            if (EPI == 2)                                                                               \
+                racc = __fdiv_rn(racc, (float)p.inner_len);                                             \
+            if (tig == 0 && active)                                                                     \
+                rout[row] = racc;                                                                       \
+        }                                                                                               \
+    }
+
 } // namespace ew
 } // namespace axb

@@ -456,4 +456,83 @@ axb_status axb_elementwise_reduce_axis(const axb_instr *prog, int n_instr, const
     return st;
 }
 
+// softmax / log_softmax over the LAST axis of a chain's value, optionally followed by a sum / mean / max over that same axis.
+// One kernel for fp32 chains with rows of at most 8192 elements (the chain's values stay in registers between the max, the
+// sum and the normalisation); otherwise the chain, axb_softmax and axb_reduce run one after the other with the same result.
+axb_status axb_elementwise_softmax(const axb_instr *prog, int n_instr, const axb_tensor *inputs, int n_inputs, int is_log,
+                                   int32_t epilogue_op, const axb_tensor *out, axb_stream_t stream) {
+    AXB_REQUIRE(prog && n_instr > 0 && n_inputs > 0 && inputs, AXB_ERR_INVALID, "axb_elementwise_softmax: bad arguments");
+    AXB_TRY(validate_tensor(out, "axb_elementwise_softmax(out)"));
+    AXB_REQUIRE(epilogue_op == 0 || epilogue_op == AXB_OP_SUM || epilogue_op == AXB_OP_MEAN || epilogue_op == AXB_OP_MAX, AXB_ERR_UNSUPPORTED,
+                "axb_elementwise_softmax: the row epilogue is none / sum / mean / max");
+    int64_t shape[AXB_MAX_DIMS];
+    int nd = inputs[0].ndim;
+    memcpy(shape, inputs[0].shape, sizeof(int64_t) * nd);
+    for (int k = 1; k < n_inputs; ++k) {
+        int64_t nxt[AXB_MAX_DIMS];
+        int nn = 0;
+        AXB_TRY(axb_broadcast_shape(shape, nd, inputs[k].shape, inputs[k].ndim, nxt, &nn));
+        memcpy(shape, nxt, sizeof(int64_t) * nn);
+        nd = nn;
+    }
+    AXB_REQUIRE(nd >= 1, AXB_ERR_SHAPE, "axb_elementwise_softmax: rank-0 chain");
+    cudaStream_t s;
+    DeviceCtx *ctx;
+    AXB_TRY(resolve_stream(stream, &s, &ctx));
+    const int32_t vdt = prog[n_instr - 1].dtype;
+    axb_tensor tmp = make_contiguous_desc(nullptr, vdt, shape, nd);
+    int64_t rows = 1;
+    for (int d = 0; d < nd - 1; ++d)
+        rows *= shape[d];
+    const int64_t want = epilogue_op ? rows : numel(tmp);
+    AXB_REQUIRE(numel(*out) == want, AXB_ERR_SHAPE, "axb_elementwise_softmax: output has %lld elements, expected %lld", (long long)numel(*out),
+                (long long)want);
+    if (numel(tmp) == 0)
+        return AXB_OK;
+    static const bool two_pass = getenv("AXB_EW_REDUCE_TWO_PASS") != nullptr; // A/B switch
+    bool wide = false;
+    for (int k = 0; k < n_inputs; ++k)
+        wide = wide || is_64bit_dtype(inputs[k].dtype);
+    for (int i = 0; i < n_instr; ++i)
+        wide = wide || is_64bit_dtype(prog[i].dtype);
+    if (!two_pass && !wide && vdt == AXB_F32 && out->dtype == AXB_F32 && is_contiguous(*out) && !(is_log && epilogue_op)) {
+        bool done = false;
+        const int epi = epilogue_op == AXB_OP_SUM ? 1 : epilogue_op == AXB_OP_MEAN ? 2 : epilogue_op == AXB_OP_MAX ? 3 : 0;
+        AXB_TRY(ew::launch_chain_softmax(prog, n_instr, inputs, n_inputs, &tmp, is_log != 0, epi, reinterpret_cast<float *>(tensor_ptr(*out)), s,
+                                         ctx, &done));
+        if (done)
+            return AXB_OK;
+    }
+    // unfused: chain -> softmax -> (row reduction)
+    void *buf = nullptr, *buf2 = nullptr;
+    const size_t bytes = (size_t)numel(tmp) * dtype_size(vdt);
+    AXB_TRY(axb_alloc(bytes, s, &buf));
+    tmp.base = buf;
+    axb_status st = axb_elementwise(prog, n_instr, inputs, n_inputs, &tmp, s);
+    if (st == AXB_OK && !epilogue_op) {
+        axb_tensor od = *out; // same element order; give it the chain's shape
+        axb_tensor shaped = make_contiguous_desc(tensor_ptr(*out), out->dtype, shape, nd);
+        (void)od;
+        st = is_contiguous(*out) ? axb_softmax(&tmp, nd - 1, is_log, &shaped, s) : fail(AXB_ERR_UNSUPPORTED, "axb_elementwise_softmax: output must be contiguous");
+    } else if (st == AXB_OK) {
+        st = axb_alloc(bytes, s, &buf2);
+        if (st == AXB_OK) {
+            axb_tensor sm = make_contiguous_desc(buf2, vdt, shape, nd);
+            st = axb_softmax(&tmp, nd - 1, is_log, &sm, s);
+            const int32_t ax = nd - 1;
+            if (st == AXB_OK) {
+                int64_t rshape[AXB_MAX_DIMS];
+                for (int d = 0; d < nd - 1; ++d)
+                    rshape[d] = shape[d];
+                axb_tensor rd = make_contiguous_desc(tensor_ptr(*out), out->dtype, rshape, nd - 1);
+                st = is_contiguous(*out) ? axb_reduce(epilogue_op, &sm, &ax, 1, 0, &rd, s) : fail(AXB_ERR_UNSUPPORTED, "axb_elementwise_softmax: output must be contiguous");
+            }
+        }
+    }
+    if (buf2)
+        axb_free(buf2, s);
+    axb_free(buf, s);
+    return st;
+}
+
 } // extern "C"

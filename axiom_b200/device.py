@@ -415,3 +415,15 @@ def elementwise_reduce_axis(prog: List[capi.AxbInstr], inputs: Sequence[DeviceAr
     check(lib().axb_elementwise_reduce_axis(P, len(prog), I, len(inputs), capi.OP[op], axis, int(keep_dims),
                                             ctypes.byref(out.desc()), None))
     return out
+
+
+def elementwise_softmax(prog: List[capi.AxbInstr], inputs: Sequence[DeviceArray], log: bool = False,
+                        epilogue: Optional[str] = None) -> DeviceArray:
+    """softmax / log_softmax over the last axis of the chain's value [+ row sum / mean / max] (axb_elementwise_softmax)."""
+    P = (capi.AxbInstr * len(prog))(*prog)
+    I = (capi.AxbTensor * len(inputs))(*[t.desc() for t in inputs])
+    shape = list(_bshape(*[x.shape for x in inputs]))
+    out = DeviceArray.empty(tuple(shape[:-1]) if epilogue else tuple(shape), prog[-1].dtype)
+    check(lib().axb_elementwise_softmax(P, len(prog), I, len(inputs), int(log), capi.OP[epilogue] if epilogue else 0,
+                                        ctypes.byref(out.desc()), None))
+    return out

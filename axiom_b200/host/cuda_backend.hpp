@@ -119,5 +119,7 @@ std::map<std::string, Tensor> load_file_tensors(const std::string &filename, con
 namespace graph {
 // cuda_graph.cpp: where() with lazy operands lowered into one elementwise program
 Tensor fused_where(const Tensor &cond, const Tensor &a, const Tensor &b);
+// cuda_graph.cpp: eager softmax / log_softmax of a lazy operand, its elementwise tree as the kernel's prologue (empty: n/a)
+Tensor fused_softmax(const Tensor &input, int axis, bool is_log);
 } // namespace graph
 } // namespace axiom

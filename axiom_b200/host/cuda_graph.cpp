@@ -184,6 +184,51 @@ struct Lowering {
         throw RuntimeError::internal("CUDA graph lowering: could not split an elementwise tree");
     }
 
+    // softmax / log_softmax over the last axis of a 32-bit float node, with the node's own elementwise producers as a prologue
+    // and an optional row reduction of the result as an epilogue. `sm` is the Softmax / LogSoftmax node;
+    // returns false when the pattern does not apply (other axis, other dtype, rows too long are decided inside libaxb).
+    bool try_fused_softmax(const GraphNode *sm, OpType epilogue, const Shape &out_shape, Tensor *result) {
+        if (sm->output_dtype != DType::Float32)
+            return false;
+        return fused_softmax_core(sm->inputs.at(0).get(), get_params<ActivationParams>(sm->params).axis,
+                                  sm->op_type == OpType::LogSoftmax, epilogue, out_shape, result);
+    }
+    // c = the node whose value is normalised (its own elementwise producers become the prologue)
+    bool fused_softmax_core(const GraphNode *c, int ax, bool is_log, OpType epilogue, const Shape &out_shape, Tensor *result) {
+        const int nd = (int)c->output_shape.size();
+        if (nd < 1 || c->output_dtype != DType::Float32)
+            return false;
+        if (!(ax == nd - 1 || ax == -1) || c->output_shape.back() < 2 || c->output_shape.back() > 8192 ||
+            ShapeUtils::size(c->output_shape) == 0)
+            return false;
+        Program pg;
+        if (!is_leaf(c) && !value.count(c) && is_fusable(c)) {
+            pg = build_program(c);
+        } else { // nothing to fuse in front: the program is the identity on the (evaluated) input
+            if (epilogue == OpType::_Count)
+                return false; // plain softmax of a tensor: the stand-alone kernel family
+            if (!is_leaf(c) && !value.count(c))
+                eval(c);
+            axb_instr id{};
+            id.op = AXB_OP_CAST;
+            id.dtype = AXB_F32;
+            id.src[0] = 0;
+            id.src[1] = id.src[2] = AXB_SRC_NONE;
+            pg.instrs.push_back(id);
+            pg.inputs.push_back(c);
+        }
+        Tensor r = empty_gpu(out_shape, DType::Float32);
+        std::vector<axb_tensor> ins(pg.inputs.size());
+        for (size_t i = 0; i < pg.inputs.size(); ++i)
+            ins[i] = describe(get(pg.inputs[i]));
+        const axb_tensor od = describe(r);
+        check(plan::elementwise_softmax(pg.instrs.data(), (int)pg.instrs.size(), ins.data(), (int)ins.size(),
+                                        is_log ? 1 : 0, epilogue == OpType::_Count ? 0 : to_axb_op(epilogue), &od),
+              "axb_elementwise_softmax");
+        *result = std::move(r);
+        return true;
+    }
+
     void run_program(const Program &pg, const axb_tensor &out, int32_t reduce_op /* <0: none */) {
         std::vector<axb_tensor> ins(pg.inputs.size());
         for (size_t i = 0; i < pg.inputs.size(); ++i)
@@ -230,7 +275,8 @@ struct Lowering {
             r = backends::cuda::gpu_matmul(input(n, 0), input(n, 1), mp.transpose_a, mp.transpose_b, nullptr, OpType::_Count,
                                            const_operands(n));
         } else if (op == OpType::Softmax || op == OpType::LogSoftmax) {
-            r = backends::cuda::gpu_softmax(input(n, 0), get_params<ActivationParams>(n->params).axis, op == OpType::LogSoftmax);
+            if (!try_fused_softmax(n, OpType::_Count, n->output_shape, &r)) // elementwise producers as a prologue
+                r = backends::cuda::gpu_softmax(input(n, 0), get_params<ActivationParams>(n->params).axis, op == OpType::LogSoftmax);
         } else if (op == OpType::LayerNorm) {
             const auto &np = get_params<NormParams>(n->params);
             r = backends::metal::gpu_layer_norm(input(n, 0), input(n, 1), input(n, 2), np.axis, np.eps);
@@ -330,6 +376,12 @@ struct Lowering {
                 Program pg = build_program(c);
                 r = empty_gpu(n->output_shape, n->output_dtype);
                 run_program(pg, describe(r), to_axb_op(op));
+            } else if (!full && rp.axes.size() == 1 && (op == OpType::Sum || op == OpType::Max || op == OpType::Mean) && !is_leaf(c) &&
+                       !value.count(c) && c->op_type == OpType::Softmax && c->ref_count <= 1 && n->output_dtype == DType::Float32 &&
+                       (rp.axes[0] == (int)c->output_shape.size() - 1 || rp.axes[0] == -1) &&
+                       try_fused_softmax(c, op, n->output_shape, &r)) {
+                // softmax(...).sum / mean / max over the softmax axis (the README chain): one kernel, the probabilities
+                // never reach HBM
             } else if (!full && rp.axes.size() == 1 && (op == OpType::Sum || op == OpType::Max || op == OpType::Min || op == OpType::Mean) &&
                        !is_leaf(c) && !value.count(c) && is_fusable(c) && c->output_dtype == DType::Float32 &&
                        n->output_dtype == DType::Float32 && ShapeUtils::size(c->output_shape) > 0 &&
@@ -486,6 +538,24 @@ void materialize_gpu_graph(GraphNode *root) {
     for (auto &inp : root->inputs)
         if (inp && !inp->is_constant && inp->ref_count > 0)
             inp->ref_count--;
+}
+
+// softmax / log_softmax that arrive EAGERLY with a lazy operand (ops::log_softmax is eager on every device,
+// operations.cpp:1437-1449): the operand's elementwise tree is lowered into the same kernel as the normalisation. Returns an
+// empty Tensor when the pattern does not apply (the caller then materialises the operand and runs the stand-alone kernel).
+Tensor fused_softmax(const Tensor &input, int axis, bool is_log) {
+    auto ln = input.lazy_node();
+    if (!ln || ln->is_materialized_ || ln->output_dtype != DType::Float32)
+        return Tensor();
+    backends::cuda::ensure_initialized();
+    materialize_shared_below(ln.get());
+    if (ln->ref_count > 1 || !is_fusable(ln.get()))
+        return Tensor(); // someone else consumes the value as well, or there is nothing elementwise to fuse
+    Lowering L;
+    Tensor r;
+    if (!L.fused_softmax_core(ln.get(), axis, is_log, OpType::_Count, ln->output_shape, &r))
+        return Tensor();
+    return r;
 }
 
 // where(cond, a, b) is eager in the reference (operations.cpp:1548-1570), which would cut `chain.where(c > 0, 0)` into

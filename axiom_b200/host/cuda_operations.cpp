@@ -335,6 +335,11 @@ class CudaOperation final : public ops::Operation {
         return gpu_unary(type_, input, type_ == OpType::LeakyReLU ? 0.01 : 0.0);
     }
     Tensor execute_reduction(const Tensor &input, const std::vector<int> &axis, bool keep_dims) const override {
+        if ((type_ == OpType::Softmax || type_ == OpType::LogSoftmax) && input.is_lazy() && input.device() == Device::GPU) {
+            Tensor r = graph::fused_softmax(input, axis.empty() ? -1 : axis[0], type_ == OpType::LogSoftmax);
+            if (r.storage())
+                return r;
+        }
         return gpu_reduce(type_, input, axis, keep_dims);
     }
     Tensor execute_matmul(const Tensor &a, const Tensor &b, bool ta, bool tb) const override {

@@ -20,7 +20,7 @@ using graph::GraphNode;
 
 enum Fn : int32_t {
     F_ELEMENTWISE, F_ELEMENTWISE_REDUCE, F_MATMUL, F_SOFTMAX, F_LAYER_NORM, F_RMS_NORM, F_REDUCE, F_ARGREDUCE, F_CAST,
-    F_GATHER_STRIDED, F_IM2COL, F_BINARY, F_UNARY, F_WHERE, F_MASKED_FILL, F_PAD, F_CONV2D, F_FILL, F_POOL, F_SORT, F_ELEMENTWISE_REDUCE_AXIS
+    F_GATHER_STRIDED, F_IM2COL, F_BINARY, F_UNARY, F_WHERE, F_MASKED_FILL, F_PAD, F_CONV2D, F_FILL, F_POOL, F_SORT, F_ELEMENTWISE_REDUCE_AXIS, F_ELEMENTWISE_SOFTMAX
 };
 enum Kind : int8_t { K_NONE = 0, K_LEAF = 1, K_TEMP = 2 };
 
@@ -201,6 +201,10 @@ axb_status invoke(const Call &c, axb_tensor *T) {
         const int n_in = (int)c.iv[0];
         return axb_elementwise_reduce_axis(c.prog.data(), (int)c.prog.size(), T, n_in, (int32_t)c.iv[1], (int)c.iv[2], (int)c.iv[3], &T[n_in],
                                            nullptr);
+    }
+    case F_ELEMENTWISE_SOFTMAX: {
+        const int n_in = (int)c.iv[0];
+        return axb_elementwise_softmax(c.prog.data(), (int)c.prog.size(), T, n_in, (int)c.iv[1], (int32_t)c.iv[2], &T[n_in], nullptr);
     }
     case F_MATMUL: {
         axb_matmul_epilogue e{};
@@ -531,6 +535,19 @@ axb_status elementwise_reduce_axis(const axb_instr *prog, int n_instr, const axb
     c->iv[1] = reduce_op;
     c->iv[2] = axis;
     c->iv[3] = keep_dims;
+    for (int i = 0; i < n_inputs; ++i)
+        c->t[i] = resolve(&inputs[i]);
+    c->t[n_inputs] = resolve(out);
+    return st_;
+}
+axb_status elementwise_softmax(const axb_instr *prog, int n_instr, const axb_tensor *inputs, int n_inputs, int is_log, int32_t epilogue_op,
+                               const axb_tensor *out) {
+    AXB_PLAN_CALL(axb_elementwise_softmax(prog, n_instr, inputs, n_inputs, is_log, epilogue_op, out, nullptr))
+    Call *c = sc.open(F_ELEMENTWISE_SOFTMAX);
+    c->prog.assign(prog, prog + n_instr);
+    c->iv[0] = n_inputs;
+    c->iv[1] = is_log;
+    c->iv[2] = epilogue_op;
     for (int i = 0; i < n_inputs; ++i)
         c->t[i] = resolve(&inputs[i]);
     c->t[n_inputs] = resolve(out);

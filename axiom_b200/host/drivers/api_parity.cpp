@@ -111,6 +111,10 @@ int main() {
         fused("chain_mean_last_axis_keepdims", p, [&](const Tensor &t) { return t.square().mean({1}, true); }, false);
         fused("chain_max_last_axis", p, [&](const Tensor &t) { return (t * Q(t)).abs().max(1); }, true);
         fused("chain_min_short_rows", sm, [&](const Tensor &t) { return (t.relu() - 0.5f).min(1); }, true);
+        // softmax with an elementwise prologue, and with a row-reduction epilogue
+        fused("chain_softmax", p, [&](const Tensor &t) { return (t * 0.5f + Q(t)).softmax(-1); }, false);
+        fused("chain_log_softmax", sm, [&](const Tensor &t) { return (t * t - 1.0f).log_softmax(-1); }, false);
+        fused("softmax_then_row_max", sm, [&](const Tensor &t) { return (t * 2.0f).softmax(-1).max(1); }, false);
     }
     // scalar-operand forms of where (the patched Tensor::where(cond, scalar) overloads, tensor.cpp:1340-1355)
     Tensor y = Tensor::randn({5, 1, 33}), c = Tensor::randn({5, 7, 33});

@@ -205,6 +205,13 @@ axb_status axb_elementwise(const axb_instr *prog, int n_instr, const axb_tensor 
  * use (the analogue of the reference's per-signature MPSGraph cache, mpsgraph_fused.mm:373-377). */
 axb_status axb_elementwise_precompile(const axb_instr *prog, int n_instr, const axb_tensor *inputs, int n_inputs,
                                       const axb_tensor *out);
+/* softmax (is_log = 0) / log_softmax over the LAST axis of the chain's value, optionally followed by a row reduction of the
+ * result over that axis (epilogue_op 0 = none: `out` holds the rows; AXB_OP_SUM / MEAN / MAX: one value per row) — SURVEY §7
+ * step 6 "softmax with elementwise prologue / epilogue": `(x * s + m).softmax(-1)` and the README chain's
+ * `.softmax(-1).sum({1})` are ONE kernel for fp32 chains with rows of at most 8192 elements (values stay in registers between
+ * max, sum and normalisation); otherwise chain, axb_softmax and axb_reduce run back to back. `out` contiguous. */
+axb_status axb_elementwise_softmax(const axb_instr *prog, int n_instr, const axb_tensor *inputs, int n_inputs, int is_log,
+                                   int32_t epilogue_op, const axb_tensor *out, axb_stream_t stream);
 axb_status axb_elementwise_reduce_precompile(const axb_instr *prog, int n_instr, const axb_tensor *inputs, int n_inputs,
                                              const axb_tensor *shape_desc, int32_t reduce_op, int reduce_kind);
 /* Launch-plan cache of the fused-chain family: program + operand LAYOUTS (dtype, shape, byte strides, alignment class —

@@ -685,3 +685,61 @@ def test_chain_axis_reduction_unfused_cases_agree(gpu):
     dxb, dyb = dev.DeviceArray.from_numpy(xb, bf16=True), dev.DeviceArray.from_numpy(yb, bf16=True)
     got = dev.elementwise_reduce_axis(progb, [dxb, dyb], "sum", -1).numpy()
     assert np.array_equal(got, dev.reduce("sum", dev.elementwise(progb, [dxb, dyb]), [2]).numpy())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("log", [False, True])
+@pytest.mark.parametrize("shape", [(37, 5000), (1000, 300), (4, 33, 1025), (5, 2), (64, 8192), (3, 1, 257)])
+def test_fused_chain_softmax_one_kernel(gpu, shape, log):
+    """softmax / log_softmax over the last axis of (a * 0.5 + b) * c — a broadcast column, a broadcast row, a full tensor — as ONE
+    kernel (axb_elementwise_softmax): the chain's values stay in registers between max, sum and normalisation. Same 1e-5
+    contract as the stand-alone softmax kernels, checked against the fp64 value of the exact op-by-op chain."""
+    rng = np.random.default_rng(23)
+    a = rng.standard_normal(shape[:-1] + (1,)).astype(np.float32)
+    b = rng.standard_normal((shape[-1],)).astype(np.float32)
+    c = (rng.standard_normal(shape) * 2).astype(np.float32)
+    F, V = capi.F32, capi.SRC_VALUE
+    prog = [capi.make_instr(capi.OP["mul"], F, 0, capi.SRC_IMM, imm=0.5), capi.make_instr(capi.OP["add"], F, V(0), 1),
+            capi.make_instr(capi.OP["mul"], F, V(1), 2)]
+    ins = [dev.DeviceArray.from_numpy(t) for t in (a, b, c)]
+    n0 = dev.launch_count()
+    got = dev.elementwise_softmax(prog, ins, log=log).numpy()
+    assert dev.launch_count() - n0 == 1, "chain + softmax must be one kernel"
+    chain = (((a * np.float32(0.5)).astype(np.float32) + b).astype(np.float32) * c).astype(np.float32).astype(np.float64)
+    z = chain - chain.max(axis=-1, keepdims=True)
+    ref = z - np.log(np.exp(z).sum(axis=-1, keepdims=True)) if log else np.exp(z) / np.exp(z).sum(axis=-1, keepdims=True)
+    assert got.shape == ref.shape
+    assert np.allclose(got, ref, rtol=1e-5, atol=1e-6 if log else 1e-8), (shape, log, float(np.abs(got - ref).max()))
+    if not log:  # every row is a probability vector
+        assert np.allclose(got.astype(np.float64).sum(axis=-1), 1.0, atol=1e-5)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("epi", ["sum", "mean", "max"])
+def test_fused_chain_softmax_row_epilogue_and_fallbacks(gpu, epi):
+    rng = np.random.default_rng(24)
+    x = (rng.standard_normal((300, 1024)) * 3).astype(np.float32)
+    F = capi.F32
+    ident = [capi.make_instr(capi.OP["cast"], F, 0)]
+    dx = dev.DeviceArray.from_numpy(x)
+    n0 = dev.launch_count()
+    got = dev.elementwise_softmax(ident, [dx], epilogue=epi).numpy()
+    assert dev.launch_count() - n0 == 1
+    z = x.astype(np.float64) - x.astype(np.float64).max(axis=1, keepdims=True)
+    p = np.exp(z) / np.exp(z).sum(axis=1, keepdims=True)
+    ref = {"sum": p.sum(axis=1), "mean": p.mean(axis=1), "max": p.max(axis=1)}[epi]
+    assert got.shape == (300,) and np.allclose(got, ref, rtol=1e-5, atol=1e-8)
+    # rows longer than 8192 elements: chain, softmax and reduction run back to back, same answer
+    xl = (rng.standard_normal((7, 10000))).astype(np.float32)
+    n0 = dev.launch_count()
+    gl = dev.elementwise_softmax(ident, [dev.DeviceArray.from_numpy(xl)], epilogue=epi).numpy()
+    assert dev.launch_count() - n0 >= 2
+    zl = xl.astype(np.float64) - xl.astype(np.float64).max(axis=1, keepdims=True)
+    pl = np.exp(zl) / np.exp(zl).sum(axis=1, keepdims=True)
+    assert np.allclose(gl, {"sum": pl.sum(axis=1), "mean": pl.mean(axis=1), "max": pl.max(axis=1)}[epi], rtol=1e-4, atol=1e-8)
+    # a NaN in a row poisons that row only; a -inf entry is an exact zero
+    xn = x[:4].copy()
+    xn[1, 5] = np.nan
+    xn[2, 7] = -np.inf
+    gn = dev.elementwise_softmax(ident, [dev.DeviceArray.from_numpy(xn)]).numpy()
+    assert np.all(np.isnan(gn[1])) and not np.any(np.isnan(gn[[0, 2, 3]])) and gn[2, 7] == 0.0
