@@ -177,6 +177,7 @@ def lib() -> ctypes.CDLL:
         "axb_rownorm_last_path": (i32, []),
         "axb_elementwise_reduce": (i32, [I, i32, T, i32, i32, T, vp]),
         "axb_elementwise_softmax": (i32, [I, i32, T, i32, i32, i32, T, vp]),
+        "axb_elementwise_norm": (i32, [I, i32, T, i32, i32, T, T, f32, T, vp]),
         "axb_elementwise_reduce_precompile": (i32, [I, i32, T, i32, T, i32, i32]),
         "axb_elementwise_reduce_axis": (i32, [I, i32, T, i32, i32, i32, i32, T, vp]),
         "axb_matmul": (i32, [T, T, i32, i32, ctypes.POINTER(AxbMatmulEpilogue), T, vp]),

@@ -168,8 +168,8 @@ axb_status launch_chain_rowreduce(const axb_instr *prog, int n_instr, const axb_
                                   const axb_tensor *shape_desc, int opk, bool is_mean, float *out, cudaStream_t s, DeviceCtx *ctx,
                                   bool *done);
 axb_status launch_chain_softmax(const axb_instr *prog, int n_instr, const axb_tensor *inputs, int n_inputs,
-                                const axb_tensor *shape_desc, bool is_log, int epilogue, float *out, cudaStream_t s, DeviceCtx *ctx,
-                                bool *done);
+                                const axb_tensor *shape_desc, int mode, int epilogue, float *out, cudaStream_t s, DeviceCtx *ctx,
+                                bool *done, const float *weight = nullptr, const float *bias = nullptr, float eps = 0.0f);
 }
 // half_lut.cu: table-lookup evaluation of a chain over one half-precision tensor (*done = false: not applicable)
 namespace lut {

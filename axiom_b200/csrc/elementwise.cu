@@ -905,10 +905,10 @@ std::string kernel_source(const std::string &loads, const std::string &body, boo
     else if (reduce_opk < 64) // chain + last-axis reduction: reduce_opk = 4 * mode + op, mode 1 = one CTA per row, 2 = one warp per row
         snprintf(hdr, sizeof hdr, "\nEW_ROWKERNEL_BEGIN(axb_ew_rowred, %d, %s, %d, %d, %d, %d, %d)\n", vec, wide ? "uint64_t" : "uint32_t",
                  n_outer, n_inputs, unroll, reduce_opk & 3, (reduce_opk >> 2) == 1 ? 256 : 32);
-    else { // chain + softmax over the last axis: 64 + (NV - 1) + 8 * (G == 256) + 16 * log + 32 * epilogue
+    else { // chain + softmax / norm over the last axis: 64 + (NV - 1) + 8 * (G == 256) + 16 * mode + 64 * epilogue
         const int k = reduce_opk - 64;
         snprintf(hdr, sizeof hdr, "\nEW_SMKERNEL_BEGIN(axb_ew_softmax, %d, %s, %d, %d, %d, %d, %d, %d)\n", vec, wide ? "uint64_t" : "uint32_t",
-                 n_outer, n_inputs, (k & 7) + 1, (k & 8) ? 256 : 32, (k >> 4) & 1, (k >> 5) & 3);
+                 n_outer, n_inputs, (k & 7) + 1, (k & 8) ? 256 : 32, (k >> 4) & 3, (k >> 6) & 3);
     }
     s += hdr;
     s += "        EW_PRELOAD_BEGIN\n" + loads + "        EW_PRELOAD_END\n";
@@ -1228,8 +1228,8 @@ static axb_tensor row_desc(const axb_tensor &shape_desc) {
 // Chain + softmax / log_softmax over the last axis [+ row sum / mean / max of the result] in one pass
 // (axb_elementwise_softmax): rows of at most 256 * 8 vectors; `out` holds the fp32 rows (epilogue 0) or one fp32 per row.
 axb_status launch_chain_softmax(const axb_instr *prog, int n_instr, const axb_tensor *inputs, int n_inputs,
-                                const axb_tensor *shape_desc, bool is_log, int epilogue, float *out, cudaStream_t s, DeviceCtx *ctx,
-                                bool *done) {
+                                const axb_tensor *shape_desc, int mode, int epilogue, float *out, cudaStream_t s, DeviceCtx *ctx,
+                                bool *done, const float *weight, const float *bias, float eps) {
     *done = false;
     const int nd = shape_desc->ndim;
     if (nd < 1 || shape_desc->shape[nd - 1] < 2 || dtype_size(shape_desc->dtype) != 4)
@@ -1248,11 +1248,14 @@ axb_status launch_chain_softmax(const axb_instr *prog, int n_instr, const axb_te
     Prepared P;
     bool empty = false;
     jit::Kernel k;
-    const int code = 64 + (nv - 1) + (cta ? 8 : 0) + (is_log ? 16 : 0) + 32 * epilogue;
+    const int code = 64 + (nv - 1) + (cta ? 8 : 0) + 16 * mode + 64 * epilogue;
     AXB_TRY(plan_lookup(prog, n_instr, inputs, n_inputs, &od, code, "axb_ew_softmax", ctx->device, &P, &k, &empty));
     if (empty || (int64_t)P.p.inner_len != len || (int64_t)(P.p.total_vec / P.p.nvec_inner) != rows || (int64_t)P.p.nvec_inner != nvec)
         return AXB_OK;
     P.p.reduce_ws = out;
+    P.p.aux0 = weight;
+    P.p.aux1 = bias;
+    P.p.eps = eps;
     const int64_t blocks = cta ? rows : (rows + 7) / 8;
     void *args[] = {&P.p};
     AXB_TRY(jit::launch(k, (unsigned)blocks, 256, 0, s, args));

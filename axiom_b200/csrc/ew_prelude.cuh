@@ -85,6 +85,9 @@ struct Params {
     int32_t pad0;
     int32_t reduce_op; // fused full reduction (axb_elementwise_reduce): 0 = none
     void *reduce_ws;   // per-block partials
+    const float *aux0, *aux1; // fused layer_norm / rms_norm: weight and bias rows (fp32, contiguous) or nullptr
+    float eps;
+    int32_t pad1;
 };
 
 __device__ __forceinline__ uint32_t fastdiv(uint32_t n, uint32_t m, uint32_t s) {
@@ -887,10 +890,13 @@ template <int G> __device__ __forceinline__ float group_sum(float v, float *sm) 
     }
     return v;
 }
-#define EW_SMKERNEL_BEGIN(NAME, VEC_, WTYPE, NOUT_, NIN_, NV_, G_, LOG_, EPI_)                          \
+// MODE: 0 softmax, 1 log_softmax, 2 layer_norm (mean, centre, biased variance, / sqrt(var + eps), * w + b: the reference's op
+// sequence, operations.cpp:1803-1817), 3 rms_norm (x / sqrt(mean(x^2) + eps) * w, :1841-1857); w / b = p.aux0 / p.aux1.
+#define EW_SMKERNEL_BEGIN(NAME, VEC_, WTYPE, NOUT_, NIN_, NV_, G_, MODE_, EPI_)                         \
     extern "C" __global__ void __launch_bounds__(256) NAME(const __grid_constant__ axb::ew::Params p) { \
         using namespace axb::ew;                                                                        \
-        constexpr int VEC = VEC_, NOUT = NOUT_, NIN = NIN_, NV = NV_, G = G_, LOG = LOG_, EPI = EPI_;   \
+        constexpr int VEC = VEC_, NOUT = NOUT_, NIN = NIN_, NV = NV_, G = G_, MODE = MODE_, EPI = EPI_; \
+        constexpr int LOG = MODE_ == 1;                                                                 \
         typedef WTYPE W;                                                                                \
         typedef Ctx<W, VEC, NIN> X;                                                                     \
         float keep[NV][VEC];                                                                            \
@@ -919,7 +925,7 @@ template <int G> __device__ __forceinline__ float group_sum(float v, float *sm) 
             }                                                                                           \
         }                                                                                               \
         _Pragma("unroll") for (int j = 0; j < NV; ++j) {                                                \
-            _Pragma("unroll") for (int i = 0; i < VEC; ++i) keep[j][i] = ninf;                          \
+            _Pragma("unroll") for (int i = 0; i < VEC; ++i) keep[j][i] = MODE >= 2 ? 0.0f : ninf;       \
             const uint32_t vi = tig + (uint32_t)(j * G);                                                \
             if (active && vi < p.nvec_inner) {                                                          \
                 X x;                                                                                    \
@@ -931,6 +937,45 @@ template <int G> __device__ __forceinline__ float group_sum(float v, float *sm) 
                 preload(x);                                                                             \
                 compute(x);                                                                             \
             }                                                                                           \
+        }                                                                                               \
+        float *rout = reinterpret_cast<float *>(p.reduce_ws);                                           \
+        if (MODE >= 2) { /* layer_norm / rms_norm: padded lanes hold 0 and are never stored */          \
+            const float n_ = (float)p.inner_len;                                                        \
+            float mean = 0.0f;                                                                          \
+            if (MODE == 2) {                                                                            \
+                float s1 = 0.0f;                                                                        \
+                _Pragma("unroll") for (int j = 0; j < NV; ++j)                                          \
+                    _Pragma("unroll") for (int i = 0; i < VEC; ++i) s1 = __fadd_rn(s1, keep[j][i]);     \
+                mean = __fdiv_rn(group_sum<G>(s1, red_sm), n_);                                         \
+            }                                                                                           \
+            float s2 = 0.0f;                                                                            \
+            _Pragma("unroll") for (int j = 0; j < NV; ++j) {                                            \
+                const uint32_t vi = tig + (uint32_t)(j * G);                                            \
+                const int valid = (active && vi < p.nvec_inner) ? (int)min((uint32_t)VEC, p.inner_len - vi * VEC) : 0; \
+                _Pragma("unroll") for (int i = 0; i < VEC; ++i) if (i < valid) {                        \
+                    const float c_ = __fsub_rn(keep[j][i], mean);                                       \
+                    keep[j][i] = c_;                                                                    \
+                    s2 = __fadd_rn(s2, __fmul_rn(c_, c_));                                              \
+                }                                                                                       \
+            }                                                                                           \
+            const float sd = __fsqrt_rn(__fadd_rn(__fdiv_rn(group_sum<G>(s2, red_sm), n_), p.eps));     \
+            _Pragma("unroll") for (int j = 0; j < NV; ++j) {                                            \
+                const uint32_t vi = tig + (uint32_t)(j * G);                                            \
+                if (!(active && vi < p.nvec_inner))                                                     \
+                    continue;                                                                           \
+                const uint32_t col = vi * VEC;                                                          \
+                const int valid = (int)min((uint32_t)VEC, p.inner_len - col);                           \
+                float *dst = rout + (size_t)row * p.inner_len + col;                                    \
+                _Pragma("unroll") for (int i = 0; i < VEC; ++i) if (i < valid) {                        \
+                    float y_ = __fdiv_rn(keep[j][i], sd);                                               \
+                    if (p.aux0)                                                                         \
+                        y_ = __fmul_rn(y_, p.aux0[col + i]);                                            \
+                    if (MODE == 2 && p.aux1)                                                            \
+                        y_ = __fadd_rn(y_, p.aux1[col + i]);                                            \
+                    dst[i] = y_;                                                                        \
+                }                                                                                       \
+            }                                                                                           \
+            return;                                                                                     \
         }                                                                                               \
         float m = ninf;                                                                                 \
         _Pragma("unroll") for (int j = 0; j < NV; ++j)                                                  \
@@ -947,7 +992,6 @@ template <int G> __device__ __forceinline__ float group_sum(float v, float *sm) 
         ssum = group_sum<G>(ssum, red_sm);                                                              \
         const float lg = LOG ? logf(ssum) : 0.0f;                                                       \
         float racc = EPI == 3 ? ninf : 0.0f;                                                            \
-        float *rout = reinterpret_cast<float *>(p.reduce_ws);                                           \
         _Pragma("unroll") for (int j = 0; j < NV; ++j) {                                                \
             const uint32_t vi = tig + (uint32_t)(j * G);                                                \
             if (!(active && vi < p.nvec_inner))                                                         \

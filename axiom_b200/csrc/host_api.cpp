@@ -498,7 +498,7 @@ axb_status axb_elementwise_softmax(const axb_instr *prog, int n_instr, const axb
     if (!two_pass && !wide && vdt == AXB_F32 && out->dtype == AXB_F32 && is_contiguous(*out) && !(is_log && epilogue_op)) {
         bool done = false;
         const int epi = epilogue_op == AXB_OP_SUM ? 1 : epilogue_op == AXB_OP_MEAN ? 2 : epilogue_op == AXB_OP_MAX ? 3 : 0;
-        AXB_TRY(ew::launch_chain_softmax(prog, n_instr, inputs, n_inputs, &tmp, is_log != 0, epi, reinterpret_cast<float *>(tensor_ptr(*out)), s,
+        AXB_TRY(ew::launch_chain_softmax(prog, n_instr, inputs, n_inputs, &tmp, is_log ? 1 : 0, epi, reinterpret_cast<float *>(tensor_ptr(*out)), s,
                                          ctx, &done));
         if (done)
             return AXB_OK;
@@ -531,6 +531,63 @@ axb_status axb_elementwise_softmax(const axb_instr *prog, int n_instr, const axb
     }
     if (buf2)
         axb_free(buf2, s);
+    axb_free(buf, s);
+    return st;
+}
+
+// layer_norm / rms_norm over the LAST axis of a chain's value (post-LN transformers: layer_norm(x + sublayer(x))). One kernel for
+// fp32 chains with rows of at most 8192 elements and contiguous fp32 weight / bias rows; otherwise the chain and the stand-alone
+// norm kernel run back to back.
+axb_status axb_elementwise_norm(const axb_instr *prog, int n_instr, const axb_tensor *inputs, int n_inputs, int32_t kind,
+                                const axb_tensor *weight, const axb_tensor *bias, float eps, const axb_tensor *out, axb_stream_t stream) {
+    AXB_REQUIRE(prog && n_instr > 0 && n_inputs > 0 && inputs, AXB_ERR_INVALID, "axb_elementwise_norm: bad arguments");
+    AXB_REQUIRE(kind == AXB_OP_LAYER_NORM || kind == AXB_OP_RMS_NORM, AXB_ERR_INVALID, "axb_elementwise_norm: kind is AXB_OP_LAYER_NORM or AXB_OP_RMS_NORM");
+    AXB_REQUIRE(kind == AXB_OP_LAYER_NORM || !bias, AXB_ERR_INVALID, "axb_elementwise_norm: rms_norm has no bias");
+    AXB_TRY(validate_tensor(out, "axb_elementwise_norm(out)"));
+    int64_t shape[AXB_MAX_DIMS];
+    int nd = inputs[0].ndim;
+    memcpy(shape, inputs[0].shape, sizeof(int64_t) * nd);
+    for (int k = 1; k < n_inputs; ++k) {
+        int64_t nxt[AXB_MAX_DIMS];
+        int nn = 0;
+        AXB_TRY(axb_broadcast_shape(shape, nd, inputs[k].shape, inputs[k].ndim, nxt, &nn));
+        memcpy(shape, nxt, sizeof(int64_t) * nn);
+        nd = nn;
+    }
+    AXB_REQUIRE(nd >= 1, AXB_ERR_SHAPE, "axb_elementwise_norm: rank-0 chain");
+    cudaStream_t s;
+    DeviceCtx *ctx;
+    AXB_TRY(resolve_stream(stream, &s, &ctx));
+    const int32_t vdt = prog[n_instr - 1].dtype;
+    axb_tensor tmp = make_contiguous_desc(nullptr, vdt, shape, nd);
+    AXB_REQUIRE(numel(*out) == numel(tmp) && is_contiguous(*out), AXB_ERR_SHAPE, "axb_elementwise_norm: output must be contiguous with the chain's shape");
+    if (numel(tmp) == 0)
+        return AXB_OK;
+    const int64_t n = shape[nd - 1];
+    auto row_ok = [&](const axb_tensor *t) { return !t || (t->dtype == AXB_F32 && numel(*t) == n && is_contiguous(*t)); };
+    static const bool two_pass = getenv("AXB_EW_REDUCE_TWO_PASS") != nullptr; // A/B switch
+    bool wide = false;
+    for (int k = 0; k < n_inputs; ++k)
+        wide = wide || is_64bit_dtype(inputs[k].dtype);
+    for (int i = 0; i < n_instr; ++i)
+        wide = wide || is_64bit_dtype(prog[i].dtype);
+    if (!two_pass && !wide && vdt == AXB_F32 && out->dtype == AXB_F32 && row_ok(weight) && row_ok(bias)) {
+        bool done = false;
+        AXB_TRY(ew::launch_chain_softmax(prog, n_instr, inputs, n_inputs, &tmp, kind == AXB_OP_LAYER_NORM ? 2 : 3, 0,
+                                         reinterpret_cast<float *>(tensor_ptr(*out)), s, ctx, &done,
+                                         weight ? reinterpret_cast<const float *>(tensor_ptr(*weight)) : nullptr,
+                                         bias ? reinterpret_cast<const float *>(tensor_ptr(*bias)) : nullptr, eps));
+        if (done)
+            return AXB_OK;
+    }
+    void *buf = nullptr;
+    AXB_TRY(axb_alloc((size_t)numel(tmp) * dtype_size(vdt), s, &buf));
+    tmp.base = buf;
+    axb_status st = axb_elementwise(prog, n_instr, inputs, n_inputs, &tmp, s);
+    if (st == AXB_OK) {
+        const axb_tensor shaped = make_contiguous_desc(tensor_ptr(*out), out->dtype, shape, nd);
+        st = kind == AXB_OP_LAYER_NORM ? axb_layer_norm(&tmp, weight, bias, nd - 1, eps, &shaped, s) : axb_rms_norm(&tmp, weight, nd - 1, eps, &shaped, s);
+    }
     axb_free(buf, s);
     return st;
 }

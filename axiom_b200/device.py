@@ -427,3 +427,14 @@ def elementwise_softmax(prog: List[capi.AxbInstr], inputs: Sequence[DeviceArray]
     check(lib().axb_elementwise_softmax(P, len(prog), I, len(inputs), int(log), capi.OP[epilogue] if epilogue else 0,
                                         ctypes.byref(out.desc()), None))
     return out
+
+
+def elementwise_norm(prog: List[capi.AxbInstr], inputs: Sequence[DeviceArray], kind: str, weight: Optional[DeviceArray] = None,
+                     bias: Optional[DeviceArray] = None, eps: float = 1e-5) -> DeviceArray:
+    """layer_norm / rms_norm over the last axis of the chain's value (axb_elementwise_norm)."""
+    P = (capi.AxbInstr * len(prog))(*prog)
+    I = (capi.AxbTensor * len(inputs))(*[t.desc() for t in inputs])
+    out = DeviceArray.empty(tuple(_bshape(*[x.shape for x in inputs])), prog[-1].dtype)
+    check(lib().axb_elementwise_norm(P, len(prog), I, len(inputs), capi.OP[kind], ctypes.byref(weight.desc()) if weight else None,
+                                     ctypes.byref(bias.desc()) if bias else None, eps, ctypes.byref(out.desc()), None))
+    return out

@@ -121,5 +121,6 @@ namespace graph {
 Tensor fused_where(const Tensor &cond, const Tensor &a, const Tensor &b);
 // cuda_graph.cpp: eager softmax / log_softmax of a lazy operand, its elementwise tree as the kernel's prologue (empty: n/a)
 Tensor fused_softmax(const Tensor &input, int axis, bool is_log);
+Tensor fused_rms_norm(const Tensor &input, const Tensor &weight, int axis, float eps);
 } // namespace graph
 } // namespace axiom

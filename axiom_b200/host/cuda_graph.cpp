@@ -229,6 +229,46 @@ struct Lowering {
         return true;
     }
 
+    // layer_norm / rms_norm over the last axis of a float32 node whose elementwise producers become the kernel's prologue
+    // (post-LN: layer_norm(x + sublayer(x))). weight / bias: float32 rows or empty tensors.
+    bool fused_norm_core(const GraphNode *c, bool layer, int ax, const Tensor &weight, const Tensor &bias, float eps, Tensor *result) {
+        const int nd = (int)c->output_shape.size();
+        if (nd < 1 || c->output_dtype != DType::Float32 || !(ax == nd - 1 || ax == -1) || c->output_shape.back() < 2 ||
+            c->output_shape.back() > 8192 || ShapeUtils::size(c->output_shape) == 0)
+            return false;
+        if (is_leaf(c) || value.count(c) || !is_fusable(c))
+            return false; // nothing to fuse in front: the stand-alone kernels
+        const size_t n = c->output_shape.back();
+        auto row = [&](const Tensor &t, Tensor *g) {
+            if (!t.storage() || t.size() == 0)
+                return true;
+            if (t.dtype() != DType::Float32 || t.size() != n)
+                return false;
+            *g = backends::cuda::gpu_contiguous(on_gpu(t));
+            return true;
+        };
+        Tensor w, b;
+        if (!row(weight, &w) || !row(bias, &b))
+            return false;
+        Program pg = build_program(c);
+        Tensor r = empty_gpu(c->output_shape, DType::Float32);
+        std::vector<axb_tensor> ins(pg.inputs.size());
+        for (size_t i = 0; i < pg.inputs.size(); ++i)
+            ins[i] = describe(get(pg.inputs[i]));
+        const axb_tensor od = describe(r);
+        axb_tensor wd{}, bd{};
+        if (w.storage())
+            wd = describe(w);
+        if (b.storage())
+            bd = describe(b);
+        check(plan::elementwise_norm(pg.instrs.data(), (int)pg.instrs.size(), ins.data(), (int)ins.size(),
+                                     layer ? AXB_OP_LAYER_NORM : AXB_OP_RMS_NORM, w.storage() ? &wd : nullptr, b.storage() ? &bd : nullptr, eps,
+                                     &od),
+              "axb_elementwise_norm");
+        *result = std::move(r);
+        return true;
+    }
+
     void run_program(const Program &pg, const axb_tensor &out, int32_t reduce_op /* <0: none */) {
         std::vector<axb_tensor> ins(pg.inputs.size());
         for (size_t i = 0; i < pg.inputs.size(); ++i)
@@ -279,7 +319,11 @@ struct Lowering {
                 r = backends::cuda::gpu_softmax(input(n, 0), get_params<ActivationParams>(n->params).axis, op == OpType::LogSoftmax);
         } else if (op == OpType::LayerNorm) {
             const auto &np = get_params<NormParams>(n->params);
-            r = backends::metal::gpu_layer_norm(input(n, 0), input(n, 1), input(n, 2), np.axis, np.eps);
+            const GraphNode *c0 = n->inputs.at(0).get();
+            const Tensor w0 = n->inputs.size() > 1 && n->inputs[1] ? input(n, 1) : Tensor(),
+                         b0 = n->inputs.size() > 2 && n->inputs[2] ? input(n, 2) : Tensor();
+            if (!(n->output_dtype == DType::Float32 && c0 && c0->ref_count <= 1 && fused_norm_core(c0, true, np.axis, w0, b0, np.eps, &r)))
+                r = backends::metal::gpu_layer_norm(input(n, 0), w0, b0, np.axis, np.eps);
         } else if (op == OpType::Conv1D) {
             const auto &cp = get_params<ConvParams>(n->params);
             r = backends::cuda::gpu_conv1d_impl(input(n, 0), input(n, 1), input(n, 2), cp.stride.at(0), cp.padding.at(0),
@@ -554,6 +598,22 @@ Tensor fused_softmax(const Tensor &input, int axis, bool is_log) {
     Lowering L;
     Tensor r;
     if (!L.fused_softmax_core(ln.get(), axis, is_log, OpType::_Count, ln->output_shape, &r))
+        return Tensor();
+    return r;
+}
+
+// rms_norm arrives eagerly through the gpu_rms_norm seam (operations.cpp:1834) with a possibly lazy operand
+Tensor fused_rms_norm(const Tensor &input, const Tensor &weight, int axis, float eps) {
+    auto ln = input.lazy_node();
+    if (!ln || ln->is_materialized_ || ln->output_dtype != DType::Float32)
+        return Tensor();
+    backends::cuda::ensure_initialized();
+    materialize_shared_below(ln.get());
+    if (ln->ref_count > 1 || !is_fusable(ln.get()))
+        return Tensor();
+    Lowering L;
+    Tensor r;
+    if (!L.fused_norm_core(ln.get(), false, axis, weight, Tensor(), eps, &r))
         return Tensor();
     return r;
 }

@@ -547,6 +547,11 @@ Tensor gpu_layer_norm(const Tensor &input, const Tensor &weight, const Tensor &b
 }
 
 Tensor gpu_rms_norm(const Tensor &input, const Tensor &weight, int axis, float eps) {
+    if (input.is_lazy() && input.device() == Device::GPU) { // elementwise producers of the operand as the kernel's prologue
+        Tensor r = graph::fused_rms_norm(input, weight, axis, eps);
+        if (r.storage())
+            return r;
+    }
     const Tensor x = on_gpu(input);
     Tensor out = empty_gpu(x.shape(), x.dtype());
     if (out.size() == 0)

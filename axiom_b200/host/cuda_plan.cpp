@@ -20,7 +20,7 @@ using graph::GraphNode;
 
 enum Fn : int32_t {
     F_ELEMENTWISE, F_ELEMENTWISE_REDUCE, F_MATMUL, F_SOFTMAX, F_LAYER_NORM, F_RMS_NORM, F_REDUCE, F_ARGREDUCE, F_CAST,
-    F_GATHER_STRIDED, F_IM2COL, F_BINARY, F_UNARY, F_WHERE, F_MASKED_FILL, F_PAD, F_CONV2D, F_FILL, F_POOL, F_SORT, F_ELEMENTWISE_REDUCE_AXIS, F_ELEMENTWISE_SOFTMAX
+    F_GATHER_STRIDED, F_IM2COL, F_BINARY, F_UNARY, F_WHERE, F_MASKED_FILL, F_PAD, F_CONV2D, F_FILL, F_POOL, F_SORT, F_ELEMENTWISE_REDUCE_AXIS, F_ELEMENTWISE_SOFTMAX, F_ELEMENTWISE_NORM
 };
 enum Kind : int8_t { K_NONE = 0, K_LEAF = 1, K_TEMP = 2 };
 
@@ -205,6 +205,11 @@ axb_status invoke(const Call &c, axb_tensor *T) {
     case F_ELEMENTWISE_SOFTMAX: {
         const int n_in = (int)c.iv[0];
         return axb_elementwise_softmax(c.prog.data(), (int)c.prog.size(), T, n_in, (int)c.iv[1], (int32_t)c.iv[2], &T[n_in], nullptr);
+    }
+    case F_ELEMENTWISE_NORM: { // T: inputs..., out, weight, bias
+        const int n_in = (int)c.iv[0];
+        return axb_elementwise_norm(c.prog.data(), (int)c.prog.size(), T, n_in, (int32_t)c.iv[1], tp(n_in + 1), tp(n_in + 2), (float)c.dv[0],
+                                    &T[n_in], nullptr);
     }
     case F_MATMUL: {
         axb_matmul_epilogue e{};
@@ -551,6 +556,25 @@ axb_status elementwise_softmax(const axb_instr *prog, int n_instr, const axb_ten
     for (int i = 0; i < n_inputs; ++i)
         c->t[i] = resolve(&inputs[i]);
     c->t[n_inputs] = resolve(out);
+    return st_;
+}
+axb_status elementwise_norm(const axb_instr *prog, int n_instr, const axb_tensor *inputs, int n_inputs, int32_t kind, const axb_tensor *w,
+                            const axb_tensor *b, float eps, const axb_tensor *out) {
+    AXB_PLAN_CALL(axb_elementwise_norm(prog, n_instr, inputs, n_inputs, kind, w, b, eps, out, nullptr))
+    if (n_inputs + 3 > kMaxT) { // cannot be expressed in one recorded call: this signature keeps the normal path
+        note_foreign("elementwise_norm with more operands than a recorded call holds");
+        return st_;
+    }
+    Call *c = sc.open(F_ELEMENTWISE_NORM);
+    c->prog.assign(prog, prog + n_instr);
+    c->iv[0] = n_inputs;
+    c->iv[1] = kind;
+    c->dv[0] = eps;
+    for (int i = 0; i < n_inputs; ++i)
+        c->t[i] = resolve(&inputs[i]);
+    c->t[n_inputs] = resolve(out);
+    c->t[n_inputs + 1] = resolve(w);
+    c->t[n_inputs + 2] = resolve(b);
     return st_;
 }
 axb_status matmul(const axb_tensor *a, const axb_tensor *b, int ta, int tb, const axb_matmul_epilogue *epi, const axb_tensor *out) {

@@ -60,6 +60,8 @@ axb_status elementwise_reduce_axis(const axb_instr *prog, int n_instr, const axb
                                    int axis, int keep_dims, const axb_tensor *out);
 axb_status elementwise_softmax(const axb_instr *prog, int n_instr, const axb_tensor *inputs, int n_inputs, int is_log, int32_t epilogue_op,
                                const axb_tensor *out);
+axb_status elementwise_norm(const axb_instr *prog, int n_instr, const axb_tensor *inputs, int n_inputs, int32_t kind, const axb_tensor *w,
+                            const axb_tensor *b, float eps, const axb_tensor *out);
 axb_status matmul(const axb_tensor *a, const axb_tensor *b, int ta, int tb, const axb_matmul_epilogue *epi, const axb_tensor *out);
 axb_status softmax(const axb_tensor *in, int axis, int is_log, const axb_tensor *out);
 axb_status layer_norm(const axb_tensor *in, const axb_tensor *w, const axb_tensor *b, int axis, float eps, const axb_tensor *out);

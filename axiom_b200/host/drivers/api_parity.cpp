@@ -115,6 +115,14 @@ int main() {
         fused("chain_softmax", p, [&](const Tensor &t) { return (t * 0.5f + Q(t)).softmax(-1); }, false);
         fused("chain_log_softmax", sm, [&](const Tensor &t) { return (t * t - 1.0f).log_softmax(-1); }, false);
         fused("softmax_then_row_max", sm, [&](const Tensor &t) { return (t * 2.0f).softmax(-1).max(1); }, false);
+        // layer_norm / rms_norm with an elementwise prologue (post-LN: layer_norm(x + sublayer(x)))
+        Tensor lw = Tensor::randn({1500}) * 0.1f + 1.0f, lb = Tensor::randn({1500}) * 0.1f;
+        lw.sync(); lb.sync();
+        Tensor lwg = lw.gpu(), lbg = lb.gpu();
+        auto W = [&](const Tensor &t) { return t.device() == Device::GPU ? lwg : lw; };
+        auto Bv = [&](const Tensor &t) { return t.device() == Device::GPU ? lbg : lb; };
+        fused("chain_layer_norm", p, [&](const Tensor &t) { return ops::layer_norm(t + Q(t), W(t), Bv(t), -1, 1e-5f); }, false);
+        fused("chain_rms_norm", p, [&](const Tensor &t) { return ops::rms_norm(t * 0.5f + 1.0f, W(t), -1, 1e-6f); }, false);
     }
     // scalar-operand forms of where (the patched Tensor::where(cond, scalar) overloads, tensor.cpp:1340-1355)
     Tensor y = Tensor::randn({5, 1, 33}), c = Tensor::randn({5, 7, 33});

@@ -212,6 +212,13 @@ axb_status axb_elementwise_precompile(const axb_instr *prog, int n_instr, const 
  * max, sum and normalisation); otherwise chain, axb_softmax and axb_reduce run back to back. `out` contiguous. */
 axb_status axb_elementwise_softmax(const axb_instr *prog, int n_instr, const axb_tensor *inputs, int n_inputs, int is_log,
                                    int32_t epilogue_op, const axb_tensor *out, axb_stream_t stream);
+/* layer_norm (kind AXB_OP_LAYER_NORM) / rms_norm (AXB_OP_RMS_NORM) over the LAST axis of the chain's value with optional fp32
+ * weight / bias rows — `layer_norm(x + sublayer(x))` of a post-LN transformer in ONE kernel (fp32 chains, rows of at most
+ * 8192 elements; the reference's op sequence, operations.cpp:1803-1817, :1841-1857); otherwise the chain and the stand-alone
+ * kernel run back to back. `out` contiguous with the chain's shape. */
+axb_status axb_elementwise_norm(const axb_instr *prog, int n_instr, const axb_tensor *inputs, int n_inputs, int32_t kind,
+                                const axb_tensor *weight /* may be NULL */, const axb_tensor *bias /* may be NULL */, float eps,
+                                const axb_tensor *out, axb_stream_t stream);
 axb_status axb_elementwise_reduce_precompile(const axb_instr *prog, int n_instr, const axb_tensor *inputs, int n_inputs,
                                              const axb_tensor *shape_desc, int32_t reduce_op, int reduce_kind);
 /* Launch-plan cache of the fused-chain family: program + operand LAYOUTS (dtype, shape, byte strides, alignment class —

@@ -743,3 +743,46 @@ def test_fused_chain_softmax_row_epilogue_and_fallbacks(gpu, epi):
     xn[2, 7] = -np.inf
     gn = dev.elementwise_softmax(ident, [dev.DeviceArray.from_numpy(xn)]).numpy()
     assert np.all(np.isnan(gn[1])) and not np.any(np.isnan(gn[[0, 2, 3]])) and gn[2, 7] == 0.0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", ["layer_norm", "rms_norm"])
+@pytest.mark.parametrize("shape", [(37, 5000), (1000, 300), (4, 33, 1025), (5, 2), (64, 8192)])
+def test_fused_chain_norm_one_kernel(gpu, shape, kind):
+    """layer_norm / rms_norm over the last axis of x + y (the post-LN pattern layer_norm(x + sublayer(x))) as ONE kernel
+    (axb_elementwise_norm), with and without the affine rows; 1e-5 against the fp64 value of the reference's op sequence
+    (operations.cpp:1803-1817, :1841-1857) applied to the exact fp32 sum."""
+    rng = np.random.default_rng(29)
+    x = (rng.standard_normal(shape) * 2 + 0.3).astype(np.float32)
+    y = rng.standard_normal(shape[-1:]).astype(np.float32)
+    w = (1 + 0.1 * rng.standard_normal(shape[-1])).astype(np.float32)
+    b = (0.1 * rng.standard_normal(shape[-1])).astype(np.float32)
+    F = capi.F32
+    prog = [capi.make_instr(capi.OP["add"], F, 0, 1)]
+    ins = [dev.DeviceArray.from_numpy(x), dev.DeviceArray.from_numpy(y)]
+    v = (x + y).astype(np.float32).astype(np.float64)
+    for affine in (True, False):
+        dw = dev.DeviceArray.from_numpy(w) if affine else None
+        db = dev.DeviceArray.from_numpy(b) if affine and kind == "layer_norm" else None
+        n0 = dev.launch_count()
+        got = dev.elementwise_norm(prog, ins, kind, dw, db, 1e-5).numpy()
+        assert dev.launch_count() - n0 == 1, "chain + norm must be one kernel"
+        if kind == "layer_norm":
+            c = v - v.mean(axis=-1, keepdims=True)
+            ref = c / np.sqrt((c * c).mean(axis=-1, keepdims=True) + 1e-5)
+        else:
+            ref = v / np.sqrt((v * v).mean(axis=-1, keepdims=True) + 1e-5)
+        if affine:
+            ref = ref * w
+            if kind == "layer_norm":
+                ref = ref + b
+        assert np.allclose(got, ref, rtol=1e-5, atol=2e-5), (shape, kind, affine, float(np.abs(got - ref).max()))
+    # rows longer than 8192 elements: chain + stand-alone kernel, same contract
+    xl = rng.standard_normal((3, 9000)).astype(np.float32)
+    yl = rng.standard_normal((9000,)).astype(np.float32)
+    n0 = dev.launch_count()
+    gl = dev.elementwise_norm(prog, [dev.DeviceArray.from_numpy(xl), dev.DeviceArray.from_numpy(yl)], kind, None, None, 1e-5).numpy()
+    assert dev.launch_count() - n0 >= 2
+    vl = (xl + yl).astype(np.float64)
+    cl = vl - vl.mean(axis=-1, keepdims=True) if kind == "layer_norm" else vl
+    assert np.allclose(gl, cl / np.sqrt((cl * cl).mean(axis=-1, keepdims=True) + 1e-5), rtol=1e-5, atol=2e-5)
