@@ -482,6 +482,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                         k0 = split_piece_a(c) * (int)p.Kp + kk;
                         k0b = split_piece_b(c) * (int)p.Kp + kk;
                     }
+                    if (!A_MN && B_MN && p.conv_taps) {
+                        // implicit-GEMM convolution straight from the NCHW tensor (half precision, stride 1): B is MN-major —
+                        // a box of 64 columns x 64 channels of input row oh + q_h is exactly one 64-wide N chunk
+                        const int tap = kb / p.conv_cblocks, c0 = (kb - tap * p.conv_cblocks) * BK;
+                        const int img = (int)(b / p.conv_oh), oh = (int)(b - (int64_t)img * p.conv_oh) * p.conv_rows;
+                        tma_load_3d(sa, &tma_a, full_bar(stage), c0, m0, tap);
+#pragma unroll
+                        for (int j = 0; j < BN_ / 64; ++j) {
+                            if (p.conv_rows == 1)
+                                tma_load_4d(sb + j * (64 * BK * 2), &tma_b, full_bar(stage), n0 + 64 * j + p.conv_qw[tap], oh + p.conv_qh[tap], c0, img);
+                            else
+                                tma_load_4d(sb + j * (64 * BK * 2), &tma_b, full_bar(stage), p.conv_qw[tap], oh + j + p.conv_qh[tap], c0, img);
+                        }
+                        if (++stage == STAGES) {
+                            stage = 0;
+                            phase ^= 1u;
+                        }
+                        continue;
+                    }
                     if (!A_MN && !B_MN && p.conv_taps) { // implicit-GEMM convolution, half-precision operands
                         const int tap = kb / p.conv_cblocks, c0 = (kb - tap * p.conv_cblocks) * BK;
                         const int img = (int)(b / p.conv_oh), oh = (int)(b - (int64_t)img * p.conv_oh) * p.conv_rows;
@@ -1329,9 +1348,12 @@ struct ConvPrepX {
     int32_t sh, sw, pieces, src_f32;
     int32_t wtiles;
 };
-// block (32, 8): a 32 (channels) x 32 (w') tile is read along w' and written along channels
-__global__ void __launch_bounds__(256) conv_prep_x_kernel(const __grid_constant__ ConvPrepX q) {
-    __shared__ float tile[32][33];
+// block (32, 8). A tile of 64 channels x TW columns (TW = 64 for 2-byte inputs, 32 for fp32) is read along w' — a warp reads
+// 128 contiguous bytes of one channel row — turned in shared memory and written along channels, 128 bytes per warp and piece
+// (the first version moved 32 x 32 tiles with 64-byte rows and ran at 1.1 TB/s: 35 % of a 256-channel 3x3 convolution).
+template <bool F32> __global__ void __launch_bounds__(256) conv_prep_x_kernel(const __grid_constant__ ConvPrepX q) {
+    constexpr int TW = F32 ? 32 : 64;
+    __shared__ uint32_t tile[TW][F32 ? 65 : 33]; // fp32: [w'][c] words; half: [w'][c pair] words (two channels per word)
     const int tx = threadIdx.x, ty = threadIdx.y;
     const int wt = blockIdx.x % q.wtiles, ct = blockIdx.x / q.wtiles;
     const int64_t hq = blockIdx.y, plane = blockIdx.z;
@@ -1339,33 +1361,62 @@ __global__ void __launch_bounds__(256) conv_prep_x_kernel(const __grid_constant_
     const int64_t n = plane / phases;
     const int ph = (int)(plane - n * phases), rh = ph / q.sw, rw = ph - rh * q.sw;
     const int64_t ih = hq * q.sh + rh;
-    const int64_t c0 = (int64_t)ct * 32, w0 = (int64_t)wt * 32;
+    const int64_t c0 = (int64_t)ct * 64, w0 = (int64_t)wt * TW;
+    const bool row_ok = ih < q.H;
+    if (F32) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) { // c = c0 + ty + 8 i, w' = w0 + tx
-        const int64_t c = c0 + ty + 8 * i, wq = w0 + tx, iw = wq * q.sw + rw;
-        float v = 0.0f;
-        if (c < q.C && ih < q.H && wq < q.Wq && iw < q.W) {
-            const char *sp = q.x + n * q.xs[0] + c * q.xs[1] + ih * q.xs[2] + iw * q.xs[3];
-            v = q.src_f32 ? *reinterpret_cast<const float *>(sp) : __uint_as_float((uint32_t) * reinterpret_cast<const uint16_t *>(sp));
+        for (int i = 0; i < 8; ++i) { // c = c0 + ty + 8 i, w' = w0 + tx
+            const int64_t c = c0 + ty + 8 * i, wq = w0 + tx, iw = wq * q.sw + rw;
+            float v = 0.0f;
+            if (row_ok && c < q.C && wq < q.Wq && iw < q.W)
+                v = *reinterpret_cast<const float *>(q.x + n * q.xs[0] + c * q.xs[1] + ih * q.xs[2] + iw * q.xs[3]);
+            tile[tx][ty + 8 * i] = __float_as_uint(v);
         }
-        tile[ty + 8 * i][tx] = v;
-    }
-    __syncthreads();
+        __syncthreads();
 #pragma unroll
-    for (int i = 0; i < 4; ++i) { // w' = w0 + ty + 8 i, c = c0 + tx
-        const int64_t wq = w0 + ty + 8 * i, c = c0 + tx;
-        if (wq >= q.Wq || c >= q.Cp)
-            continue;
-        const float v = tile[tx][ty + 8 * i];
-        uint16_t *row = q.dst + (((plane * q.Hq + hq) * q.Wq + wq) * q.pieces) * q.Cp + c;
-        if (q.src_f32) {
-            uint16_t h, m, l;
-            split3(v, h, m, l);
-            row[0] = h;
-            row[q.Cp] = m;
-            row[2 * q.Cp] = l;
-        } else {
-            row[0] = (uint16_t)__float_as_uint(v); // the 16 raw bits travelled in the low half
+        for (int i = 0; i < 4; ++i) { // w' = w0 + ty + 8 i, channels c0 + 2 tx, + 1
+            const int64_t wq = w0 + ty + 8 * i, c = c0 + 2 * tx;
+            if (wq >= q.Wq || c >= q.Cp)
+                continue;
+            uint16_t h0, m0, l0, h1, m1, l1;
+            split3(__uint_as_float(tile[ty + 8 * i][2 * tx]), h0, m0, l0);
+            split3(__uint_as_float(tile[ty + 8 * i][2 * tx + 1]), h1, m1, l1);
+            uint16_t *row = q.dst + (((plane * q.Hq + hq) * q.Wq + wq) * 3) * q.Cp + c; // c even, Cp % 64 == 0: 4-byte aligned
+            *reinterpret_cast<uint32_t *>(row) = (uint32_t)h0 | ((uint32_t)h1 << 16);
+            *reinterpret_cast<uint32_t *>(row + q.Cp) = (uint32_t)m0 | ((uint32_t)m1 << 16);
+            *reinterpret_cast<uint32_t *>(row + 2 * q.Cp) = (uint32_t)l0 | ((uint32_t)l1 << 16);
+        }
+    } else {
+        uint16_t *t16 = reinterpret_cast<uint16_t *>(&tile[0][0]); // element (w', c) at t16[w' * 66 + c]
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { // c = c0 + ty + 8 i, w' = w0 + 2 tx, + 1
+            const int64_t c = c0 + ty + 8 * i, wq = w0 + 2 * tx;
+            uint16_t v0 = 0, v1 = 0;
+            if (row_ok && c < q.C) {
+                const char *rp = q.x + n * q.xs[0] + c * q.xs[1] + ih * q.xs[2];
+                const int64_t iw0 = wq * q.sw + rw, iw1 = iw0 + q.sw;
+                if (q.sw == 1 && q.xs[3] == 2 && iw1 < q.W && wq + 1 < q.Wq && ((reinterpret_cast<uintptr_t>(rp) + iw0 * 2) & 3) == 0) {
+                    const uint32_t two = *reinterpret_cast<const uint32_t *>(rp + iw0 * 2);
+                    v0 = (uint16_t)two;
+                    v1 = (uint16_t)(two >> 16);
+                } else {
+                    if (wq < q.Wq && iw0 < q.W)
+                        v0 = *reinterpret_cast<const uint16_t *>(rp + iw0 * q.xs[3]);
+                    if (wq + 1 < q.Wq && iw1 < q.W)
+                        v1 = *reinterpret_cast<const uint16_t *>(rp + iw1 * q.xs[3]);
+                }
+            }
+            t16[(2 * tx) * 66 + ty + 8 * i] = v0;
+            t16[(2 * tx + 1) * 66 + ty + 8 * i] = v1;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { // w' = w0 + ty + 8 i, channels c0 + 2 tx, + 1
+            const int64_t wq = w0 + ty + 8 * i, c = c0 + 2 * tx;
+            if (wq >= q.Wq || c >= q.Cp)
+                continue;
+            const uint32_t two = *reinterpret_cast<const uint32_t *>(&t16[(ty + 8 * i) * 66 + 2 * tx]);
+            *reinterpret_cast<uint32_t *>(q.dst + ((plane * q.Hq + hq) * q.Wq + wq) * q.Cp + c) = two;
         }
     }
 }
@@ -1377,29 +1428,45 @@ struct ConvPrepW {
     int32_t pieces, src_f32;
     int64_t total; // taps * Cout * Cp
 };
+// grid (Cp / 64, C_out), block 256: the 64 channels x taps block of one output channel is read in memory order (channel-
+// major, taps contiguous for a contiguous weight), staged in shared memory and written tap by tap, 64 channels (128 bytes)
+// per row and piece
 __global__ void __launch_bounds__(256) conv_prep_w_kernel(const __grid_constant__ ConvPrepW q) {
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < q.total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t c = i % q.Cp, t1 = i / q.Cp, co = t1 % q.Cout, tap = t1 / q.Cout;
-        const int64_t kh = tap / q.KW, kw = tap - kh * q.KW;
-        uint16_t *row = q.dst + ((tap * q.Cout + co) * q.pieces) * q.Cp + c;
+    __shared__ uint32_t stage[64 * 64]; // [c local][tap], raw bits (fp32 word or 16-bit value)
+    const int64_t c0 = (int64_t)blockIdx.x * 64, co = blockIdx.y;
+    const int taps = (int)(q.KH * q.KW);
+    for (int e = threadIdx.x; e < 64 * taps; e += 256) {
+        const int cl = e / taps, tap = e - cl * taps;
+        const int64_t c = c0 + cl, kh = tap / q.KW, kw = tap - kh * q.KW;
+        uint32_t v = 0;
+        if (c < q.Cin) {
+            const char *sp = q.w + co * q.ws[0] + c * q.ws[1] + kh * q.ws[2] + kw * q.ws[3];
+            v = q.src_f32 ? *reinterpret_cast<const uint32_t *>(sp) : (uint32_t) * reinterpret_cast<const uint16_t *>(sp);
+        }
+        stage[cl * taps + tap] = v;
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < 64 * taps; e += 256) {
+        const int tap = e / 64, cl = e - tap * 64;
+        const uint32_t v = stage[cl * taps + tap];
+        uint16_t *row = q.dst + ((tap * q.Cout + co) * q.pieces) * q.Cp + c0 + cl;
         if (q.src_f32) {
-            const float v = c < q.Cin ? *reinterpret_cast<const float *>(q.w + co * q.ws[0] + c * q.ws[1] + kh * q.ws[2] + kw * q.ws[3]) : 0.0f;
             uint16_t h, m, l;
-            split3(v, h, m, l);
+            split3(__uint_as_float(v), h, m, l);
             row[0] = h;
             row[q.Cp] = m;
             row[2 * q.Cp] = l;
         } else {
-            row[0] = c < q.Cin ? *reinterpret_cast<const uint16_t *>(q.w + co * q.ws[0] + c * q.ws[1] + kh * q.ws[2] + kw * q.ws[3]) : (uint16_t)0;
+            row[0] = (uint16_t)v;
         }
     }
 }
 
 axb_status make_map4(CUtensorMap *map, const drv::Api *api, int dtype, const void *base, const uint64_t dims[4], const uint64_t strides[3],
-                     uint32_t b0, uint32_t b1) {
+                     uint32_t b0, uint32_t b1, uint32_t b2 = 1) {
     cuuint64_t gdim[4] = {dims[0], dims[1], dims[2], dims[3]};
     cuuint64_t gstr[3] = {strides[0], strides[1], strides[2]};
-    cuuint32_t box[4] = {b0, b1, 1, 1};
+    cuuint32_t box[4] = {b0, b1, b2, 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = api->TensorMapEncodeTiled(map, dtype == AXB_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4,
                                            const_cast<void *>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -1450,7 +1517,17 @@ axb_status conv_tc(const ConvDesc &d, DeviceCtx *ctx, cudaStream_t s, bool *done
             qw[t] = (int16_t)q_w;
             phs[t] = (int16_t)(r_h * d.sw + r_w);
         }
-    const size_t x_bytes = (size_t)planes * Hq * Wq * pieces * Cp * 2, w_bytes = (size_t)taps * d.Cout * pieces * Cp * 2;
+    // half precision, stride 1, filters ONE column wide without horizontal padding (1x1 / KHx1 convolutions), a tensor TMA can
+    // describe as it is (unit-stride columns, 16-byte aligned rows / planes / base): the input is read in place as an MN-major
+    // operand — no preparation pass over it at all. Wider filters cannot take this route: a tap would shift the box by single
+    // elements along the INNERMOST dimension, and TMA faults on box starts there that are not 16-byte aligned (measured with
+    // tools/tma_probe.cu: box {64,1,64,1} at w = -1 -> illegal instruction; shifts in the outer dimensions are fine)
+    static const bool no_direct = getenv("AXB_CONV_NO_DIRECT") != nullptr; // A/B switch
+    const bool direct = !no_direct && !f32 && d.sh == 1 && d.sw == 1 && d.KW == 1 && d.pw == 0 && d.x_s[3] == 2 && d.x_s[1] > 0 &&
+                        d.x_s[1] % 16 == 0 &&
+                        (d.N == 1 || (d.x_s[0] > 0 && d.x_s[0] % 16 == 0)) && (d.H == 1 || (d.x_s[2] >= d.W * 2 && d.x_s[2] % 16 == 0)) &&
+                        (reinterpret_cast<uintptr_t>(d.x) & 15) == 0;
+    const size_t x_bytes = direct ? 256 : (size_t)planes * Hq * Wq * pieces * Cp * 2, w_bytes = (size_t)taps * d.Cout * pieces * Cp * 2;
     void *xq = nullptr, *wq = nullptr;
     AXB_TRY(axb_alloc(x_bytes, s, &xq));
     axb_status st = axb_alloc(w_bytes, s, &wq);
@@ -1461,16 +1538,22 @@ axb_status conv_tc(const ConvDesc &d, DeviceCtx *ctx, cudaStream_t s, bool *done
     auto body = [&]() -> axb_status {
         ConvPrepX px;
         memset(&px, 0, sizeof px);
+        if (!direct) {
         px.x = d.x; px.dst = static_cast<uint16_t *>(xq);
         for (int i = 0; i < 4; ++i)
             px.xs[i] = d.x_s[i];
         px.C = d.Cin; px.H = d.H; px.W = d.W; px.Cp = Cp; px.Hq = Hq; px.Wq = Wq;
         px.sh = d.sh; px.sw = d.sw; px.pieces = pieces; px.src_f32 = f32 ? 1 : 0;
-        px.wtiles = (int)((Wq + 31) / 32);
-        const int64_t gx = (int64_t)px.wtiles * (Cp / 32);
+        const int tw = f32 ? 32 : 64;
+        px.wtiles = (int)((Wq + tw - 1) / tw);
+        const int64_t gx = (int64_t)px.wtiles * (Cp / 64);
         AXB_REQUIRE(gx < (1ll << 31), AXB_ERR_UNSUPPORTED, "conv: input too wide for the preparation pass");
-        conv_prep_x_kernel<<<dim3((unsigned)gx, (unsigned)Hq, (unsigned)planes), dim3(32, 8), 0, s>>>(px);
+        if (f32)
+            conv_prep_x_kernel<true><<<dim3((unsigned)gx, (unsigned)Hq, (unsigned)planes), dim3(32, 8), 0, s>>>(px);
+        else
+            conv_prep_x_kernel<false><<<dim3((unsigned)gx, (unsigned)Hq, (unsigned)planes), dim3(32, 8), 0, s>>>(px);
         AXB_CHECK_LAUNCH();
+        }
         ConvPrepW pw;
         memset(&pw, 0, sizeof pw);
         pw.w = d.w; pw.dst = static_cast<uint16_t *>(wq);
@@ -1478,7 +1561,8 @@ axb_status conv_tc(const ConvDesc &d, DeviceCtx *ctx, cudaStream_t s, bool *done
             pw.ws[i] = d.w_s[i];
         pw.Cout = d.Cout; pw.Cin = d.Cin; pw.Cp = Cp; pw.KH = d.KH; pw.KW = d.KW; pw.pieces = pieces; pw.src_f32 = f32 ? 1 : 0;
         pw.total = taps * d.Cout * Cp;
-        conv_prep_w_kernel<<<(unsigned)std::min<int64_t>((pw.total + 255) / 256, (int64_t)ctx->sm_count * 16), 256, 0, s>>>(pw);
+        AXB_REQUIRE(d.Cout <= 65535, AXB_ERR_UNSUPPORTED, "conv: more than 65535 output channels");
+        conv_prep_w_kernel<<<dim3((unsigned)(Cp / 64), (unsigned)d.Cout), 256, 0, s>>>(pw);
         AXB_CHECK_LAUNCH();
 
         const int mdt = d.dtype == AXB_F16 ? AXB_F16 : AXB_BF16;
@@ -1495,9 +1579,16 @@ axb_status conv_tc(const ConvDesc &d, DeviceCtx *ctx, cudaStream_t s, bool *done
         const uint64_t rowb = (uint64_t)pieces * Cp * 2;
         CUtensorMap ma, mb;
         AXB_TRY(make_map(&ma, api, mdt, wq, (uint64_t)pieces * Cp, (uint64_t)d.Cout, (uint64_t)taps, rowb, (uint64_t)d.Cout * rowb, BK, BM));
-        const uint64_t dims[4] = {(uint64_t)pieces * Cp, (uint64_t)Wq, (uint64_t)Hq, (uint64_t)planes};
-        const uint64_t strides[3] = {rowb, (uint64_t)Wq * rowb, (uint64_t)Hq * Wq * rowb};
-        AXB_TRY(make_map4(&mb, api, mdt, xq, dims, strides, BK, rows_per_tile > 1 ? 64u : (uint32_t)bn));
+        if (direct) { // (w, h, c, n) over the caller's tensor; one box = 64 columns x 64 channels of one input row
+            const uint64_t dims[4] = {(uint64_t)d.W, (uint64_t)d.H, (uint64_t)d.Cin, (uint64_t)d.N};
+            const uint64_t strides[3] = {(uint64_t)(d.H == 1 ? (d.W * 2 + 15) / 16 * 16 : d.x_s[2]), (uint64_t)d.x_s[1],
+                                         (uint64_t)(d.N == 1 ? d.x_s[1] * d.Cin : d.x_s[0])};
+            AXB_TRY(make_map4(&mb, api, mdt, d.x, dims, strides, 64, 1, BK));
+        } else {
+            const uint64_t dims[4] = {(uint64_t)pieces * Cp, (uint64_t)Wq, (uint64_t)Hq, (uint64_t)planes};
+            const uint64_t strides[3] = {rowb, (uint64_t)Wq * rowb, (uint64_t)Hq * Wq * rowb};
+            AXB_TRY(make_map4(&mb, api, mdt, xq, dims, strides, BK, rows_per_tile > 1 ? 64u : (uint32_t)bn));
+        }
         TcParams p;
         memset(&p, 0, sizeof p);
         p.M = d.Cout; p.N = d.OW; p.batch = d.N * groups;
@@ -1519,7 +1610,9 @@ axb_status conv_tc(const ConvDesc &d, DeviceCtx *ctx, cudaStream_t s, bool *done
             p.conv_ph[t] = phs[t];
         }
         const uint32_t fmt = mdt == AXB_BF16 ? 1u : 0u;
-        p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+        p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((direct ? 1u : 0u) << 16) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+        if (direct)
+            return launch<false, true>(ma, mb, p, ctx->sm_count, s);
         return launch_ff(ma, mb, p, ctx->sm_count, s);
     };
     st = body();

@@ -185,6 +185,37 @@ def test_conv1d_implicit_gemm_whisper_shapes(gpu, dt):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("dt", ["bf16", "f16"])
+def test_conv_direct_nchw_path_equals_the_prepared_path(gpu, dt, monkeypatch):
+    """Half-precision stride-1 convolutions with one-column filters (1x1, KHx1) read the NCHW input in place (MN-major TMA
+    boxes); AXB_CONV_NO_DIRECT forces the channels-last preparation pass. Both are the same sum in the same order: the results must be IDENTICAL bit for bit."""
+    import subprocess, sys, os, json
+    code = r"""
+import sys, json, numpy as np
+sys.path.insert(0, %r)
+from axiom_b200 import capi, device as dev
+from oracle import axiom_oracle as ao
+capi.check(capi.lib().axb_set_device(0))
+rng = np.random.default_rng(51)
+outs = []
+for xs, ws, cfg in (((4, 256, 56, 56), (128, 256, 1, 1), dict(stride=(1, 1), padding=(0, 0), dilation=(1, 1))),
+                    ((1, 72, 24, 200), (96, 72, 3, 1), dict(stride=(1, 1), padding=(2, 0), dilation=(2, 1))),
+                    ((3, 200, 28, 40), (256, 200, 1, 1), dict(stride=(1, 1), padding=(0, 0), dilation=(1, 1)))):
+    x = rng.standard_normal(xs).astype(np.float32); w = (rng.standard_normal(ws) / 20).astype(np.float32)
+    cv = ao.f32_to_bf16 if %r == "bf16" else (lambda a: a.astype(np.float16))
+    dx = dev.DeviceArray.from_numpy(cv(x), bf16=%r == "bf16"); dw = dev.DeviceArray.from_numpy(cv(w), bf16=%r == "bf16")
+    o = dev.conv(dx, dw, None, **cfg); assert capi.lib().axb_matmul_last_path() == 4
+    outs.append(o.numpy().view(np.uint16).tobytes().hex()[:0] + str(hash(o.numpy().view(np.uint16).tobytes())))
+print(json.dumps(outs))
+""" % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), dt, dt, dt)
+    env = dict(os.environ, PYTHONHASHSEED="0")
+    a = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=600)
+    b = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=dict(env, AXB_CONV_NO_DIRECT="1"), timeout=600)
+    assert a.returncode == 0 and b.returncode == 0, a.stderr[-800:] + b.stderr[-800:]
+    assert json.loads(a.stdout.strip().splitlines()[-1]) == json.loads(b.stdout.strip().splitlines()[-1])
+
+
+@pytest.mark.gpu
 def test_conv_implicit_gemm_views_and_small_fallback(gpu):
     from axiom_b200 import capi
     rng = np.random.default_rng(45)
