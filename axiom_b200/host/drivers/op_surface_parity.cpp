@@ -172,6 +172,31 @@ int main() {
         g_cases.push_back(c);
     }
 
+    // ---- Tensor::zeros / ones / eye on Device::GPU (patched: device-side fill instead of host fill + upload) --------------------
+    {
+        Case c{"zeros_ones_eye_on_gpu", false, ""};
+        try {
+            axb_transfer_stats t0{}, t1{};
+            axb_get_transfer_stats(&t0);
+            Tensor z = Tensor::zeros({257, 33}, DType::Float32, Device::GPU), o = Tensor::ones({64, 5, 7}, DType::BFloat16, Device::GPU);
+            Tensor oi = Tensor::ones({1000}, DType::Int64, Device::GPU), zb = Tensor::zeros({77}, DType::Bool, Device::GPU);
+            z.sync(); o.sync(); oi.sync(); zb.sync();
+            axb_get_transfer_stats(&t1);
+            std::string why;
+            c.ok = same(z, Tensor::zeros({257, 33}), &why) && same(o, Tensor::ones({64, 5, 7}, DType::BFloat16), &why) &&
+                   same(oi, Tensor::ones({1000}, DType::Int64), &why) && same(zb, Tensor::zeros({77}, DType::Bool), &why) &&
+                   same(Tensor::eye(9, DType::Float32, Device::GPU), Tensor::eye(9), &why);
+            if (c.ok && t1.h2d_bytes != t0.h2d_bytes) {
+                c.ok = false;
+                why = "zeros / ones on the GPU uploaded " + std::to_string(t1.h2d_bytes - t0.h2d_bytes) + " bytes from the host";
+            }
+            c.why = why;
+        } catch (const std::exception &e) {
+            c.why = e.what();
+        }
+        g_cases.push_back(c);
+    }
+
     // ---- transfers of contiguous views that start inside their storage (patched Tensor::to, tensor.cpp:1625-1636) -------------
     {
         Case c{"transfer_of_offset_views", false, ""};

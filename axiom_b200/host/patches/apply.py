@@ -37,6 +37,22 @@ RULES = {
          "        }\n"
          "    }\n"
          "    const Tensor &src = compact_.storage_ ? compact_ : (is_contiguous() ? *this : ascontiguousarray());\n", 1),
+        # Tensor::zeros / ones on Device::GPU fill a host tensor and upload it (src/tensor/tensor.cpp:1785-1810). The reference
+        # already has the device-side fill hook for its own GPU backend (gpu_fill_constant, metal_operations.hpp:57-58): use it.
+        (r"    auto tensor = Tensor\(shape, dtype, Device::CPU, order\);\n    std::memset\(tensor\.data\(\), 0, tensor\.nbytes\(\)\);\n",
+         "    if (device == Device::GPU && order == MemoryOrder::RowMajor && !is_complex_dtype(dtype))\n"
+         "        return backends::metal::gpu_fill_constant(shape, dtype, 0.0);\n"
+         "    auto tensor = Tensor(shape, dtype, Device::CPU, order);\n    std::memset(tensor.data(), 0, tensor.nbytes());\n", 1),
+        (r"    auto tensor = Tensor\(shape, dtype, Device::CPU, order\);\n    dispatch\(dtype, \[&\]<typename DT>\(DT\) \{\n        tensor\.fill<typename DT::value_type>\(DT::one\(\)\);\n",
+         "    if (device == Device::GPU && order == MemoryOrder::RowMajor && !is_complex_dtype(dtype))\n"
+         "        return backends::metal::gpu_fill_constant(shape, dtype, 1.0);\n"
+         "    auto tensor = Tensor(shape, dtype, Device::CPU, order);\n    dispatch(dtype, [&]<typename DT>(DT) {\n        tensor.fill<typename DT::value_type>(DT::one());\n", 1),
+        # Tensor::eye on Device::GPU returns all zeros upstream (the diagonal is only written `if (device == Device::CPU)`,
+        # :1827-1839; Apple's unified memory hides nothing here — it is simply missing): build on the host, then transfer.
+        (r"Tensor Tensor::eye\(size_t n, DType dtype, Device device, MemoryOrder order\) \{\n    auto tensor = zeros\(\{n, n\}, dtype, device, order\);\n",
+         "Tensor Tensor::eye(size_t n, DType dtype, Device device, MemoryOrder order) {\n"
+         "    if (device == Device::GPU)\n        return eye(n, dtype, Device::CPU, order).to(Device::GPU, order);\n"
+         "    auto tensor = zeros({n, n}, dtype, device, order);\n", 1),
         (r"\nnamespace axiom \{\n\ntemplate <typename T> std::string vec_to_string",
          "\nnamespace axiom { namespace backends { namespace cuda { Tensor gpu_compact(const Tensor &); }}}\n"
          "\nnamespace axiom {\n\ntemplate <typename T> std::string vec_to_string", 1),
