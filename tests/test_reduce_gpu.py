@@ -786,3 +786,33 @@ def test_fused_chain_norm_one_kernel(gpu, shape, kind):
     vl = (xl + yl).astype(np.float64)
     cl = vl - vl.mean(axis=-1, keepdims=True) if kind == "layer_norm" else vl
     assert np.allclose(gl, cl / np.sqrt((cl * cl).mean(axis=-1, keepdims=True) + 1e-5), rtol=1e-5, atol=2e-5)
+
+
+@pytest.mark.gpu
+def test_fused_row_kernels_at_baseline_size_agree_with_the_unfused_path(gpu):
+    """BASELINE config-3 shape {8192, 32768} fp32 (and {8192, 8192} for the register-resident softmax / norm): the fused
+    single-kernel paths against chain + stand-alone kernel on the SAME device data — max exact, sums / softmax / layer_norm
+    inside the 1e-5 contracts — plus size-independent properties (softmax rows sum to 1, normalised rows have zero mean)."""
+    F, V = capi.F32, capi.SRC_VALUE
+    a, b = dev.randn((8192, 32768), 71), dev.randn((1, 32768), 72)
+    prog = [capi.make_instr(capi.OP["mul"], F, 0, 1), capi.make_instr(capi.OP["abs"], F, V(0))]
+    chain = dev.elementwise(prog, [a, b])
+    n0 = dev.launch_count()
+    fmax = dev.elementwise_reduce_axis(prog, [a, b], "max", 1)
+    fsum = dev.elementwise_reduce_axis(prog, [a, b], "sum", 1)
+    assert dev.launch_count() - n0 == 2
+    assert np.array_equal(fmax.numpy(), dev.reduce("max", chain, [1]).numpy())
+    s_ref = dev.reduce("sum", chain, [1]).numpy().astype(np.float64)
+    assert np.all(np.abs(fsum.numpy() - s_ref) <= 2e-5 * s_ref)  # |values| summed: sum == sum of magnitudes
+    del chain, a, b
+    x, y = dev.randn((8192, 8192), 73), dev.randn((8192, 1), 74)
+    prog2 = [capi.make_instr(capi.OP["add"], F, 0, 1)]
+    v = dev.elementwise(prog2, [x, y])
+    n0 = dev.launch_count()
+    sm = dev.elementwise_softmax(prog2, [x, y]).numpy()
+    ln = dev.elementwise_norm(prog2, [x, y], "layer_norm", None, None, 1e-5).numpy()
+    assert dev.launch_count() - n0 == 2
+    assert np.allclose(sm, dev.softmax(v, -1).numpy(), rtol=2e-5, atol=1e-9)
+    assert np.allclose(sm.astype(np.float64).sum(axis=1), 1.0, atol=1e-5)
+    assert np.allclose(ln, dev.layer_norm(v, None, None, -1, 1e-5).numpy(), rtol=1e-5, atol=2e-5)
+    assert np.all(np.abs(ln.astype(np.float64).mean(axis=1)) < 1e-5)

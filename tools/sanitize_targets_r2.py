@@ -37,5 +37,17 @@ pr = [capi.make_instr(capi.OP["add"], F_, 0, 1), capi.make_instr(capi.OP["mul"],
 for shp in ((37, 5000), (1000, 300), (4, 33, 1025), (5, 2)):
     for op in ("sum", "mean", "max"):
         dev.elementwise_reduce_axis(pr, [f(*shp[:-1], 1), f(shp[-1]), f(*shp)], op, -1)
+# chain + softmax / log_softmax / layer_norm / rms_norm in one kernel (register-resident rows), with row epilogue
+pr2 = [capi.make_instr(capi.OP["mul"], F_, 0, capi.SRC_IMM, imm=0.5), capi.make_instr(capi.OP["add"], F_, V_(0), 1)]
+for shp in ((37, 5000), (1000, 300), (5, 2), (9, 8192)):
+    ins = [f(*shp), f(shp[-1])]
+    dev.elementwise_softmax(pr2, ins); dev.elementwise_softmax(pr2, ins, log=True); dev.elementwise_softmax(pr2, ins, epilogue="sum")
+    dev.elementwise_norm(pr2, ins, "layer_norm", f(shp[-1]), f(shp[-1]), 1e-5); dev.elementwise_norm(pr2, ins, "rms_norm", f(shp[-1]), None, 1e-5)
+# direct NCHW convolution (1x1, half precision) and multi-row tiles with a ragged last group
+x1, w1 = dev.cast(f(3, 200, 27, 40), capi.BF16), dev.cast(f(256, 200, 1, 1), capi.BF16)
+dev.conv(x1, w1, None, stride=(1, 1), padding=(0, 0), dilation=(1, 1)); assert L.axb_matmul_last_path() == 4
+dev.conv(f(8, 64, 3, 64), f(64, 64, 3, 3), None, stride=(1, 1), padding=(1, 1), dilation=(1, 1)); assert L.axb_matmul_last_path() == 4
+# staged pageable copies (six host threads, pinned lanes)
+big = np.arange((40 << 20) // 4 + 3, dtype=np.int32); assert np.array_equal(dev.DeviceArray.from_numpy(big).numpy(), big)
 dev.synchronize()
 print("sanitize targets ok")
