@@ -264,8 +264,8 @@ bool launch_wide_typed(RowParams p, DeviceCtx *ctx, cudaStream_t s, axb_status *
     if (per_stage > budget)
         return false;
     p.stages = (int)std::min<size_t>(p.stages, std::max<size_t>(1, (64 * 1024 + per_stage - 1) / per_stage)); // ~64 KiB in flight
-    if (const char *e = getenv("AXB_WIDE_STAGES"))
-        p.stages = std::max(1, std::min(p.stages, atoi(e)));
+    if (const char *e = getenv("AXB_WIDE_STAGES")) // probe switch: any depth the shared memory holds
+        p.stages = std::max(1, std::min<int>((int)std::min<size_t>(kWideMaxStages, budget / per_stage), atoi(e)));
     static const bool no_alt = getenv("AXB_WB_NO_ALTERNATE") != nullptr;
     p.wb_alternate = no_alt ? 0 : 1;
     const size_t dyn = (size_t)p.stages * per_stage;
@@ -287,6 +287,48 @@ bool launch_wide_typed(RowParams p, DeviceCtx *ctx, cudaStream_t s, axb_status *
         *st = AXB_OK;
     };
     const bool exact = p.vpw == JMAX * 32 && nv == (int64_t)kWideWarps * p.vpw;
+    auto go_dyn = [&](auto kern, size_t bytes) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        if (e != cudaSuccess) {
+            *st = fail(AXB_ERR_CUDA, "wide row kernel: cannot reserve %zu bytes of shared memory: %s", bytes, cudaGetErrorString(e));
+            return;
+        }
+        kern<<<grid, kWideThreads, bytes, s>>>(p);
+        cudaError_t le = cudaGetLastError();
+        if (le != cudaSuccess) {
+            *st = fail(AXB_ERR_CUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(le), __FILE__, __LINE__);
+            return;
+        }
+        count_launch();
+        *st = AXB_OK;
+    };
+    if constexpr (KIND == K_SOFTMAX || KIND == K_LOG_SOFTMAX) {
+        if constexpr (sizeof(In) == 4) {
+            // full-width fp32 rows (128 KiB, one row fills the ring): every warp fetches its 4 KiB slice as four 1 KiB
+            // pieces and re-arms each piece as soon as it has been read. Measured on B200 at {8192, 32768}: 0.889 of the
+            // copy peak with one 4 KiB copy per warp, 0.87 with two pieces, 1.009 with four (same 128 KiB ring, results
+            // bit-identical), 0.77 with eight (512-byte copies).
+            int pieces = 4;
+            if (const char *e = getenv("AXB_WIDE_PIECES"))
+                pieces = atoi(e);
+            if (exact && (pieces == 2 || pieces == 4 || pieces == 8)) {
+                const size_t slot = row_bytes / (size_t)pieces;
+                int slots = (int)std::min<size_t>(kWideMaxSlots, budget / slot);
+                slots = std::min(slots, pieces); // one row in flight: deeper rings measured the same or worse
+                if (const char *e = getenv("AXB_WIDE_STAGES"))
+                    slots = std::max(1, std::min<int>((int)std::min<size_t>(kWideMaxSlots, budget / slot), atoi(e)));
+                p.stages = slots;
+                const size_t bytes = (size_t)slots * slot;
+                if (pieces == 2)
+                    go_dyn(rowwide_kernel<In, Out, W, KIND, JMAX, true, 2>, bytes);
+                else if (pieces == 4)
+                    go_dyn(rowwide_kernel<In, Out, W, KIND, JMAX, true, 4>, bytes);
+                else
+                    go_dyn(rowwide_kernel<In, Out, W, KIND, JMAX, true, 8>, bytes);
+                return true;
+            }
+        }
+    }
     if (exact)
         go(rowwide_kernel<In, Out, W, KIND, JMAX, true>);
     else if (j_need * 4 <= JMAX && JMAX >= 4)
