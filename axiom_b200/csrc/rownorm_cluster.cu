@@ -58,15 +58,11 @@ template <> __device__ __forceinline__ float wb_to_f32<bf16_t>(const char *p) { 
 template <> __device__ __forceinline__ float wb_to_f32<f16_t>(const char *p) { return h2f(*reinterpret_cast<const uint16_t *>(p)); }
 
 // J = 16-byte vectors per lane per row-slice, R = rows per pass, EXACT: every lane owns J valid vectors (no masks). p.nv / p.vpw describe ONE slice (row / kClusterSize).
-// C > 1 (needs R == 1, EXACT, one stage): a warp's chunk is fetched as C pieces with a barrier each, and a piece is
-// re-armed with the next row's as soon as it has been read — four 1 KiB copies per warp instead of one 4 KiB copy, the
-// change that took the single-CTA fp32 softmax from 0.889 to 1.009 of the copy peak (rownorm_wide.cuh).
-template <typename In, typename Out, typename W, int KIND, int J, int R, bool EXACT, int C = 1>
+template <typename In, typename Out, typename W, int KIND, int J, int R, bool EXACT>
 __global__ void __cluster_dims__(kClusterSize, 1, 1) __launch_bounds__(kClThreads, 1)
     rowcluster_kernel(const __grid_constant__ RowParams p) {
     constexpr int E = Vec16<In>::E;
     constexpr int V = J * E;
-    static_assert(C == 1 || (R == 1 && EXACT && J % C == 0 && C <= kWideMaxStages), "pieces: one exact row per pass");
     constexpr int PCS = E / 4; // float4 pieces per vector of parameters
     extern __shared__ __align__(128) unsigned char cl_smem[];
     __shared__ __align__(8) uint64_t full_bar[kWideMaxStages * kClWarps];
@@ -91,7 +87,7 @@ __global__ void __cluster_dims__(kClusterSize, 1, 1) __launch_bounds__(kClThread
     const int64_t n_groups = (p.rows + R - 1) / R;
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < (C > 1 ? C : S) * kClWarps; ++i)
+        for (int i = 0; i < S * kClWarps; ++i)
             w_mbar_init(w_smem_u32(&full_bar[i]), 1);
         w_mbar_init(w_smem_u32(&xbar[0]), 1); // armed by this CTA's thread 0 with the expected byte count each use
         w_mbar_init(w_smem_u32(&xbar[1]), 1);
@@ -119,26 +115,11 @@ __global__ void __cluster_dims__(kClusterSize, 1, 1) __launch_bounds__(kClThread
                         p.in + in_off + slice_off_in + (int64_t)v0 * 16, chunk_bytes, bar);
         }
     };
-    auto issue_piece = [&](int64_t row, int c) { // C > 1: piece c of this warp's chunk of `row` into its fixed place
-        const uint32_t bar = w_smem_u32(&full_bar[c * kClWarps + warp]);
-        const uint32_t pb = chunk_bytes / C;
-        int64_t in_off, out_off;
-        offsets(row, &in_off, &out_off);
-        w_mbar_expect_tx(bar, pb);
-        w_bulk_load(rows_base + (uint32_t)v0 * 16u + (uint32_t)c * pb, p.in + in_off + slice_off_in + (int64_t)v0 * 16 + (int64_t)c * pb,
-                    pb, bar);
-    };
     if (lane == 0 && chunk_bytes) {
-        if constexpr (C > 1) {
-            if (cluster_id < n_groups)
-                for (int c = 0; c < C; ++c)
-                    issue_piece(cluster_id, c);
-        } else {
-            for (int s = 0; s < S; ++s) {
-                const int64_t g = cluster_id + (int64_t)s * n_clusters;
-                if (g < n_groups)
-                    issue(g, s);
-            }
+        for (int s = 0; s < S; ++s) {
+            const int64_t g = cluster_id + (int64_t)s * n_clusters;
+            if (g < n_groups)
+                issue(g, s);
         }
     }
     // resident parameters: element e of the slice -> vector vi = e / E, piece h, component k; stored so that lane L's
@@ -219,22 +200,6 @@ __global__ void __cluster_dims__(kClusterSize, 1, 1) __launch_bounds__(kClThread
     uint32_t parity = 0;
     for (int64_t g = cluster_id; g < n_groups; g += n_clusters) {
         float x[R][V];
-        if constexpr (C > 1) {
-            constexpr int JC = J / C;
-#pragma unroll
-            for (int c = 0; c < C; ++c) {
-                w_mbar_wait(w_smem_u32(&full_bar[c * kClWarps + warp]), parity);
-#pragma unroll
-                for (int jj = 0; jj < JC; ++jj) {
-                    const int j = c * JC + jj;
-                    Vec16<In>::unpack(w_lds128(rows_base + (uint32_t)(v0 + j * 32 + lane) * 16u), &x[0][j * E]);
-                }
-                __syncwarp();
-                if (lane == 0 && g + n_clusters < n_groups)
-                    issue_piece(g + n_clusters, c);
-            }
-            parity ^= 1u;
-        } else {
         if (chunk_bytes)
             w_mbar_wait(w_smem_u32(&full_bar[stage * kClWarps + warp]), parity);
 #pragma unroll
@@ -252,17 +217,28 @@ __global__ void __cluster_dims__(kClusterSize, 1, 1) __launch_bounds__(kClThread
                 }
             }
         }
-        __syncwarp();
-        if (lane == 0 && chunk_bytes) {
-            const int64_t ng = g + (int64_t)S * n_clusters;
-            if (ng < n_groups)
-                issue(ng, stage);
-        }
-        if (++stage == S) {
-            stage = 0;
-            parity ^= 1u;
-        }
-        }
+        // The stage is refilled only after its reads have HAPPENED (w_loads_landed, rownorm_wide.cuh: issuing the LDS
+        // is not enough, a refill from an L2-resident input can overtake them), and after the first sweep over the
+        // row's values so that the wait for the data is not exposed.
+        auto refill = [&]() {
+            uint32_t landed = 0;
+#pragma unroll
+            for (int r = 0; r < R; ++r)
+#pragma unroll
+                for (int j = 0; j < J; ++j)
+                    landed |= __float_as_uint(x[r][j * E]);
+            w_loads_landed(landed);
+            __syncwarp();
+            if (lane == 0 && chunk_bytes) {
+                const int64_t ng = g + (int64_t)S * n_clusters;
+                if (ng < n_groups)
+                    issue(ng, stage);
+            }
+            if (++stage == S) {
+                stage = 0;
+                parity ^= 1u;
+            }
+        };
 
         float scale[R];
         bool exact_row[R]; // NaN/inf statistics: every output of the row is NaN -> use the reference's NaN encoding
@@ -277,6 +253,7 @@ __global__ void __cluster_dims__(kClusterSize, 1, 1) __launch_bounds__(kClThread
                 }
                 s[r] = (s0 + s1) + (s2 + s3);
             }
+            refill();
             allreduce(s);
             float q[R];
 #pragma unroll
@@ -324,6 +301,7 @@ __global__ void __cluster_dims__(kClusterSize, 1, 1) __launch_bounds__(kClThread
                 }
                 q[r] = (q0 + q1) + (q2 + q3);
             }
+            refill();
             allreduce(q);
 #pragma unroll
             for (int r = 0; r < R; ++r) {
@@ -468,10 +446,7 @@ bool launch_cluster_typed(RowParams p, DeviceCtx *ctx, cudaStream_t s, axb_statu
         else
             go(rowcluster_kernel<In, Out, W, KIND, JC, 2, false>);
     } else {
-        static const bool no_pieces = getenv("AXB_CLUSTER_NO_PIECES") != nullptr;
-        if (exact && JA == 8 && stages == 1 && !no_pieces) // full-width fp32 rows: 4 KiB per warp as four 1 KiB copies
-            go(rowcluster_kernel<In, Out, W, KIND, JA, 1, true, (JA == 8 ? 4 : 1)>);
-        else if (exact)
+        if (exact)
             go(rowcluster_kernel<In, Out, W, KIND, JA, 1, true>);
         else if (jsel == JA)
             go(rowcluster_kernel<In, Out, W, KIND, JA, 1, false>);

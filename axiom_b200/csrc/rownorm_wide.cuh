@@ -46,6 +46,15 @@ __device__ __forceinline__ uint4 w_lds128(uint32_t addr) {
     asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
     return r;
 }
+// Orders a warp's LDS of a ring slot before the bulk copy that refills it. The LDS instructions only have to be ISSUED
+// for the program to move on to the re-arm, their reads happen later in the shared-memory pipeline, and nothing orders
+// a generic-proxy read against a later async-proxy write of the same bytes: with 1 KiB pieces out of an L2-resident
+// input the refill did overtake the read (layer_norm {700, 32768}: one 256-column piece of ~10 % of the rows held the
+// NEXT row's values). Consuming one result register of every LDS makes the warp wait on the scoreboard until the data
+// has arrived; the comparison feeds a predicated no-op so that ptxas keeps it.
+__device__ __forceinline__ void w_loads_landed(uint32_t bits) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.u32 p, %0, 0x7FC0DEAD;\n\t@p nanosleep.u32 0;\n\t}" ::"r"(bits) : "memory");
+}
 __device__ __forceinline__ float w_ex2(float x) {
     float r;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
@@ -257,9 +266,29 @@ __global__ void __launch_bounds__(kWideThreads, 1) rowwide_kernel(const __grid_c
     int next_piece = S % C;
     for (int64_t row = blockIdx.x; row < p.rows; row += gridDim.x) {
         float x[V];
-        // ---- ring -> registers ----------------------------------------------------------------------------
+        // Refill of the slot that piece `c` of this row was read from: first the reads must have HAPPENED (see
+        // w_loads_landed), then one lane re-arms the barrier and starts the copy of the piece S pieces ahead. It runs one
+        // piece late — after the LDS of the following piece have been issued, the last one after the first sweep over the
+        // row's values — so the wait for the data never sits between two loads.
+        auto refill = [&](auto cc, int slot_read) {
+            constexpr int c = decltype(cc)::value;
+            uint32_t landed = 0;
 #pragma unroll
-        for (int c = 0; c < C; ++c) {
+            for (int jj = 0; jj < JC; ++jj)
+                landed |= __float_as_uint(x[(c * JC + jj) * E]);
+            w_loads_landed(landed);
+            __syncwarp();
+            if (lane == 0 && chunk_bytes && next_row < p.rows)
+                issue(next_row, next_piece, slot_read);
+            if (++next_piece == C) {
+                next_piece = 0;
+                next_row += gridDim.x;
+            }
+        };
+        // ---- ring -> registers ----------------------------------------------------------------------------
+        int slot_prev = 0;
+        auto fetch = [&](auto cc) {
+            constexpr int c = decltype(cc)::value;
             if (chunk_bytes)
                 w_mbar_wait(w_smem_u32(&full_bar[slot * kWideWarps + warp]), parity);
             const uint32_t buf = smem_base + (uint32_t)slot * slot_stride;
@@ -275,18 +304,16 @@ __global__ void __launch_bounds__(kWideThreads, 1) rowwide_kernel(const __grid_c
                         x[j * E + k] = (KIND == K_SOFTMAX || KIND == K_LOG_SOFTMAX) ? -INFINITY : 0.0f;
                 }
             }
-            __syncwarp();
-            if (lane == 0 && chunk_bytes && next_row < p.rows)
-                issue(next_row, next_piece, slot);
-            if (++next_piece == C) {
-                next_piece = 0;
-                next_row += gridDim.x;
-            }
+            if constexpr (c > 0)
+                refill(std::integral_constant<int, (c > 0 ? c - 1 : 0)>{}, slot_prev);
+            slot_prev = slot;
             if (++slot == S) {
                 slot = 0;
                 parity ^= 1u;
             }
-        }
+        };
+        static_for_up<C>(fetch);
+        auto refill_last = [&]() { refill(std::integral_constant<int, C - 1>{}, slot_prev); };
         int64_t in_off, out_off;
         offsets(row, &in_off, &out_off);
         char *dst = p.out + out_off;
@@ -298,6 +325,7 @@ __global__ void __launch_bounds__(kWideThreads, 1) rowwide_kernel(const __grid_c
                 m0 = fmaxf(m0, x[i]);
                 m1 = fmaxf(m1, x[i + 1]);
             }
+            refill_last();
             const float m = wide_allreduce<FMax>(fmaxf(m0, m1), scratch, flip);
             float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
             if (KIND == K_SOFTMAX) {
@@ -376,6 +404,7 @@ __global__ void __launch_bounds__(kWideThreads, 1) rowwide_kernel(const __grid_c
                 for (int i = 0; i < V; i += 4) {
                     s0 += x[i]; s1 += x[i + 1]; s2 += x[i + 2]; s3 += x[i + 3];
                 }
+                refill_last();
                 const float s = wide_allreduce<FAdd>((s0 + s1) + (s2 + s3), scratch, flip);
                 const float mean = round_to<In>(__fdiv_rn(s, n_f));
                 float q0 = 0.0f, q1 = 0.0f, q2 = 0.0f, q3 = 0.0f;
@@ -402,6 +431,7 @@ __global__ void __launch_bounds__(kWideThreads, 1) rowwide_kernel(const __grid_c
                     q2 += round_to<In>(__fmul_rn(x[i + 2], x[i + 2]));
                     q3 += round_to<In>(__fmul_rn(x[i + 3], x[i + 3]));
                 }
+                refill_last();
                 const float q = wide_allreduce<FAdd>((q0 + q1) + (q2 + q3), scratch, flip);
                 const float ms = round_to<In>(__fdiv_rn(q, n_f));
                 scale = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(ms, p.eps)));

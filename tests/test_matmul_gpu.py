@@ -243,6 +243,26 @@ def test_f32_tensor_core_split_is_fp32_accurate(gpu, case):
     _close_f32(got, a, b, rtol=2e-6)
 
 
+def test_f32_gelu_epilogue_tracks_the_reference_gelu(gpu):
+    """The fp32 GEMM epilogue evaluates GELU with the reference's Abramowitz-Stegun formula on the MUFU unit
+    (gemm_tcgen05.cu gelu_epilogue_f32) instead of the bit-exact Highway sequence the elementwise kernels use. Isolated
+    from the matmul's own rounding: the same GEMM without the activation, pushed through the oracle's gelu, has to agree
+    to 4e-7 * max(1, |x|) over a range that covers both tails (x in [-9, 9]) and the special values."""
+    rng = np.random.default_rng(5)
+    a = rand_f32(rng, (512, 384), 1.0)
+    a[0, :] = 0.0
+    w = rand_f32(rng, (640, 384), 0.15)
+    bias = np.linspace(-6.0, 6.0, 640).astype(np.float32)
+    da, dw, db = (dev.DeviceArray.from_numpy(t) for t in (a, w, bias))
+    plain = dev.matmul(da, dw, transpose_b=True, bias=db).numpy()
+    fused = dev.matmul(da, dw, transpose_b=True, bias=db, activation="gelu").numpy()
+    assert capi.lib().axb_matmul_last_path() == 3  # fp32 on the tensor cores
+    exp, _ = ao.unary("gelu", np.ascontiguousarray(plain), ao.F32)
+    err = np.abs(fused.astype(np.float64) - exp.astype(np.float64))
+    assert np.all(err <= 4e-7 * np.maximum(1.0, np.abs(plain))), float(err.max())
+    assert np.abs(plain).max() > 8.0 and np.all(fused[plain < -8.5] <= 0.0)
+
+
 def test_constant_operand_split_is_cached_and_invalidated(gpu):
     """AXB_MM_CONST_B (nn::Linear weights): the fp32 three-piece split of B is computed once; overwriting B's bytes through
     the library (or freeing its block) drops the cached pieces, so results always follow the CURRENT contents."""

@@ -1,0 +1,7 @@
+set -x
+mkdir -p gpurun_out
+cd axiom_b200/host/_build
+timeout 300 ./whisper_encoder 8 10 1 2>&1 | tail -1 | cut -c1-600
+timeout 300 ./whisper_encoder 1 10 0 2>&1 | tail -1 | cut -c1-600
+ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file /root/repo/gpurun_out/r3_whisper_launches_b8.csv ./whisper_encoder 8 1 0 > /root/repo/gpurun_out/whisper_ncu.log 2>&1
+wc -l /root/repo/gpurun_out/r3_whisper_launches_b8.csv
