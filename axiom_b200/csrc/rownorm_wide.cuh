@@ -350,19 +350,29 @@ __global__ void __launch_bounds__(kWideThreads, 1) rowwide_kernel(const __grid_c
                 const float s = wide_allreduce<FAdd>((s0 + s1) + (s2 + s3), scratch, flip);
                 const float inv = __fdiv_rn(1.0f, s);
                 const bool row_nan = !(s == s); // a NaN anywhere makes every output of the row NaN
+                // every vector leaves through the hardware converter; a row that produced NaNs (rare, block-uniform) is
+                // stored a second time with the reference's NaN encoding — no per-vector branch on the hot path
+                char *d0 = dst + (int64_t)(v0 + lane) * (E * sizeof(Out));
 #pragma unroll
                 for (int j = 0; j < J; ++j) {
-                    const int vi = v0 + j * 32 + lane;
-                    if (EXACT || vi < v1) {
+                    if (EXACT || v0 + j * 32 + lane < v1) {
                         float y[E];
 #pragma unroll
                         for (int k = 0; k < E; ++k)
                             y[k] = x[j * E + k] * inv;
-                        char *d = dst + (int64_t)vi * (E * sizeof(Out));
-                        if (row_nan)
-                            store_vec<Out, E, false>(d, y);
-                        else
-                            store_vec<Out, E, true>(d, y);
+                        store_vec<Out, E, true>(d0 + j * (32 * E * (int)sizeof(Out)), y);
+                    }
+                }
+                if (sizeof(Out) == 2 && row_nan) {
+#pragma unroll
+                    for (int j = 0; j < J; ++j) {
+                        if (EXACT || v0 + j * 32 + lane < v1) {
+                            float y[E];
+#pragma unroll
+                            for (int k = 0; k < E; ++k)
+                                y[k] = x[j * E + k] * inv;
+                            store_vec<Out, E, false>(d0 + j * (32 * E * (int)sizeof(Out)), y);
+                        }
                     }
                 }
             } else {
@@ -378,21 +388,27 @@ __global__ void __launch_bounds__(kWideThreads, 1) rowwide_kernel(const __grid_c
                 // any NaN result (a NaN input, inf - inf) also makes s and ls NaN, so the hardware bf16 converter
                 // (NaN -> 0x7FFF instead of the reference's 0x7FC0) is only used on rows where ls is a number
                 const bool row_nan = !(ls == ls);
-                // (the branch stays inside the loop: hoisting it around two copies of the loop measured 0.83 vs 0.87
-                // of the copy peak for bf16 rows)
+                char *d0 = dst + (int64_t)(v0 + lane) * (E * sizeof(Out));
 #pragma unroll
                 for (int j = 0; j < J; ++j) {
-                    const int vi = v0 + j * 32 + lane;
-                    if (EXACT || vi < v1) {
+                    if (EXACT || v0 + j * 32 + lane < v1) {
                         float y[E];
 #pragma unroll
                         for (int k = 0; k < E; ++k)
                             y[k] = __fsub_rn(__fsub_rn(x[j * E + k], m), ls);
-                        char *d = dst + (int64_t)vi * (E * sizeof(Out));
-                        if (row_nan)
-                            store_vec<Out, E, false>(d, y);
-                        else
-                            store_vec<Out, E, true>(d, y);
+                        store_vec<Out, E, true>(d0 + j * (32 * E * (int)sizeof(Out)), y);
+                    }
+                }
+                if (sizeof(Out) == 2 && row_nan) {
+#pragma unroll
+                    for (int j = 0; j < J; ++j) {
+                        if (EXACT || v0 + j * 32 + lane < v1) {
+                            float y[E];
+#pragma unroll
+                            for (int k = 0; k < E; ++k)
+                                y[k] = __fsub_rn(__fsub_rn(x[j * E + k], m), ls);
+                            store_vec<Out, E, false>(d0 + j * (32 * E * (int)sizeof(Out)), y);
+                        }
                     }
                 }
             }
