@@ -410,6 +410,42 @@ def test_layer_and_rms_norm_wide_and_cluster_f32(gpu, shape, affine):
     assert np.allclose(got[sl], e, rtol=1e-5, atol=2e-5)
 
 
+@pytest.mark.parametrize("op", ["layer_norm", "rms_norm", "softmax", "log_softmax"])
+@pytest.mark.parametrize("dt", ["f32", "bf16"])
+def test_tma_staged_row_kernels_are_deterministic_on_l2_resident_rows(gpu, op, dt):
+    """Regression for a read-before-refill race in the TMA-staged row kernels: a ring slot was re-armed once the LDS of the
+    slot had been ISSUED, and a refill served from L2 (the input of a test fits the 126 MB L2) could overwrite the slot before
+    the reads happened — one 256-column piece of ~10 % of the rows of layer_norm {700, 32768} came out with the NEXT row's
+    values, in about half of the runs. Every repetition has to return the same bytes, and they have to be the right ones."""
+    rng = np.random.default_rng(61)
+    rows, n = 700, 32768
+    x = rand_f32(rng, (rows, n), 2.0) + np.float32(0.75)
+    w = (1 + 0.1 * rng.standard_normal(n)).astype(np.float32)
+    b = (0.1 * rng.standard_normal(n)).astype(np.float32)
+    if dt == "bf16":
+        dx = dev.DeviceArray.from_numpy(as_bf16(x), bf16=True)
+        x = ao.bf16_to_f32(as_bf16(x))
+    else:
+        dx = dev.DeviceArray.from_numpy(x)
+    dw, db = dev.DeviceArray.from_numpy(w), dev.DeviceArray.from_numpy(b)
+    call = {"layer_norm": lambda: dev.layer_norm(dx, dw, db, -1, 1e-5), "rms_norm": lambda: dev.rms_norm(dx, dw, -1, 1e-5),
+            "softmax": lambda: dev.softmax(dx, -1), "log_softmax": lambda: dev.softmax(dx, -1, log=True)}[op]
+    first = call().numpy()
+    for _ in range(8):
+        again = call().numpy()
+        assert again.tobytes() == first.tobytes(), (op, dt, "result changes from call to call")
+    got = ao.bf16_to_f32(first) if first.dtype == np.uint16 else first.astype(np.float32)
+    x64 = x.astype(np.float64)
+    if op in ("softmax", "log_softmax"):
+        e = np.exp(x64 - x64.max(axis=-1, keepdims=True))
+        truth = e / e.sum(axis=-1, keepdims=True)
+        truth = np.log(truth) if op == "log_softmax" else truth
+    else:
+        truth = _ln_truth(x, w, b if op == "layer_norm" else None, 1e-5, rms=(op == "rms_norm"))
+    tol = 1e-5 if first.dtype != np.uint16 else 2.0 ** -7
+    assert np.allclose(got, truth, rtol=tol, atol=2e-5 if first.dtype != np.uint16 else 2.0 ** -7 * np.abs(truth).max()), (op, dt)
+
+
 @pytest.mark.parametrize("wdt", ["f32", "bf16"])
 @pytest.mark.parametrize("shape", [(1200, 16384), (601, 32768), (800, 8192)])
 def test_layer_norm_cluster_bf16_rows(gpu, shape, wdt):
