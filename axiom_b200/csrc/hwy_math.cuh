@@ -141,6 +141,23 @@ __device__ __forceinline__ float Tanh(float x) {
     return f_from_bits(bits(z) ^ sign);
 }
 
+// Exp(x) as Erf below needs it: x = -(s * s) is never positive and the result e only enters 1 - poly * e with
+// 0 <= poly <= 1.1. Same value as Exp(x) wherever it can matter, in 10 instructions fewer:
+//  * x <= -0 always, so Exp's half_signed is the constant -0.5;
+//  * x is clamped at -86: there e <= 4.5e-38, poly * e < 2^-25 and 1 - poly * e rounds to exactly 1 for the clamped and
+//    for the true argument alike (Exp's own cut-off to 0 below -104 included); NaN and -inf still end as they did — NaN
+//    through poly, -inf through poly = 0;
+//  * inside [-86, 0] q >= -124, so both power-of-two factors of load_exp_short_range and both products are normal and
+//    exact: y * 2^y1 * 2^y2 == y * 2^q, which is one integer add on y's exponent field.
+// tools/erf_equiv.cu compares Erf built on this with Erf built on Exp for all 2^32 inputs.
+__device__ __forceinline__ float ExpNegForErf(float x) {
+    const float kOneOverLog2 = 1.442695040888963407359924681f;
+    x = fmaxf(x, -86.0f);
+    int32_t q = __float2int_rz(fma_(x, kOneOverLog2, -0.5f));
+    float y = add(exp_poly(exp_reduce(x, q)), 1.0f);
+    return f_from_bits(bits(y) + ((uint32_t)q << 23));
+}
+
 // ---- reference Erf: Abramowitz-Stegun 7.1.26 (hwy_math_ext-inl.h:1-37) --------------------------------
 __device__ __forceinline__ float Erf(float x) {
     const float p = 0.3275911f, a1 = 0.254829592f, a2 = -0.284496736f, a3 = 1.421413741f, a4 = -1.453152027f,
@@ -153,7 +170,7 @@ __device__ __forceinline__ float Erf(float x) {
     poly = fma_(t, poly, a2);
     poly = fma_(t, poly, a1);
     poly = mul(t, poly);
-    float e = Exp(-mul(x, x));
+    float e = ExpNegForErf(-mul(x, x)); // == Exp(-x*x) wherever r depends on it
     float r = fma_(-poly, e, 1.0f); // NegMulAdd(poly, e, one) = one - poly*e
     return mul(sign, r);
 }
