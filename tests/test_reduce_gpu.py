@@ -352,6 +352,54 @@ def test_softmax_wide_rows_masked_inf_nan(gpu):
     assert np.max(np.abs(ao.bf16_to_f32(gb[ok]) - ao.bf16_to_f32(eb))) <= 2 ** -8 * ao.bf16_to_f32(eb).max()
 
 
+def test_log_softmax_wide_rows_masked_inf_nan(gpu):
+    """log_softmax on the TMA-staged kernel: masked (-inf) entries stay -inf, a NaN anywhere / an all -inf row / a +inf entry
+    make the whole row NaN (x - max = NaN in the reference loop, cpu_operations.cpp:3132-3158), other rows are unaffected.
+    bf16 rows go through the hardware converter; rows that produced NaNs are stored again with the reference's 0x7FC0."""
+    rng = np.random.default_rng(44)
+    for n in (8192, 32768):
+        x = rand_f32(rng, (150, n), 2.0)
+        x[:, n // 2:] = -np.inf
+        x[7, 13] = np.nan
+        x[9, :] = -np.inf
+        x[11, 5] = np.inf
+        ok = np.ones(150, bool)
+        ok[[7, 9, 11]] = False
+        m = x[ok].astype(np.float64).max(axis=-1, keepdims=True)
+        with np.errstate(divide="ignore"):
+            truth = (x[ok] - m) - np.log(np.exp(x[ok].astype(np.float64) - m).sum(axis=-1, keepdims=True))
+        got = dev.softmax(dev.DeviceArray.from_numpy(x), -1, log=True).numpy()
+        assert np.all(np.isnan(got[~ok])) and np.all(got[ok][:, n // 2:] == -np.inf)
+        assert np.allclose(got[ok][:, :n // 2], truth[:, :n // 2], rtol=1e-5, atol=1e-5)
+        xb = as_bf16(x)
+        gb = dev.softmax(dev.DeviceArray.from_numpy(xb, bf16=True), -1, log=True).numpy()
+        assert np.all(gb[~ok] == 0x7FC0), "NaN rows must use the reference's bf16 NaN encoding"
+        assert np.all(gb[ok][:, n // 2:] == 0xFF80)  # -inf
+        eb = ao.bf16_to_f32(ao.softmax(xb[ok], ao.BF16, -1, log=True))[:, :n // 2]
+        gf = ao.bf16_to_f32(gb[ok])[:, :n // 2]
+        xf = ao.bf16_to_f32(xb[ok]).astype(np.float64)
+        mb = xf.max(axis=-1, keepdims=True)
+        with np.errstate(divide="ignore"):
+            tb = ((xf - mb) - np.log(np.exp(xf - mb).sum(axis=-1, keepdims=True)))[:, :n // 2]
+        assert np.all(np.abs(gf - tb) <= 2.0 ** -7 * np.abs(tb) + 1e-6)
+        assert np.all(np.abs(gf - eb) <= 2.0 ** -7 * np.abs(eb) + 1e-6)
+
+
+def test_softmax_wide_rows_two_outer_dims_and_row_pitch(gpu):
+    """128 KiB fp32 rows (the four-piece fetch) under a {3, 50, 32768} tensor and under a view whose rows sit 16 elements
+    apart from dense (outer strides walked with the div / mod path, every piece copy offset by the pitch)."""
+    rng = np.random.default_rng(45)
+    x = rand_f32(rng, (3, 50, 32768), 3.0)
+    got = dev.softmax(dev.DeviceArray.from_numpy(x), -1).numpy()
+    assert np.allclose(got, _f64_softmax(x), rtol=1e-5, atol=1e-12)
+    wide = rand_f32(rng, (60, 32768 + 16), 3.0)
+    view = dev.DeviceArray.from_numpy(wide[:, :32768])  # a view of the uploaded {60, 32784} buffer
+    assert not view.is_contiguous()
+    got = dev.softmax(view, -1).numpy()
+    assert np.allclose(got, _f64_softmax(wide[:, :32768]), rtol=1e-5, atol=1e-12)
+    assert capi.lib().axb_rownorm_last_path() == 1
+
+
 @pytest.mark.parametrize("dt", ["bf16", "f16"])
 @pytest.mark.parametrize("shape", [(200, 8192), (33, 32768), (150, 20000)])
 def test_softmax_wide_rows_half(gpu, dt, shape):
