@@ -344,7 +344,10 @@ axb_status axb_elementwise_reduce_axis(const axb_instr *prog, int n_instr, const
 #define AXB_MM_CONST_B 2 /* operand B is a constant */
 typedef struct axb_matmul_epilogue {
     const axb_tensor *bias; /* NULL, or broadcastable to [.., M, N] (Linear: {N}) — nn/linear.cpp:22-25 */
-    int32_t activation;     /* 0 = none, else a unary axb_op (RELU, GELU, SILU, SIGMOID, TANH) */
+    int32_t activation;     /* 0 = none, else a unary axb_op (RELU, GELU, SILU, SIGMOID, TANH). Same function as the
+                             * elementwise op (bit-identical for half-precision outputs); GELU of a float32 tensor-core
+                             * result evaluates the reference's Abramowitz-Stegun erf with MUFU reciprocal / exponential:
+                             * within 3e-7 * max(1, |x|) of the elementwise op, below the matmul's own rounding. */
     /* AXB_MM_CONST_*: the caller promises that the flagged operand's bytes only change through this library (axb_free of
      * its block, axb_memcpy_* / axb_memset into it) or are announced with axb_invalidate_cached. The fp32 tensor-core path
      * then keeps the operand's three-piece bf16 split (nn::Linear / conv weights) instead of re-splitting it per call. */
