@@ -56,7 +56,11 @@ struct ConvDesc {
     int64_t N, Cin, H, W, Cout, KH, KW, OH, OW;
     int64_t x_s[4], w_s[4]; // byte strides
     int64_t bias_s;
-    int32_t sh, sw, ph, pw, dh, dw;
+    int32_t sh, sw, ph, pw, dh, dw; // dh / dw may be negative (the sub-convolutions of a transposed convolution walk their taps backwards)
+    // optional: byte strides of the output over (N, C_out, OH, OW); all zero = contiguous. A transposed convolution writes each
+    // output phase (oh % stride, ow % stride) as its own stride-1 convolution into an interleaved view of the result.
+    int64_t o_s[4];
+    int32_t force;  // skip the "too small to pay for the preparation passes" heuristics (the caller sized the whole problem)
 };
 axb_status conv_tc(const ConvDesc &d, DeviceCtx *ctx, cudaStream_t s, bool *done);
 

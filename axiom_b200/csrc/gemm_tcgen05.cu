@@ -1508,7 +1508,9 @@ axb_status conv_tc(const ConvDesc &d, DeviceCtx *ctx, cudaStream_t s, bool *done
         return AXB_OK;
     const int64_t taps = d.KH * d.KW;
     const double flops = 2.0 * (double)d.N * (double)d.Cout * (double)d.OH * (double)d.OW * (double)d.Cin * (double)taps;
-    if (taps < 1 || taps > kMaxTaps || flops < 1.0e8 || d.Cout < 32 || d.OW < 8 || d.Cin < 8 || d.N * d.OH >= (1ll << 31))
+    if (taps < 1 || taps > kMaxTaps || d.N * d.OH >= (1ll << 31))
+        return AXB_OK;
+    if (!d.force && (flops < 1.0e8 || d.Cout < 32 || d.OW < 8 || d.Cin < 8))
         return AXB_OK; // small problems: the preparation passes and the 128-row tile would dominate (gather kernel / im2col path)
     if (d.sh < 1 || d.sw < 1 || d.sh * d.sw > 64 || d.N * d.sh * d.sw > 65535 || (d.H + d.sh - 1) / d.sh > 65535)
         return AXB_OK;
@@ -1618,6 +1620,9 @@ axb_status conv_tc(const ConvDesc &d, DeviceCtx *ctx, cudaStream_t s, bool *done
         p.num_tiles = (int64_t)p.tiles_m * p.tiles_n * p.batch;
         p.c = d.out;
         p.c_rs = d.OH * d.OW * esz; p.c_cs = esz; p.c_bs = d.Cout * d.OH * d.OW * esz; p.c_hs = d.OW * esz;
+        if (d.o_s[0] | d.o_s[1] | d.o_s[2] | d.o_s[3]) { // a strided view of the result (one phase of a transposed convolution)
+            p.c_bs = d.o_s[0]; p.c_rs = d.o_s[1]; p.c_hs = d.o_s[2]; p.c_cs = d.o_s[3];
+        }
         p.bias = d.bias; p.bias_rs = d.bias ? d.bias_s : 0; p.bias_cs = 0; p.bias_bs = 0;
         p.bias_dtype = d.bias_dtype; p.act = d.act; p.out_dtype = d.dtype;
         p.split = f32 ? 2 : 0; p.kbp = (int)(taps * cblocks); p.Kp = Cp;

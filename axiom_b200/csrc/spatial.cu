@@ -223,6 +223,92 @@ unsigned grid_for(int64_t total, const DeviceCtx *ctx) {
     default: KERNEL<F16><<<grid, 256, 0, s>>>(params); break;                                                          \
     }
 
+// Transposed convolution on the tensor cores. out[n, co, ih*sh - ph + kh*dh, iw*sw - pw + kw*dw] += x[n, ci, ih, iw] * w[ci, co, kh, kw]
+// (ops::conv_transpose1d / 2d, src/tensor/operations.cpp:3425-3690) is, for the outputs of ONE phase (oh % sh, ow % sw) = (rh, rw),
+// an ordinary stride-1 convolution of the un-dilated input: with oh = oh' * sh + rh only the taps with (rh + ph - kh*dh) % sh == 0
+// contribute, they form an arithmetic progression kh = kh0 + i * step, and tap i reads input row oh' + q0 - i * (step * dh / sh).
+// So every phase is one call of the implicit-GEMM convolution (gemm::conv_tc) with
+//   * the weights seen through a strided VIEW (C_out / C_in strides swapped, taps kh0 :: step) — no re-layout pass of its own,
+//   * a negative "dilation" and "padding" -q0 (conv_tc only turns them into per-tap TMA coordinates; rows / columns outside the
+//     input are zero-filled, which is exactly the scatter's bounds test),
+//   * the result written into the interleaved view out[:, :, rh :: sh, rw :: sw] (bias added once per element in the epilogue).
+// Phases without taps (kernel smaller than the stride) and small problems stay on the gather kernel. Numerics as for conv_tc:
+// fp32 through the exact three-piece bf16 split (fp32-FMA accuracy, tolerance-based parity, not the fp64 products of the loop).
+axb_status conv_transpose_tc(const ConvParams &p, int dtype, DeviceCtx *ctx, cudaStream_t s, bool *done) {
+    *done = false;
+    static const bool off = getenv("AXB_CONVT_NO_TC") != nullptr; // A/B switch
+    if (off || !(dtype == AXB_F32 || dtype == AXB_BF16 || dtype == AXB_F16))
+        return AXB_OK;
+    const double flops = 2.0 * (double)p.N * (double)p.Cin * (double)p.H * (double)p.W * (double)p.Cout * (double)(p.KH * p.KW);
+    if (flops < 2.0e8 || p.Cout < 32 || p.Cin < 8 || p.OW < 8 * p.sw || p.sh * p.sw > 16)
+        return AXB_OK;
+    struct Axis {
+        int64_t k0, step, count, q0, dil; // first tap, tap spacing, taps, input offset of the first tap, offset change per tap
+    };
+    auto plan = [](int64_t r, int64_t stride, int64_t pad, int64_t dil, int64_t K, Axis *a) {
+        a->count = 0;
+        int64_t prev = -1;
+        for (int64_t k = 0; k < K; ++k) {
+            const int64_t t = r + pad - k * dil;
+            if (((t % stride) + stride) % stride != 0)
+                continue;
+            if (a->count == 0) {
+                a->k0 = k;
+                a->q0 = t / stride; // exact
+                a->step = 1;
+                a->dil = 0;
+            } else if (a->count == 1) {
+                a->step = k - prev;
+                a->dil = t / stride - a->q0;
+            }
+            prev = k;
+            a->count++;
+        }
+    };
+    const int esz = (int)dtype_size(dtype);
+    // every phase must have taps and rows, otherwise the gather kernel does the whole tensor
+    for (int64_t rh = 0; rh < p.sh; ++rh)
+        for (int64_t rw = 0; rw < p.sw; ++rw) {
+            Axis ah, aw;
+            plan(rh, p.sh, p.ph, p.dh, p.KH, &ah);
+            plan(rw, p.sw, p.pw, p.dw, p.KW, &aw);
+            if (ah.count == 0 || aw.count == 0 || rh >= p.OH || rw >= p.OW)
+                return AXB_OK;
+        }
+    bool all = true;
+    for (int64_t rh = 0; rh < p.sh && all; ++rh)
+        for (int64_t rw = 0; rw < p.sw && all; ++rw) {
+            Axis ah, aw;
+            plan(rh, p.sh, p.ph, p.dh, p.KH, &ah);
+            plan(rw, p.sw, p.pw, p.dw, p.KW, &aw);
+            gemm::ConvDesc cd;
+            memset(&cd, 0, sizeof cd);
+            cd.x = p.in;
+            cd.w = p.w + ah.k0 * p.w_s[2] + aw.k0 * p.w_s[3];
+            cd.bias = p.bias;
+            cd.out = p.out + (rh * p.OW + rw) * esz;
+            cd.dtype = dtype; cd.bias_dtype = dtype; cd.act = 0;
+            cd.N = p.N; cd.Cin = p.Cin; cd.H = p.H; cd.W = p.W; cd.Cout = p.Cout;
+            cd.KH = ah.count; cd.KW = aw.count;
+            cd.OH = (p.OH - rh + p.sh - 1) / p.sh; cd.OW = (p.OW - rw + p.sw - 1) / p.sw;
+            for (int i = 0; i < 4; ++i)
+                cd.x_s[i] = p.in_s[i];
+            cd.w_s[0] = p.w_s[1]; cd.w_s[1] = p.w_s[0]; // (C_in, C_out, ..) read as (C_out, C_in, ..)
+            cd.w_s[2] = ah.step * p.w_s[2]; cd.w_s[3] = aw.step * p.w_s[3];
+            cd.bias_s = p.bias_s;
+            cd.sh = 1; cd.sw = 1;
+            cd.ph = (int32_t)-ah.q0; cd.pw = (int32_t)-aw.q0;
+            cd.dh = (int32_t)ah.dil; cd.dw = (int32_t)aw.dil;
+            cd.o_s[0] = p.Cout * p.OH * p.OW * esz; cd.o_s[1] = p.OH * p.OW * esz; cd.o_s[2] = p.sh * p.OW * esz; cd.o_s[3] = p.sw * esz;
+            cd.force = 1;
+            bool one = false;
+            AXB_TRY(gemm::conv_tc(cd, ctx, s, &one));
+            all = all && one;
+        }
+    *done = all; // a phase the tensor-core path declined: the gather kernel rewrites the whole result
+    return AXB_OK;
+}
+
 // shared argument handling of conv2d / conv_transpose: 3-D (N, C, L) tensors are the 1-D case (H = KH = 1)
 axb_status run_conv(bool transposed, const axb_tensor *in, const axb_tensor *weight, const axb_tensor *bias, int spatial_dims,
                     const int32_t *stride, const int32_t *padding, const int32_t *dilation, int groups, const axb_tensor *out,
@@ -293,6 +379,12 @@ axb_status run_conv(bool transposed, const axb_tensor *in, const axb_tensor *wei
         cd.sh = p.sh; cd.sw = p.sw; cd.ph = p.ph; cd.pw = p.pw; cd.dh = p.dh; cd.dw = p.dw;
         bool done = false;
         AXB_TRY(gemm::conv_tc(cd, ctx, s, &done));
+        if (done)
+            return AXB_OK;
+    }
+    if (transposed && groups == 1) {
+        bool done = false;
+        AXB_TRY(conv_transpose_tc(p, in->dtype, ctx, s, &done));
         if (done)
             return AXB_OK;
     }

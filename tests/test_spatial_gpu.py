@@ -5,8 +5,9 @@ CPU-vs-GPU sweep through the reference API is tests/test_axiom_cpp.py::test_spat
 import numpy as np
 import pytest
 
-from axiom_b200 import device as dev
+from axiom_b200 import capi, device as dev
 from oracle import axiom_oracle as ao
+from tests.helpers import as_bf16
 
 
 # ---- CPU: the restatements against the reference's known answers --------------------------------------------------------
@@ -75,6 +76,105 @@ def test_conv_transpose1d_matches_the_2d_restatement(gpu):
                              output_padding=1, dilation=2, groups=2).numpy()
     exp = ao.conv_transpose2d_f32(x[:, :, None, :], w[:, :, None, :], None, (1, 3), (0, 2), (0, 1), (1, 2), 2)[:, :, 0, :]
     assert np.array_equal(got, exp)
+
+
+def _conv_transpose_f64(x, w, bias, stride, padding, output_padding, dilation):
+    """fp64 truth of ops::conv_transpose2d (operations.cpp:3590-3690), one einsum per filter tap; also returns the same sum over
+    absolute values (the scale a rounding-error bound is stated against)."""
+    n, cin, h, wd = x.shape
+    _, cout, kh, kw = w.shape
+    oh = (h - 1) * stride[0] - 2 * padding[0] + dilation[0] * (kh - 1) + output_padding[0] + 1
+    ow = (wd - 1) * stride[1] - 2 * padding[1] + dilation[1] * (kw - 1) + output_padding[1] + 1
+    ph, pw = max(padding[0], 0) + dilation[0] * kh, max(padding[1], 0) + dilation[1] * kw  # margin: scatter first, crop after
+    full = np.zeros((2, n, cout, oh + 2 * ph + stride[0], ow + 2 * pw + stride[1]))
+    x64, w64 = x.astype(np.float64), w.astype(np.float64)
+    for fh in range(kh):
+        for fw in range(kw):
+            t = np.einsum("nchw,co->nohw", x64, w64[:, :, fh, fw])
+            ta = np.einsum("nchw,co->nohw", np.abs(x64), np.abs(w64[:, :, fh, fw]))
+            r0, c0 = ph - padding[0] + fh * dilation[0], pw - padding[1] + fw * dilation[1]
+            full[0][:, :, r0:r0 + (h - 1) * stride[0] + 1:stride[0], c0:c0 + (wd - 1) * stride[1] + 1:stride[1]] += t
+            full[1][:, :, r0:r0 + (h - 1) * stride[0] + 1:stride[0], c0:c0 + (wd - 1) * stride[1] + 1:stride[1]] += ta
+    out = full[:, :, :, ph:ph + oh, pw:pw + ow]
+    if bias is not None:
+        out[0] += bias.astype(np.float64)[None, :, None, None]
+        out[1] += np.abs(bias.astype(np.float64))[None, :, None, None]
+    return out[0], out[1]
+
+
+def test_conv_transpose_f64_helper_matches_the_loop_restatement():
+    rng = np.random.default_rng(40)
+    x = rng.standard_normal((2, 3, 4, 5)).astype(np.float32)
+    w = rng.standard_normal((3, 2, 3, 2)).astype(np.float32)
+    b = rng.standard_normal(2).astype(np.float32)
+    for cfg in (dict(stride=(2, 3), padding=(1, 0), output_padding=(1, 2), dilation=(1, 1)),
+                dict(stride=(2, 2), padding=(1, 1), output_padding=(0, 1), dilation=(2, 1))):
+        t, _ = _conv_transpose_f64(x, w, b, **cfg)
+        assert np.allclose(t, ao.conv_transpose2d_f32(x, w, b, groups=1, **cfg), rtol=1e-5, atol=1e-5)
+
+
+CONVT_TC = [  # (x shape, w shape, kwargs)
+    ((2, 64, 32, 32), (64, 64, 4, 4), dict(stride=(2, 2), padding=(1, 1), output_padding=(0, 0), dilation=(1, 1))),   # 2x upsampling
+    ((2, 96, 30, 33), (96, 72, 3, 3), dict(stride=(2, 2), padding=(1, 1), output_padding=(1, 1), dilation=(1, 1))),   # 1 / 2 / 2 / 4 taps per phase
+    ((2, 40, 25, 40), (40, 96, 5, 5), dict(stride=(3, 2), padding=(2, 0), output_padding=(2, 1), dilation=(2, 1))),   # dilation 2 against stride 3
+    ((3, 64, 20, 64), (64, 64, 3, 5), dict(stride=(1, 1), padding=(1, 2), output_padding=(0, 0), dilation=(1, 1))),   # stride 1: one phase, vector stores
+    ((3, 64, 24, 40), (64, 64, 4, 3), dict(stride=(2, 1), padding=(1, 1), output_padding=(0, 0), dilation=(1, 1))),   # strided rows, dense columns
+]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", range(len(CONVT_TC)))
+@pytest.mark.parametrize("dt", ["f32", "bf16"])
+def test_conv_transpose_on_the_tensor_cores(gpu, case, dt):
+    """Transposed convolutions large enough for the tensor cores run as one implicit-GEMM convolution per output phase
+    (spatial.cu conv_transpose_tc): path asserted, result against the fp64 truth — fp32 to 2e-6 of sum |x||w| (the exact
+    three-piece split), bf16 to half a bf16 ulp of the result plus the fp32 accumulation bound."""
+    xs, ws, kw = CONVT_TC[case]
+    rng = np.random.default_rng(41 + case)
+    x = rng.standard_normal(xs).astype(np.float32)
+    w = (rng.standard_normal(ws) * 0.2).astype(np.float32)
+    b = rng.standard_normal(ws[1]).astype(np.float32)
+    if dt == "bf16":
+        xb, wb, bb = as_bf16(x), as_bf16(w), as_bf16(b)
+        x, w, b = ao.bf16_to_f32(xb), ao.bf16_to_f32(wb), ao.bf16_to_f32(bb)
+        got = ao.bf16_to_f32(dev.conv_transpose(dev.DeviceArray.from_numpy(xb, bf16=True), dev.DeviceArray.from_numpy(wb, bf16=True),
+                                                dev.DeviceArray.from_numpy(bb, bf16=True), **kw).numpy())
+    else:
+        got = dev.conv_transpose(dev.DeviceArray.from_numpy(x), dev.DeviceArray.from_numpy(w), dev.DeviceArray.from_numpy(b), **kw).numpy()
+    assert capi.lib().axb_matmul_last_path() == 4, "expected the implicit-GEMM path"
+    truth, scale = _conv_transpose_f64(x, w, b, **kw)
+    assert got.shape == truth.shape
+    err = np.abs(got.astype(np.float64) - truth)
+    if dt == "f32":
+        assert np.all(err <= 2e-6 * scale + 1e-7), float((err / (scale + 1e-30)).max())
+    else:  # conv result rounded to bf16, + bias rounded to bf16 (two roundings, the reference's op order)
+        # half a bf16 ulp is up to 2^-8 |v|: once on the convolution (|conv| <= |truth| + |b|), once on the sum
+        assert np.all(err <= 2.0 ** -8 * (2.0 * np.abs(truth) + np.abs(b).max()) + 1e-5 * scale), float(err.max())
+
+
+@pytest.mark.gpu
+def test_conv_transpose1d_on_the_tensor_cores(gpu):
+    rng = np.random.default_rng(49)
+    x = rng.standard_normal((4, 128, 500)).astype(np.float32)
+    w = (rng.standard_normal((128, 96, 8)) * 0.1).astype(np.float32)
+    got = dev.conv_transpose(dev.DeviceArray.from_numpy(x), dev.DeviceArray.from_numpy(w), None, stride=4, padding=2).numpy()
+    assert capi.lib().axb_matmul_last_path() == 4
+    truth, scale = _conv_transpose_f64(x[:, :, None, :], w[:, :, None, :], None, (1, 4), (0, 2), (0, 0), (1, 1))
+    assert np.all(np.abs(got - truth[:, :, 0, :]) <= 2e-6 * scale[:, :, 0, :] + 1e-7)
+
+
+@pytest.mark.gpu
+def test_conv_transpose_kernel_smaller_than_stride_stays_on_the_gather_kernel(gpu):
+    """A 2 x 2 filter under stride 3 leaves output phases without any tap (they hold the bias only): not a convolution the
+    implicit GEMM can express, the gather kernel runs (and stays bit-identical to the loop restatement on a sample)."""
+    rng = np.random.default_rng(50)
+    x = rng.standard_normal((2, 64, 40, 40)).astype(np.float32)
+    w = (rng.standard_normal((64, 64, 2, 2)) * 0.2).astype(np.float32)
+    b = rng.standard_normal(64).astype(np.float32)
+    got = dev.conv_transpose(dev.DeviceArray.from_numpy(x), dev.DeviceArray.from_numpy(w), dev.DeviceArray.from_numpy(b), stride=3).numpy()
+    assert capi.lib().axb_matmul_last_path() == 0
+    truth, scale = _conv_transpose_f64(x, w, b, (3, 3), (0, 0), (0, 0), (1, 1))
+    assert np.allclose(got, truth, rtol=1e-5, atol=1e-5)
 
 
 @pytest.mark.gpu
