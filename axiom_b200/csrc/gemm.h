@@ -61,6 +61,10 @@ struct ConvDesc {
     // output phase (oh % stride, ow % stride) as its own stride-1 convolution into an interleaved view of the result.
     int64_t o_s[4];
     int32_t force;  // skip the "too small to pay for the preparation passes" heuristics (the caller sized the whole problem)
+    // optional: where the caller keeps the prepared (channels-last, split) form of x between calls that share the same input
+    // and strides (the phases of a transposed convolution). *x_prepared == nullptr: this call prepares x and leaves the buffer
+    // there; otherwise it is used as it is. The caller frees it (axb_free, stream-ordered).
+    void **x_prepared;
 };
 axb_status conv_tc(const ConvDesc &d, DeviceCtx *ctx, cudaStream_t s, bool *done);
 

@@ -240,8 +240,11 @@ __device__ __forceinline__ void epilogue_tile(const TcParams &p, int64_t b, int 
         // a ragged last chunk still takes the 128-bit exchange store when N is a whole number of 16-byte segments (the
         // segments past N are simply not written): N = 56 bf16 columns would otherwise leave 24 of them to 2-byte stores
         const bool vec_store = c_vec && (full || (p.N * osz) % 16 == 0);
-        if (m >= p.M && !vec_store)
-            continue; // (the exchange-based store below needs the whole warp)
+        // columns a few elements apart and rows far apart (one phase of a transposed convolution writing out[.., rw :: sw]):
+        // the same shared-memory exchange, then element stores with the lanes of a row on neighbouring columns
+        const bool strided_store = !c_vec && p.c_cs > osz && p.c_cs <= 64 && p.c_rs > 32 * p.c_cs;
+        if (m >= p.M && !vec_store && !strided_store)
+            continue; // (the exchange-based stores below need the whole warp)
         float f[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i)
@@ -340,6 +343,33 @@ __device__ __forceinline__ void epilogue_tile(const TcParams &p, int64_t b, int 
                         *reinterpret_cast<uint4 *>(p.c + cbase + mm * p.c_rs + (nbase + cw * 4) * 4) = w;
                 }
                 __syncwarp();
+            } else if (strided_store) {
+                // written straight out, a warp store would touch 32 rows with 4 bytes each; after the exchange 8 lanes
+                // cover 8 neighbouring columns of one row (2 sectors at a column stride of 8 bytes) and an instruction 4 rows
+                const uint32_t tile = staging_base + (uint32_t)ewarp * 4096u;
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(tile + lane * 128u + ((i ^ (lane & 7)) << 4)),
+                                 "r"(__float_as_uint(f[4 * i])), "r"(__float_as_uint(f[4 * i + 1])), "r"(__float_as_uint(f[4 * i + 2])),
+                                 "r"(__float_as_uint(f[4 * i + 3]))
+                                 : "memory");
+                __syncwarp();
+                const int cw = lane & 7;
+#pragma unroll
+                for (int it = 0; it < 8; ++it) {
+                    const int rr = it * 4 + (lane >> 3);
+                    const int64_t mm = (int64_t)m0 + q * 32 + rr;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const int col = k * 8 + cw;
+                        uint32_t w;
+                        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w)
+                                     : "r"(tile + rr * 128u + ((((uint32_t)col >> 2) ^ (rr & 7)) << 4) + ((uint32_t)col & 3u) * 4u));
+                        if (mm < p.M && nbase + col < p.N)
+                            *reinterpret_cast<uint32_t *>(p.c + cbase + mm * p.c_rs + (nbase + col) * p.c_cs) = w;
+                    }
+                }
+                __syncwarp();
             } else {
 #pragma unroll
                 for (int i = 0; i < 32; ++i)
@@ -387,6 +417,30 @@ __device__ __forceinline__ void epilogue_tile(const TcParams &p, int64_t b, int 
                 const int64_t mm = (int64_t)m0 + q * 32 + rr;
                 if (mm < p.M && nbase + cw * 8 < p.N)
                     *reinterpret_cast<uint4 *>(p.c + cbase + mm * p.c_rs + (nbase + cw * 8) * 2) = w;
+            }
+            __syncwarp();
+        } else if (strided_store) { // 64-byte rows: 4 lanes per row on neighbouring columns, 8 rows per instruction
+            const uint32_t tile = staging_base + (uint32_t)ewarp * 4096u;
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(tile + lane * 64u + ((i ^ ((lane >> 1) & 3)) << 4)),
+                             "r"(h[4 * i]), "r"(h[4 * i + 1]), "r"(h[4 * i + 2]), "r"(h[4 * i + 3])
+                             : "memory");
+            __syncwarp();
+            const int cw = lane & 3;
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {
+                const int rr = it * 8 + (lane >> 2);
+                const int64_t mm = (int64_t)m0 + q * 32 + rr;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const int col = k * 4 + cw;
+                    uint16_t w;
+                    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(w)
+                                 : "r"(tile + rr * 64u + ((((uint32_t)col >> 3) ^ ((rr >> 1) & 3)) << 4) + ((uint32_t)col & 7u) * 2u));
+                    if (mm < p.M && nbase + col < p.N)
+                        *reinterpret_cast<uint16_t *>(p.c + cbase + mm * p.c_rs + (nbase + col) * p.c_cs) = w;
+                }
             }
             __syncwarp();
         } else {
@@ -1550,16 +1604,22 @@ axb_status conv_tc(const ConvDesc &d, DeviceCtx *ctx, cudaStream_t s, bool *done
                         (reinterpret_cast<uintptr_t>(d.x) & 15) == 0;
     const size_t x_bytes = direct ? 256 : (size_t)planes * Hq * Wq * pieces * Cp * 2, w_bytes = (size_t)taps * d.Cout * pieces * Cp * 2;
     void *xq = nullptr, *wq = nullptr;
-    AXB_TRY(axb_alloc(x_bytes, s, &xq));
+    const bool x_shared = d.x_prepared && !direct;      // the prepared input outlives this call
+    const bool x_ready = x_shared && *d.x_prepared;     // ... and an earlier call already filled it
+    if (x_ready)
+        xq = *d.x_prepared;
+    else
+        AXB_TRY(axb_alloc(x_bytes, s, &xq));
     axb_status st = axb_alloc(w_bytes, s, &wq);
     if (st != AXB_OK) {
-        axb_free(xq, s);
+        if (!x_ready)
+            axb_free(xq, s);
         return st;
     }
     auto body = [&]() -> axb_status {
         ConvPrepX px;
         memset(&px, 0, sizeof px);
-        if (!direct) {
+        if (!direct && !x_ready) {
         px.x = d.x; px.dst = static_cast<uint16_t *>(xq);
         for (int i = 0; i < 4; ++i)
             px.xs[i] = d.x_s[i];
@@ -1640,7 +1700,10 @@ axb_status conv_tc(const ConvDesc &d, DeviceCtx *ctx, cudaStream_t s, bool *done
         return launch_ff(ma, mb, p, ctx->sm_count, s);
     };
     st = body();
-    axb_free(xq, s); // stream-ordered: reusable after the GEMM
+    if (x_shared && st == AXB_OK)
+        *d.x_prepared = xq; // the caller's to free
+    else if (!x_ready)
+        axb_free(xq, s); // stream-ordered: reusable after the GEMM
     axb_free(wq, s);
     if (st == AXB_OK) {
         *done = true;

@@ -276,6 +276,7 @@ axb_status conv_transpose_tc(const ConvParams &p, int dtype, DeviceCtx *ctx, cud
                 return AXB_OK;
         }
     bool all = true;
+    void *x_prepared = nullptr; // channels-last (split) form of the input: made by the first phase, read by all of them
     for (int64_t rh = 0; rh < p.sh && all; ++rh)
         for (int64_t rw = 0; rw < p.sw && all; ++rw) {
             Axis ah, aw;
@@ -301,10 +302,18 @@ axb_status conv_transpose_tc(const ConvParams &p, int dtype, DeviceCtx *ctx, cud
             cd.dh = (int32_t)ah.dil; cd.dw = (int32_t)aw.dil;
             cd.o_s[0] = p.Cout * p.OH * p.OW * esz; cd.o_s[1] = p.OH * p.OW * esz; cd.o_s[2] = p.sh * p.OW * esz; cd.o_s[3] = p.sw * esz;
             cd.force = 1;
+            cd.x_prepared = &x_prepared;
             bool one = false;
-            AXB_TRY(gemm::conv_tc(cd, ctx, s, &one));
+            const axb_status st = gemm::conv_tc(cd, ctx, s, &one);
+            if (st != AXB_OK) {
+                if (x_prepared)
+                    axb_free(x_prepared, s);
+                return st;
+            }
             all = all && one;
         }
+    if (x_prepared)
+        axb_free(x_prepared, s); // stream-ordered: after the last phase's GEMM
     *done = all; // a phase the tensor-core path declined: the gather kernel rewrites the whole result
     return AXB_OK;
 }

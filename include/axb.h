@@ -413,8 +413,11 @@ axb_status axb_pad_constant(const axb_tensor *in, const int64_t *pad_lo, const i
  *                       shape (which carries output_padding) is the caller's, as in the reference.
  *   axb_interpolate     ops::interpolate (:3694-3975, hook gpu_interpolate :3742): in (N, C, L) or (N, C, H, W);
  *                       mode 0 nearest, 1 linear / bilinear, 2 bicubic (1-d inputs: every non-nearest mode is linear)
- * Inputs and weights may be strided views; outputs are contiguous; floating dtypes; fp32 results are bit-identical to the
- * CPU loops (same accumulation type and term order).
+ * Inputs and weights may be strided views; outputs are contiguous; floating dtypes; fp32 results of the gather kernels are
+ * bit-identical to the CPU loops (same accumulation type and term order). Large axb_conv_transpose problems (groups == 1,
+ * >= 2e8 flop, C_out >= 32, C_in >= 8, every output phase reached by at least one filter tap; float32 / bf16 / fp16) run on the
+ * tensor cores as one implicit-GEMM convolution per output phase (axb_matmul_last_path() == 4): float32 through the exact
+ * three-piece bf16 split — fp32-FMA accuracy, tolerance-based parity like axb_conv.
  * ---------------------------------------------------------------------------------------------- */
 axb_status axb_conv2d(const axb_tensor *in, const axb_tensor *weight, const axb_tensor *bias /* may be NULL */,
                       const int32_t stride[2], const int32_t padding[2], const int32_t dilation[2], int groups,
