@@ -391,6 +391,34 @@ axb_status run_conv(bool transposed, const axb_tensor *in, const axb_tensor *wei
         if (done)
             return AXB_OK;
     }
+    if (!transposed && groups > 1 && groups <= 64 && p.cin_g >= 8 && p.cout_g >= 32) {
+        // grouped convolution: every group is a convolution of a channel slice of the input into a channel slice of the
+        // result — views of the same tensors, so the tensor-core path runs once per group (each call sizes itself; if one
+        // declines, the gather kernel below rewrites the whole result)
+        bool all = true;
+        for (int g = 0; g < groups && all; ++g) {
+            gemm::ConvDesc cd;
+            memset(&cd, 0, sizeof cd);
+            cd.x = p.in + g * p.cin_g * p.in_s[1];
+            cd.w = p.w + g * p.cout_g * p.w_s[0];
+            cd.bias = p.bias ? p.bias + g * p.cout_g * p.bias_s : nullptr;
+            cd.out = p.out + g * p.cout_g * p.OH * p.OW * p.esize;
+            cd.dtype = in->dtype; cd.bias_dtype = in->dtype; cd.act = activation;
+            cd.N = p.N; cd.Cin = p.cin_g; cd.H = p.H; cd.W = p.W; cd.Cout = p.cout_g; cd.KH = p.KH; cd.KW = p.KW; cd.OH = p.OH; cd.OW = p.OW;
+            for (int i = 0; i < 4; ++i) {
+                cd.x_s[i] = p.in_s[i];
+                cd.w_s[i] = p.w_s[i];
+            }
+            cd.bias_s = p.bias_s;
+            cd.sh = p.sh; cd.sw = p.sw; cd.ph = p.ph; cd.pw = p.pw; cd.dh = p.dh; cd.dw = p.dw;
+            cd.o_s[0] = p.Cout * p.OH * p.OW * p.esize; cd.o_s[1] = p.OH * p.OW * p.esize; cd.o_s[2] = p.OW * p.esize; cd.o_s[3] = p.esize;
+            bool one = false;
+            AXB_TRY(gemm::conv_tc(cd, ctx, s, &one));
+            all = all && one;
+        }
+        if (all)
+            return AXB_OK;
+    }
     if (transposed && groups == 1) {
         bool done = false;
         AXB_TRY(conv_transpose_tc(p, in->dtype, ctx, s, &done));

@@ -269,6 +269,35 @@ def test_conv2d_implicit_gemm(gpu, xs, ws, cfg, dt):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("dt", ["f32", "bf16"])
+@pytest.mark.parametrize("groups,odd", [(2, False), (4, True)])
+def test_grouped_conv2d_runs_one_implicit_gemm_per_group(gpu, dt, groups, odd):
+    """groups > 1 with enough channels per group: every group is the tensor-core convolution of a channel slice (views of
+    the same tensors, result written into its channel slice; an odd OH * OW leaves the slice unaligned for the 128-bit stores).
+    Truth: the fp64 convolution of each slice. + bias + relu in the epilogue."""
+    rng = np.random.default_rng(47)
+    cin_g, cout_g = 32, 48
+    hw = (27, 33) if odd else (28, 32)
+    x = rng.standard_normal((6, cin_g * groups, *hw)).astype(np.float32)
+    w = (rng.standard_normal((cout_g * groups, cin_g, 3, 3)) / np.sqrt(cin_g * 9)).astype(np.float32)
+    b = rng.standard_normal(cout_g * groups).astype(np.float32)
+    cfg = dict(stride=(1, 1), padding=(1, 1), dilation=(1, 1))
+    if dt == "bf16":
+        xb, wb, bb = as_bf16(x), as_bf16(w), as_bf16(b)
+        x, w, b = ao.bf16_to_f32(xb), ao.bf16_to_f32(wb), ao.bf16_to_f32(bb)
+        got = ao.bf16_to_f32(dev.conv(dev.DeviceArray.from_numpy(xb, bf16=True), dev.DeviceArray.from_numpy(wb, bf16=True),
+                                      dev.DeviceArray.from_numpy(bb, bf16=True), groups=groups, activation="relu", **cfg).numpy())
+    else:
+        got = dev.conv(dev.DeviceArray.from_numpy(x), dev.DeviceArray.from_numpy(w), dev.DeviceArray.from_numpy(b), groups=groups,
+                       activation="relu", **cfg).numpy()
+    assert capi.lib().axb_matmul_last_path() == 4
+    for g in range(groups):
+        exp, mag = ao.conv2d_f64(x[:, g * cin_g:(g + 1) * cin_g], w[g * cout_g:(g + 1) * cout_g], b[g * cout_g:(g + 1) * cout_g], **cfg)
+        err = np.abs(got[:, g * cout_g:(g + 1) * cout_g].astype(np.float64) - np.maximum(exp, 0))
+        assert np.all(err <= (4e-6 if dt == "f32" else 1e-2) * mag), (g, float((err / mag).max()))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dt", ["f32", "bf16"])
 def test_conv1d_implicit_gemm_whisper_shapes(gpu, dt):
     """The two convolutions of the whisper encoder (examples/whisper_poc.cpp:57-60): 80 -> 384, k 3, pad 1 and 384 -> 384,
     k 3, stride 2, pad 1, with the bias and a fused GELU in the GEMM epilogue."""
