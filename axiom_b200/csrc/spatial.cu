@@ -234,14 +234,16 @@ unsigned grid_for(int64_t total, const DeviceCtx *ctx) {
 //   * the result written into the interleaved view out[:, :, rh :: sh, rw :: sw] (bias added once per element in the epilogue).
 // Phases without taps (kernel smaller than the stride) and small problems stay on the gather kernel. Numerics as for conv_tc:
 // fp32 through the exact three-piece bf16 split (fp32-FMA accuracy, tolerance-based parity, not the fp64 products of the loop).
-axb_status conv_transpose_tc(const ConvParams &p, int dtype, DeviceCtx *ctx, cudaStream_t s, bool *done) {
+// Groups: each group is the same computation on channel slices (input channels g*cin_g.., weight rows g*cin_g.., result
+// channels g*cout_g..), taken as views.
+axb_status conv_transpose_tc(const ConvParams &p, int dtype, int groups, DeviceCtx *ctx, cudaStream_t s, bool *done) {
     *done = false;
     static const bool off = getenv("AXB_CONVT_NO_TC") != nullptr; // A/B switch
     if (off || !(dtype == AXB_F32 || dtype == AXB_BF16 || dtype == AXB_F16))
         return AXB_OK;
-    const double flops = 2.0 * (double)p.N * (double)p.Cin * (double)p.H * (double)p.W * (double)p.Cout * (double)(p.KH * p.KW);
-    if (flops < 2.0e8 || p.Cout < 32 || p.Cin < 8 || p.OW < 8 * p.sw || p.sh * p.sw > 16)
-        return AXB_OK;
+    const double flops = 2.0 * (double)p.N * (double)p.cin_g * (double)p.H * (double)p.W * (double)p.cout_g * (double)(p.KH * p.KW);
+    if (flops < 2.0e8 || p.cout_g < 32 || p.cin_g < 8 || p.OW < 8 * p.sw || p.sh * p.sw > 16 || groups > 64)
+        return AXB_OK; // (sized per group: every group pays its own preparation passes)
     struct Axis {
         int64_t k0, step, count, q0, dil; // first tap, tap spacing, taps, input offset of the first tap, offset change per tap
     };
@@ -276,6 +278,7 @@ axb_status conv_transpose_tc(const ConvParams &p, int dtype, DeviceCtx *ctx, cud
                 return AXB_OK;
         }
     bool all = true;
+    for (int g = 0; g < groups && all; ++g) {
     void *x_prepared = nullptr; // channels-last (split) form of the input: made by the first phase, read by all of them
     for (int64_t rh = 0; rh < p.sh && all; ++rh)
         for (int64_t rw = 0; rw < p.sw && all; ++rw) {
@@ -284,12 +287,12 @@ axb_status conv_transpose_tc(const ConvParams &p, int dtype, DeviceCtx *ctx, cud
             plan(rw, p.sw, p.pw, p.dw, p.KW, &aw);
             gemm::ConvDesc cd;
             memset(&cd, 0, sizeof cd);
-            cd.x = p.in;
-            cd.w = p.w + ah.k0 * p.w_s[2] + aw.k0 * p.w_s[3];
-            cd.bias = p.bias;
-            cd.out = p.out + (rh * p.OW + rw) * esz;
+            cd.x = p.in + g * p.cin_g * p.in_s[1];
+            cd.w = p.w + g * p.cin_g * p.w_s[0] + ah.k0 * p.w_s[2] + aw.k0 * p.w_s[3];
+            cd.bias = p.bias ? p.bias + g * p.cout_g * p.bias_s : nullptr;
+            cd.out = p.out + (g * p.cout_g * p.OH * p.OW + rh * p.OW + rw) * esz;
             cd.dtype = dtype; cd.bias_dtype = dtype; cd.act = 0;
-            cd.N = p.N; cd.Cin = p.Cin; cd.H = p.H; cd.W = p.W; cd.Cout = p.Cout;
+            cd.N = p.N; cd.Cin = p.cin_g; cd.H = p.H; cd.W = p.W; cd.Cout = p.cout_g;
             cd.KH = ah.count; cd.KW = aw.count;
             cd.OH = (p.OH - rh + p.sh - 1) / p.sh; cd.OW = (p.OW - rw + p.sw - 1) / p.sw;
             for (int i = 0; i < 4; ++i)
@@ -314,6 +317,7 @@ axb_status conv_transpose_tc(const ConvParams &p, int dtype, DeviceCtx *ctx, cud
         }
     if (x_prepared)
         axb_free(x_prepared, s); // stream-ordered: after the last phase's GEMM
+    }
     *done = all; // a phase the tensor-core path declined: the gather kernel rewrites the whole result
     return AXB_OK;
 }
@@ -419,9 +423,9 @@ axb_status run_conv(bool transposed, const axb_tensor *in, const axb_tensor *wei
         if (all)
             return AXB_OK;
     }
-    if (transposed && groups == 1) {
+    if (transposed) {
         bool done = false;
-        AXB_TRY(conv_transpose_tc(p, in->dtype, ctx, s, &done));
+        AXB_TRY(conv_transpose_tc(p, in->dtype, groups, ctx, s, &done));
         if (done)
             return AXB_OK;
     }

@@ -682,6 +682,14 @@ def sharded_configs(env):
         ex["conv1d_f32_whisper_conv2_gelu"]["kernel_path"] = int(L.axb_matmul_last_path())
         ex["conv1d_f32_whisper_conv2_gelu"]["note"] = "fp32 through the three-piece bf16 split: 6 bf16 MMAs per fp32 MAC"
         del xw, ww, bw
+        # transposed convolution (2x upsampling block): one implicit-GEMM convolution per output phase
+        nbt = max(1, 8 // world)
+        xt = dev.cast(dev.randn((nbt, 256, 32, 32), 47 + 100 * rank), capi.BF16)
+        wt = dev.cast(dev.randn((256, 128, 4, 4), 48, 0.0, 0.02), capi.BF16)
+        run("conv_transpose2d_bf16_256to128_k4s2", lambda: dev.conv_transpose(xt, wt, None, stride=2, padding=1),
+            flops=2.0 * nbt * 256 * 32 * 32 * 128 * 16, per_gpu={"images_per_gpu": nbt})
+        ex["conv_transpose2d_bf16_256to128_k4s2"]["kernel_path"] = int(L.axb_matmul_last_path())
+        del xt, wt
         # flash attention at the whisper shape {8/N, 6, 1500, 64}, fp32 (three-piece) and bf16
         for dt in ("f32", "bf16"):
             q, k, v = (dev.randn((nbw, 6, 1500, 64), 50 + i + 100 * rank) for i in range(3))

@@ -164,6 +164,23 @@ def test_conv_transpose1d_on_the_tensor_cores(gpu):
 
 
 @pytest.mark.gpu
+def test_grouped_conv_transpose_on_the_tensor_cores(gpu):
+    """groups = 2: each group is the phase-wise tensor-core path on channel-slice views (weight rows g * C_in/groups ..)."""
+    rng = np.random.default_rng(51)
+    groups, cin_g, cout_g = 2, 48, 40
+    x = rng.standard_normal((6, cin_g * groups, 24, 28)).astype(np.float32)
+    w = (rng.standard_normal((cin_g * groups, cout_g, 4, 4)) * 0.1).astype(np.float32)
+    b = rng.standard_normal(cout_g * groups).astype(np.float32)
+    kw = dict(stride=(2, 2), padding=(1, 1), output_padding=(0, 0), dilation=(1, 1))
+    got = dev.conv_transpose(dev.DeviceArray.from_numpy(x), dev.DeviceArray.from_numpy(w), dev.DeviceArray.from_numpy(b), groups=groups, **kw).numpy()
+    assert capi.lib().axb_matmul_last_path() == 4
+    for g in range(groups):
+        truth, scale = _conv_transpose_f64(x[:, g * cin_g:(g + 1) * cin_g], w[g * cin_g:(g + 1) * cin_g], b[g * cout_g:(g + 1) * cout_g], **kw)
+        err = np.abs(got[:, g * cout_g:(g + 1) * cout_g].astype(np.float64) - truth)
+        assert np.all(err <= 2e-6 * scale + 1e-7), (g, float((err / (scale + 1e-30)).max()))
+
+
+@pytest.mark.gpu
 def test_conv_transpose_kernel_smaller_than_stride_stays_on_the_gather_kernel(gpu):
     """A 2 x 2 filter under stride 3 leaves output phases without any tap (they hold the bias only): not a convolution the
     implicit GEMM can express, the gather kernel runs (and stays bit-identical to the loop restatement on a sample)."""
