@@ -74,6 +74,9 @@ struct TcParams {
     // so the weights are fetched once per four rows instead of once per row); c_hs is the byte stride of an output row,
     // conv_ohs the number of output rows of an image.
     int32_t conv_taps, conv_cblocks, conv_oh, conv_phases, conv_rows, conv_ohs;
+    // conv_rows > 1: output rows per 64-column chunk of the tile (1: a chunk is one row of up to 64 columns; 2: images at most 32
+    // columns wide, a chunk is a {2 rows x 32 columns} TMA box, i.e. twice the rows per tile for the same MMA work)
+    int32_t conv_rpc;
     int64_t c_hs;
     int16_t conv_qw[kMaxTaps], conv_qh[kMaxTaps], conv_ph[kMaxTaps];
 };
@@ -215,9 +218,9 @@ __device__ __forceinline__ void epilogue_tile(const TcParams &p, int64_t b, int 
 #pragma unroll 1
     for (int c = half; c < BN_ / 32; c += 2) {
         int64_t nbase = n0 + c * 32, cbase = cbase0;
-        if (p.conv_rows > 1) { // 64-column chunk r of the tile is output row conv_oh0 + r
-            const int r = c >> 1;
-            nbase = (c & 1) * 32;
+        if (p.conv_rows > 1) { // 64-column chunk k of the tile holds output rows conv_oh0 + k * rpc .. (rpc = 1: one 64-column row,
+            const int r = p.conv_rpc == 2 ? c : c >> 1; // two 32-column segments; rpc = 2: two rows of 32 columns, one segment each)
+            nbase = p.conv_rpc == 2 ? 0 : (c & 1) * 32;
             if (conv_oh0 + r >= p.conv_ohs || nbase >= p.N)
                 continue; // warp-uniform
             cbase += r * p.c_hs;
@@ -528,7 +531,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                                 } else { // one 64-column box per output row of the group
                                     for (int r = 0; r < BN_ / 64; ++r)
                                         tma_load_4d(sb + pc * (BN_ * BK * 2) + r * (64 * BK * 2), &tma_b, full_bar(stage), pc * (int)p.Kp + c0,
-                                                    p.conv_qw[tap], oh + r + p.conv_qh[tap], img * p.conv_phases + p.conv_ph[tap]);
+                                                    p.conv_qw[tap], oh + r * p.conv_rpc + p.conv_qh[tap], img * p.conv_phases + p.conv_ph[tap]);
                                 }
                             }
                         } else {
@@ -583,7 +586,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                                         img * p.conv_phases + p.conv_ph[tap]);
                         } else { // one 64-column box per output row of the group
                             for (int r = 0; r < BN_ / 64; ++r)
-                                tma_load_4d(sb + r * (64 * BK * 2), &tma_b, full_bar(stage), c0, p.conv_qw[tap], oh + r + p.conv_qh[tap],
+                                tma_load_4d(sb + r * (64 * BK * 2), &tma_b, full_bar(stage), c0, p.conv_qw[tap], oh + r * p.conv_rpc + p.conv_qh[tap],
                                             img * p.conv_phases + p.conv_ph[tap]);
                         }
                         if (++stage == STAGES) {
@@ -1651,10 +1654,17 @@ axb_status conv_tc(const ConvDesc &d, DeviceCtx *ctx, cudaStream_t s, bool *done
         // images at most 64 columns wide: a tile holds bn / 64 consecutive output rows (one 64-column chunk each), so the
         // weight tile is fetched once per group of rows instead of once per row (L2 -> SM traffic per flop halves / quarters)
         static const bool no_rows = getenv("AXB_CONV_ONE_ROW") != nullptr; // A/B switch
-        int rows_per_tile = 1;
+        int rows_per_tile = 1, rpc = 1;
         if (!no_rows && d.OW <= 64 && d.OH >= 2) {
-            bn = (f32 || d.OH < 4) ? 128 : 256;
-            rows_per_tile = bn / 64;
+            static const bool no_pack = getenv("AXB_CONV_NO_PACK") != nullptr; // A/B switch
+            rpc = (!no_pack && !direct && d.OW <= 32 && d.OH >= 4) ? 2 : 1; // narrow images: two rows share a 64-column chunk
+            bn = (f32 || d.OH < 4 * rpc) ? 128 : 256;
+            if (rpc == 2) { // the widest tile that still occupies half of the SMs: small problems prefer more, narrower tiles
+                const int64_t tm = (d.Cout + BM - 1) / BM; // (measured: 128 wide tiles on 148 SMs beat 256 narrow ones, 64 do not)
+                while (bn > 64 && tm * d.N * ((d.OH + bn / 32 - 1) / (bn / 32)) < ctx->sm_count / 2)
+                    bn >>= 1;
+            }
+            rows_per_tile = bn / 64 * rpc;
         }
         const int64_t groups = (d.OH + rows_per_tile - 1) / rows_per_tile;
         const uint64_t rowb = (uint64_t)pieces * Cp * 2;
@@ -1668,7 +1678,7 @@ axb_status conv_tc(const ConvDesc &d, DeviceCtx *ctx, cudaStream_t s, bool *done
         } else {
             const uint64_t dims[4] = {(uint64_t)pieces * Cp, (uint64_t)Wq, (uint64_t)Hq, (uint64_t)planes};
             const uint64_t strides[3] = {rowb, (uint64_t)Wq * rowb, (uint64_t)Hq * Wq * rowb};
-            AXB_TRY(make_map4(&mb, api, mdt, xq, dims, strides, BK, rows_per_tile > 1 ? 64u : (uint32_t)bn));
+            AXB_TRY(make_map4(&mb, api, mdt, xq, dims, strides, BK, rows_per_tile > 1 ? (rpc == 2 ? 32u : 64u) : (uint32_t)bn, (uint32_t)rpc));
         }
         TcParams p;
         memset(&p, 0, sizeof p);
@@ -1687,7 +1697,7 @@ axb_status conv_tc(const ConvDesc &d, DeviceCtx *ctx, cudaStream_t s, bool *done
         p.bias_dtype = d.bias_dtype; p.act = d.act; p.out_dtype = d.dtype;
         p.split = f32 ? 2 : 0; p.kbp = (int)(taps * cblocks); p.Kp = Cp;
         p.conv_taps = (int)taps; p.conv_cblocks = (int)cblocks; p.conv_oh = (int)groups; p.conv_phases = d.sh * d.sw;
-        p.conv_rows = rows_per_tile; p.conv_ohs = (int)d.OH;
+        p.conv_rows = rows_per_tile; p.conv_ohs = (int)d.OH; p.conv_rpc = rpc;
         for (int64_t t = 0; t < taps; ++t) {
             p.conv_qw[t] = qw[t];
             p.conv_qh[t] = qh[t];
