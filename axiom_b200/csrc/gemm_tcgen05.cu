@@ -218,15 +218,30 @@ __device__ __forceinline__ void epilogue_tile(const TcParams &p, int64_t b, int 
 #pragma unroll 1
     for (int c = half; c < BN_ / 32; c += 2) {
         int64_t nbase = n0 + c * 32, cbase = cbase0;
+        // rpc4: this 32-column segment is TWO output rows of at most 16 columns (columns 0..15 -> row r, 16..31 -> row r + 1)
+        const bool rpc4 = p.conv_rows > 1 && p.conv_rpc == 4;
+        int64_t rows_left = 1;
         if (p.conv_rows > 1) { // 64-column chunk k of the tile holds output rows conv_oh0 + k * rpc .. (rpc = 1: one 64-column row,
-            const int r = p.conv_rpc == 2 ? c : c >> 1; // two 32-column segments; rpc = 2: two rows of 32 columns, one segment each)
-            nbase = p.conv_rpc == 2 ? 0 : (c & 1) * 32;
-            if (conv_oh0 + r >= p.conv_ohs || nbase >= p.N)
+            // two 32-column segments; rpc = 2: two rows of 32 columns, one segment each; rpc = 4: four rows of 16, two per segment)
+            const int r = rpc4 ? 2 * c : p.conv_rpc == 2 ? c : c >> 1;
+            nbase = p.conv_rpc >= 2 ? 0 : (c & 1) * 32;
+            rows_left = p.conv_ohs - (conv_oh0 + r);
+            if (rows_left <= 0 || nbase >= p.N)
                 continue; // warp-uniform
             cbase += r * p.c_hs;
         } else if (nbase >= p.N) {
             break; // warp-uniform
         }
+        // byte offset (from the segment's first row) of column `col` of the segment, and whether it exists
+        auto col_off = [&](int col, bool *ok) -> int64_t {
+            if (rpc4) {
+                const int sub = col >> 4, cl = col & 15;
+                *ok = cl < p.N && sub < rows_left;
+                return sub * p.c_hs + (int64_t)cl * p.c_cs;
+            }
+            *ok = nbase + col < p.N;
+            return (nbase + col) * p.c_cs;
+        };
         char *crow = p.c + cbase + m * p.c_rs;
         uint32_t v[32];
         tc_ld32(taddr + c * 32, v);
@@ -284,7 +299,7 @@ __device__ __forceinline__ void epilogue_tile(const TcParams &p, int64_t b, int 
             } else {
 #pragma unroll
                 for (int i = 0; i < 32; ++i)
-                    if (nbase + i < p.N)
+                    if (rpc4 || nbase + i < p.N) // (rpc4: a convolution's bias is per output channel, bias_cs == 0)
                         f[i] += ld_bias(brow + (nbase + i) * p.bias_cs, p.bias_dtype);
             }
         }
@@ -342,8 +357,10 @@ __device__ __forceinline__ void epilogue_tile(const TcParams &p, int64_t b, int 
                     asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(w.x), "=r"(w.y), "=r"(w.z), "=r"(w.w)
                                  : "r"(tile + rr * 128u + ((cw ^ (rr & 7)) << 4)));
                     const int64_t mm = (int64_t)m0 + q * 32 + rr;
-                    if (mm < p.M && nbase + cw * 4 < p.N)
-                        *reinterpret_cast<uint4 *>(p.c + cbase + mm * p.c_rs + (nbase + cw * 4) * 4) = w;
+                    bool ok;
+                    const int64_t off = col_off(cw * 4, &ok);
+                    if (mm < p.M && ok)
+                        *reinterpret_cast<uint4 *>(p.c + cbase + mm * p.c_rs + off) = w;
                 }
                 __syncwarp();
             } else if (strided_store) {
@@ -368,16 +385,21 @@ __device__ __forceinline__ void epilogue_tile(const TcParams &p, int64_t b, int 
                         uint32_t w;
                         asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w)
                                      : "r"(tile + rr * 128u + ((((uint32_t)col >> 2) ^ (rr & 7)) << 4) + ((uint32_t)col & 3u) * 4u));
-                        if (mm < p.M && nbase + col < p.N)
-                            *reinterpret_cast<uint32_t *>(p.c + cbase + mm * p.c_rs + (nbase + col) * p.c_cs) = w;
+                        bool ok;
+                        const int64_t off = col_off(col, &ok);
+                        if (mm < p.M && ok)
+                            *reinterpret_cast<uint32_t *>(p.c + cbase + mm * p.c_rs + off) = w;
                     }
                 }
                 __syncwarp();
             } else {
 #pragma unroll
-                for (int i = 0; i < 32; ++i)
-                    if (nbase + i < p.N)
-                        *reinterpret_cast<float *>(crow + (nbase + i) * p.c_cs) = f[i];
+                for (int i = 0; i < 32; ++i) {
+                    bool ok;
+                    const int64_t off = col_off(i, &ok);
+                    if (ok)
+                        *reinterpret_cast<float *>(crow + off) = f[i];
+                }
             }
             continue;
         }
@@ -418,8 +440,10 @@ __device__ __forceinline__ void epilogue_tile(const TcParams &p, int64_t b, int 
                 asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(w.x), "=r"(w.y), "=r"(w.z), "=r"(w.w)
                              : "r"(tile + rr * 64u + ((cw ^ ((rr >> 1) & 3)) << 4)));
                 const int64_t mm = (int64_t)m0 + q * 32 + rr;
-                if (mm < p.M && nbase + cw * 8 < p.N)
-                    *reinterpret_cast<uint4 *>(p.c + cbase + mm * p.c_rs + (nbase + cw * 8) * 2) = w;
+                bool ok;
+                const int64_t off = col_off(cw * 8, &ok);
+                if (mm < p.M && ok)
+                    *reinterpret_cast<uint4 *>(p.c + cbase + mm * p.c_rs + off) = w;
             }
             __syncwarp();
         } else if (strided_store) { // 64-byte rows: 4 lanes per row on neighbouring columns, 8 rows per instruction
@@ -441,17 +465,21 @@ __device__ __forceinline__ void epilogue_tile(const TcParams &p, int64_t b, int 
                     uint16_t w;
                     asm volatile("ld.shared.u16 %0, [%1];" : "=h"(w)
                                  : "r"(tile + rr * 64u + ((((uint32_t)col >> 3) ^ ((rr >> 1) & 3)) << 4) + ((uint32_t)col & 7u) * 2u));
-                    if (mm < p.M && nbase + col < p.N)
-                        *reinterpret_cast<uint16_t *>(p.c + cbase + mm * p.c_rs + (nbase + col) * p.c_cs) = w;
+                    bool ok;
+                    const int64_t off = col_off(col, &ok);
+                    if (mm < p.M && ok)
+                        *reinterpret_cast<uint16_t *>(p.c + cbase + mm * p.c_rs + off) = w;
                 }
             }
             __syncwarp();
         } else {
 #pragma unroll
-            for (int i = 0; i < 32; ++i)
-                if (nbase + i < p.N)
-                    *reinterpret_cast<uint16_t *>(crow + (nbase + i) * p.c_cs) =
-                        (uint16_t)((i & 1) ? (h[i >> 1] >> 16) : (h[i >> 1] & 0xFFFFu));
+            for (int i = 0; i < 32; ++i) {
+                bool ok;
+                const int64_t off = col_off(i, &ok);
+                if (ok)
+                    *reinterpret_cast<uint16_t *>(crow + off) = (uint16_t)((i & 1) ? (h[i >> 1] >> 16) : (h[i >> 1] & 0xFFFFu));
+            }
         }
     }
 }
@@ -1657,11 +1685,14 @@ axb_status conv_tc(const ConvDesc &d, DeviceCtx *ctx, cudaStream_t s, bool *done
         int rows_per_tile = 1, rpc = 1;
         if (!no_rows && d.OW <= 64 && d.OH >= 2) {
             static const bool no_pack = getenv("AXB_CONV_NO_PACK") != nullptr; // A/B switch
-            rpc = (!no_pack && !direct && d.OW <= 32 && d.OH >= 4) ? 2 : 1; // narrow images: two rows share a 64-column chunk
+            // narrow images: two rows of <= 32 columns, or four of <= 16, share a 64-column chunk
+            static const bool no_pack4 = getenv("AXB_CONV_NO_PACK4") != nullptr;
+            rpc = (no_pack || direct) ? 1 : (!no_pack4 && d.OW <= 16 && d.OH >= 8) ? 4 : (d.OW <= 32 && d.OH >= 4) ? 2 : 1;
             bn = (f32 || d.OH < 4 * rpc) ? 128 : 256;
-            if (rpc == 2) { // the widest tile that still occupies half of the SMs: small problems prefer more, narrower tiles
+            if (rpc >= 2) { // the widest tile that still occupies half of the SMs: small problems prefer more, narrower tiles
                 const int64_t tm = (d.Cout + BM - 1) / BM; // (measured: 128 wide tiles on 148 SMs beat 256 narrow ones, 64 do not)
-                while (bn > 64 && tm * d.N * ((d.OH + bn / 32 - 1) / (bn / 32)) < ctx->sm_count / 2)
+                auto rows_of = [&](int w) { return (int64_t)(w / 64 * rpc); };
+                while (bn > 64 && tm * d.N * ((d.OH + rows_of(bn) - 1) / rows_of(bn)) < ctx->sm_count / 2)
                     bn >>= 1;
             }
             rows_per_tile = bn / 64 * rpc;
@@ -1678,7 +1709,7 @@ axb_status conv_tc(const ConvDesc &d, DeviceCtx *ctx, cudaStream_t s, bool *done
         } else {
             const uint64_t dims[4] = {(uint64_t)pieces * Cp, (uint64_t)Wq, (uint64_t)Hq, (uint64_t)planes};
             const uint64_t strides[3] = {rowb, (uint64_t)Wq * rowb, (uint64_t)Hq * Wq * rowb};
-            AXB_TRY(make_map4(&mb, api, mdt, xq, dims, strides, BK, rows_per_tile > 1 ? (rpc == 2 ? 32u : 64u) : (uint32_t)bn, (uint32_t)rpc));
+            AXB_TRY(make_map4(&mb, api, mdt, xq, dims, strides, BK, rows_per_tile > 1 ? (uint32_t)(64 / rpc) : (uint32_t)bn, (uint32_t)rpc));
         }
         TcParams p;
         memset(&p, 0, sizeof p);

@@ -114,6 +114,7 @@ def test_conv_transpose_f64_helper_matches_the_loop_restatement():
 
 
 CONVT_TC = [  # (x shape, w shape, kwargs)
+    ((8, 128, 16, 16), (128, 64, 4, 4), dict(stride=(2, 2), padding=(1, 1), output_padding=(0, 0), dilation=(1, 1))),   # 16-wide phases: four rows per chunk
     ((2, 64, 32, 32), (64, 64, 4, 4), dict(stride=(2, 2), padding=(1, 1), output_padding=(0, 0), dilation=(1, 1))),   # 2x upsampling
     ((2, 96, 30, 33), (96, 72, 3, 3), dict(stride=(2, 2), padding=(1, 1), output_padding=(1, 1), dilation=(1, 1))),   # 1 / 2 / 2 / 4 taps per phase
     ((2, 40, 25, 40), (40, 96, 5, 5), dict(stride=(3, 2), padding=(2, 0), output_padding=(2, 1), dilation=(2, 1))),   # dilation 2 against stride 3
@@ -270,7 +271,10 @@ CONV_TC_2D = [((2, 64, 56, 56), (128, 64, 3, 3), dict(stride=(1, 1), padding=(1,
               ((2, 64, 60, 96), (64, 64, 3, 3), dict(stride=(3, 2), padding=(0, 1), dilation=(2, 1))),
               ((1, 64, 21, 200), (72, 64, 3, 3), dict(stride=(1, 1), padding=(1, 1), dilation=(1, 1))),   # wider than a tile: one row per tile
               ((8, 64, 3, 64), (64, 64, 3, 3), dict(stride=(1, 1), padding=(1, 1), dilation=(1, 1))),     # OH = 3: two-row groups, ragged
-              ((4, 128, 14, 14), (256, 128, 3, 3), dict(stride=(1, 1), padding=(1, 1), dilation=(1, 1)))] # 14 x 14 feature map
+              ((4, 128, 14, 14), (256, 128, 3, 3), dict(stride=(1, 1), padding=(1, 1), dilation=(1, 1))), # 14 x 14 feature map: four rows per chunk
+              ((5, 64, 29, 16), (96, 64, 3, 3), dict(stride=(1, 1), padding=(1, 1), dilation=(1, 1))),   # OW = 16 (vector stores), OH = 29 ragged groups
+              ((6, 64, 26, 28), (64, 64, 5, 3), dict(stride=(1, 1), padding=(2, 1), dilation=(1, 1))),   # OW = 28: two rows per chunk
+              ((3, 96, 40, 23), (160, 96, 3, 3), dict(stride=(2, 2), padding=(1, 1), dilation=(1, 1)))]  # strided, OW = 12 (odd row pitch)
 
 
 @pytest.mark.gpu
