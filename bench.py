@@ -578,7 +578,11 @@ def sharded_configs(env):
                     (best of 10), so `frac_hbm` / `frac_bf16_peak` compare like with like;
         sustained = one loop of >= min_s seconds with NVML clocks and power sampled during it (memory-bound kernels reach
                     the cap too: ~990 W, SM clocks 1.5-1.8 GHz) — compares with bf16_tflops_sustained for the GEMM.
-        `primary` selects which regime fills the entry's top-level ms / GBps / TFLOPs keys."""
+        `primary` selects which regime fills the entry's top-level ms / GBps / TFLOPs keys. The burst is taken from a rested
+        GPU (0.5 s idle first): the previous entry's sustained loop leaves the part at its power cap (~990 W, SM clocks
+        1.5-1.8 GHz) for a few hundred milliseconds, and the peaks the fractions refer to were measured from idle."""
+        dev.synchronize()
+        time.sleep(0.5)
         for _ in range(3):
             fn()
         env["barrier"]()
