@@ -113,6 +113,69 @@ def test_conv_transpose_f64_helper_matches_the_loop_restatement():
         assert np.allclose(t, ao.conv_transpose2d_f32(x, w, b, groups=1, **cfg), rtol=1e-5, atol=1e-5)
 
 
+def _conv_transpose_by_phases(x, w, stride, padding, output_padding, dilation):
+    """The decomposition spatial.cu conv_transpose_tc hands to the tensor cores, restated with numpy: for every output phase
+    (oh % s_h, ow % s_w) the taps with (r + p - k * d) % s == 0 form an arithmetic progression k0 + i * step, tap i reads input row
+    oh' + q0 + i * dil with q0 = (r + p - k0 * d) / s and dil = -(step * d / s); rows outside the input count as zero. Returns the
+    fp64 result, or None when some phase has no tap (the case the library leaves to the gather kernel)."""
+    n, cin, h, wd = x.shape
+    _, cout, kh, kw = w.shape
+    oh = (h - 1) * stride[0] - 2 * padding[0] + dilation[0] * (kh - 1) + output_padding[0] + 1
+    ow = (wd - 1) * stride[1] - 2 * padding[1] + dilation[1] * (kw - 1) + output_padding[1] + 1
+
+    def plan(r, s, p, d, k):
+        ks = [kk for kk in range(k) if (r + p - kk * d) % s == 0]
+        if not ks:
+            return None
+        step = ks[1] - ks[0] if len(ks) > 1 else 1
+        assert all(b - a == step for a, b in zip(ks, ks[1:])), "taps of a phase are equally spaced"
+        q0 = (r + p - ks[0] * d) // s
+        dil = (r + p - ks[1] * d) // s - q0 if len(ks) > 1 else 0
+        assert len(ks) == 1 or dil * s == -step * d
+        return ks[0], step, len(ks), q0, dil
+
+    out = np.zeros((n, cout, oh, ow))
+    x64, w64 = x.astype(np.float64), w.astype(np.float64)
+    for rh in range(stride[0]):
+        for rw in range(stride[1]):
+            ph, pw = plan(rh, stride[0], padding[0], dilation[0], kh), plan(rw, stride[1], padding[1], dilation[1], kw)
+            if ph is None or pw is None:
+                return None
+            ohr, owr = len(range(rh, oh, stride[0])), len(range(rw, ow, stride[1]))
+            acc = np.zeros((n, cout, ohr, owr))
+            for i in range(ph[2]):
+                for j in range(pw[2]):
+                    tap = w64[:, :, ph[0] + i * ph[1], pw[0] + j * pw[1]]           # (C_in, C_out): the strided weight view
+                    r0, c0 = ph[3] + i * ph[4], pw[3] + j * pw[4]                     # input row / column of output (0, 0)
+                    rows, cols = np.arange(ohr) + r0, np.arange(owr) + c0
+                    rv, cv = (rows >= 0) & (rows < h), (cols >= 0) & (cols < wd)      # out-of-range = TMA zero fill
+                    patch = np.zeros((n, cin, ohr, owr))
+                    patch[:, :, np.ix_(rv, cv)[0], np.ix_(rv, cv)[1]] = x64[:, :, rows[rv]][:, :, :, cols[cv]]
+                    acc += np.einsum("nchw,co->nohw", patch, tap)
+            out[:, :, rh::stride[0], rw::stride[1]] = acc
+    return out
+
+
+@pytest.mark.parametrize("cfg", [dict(stride=(2, 2), padding=(1, 1), output_padding=(0, 0), dilation=(1, 1)),
+                                 dict(stride=(2, 3), padding=(1, 0), output_padding=(1, 2), dilation=(1, 1)),
+                                 dict(stride=(3, 2), padding=(2, 0), output_padding=(2, 1), dilation=(2, 1)),
+                                 dict(stride=(1, 4), padding=(0, 2), output_padding=(0, 3), dilation=(1, 3)),
+                                 dict(stride=(2, 2), padding=(0, 3), output_padding=(1, 0), dilation=(2, 2))])
+def test_conv_transpose_phase_decomposition_is_the_transposed_convolution(cfg):
+    """CPU pin of the algorithm behind the tensor-core path: phase by phase it is the scatter loop of ops::conv_transpose2d
+    (operations.cpp:3590-3690), including dilation against stride, output_padding and negative effective padding."""
+    rng = np.random.default_rng(60)
+    x = rng.standard_normal((2, 3, 5, 7)).astype(np.float32)
+    w = rng.standard_normal((3, 4, 5, 4)).astype(np.float32)
+    got = _conv_transpose_by_phases(x, w, **cfg)
+    if cfg["dilation"] == (2, 2):  # dilation 2 under stride 2: odd phases have no tap at all
+        assert got is None
+        return
+    truth, _ = _conv_transpose_f64(x, w, None, **cfg)
+    assert got is not None and np.allclose(got, truth, rtol=1e-12, atol=1e-12)
+    assert np.allclose(truth, ao.conv_transpose2d_f32(x, w, None, groups=1, **cfg), rtol=1e-5, atol=1e-5)
+
+
 CONVT_TC = [  # (x shape, w shape, kwargs)
     ((8, 128, 16, 16), (128, 64, 4, 4), dict(stride=(2, 2), padding=(1, 1), output_padding=(0, 0), dilation=(1, 1))),   # 16-wide phases: four rows per chunk
     ((2, 64, 32, 32), (64, 64, 4, 4), dict(stride=(2, 2), padding=(1, 1), output_padding=(0, 0), dilation=(1, 1))),   # 2x upsampling
